@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures by executing the UNMODIFIED reference classes.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU
+box):  ``python tests/golden/make_golden.py``  ->  tests/golden/*.npz
+
+The reference ships no tests or golden vectors, so the
+pins are outputs of its own classes (modules.py blocks, models.flatten_vae_nl,
+losses.KLDivergenceLoss / ReconLoss) on CPU fp32.  Inputs and weights come from
+the closed-form generators in ``oracle/detgen.py`` and are therefore NOT stored:
+tests regenerate them.  ``flatten_vae_nl`` draws eps inline with ``torch.randn``
+(models.py:561); the draw is intercepted (torch.randn is patched for the duration
+of the call, the reference source is untouched) so that eps is the deterministic
+tensor the tests also use.
+
+Large tensors are stored as (sum, l2, absmax) plus a strided sample so the
+fixtures stay small.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from collections import OrderedDict
+from contextlib import contextmanager
+
+import numpy as np
+import torch
+from torch import nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("FACEVAE_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+
+import modules as ref_modules          # noqa: E402  (reference)
+import models as ref_models            # noqa: E402  (reference)
+import losses as ref_losses            # noqa: E402  (reference)
+
+from oracle import detgen              # noqa: E402
+from oracle import facevae_oracle as O  # noqa: E402
+
+SAMPLE = 257   # prime-ish count of strided samples per large tensor
+
+
+def summarise(t: torch.Tensor, full_below: int = 4096):
+    a = t.detach().to(torch.float64).flatten().numpy()
+    d = {"shape": np.array(t.shape, np.int64), "sum": a.sum(), "l2": np.sqrt((a * a).sum()),
+         "absmax": np.abs(a).max() if a.size else 0.0}
+    if a.size <= full_below:
+        d["full"] = a.astype(np.float32)
+    else:
+        idx = sample_index(a.size)
+        d["sample"] = a[idx].astype(np.float32)
+    return d
+
+
+def sample_index(n: int) -> np.ndarray:
+    return (np.arange(SAMPLE, dtype=np.int64) * (n // SAMPLE + 1) * 7919 + 13) % n
+
+
+def put(store: dict, name: str, t: torch.Tensor, **kw):
+    for k, v in summarise(t, **kw).items():
+        store[f"{name}/{k}"] = v
+
+
+@contextmanager
+def injected_randn(eps: torch.Tensor):
+    orig = torch.randn
+
+    def fake(*size, **kw):
+        shape = tuple(size[0]) if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)) else tuple(size)
+        assert shape == tuple(eps.shape), (shape, eps.shape)
+        return eps.clone()
+
+    torch.randn = fake
+    try:
+        yield
+    finally:
+        torch.randn = orig
+
+
+class RefAnchor(nn.Module):
+    """Composition of SURVEY.md section 8 from unmodified reference classes."""
+
+    def __init__(self, cfg: O.AnchorConfig):
+        super().__init__()
+        d, u = cfg.down_seq, cfg.up_seq
+        self.enc = nn.Sequential(*[ref_modules.SameBlock2D(d[i], d[i + 1], False) if i == 0 else
+                                   ref_modules.DownBlock2D(d[i], d[i + 1], False) for i in range(len(d) - 1)])
+        self.vae = ref_models.flatten_vae_nl()
+        self.mid_conv = nn.Conv2d(cfg.zc, u[0], 1, 1, 0)
+        self.res = nn.Sequential(*[ref_modules.ResBlock2D(u[0], False) for _ in range(cfg.n_res)])
+        self.up = nn.Sequential(*[ref_modules.UpBlock2D(u[i], u[i + 1], False) for i in range(len(u) - 1)])
+        self.out_conv = nn.Conv2d(u[-1], 3, 7, 1, 3)
+        self.kl = ref_losses.KLDivergenceLoss()
+        self.rec = ref_losses.ReconLoss()
+        self.cfg = cfg
+
+    def forward(self, x, eps, taps):
+        h = x
+        for i, blk in enumerate(self.enc):
+            h = blk(h)
+            taps[f"enc.{i}"] = h
+        with injected_randn(eps):
+            mu, logstd, z = self.vae(h, True)
+        taps["z"] = z
+        dd = self.mid_conv(z)
+        taps["mid_conv"] = dd
+        for i, blk in enumerate(self.res):
+            dd = blk(dd)
+            taps[f"res.{i}"] = dd
+        for i, blk in enumerate(self.up):
+            dd = blk(dd)
+            taps[f"up.{i}"] = dd
+        logits = self.out_conv(dd)
+        x_hat = torch.sigmoid(logits)
+        K = self.kl((mu, logstd))
+        R = self.rec((x, x_hat))
+        return dict(mu=mu, logstd=logstd, z=z, logits=logits, x_hat=x_hat, K=K, R=R,
+                    loss=self.cfg.w_kl * K + self.cfg.w_rec * R)
+
+
+def load_det(model: nn.Module, params):
+    sd = model.state_dict()
+    for k, v in params.items():
+        assert k in sd and tuple(sd[k].shape) == tuple(v.shape), k
+        sd[k] = v.clone()
+    missing = [k for k in sd if k not in params and not k.endswith("num_batches_tracked")]
+    assert not missing, missing
+    model.load_state_dict(sd)
+
+
+def golden_anchor(n, hw, base, path):
+    cfg = O.CFG_256
+    p = O.det_anchor_params(cfg, base)
+    x, eps = O.det_inputs(n, hw, hw, cfg, base)
+    m = RefAnchor(cfg).train()
+    load_det(m, p)
+    taps = {}
+    out = m(x, eps, taps)
+    out["loss"].backward()
+    store = {"meta/n": n, "meta/hw": hw, "meta/base": base}
+    for k in ("K", "R", "loss"):
+        store[f"out/{k}"] = np.float64(out[k].item())
+    for k in ("mu", "logstd", "z"):
+        put(store, f"out/{k}", out[k].reshape(n, -1))
+    put(store, "out/logits", out["logits"])
+    put(store, "out/x_hat", out["x_hat"])
+    for k, v in taps.items():
+        put(store, f"act/{k}", v)
+    for k, v in m.named_parameters():
+        put(store, f"grad/{k}", v.grad)
+    for k, v in m.named_buffers():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            put(store, f"buf/{k}", v)
+    # one Adam step exactly as the reference configures it (logger.py:60)
+    opt = torch.optim.Adam(m.parameters(), lr=5e-5, betas=(0.5, 0.999))
+    opt.step()
+    for k in ("enc.1.layers.0.layers.0.weight", "out_conv.weight", "res.0.layers.0.layers.0.weight"):
+        put(store, f"adam/{k}", dict(m.named_parameters())[k])
+    np.savez_compressed(path, **store)
+    print(path, "K=%.8f R=%.8f loss=%.8f" % (out["K"].item(), out["R"].item(), out["loss"].item()))
+
+
+def golden_blocks(path):
+    """Each block on its own: outputs, input grads and parameter grads, stored in full."""
+    store = {}
+    n, hw = 2, 8
+
+    def run(tag, blk, ci, upstream_seed):
+        blk.train()
+        sd = blk.state_dict()
+        for k in list(sd):
+            if k.endswith("num_batches_tracked"):
+                continue
+            seed = detgen.name_seed(tag + "." + k)
+            shape = tuple(sd[k].shape)
+            if k.endswith("running_mean"):
+                v = np.zeros(shape, np.float32)
+            elif k.endswith("running_var"):
+                v = np.ones(shape, np.float32)
+            elif len(shape) == 4:
+                b = 1.0 / np.sqrt(shape[1] * shape[2] * shape[3])
+                v = detgen.det_uniform(shape, seed, -b, b)
+            elif k.endswith("weight"):
+                v = detgen.det_uniform(shape, seed, 0.5, 1.5)
+            else:
+                v = detgen.det_uniform(shape, seed, -0.2, 0.2)
+            sd[k] = torch.from_numpy(v)
+        blk.load_state_dict(sd)
+        x = torch.from_numpy(detgen.det_uniform((n, ci, hw, hw), detgen.name_seed(tag + ".x"), -1.0, 1.0)).requires_grad_(True)
+        y = blk(x)
+        g = torch.from_numpy(detgen.det_uniform(tuple(y.shape), upstream_seed, -1.0, 1.0))
+        (y * g).sum().backward()
+        put(store, f"{tag}/y", y, full_below=1 << 20)
+        put(store, f"{tag}/dx", x.grad, full_below=1 << 20)
+        for k, v in blk.named_parameters():
+            put(store, f"{tag}/grad/{k}", v.grad, full_below=1 << 20)
+        for k, v in blk.named_buffers():
+            if not k.endswith("num_batches_tracked"):
+                put(store, f"{tag}/buf/{k}", v, full_below=1 << 20)
+
+    run("down", ref_modules.DownBlock2D(16, 32, False), 16, 11)
+    run("up", ref_modules.UpBlock2D(32, 16, False), 32, 12)
+    run("same", ref_modules.SameBlock2D(16, 32, False), 16, 13)
+    run("same3", ref_modules.SameBlock2D(3, 32, False), 3, 14)
+    run("res", ref_modules.ResBlock2D(32, False), 32, 15)
+    run("convblock_leaky", ref_modules.ConvBlock2D("CNA", 16, 16, 3, 1, 1, False, nonlinearity_type="leakyrelu"), 16, 16)
+    np.savez_compressed(path, **store)
+    print(path, len(store), "arrays")
+
+
+def golden_losses(path):
+    """KLDivergenceLoss / ReconLoss / l1 / l2 / flatten_vae_nl known answers."""
+    store = {}
+    kl = ref_losses.KLDivergenceLoss()
+    rec = ref_losses.ReconLoss()
+    for tag, (m, s) in {"zero": (0.0, 0.0), "mu1": (1.0, 0.0), "ls1": (0.0, 1.0), "lsm1": (0.0, -1.0)}.items():
+        store[f"kl/{tag}"] = np.float64(kl((torch.full((4, 256), m), torch.full((4, 256), s))).item())
+    i = torch.arange(1024, dtype=torch.float32).view(4, 256)
+    mu = torch.sin(0.01 * i).requires_grad_(True)
+    ls = (0.5 * torch.cos(0.013 * i)).requires_grad_(True)
+    v = kl((mu, ls))
+    v.backward()
+    store["kl/sincos"] = np.float64(v.item())
+    store["kl/sincos_dmu"] = mu.grad.numpy()
+    store["kl/sincos_dlogstd"] = ls.grad.numpy()
+    a = torch.sin(0.1 * torch.arange(384, dtype=torch.float32)).view(2, 3, 8, 8).requires_grad_(True)
+    b = torch.cos(0.07 * torch.arange(384, dtype=torch.float32)).view(2, 3, 8, 8)
+    r = rec((a, b))
+    r.backward()
+    store["rec/mse"] = np.float64(r.item())
+    store["rec/mse_da"] = a.grad.numpy()
+    store["rec/l1"] = np.float64(nn.L1Loss()(a.detach(), b).item())
+    store["rec/l1_elem"] = ref_losses.l1(a.detach(), b).numpy()
+    store["rec/l2_elem"] = ref_losses.l2(a.detach(), b).numpy()
+    # flatten_vae_nl: eval returns (None, None, x[:, :16]); train follows mu + exp(logstd) * eps
+    vae = ref_models.flatten_vae_nl()
+    x = torch.from_numpy(detgen.det_uniform((3, 32, 4, 4), 77, 0.0, 2.0))
+    eps = torch.from_numpy(detgen.det_normal((3, 256), 78))
+    m0, s0, xh0 = vae(x, False)
+    assert m0 is None and s0 is None
+    store["vae/eval_xhat"] = xh0.numpy()
+    with injected_randn(eps):
+        m1, s1, xh1 = vae(x, True)
+    store["vae/train_mu"] = m1.numpy()
+    store["vae/train_logstd"] = s1.numpy()
+    store["vae/train_xhat"] = xh1.numpy()
+    np.savez_compressed(path, **store)
+    print(path, {k: float(v) for k, v in store.items() if np.ndim(v) == 0})
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    golden_losses(os.path.join(HERE, "losses.npz"))
+    golden_blocks(os.path.join(HERE, "blocks.npz"))
+    golden_anchor(4, 64, 0, os.path.join(HERE, "anchor_n4_64.npz"))     # BASELINE.json configs[0]
+    golden_anchor(2, 64, 1, os.path.join(HERE, "anchor_n2_64_b1.npz"))
