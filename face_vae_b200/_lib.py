@@ -1,0 +1,88 @@
+"""ctypes binding of libfacevae_b200.so (the C ABI declared in include/facevae_b200.h).
+
+There is no fallback: if the library cannot be loaded (or built) the import of any compute path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfacevae_b200.so")
+
+# enums of include/facevae_b200.h
+DT_BF16, DT_F32 = 0, 1
+OUT_NHWC_BF16, OUT_NHWC_F32, OUT_NCHW_F32 = 0, 1, 2
+MODE_NONE, MODE_POOL, MODE_UP = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+_p, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+
+# name -> argument ctypes (all return int unless listed in _STR)
+SIGNATURES = {
+    "fv_device_ok": [],
+    "fv_nchw_to_nhwc": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_nhwc_to_nchw": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_weight_prep": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_conv2d": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "fv_conv2d_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "fv_wgrad_finish": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_colsum": [_p, _p, _ll, _i, _p],
+    "fv_bn_stats": [_p, _i, _p, _ll, _i, _p],
+    "fv_bn_finalize": [_p, _d, _p, _p, _p, _p, _f, _f, _p, _i, _p],
+    "fv_bn_eval_affine": [_p, _p, _p, _p, _f, _p, _i, _p],
+    "fv_bn_act_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "fv_bn_act_bwd_reduce": [_p, _i, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_bn_bwd_finalize": [_p, _p, _d, _p, _p, _p, _i, _i, _p],
+    "fv_bn_act_bwd_apply": [_p, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_reparam_kl_fwd": [_p, _p, _ll, _p, _p, _p, _i, _i, _p],
+    "fv_reparam_kl_bwd": [_p, _p, _ll, _p, _p, _p, _p, _f, _p, _p, _p, _ll, _i, _i, _p],
+    "fv_recon_loss": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
+    "fv_recon_loss_flat": [_p, _p, _p, _p, _ll, _i, _f, _p],
+    "fv_scale": [_p, _p, _i, _ll, _p, _f, _p],
+}
+_STR = ("fv_last_error", "fv_version")
+
+_lock = threading.Lock()
+_lib = None
+
+
+class FaceVaeError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    """Load (once) and return the ctypes library handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise FaceVaeError(f"{LIB_PATH} is missing; run `python -m face_vae_b200.build` (needs nvcc)")
+            from . import build as _build
+            _build.build()
+        lib = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        for name in _STR:
+            getattr(lib, name).restype = C.c_char_p
+            getattr(lib, name).argtypes = []
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().fv_last_error().decode("utf-8", "replace")
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point; non-zero -> FaceVaeError with the library's message."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise FaceVaeError(f"{name} failed ({rc}): {last_error()}")

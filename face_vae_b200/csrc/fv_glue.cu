@@ -1,0 +1,778 @@
+// Memory-bound glue of the face-vae hot path: layout conversion, filter preparation, batch-norm statistics,
+// fused norm + activation (+ 2x2 average pool / nearest up-sample) forward and backward, the re-parameterisation
+// fused with the KL reduction, and the reconstruction loss fused with its gradient.  Every kernel is a single
+// coalesced, 16-byte-vectorised pass (8 channels per thread in NHWC), sized in multiples of the SM count.
+#include <cmath>
+
+#include "../../include/facevae_b200.h"
+#include "fv_host.h"
+#include "fv_ptx.cuh"
+
+namespace fv {
+
+static constexpr int kThreads = 256;
+
+static inline int grid_for(long long work_items, int per_block = kThreads, int waves = 8) {
+    long long b = (work_items + per_block - 1) / per_block;
+    long long cap = (long long)num_sms() * waves;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------- 8-wide load / store helpers
+template <typename T> struct V8;
+template <> struct V8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+        *reinterpret_cast<uint4*>(p) =
+            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    }
+};
+template <> struct V8<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&f)[8]) {
+        *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+};
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+    return act == FV_ACT_RELU ? fmaxf(z, 0.f) : (act == FV_ACT_LEAKY ? (z > 0.f ? z : 0.2f * z) : z);
+}
+__device__ __forceinline__ float act_grad(float z, int act) {
+    return act == FV_ACT_RELU ? (z > 0.f ? 1.f : 0.f) : (act == FV_ACT_LEAKY ? (z > 0.f ? 1.f : 0.2f) : 1.f);
+}
+
+// ---------------------------------------------------------------- layout
+// NCHW fp32 -> NHWC (C padded to Cp with zeros).  One thread per (pixel, 8-channel group); consecutive threads walk
+// consecutive pixels so the per-plane reads coalesce.
+template <typename TO>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, TO* __restrict__ dst, int N, int C, int HW, int Cp) {
+    const int groups = Cp / 8;
+    const long long total = (long long)N * HW * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i % ((long long)N * HW);
+        const int g = (int)(i / ((long long)N * HW));
+        const int n = (int)(pix / HW), hw = (int)(pix % HW);
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = g * 8 + k;
+            f[k] = c < C ? __ldg(src + ((long long)n * C + c) * HW + hw) : 0.f;
+        }
+        V8<TO>::store(dst + pix * Cp + g * 8, f);
+    }
+}
+
+// NHWC (channel stride Cs) -> NCHW fp32 (first C channels); optionally accumulates into dst.
+template <typename TI>
+__global__ void nhwc_to_nchw_kernel(const TI* __restrict__ src, float* __restrict__ dst, int N, int C, int HW, int Cs,
+                                    int accumulate) {
+    const int groups = (C + 7) / 8;
+    const long long total = (long long)N * HW * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i % ((long long)N * HW);
+        const int g = (int)(i / ((long long)N * HW));
+        const int n = (int)(pix / HW), hw = (int)(pix % HW);
+        float f[8];
+        V8<TI>::load(src + pix * Cs + g * 8, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = g * 8 + k;
+            if (c < C) {
+                float* o = dst + ((long long)n * C + c) * HW + hw;
+                *o = accumulate ? *o + f[k] : f[k];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- filters
+// w fp32 [Co][Ci][R][S] (nn.Conv2d layout) -> wf bf16 [Co_pad][taps][Ci_pad] (fprop, K-major) and
+// wd bf16 [Ci_pad][taps][Co_pad] with the taps rotated by 180 degrees (data gradient as a forward conv of dY).
+__global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
+                                   int Co, int Ci, int R, int S, int Co_pad, int Ci_pad) {
+    const int taps = R * S;
+    const long long nf = (long long)Co_pad * taps * Ci_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nf; i += (long long)gridDim.x * blockDim.x) {
+        if (wf) {
+            const int ci = (int)(i % Ci_pad);
+            const int tap = (int)((i / Ci_pad) % taps);
+            const int co = (int)(i / ((long long)Ci_pad * taps));
+            const float v = (co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * taps + tap] : 0.f;
+            wf[i] = __float2bfloat16(v);
+        }
+        if (wd) {
+            const int co = (int)(i % Co_pad);
+            const int tap = (int)((i / Co_pad) % taps);
+            const int ci = (int)(i / ((long long)Co_pad * taps));
+            const float v = (co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * taps + (taps - 1 - tap)] : 0.f;
+            wd[i] = __float2bfloat16(v);
+        }
+    }
+}
+
+// dWacc fp32 [Co_pad][taps][Ci_pad] -> grad fp32 [Co][Ci][R][S]
+__global__ void wgrad_finish_kernel(const float* __restrict__ acc, float* __restrict__ grad, int Co, int Ci, int taps,
+                                    int Ci_pad, int accumulate) {
+    const long long total = (long long)Co * Ci * taps;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % taps);
+        const int ci = (int)((i / taps) % Ci);
+        const int co = (int)(i / ((long long)taps * Ci));
+        const float v = acc[((long long)co * taps + tap) * Ci_pad + ci];
+        grad[i] = accumulate ? grad[i] + v : v;
+    }
+}
+
+// ---------------------------------------------------------------- batch-norm statistics
+// sums[0..C) += sum_p y[p,c], sums[C..2C) += sum_p y[p,c]^2 over P rows of an NHWC tensor (channel stride C).
+// blockDim = 256; a block covers rows_per_iter = 256 / (C/8) rows per step; cross-row reduction through shared memory,
+// then one atomicAdd per channel per block.
+template <typename T>
+__global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sums, long long P, int C) {
+    extern __shared__ float sh[];   // [2][rows_per_iter][C]
+    const int tpr = C / 8;                       // threads per row
+    const int rpi = blockDim.x / tpr;            // rows per iteration
+    const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (tr < rpi) {
+        for (long long r = (long long)blockIdx.x * rpi + tr; r < P; r += (long long)gridDim.x * rpi) {
+            float f[8];
+            V8<T>::load(y + r * C + tc * 8, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                s[k] += f[k];
+                q[k] += f[k] * f[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sh[tr * C + tc * 8 + k] = s[k];
+            sh[(rpi + tr) * C + tc * 8 + k] = q[k];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+        const int which = c / C, ch = c % C;
+        float a = 0.f;
+        for (int r = 0; r < rpi; ++r) a += sh[(which * rpi + r) * C + ch];
+        atomicAdd(sums + c, a);
+    }
+}
+
+// mean / invstd / folded scale+shift from the (possibly cross-rank reduced) sums; running-stat update with the
+// unbiased variance (momentum form of nn.SyncBatchNorm, reference modules.py:19).
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                                   float momentum, float eps, float* __restrict__ stat /* [4][C]: mean invstd scale shift */,
+                                   int C) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        const double mean = (double)sums[c] / count;
+        double var = (double)sums[C + c] / count - mean * mean;
+        if (var < 0) var = 0;
+        const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float sc = gamma[c] * invstd;
+        stat[c] = (float)mean;
+        stat[C + c] = invstd;
+        stat[2 * C + c] = sc;
+        stat[3 * C + c] = beta[c] - (float)mean * sc;
+        if (running_mean) {
+            const double unbiased = count > 1 ? var * count / (count - 1) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+    }
+}
+
+// eval mode: scale/shift from the running statistics
+__global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                      float* __restrict__ stat, int C) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        const float invstd = rsqrtf(rv[c] + eps);
+        const float sc = gamma[c] * invstd;
+        stat[c] = rm[c];
+        stat[C + c] = invstd;
+        stat[2 * C + c] = sc;
+        stat[3 * C + c] = beta[c] - rm[c] * sc;
+    }
+}
+
+// ---------------------------------------------------------------- norm + act (+pool / +upsample) forward
+// a = act(scale[c] * y + shift[c]); mode POOL averages 2x2 windows on the way out (DownBlock2D, reference
+// modules.py:59-70), mode UP replicates each pixel 2x2 (the nn.Upsample in front of UpBlock2D's conv, modules.py:78-89).
+// H, W are the INPUT spatial sizes.  Output is NHWC (TO) or, with nchw_out, NCHW fp32.
+template <typename TI, typename TO>
+__global__ void bn_act_fwd_kernel(const TI* __restrict__ y, const float* __restrict__ stat, TO* __restrict__ out,
+                                  int N, int H, int W, int C, int mode, int act, int nchw_out) {
+    const float* scale = stat + 2 * C;
+    const float* shift = stat + 3 * C;
+    const int groups = C / 8;
+    const int Ho = mode == FV_MODE_POOL ? H / 2 : H, Wo = mode == FV_MODE_POOL ? W / 2 : W;   // iteration domain
+    const long long total = (long long)N * Ho * Wo * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        long long pix = i / groups;
+        const int wo = (int)(pix % Wo);
+        const int ho = (int)((pix / Wo) % Ho);
+        const int n = (int)(pix / ((long long)Wo * Ho));
+        float sc[8], sf[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sc[k] = __ldg(scale + g * 8 + k);
+            sf[k] = __ldg(shift + g * 8 + k);
+        }
+        float r[8];
+        if (mode == FV_MODE_POOL) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    float f[8];
+                    V8<TI>::load(y + (((long long)n * H + 2 * ho + dy) * W + 2 * wo + dx) * C + g * 8, f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) r[k] += act_fwd(fmaf(f[k], sc[k], sf[k]), act);
+                }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] *= 0.25f;
+        } else {
+            float f[8];
+            V8<TI>::load(y + (((long long)n * H + ho) * W + wo) * C + g * 8, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = act_fwd(fmaf(f[k], sc[k], sf[k]), act);
+        }
+        if (mode == FV_MODE_UP) {
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx)
+                    V8<TO>::store(out + (((long long)n * 2 * H + 2 * ho + dy) * (2 * W) + 2 * wo + dx) * C + g * 8, r);
+        } else if (nchw_out) {
+            float* o = reinterpret_cast<float*>(out);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[(((long long)n * C + g * 8 + k) * Ho + ho) * Wo + wo] = r[k];
+        } else {
+            V8<TO>::store(out + (((long long)n * Ho + ho) * Wo + wo) * C + g * 8, r);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- norm + act backward
+// Effective upstream gradient at the (pre-pool / pre-upsample) activation:  POOL: g/4 of the pooled pixel,
+// UP: sum of the 2x2 replicated pixels, NONE: g.  g is NHWC (TG) or NCHW fp32 when g_nchw.
+template <typename TG>
+__device__ __forceinline__ void load_g(const TG* g, int g_nchw, int mode, int n, int h, int w, int H, int W, int C,
+                                       int grp, float (&r)[8]) {
+    if (mode == FV_MODE_POOL) {
+        const int Hp = H / 2, Wp = W / 2;
+        if (g_nchw) {
+            const float* gf = reinterpret_cast<const float*>(g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = 0.25f * __ldg(gf + (((long long)n * C + grp * 8 + k) * Hp + h / 2) * Wp + w / 2);
+        } else {
+            V8<TG>::load(g + (((long long)n * Hp + h / 2) * Wp + w / 2) * C + grp * 8, r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] *= 0.25f;
+        }
+    } else if (mode == FV_MODE_UP) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                float f[8];
+                V8<TG>::load(g + (((long long)n * 2 * H + 2 * h + dy) * (2 * W) + 2 * w + dx) * C + grp * 8, f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] += f[k];
+            }
+    } else {
+        V8<TG>::load(g + (((long long)n * H + h) * W + w) * C + grp * 8, r);
+    }
+}
+
+// pass 1: sums[0..C) += sum dz, sums[C..2C) += sum dz * xhat,  dz = g_eff * act'(scale*y+shift), xhat = (y-mean)*invstd
+template <typename TY, typename TG>
+__global__ void bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
+                                         float* __restrict__ sums, int N, int H, int W, int C, int mode, int act, int g_nchw) {
+    extern __shared__ float sh[];
+    const int tpr = C / 8, rpi = blockDim.x / tpr;
+    const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
+    const long long P = (long long)N * H * W;
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (tr < rpi) {
+        float mean[8], invstd[8], sc[8], sf[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            mean[k] = __ldg(stat + tc * 8 + k);
+            invstd[k] = __ldg(stat + C + tc * 8 + k);
+            sc[k] = __ldg(stat + 2 * C + tc * 8 + k);
+            sf[k] = __ldg(stat + 3 * C + tc * 8 + k);
+        }
+        for (long long r = (long long)blockIdx.x * rpi + tr; r < P; r += (long long)gridDim.x * rpi) {
+            const int w = (int)(r % W), h = (int)((r / W) % H), n = (int)(r / ((long long)W * H));
+            float f[8], ge[8];
+            V8<TY>::load(y + r * C + tc * 8, f);
+            load_g<TG>(g, g_nchw, mode, n, h, w, H, W, C, tc, ge);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
+                s1[k] += dz;
+                s2[k] += dz * (f[k] - mean[k]) * invstd[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sh[tr * C + tc * 8 + k] = s1[k];
+            sh[(rpi + tr) * C + tc * 8 + k] = s2[k];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+        const int which = c / C, ch = c % C;
+        float a = 0.f;
+        for (int r = 0; r < rpi; ++r) a += sh[(which * rpi + r) * C + ch];
+        atomicAdd(sums + c, a);
+    }
+}
+
+// dgamma += s2, dbeta += s1 (local sums: autograd's gradient all-reduce averages them later); coef = (cross-rank) sums / count
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums_local, const float* __restrict__ sums_global, double count,
+                                       float* dgamma, float* dbeta, float* __restrict__ coef, int C, int accumulate) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+        const float s1 = sums_local[c], s2 = sums_local[C + c];
+        if (dbeta) dbeta[c] = accumulate ? dbeta[c] + s1 : s1;
+        if (dgamma) dgamma[c] = accumulate ? dgamma[c] + s2 : s2;
+        coef[c] = (float)((double)sums_global[c] / count);
+        coef[C + c] = (float)((double)sums_global[C + c] / count);
+    }
+}
+
+// pass 2: dy = scale * (dz - c1 - xhat * c2) (+ add), written bf16 NHWC: the conv-output gradient fed to dgrad / wgrad
+template <typename TY, typename TG>
+__global__ void bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
+                                        const float* __restrict__ coef, const __nv_bfloat16* __restrict__ add,
+                                        __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C, int mode, int act, int g_nchw) {
+    const int groups = C / 8;
+    const long long total = (long long)N * H * W * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int grp = (int)(i % groups);
+        const long long r = i / groups;
+        const int w = (int)(r % W), h = (int)((r / W) % H), n = (int)(r / ((long long)W * H));
+        float f[8], ge[8], o[8];
+        V8<TY>::load(y + r * C + grp * 8, f);
+        load_g<TG>(g, g_nchw, mode, n, h, w, H, W, C, grp, ge);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = grp * 8 + k;
+            const float mean = __ldg(stat + c), invstd = __ldg(stat + C + c), sc = __ldg(stat + 2 * C + c),
+                        sf = __ldg(stat + 3 * C + c);
+            const float dz = ge[k] * act_grad(fmaf(f[k], sc, sf), act);
+            const float xhat = (f[k] - mean) * invstd;
+            o[k] = sc * (dz - __ldg(coef + c) - xhat * __ldg(coef + C + c));
+        }
+        if (add) {
+            float a[8];
+            V8<__nv_bfloat16>::load(add + r * C + grp * 8, a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] += a[k];
+        }
+        V8<__nv_bfloat16>::store(dy + r * C + grp * 8, o);
+    }
+}
+
+// per-channel column sums of an NHWC bf16 tensor (bias gradient of a conv that does not feed a batch norm)
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ sums, long long P, int C) {
+    extern __shared__ float sh[];
+    const int tpr = C / 8, rpi = blockDim.x / tpr;
+    const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (tr < rpi) {
+        for (long long r = (long long)blockIdx.x * rpi + tr; r < P; r += (long long)gridDim.x * rpi) {
+            float f[8];
+            V8<__nv_bfloat16>::load(y + r * C + tc * 8, f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s[k] += f[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sh[tr * C + tc * 8 + k] = s[k];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f;
+        for (int r = 0; r < rpi; ++r) a += sh[r * C + c];
+        atomicAdd(sums + c, a);
+    }
+}
+
+// ---------------------------------------------------------------- re-parameterisation + KL
+// h = [N][2*Dz] fp32 (mu | logstd, the NCHW flatten of the encoder output; reference models.py:559-560),
+// z = mu + exp(logstd) * eps (models.py:561), kl_rows[n] = sum_d(-0.5 - ls + 0.5 mu^2 + 0.5 exp(2 ls)) (losses.py:392).
+// One block row per sample chunk; warp-shuffle reduction, one atomicAdd per warp.
+__global__ void reparam_kl_fwd_kernel(const float* __restrict__ mu_p, const float* __restrict__ ls_p, long long row_stride,
+                                      const float* __restrict__ eps, float* __restrict__ z, float* __restrict__ kl_rows,
+                                      int Dz) {
+    const int n = blockIdx.y;
+    const float4* mu4 = reinterpret_cast<const float4*>(mu_p + (long long)n * row_stride);
+    const float4* ls4 = reinterpret_cast<const float4*>(ls_p + (long long)n * row_stride);
+    const float4* e4 = eps ? reinterpret_cast<const float4*>(eps + (long long)n * Dz) : nullptr;
+    float4* z4 = z ? reinterpret_cast<float4*>(z + (long long)n * Dz) : nullptr;
+    float acc = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Dz / 4; i += gridDim.x * blockDim.x) {
+        const float4 m = __ldg(mu4 + i), l = __ldg(ls4 + i);
+        const float sx = __expf(l.x), sy = __expf(l.y), sz = __expf(l.z), sw = __expf(l.w);
+        if (z4) {
+            float4 e = e4 ? __ldg(e4 + i) : make_float4(0, 0, 0, 0);
+            z4[i] = make_float4(fmaf(sx, e.x, m.x), fmaf(sy, e.y, m.y), fmaf(sz, e.z, m.z), fmaf(sw, e.w, m.w));
+        }
+        acc += (-0.5f - l.x + 0.5f * m.x * m.x + 0.5f * sx * sx) + (-0.5f - l.y + 0.5f * m.y * m.y + 0.5f * sy * sy) +
+               (-0.5f - l.z + 0.5f * m.z * m.z + 0.5f * sz * sz) + (-0.5f - l.w + 0.5f * m.w * m.w + 0.5f * sw * sw);
+    }
+    if (kl_rows) {
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) atomicAdd(kl_rows + n, acc);
+    }
+}
+
+// dmu = dz + kscale * mu (+ dmu_ext);  dls = dz * eps * exp(ls) + kscale * (exp(2 ls) - 1) (+ dls_ext)
+// kscale = (upstream dK) / (N * Dz), read from device memory when kscale_ptr is given (times kscale).
+__global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu_p, const float* __restrict__ ls_p, long long row_stride,
+                                      const float* __restrict__ eps, const float* __restrict__ dz,
+                                      const float* __restrict__ dmu_ext, const float* __restrict__ dls_ext,
+                                      float kscale, const float* __restrict__ kscale_ptr, float* __restrict__ dmu,
+                                      float* __restrict__ dls, long long out_stride, int Dz) {
+    const int n = blockIdx.y;
+    const float ks = kscale_ptr ? kscale * __ldg(kscale_ptr) : kscale;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Dz; i += gridDim.x * blockDim.x) {
+        const float m = mu_p[(long long)n * row_stride + i], l = ls_p[(long long)n * row_stride + i];
+        const float s = __expf(l);
+        const float g = dz ? dz[(long long)n * Dz + i] : 0.f;
+        const float e = eps ? eps[(long long)n * Dz + i] : 0.f;
+        float a = g + ks * m, b = g * e * s + ks * (s * s - 1.f);
+        if (dmu_ext) a += dmu_ext[(long long)n * Dz + i];
+        if (dls_ext) b += dls_ext[(long long)n * Dz + i];
+        dmu[(long long)n * out_stride + i] = a;
+        dls[(long long)n * out_stride + i] = b;
+    }
+}
+
+// ---------------------------------------------------------------- reconstruction loss (+ sigmoid) forward + gradient
+// pred = sigmoid(logits) if use_sigmoid else logits (reference models.py:1110); loss_sum += sum l(pred - target) with
+// l = squared (ReconLoss / nn.MSELoss, losses.py:396-403) or absolute (nn.L1Loss, losses.py:128) error;
+// grad = gscale * dl/dlogits, written fp32 (same layout as the inputs) and/or bf16 NHWC padded to Cp channels.
+// Block reduce: warp shuffle -> shared -> one atomicAdd per block.
+__global__ void recon_loss_kernel(const float* __restrict__ logits, const float* __restrict__ target, float* __restrict__ pred_out,
+                                  float* __restrict__ grad_f32, __nv_bfloat16* __restrict__ grad_nhwc, float* __restrict__ loss_sum,
+                                  int N, int C, int HW, int Cp, int l1, int use_sigmoid, float gscale) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    const long long P = (long long)N * HW;
+    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < P; pix += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(pix / HW), hw = (int)(pix % HW);
+        float gr[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) gr[k] = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const long long idx = ((long long)n * C + c) * HW + hw;
+            const float o = __ldg(logits + idx), t = __ldg(target + idx);
+            const float s = use_sigmoid ? 1.f / (1.f + __expf(-o)) : o;
+            const float d = s - t;
+            acc += l1 ? fabsf(d) : d * d;
+            float gd = l1 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : 2.f * d;
+            if (use_sigmoid) gd *= s * (1.f - s);
+            gd *= gscale;
+            if (pred_out) pred_out[idx] = s;
+            if (grad_f32) grad_f32[idx] = gd;
+            if (c < 16) gr[c] = gd;
+        }
+        if (grad_nhwc) {
+            for (int c0 = 0; c0 < Cp; c0 += 8) {
+                float f[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = (c0 + k < 16) ? gr[c0 + k] : 0.f;
+                V8<__nv_bfloat16>::store(grad_nhwc + pix * Cp + c0, f);
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+    }
+}
+
+// flat variant for arbitrary same-shape fp32 tensors (the drop-in ReconLoss()((a, b))): float4 vectorised
+__global__ void recon_loss_flat_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ grad,
+                                       float* __restrict__ loss_sum, long long E, int l1, float gscale) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    const long long E4 = E / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < E4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+        const float d[4] = {x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w};
+        float g[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc += l1 ? fabsf(d[k]) : d[k] * d[k];
+            g[k] = gscale * (l1 ? (d[k] > 0.f ? 1.f : (d[k] < 0.f ? -1.f : 0.f)) : 2.f * d[k]);
+        }
+        if (grad) reinterpret_cast<float4*>(grad)[i] = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(E - E4 * 4)) {
+        const long long i = E4 * 4 + threadIdx.x;
+        const float d = a[i] - b[i];
+        acc += l1 ? fabsf(d) : d * d;
+        if (grad) grad[i] = gscale * (l1 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : 2.f * d);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+    }
+}
+
+// out[i] = in[i] * scale_ptr[0] * scale  (chain rule for a scalar upstream gradient living on the device)
+template <typename T>
+__global__ void scale_kernel(const T* __restrict__ in, T* __restrict__ out, long long n8, const float* __restrict__ scale_ptr,
+                             float scale) {
+    const float s = scale_ptr ? scale * __ldg(scale_ptr) : scale;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float f[8];
+        V8<T>::load(in + i * 8, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] *= s;
+        V8<T>::store(out + i * 8, f);
+    }
+}
+
+}  // namespace fv
+
+// =================================================================== C ABI
+using namespace fv;
+#define STREAM ((cudaStream_t)stream)
+
+static int check_c8(const char* who, int C) {
+    if (C < 8 || C % 8 || C > 2048) return fail(FV_ERR_UNSUPPORTED, "%s: channel count %d must be a multiple of 8 (<= 2048)", who, C);
+    if (kThreads % (C / 8) && (C / 8) <= kThreads) return fail(FV_ERR_UNSUPPORTED, "%s: C/8 = %d must divide %d", who, C / 8, kThreads);
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int H, int W, int Cp, void* stream) {
+    if (!src || !dst || Cp % 8 || Cp < C) return fail(FV_ERR_ARG, "fv_nchw_to_nhwc: bad arguments (C=%d Cp=%d)", C, Cp);
+    const long long items = (long long)N * H * W * (Cp / 8);
+    if (dst_dtype == FV_DT_BF16)
+        nchw_to_nhwc_kernel<__nv_bfloat16><<<grid_for(items), kThreads, 0, STREAM>>>(src, (__nv_bfloat16*)dst, N, C, H * W, Cp);
+    else
+        nchw_to_nhwc_kernel<float><<<grid_for(items), kThreads, 0, STREAM>>>(src, (float*)dst, N, C, H * W, Cp);
+    FV_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int N, int C, int H, int W, int Cs, int accumulate,
+                               void* stream) {
+    if (!src || !dst || Cs % 8 || Cs < C) return fail(FV_ERR_ARG, "fv_nhwc_to_nchw: bad arguments (C=%d Cs=%d)", C, Cs);
+    const long long items = (long long)N * H * W * ((C + 7) / 8);
+    if (src_dtype == FV_DT_BF16)
+        nhwc_to_nchw_kernel<__nv_bfloat16><<<grid_for(items), kThreads, 0, STREAM>>>((const __nv_bfloat16*)src, dst, N, C, H * W, Cs, accumulate);
+    else
+        nhwc_to_nchw_kernel<float><<<grid_for(items), kThreads, 0, STREAM>>>((const float*)src, dst, N, C, H * W, Cs, accumulate);
+    FV_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_weight_prep(const float* w, void* wf, void* wd, int Co, int Ci, int R, int S, int Co_pad, int Ci_pad, void* stream) {
+    if (!w || (!wf && !wd) || Co_pad < Co || Ci_pad < Ci) return fail(FV_ERR_ARG, "fv_weight_prep: bad arguments");
+    const long long items = (long long)Co_pad * Ci_pad * R * S;
+    weight_prep_kernel<<<grid_for(items), kThreads, 0, STREAM>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Co, Ci, R, S, Co_pad, Ci_pad);
+    FV_LAUNCH_CHECK("weight_prep_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const float* acc, float* grad, int Co, int Ci, int R, int S, int Ci_pad, int accumulate, void* stream) {
+    if (!acc || !grad) return fail(FV_ERR_ARG, "fv_wgrad_finish: null pointer");
+    wgrad_finish_kernel<<<grid_for((long long)Co * Ci * R * S), kThreads, 0, STREAM>>>(acc, grad, Co, Ci, R * S, Ci_pad, accumulate);
+    FV_LAUNCH_CHECK("wgrad_finish_kernel");
+    return FV_OK;
+}
+
+static int reduce_geometry(int C, long long P, int& grid, size_t& shmem) {
+    const int rpi = kThreads / (C / 8) > 0 ? kThreads / (C / 8) : 1;
+    long long blocks = (P + rpi - 1) / rpi;
+    const long long cap = (long long)num_sms() * 4;
+    grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+    shmem = (size_t)2 * rpi * C * sizeof(float);
+    return rpi;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bn_stats(const void* y, int dtype, float* sums, long long P, int C, void* stream) {
+    if (!y || !sums) return fail(FV_ERR_ARG, "fv_bn_stats: null pointer");
+    if (int e = check_c8("fv_bn_stats", C)) return e;
+    int grid; size_t sh;
+    reduce_geometry(C, P, grid, sh);
+    if (dtype == FV_DT_BF16)
+        bn_stats_kernel<__nv_bfloat16><<<grid, kThreads, sh, STREAM>>>((const __nv_bfloat16*)y, sums, P, C);
+    else
+        bn_stats_kernel<float><<<grid, kThreads, sh, STREAM>>>((const float*)y, sums, P, C);
+    FV_LAUNCH_CHECK("bn_stats_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bn_finalize(const float* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, float momentum, float eps, float* stat, int C, void* stream) {
+    if (!sums || !gamma || !beta || !stat || count <= 0) return fail(FV_ERR_ARG, "fv_bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums, count, gamma, beta, running_mean, running_var, momentum, eps, stat, C);
+    FV_LAUNCH_CHECK("bn_finalize_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                                 float eps, float* stat, int C, void* stream) {
+    if (!gamma || !beta || !running_mean || !running_var || !stat) return fail(FV_ERR_ARG, "fv_bn_eval_affine: null pointer");
+    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(gamma, beta, running_mean, running_var, eps, stat, C);
+    FV_LAUNCH_CHECK("bn_eval_affine_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bn_act_fwd(const void* y, int in_dtype, const float* stat, void* out, int out_dtype, int nchw_out, int N, int H,
+                             int W, int C, int mode, int act, void* stream) {
+    if (!y || !stat || !out) return fail(FV_ERR_ARG, "fv_bn_act_fwd: null pointer");
+    if (C % 8) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: C=%d must be a multiple of 8", C);
+    if (mode == FV_MODE_POOL && ((H | W) & 1)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: pooling needs even H, W");
+    if (nchw_out && (out_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: NCHW output is fp32, no upsample");
+    const int Ho = mode == FV_MODE_POOL ? H / 2 : H, Wo = mode == FV_MODE_POOL ? W / 2 : W;
+    const int grid = grid_for((long long)N * Ho * Wo * (C / 8));
+#define LAUNCH(TI, TO) bn_act_fwd_kernel<TI, TO><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, mode, act, nchw_out)
+    if (in_dtype == FV_DT_BF16 && out_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
+    else if (in_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, float);
+    else if (out_dtype == FV_DT_BF16) LAUNCH(float, __nv_bfloat16);
+    else LAUNCH(float, float);
+#undef LAUNCH
+    FV_LAUNCH_CHECK("bn_act_fwd_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_reduce(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat,
+                                    float* sums, int N, int H, int W, int C, int mode, int act, void* stream) {
+    if (!y || !g || !stat || !sums) return fail(FV_ERR_ARG, "fv_bn_act_bwd_reduce: null pointer");
+    if (int e = check_c8("fv_bn_act_bwd_reduce", C)) return e;
+    if (g_nchw && (g_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_reduce: NCHW g is fp32, no upsample");
+    int grid; size_t sh;
+    reduce_geometry(C, (long long)N * H * W, grid, sh);
+#define LAUNCH(TY, TG) bn_act_bwd_reduce_kernel<TY, TG><<<grid, kThreads, sh, STREAM>>>((const TY*)y, (const TG*)g, stat, sums, N, H, W, C, mode, act, g_nchw)
+    if (y_dtype == FV_DT_BF16 && g_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
+    else if (y_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, float);
+    else if (g_dtype == FV_DT_BF16) LAUNCH(float, __nv_bfloat16);
+    else LAUNCH(float, float);
+#undef LAUNCH
+    FV_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bn_bwd_finalize(const float* sums_local, const float* sums_global, double count, float* dgamma, float* dbeta,
+                                  float* coef, int C, int accumulate, void* stream) {
+    if (!sums_local || !sums_global || !coef || count <= 0) return fail(FV_ERR_ARG, "fv_bn_bwd_finalize: bad arguments");
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, STREAM>>>(sums_local, sums_global, count, dgamma, dbeta, coef, C, accumulate);
+    FV_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_apply(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat,
+                                   const float* coef, const void* add, void* dy, int N, int H, int W, int C, int mode, int act,
+                                   void* stream) {
+    if (!y || !g || !stat || !coef || !dy) return fail(FV_ERR_ARG, "fv_bn_act_bwd_apply: null pointer");
+    if (C % 8) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: C=%d must be a multiple of 8", C);
+    if (g_nchw && (g_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: NCHW g is fp32, no upsample");
+    const int grid = grid_for((long long)N * H * W * (C / 8));
+#define LAUNCH(TY, TG) bn_act_bwd_apply_kernel<TY, TG><<<grid, kThreads, 0, STREAM>>>((const TY*)y, (const TG*)g, stat, coef, (const __nv_bfloat16*)add, (__nv_bfloat16*)dy, N, H, W, C, mode, act, g_nchw)
+    if (y_dtype == FV_DT_BF16 && g_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
+    else if (y_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, float);
+    else if (g_dtype == FV_DT_BF16) LAUNCH(float, __nv_bfloat16);
+    else LAUNCH(float, float);
+#undef LAUNCH
+    FV_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_colsum(const void* y, float* sums, long long P, int C, void* stream) {
+    if (!y || !sums) return fail(FV_ERR_ARG, "fv_colsum: null pointer");
+    if (int e = check_c8("fv_colsum", C)) return e;
+    int grid; size_t sh;
+    reduce_geometry(C, P, grid, sh);
+    colsum_kernel<<<grid, kThreads, sh / 2, STREAM>>>((const __nv_bfloat16*)y, sums, P, C);
+    FV_LAUNCH_CHECK("colsum_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_reparam_kl_fwd(const float* mu, const float* logstd, long long row_stride, const float* eps, float* z,
+                                 float* kl_rows, int N, int Dz, void* stream) {
+    if (!mu || !logstd || Dz % 4 || N < 1) return fail(FV_ERR_ARG, "fv_reparam_kl_fwd: bad arguments (Dz=%d must be a multiple of 4)", Dz);
+    int bx = (Dz / 4 + kThreads - 1) / kThreads;
+    const int cap = (num_sms() * 8 + N - 1) / N;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    reparam_kl_fwd_kernel<<<dim3(bx, N), kThreads, 0, STREAM>>>(mu, logstd, row_stride, eps, z, kl_rows, Dz);
+    FV_LAUNCH_CHECK("reparam_kl_fwd_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_reparam_kl_bwd(const float* mu, const float* logstd, long long row_stride, const float* eps, const float* dz,
+                                 const float* dmu_ext, const float* dls_ext, float kscale, const float* kscale_ptr, float* dmu,
+                                 float* dls, long long out_stride, int N, int Dz, void* stream) {
+    if (!mu || !logstd || !dmu || !dls || N < 1) return fail(FV_ERR_ARG, "fv_reparam_kl_bwd: bad arguments");
+    int bx = (Dz + kThreads - 1) / kThreads;
+    const int cap = (num_sms() * 8 + N - 1) / N;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    reparam_kl_bwd_kernel<<<dim3(bx, N), kThreads, 0, STREAM>>>(mu, logstd, row_stride, eps, dz, dmu_ext, dls_ext, kscale, kscale_ptr,
+                                                                dmu, dls, out_stride, Dz);
+    FV_LAUNCH_CHECK("reparam_kl_bwd_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_recon_loss(const float* logits, const float* target, float* pred_out, float* grad_f32, void* grad_nhwc,
+                             float* loss_sum, int N, int C, int H, int W, int Cp, int l1, int use_sigmoid, float gscale,
+                             void* stream) {
+    if (!logits || !target || !loss_sum) return fail(FV_ERR_ARG, "fv_recon_loss: null pointer");
+    if (grad_nhwc && (Cp % 8 || Cp < C || C > 16)) return fail(FV_ERR_UNSUPPORTED, "fv_recon_loss: NHWC gradient needs C <= 16 <= Cp, Cp %% 8 == 0");
+    recon_loss_kernel<<<grid_for((long long)N * H * W), kThreads, 0, STREAM>>>(logits, target, pred_out, grad_f32, (__nv_bfloat16*)grad_nhwc,
+                                                                             loss_sum, N, C, H * W, Cp, l1, use_sigmoid, gscale);
+    FV_LAUNCH_CHECK("recon_loss_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_recon_loss_flat(const float* a, const float* b, float* grad, float* loss_sum, long long E, int l1, float gscale,
+                                  void* stream) {
+    if (!a || !b || !loss_sum || E < 1) return fail(FV_ERR_ARG, "fv_recon_loss_flat: bad arguments");
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(grad)) & 15)
+        return fail(FV_ERR_ARG, "fv_recon_loss_flat: pointers must be 16-byte aligned");
+    recon_loss_flat_kernel<<<grid_for(E / 4 + 1), kThreads, 0, STREAM>>>(a, b, grad, loss_sum, E, l1, gscale);
+    FV_LAUNCH_CHECK("recon_loss_flat_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_scale(const void* in, void* out, int dtype, long long n, const float* scale_ptr, float scale, void* stream) {
+    if (!in || !out || n % 8) return fail(FV_ERR_ARG, "fv_scale: element count %lld must be a multiple of 8", n);
+    if (dtype == FV_DT_BF16)
+        scale_kernel<__nv_bfloat16><<<grid_for(n / 8), kThreads, 0, STREAM>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n / 8, scale_ptr, scale);
+    else
+        scale_kernel<float><<<grid_for(n / 8), kThreads, 0, STREAM>>>((const float*)in, (float*)out, n / 8, scale_ptr, scale);
+    FV_LAUNCH_CHECK("scale_kernel");
+    return FV_OK;
+}

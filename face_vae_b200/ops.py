@@ -1,0 +1,279 @@
+"""Tensor-level wrappers over the C ABI (include/facevae_b200.h).
+
+PyTorch is used for device memory and streams only: every function allocates its outputs with torch, passes raw
+device pointers plus the current CUDA stream to libfacevae_b200.so and returns immediately (asynchronous).
+Activations are explicit NHWC tensors ``[N, H, W, C]`` (bf16 unless stated), C padded with ``pad_channels``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LEAKY, ACT_NONE, ACT_RELU, DT_BF16, DT_F32, MODE_NONE, MODE_POOL, MODE_UP, OUT_NCHW_F32,
+                   OUT_NHWC_BF16, OUT_NHWC_F32, call)
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def pad_channels(c: int) -> int:
+    """Channel padding accepted by the tcgen05 kernels: 16, 32 or a multiple of 64."""
+    if c <= 16:
+        return 16
+    if c <= 32:
+        return 32
+    return (c + 63) // 64 * 64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return DT_BF16
+    if t.dtype == torch.float32:
+        return DT_F32
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _chk(t: torch.Tensor, name: str, dtype=None):
+    if not t.is_cuda:
+        raise _lib.FaceVaeError(f"{name}: expected a CUDA tensor (this package has no CPU path)")
+    if not t.is_contiguous():
+        raise _lib.FaceVaeError(f"{name}: expected a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.FaceVaeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def nchw_to_nhwc(x: torch.Tensor, cp: Optional[int] = None, dtype=torch.bfloat16) -> torch.Tensor:
+    _chk(x, "x", torch.float32)
+    n, c, h, w = x.shape
+    cp = pad_channels(c) if cp is None else cp
+    out = torch.empty((n, h, w, cp), device=x.device, dtype=dtype)
+    call("fv_nchw_to_nhwc", x.data_ptr(), out.data_ptr(), _dt(out), n, c, h, w, cp, _stream())
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                 accumulate: bool = False) -> torch.Tensor:
+    _chk(x, "x")
+    n, h, w, cs = x.shape
+    c = cs if c is None else c
+    if out is None:
+        out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+        accumulate = False
+    call("fv_nhwc_to_nchw", x.data_ptr(), _dt(x), _chk(out, "out", torch.float32).data_ptr(), n, c, h, w, cs,
+         int(accumulate), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+def weight_prep(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = True
+                ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """nn.Conv2d weight [Co,Ci,R,S] fp32 -> (wf [Co_pad,R*S,Ci_pad], wd [Ci_pad,R*S,Co_pad]) bf16."""
+    _chk(w, "weight", torch.float32)
+    co, ci, r, s = w.shape
+    cop, cip = pad_channels(co), pad_channels(ci)
+    wf = torch.empty((cop, r * s, cip), device=w.device, dtype=torch.bfloat16) if want_fwd else None
+    wd = torch.empty((cip, r * s, cop), device=w.device, dtype=torch.bfloat16) if want_dgrad else None
+    call("fv_weight_prep", w.data_ptr(), _ptr(wf), _ptr(wd), co, ci, r, s, cop, cip, _stream())
+    return wf, wd
+
+
+def conv2d(x: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], co: int, ksize: int,
+           residual: Optional[torch.Tensor] = None, out_mode: int = OUT_NHWC_BF16) -> torch.Tensor:
+    """x NHWC bf16 [N,H,W,Ci]; wf [Co_pad, k*k, Ci] bf16 -> y (NHWC [N,H,W,Co_pad] or NCHW fp32 [N,co,H,W])."""
+    _chk(x, "x", torch.bfloat16)
+    _chk(wf, "wf", torch.bfloat16)
+    n, h, w, ci = x.shape
+    cop, taps, ci2 = wf.shape
+    if ci2 != ci or taps != ksize * ksize:
+        raise _lib.FaceVaeError(f"conv2d: filter {tuple(wf.shape)} does not match input channels {ci} / k={ksize}")
+    if out_mode == OUT_NCHW_F32:
+        y = torch.empty((n, co, h, w), device=x.device, dtype=torch.float32)
+    else:
+        y = torch.empty((n, h, w, cop), device=x.device,
+                        dtype=torch.bfloat16 if out_mode == OUT_NHWC_BF16 else torch.float32)
+    if bias is not None:
+        _chk(bias, "bias", torch.float32)
+    if residual is not None:
+        _chk(residual, "residual", torch.bfloat16)
+        if tuple(residual.shape) != (n, h, w, cop):
+            raise _lib.FaceVaeError("conv2d: residual shape mismatch")
+    call("fv_conv2d", x.data_ptr(), wf.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), out_mode, n, h, w, ci, co,
+         cop, ksize, ksize, (ksize - 1) // 2, _stream())
+    return y
+
+
+def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int) -> torch.Tensor:
+    """x NHWC bf16 [N,H,W,Ci], dy NHWC bf16 [N,H,W,Co_pad] -> dw_acc fp32 [Co_pad, k*k, Ci]."""
+    _chk(x, "x", torch.bfloat16)
+    _chk(dy, "dy", torch.bfloat16)
+    n, h, w, ci = x.shape
+    cop = dy.shape[3]
+    if tuple(dy.shape[:3]) != (n, h, w):
+        raise _lib.FaceVaeError("conv2d_wgrad: x / dy shape mismatch")
+    acc = torch.zeros((cop, ksize * ksize, ci), device=x.device, dtype=torch.float32)
+    call("fv_conv2d_wgrad", x.data_ptr(), dy.data_ptr(), acc.data_ptr(), n, h, w, ci, cop, ksize, ksize,
+         (ksize - 1) // 2, _stream())
+    return acc
+
+
+def wgrad_finish(acc: torch.Tensor, co: int, ci: int, ksize: int, grad: Optional[torch.Tensor] = None) -> torch.Tensor:
+    accumulate = grad is not None
+    if grad is None:
+        grad = torch.empty((co, ci, ksize, ksize), device=acc.device, dtype=torch.float32)
+    call("fv_wgrad_finish", acc.data_ptr(), _chk(grad, "grad", torch.float32).data_ptr(), co, ci, ksize, ksize,
+         acc.shape[2], int(accumulate), _stream())
+    return grad
+
+
+def colsum(y: torch.Tensor) -> torch.Tensor:
+    _chk(y, "y", torch.bfloat16)
+    c = y.shape[-1]
+    sums = torch.zeros((c,), device=y.device, dtype=torch.float32)
+    call("fv_colsum", y.data_ptr(), sums.data_ptr(), y.numel() // c, c, _stream())
+    return sums
+
+
+# ------------------------------------------------------------------------------------------------ batch norm glue
+def bn_stats(y: torch.Tensor) -> torch.Tensor:
+    _chk(y, "y")
+    c = y.shape[-1]
+    sums = torch.zeros((2 * c,), device=y.device, dtype=torch.float32)
+    call("fv_bn_stats", y.data_ptr(), _dt(y), sums.data_ptr(), y.numel() // c, c, _stream())
+    return sums
+
+
+def bn_finalize(sums: torch.Tensor, count: float, gamma: torch.Tensor, beta: torch.Tensor,
+                running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
+                momentum: float = BN_MOMENTUM, eps: float = BN_EPS) -> torch.Tensor:
+    c = gamma.numel()
+    stat = torch.empty((4, c), device=sums.device, dtype=torch.float32)
+    call("fv_bn_finalize", sums.data_ptr(), float(count), gamma.data_ptr(), beta.data_ptr(), _ptr(running_mean),
+         _ptr(running_var), momentum, eps, stat.data_ptr(), c, _stream())
+    return stat
+
+
+def bn_eval_affine(gamma, beta, running_mean, running_var, eps: float = BN_EPS) -> torch.Tensor:
+    c = gamma.numel()
+    stat = torch.empty((4, c), device=gamma.device, dtype=torch.float32)
+    call("fv_bn_eval_affine", gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(), eps,
+         stat.data_ptr(), c, _stream())
+    return stat
+
+
+def bn_act_fwd(y: torch.Tensor, stat: torch.Tensor, mode: int = MODE_NONE, act: int = ACT_RELU,
+               out_dtype=torch.bfloat16, nchw_out: bool = False) -> torch.Tensor:
+    _chk(y, "y")
+    n, h, w, c = y.shape
+    ho, wo = (h // 2, w // 2) if mode == MODE_POOL else ((2 * h, 2 * w) if mode == MODE_UP else (h, w))
+    shape = (n, c, ho, wo) if nchw_out else (n, ho, wo, c)
+    out = torch.empty(shape, device=y.device, dtype=out_dtype)
+    call("fv_bn_act_fwd", y.data_ptr(), _dt(y), stat.data_ptr(), out.data_ptr(), _dt(out), int(nchw_out), n, h, w, c,
+         mode, act, _stream())
+    return out
+
+
+def bn_act_bwd_reduce(y: torch.Tensor, g: torch.Tensor, stat: torch.Tensor, mode: int, act: int,
+                      g_nchw: bool = False) -> torch.Tensor:
+    _chk(y, "y")
+    _chk(g, "g")
+    n, h, w, c = y.shape
+    sums = torch.zeros((2 * c,), device=y.device, dtype=torch.float32)
+    call("fv_bn_act_bwd_reduce", y.data_ptr(), _dt(y), g.data_ptr(), _dt(g), int(g_nchw), stat.data_ptr(),
+         sums.data_ptr(), n, h, w, c, mode, act, _stream())
+    return sums
+
+
+def bn_bwd_finalize(sums_local: torch.Tensor, sums_global: torch.Tensor, count: float, c: int,
+                    dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None):
+    accumulate = dgamma is not None
+    if dgamma is None:
+        dgamma = torch.empty((c,), device=sums_local.device, dtype=torch.float32)
+        dbeta = torch.empty((c,), device=sums_local.device, dtype=torch.float32)
+    coef = torch.empty((2, c), device=sums_local.device, dtype=torch.float32)
+    call("fv_bn_bwd_finalize", sums_local.data_ptr(), sums_global.data_ptr(), float(count), dgamma.data_ptr(),
+         dbeta.data_ptr(), coef.data_ptr(), c, int(accumulate), _stream())
+    return dgamma, dbeta, coef
+
+
+def bn_act_bwd_apply(y: torch.Tensor, g: torch.Tensor, stat: torch.Tensor, coef: torch.Tensor, mode: int, act: int,
+                     add: Optional[torch.Tensor] = None, g_nchw: bool = False) -> torch.Tensor:
+    n, h, w, c = y.shape
+    dy = torch.empty((n, h, w, c), device=y.device, dtype=torch.bfloat16)
+    if add is not None:
+        _chk(add, "add", torch.bfloat16)
+    call("fv_bn_act_bwd_apply", y.data_ptr(), _dt(y), g.data_ptr(), _dt(g), int(g_nchw), stat.data_ptr(),
+         coef.data_ptr(), _ptr(add), dy.data_ptr(), n, h, w, c, mode, act, _stream())
+    return dy
+
+
+# ------------------------------------------------------------------------------------------------ VAE bottleneck + losses
+def reparam_kl_fwd(mu: torch.Tensor, logstd: torch.Tensor, eps: Optional[torch.Tensor], want_z: bool = True,
+                   want_kl: bool = True):
+    """mu / logstd: fp32 [N, Dz] row views (unit inner stride, common row stride).  Returns (z [N,Dz] | None, kl_rows [N] | None)."""
+    n, dz = mu.shape
+    if mu.stride(1) != 1 or logstd.stride(1) != 1 or mu.stride(0) != logstd.stride(0):
+        raise _lib.FaceVaeError("reparam_kl_fwd: mu/logstd must be row views with a common row stride")
+    z = torch.empty((n, dz), device=mu.device, dtype=torch.float32) if want_z else None
+    kl = torch.zeros((n,), device=mu.device, dtype=torch.float32) if want_kl else None
+    if eps is not None:
+        _chk(eps, "eps", torch.float32)
+    call("fv_reparam_kl_fwd", mu.data_ptr(), logstd.data_ptr(), mu.stride(0), _ptr(eps), _ptr(z), _ptr(kl), n, dz,
+         _stream())
+    return z, kl
+
+
+def reparam_kl_bwd(mu, logstd, eps, dz, dmu_ext, dls_ext, kscale: float, kscale_ptr: Optional[torch.Tensor],
+                   out: Optional[torch.Tensor] = None):
+    """Returns dh fp32 [N, 2*Dz] = (dmu | dlogstd)."""
+    n, d = mu.shape
+    if out is None:
+        out = torch.empty((n, 2 * d), device=mu.device, dtype=torch.float32)
+    dmu, dls = out[:, :d], out[:, d:]
+    call("fv_reparam_kl_bwd", mu.data_ptr(), logstd.data_ptr(), mu.stride(0), _ptr(eps), _ptr(dz), _ptr(dmu_ext),
+         _ptr(dls_ext), float(kscale), _ptr(kscale_ptr), dmu.data_ptr(), dls.data_ptr(), out.stride(0), n, d, _stream())
+    return out
+
+
+def recon_loss(logits: torch.Tensor, target: torch.Tensor, l1: bool = False, use_sigmoid: bool = True,
+               gscale: float = 1.0, want_pred: bool = True, want_grad_f32: bool = False, want_grad_nhwc: bool = True):
+    """Returns (loss_sum [1], pred | None, grad_f32 | None, grad_nhwc [N,H,W,16] bf16 | None)."""
+    _chk(logits, "logits", torch.float32)
+    _chk(target, "target", torch.float32)
+    n, c, h, w = logits.shape
+    cp = pad_channels(c)
+    loss = torch.zeros((1,), device=logits.device, dtype=torch.float32)
+    pred = torch.empty_like(logits) if want_pred else None
+    gf = torch.empty_like(logits) if want_grad_f32 else None
+    gn = torch.empty((n, h, w, cp), device=logits.device, dtype=torch.bfloat16) if want_grad_nhwc else None
+    call("fv_recon_loss", logits.data_ptr(), target.data_ptr(), _ptr(pred), _ptr(gf), _ptr(gn), loss.data_ptr(), n, c, h,
+         w, cp, int(l1), int(use_sigmoid), float(gscale), _stream())
+    return loss, pred, gf, gn
+
+
+def recon_loss_flat(a: torch.Tensor, b: torch.Tensor, l1: bool = False, gscale: float = 1.0, want_grad: bool = True):
+    _chk(a, "a", torch.float32)
+    _chk(b, "b", torch.float32)
+    loss = torch.zeros((1,), device=a.device, dtype=torch.float32)
+    grad = torch.empty_like(a) if want_grad else None
+    call("fv_recon_loss_flat", a.data_ptr(), b.data_ptr(), _ptr(grad), loss.data_ptr(), a.numel(), int(l1), float(gscale),
+         _stream())
+    return loss, grad
+
+
+def scale(t: torch.Tensor, scale_ptr: Optional[torch.Tensor], s: float = 1.0, out: Optional[torch.Tensor] = None):
+    _chk(t, "t")
+    out = torch.empty_like(t) if out is None else out
+    call("fv_scale", t.data_ptr(), out.data_ptr(), _dt(t), t.numel(), _ptr(scale_ptr), float(s), _stream())
+    return out

@@ -1,0 +1,107 @@
+/* facevae_b200.h -- C ABI of libfacevae_b200.so (sm_100a only).
+ *
+ * The reference (Luh1124/face-vae) has no C/FFI boundary: its hot path is PyTorch nn.Modules whose arithmetic
+ * dispatches into ATen/cuDNN.  This header is the boundary a maintainer binds instead: each
+ * entry point names the reference call site (file:line in /root/reference) whose device work it replaces.  The
+ * Python facade in face_vae_b200/ (same class names and signatures as the reference's modules.py / models.py /
+ * losses.py) calls these through ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - return 0 on success, non-zero on failure (bad shape / unsupported configuration / CUDA error); the message
+ *     is available from fv_last_error() (thread-local).  Nothing is thrown, nothing falls back to another path;
+ *   - the library never allocates, frees or retains caller memory;
+ *   - activations are NHWC ("channels last") bf16 or fp32 with the channel count padded to a multiple of 16
+ *     (Cp / Ci / Co_pad below); the NCHW fp32 tensors of the reference API are converted at the edges.
+ */
+#pragma once
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { FV_DT_BF16 = 0, FV_DT_F32 = 1 };
+enum { FV_OUT_NHWC_BF16 = 0, FV_OUT_NHWC_F32 = 1, FV_OUT_NCHW_F32 = 2 };
+enum { FV_MODE_NONE = 0, FV_MODE_POOL = 1, FV_MODE_UP = 2 };   /* fused 2x2 avg-pool / nearest 2x up-sample */
+enum { FV_ACT_NONE = 0, FV_ACT_RELU = 1, FV_ACT_LEAKY = 2 };   /* LeakyReLU slope 0.2 (reference modules.py:29) */
+
+const char* fv_last_error(void);
+const char* fv_version(void);
+int fv_device_ok(void);   /* 0 iff the current device is sm_10x */
+
+/* ---- layout at the edges of the path -------------------------------------------------------------------- */
+/* NCHW fp32 [N,C,H,W] -> NHWC [N,H,W,Cp] (bf16 or fp32), channels C..Cp-1 zero.  Frames enter the reference as
+ * NCHW fp32 in [0,1] (dataset.py:116-129, logger.py:144-148). */
+int fv_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, int H, int W, int Cp, void* stream);
+/* NHWC (channel stride Cs) -> NCHW fp32, first C channels; accumulate != 0 adds into dst. */
+int fv_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int N, int C, int H, int W, int Cs, int accumulate, void* stream);
+
+/* ---- convolution: nn.Conv2d inside _ConvBlock (modules.py:15,32), mid_conv (models.py:750,1096), out_conv
+ *      (models.py:1099) and their autograd (aten::convolution_backward) ----------------------------------- */
+/* nn.Conv2d weight [Co,Ci,R,S] fp32 -> wf bf16 [Co_pad][R*S][Ci_pad] (forward operand) and
+ * wd bf16 [Ci_pad][R*S][Co_pad], taps rotated 180 degrees (data-gradient operand).  Either may be NULL. */
+int fv_weight_prep(const float* w, void* wf, void* wd, int Co, int Ci, int R, int S, int Co_pad, int Ci_pad, void* stream);
+/* y = conv(x, wf) + bias (+ residual); stride 1, odd square filter, pad = (R-1)/2.  tcgen05 implicit GEMM.
+ * x: NHWC bf16 [N,H,W,Ci] (Ci = 16, 32 or a multiple of 64); wf: [Co_pad][R*S][Ci]; bias: fp32 [Co] or NULL;
+ * residual: NHWC bf16 [N,H,W,Co_pad] or NULL (the `x +` of ResBlock2D, modules.py:124-125);
+ * y: NHWC bf16 / NHWC fp32 with Co_pad channels, or NCHW fp32 [N,Co,H,W], per out_mode.
+ * The data gradient is the same call with x := dY, wf := wd, (Ci, Co, Co_pad) := (Co_pad, Ci, Ci_pad). */
+int fv_conv2d(const void* x, const void* wf, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W,
+              int Ci, int Co, int Co_pad, int R, int S, int pad, void* stream);
+/* dw_acc[Co_pad][R*S][Ci] (fp32, caller-zeroed) += sum_pixels x[pixel + tap] * dy[pixel]; tcgen05, split over pixels. */
+int fv_conv2d_wgrad(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
+                    void* stream);
+/* dw_acc -> nn.Conv2d layout grad [Co,Ci,R,S] fp32 (accumulate != 0 adds, as autograd does into .grad). */
+int fv_wgrad_finish(const float* dw_acc, float* grad, int Co, int Ci, int R, int S, int Ci_pad, int accumulate, void* stream);
+/* sums[C] (caller-zeroed) += per-channel sums over P rows of an NHWC bf16 tensor: the bias gradient. */
+int fv_colsum(const void* y, float* sums, long long P, int C, void* stream);
+
+/* ---- nn.SyncBatchNorm (modules.py:19) + ReLU/LeakyReLU (modules.py:27,29) + AvgPool2d (modules.py:62,70) /
+ *      nn.Upsample (modules.py:81,89) ---------------------------------------------------------------------- */
+/* sums[0..C) += sum y, sums[C..2C) += sum y^2 over P = N*H*W rows (caller-zeroed; all-reduced across ranks by the
+ * host before fv_bn_finalize -- the stat exchange of torch/nn/modules/_functions.py:39-83). */
+int fv_bn_stats(const void* y, int dtype, float* sums, long long P, int C, void* stream);
+/* stat[4][C] = mean, invstd (biased variance, eps), scale = gamma*invstd, shift = beta - mean*scale; updates
+ * running_mean / running_var (unbiased variance, momentum) when given. */
+int fv_bn_finalize(const float* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, float momentum, float eps, float* stat, int C, void* stream);
+/* eval mode: the same stat block from the running statistics. */
+int fv_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                      float* stat, int C, void* stream);
+/* out = [pool2x2 | up2x]( act(scale*y + shift) ).  H, W are the input sizes.  out: NHWC (bf16/fp32) or NCHW fp32. */
+int fv_bn_act_fwd(const void* y, int in_dtype, const float* stat, void* out, int out_dtype, int nchw_out, int N, int H, int W,
+                  int C, int mode, int act, void* stream);
+/* backward pass 1: sums[0..C) += sum dz, sums[C..2C) += sum dz*xhat (caller-zeroed; all-reduced across ranks like
+ * torch/nn/modules/_functions.py:144-159).  g is the gradient of the block output (pooled / up-sampled domain). */
+int fv_bn_act_bwd_reduce(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat, float* sums,
+                         int N, int H, int W, int C, int mode, int act, void* stream);
+/* dgamma/dbeta (+)= local sums; coef[2][C] = global sums / count. */
+int fv_bn_bwd_finalize(const float* sums_local, const float* sums_global, double count, float* dgamma, float* dbeta, float* coef,
+                       int C, int accumulate, void* stream);
+/* backward pass 2: dy = scale*(dz - coef0 - xhat*coef1) (+ add), bf16 NHWC: the conv-output gradient. */
+int fv_bn_act_bwd_apply(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat, const float* coef,
+                        const void* add, void* dy, int N, int H, int W, int C, int mode, int act, void* stream);
+
+/* ---- re-parameterisation (models.py:559-561) fused with KLDivergenceLoss (losses.py:385-393) ------------- */
+/* mu/logstd: fp32 rows of Dz values, row_stride apart; z[N,Dz] = mu + exp(logstd)*eps (NULL eps => z = mu; NULL z =>
+ * KL only); kl_rows[N] (caller-zeroed, may be NULL) += sum_d(-0.5 - logstd + 0.5 mu^2 + 0.5 exp(2 logstd)). */
+int fv_reparam_kl_fwd(const float* mu, const float* logstd, long long row_stride, const float* eps, float* z, float* kl_rows,
+                      int N, int Dz, void* stream);
+/* dmu = dz + k*mu (+dmu_ext); dlogstd = dz*eps*exp(logstd) + k*(exp(2 logstd)-1) (+dls_ext); k = kscale * (*kscale_ptr). */
+int fv_reparam_kl_bwd(const float* mu, const float* logstd, long long row_stride, const float* eps, const float* dz,
+                      const float* dmu_ext, const float* dls_ext, float kscale, const float* kscale_ptr, float* dmu, float* dls,
+                      long long out_stride, int N, int Dz, void* stream);
+
+/* ---- ReconLoss / nn.MSELoss (losses.py:396-403), nn.L1Loss (losses.py:128), torch.sigmoid (models.py:1110) - */
+/* NCHW fp32 logits/target [N,C,H,W]; loss_sum (caller-zeroed) += sum l(pred - target); optional outputs: pred
+ * (= sigmoid(logits) when use_sigmoid), gradient w.r.t. logits times gscale as fp32 NCHW and/or bf16 NHWC [N,H,W,Cp]. */
+int fv_recon_loss(const float* logits, const float* target, float* pred_out, float* grad_f32, void* grad_nhwc, float* loss_sum,
+                  int N, int C, int H, int W, int Cp, int l1, int use_sigmoid, float gscale, void* stream);
+/* same-shape flat fp32 tensors a, b of E elements: loss_sum += sum l(a-b); grad (optional) = gscale * dl/da. */
+int fv_recon_loss_flat(const float* a, const float* b, float* grad, float* loss_sum, long long E, int l1, float gscale, void* stream);
+/* out = in * scale * (*scale_ptr) (scale_ptr may be NULL); n elements, n % 8 == 0. */
+int fv_scale(const void* in, void* out, int dtype, long long n, const float* scale_ptr, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif

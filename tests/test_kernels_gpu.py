@@ -1,0 +1,252 @@
+"""Kernel-level parity on a real B200: every C-ABI entry point against a plain PyTorch fp32 reference of the same
+op on identical (bf16-representable) inputs.  bf16 outputs: rtol 2e-2 (north_star); fp32 reductions: rtol 1e-4."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from face_vae_b200 import ops as _ops
+    from face_vae_b200 import _lib
+    _lib.call("fv_device_ok")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _ops
+
+
+def _rand(shape, seed, lo=-1.0, hi=1.0, bf16_exact=True):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    t = (torch.rand(shape, generator=g) * (hi - lo) + lo)
+    if bf16_exact:
+        t = t.bfloat16().float()
+    return t.cuda()
+
+
+def _report(name, got, ref, rtol, atol_frac):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    tol = rtol * ref.abs() + atol_frac * ref.abs().max()
+    bad = err > tol
+    msg = f"{name}: max_err {err.max().item():.4e} ref_absmax {ref.abs().max().item():.4e} bad {bad.float().mean().item():.4f}"
+    if bad.any():
+        idx = bad.nonzero()[:6]
+        for i in idx:
+            t = tuple(i.tolist())
+            msg += f"\n   at {t}: got {got[t].item():.5f} ref {ref[t].item():.5f}"
+        if got.dim() == 4:   # NHWC error maps
+            msg += "\n   bad frac by c//16: " + str([round(v, 3) for v in bad.float().mean(dim=(0, 1, 2)).view(-1, min(16, bad.shape[3])).mean(1).tolist()])
+            msg += "\n   bad frac by w%8 : " + str([round(bad[:, :, i::8].float().mean().item(), 3) for i in range(min(8, bad.shape[2]))])
+            msg += "\n   bad frac by h   : " + str([round(v, 3) for v in bad.float().mean(dim=(0, 2, 3)).tolist()][:16])
+            msg += "\n   bad frac by n   : " + str([round(v, 3) for v in bad.float().mean(dim=(1, 2, 3)).tolist()][:16])
+    print(msg)
+    assert not bad.any(), msg
+
+
+def _conv_case(ops, n, h, w, ci, co, k, bias=True, residual=False, out_mode=0, seed=0):
+    from face_vae_b200.ops import pad_channels, OUT_NCHW_F32
+    x = _rand((n, ci, h, w), seed)
+    wt = _rand((co, ci, k, k), seed + 1, -1.0 / math.sqrt(ci * k * k), 1.0 / math.sqrt(ci * k * k), bf16_exact=True)
+    b = _rand((co,), seed + 2, bf16_exact=False) if bias else None
+    ref = F.conv2d(x, wt, b, padding=(k - 1) // 2)
+    x_nhwc = ops.nchw_to_nhwc(x)
+    assert x_nhwc.shape[-1] == pad_channels(ci)
+    wf, _ = ops.weight_prep(wt, True, False)
+    res = None
+    if residual:
+        r = _rand((n, co, h, w), seed + 3)
+        res = ops.nchw_to_nhwc(r, pad_channels(co))
+        ref = ref + r
+    y = ops.conv2d(x_nhwc, wf, b, co, k, residual=res, out_mode=out_mode)
+    torch.cuda.synchronize()
+    if out_mode == OUT_NCHW_F32:
+        got = y.permute(0, 2, 3, 1)
+    else:
+        got = y[..., :co]
+        if y.shape[-1] > co:
+            assert float(y[..., co:].float().abs().max()) == 0.0, "padded output channels must be zero"
+    _report(f"conv n{n} {h}x{w} ci{ci} co{co} k{k} res{int(residual)} out{out_mode}", got, ref.permute(0, 2, 3, 1),
+            2e-2 if out_mode == 0 else 1e-4, 4e-3 if out_mode == 0 else 1e-5)
+
+
+@pytest.mark.parametrize("ci,co", [(64, 64), (16, 16), (32, 64), (128, 128), (256, 32), (64, 256)])
+def test_conv_1x1(ops, ci, co):
+    _conv_case(ops, 2, 16, 64, ci, co, 1)
+
+
+@pytest.mark.parametrize("h,w,n", [(8, 128, 2), (16, 64, 2), (16, 16, 4), (8, 8, 3), (4, 4, 5), (4, 256, 1), (32, 32, 2)])
+def test_conv_3x3_tilings(ops, h, w, n):
+    _conv_case(ops, n, h, w, 64, 64, 3)
+
+
+@pytest.mark.parametrize("ci,co", [(32, 64), (64, 128), (128, 256), (256, 32), (256, 256), (64, 32), (16, 256)])
+def test_conv_3x3_channels(ops, ci, co):
+    _conv_case(ops, 2, 16, 32, ci, co, 3)
+
+
+def test_conv_7x7_rgb_out_nchw(ops):
+    from face_vae_b200.ops import OUT_NCHW_F32
+    _conv_case(ops, 2, 32, 32, 32, 3, 7, out_mode=OUT_NCHW_F32)
+
+
+def test_conv_rgb_in_1x1(ops):
+    _conv_case(ops, 2, 16, 64, 3, 32, 1)
+
+
+def test_conv_residual_and_f32_out(ops):
+    from face_vae_b200.ops import OUT_NHWC_F32
+    _conv_case(ops, 2, 16, 16, 256, 256, 3, residual=True)
+    _conv_case(ops, 2, 16, 16, 64, 32, 3, out_mode=OUT_NHWC_F32)
+
+
+def test_conv_many_tiles_persistent(ops):
+    # more tiles than SMs: exercises the persistent loop, TMEM double buffering and mbarrier phase wrap-around
+    _conv_case(ops, 8, 64, 128, 32, 64, 3)
+
+
+@pytest.mark.parametrize("ci,co,k,h,w,n", [(64, 64, 3, 16, 64, 2), (32, 64, 3, 16, 64, 2), (16, 32, 3, 8, 8, 4),
+                                           (128, 256, 3, 16, 16, 2), (256, 256, 3, 16, 16, 2), (64, 32, 3, 8, 128, 2),
+                                           (16, 256, 1, 16, 16, 2), (32, 3, 7, 32, 32, 2), (64, 128, 3, 4, 4, 6),
+                                           (3, 32, 1, 16, 64, 2)])
+def test_conv_dgrad_wgrad(ops, ci, co, k, h, w, n):
+    from face_vae_b200.ops import pad_channels
+    x = _rand((n, ci, h, w), 10).requires_grad_(True)
+    wt = _rand((co, ci, k, k), 11, -0.2, 0.2).requires_grad_(True)
+    dy = _rand((n, co, h, w), 12)
+    y = F.conv2d(x, wt, None, padding=(k - 1) // 2)
+    y.backward(dy)
+    x_nhwc = ops.nchw_to_nhwc(x.detach())
+    dy_nhwc = ops.nchw_to_nhwc(dy, pad_channels(co))
+    _, wd = ops.weight_prep(wt.detach(), False, True)
+    dx = ops.conv2d(dy_nhwc, wd, None, pad_channels(ci), k)          # data gradient = conv with the rotated filter
+    acc = ops.conv2d_wgrad(x_nhwc, dy_nhwc, k)
+    dw = ops.wgrad_finish(acc, co, ci, k)
+    torch.cuda.synchronize()
+    _report(f"dgrad ci{ci} co{co} k{k} {h}x{w}", dx[..., :ci], x.grad.permute(0, 2, 3, 1), 2e-2, 4e-3)
+    err = (dw - wt.grad).abs().max().item()
+    scale = wt.grad.abs().max().item()
+    print(f"wgrad ci{ci} co{co} k{k} {h}x{w}: max_err {err:.4e} absmax {scale:.4e}")
+    assert err <= 2e-3 * scale + 1e-5, f"wgrad mismatch {err} vs {scale}"
+
+
+def test_layout_roundtrip(ops):
+    x = _rand((3, 5, 8, 16), 1, bf16_exact=True)
+    y = ops.nchw_to_nhwc(x, 16)
+    assert torch.equal(y[..., :5].float(), x.permute(0, 2, 3, 1))
+    assert float(y[..., 5:].float().abs().max()) == 0
+    back = ops.nhwc_to_nchw(y, 5)
+    assert torch.equal(back, x)
+    back2 = ops.nhwc_to_nchw(y, 5, out=back.clone(), accumulate=True)
+    assert torch.equal(back2, 2 * x)
+    yf = ops.nchw_to_nhwc(x, 8, dtype=torch.float32)
+    assert torch.equal(yf[..., :5], x.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("c,dtype", [(32, torch.bfloat16), (64, torch.bfloat16), (256, torch.bfloat16), (16, torch.float32), (32, torch.float32)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_bn_act_fwd_bwd(ops, c, dtype, mode):
+    from face_vae_b200.ops import ACT_RELU
+    n, h, w = 3, 8, 16
+    y = _rand((n, c, h, w), 3, -2, 2).to(dtype).float().requires_grad_(True)
+    gamma = _rand((c,), 4, 0.5, 1.5, False).requires_grad_(True)
+    beta = _rand((c,), 5, -0.3, 0.3, False).requires_grad_(True)
+    rm, rv = torch.zeros(c).cuda(), torch.ones(c).cuda()
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    a = F.relu(F.batch_norm(y, rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5))
+    if mode == 1:
+        a = F.avg_pool2d(a, 2)
+    elif mode == 2:
+        a = F.interpolate(a, scale_factor=2, mode="nearest")
+    g = _rand(tuple(a.shape), 6)
+    a.backward(g)
+    y_nhwc = y.detach().permute(0, 2, 3, 1).contiguous().to(dtype)
+    sums = ops.bn_stats(y_nhwc)
+    stat = ops.bn_finalize(sums, n * h * w, gamma.detach(), beta.detach(), rm, rv)
+    out = ops.bn_act_fwd(y_nhwc, stat, mode, ACT_RELU, torch.bfloat16)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(rm, rm_ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rv, rv_ref, rtol=1e-4, atol=1e-5)
+    _report(f"bn_act_fwd c{c} mode{mode}", out, a.detach().permute(0, 2, 3, 1), 1e-2, 4e-3)
+    g_nhwc = g.permute(0, 2, 3, 1).contiguous().bfloat16()
+    s = ops.bn_act_bwd_reduce(y_nhwc, g_nhwc, stat, mode, ACT_RELU)
+    dgamma, dbeta, coef = ops.bn_bwd_finalize(s, s, n * h * w, c)
+    dy = ops.bn_act_bwd_apply(y_nhwc, g_nhwc, stat, coef, mode, ACT_RELU)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dgamma, gamma.grad, rtol=2e-3, atol=2e-3 * gamma.grad.abs().max().item())
+    torch.testing.assert_close(dbeta, beta.grad, rtol=2e-3, atol=2e-3 * beta.grad.abs().max().item())
+    _report(f"bn_act_bwd c{c} mode{mode}", dy, y.grad.permute(0, 2, 3, 1), 2e-2, 4e-3)
+    # NCHW fp32 output / gradient variants used at the VAE bottleneck
+    if mode != 2:
+        out_nchw = ops.bn_act_fwd(y_nhwc, stat, mode, ACT_RELU, torch.float32, nchw_out=True)
+        torch.testing.assert_close(out_nchw, a.detach(), rtol=1e-4, atol=1e-4)
+        s2 = ops.bn_act_bwd_reduce(y_nhwc, g.contiguous(), stat, mode, ACT_RELU, g_nchw=True)
+        _, _, coef2 = ops.bn_bwd_finalize(s2, s2, n * h * w, c)
+        dy2 = ops.bn_act_bwd_apply(y_nhwc, g.contiguous(), stat, coef2, mode, ACT_RELU, g_nchw=True)
+        _report(f"bn_act_bwd nchw-g c{c} mode{mode}", dy2, y.grad.permute(0, 2, 3, 1), 2e-2, 4e-3)
+
+
+def test_bn_eval_and_colsum(ops):
+    from face_vae_b200.ops import ACT_LEAKY
+    c = 64
+    y = _rand((2, c, 8, 8), 7, -2, 2)
+    gamma, beta = _rand((c,), 8, 0.5, 1.5, False), _rand((c,), 9, -0.3, 0.3, False)
+    rm, rv = _rand((c,), 10, -0.5, 0.5, False), _rand((c,), 11, 0.5, 2.0, False)
+    ref = F.leaky_relu(F.batch_norm(y, rm, rv, gamma, beta, False, 0.1, 1e-5), 0.2)
+    stat = ops.bn_eval_affine(gamma, beta, rm, rv)
+    y_nhwc = y.permute(0, 2, 3, 1).contiguous().bfloat16()
+    out = ops.bn_act_fwd(y_nhwc, stat, 0, ACT_LEAKY, torch.float32)
+    _report("bn eval leaky", out, ref.permute(0, 2, 3, 1), 1e-4, 1e-5)
+    cs = ops.colsum(y_nhwc)
+    torch.testing.assert_close(cs, y.sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
+
+
+def test_reparam_kl(ops):
+    n, dz = 5, 4096
+    h = _rand((n, 2 * dz), 20, 0.0, 2.0, False)
+    eps = torch.randn((n, dz), generator=torch.Generator().manual_seed(21)).cuda()
+    mu, ls = h[:, :dz], h[:, dz:]
+    z, kl = ops.reparam_kl_fwd(mu, ls, eps)
+    z_ref = mu + torch.exp(ls) * eps
+    kl_ref = (-0.5 - ls + 0.5 * mu ** 2 + 0.5 * torch.exp(2 * ls)).double().sum(dim=1)
+    torch.testing.assert_close(z, z_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(kl.double(), kl_ref, rtol=1e-4, atol=0)            # KL: rtol 1e-4 (north_star)
+    # known answers of SURVEY.md section 4
+    i = torch.arange(1024, dtype=torch.float32).view(4, 256).cuda()
+    mu2, ls2 = torch.sin(0.01 * i), 0.5 * torch.cos(0.013 * i)
+    _, kl2 = ops.reparam_kl_fwd(mu2, ls2, None, want_z=False)
+    assert abs(kl2.sum().item() / 1024 - 0.37965357) < 1e-4 * 0.37965357
+    # backward: dz given, KL weight kscale
+    dzt = _rand((n, dz), 22, bf16_exact=False)
+    dh = ops.reparam_kl_bwd(mu, ls, eps, dzt, None, None, 0.2 / (n * dz), None)
+    torch.testing.assert_close(dh[:, :dz], dzt + 0.2 / (n * dz) * mu, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(dh[:, dz:], dzt * eps * torch.exp(ls) + 0.2 / (n * dz) * (torch.exp(2 * ls) - 1), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("l1", [False, True])
+def test_recon_loss(ops, l1):
+    n, c, h, w = 3, 3, 16, 32
+    logits = _rand((n, c, h, w), 30, -3, 3, False).requires_grad_(True)
+    target = _rand((n, c, h, w), 31, 0, 1, False)
+    pred = torch.sigmoid(logits)
+    ref = (pred - target).abs().sum() if l1 else ((pred - target) ** 2).sum()
+    ref.backward()
+    loss, p, gf, gn = ops.recon_loss(logits.detach(), target, l1=l1, use_sigmoid=True, gscale=1.0, want_grad_f32=True)
+    torch.testing.assert_close(loss[0], ref.detach(), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(p, pred.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(gf, logits.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(gn[..., :c].float(), logits.grad.permute(0, 2, 3, 1), rtol=1e-2, atol=1e-3)
+    assert float(gn[..., c:].float().abs().max()) == 0
+    a, b = _rand((7, 333), 32, bf16_exact=False), _rand((7, 333), 33, bf16_exact=False)
+    loss2, g2 = ops.recon_loss_flat(a, b, l1=l1, gscale=0.5)
+    ref2 = (a - b).abs().sum() if l1 else ((a - b) ** 2).sum()
+    torch.testing.assert_close(loss2[0], ref2, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(g2, 0.5 * (torch.sign(a - b) if l1 else 2 * (a - b)), rtol=1e-5, atol=1e-6)
+    s = torch.tensor([3.0]).cuda()
+    sc = ops.scale(g2.view(-1)[:2328].contiguous(), s, 2.0)
+    torch.testing.assert_close(sc, g2.view(-1)[:2328] * 6.0, rtol=1e-6, atol=1e-7)
