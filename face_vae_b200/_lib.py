@@ -81,8 +81,39 @@ def last_error() -> str:
     return load().fv_last_error().decode("utf-8", "replace")
 
 
-def call(name: str, *args):
+launch_count = 0          # every int-returning entry point launches exactly one kernel
+_profile = None
+
+
+def profile_start() -> None:
+    """Record a CUDA-event pair around every subsequent call (bench.py's per-kernel timing pass)."""
+    global _profile
+    _profile = []
+
+
+def profile_stop():
+    """-> list of (entry point, milliseconds, meta) for the calls since profile_start(); synchronises."""
+    global _profile
+    import torch
+    torch.cuda.synchronize()
+    out = [(n, e0.elapsed_time(e1), meta) for n, e0, e1, meta in (_profile or [])]
+    _profile = None
+    return out
+
+
+def call(name: str, *args, meta=None):
     """Call an int-returning entry point; non-zero -> FaceVaeError with the library's message."""
-    rc = getattr(load(), name)(*args)
+    global launch_count
+    fn = getattr(load(), name)
+    if _profile is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _profile.append((name, e0, e1, meta))
+    else:
+        rc = fn(*args)
+    launch_count += 1
     if rc != 0:
         raise FaceVaeError(f"{name} failed ({rc}): {last_error()}")

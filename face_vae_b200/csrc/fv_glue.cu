@@ -297,6 +297,10 @@ __device__ __forceinline__ void load_g(const TG* g, int g_nchw, int mode, int n,
 #pragma unroll
                 for (int k = 0; k < 8; ++k) r[k] += f[k];
             }
+    } else if (g_nchw) {
+        const float* gf = reinterpret_cast<const float*>(g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = __ldg(gf + (((long long)n * C + grp * 8 + k) * H + h) * W + w);
     } else {
         V8<TG>::load(g + (((long long)n * H + h) * W + w) * C + grp * 8, r);
     }

@@ -1,0 +1,331 @@
+"""autograd.Functions that wire the C-ABI kernels into PyTorch's autograd.
+
+Internal activation format: explicit NHWC bf16 tensors ``[N, H, W, Cp]`` (Cp = ops.pad_channels(C)); fp32 NCHW only at
+the edges of the path (input frames, the VAE latent, the reconstruction).  Batch-norm statistics are exchanged across
+data-parallel ranks here (sum all-reduce of ``[sum, sum_sq]`` forward and ``[sum_dz, sum_dz_xhat]`` backward), which
+is what ``nn.SyncBatchNorm`` does under DDP in the reference (modules.py:19, logger.py:55).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .ops import (ACT_LEAKY, ACT_NONE, ACT_RELU, MODE_NONE, MODE_POOL, MODE_UP, OUT_NCHW_F32, OUT_NHWC_BF16,
+                  OUT_NHWC_F32, pad_channels)
+
+_SYNC_BN = True
+
+
+def set_sync_bn(enabled: bool) -> None:
+    """Cross-rank batch statistics on/off (on by default whenever a process group with world_size > 1 exists)."""
+    global _SYNC_BN
+    _SYNC_BN = bool(enabled)
+
+
+def _world() -> int:
+    if _SYNC_BN and dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+def _allreduce_sum(t: torch.Tensor) -> torch.Tensor:
+    """Sum across ranks; returns a new tensor (the local sums are still needed for dgamma / dbeta)."""
+    if _world() == 1:
+        return t
+    g = t.clone()
+    dist.all_reduce(g, op=dist.ReduceOp.SUM)
+    return g
+
+
+# ---------------------------------------------------------------------------------------------------- layout
+class ToNHWC(torch.autograd.Function):
+    """NCHW fp32 -> NHWC bf16 (channels zero-padded to pad_channels(C))."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.c = x.shape[1]
+        return ops.nchw_to_nhwc(x.contiguous().float())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.nhwc_to_nchw(g.contiguous(), ctx.c)
+
+
+class ToNCHW(torch.autograd.Function):
+    """NHWC (bf16 / fp32) -> NCHW fp32, first ``c`` channels."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.cp = x.shape[3]
+        return ops.nhwc_to_nchw(x, c)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.nchw_to_nhwc(g.contiguous().float(), ctx.cp), None
+
+
+class Upsample2x(torch.autograd.Function):
+    """nn.Upsample(scale_factor=2, nearest) on NHWC bf16 (reference modules.py:81); backward sums the 2x2 replicas."""
+
+    @staticmethod
+    def forward(ctx, x):
+        c = x.shape[3]
+        stat = torch.zeros((4, c), device=x.device, dtype=torch.float32)
+        stat[1:3].fill_(1.0)                     # mean 0, invstd 1, scale 1, shift 0: identity affine
+        ctx.save_for_backward(x, stat)
+        return ops.bn_act_fwd(x, stat, MODE_UP, ACT_NONE, torch.bfloat16)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, stat = ctx.saved_tensors
+        coef = torch.zeros((2, x.shape[3]), device=x.device, dtype=torch.float32)
+        return ops.bn_act_bwd_apply(x, g.contiguous(), stat, coef, MODE_UP, ACT_NONE)
+
+
+# ---------------------------------------------------------------------------------------------------- conv blocks
+def _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, eps):
+    """Returns the [4, C] stat block (mean, invstd, scale, shift) and the global element count per channel."""
+    n, h, w, c = y.shape
+    if not training:
+        return ops.bn_eval_affine(gamma, beta, running_mean, running_var, eps), n * h * w
+    sums = _allreduce_sum(ops.bn_stats(y))
+    count = n * h * w * _world()
+    return ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps), count
+
+
+class ConvBNAct(torch.autograd.Function):
+    """Pattern "CNA" of _ConvBlock (reference modules.py:8-42) plus the block's own pooling (DownBlock2D,
+    modules.py:59-70) or the *next* block's up-sampling (UpBlock2D, modules.py:78-89) folded into the norm+act pass.
+
+    x: NHWC bf16 [N,H,W,Ci_pad].  Returns NHWC (bf16 / fp32) or NCHW fp32 per ``out_nchw_f32``.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, ksize, post_mode, act, training,
+                out_nchw_f32, momentum, eps):
+        co, ci = weight.shape[0], weight.shape[1]
+        wf, _ = ops.weight_prep(weight, True, False)
+        y = ops.conv2d(x, wf, bias, co, ksize, None, OUT_NHWC_BF16, (ci, co))
+        stat, count = _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, eps)
+        out = ops.bn_act_fwd(y, stat, post_mode, act, torch.float32 if out_nchw_f32 else torch.bfloat16, out_nchw_f32)
+        ctx.save_for_backward(x, y, stat, weight)
+        ctx.cfg = (ksize, post_mode, act, training, out_nchw_f32, count, co, ci)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, stat, weight = ctx.saved_tensors
+        ksize, post_mode, act, training, out_nchw_f32, count, co, ci = ctx.cfg
+        g = g.contiguous()
+        c = y.shape[3]
+        if training:
+            s_local = ops.bn_act_bwd_reduce(y, g, stat, post_mode, act, out_nchw_f32)
+            s_global = _allreduce_sum(s_local)
+        else:   # running statistics are constants: dy = scale * dz, no coupling terms
+            s_local = ops.bn_act_bwd_reduce(y, g, stat, post_mode, act, out_nchw_f32)
+            s_global = torch.zeros_like(s_local)
+        dgamma, dbeta, coef = ops.bn_bwd_finalize(s_local, s_global, count, c)
+        dy = ops.bn_act_bwd_apply(y, g, stat, coef, post_mode, act, None, out_nchw_f32)
+        acc = ops.conv2d_wgrad(x, dy, ksize, (ci, co))
+        dw = ops.wgrad_finish(acc, co, ci, ksize)
+        db = None
+        if ctx.has_bias:
+            # a bias in front of a (training-mode) batch norm has zero gradient analytically; eval mode: real sum
+            db = torch.zeros((co,), device=x.device, dtype=torch.float32) if training else ops.colsum(dy)[:co].clone()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wd = ops.weight_prep(weight, False, True)
+            dx = ops.conv2d(dy, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
+        return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None, None
+
+
+class BNActConv(torch.autograd.Function):
+    """Pattern "NAC" of _ConvBlock as used by ResBlock2D (reference modules.py:116-130): norm + act on the block
+    input, then the conv; ``residual`` (NHWC bf16) is added in the conv epilogue (the ``x +`` of modules.py:125)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, gamma, beta, running_mean, running_var, ksize, act, training, momentum, eps):
+        co, ci = weight.shape[0], weight.shape[1]
+        stat, count = _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps)
+        a = ops.bn_act_fwd(x, stat, MODE_NONE, act, torch.bfloat16)
+        wf, _ = ops.weight_prep(weight, True, False)
+        y = ops.conv2d(a, wf, bias, co, ksize, residual, OUT_NHWC_BF16, (ci, co))
+        ctx.save_for_backward(x, a, stat, weight)
+        ctx.cfg = (ksize, act, training, count, co, ci)
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, a, stat, weight = ctx.saved_tensors
+        ksize, act, training, count, co, ci = ctx.cfg
+        g = g.contiguous()
+        db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
+        acc = ops.conv2d_wgrad(a, g, ksize, (ci, co))
+        dw = ops.wgrad_finish(acc, co, ci, ksize)
+        _, wd = ops.weight_prep(weight, False, True)
+        da = ops.conv2d(g, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
+        c = x.shape[3]
+        s_local = ops.bn_act_bwd_reduce(x, da, stat, MODE_NONE, act)
+        s_global = _allreduce_sum(s_local) if training else torch.zeros_like(s_local)
+        dgamma, dbeta, coef = ops.bn_bwd_finalize(s_local, s_global, count, c)
+        dx = ops.bn_act_bwd_apply(x, da, stat, coef, MODE_NONE, act) if ctx.needs_input_grad[0] else None
+        dres = g if ctx.has_res else None
+        return dx, dres, dw, db, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+class ConvOnly(torch.autograd.Function):
+    """Plain nn.Conv2d (mid_conv, reference models.py:750 / 1096; out_conv, models.py:1099)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, ksize, out_mode):
+        co, ci = weight.shape[0], weight.shape[1]
+        wf, _ = ops.weight_prep(weight, True, False)
+        y = ops.conv2d(x, wf, bias, co, ksize, None, out_mode, (ci, co))
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (ksize, out_mode, co, ci)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        ksize, out_mode, co, ci = ctx.cfg
+        if out_mode == OUT_NCHW_F32:
+            g = ops.nchw_to_nhwc(g.contiguous().float(), pad_channels(co))
+        elif g.dtype != torch.bfloat16:
+            g = g.to(torch.bfloat16)
+        g = g.contiguous()
+        db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
+        acc = ops.conv2d_wgrad(x, g, ksize, (ci, co))
+        dw = ops.wgrad_finish(acc, co, ci, ksize)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wd = ops.weight_prep(weight, False, True)
+            dx = ops.conv2d(g, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
+        return dx, dw, db, None, None
+
+
+# ---------------------------------------------------------------------------------------------------- VAE bottleneck / losses
+class Reparam(torch.autograd.Function):
+    """z = mu + exp(logstd) * eps (reference models.py:561).  mu/logstd: fp32 [N, Dz] row views."""
+
+    @staticmethod
+    def forward(ctx, mu, logstd, eps):
+        z, _ = ops.reparam_kl_fwd(mu, logstd, eps, True, False)
+        ctx.save_for_backward(mu, logstd, eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        mu, logstd, eps = ctx.saved_tensors
+        dh = ops.reparam_kl_bwd(mu, logstd, eps, dz.contiguous(), None, None, 0.0, None)
+        d = mu.shape[1]
+        return dh[:, :d], dh[:, d:], None
+
+
+class KLDivergence(torch.autograd.Function):
+    """KLDivergenceLoss (reference losses.py:385-393): mean_n mean_d(-0.5 - ls + 0.5 mu^2 + 0.5 exp(2 ls))."""
+
+    @staticmethod
+    def forward(ctx, mu, logstd):
+        _, rows = ops.reparam_kl_fwd(mu, logstd, None, False, True)
+        ctx.save_for_backward(mu, logstd)
+        n, d = mu.shape
+        return rows.sum() / (n * d)
+
+    @staticmethod
+    def backward(ctx, gk):
+        mu, logstd = ctx.saved_tensors
+        n, d = mu.shape
+        dh = ops.reparam_kl_bwd(mu, logstd, None, None, None, None, 1.0 / (n * d), gk.reshape(1).float().contiguous())
+        return dh[:, :d], dh[:, d:]
+
+
+class ReparamKL(torch.autograd.Function):
+    """Fused bottleneck of the training path: h [N, 2*Dz] fp32 (mu | logstd) and eps -> (z [N, Dz], KL mean)."""
+
+    @staticmethod
+    def forward(ctx, h, eps):
+        n, d2 = h.shape
+        d = d2 // 2
+        mu, ls = h[:, :d], h[:, d:]
+        z, rows = ops.reparam_kl_fwd(mu, ls, eps, True, True)
+        ctx.save_for_backward(h, eps)
+        return z, rows.sum() / (n * d)
+
+    @staticmethod
+    def backward(ctx, dz, gk):
+        h, eps = ctx.saved_tensors
+        n, d2 = h.shape
+        d = d2 // 2
+        dh = ops.reparam_kl_bwd(h[:, :d], h[:, d:], eps, dz.contiguous(), None, None, 1.0 / (n * d),
+                                gk.reshape(1).float().contiguous())
+        return dh, None
+
+
+class ReconLossFlat(torch.autograd.Function):
+    """nn.MSELoss / nn.L1Loss mean over two same-shape fp32 tensors (reference losses.py:396-403, 128); the gradient
+    is produced by the same pass that computes the loss."""
+
+    @staticmethod
+    def forward(ctx, a, b, l1):
+        a, b = a.contiguous().float(), b.contiguous().float()
+        e = a.numel()
+        loss, grad = ops.recon_loss_flat(a, b, l1, 1.0 / e, True)
+        ctx.save_for_backward(grad)
+        ctx.shape = a.shape
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, gl):
+        (grad,) = ctx.saved_tensors
+        n = grad.numel()
+        flat = grad.view(-1)
+        n8 = n // 8 * 8
+        gptr = gl.reshape(1).float().contiguous()
+        out = torch.empty_like(flat)
+        if n8:
+            ops.scale(flat[:n8], gptr, 1.0, out[:n8])
+        if n8 < n:
+            out[n8:] = flat[n8:] * gptr
+        out = out.view(ctx.shape)
+        return (out if ctx.needs_input_grad[0] else None), (-out if ctx.needs_input_grad[1] else None), None
+
+
+class ConvSigmoidRecon(torch.autograd.Function):
+    """out_conv (7x7, reference models.py:1099) -> sigmoid (models.py:1110) -> ReconLoss against the target frame
+    (losses.py:396-403, trainer.py:314), fused: the loss kernel also emits d(loss)/d(logits) as the NHWC bf16 tensor the
+    conv's dgrad / wgrad consume.  Returns (x_hat NCHW fp32, mean loss)."""
+
+    @staticmethod
+    def forward(ctx, d, weight, bias, target, l1):
+        co, ci, ksize = weight.shape[0], weight.shape[1], weight.shape[2]
+        wf, _ = ops.weight_prep(weight, True, False)
+        logits = ops.conv2d(d, wf, bias, co, ksize, None, OUT_NCHW_F32, (ci, co))
+        e = logits.numel()
+        loss, pred, _, gn = ops.recon_loss(logits, target.contiguous().float(), l1, True, 1.0 / e, True, False, True)
+        ctx.save_for_backward(d, weight, gn)
+        ctx.cfg = (ksize, co, ci)
+        ctx.has_bias = bias is not None
+        ctx.mark_non_differentiable(pred)
+        return pred, loss[0] / e
+
+    @staticmethod
+    def backward(ctx, _gpred, gl):
+        d, weight, gn = ctx.saved_tensors
+        ksize, co, ci = ctx.cfg
+        g = ops.scale(gn, gl.reshape(1).float().contiguous(), 1.0)
+        db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
+        acc = ops.conv2d_wgrad(d, g, ksize, (ci, co))
+        dw = ops.wgrad_finish(acc, co, ci, ksize)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wd = ops.weight_prep(weight, False, True)
+            dx = ops.conv2d(g, wd, None, d.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
+        return dx, dw, db, None, None

@@ -1,0 +1,123 @@
+"""VAE bottleneck and the anchor model of the hot path.
+
+``flatten_vae_nl`` keeps the reference's class name, forward signature and return convention (reference
+models.py:525-570).  ``FaceVAE`` is the composition SURVEY.md section 8 defines from reference patterns (the reference
+has no single image->image VAE class): EFE_conv5.down encoder (models.py:731,749) -> flatten_vae_nl bottleneck
+(models.py:559-561) -> mid_conv (models.py:750/1096) -> ResBlock2D x n_res (models.py:1097) -> UpBlock2D stack
+(models.py:1098, 462) -> 7x7 out_conv + sigmoid (models.py:1099,1110).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import functional as Fn
+from . import ops
+from .modules import (Conv2d, DownBlock2D, ResBlock2D, SameBlock2D, UpBlock2D, as_nchw, as_nhwc, to_float_nchw)
+from .ops import MODE_NONE, MODE_UP, OUT_NCHW_F32, OUT_NHWC_BF16
+
+
+class flatten_vae_nl(nn.Module):
+    """Parameter-free VAE bottleneck (reference models.py:525-570): mu / logstd are the first / last half of the
+    channels, flattened; z = mu + exp(logstd) * randn.  The network predicts log(sigma), not log(sigma^2).
+
+    ``forward(x, train_vae)`` -> ``(mu, logstd, x_hat)`` when train_vae else ``(None, None, x_hat)`` with x_hat == mu
+    exactly.  The reference hard-codes ``view(b, 16, 4, 4)`` (models.py:564); here x_hat keeps x's spatial size.
+    ``eps`` may be injected (tests, reproducibility); otherwise it is drawn with torch.randn as in the reference.
+    """
+
+    def forward(self, x, train_vae, eps: Optional[torch.Tensor] = None):
+        x = to_float_nchw(x)
+        b, c2, h, w = x.shape
+        zc = c2 // 2
+        flat = x.reshape(b, -1)
+        d = zc * h * w
+        mu, logstd = flat[:, :d], flat[:, d:]
+        if not train_vae:
+            return None, None, mu.reshape(b, zc, h, w)
+        if eps is None:
+            eps = torch.randn(b, d, device=x.device)
+        z = Fn.Reparam.apply(mu, logstd, eps.reshape(b, d).contiguous().float())
+        return mu, logstd, z.view(b, zc, h, w)
+
+
+class FaceVAE(nn.Module):
+    """The anchor "face-vae" (SURVEY.md section 8).  Sub-module names give the oracle's state_dict keys."""
+
+    def __init__(self, down_seq: Sequence[int] = (3, 32, 64, 128, 256, 32), up_seq: Sequence[int] = (256, 256, 128, 64, 32),
+                 n_res: int = 2, use_weight_norm: bool = False):
+        super().__init__()
+        d, u = list(down_seq), list(up_seq)
+        self.enc = nn.Sequential(*[SameBlock2D(d[i], d[i + 1], use_weight_norm) if i == 0 else
+                                   DownBlock2D(d[i], d[i + 1], use_weight_norm) for i in range(len(d) - 1)])
+        self.vae = flatten_vae_nl()
+        self.zc = d[-1] // 2
+        self.mid_conv = Conv2d(self.zc, u[0], 1, 1, 0)
+        self.res = nn.Sequential(*[ResBlock2D(u[0], use_weight_norm) for _ in range(n_res)])
+        self.up = nn.Sequential(*[UpBlock2D(u[i], u[i + 1], use_weight_norm) for i in range(len(u) - 1)])
+        self.out_conv = Conv2d(u[-1], 3, 7, 1, 3)
+        self.n_down = len(d) - 2
+
+    def latent_dim(self, h: int, w: int) -> int:
+        f = 2 ** self.n_down
+        return self.zc * (h // f) * (w // f)
+
+    # -- pieces ---------------------------------------------------------------------------------------------
+    def encode_nchw(self, x: torch.Tensor) -> torch.Tensor:
+        """frames [N,3,H,W] fp32 -> h [N, 2*zc, H/f, W/f] fp32 NCHW (mu | logstd kept in fp32 for the KL term)."""
+        t = as_nhwc(x)
+        last = len(self.enc) - 1
+        for i, blk in enumerate(self.enc):
+            if i == 0:
+                t = blk.forward_nhwc(t)
+            else:
+                t = blk.forward_nhwc(t, out_nchw_f32=(i == last))
+        return t
+
+    def decode_nhwc(self, z_nchw: torch.Tensor) -> torch.Tensor:
+        """z [N,zc,h,w] fp32 -> decoder features NHWC bf16 in front of out_conv."""
+        t = Fn.ToNHWC.apply(z_nchw)
+        t = Fn.ConvOnly.apply(t, self.mid_conv.weight, self.mid_conv.bias, 1, OUT_NHWC_BF16)
+        for blk in self.res:
+            t = blk.forward_nhwc(t)
+        t = Fn.Upsample2x.apply(t)
+        n_up = len(self.up)
+        for i, blk in enumerate(self.up):
+            # this block's norm+act pass also writes the 2x up-sampled tensor the next UpBlock2D starts with
+            t = blk.forward_nhwc(t, pre_upsampled=True, post_mode=MODE_UP if i + 1 < n_up else MODE_NONE)
+        return t
+
+    # -- public ---------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, train_vae: bool = True, eps: Optional[torch.Tensor] = None):
+        """-> (mu, logstd, x_hat): mu/logstd [N,Dz] fp32 (None when not train_vae), x_hat [N,3,H,W] fp32 in (0,1)."""
+        h = self.encode_nchw(x)
+        mu, logstd, z = self.vae(h, train_vae, eps)
+        d = self.decode_nhwc(z)
+        logits = Fn.ConvOnly.apply(d, self.out_conv.weight, self.out_conv.bias, 7, OUT_NCHW_F32)
+        return mu, logstd, torch.sigmoid(logits)
+
+    def forward_loss(self, x: torch.Tensor, eps: Optional[torch.Tensor] = None, l1: bool = False):
+        """Fused training path -> dict(K, R, x_hat, mu, logstd): un-weighted KL and reconstruction terms with the
+        re-parameterisation+KL and out_conv+sigmoid+loss(+gradient) stages each running as one fused kernel."""
+        h = self.encode_nchw(x)
+        b, c2, hh, ww = h.shape
+        dz = self.zc * hh * ww
+        if eps is None:
+            eps = torch.randn(b, dz, device=x.device)
+        flat = h.view(b, 2 * dz)
+        z, kl = Fn.ReparamKL.apply(flat, eps.reshape(b, dz).contiguous().float())
+        d = self.decode_nhwc(z.view(b, self.zc, hh, ww))
+        x_hat, rec = Fn.ConvSigmoidRecon.apply(d, self.out_conv.weight, self.out_conv.bias, x, l1)
+        return {"K": kl, "R": rec, "x_hat": x_hat, "mu": flat[:, :dz], "logstd": flat[:, dz:]}
+
+
+def face_vae_256(**kw) -> FaceVAE:
+    """BASELINE.json configs[1..2]: 256x256 anchor."""
+    return FaceVAE(**kw)
+
+
+def face_vae_512(**kw) -> FaceVAE:
+    """BASELINE.json configs[3]: deeper encoder/decoder, larger latent."""
+    return FaceVAE(down_seq=(3, 32, 64, 128, 256, 512, 64), up_seq=(512, 512, 256, 128, 64, 32), **kw)

@@ -1,0 +1,220 @@
+"""Drop-in 2-D blocks with the reference's class names, constructor signatures and state_dict keys
+(reference modules.py:8-135; SURVEY.md 3.4 for the key layout), backed by the sm_100a kernels.
+
+Tensors cross the module boundary as logical NCHW: fp32 contiguous frames/latents are converted once by a CUDA
+kernel; between blocks the tensors stay bf16 channels-last (a zero-copy view of the internal NHWC buffer), which is
+what the blocks hand to each other.  Only 2-D blocks with ``activation_type="batch"`` and ``use_weight_norm=False``
+are in scope; anything else raises.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from . import functional as Fn
+from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, MODE_NONE, MODE_POOL, MODE_UP, OUT_NHWC_BF16, pad_channels
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+# ---------------------------------------------------------------------------------------------------- tensor plumbing
+def as_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW tensor -> internal NHWC bf16 [N,H,W,pad_channels(C)] (zero-copy when it already is one)."""
+    if x.dim() != 4:
+        raise ValueError(f"expected a 4-d NCHW tensor, got {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("face_vae_b200 has no CPU path: move the input to a CUDA device")
+    c = x.shape[1]
+    if x.dtype == torch.bfloat16 and c == pad_channels(c):
+        v = x.permute(0, 2, 3, 1)
+        if v.is_contiguous():
+            return v
+    return Fn.ToNHWC.apply(x)
+
+
+def as_nchw(y: torch.Tensor, c: int) -> torch.Tensor:
+    """Internal NHWC -> logical NCHW view (bf16, channels-last memory)."""
+    v = y.permute(0, 3, 1, 2)
+    return v if c == y.shape[3] else v[:, :c]
+
+
+def to_float_nchw(x: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW (any layout/dtype produced by these blocks) -> contiguous NCHW fp32 via the layout kernel."""
+    if x.dtype == torch.float32 and x.is_contiguous():
+        return x
+    return Fn.ToNCHW.apply(as_nhwc(x), x.shape[1])
+
+
+# ---------------------------------------------------------------------------------------------------- parameter holders
+class _BatchNormParams(nn.Module):
+    """Parameter/buffer holder with nn.SyncBatchNorm's state_dict keys (weight, bias, running_mean, running_var,
+    num_batches_tracked)."""
+
+    def __init__(self, c: int):
+        super().__init__()
+        self.num_features = c
+        self.eps = BN_EPS
+        self.momentum = BN_MOMENTUM
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+
+class _Conv2dParams(nn.Module):
+    """Parameter holder with nn.Conv2d's keys and default initialisation (kaiming-uniform a=sqrt(5), bias +-1/sqrt(fan_in))."""
+
+    def __init__(self, ci: int, co: int, k: int, stride: int, padding: int):
+        super().__init__()
+        if stride != 1 or padding != (k - 1) // 2 or k % 2 == 0:
+            raise NotImplementedError("only stride-1 'same' convolutions with odd kernels are on the hot path "
+                                      "(SURVEY.md section 8); strided Conv2dELR is listed under 8f")
+        self.in_channels, self.out_channels, self.kernel_size = ci, co, k
+        self.weight = nn.Parameter(torch.empty(co, ci, k, k))
+        self.bias = nn.Parameter(torch.empty(co))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        bound = 1.0 / math.sqrt(ci * k * k)
+        nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x):                      # plain conv on a logical NCHW tensor
+        y = Fn.ConvOnly.apply(as_nhwc(x), self.weight, self.bias, self.kernel_size, OUT_NHWC_BF16)
+        return as_nchw(y, self.out_channels)
+
+
+class _Act(nn.Module):
+    def __init__(self, code):
+        super().__init__()
+        self.code = code
+
+
+class Conv2d(_Conv2dParams):
+    """nn.Conv2d stand-in for the un-normalised convs of the path (mid_conv, reference models.py:750,1096)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding)
+
+
+# ---------------------------------------------------------------------------------------------------- blocks
+class ConvBlock2D(nn.Module):
+    """_ConvBlock / ConvBlock2D (reference modules.py:8-49): ``pattern`` in {"CNA", "NAC", "CN"}."""
+
+    def __init__(self, pattern, in_channels, out_channels, kernel_size, stride, padding, use_weight_norm,
+                 activation_type="batch", nonlinearity_type="relu"):
+        super().__init__()
+        if use_weight_norm:
+            raise NotImplementedError("spectral-norm blocks are outside the hot path (SURVEY.md 2.1 row 1, 8f rank 2)")
+        if activation_type != "batch":
+            raise NotImplementedError("only activation_type='batch' (SyncBatchNorm) is on the hot path")
+        if pattern not in ("CNA", "NAC", "CN"):
+            raise NotImplementedError(f"pattern {pattern!r}: the reference uses CNA, NAC and CN only")
+        norm_channels = out_channels if pattern.find("C") < pattern.find("N") else in_channels
+        if norm_channels != pad_channels(norm_channels):
+            raise NotImplementedError("normalised channel counts must be 16, 32 or a multiple of 64")
+        self.pattern = pattern
+        self.act = ACT_NONE if "A" not in pattern else (ACT_RELU if nonlinearity_type == "relu" else ACT_LEAKY)
+        mods = {"C": _Conv2dParams(in_channels, out_channels, kernel_size, stride, padding),
+                "N": _BatchNormParams(norm_channels), "A": _Act(self.act)}
+        self.layers = nn.Sequential(*[mods[ch] for ch in pattern])      # same indices as the reference => same keys
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+
+    @property
+    def conv(self) -> _Conv2dParams:
+        return self.layers[self.pattern.index("C")]
+
+    @property
+    def norm(self) -> _BatchNormParams:
+        return self.layers[self.pattern.index("N")]
+
+    def forward_nhwc(self, x, post_mode=MODE_NONE, residual=None, out_nchw_f32=False):
+        conv, bn = self.conv, self.norm
+        if self.training:
+            bn.num_batches_tracked += 1
+        if self.pattern in ("CNA", "CN"):
+            return Fn.ConvBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                      self.kernel_size, post_mode, self.act, self.training, out_nchw_f32, bn.momentum, bn.eps)
+        if post_mode != MODE_NONE or out_nchw_f32:
+            raise NotImplementedError("NAC blocks have no fused pool/upsample")
+        return Fn.BNActConv.apply(x, residual, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                  self.kernel_size, self.act, self.training, bn.momentum, bn.eps)
+
+    def forward(self, x):
+        return as_nchw(self.forward_nhwc(as_nhwc(x)), self.out_channels)
+
+
+class _Pool(nn.Module):
+    """Marker for nn.AvgPool2d((2, 2)) -- executed inside the block's fused norm+act pass."""
+
+
+class _Up(nn.Module):
+    """Marker for nn.Upsample(scale_factor=(2, 2)) (nearest)."""
+
+
+class DownBlock2D(nn.Module):
+    """reference modules.py:59-70: CNA 3x3 s1 p1 -> AvgPool2d(2); the pool is fused into the norm+ReLU kernel."""
+
+    def __init__(self, in_channels, out_channels, use_weight_norm):
+        super().__init__()
+        self.layers = nn.Sequential(ConvBlock2D("CNA", in_channels, out_channels, 3, 1, 1, use_weight_norm), _Pool())
+        self.out_channels = out_channels
+
+    def forward_nhwc(self, x, out_nchw_f32=False):
+        return self.layers[0].forward_nhwc(x, MODE_POOL, None, out_nchw_f32)
+
+    def forward(self, x):
+        return as_nchw(self.forward_nhwc(as_nhwc(x)), self.out_channels)
+
+
+class UpBlock2D(nn.Module):
+    """reference modules.py:78-89: Upsample(x2, nearest) -> CNA 3x3 s1 p1.  ``forward_nhwc(pre_upsampled=True)`` lets
+    a producer that already wrote the 2x-replicated tensor (fused into its own norm+act pass) skip the copy."""
+
+    def __init__(self, in_channels, out_channels, use_weight_norm):
+        super().__init__()
+        self.layers = nn.Sequential(_Up(), ConvBlock2D("CNA", in_channels, out_channels, 3, 1, 1, use_weight_norm))
+        self.out_channels = out_channels
+
+    def forward_nhwc(self, x, pre_upsampled=False, post_mode=MODE_NONE):
+        if not pre_upsampled:
+            x = Fn.Upsample2x.apply(x)
+        return self.layers[1].forward_nhwc(x, post_mode)
+
+    def forward(self, x):
+        return as_nchw(self.forward_nhwc(as_nhwc(x)), self.out_channels)
+
+
+class SameBlock2D(nn.Module):
+    """reference modules.py:97-108: CNA 1x1."""
+
+    def __init__(self, in_channels, out_channels, use_weight_norm):
+        super().__init__()
+        self.layers = ConvBlock2D("CNA", in_channels, out_channels, 1, 1, 0, use_weight_norm)
+        self.out_channels = out_channels
+
+    def forward_nhwc(self, x, post_mode=MODE_NONE):
+        return self.layers.forward_nhwc(x, post_mode)
+
+    def forward(self, x):
+        return as_nchw(self.forward_nhwc(as_nhwc(x)), self.out_channels)
+
+
+class ResBlock2D(nn.Module):
+    """reference modules.py:116-130: x + NAC(NAC(x)); the residual add lives in the second conv's epilogue."""
+
+    def __init__(self, in_channels, use_weight_norm):
+        super().__init__()
+        self.layers = nn.Sequential(
+            ConvBlock2D("NAC", in_channels, in_channels, 3, 1, 1, use_weight_norm),
+            ConvBlock2D("NAC", in_channels, in_channels, 3, 1, 1, use_weight_norm),
+        )
+        self.out_channels = in_channels
+
+    def forward_nhwc(self, x):
+        h = self.layers[0].forward_nhwc(x)
+        return self.layers[1].forward_nhwc(h, residual=x)
+
+    def forward(self, x):
+        return as_nchw(self.forward_nhwc(as_nhwc(x)), self.out_channels)

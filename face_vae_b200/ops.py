@@ -77,6 +77,17 @@ def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None, out: Optional[torch.T
 
 
 # ------------------------------------------------------------------------------------------------ convolution
+def _conv_meta(n, h, w, ci, cop, k, real_dims):
+    """Profiling record: executed (padded) FLOPs and algorithmic FLOPs (real channel counts) of one launch."""
+    rci, rco = real_dims if real_dims is not None else (ci, cop)
+    return {"shape": (n, h, w, ci, cop, k), "flops_exec": 2.0 * n * h * w * ci * cop * k * k,
+            "flops": 2.0 * n * h * w * rci * rco * k * k}
+
+
+def _bytes(*tensors) -> dict:
+    return {"bytes": float(sum(t.numel() * t.element_size() for t in tensors if t is not None))}
+
+
 def weight_prep(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = True
                 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """nn.Conv2d weight [Co,Ci,R,S] fp32 -> (wf [Co_pad,R*S,Ci_pad], wd [Ci_pad,R*S,Co_pad]) bf16."""
@@ -90,7 +101,7 @@ def weight_prep(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = True
 
 
 def conv2d(x: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], co: int, ksize: int,
-           residual: Optional[torch.Tensor] = None, out_mode: int = OUT_NHWC_BF16) -> torch.Tensor:
+           residual: Optional[torch.Tensor] = None, out_mode: int = OUT_NHWC_BF16, real_dims=None) -> torch.Tensor:
     """x NHWC bf16 [N,H,W,Ci]; wf [Co_pad, k*k, Ci] bf16 -> y (NHWC [N,H,W,Co_pad] or NCHW fp32 [N,co,H,W])."""
     _chk(x, "x", torch.bfloat16)
     _chk(wf, "wf", torch.bfloat16)
@@ -110,11 +121,11 @@ def conv2d(x: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], co: 
         if tuple(residual.shape) != (n, h, w, cop):
             raise _lib.FaceVaeError("conv2d: residual shape mismatch")
     call("fv_conv2d", x.data_ptr(), wf.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), out_mode, n, h, w, ci, co,
-         cop, ksize, ksize, (ksize - 1) // 2, _stream())
+         cop, ksize, ksize, (ksize - 1) // 2, _stream(), meta=_conv_meta(n, h, w, ci, cop, ksize, real_dims))
     return y
 
 
-def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int) -> torch.Tensor:
+def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, real_dims=None) -> torch.Tensor:
     """x NHWC bf16 [N,H,W,Ci], dy NHWC bf16 [N,H,W,Co_pad] -> dw_acc fp32 [Co_pad, k*k, Ci]."""
     _chk(x, "x", torch.bfloat16)
     _chk(dy, "dy", torch.bfloat16)
@@ -124,7 +135,7 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int) -> torch.Tensor:
         raise _lib.FaceVaeError("conv2d_wgrad: x / dy shape mismatch")
     acc = torch.zeros((cop, ksize * ksize, ci), device=x.device, dtype=torch.float32)
     call("fv_conv2d_wgrad", x.data_ptr(), dy.data_ptr(), acc.data_ptr(), n, h, w, ci, cop, ksize, ksize,
-         (ksize - 1) // 2, _stream())
+         (ksize - 1) // 2, _stream(), meta=_conv_meta(n, h, w, ci, cop, ksize, real_dims))
     return acc
 
 
@@ -150,7 +161,7 @@ def bn_stats(y: torch.Tensor) -> torch.Tensor:
     _chk(y, "y")
     c = y.shape[-1]
     sums = torch.zeros((2 * c,), device=y.device, dtype=torch.float32)
-    call("fv_bn_stats", y.data_ptr(), _dt(y), sums.data_ptr(), y.numel() // c, c, _stream())
+    call("fv_bn_stats", y.data_ptr(), _dt(y), sums.data_ptr(), y.numel() // c, c, _stream(), meta=_bytes(y))
     return sums
 
 
@@ -180,7 +191,7 @@ def bn_act_fwd(y: torch.Tensor, stat: torch.Tensor, mode: int = MODE_NONE, act: 
     shape = (n, c, ho, wo) if nchw_out else (n, ho, wo, c)
     out = torch.empty(shape, device=y.device, dtype=out_dtype)
     call("fv_bn_act_fwd", y.data_ptr(), _dt(y), stat.data_ptr(), out.data_ptr(), _dt(out), int(nchw_out), n, h, w, c,
-         mode, act, _stream())
+         mode, act, _stream(), meta=_bytes(y, out))
     return out
 
 
@@ -191,7 +202,7 @@ def bn_act_bwd_reduce(y: torch.Tensor, g: torch.Tensor, stat: torch.Tensor, mode
     n, h, w, c = y.shape
     sums = torch.zeros((2 * c,), device=y.device, dtype=torch.float32)
     call("fv_bn_act_bwd_reduce", y.data_ptr(), _dt(y), g.data_ptr(), _dt(g), int(g_nchw), stat.data_ptr(),
-         sums.data_ptr(), n, h, w, c, mode, act, _stream())
+         sums.data_ptr(), n, h, w, c, mode, act, _stream(), meta=_bytes(y, g))
     return sums
 
 
@@ -214,7 +225,7 @@ def bn_act_bwd_apply(y: torch.Tensor, g: torch.Tensor, stat: torch.Tensor, coef:
     if add is not None:
         _chk(add, "add", torch.bfloat16)
     call("fv_bn_act_bwd_apply", y.data_ptr(), _dt(y), g.data_ptr(), _dt(g), int(g_nchw), stat.data_ptr(),
-         coef.data_ptr(), _ptr(add), dy.data_ptr(), n, h, w, c, mode, act, _stream())
+         coef.data_ptr(), _ptr(add), dy.data_ptr(), n, h, w, c, mode, act, _stream(), meta=_bytes(y, g, add, dy))
     return dy
 
 
@@ -230,7 +241,7 @@ def reparam_kl_fwd(mu: torch.Tensor, logstd: torch.Tensor, eps: Optional[torch.T
     if eps is not None:
         _chk(eps, "eps", torch.float32)
     call("fv_reparam_kl_fwd", mu.data_ptr(), logstd.data_ptr(), mu.stride(0), _ptr(eps), _ptr(z), _ptr(kl), n, dz,
-         _stream())
+         _stream(), meta=_bytes(mu, logstd, eps, z))
     return z, kl
 
 
@@ -258,7 +269,7 @@ def recon_loss(logits: torch.Tensor, target: torch.Tensor, l1: bool = False, use
     gf = torch.empty_like(logits) if want_grad_f32 else None
     gn = torch.empty((n, h, w, cp), device=logits.device, dtype=torch.bfloat16) if want_grad_nhwc else None
     call("fv_recon_loss", logits.data_ptr(), target.data_ptr(), _ptr(pred), _ptr(gf), _ptr(gn), loss.data_ptr(), n, c, h,
-         w, cp, int(l1), int(use_sigmoid), float(gscale), _stream())
+         w, cp, int(l1), int(use_sigmoid), float(gscale), _stream(), meta=_bytes(logits, target, pred, gf, gn))
     return loss, pred, gf, gn
 
 

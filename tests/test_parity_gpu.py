@@ -1,0 +1,216 @@
+"""Parity of the CUDA path (through the nn.Module facade and the C ABI) with the reference:
+ * against the committed golden fixtures produced by the unmodified reference classes (tests/golden/*.npz),
+ * against the CPU oracle on other seeded inputs / sizes,
+ * through size-independent properties at BASELINE.json's full size (batch 32 at 256x256).
+Tolerances (north_star): bf16 path rtol 2e-2 (with an absolute floor of a fraction of the tensor's max);
+KL term / fp32 kernels rtol 1e-4 (tested at kernel level in test_kernels_gpu.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import detgen
+from oracle import facevae_oracle as O
+from tests import goldenlib as G
+from tests.test_oracle_golden import block_io, block_params
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-2          # bf16 path (north_star)
+AFRAC = 2e-2         # absolute floor as a fraction of max |ref| of the tensor
+
+
+@pytest.fixture(scope="module")
+def fv():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import face_vae_b200.modules as M
+    import face_vae_b200.models as MO
+    import face_vae_b200.losses as L
+    import face_vae_b200.trainer as T
+    from face_vae_b200 import _lib
+    _lib.call("fv_device_ok")
+
+    class NS:
+        modules, models, losses, trainer = M, MO, L, T
+    return NS
+
+
+def _load(module, params):
+    sd = module.state_dict()
+    for k, v in params.items():
+        assert k in sd, k
+        sd[k] = v.clone()
+    module.load_state_dict(sd)
+    return module.cuda().train()
+
+
+BLOCK_CTORS = {
+    "down": lambda M: M.DownBlock2D(16, 32, False),
+    "up": lambda M: M.UpBlock2D(32, 16, False),
+    "same": lambda M: M.SameBlock2D(16, 32, False),
+    "same3": lambda M: M.SameBlock2D(3, 32, False),
+    "res": lambda M: M.ResBlock2D(32, False),
+    "convblock_leaky": lambda M: M.ConvBlock2D("CNA", 16, 16, 3, 1, 1, False, nonlinearity_type="leakyrelu"),
+}
+BLOCK_CI = {"down": 16, "up": 32, "same": 16, "same3": 3, "res": 32, "convblock_leaky": 16}
+
+
+@pytest.mark.parametrize("tag", sorted(BLOCK_CTORS))
+def test_block_matches_reference_golden(fv, tag):
+    g = G.load("blocks.npz")
+    blk = _load(BLOCK_CTORS[tag](fv.modules), block_params(g, tag))
+    x, gy = block_io(g, tag, BLOCK_CI[tag])
+    x = x.cuda().requires_grad_(True)
+    y = blk(x)
+    assert y.shape == tuple(g[f"{tag}/y/shape"]) or tuple(y.shape) == tuple(int(v) for v in g[f"{tag}/y/shape"])
+    (y.float() * gy.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    G.check(g, f"{tag}/y", y.float().contiguous(), RTOL, AFRAC)
+    G.check(g, f"{tag}/dx", x.grad, RTOL, AFRAC)
+    for k, p in blk.named_parameters():
+        G.check(g, f"{tag}/grad/{k}", p.grad, RTOL, AFRAC, zero_floor=2e-2)
+    for k, b in blk.named_buffers():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            G.check(g, f"{tag}/buf/{k}", b, 1e-2, 1e-2)
+
+
+def _anchor(fv, cfg, base):
+    m = fv.models.FaceVAE(cfg.down_seq, cfg.up_seq, cfg.n_res)
+    return _load(m, O.det_anchor_params(cfg, base))
+
+
+@pytest.mark.parametrize("fixture,n,base", [("anchor_n4_64.npz", 4, 0), ("anchor_n2_64_b1.npz", 2, 1)])
+def test_anchor_matches_reference_golden(fv, fixture, n, base):
+    """BASELINE.json configs[0]: batch 4 at 64x64 -- forward activations, losses, gradients, running stats."""
+    g = G.load(fixture)
+    cfg = O.CFG_256
+    m = _anchor(fv, cfg, base)
+    x, eps = O.det_inputs(n, 64, 64, cfg, base)
+    x, eps = x.cuda(), eps.cuda()
+    out = m.forward_loss(x, eps)
+    loss = cfg.w_kl * out["K"] + cfg.w_rec * out["R"]
+    loss.backward()
+    torch.cuda.synchronize()
+    for k in ("K", "R"):
+        ref = float(g[f"out/{k}"])
+        assert abs(out[k].item() - ref) <= RTOL * abs(ref), (k, out[k].item(), ref)
+    assert abs(loss.item() - float(g["out/loss"])) <= RTOL * abs(float(g["out/loss"]))
+    G.check(g, "out/mu", out["mu"], RTOL, AFRAC)
+    G.check(g, "out/logstd", out["logstd"], RTOL, AFRAC)
+    G.check(g, "out/x_hat", out["x_hat"], RTOL, AFRAC)
+    worst = {}
+    for k, p in m.named_parameters():
+        worst[k] = G.check(g, f"grad/{k}", p.grad, RTOL, AFRAC, zero_floor=1e-3)
+    for k, b in m.named_buffers():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            G.check(g, f"buf/{k}", b, 1e-2, 1e-2)
+    print("worst grad errs:", sorted(worst.items(), key=lambda kv: -kv[1])[:3])
+
+
+def test_anchor_modular_forward_matches_fused(fv):
+    """model(x, train_vae, eps) (separate Reparam / KLDivergenceLoss / ReconLoss modules, the reference's call
+    pattern trainer.py:312,314) gives the same numbers as the fused forward_loss path."""
+    cfg = O.CFG_256
+    m = _anchor(fv, cfg, 0)
+    x, eps = O.det_inputs(2, 64, 64, cfg, 3)
+    x, eps = x.cuda(), eps.cuda()
+    out = m.forward_loss(x, eps)
+    (cfg.w_kl * out["K"] + cfg.w_rec * out["R"]).backward()
+    g_fused = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad(set_to_none=True)
+    for b in m.buffers():            # same starting running stats do not matter for training-mode outputs
+        pass
+    mu, logstd, x_hat = m(x, True, eps)
+    K = fv.losses.KLDivergenceLoss()((mu, logstd))
+    R = fv.losses.ReconLoss()((x, x_hat))
+    (cfg.w_kl * K + cfg.w_rec * R).backward()
+    torch.cuda.synchronize()
+    assert abs(K.item() - out["K"].item()) <= 1e-5 * abs(K.item())
+    assert abs(R.item() - out["R"].item()) <= 1e-4 * abs(R.item())
+    torch.testing.assert_close(x_hat, out["x_hat"], rtol=1e-5, atol=1e-6)
+    for k, p in m.named_parameters():
+        ref = g_fused[k]
+        tol = 2e-2 * ref.abs().max().item() + 1e-6
+        assert (p.grad - ref).abs().max().item() <= tol, k
+    # eval / train_vae False: z == mu exactly, (None, None, x_hat)
+    m.eval()
+    mu0, ls0, xh0 = m(x, False)
+    assert mu0 is None and ls0 is None and xh0.shape == x.shape
+
+
+def test_anchor_matches_oracle_other_size(fv):
+    """Same comparison against the CPU oracle at 128x128, batch 2 (oracle finishes in seconds)."""
+    cfg = O.CFG_256
+    p = O.det_anchor_params(cfg, 5)
+    x, eps = O.det_inputs(2, 128, 128, cfg, 5)
+    ref_out, ref_grads, ref_bufs, _ = O.anchor_train_grads(p, x, eps, cfg)
+    m = _load(fv.models.FaceVAE(), p)
+    out = m.forward_loss(x.cuda(), eps.cuda())
+    (cfg.w_kl * out["K"] + cfg.w_rec * out["R"]).backward()
+    torch.cuda.synchronize()
+    assert abs(out["K"].item() - ref_out["K"].item()) <= RTOL * abs(ref_out["K"].item())
+    assert abs(out["R"].item() - ref_out["R"].item()) <= RTOL * abs(ref_out["R"].item())
+    for k, pr in m.named_parameters():
+        ref = ref_grads[k]
+        am = ref.abs().max().item()
+        if am < 1e-3:
+            assert pr.grad.abs().max().item() <= 1e-3
+            continue
+        err = (pr.grad.cpu() - ref).abs()
+        assert bool((err <= RTOL * ref.abs() + AFRAC * am).all()), (k, err.max().item(), am)
+
+
+def test_train_step_reduces_loss(fv):
+    torch.manual_seed(0)
+    m = fv.models.FaceVAE().cuda().train()
+    tr = fv.trainer.VAETrainer(m, lr=2e-3)
+    x, eps = O.det_inputs(4, 64, 64, O.CFG_256, 9)
+    x, eps = x.cuda(), eps.cuda()
+    vals = []
+    for _ in range(8):
+        losses, gen = tr.step(x, eps)
+        vals.append(sum(v.item() for v in losses.values()))
+    assert all(np.isfinite(vals)), vals
+    assert vals[-1] < vals[0], vals
+    assert gen.shape == x.shape and float(gen.min()) >= 0 and float(gen.max()) <= 1
+
+
+def test_full_size_properties(fv):
+    """Batch 32 at 256x256 (BASELINE.json configs[1]): properties that hold at any size.
+    (1) training-mode BN output has per-channel mean beta and variance gamma^2 before the ReLU -> checked through the
+        gradient identities sum(dy) = 0 and sum(dy * xhat) = 0 of the conv-output gradient;
+    (2) pooling / up-sampling shapes; (3) finite loss and gradients; (4) eval-mode determinism."""
+    from face_vae_b200 import ops
+    from face_vae_b200.ops import ACT_RELU, MODE_POOL
+    torch.manual_seed(1)
+    n, h, w, c = 32, 256, 256, 64
+    y = torch.randn((n, h, w, c), device="cuda").bfloat16()
+    gamma = (torch.rand(c, device="cuda") + 0.5)
+    beta = torch.rand(c, device="cuda") - 0.5
+    stat = ops.bn_finalize(ops.bn_stats(y), n * h * w, gamma, beta, None, None)
+    a = ops.bn_act_fwd(y, stat, MODE_POOL, ACT_RELU)
+    assert a.shape == (n, h // 2, w // 2, c)
+    g = torch.randn_like(a)
+    s = ops.bn_act_bwd_reduce(y, g, stat, MODE_POOL, ACT_RELU)
+    _, _, coef = ops.bn_bwd_finalize(s, s, n * h * w, c)
+    dy = ops.bn_act_bwd_apply(y, g, stat, coef, MODE_POOL, ACT_RELU)
+    cs = ops.colsum(dy)                                     # sum over 2M pixels of dy ~ 0 relative to sum |dy|
+    denom = dy.float().abs().sum(dim=(0, 1, 2))
+    assert float((cs.abs() / denom).max()) < 2e-3
+    xhat = (y.float() - stat[0]) * stat[1]
+    ortho = (dy.float() * xhat).sum(dim=(0, 1, 2)).abs() / (dy.float().abs() * xhat.abs()).sum(dim=(0, 1, 2))
+    assert float(ortho.max()) < 2e-3
+    # whole model at full size: finite, right shapes, deterministic in eval mode
+    m = fv.models.FaceVAE().cuda().train()
+    x = torch.rand((32, 3, 256, 256), device="cuda")
+    out = m.forward_loss(x)
+    (0.2 * out["K"] + 10 * out["R"]).backward()
+    assert out["x_hat"].shape == x.shape and out["mu"].shape == (32, 4096)
+    assert np.isfinite(out["K"].item()) and np.isfinite(out["R"].item())
+    for k, p in m.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+    m.eval()
+    with torch.no_grad():
+        a1 = m(x[:4], False)[2]
+        a2 = m(x[:4], False)[2]
+    assert torch.equal(a1, a2)
