@@ -40,7 +40,7 @@ import losses as ref_losses            # noqa: E402  (reference)
 from oracle import detgen              # noqa: E402
 from oracle import facevae_oracle as O  # noqa: E402
 
-SAMPLE = 257   # prime-ish count of strided samples per large tensor
+SAMPLE = 4099  # prime count of strided samples per large tensor
 
 
 def summarise(t: torch.Tensor, full_below: int = 4096):
@@ -57,6 +57,19 @@ def summarise(t: torch.Tensor, full_below: int = 4096):
 
 def sample_index(n: int) -> np.ndarray:
     return (np.arange(SAMPLE, dtype=np.int64) * (n // SAMPLE + 1) * 7919 + 13) % n
+
+
+def rel_l2(a: torch.Tensor, ref: torch.Tensor) -> float:
+    a, ref = a.detach().double().flatten(), ref.detach().double().flatten()
+    return float((a - ref).norm() / ref.norm().clamp_min(1e-30))
+
+
+def put_yard(store: dict, name: str, lowp: torch.Tensor, ref: torch.Tensor):
+    """Yardstick: how far the reference's OWN bf16-autocast run is from its fp32 run (relative L2 over the full tensor,
+    and max error / max |ref|).  The bf16 CUDA path is required to be no worse than this (tests/test_parity_gpu.py)."""
+    store[f"{name}/yard_l2"] = np.float64(rel_l2(lowp.float(), ref))
+    store[f"{name}/yard_max"] = np.float64(float((lowp.detach().double() - ref.detach().double()).abs().max() /
+                                                 ref.detach().double().abs().max().clamp_min(1e-30)))
 
 
 def put(store: dict, name: str, t: torch.Tensor, **kw):
@@ -154,6 +167,19 @@ def golden_anchor(n, hw, base, path):
     for k, v in m.named_buffers():
         if k.endswith("running_mean") or k.endswith("running_var"):
             put(store, f"buf/{k}", v)
+    # yardstick: the same reference modules under CPU bf16 autocast
+    m2 = RefAnchor(cfg).train()
+    load_det(m2, p)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        out2 = m2(x, eps, {})
+    out2["loss"].float().backward()
+    for k in ("mu", "logstd", "x_hat"):
+        put_yard(store, f"out/{k}", out2[k].reshape(out[k].shape if k == "x_hat" else (n, -1)), out[k].reshape(out[k].shape if k == "x_hat" else (n, -1)))
+    g1 = dict(m.named_parameters())
+    for k, v in m2.named_parameters():
+        put_yard(store, f"grad/{k}", v.grad, g1[k].grad)
+    store["yard/K"] = np.float64(out2["K"].item())
+    store["yard/R"] = np.float64(out2["R"].item())
     # one Adam step exactly as the reference configures it (logger.py:60)
     opt = torch.optim.Adam(m.parameters(), lr=5e-5, betas=(0.5, 0.999))
     opt.step()
@@ -169,6 +195,7 @@ def golden_blocks(path):
     n, hw = 2, 8
 
     def run(tag, blk, ci, upstream_seed):
+        import copy
         blk.train()
         sd = blk.state_dict()
         for k in list(sd):
@@ -189,6 +216,7 @@ def golden_blocks(path):
                 v = detgen.det_uniform(shape, seed, -0.2, 0.2)
             sd[k] = torch.from_numpy(v)
         blk.load_state_dict(sd)
+        blk2 = copy.deepcopy(blk)
         x = torch.from_numpy(detgen.det_uniform((n, ci, hw, hw), detgen.name_seed(tag + ".x"), -1.0, 1.0)).requires_grad_(True)
         y = blk(x)
         g = torch.from_numpy(detgen.det_uniform(tuple(y.shape), upstream_seed, -1.0, 1.0))
@@ -200,6 +228,16 @@ def golden_blocks(path):
         for k, v in blk.named_buffers():
             if not k.endswith("num_batches_tracked"):
                 put(store, f"{tag}/buf/{k}", v, full_below=1 << 20)
+        blk2.train()
+        x2 = x.detach().clone().requires_grad_(True)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            y2 = blk2(x2)
+        (y2.float() * g).sum().backward()
+        put_yard(store, f"{tag}/y", y2, y)
+        put_yard(store, f"{tag}/dx", x2.grad, x.grad)
+        g1 = dict(blk.named_parameters())
+        for k, v in blk2.named_parameters():
+            put_yard(store, f"{tag}/grad/{k}", v.grad, g1[k].grad)
 
     run("down", ref_modules.DownBlock2D(16, 32, False), 16, 11)
     run("up", ref_modules.UpBlock2D(32, 16, False), 32, 12)
