@@ -280,7 +280,7 @@ class ReconLossFlat(torch.autograd.Function):
         loss, grad = ops.recon_loss_flat(a, b, l1, 1.0 / e, True)
         ctx.save_for_backward(grad)
         ctx.shape = a.shape
-        return loss[0]
+        return loss[0] / e
 
     @staticmethod
     def backward(ctx, gl):

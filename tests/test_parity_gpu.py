@@ -66,19 +66,20 @@ def test_block_matches_reference_golden(fv, tag):
     (y.float() * gy.cuda()).sum().backward()
     torch.cuda.synchronize()
     G.check(g, f"{tag}/y", y.float().contiguous(), RTOL, AFRAC)            # forward: per element
+    scale = max(float(g[f"{tag}/grad/{k}/absmax"]) for k, _ in blk.named_parameters())
     _check_grad(g, f"{tag}/dx", x.grad, slack=2.0)
     for k, p in blk.named_parameters():
-        _check_grad(g, f"{tag}/grad/{k}", p.grad, slack=2.0)
+        _check_grad(g, f"{tag}/grad/{k}", p.grad, slack=2.0, zero_tol=2e-3 * scale)
     for k, b in blk.named_buffers():
         if k.endswith("running_mean") or k.endswith("running_var"):
             G.check(g, f"{tag}/buf/{k}", b, 1e-2, 1e-2)
 
 
-def _check_grad(g, name, t, slack=1.5, floor=1e-2):
+def _check_grad(g, name, t, slack=1.5, floor=1e-2, zero_tol=1e-3):
     """Gradients: relative L2 against the fp32 golden no worse than slack x the reference's own bf16-autocast deviation
     (+ floor); analytically-zero gradients (bias of a conv feeding a batch norm) must stay ~0."""
     if float(g[f"{name}/absmax"]) < 1e-5:
-        assert float(t.detach().abs().max()) <= 1e-3, name
+        assert float(t.detach().abs().max()) <= zero_tol, (name, float(t.detach().abs().max()))   # bf16 rounding noise only
         return 0.0, 0.0
     return G.check_vs_yardstick(g, name, t, slack, floor)
 
