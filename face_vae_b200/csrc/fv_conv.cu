@@ -7,15 +7,22 @@
 // rotated/transposed filter produced by fv_weight_prep) its data gradient.
 //
 // Structure (one persistent CTA per SM, 6 warps):
-//   warp 0  : TMA producer.  Per K block it loads one filter tap of the activation tile with a 4-D tensor map over
-//             (C, W, H, N): box = (KB channels, tw, th, tn) at (kc, w0 + s - pad, h0 + r - pad, n0).  Halo pixels
-//             outside the image are zero-filled by the TMA unit, so padding costs no memory and no branches.
-//             The matching [Co_pad x KB] slice of the K-major filter matrix comes through a 2-D map.
+//   warp 0  : TMA producer.  Activations come through a 4-D tensor map over (C, W, H, N); pixels outside the image
+//             are zero-filled by the TMA unit, so padding costs no memory and no branches.  Two load schedules:
+//               tap mode  : one box (KB ch, tw, th, tn) per filter tap, at (kc, w0 + s - pad, h0 + r - pad, n0);
+//               slab mode : (tiles that are one image-row segment, th == tn == 1) one box (KB ch, tw + S - 1) per
+//                           filter ROW; the S taps of that row are the same shared-memory slab read through UMMA
+//                           descriptors whose start address is shifted by s pixel rows -- S x fewer bytes through
+//                           L2 -> SMEM and S x fewer TMA transactions.
+//             The matching [Co_pad x KB] slices of the K-major filter matrix come through a 2-D map.
 //   warp 1  : one thread issues tcgen05.mma (UMMA 128 x Co_pad x 16, bf16 -> fp32) into one of two TMEM
 //             accumulator buffers and commits to the stage / accumulator mbarriers.
 //   warps 2-5: epilogue.  tcgen05.ld their TMEM lane quarter (row = pixel), add bias / residual, convert and store
 //             (NHWC bf16, NHWC fp32 or NCHW fp32); overlapped with the next tile's MMAs via the second buffer.
+// The single-thread producer / issuer loops carry no divisions: stage index and phase advance incrementally and the
+// UMMA descriptors are formed by 32-bit adds on a precomputed template.
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/facevae_b200.h"
 #include "fv_host.h"
@@ -26,8 +33,11 @@ namespace fv {
 struct ConvParams {
     int N, H, W, Ci, Co, Co_pad, R, S, pad;
     int tw, th, tn, tiles_w, tiles_h, tiles_n, num_tiles;
-    int KB, kc_blocks, stages, row_bytes;
-    int a_bytes, b_bytes, stage_stride;
+    int kc_blocks, stages, slab;
+    int a_off_b;          // byte offset of the filter slices inside a stage (activation region, rounded to 1 KB)
+    int b_slice_stride;   // placement stride of one [Co_pad x KB] filter slice (rounded to 1 KB)
+    int stage_stride;
+    int tx_bytes;         // bytes the TMA unit delivers per stage (what the full barrier is armed with)
     int out_mode, tmem_cols;
     const float* bias;
     const __nv_bfloat16* residual;
@@ -36,8 +46,25 @@ struct ConvParams {
 
 static constexpr int kConvThreads = 192;
 
+struct TileCoord {
+    int w0, h0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+    const int per_n = p.tiles_w * p.tiles_h;
+    const int tn_i = tile / per_n;
+    const int rem = tile - tn_i * per_n;
+    const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+    return {tw_i * p.tw, th_i * p.th, tn_i * p.tn};
+}
+
+template <int KB>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+    constexpr int ROW = KB * 2;                       // bytes per pixel row of a K block == swizzle span
+    constexpr int KSUB = KB / 16;                     // UMMA K steps per K block
+    constexpr uint32_t LAYOUT = ROW == 128 ? 2u : (ROW == 64 ? 4u : 6u);
+    constexpr uint32_t SBO = 8u * ROW;
+
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_stride);
@@ -45,6 +72,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint64_t* tfull = empty + p.stages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);      // [Co_pad]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -65,59 +93,68 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
         tmem_relinquish();
     }
+    for (int c = threadIdx.x; c < p.Co_pad; c += blockDim.x) bias_s[c] = (p.bias && c < p.Co) ? p.bias[c] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
-    const int k_iters = p.R * p.S * p.kc_blocks;
-    const int tiles_per_img_group = p.tiles_w * p.tiles_h;
+    const int s_loads = p.slab ? 1 : p.S;             // activation boxes per (r, kc) group
+    const int s_mmas = p.slab ? p.S : 1;              // filter taps consumed per stage
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t st = 0, ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int tn_i = tile / tiles_per_img_group;
-                const int rem = tile - tn_i * tiles_per_img_group;
-                const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
-                const int w0 = tw_i * p.tw, h0 = th_i * p.th, n0 = tn_i * p.tn;
-                for (int r = 0; r < p.R; ++r)
-                    for (int s = 0; s < p.S; ++s)
-                        for (int kc = 0; kc < p.kc_blocks; ++kc, ++it) {
-                            const uint32_t st = it % p.stages, ph = (it / p.stages) & 1;
+                const TileCoord t = decode_tile(p, tile);
+                for (int r = 0; r < p.R; ++r) {
+                    const int hh = t.h0 + r - p.pad;
+                    for (int sl = 0; sl < s_loads; ++sl) {
+                        const int ww = t.w0 + sl - p.pad;                 // slab mode: sl == 0, the box is S - 1 pixels wider
+                        const int wtap = (r * p.S + sl) * p.Ci;           // first filter column of this stage
+                        for (int kc = 0; kc < p.kc_blocks; ++kc) {
                             mbar_wait(&empty[st], ph ^ 1);
                             uint8_t* a_dst = smem + (size_t)st * p.stage_stride;
-                            uint8_t* b_dst = a_dst + p.a_bytes;
-                            mbar_arrive_expect_tx(&full[st], (uint32_t)(p.a_bytes + p.b_bytes));
-                            tma_load_4d(a_dst, &tmX, &full[st], kc * p.KB, w0 + s - p.pad, h0 + r - p.pad, n0);
-                            tma_load_2d(b_dst, &tmW, &full[st], (r * p.S + s) * p.Ci + kc * p.KB, 0);
+                            uint8_t* b_dst = a_dst + p.a_off_b;
+                            mbar_arrive_expect_tx(&full[st], (uint32_t)p.tx_bytes);
+                            tma_load_4d(a_dst, &tmX, &full[st], kc * KB, ww, hh, t.n0);
+                            for (int sm = 0; sm < s_mmas; ++sm)
+                                tma_load_2d(b_dst + sm * p.b_slice_stride, &tmW, &full[st], wtap + sm * p.Ci + kc * KB, 0);
+                            if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
                         }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, p.Co_pad, 0, 0);
-            const uint32_t layout = umma_layout_code(p.row_bytes);
-            const uint32_t sbo = 8u * p.row_bytes;
-            const int k_sub = p.KB / 16;
-            uint32_t it = 0, tcount = 0;
+            const uint64_t desc_hi = umma_smem_desc(0, 16, SBO, LAYOUT);   // template: all fields but the start address
+            const uint32_t smem_base = smem_u32(smem);
+            const int groups = p.R * s_loads * p.kc_blocks;
+            uint32_t st = 0, ph = 0, tcount = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
                 mbar_wait(&tempty[acc], aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co_pad;
-                for (int ki = 0; ki < k_iters; ++ki, ++it) {
-                    const uint32_t st = it % p.stages, ph = (it / p.stages) & 1;
+                uint32_t accumulate = 0;
+                for (int g = 0; g < groups; ++g) {
                     mbar_wait(&full[st], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)st * p.stage_stride);
-                    const uint32_t b_addr = a_addr + p.a_bytes;
-                    for (int j = 0; j < k_sub; ++j) {
-                        const uint64_t adesc = umma_smem_desc(a_addr + j * 32, 16, sbo, layout);
-                        const uint64_t bdesc = umma_smem_desc(b_addr + j * 32, 16, sbo, layout);
-                        tc_mma_f16(d_tmem, adesc, bdesc, idesc, (ki > 0 || j > 0) ? 1u : 0u);
+                    const uint32_t a_addr = smem_base + st * (uint32_t)p.stage_stride;
+                    const uint32_t b_addr = a_addr + (uint32_t)p.a_off_b;
+                    for (int sm = 0; sm < s_mmas; ++sm) {
+                        const uint32_t a_lo = (a_addr + (uint32_t)sm * ROW) >> 4;   // slab: tap sm == slab shifted by sm pixel rows
+                        const uint32_t b_lo = (b_addr + (uint32_t)sm * p.b_slice_stride) >> 4;
+#pragma unroll
+                        for (int j = 0; j < KSUB; ++j) {
+                            tc_mma_f16(d_tmem, desc_hi | (uint64_t)((a_lo + 2 * j) & 0x3FFFu),
+                                       desc_hi | (uint64_t)((b_lo + 2 * j) & 0x3FFFu), idesc, accumulate);
+                            accumulate = 1;
+                        }
                     }
                     tc_commit(&empty[st]);   // frees the smem stage once these MMAs have read it
+                    if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
                 }
                 tc_commit(&tfull[acc]);      // accumulator complete -> epilogue
             }
@@ -128,10 +165,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int w_l = row % p.tw, h_l = (row / p.tw) % p.th, n_l = row / (p.tw * p.th);
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-            const int tn_i = tile / tiles_per_img_group;
-            const int rem = tile - tn_i * tiles_per_img_group;
-            const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
-            const int w = tw_i * p.tw + w_l, h = th_i * p.th + h_l, n = tn_i * p.tn + n_l;
+            const TileCoord t = decode_tile(p, tile);
+            const int w = t.w0 + w_l, h = t.h0 + h_l, n = t.n0 + n_l;
             const bool valid = n < p.N;
             const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&tfull[acc], aph);
@@ -143,42 +178,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 tmem_ld16(taddr + c0, v);
                 tmem_ld_wait();
                 if (valid) {
-                float f[16];
+                    float f[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-                if (p.bias) {
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias_s[c0 + i];
+                    if (p.out_mode == FV_OUT_NCHW_F32) {
+                        float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < p.Co) f[i] += __ldg(p.bias + c0 + i);
-                }
-                if (p.out_mode == FV_OUT_NCHW_F32) {
-                    float* o = reinterpret_cast<float*>(p.out);
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < p.Co) o[(((size_t)n * p.Co + c0 + i) * p.H + h) * p.W + w] = f[i];
+                    } else {
+                        if (p.residual) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Co_pad + c0);
+                            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < p.Co) o[(((size_t)n * p.Co + c0 + i) * p.H + h) * p.W + w] = f[i];
-                } else {
-                    if (p.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Co_pad + c0);
-                        const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                            for (int i = 0; i < 8; ++i) {
+                                f[2 * i] += bf16_lo(rr[i]);
+                                f[2 * i + 1] += bf16_hi(rr[i]);
+                            }
+                        }
+                        if (p.out_mode == FV_OUT_NHWC_BF16) {
+                            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Co_pad + c0);
+                            o[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                              pack_bf16(f[6], f[7]));
+                            o[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
+                                              pack_bf16(f[14], f[15]));
+                        } else {
+                            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Co_pad + c0);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            f[2 * i] += bf16_lo(rr[i]);
-                            f[2 * i + 1] += bf16_hi(rr[i]);
+                            for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
                         }
                     }
-                    if (p.out_mode == FV_OUT_NHWC_BF16) {
-                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Co_pad + c0);
-                        o[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                                          pack_bf16(f[6], f[7]));
-                        o[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
-                                          pack_bf16(f[14], f[15]));
-                    } else {
-                        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Co_pad + c0);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                    }
-                }
                 }
             }
             tc_fence_before();
@@ -216,6 +246,23 @@ static int pick_tile(int N, int H, int W, int& tw, int& th, int& tn) {
     return 0;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int KB>
+static int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvParams& p, size_t smem, int grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FV_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    conv_igemm_kernel<KB><<<grid, kConvThreads, smem, stream>>>(tmX, tmW, p);
+    FV_LAUNCH_CHECK("conv_igemm_kernel");
+    return FV_OK;
+}
+
 }  // namespace fv
 
 extern "C" __attribute__((visibility("default"))) int fv_conv2d(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode,
@@ -237,17 +284,24 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d(const void* x, c
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: H=%d W=%d not tileable (W multiple of 128, or W,H powers of two)", H, W);
     p.tiles_w = W / p.tw; p.tiles_h = H / p.th; p.tiles_n = (N + p.tn - 1) / p.tn;
     p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    p.KB = Ci >= 64 ? 64 : Ci;
-    p.kc_blocks = Ci / p.KB;
-    p.row_bytes = p.KB * 2;
-    p.a_bytes = 128 * p.row_bytes;
-    p.b_bytes = Co_pad * p.row_bytes;
-    p.stage_stride = p.a_bytes + ((p.b_bytes + 1023) & ~1023);
-    const int k_iters = R * S * p.kc_blocks;
-    int stages = (200 * 1024) / p.stage_stride;
+    const int KB = Ci >= 64 ? 64 : Ci;
+    const int row_bytes = KB * 2;
+    p.kc_blocks = Ci / KB;
+    // slab schedule: one activation box per filter row, taps = shifted descriptor views (row-segment tiles only)
+    p.slab = (S > 1 && p.th == 1 && p.tn == 1) ? env_int("FV_CONV_SLAB", 1) : 0;
+    const int a_rows = p.slab ? p.tw + S - 1 : 128;
+    const int b_slices = p.slab ? S : 1;
+    p.a_off_b = (a_rows * row_bytes + 1023) & ~1023;
+    p.b_slice_stride = (Co_pad * row_bytes + 1023) & ~1023;
+    p.stage_stride = p.a_off_b + p.b_slice_stride * b_slices;
+    p.tx_bytes = a_rows * row_bytes + b_slices * Co_pad * row_bytes;
+    const int groups = R * (p.slab ? 1 : S) * p.kc_blocks;
+    int stages = (196 * 1024) / p.stage_stride;
     if (stages > 8) stages = 8;
-    if (stages > k_iters) stages = k_iters;
+    if (stages > groups) stages = groups;
     if (stages < 2) stages = 2;
+    if ((size_t)stages * p.stage_stride > 200 * 1024)
+        return fail(FV_ERR_INTERNAL, "fv_conv2d: stage of %d bytes does not fit twice in shared memory", p.stage_stride);
     p.stages = stages;
     p.out_mode = out_mode;
     int cols = 32;
@@ -261,23 +315,19 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d(const void* x, c
     {
         uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         uint64_t str[3] = {(uint64_t)Ci * 2, (uint64_t)W * Ci * 2, (uint64_t)H * W * Ci * 2};
-        uint32_t box[4] = {(uint32_t)p.KB, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
-        if (int e = encode_tmap_bf16(&tmX, x, 4, dims, str, box, p.row_bytes)) return e;
+        uint32_t box[4] = {(uint32_t)KB, (uint32_t)(p.slab ? p.tw + S - 1 : p.tw), (uint32_t)p.th, (uint32_t)p.tn};
+        if (int e = encode_tmap_bf16(&tmX, x, 4, dims, str, box, row_bytes)) return e;
     }
     {
         uint64_t dims[2] = {(uint64_t)R * S * Ci, (uint64_t)Co_pad};
         uint64_t str[1] = {(uint64_t)R * S * Ci * 2};
-        uint32_t box[2] = {(uint32_t)p.KB, (uint32_t)Co_pad};
-        if (int e = encode_tmap_bf16(&tmW, w, 2, dims, str, box, p.row_bytes)) return e;
+        uint32_t box[2] = {(uint32_t)KB, (uint32_t)Co_pad};
+        if (int e = encode_tmap_bf16(&tmW, w, 2, dims, str, box, row_bytes)) return e;
     }
-    const size_t smem = (size_t)p.stages * p.stage_stride + 1024 + 512;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FV_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
-    int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    conv_igemm_kernel<<<grid, kConvThreads, smem, (cudaStream_t)stream>>>(tmX, tmW, p);
-    FV_LAUNCH_CHECK("conv_igemm_kernel");
-    return FV_OK;
+    const size_t smem = (size_t)p.stages * p.stage_stride + 1024 + 256 + (size_t)Co_pad * 4 + 64;
+    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    cudaStream_t s = (cudaStream_t)stream;
+    if (KB == 64) return launch_conv<64>(tmX, tmW, p, smem, grid, s);
+    if (KB == 32) return launch_conv<32>(tmX, tmW, p, smem, grid, s);
+    return launch_conv<16>(tmX, tmW, p, smem, grid, s);
 }

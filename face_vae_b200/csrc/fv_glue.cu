@@ -216,21 +216,23 @@ __global__ void bn_act_fwd_kernel(const TI* __restrict__ y, const float* __restr
                                   int N, int H, int W, int C, int mode, int act, int nchw_out) {
     const float* scale = stat + 2 * C;
     const float* shift = stat + 3 * C;
-    const int groups = C / 8;
-    const int Ho = mode == FV_MODE_POOL ? H / 2 : H, Wo = mode == FV_MODE_POOL ? W / 2 : W;   // iteration domain
-    const long long total = (long long)N * Ho * Wo * groups;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(i % groups);
-        long long pix = i / groups;
-        const int wo = (int)(pix % Wo);
-        const int ho = (int)((pix / Wo) % Ho);
-        const int n = (int)(pix / ((long long)Wo * Ho));
-        float sc[8], sf[8];
+    const unsigned groups = C / 8;
+    const unsigned Ho = mode == FV_MODE_POOL ? H / 2 : H, Wo = mode == FV_MODE_POOL ? W / 2 : W;   // iteration domain
+    const unsigned total = (unsigned)N * Ho * Wo * groups;
+    // blockDim (256) is a multiple of groups, so a thread keeps the same channel group for its whole grid-stride walk
+    const unsigned g = threadIdx.x % groups;
+    float sc[8], sf[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            sc[k] = __ldg(scale + g * 8 + k);
-            sf[k] = __ldg(shift + g * 8 + k);
-        }
+    for (int k = 0; k < 8; ++k) {
+        sc[k] = __ldg(scale + g * 8 + k);
+        sf[k] = __ldg(shift + g * 8 + k);
+    }
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned pix = i / groups;
+        const unsigned wo = pix % Wo;
+        const unsigned t2 = pix / Wo;
+        const unsigned ho = t2 % Ho;
+        const unsigned n = t2 / Ho;
         float r[8];
         if (mode == FV_MODE_POOL) {
 #pragma unroll
@@ -324,10 +326,11 @@ __global__ void bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __r
             sc[k] = __ldg(stat + 2 * C + tc * 8 + k);
             sf[k] = __ldg(stat + 3 * C + tc * 8 + k);
         }
-        for (long long r = (long long)blockIdx.x * rpi + tr; r < P; r += (long long)gridDim.x * rpi) {
-            const int w = (int)(r % W), h = (int)((r / W) % H), n = (int)(r / ((long long)W * H));
+        for (unsigned r = blockIdx.x * rpi + tr; r < (unsigned)P; r += gridDim.x * rpi) {
+            const unsigned w = r % (unsigned)W, t2 = r / (unsigned)W;
+            const unsigned h = t2 % (unsigned)H, n = t2 / (unsigned)H;
             float f[8], ge[8];
-            V8<TY>::load(y + r * C + tc * 8, f);
+            V8<TY>::load(y + (size_t)r * C + tc * 8, f);
             load_g<TG>(g, g_nchw, mode, n, h, w, H, W, C, tc, ge);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -368,31 +371,40 @@ template <typename TY, typename TG>
 __global__ void bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
                                         const float* __restrict__ coef, const __nv_bfloat16* __restrict__ add,
                                         __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C, int mode, int act, int g_nchw) {
-    const int groups = C / 8;
-    const long long total = (long long)N * H * W * groups;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int grp = (int)(i % groups);
-        const long long r = i / groups;
-        const int w = (int)(r % W), h = (int)((r / W) % H), n = (int)(r / ((long long)W * H));
+    const unsigned groups = C / 8;
+    const unsigned total = (unsigned)N * H * W * groups;
+    const unsigned grp = threadIdx.x % groups;        // constant per thread: blockDim is a multiple of groups
+    float mean[8], invstd[8], sc[8], sf[8], c1[8], c2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = grp * 8 + k;
+        mean[k] = __ldg(stat + c);
+        invstd[k] = __ldg(stat + C + c);
+        sc[k] = __ldg(stat + 2 * C + c);
+        sf[k] = __ldg(stat + 3 * C + c);
+        c1[k] = __ldg(coef + c);
+        c2[k] = __ldg(coef + C + c);
+    }
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned r = i / groups;
+        const unsigned w = r % (unsigned)W, t2 = r / (unsigned)W;
+        const unsigned h = t2 % (unsigned)H, n = t2 / (unsigned)H;
         float f[8], ge[8], o[8];
-        V8<TY>::load(y + r * C + grp * 8, f);
+        V8<TY>::load(y + (size_t)r * C + grp * 8, f);
         load_g<TG>(g, g_nchw, mode, n, h, w, H, W, C, grp, ge);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int c = grp * 8 + k;
-            const float mean = __ldg(stat + c), invstd = __ldg(stat + C + c), sc = __ldg(stat + 2 * C + c),
-                        sf = __ldg(stat + 3 * C + c);
-            const float dz = ge[k] * act_grad(fmaf(f[k], sc, sf), act);
-            const float xhat = (f[k] - mean) * invstd;
-            o[k] = sc * (dz - __ldg(coef + c) - xhat * __ldg(coef + C + c));
+            const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
+            const float xhat = (f[k] - mean[k]) * invstd[k];
+            o[k] = sc[k] * (dz - c1[k] - xhat * c2[k]);
         }
         if (add) {
             float a[8];
-            V8<__nv_bfloat16>::load(add + r * C + grp * 8, a);
+            V8<__nv_bfloat16>::load(add + (size_t)r * C + grp * 8, a);
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] += a[k];
         }
-        V8<__nv_bfloat16>::store(dy + r * C + grp * 8, o);
+        V8<__nv_bfloat16>::store(dy + (size_t)r * C + grp * 8, o);
     }
 }
 
@@ -619,7 +631,7 @@ extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const floa
 static int reduce_geometry(int C, long long P, int& grid, size_t& shmem) {
     const int rpi = kThreads / (C / 8) > 0 ? kThreads / (C / 8) : 1;
     long long blocks = (P + rpi - 1) / rpi;
-    const long long cap = (long long)num_sms() * 4;
+    const long long cap = (long long)num_sms() * 8;
     grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
     shmem = (size_t)2 * rpi * C * sizeof(float);
     return rpi;
@@ -657,7 +669,8 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_eval_affine(const fl
 extern "C" __attribute__((visibility("default"))) int fv_bn_act_fwd(const void* y, int in_dtype, const float* stat, void* out, int out_dtype, int nchw_out, int N, int H,
                              int W, int C, int mode, int act, void* stream) {
     if (!y || !stat || !out) return fail(FV_ERR_ARG, "fv_bn_act_fwd: null pointer");
-    if (C % 8) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: C=%d must be a multiple of 8", C);
+    if (C % 8 || 256 % (C / 8)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: C=%d must be 8 * (a divisor of 256)", C);
+    if ((long long)N * H * W * (C / 8) >= (1LL << 31)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: tensor too large for 32-bit indexing");
     if (mode == FV_MODE_POOL && ((H | W) & 1)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: pooling needs even H, W");
     if (nchw_out && (out_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: NCHW output is fp32, no upsample");
     const int Ho = mode == FV_MODE_POOL ? H / 2 : H, Wo = mode == FV_MODE_POOL ? W / 2 : W;
@@ -676,6 +689,7 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_reduce(const
                                     float* sums, int N, int H, int W, int C, int mode, int act, void* stream) {
     if (!y || !g || !stat || !sums) return fail(FV_ERR_ARG, "fv_bn_act_bwd_reduce: null pointer");
     if (int e = check_c8("fv_bn_act_bwd_reduce", C)) return e;
+    if ((long long)N * H * W >= (1LL << 31)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_reduce: tensor too large for 32-bit indexing");
     if (g_nchw && (g_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_reduce: NCHW g is fp32, no upsample");
     int grid; size_t sh;
     reduce_geometry(C, (long long)N * H * W, grid, sh);
@@ -701,7 +715,8 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_apply(const 
                                    const float* coef, const void* add, void* dy, int N, int H, int W, int C, int mode, int act,
                                    void* stream) {
     if (!y || !g || !stat || !coef || !dy) return fail(FV_ERR_ARG, "fv_bn_act_bwd_apply: null pointer");
-    if (C % 8) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: C=%d must be a multiple of 8", C);
+    if (C % 8 || 256 % (C / 8)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: C=%d must be 8 * (a divisor of 256)", C);
+    if ((long long)N * H * W * (C / 8) >= (1LL << 31)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: tensor too large for 32-bit indexing");
     if (g_nchw && (g_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: NCHW g is fp32, no upsample");
     const int grid = grid_for((long long)N * H * W * (C / 8));
 #define LAUNCH(TY, TG) bn_act_bwd_apply_kernel<TY, TG><<<grid, kThreads, 0, STREAM>>>((const TY*)y, (const TG*)g, stat, coef, (const __nv_bfloat16*)add, (__nv_bfloat16*)dy, N, H, W, C, mode, act, g_nchw)

@@ -68,25 +68,33 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             const uint32_t tx = (uint32_t)(n_chunks * p.a_chunk_bytes + p.b_bytes);
-            uint32_t it = 0;
-            for (int pb = pb0; pb < pb1; ++pb, ++it) {
-                const int tn_i = pb / (p.tiles_w * p.tiles_h);
-                const int rem = pb - tn_i * (p.tiles_w * p.tiles_h);
-                const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+            uint32_t st = 0, phs = 0;
+            // pixel-block coordinates advance incrementally (no divisions in the steady state)
+            int tn_i = pb0 / (p.tiles_w * p.tiles_h);
+            int rem = pb0 - tn_i * (p.tiles_w * p.tiles_h);
+            int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+            for (int pb = pb0; pb < pb1; ++pb) {
                 const int w0 = tw_i * p.pw, h0 = th_i * p.ph, n0 = tn_i * p.pn;
-                const uint32_t st = it % p.stages, phs = (it / p.stages) & 1;
                 mbar_wait(&empty[st], phs ^ 1);
                 uint8_t* a_dst = smem + (size_t)st * p.stage_stride;
                 uint8_t* b_dst = a_dst + p.a_bytes;
                 mbar_arrive_expect_tx(&full[st], tx);
                 for (int bc = 0; bc < p.b_chunks; ++bc)
                     tma_load_4d(b_dst + (size_t)bc * p.b_chunk_bytes, &tmDY, &full[st], bc * p.bw, w0, h0, n0);
+                int tap = chunk0 / p.chunks_per_tap, cc = chunk0 - tap * p.chunks_per_tap;
+                int r = tap / p.S, sx = tap - r * p.S;
                 for (int j = 0; j < n_chunks; ++j) {
-                    const int cj = chunk0 + j;
-                    const int tap = cj / p.chunks_per_tap, cc = cj - tap * p.chunks_per_tap;
-                    const int r = tap / p.S, s = tap - r * p.S;
-                    tma_load_4d(a_dst + (size_t)j * p.a_chunk_bytes, &tmX, &full[st], cc * p.cw, w0 + s - p.pad,
+                    tma_load_4d(a_dst + (size_t)j * p.a_chunk_bytes, &tmX, &full[st], cc * p.cw, w0 + sx - p.pad,
                                 h0 + r - p.pad, n0);
+                    if (++cc == p.chunks_per_tap) {
+                        cc = 0;
+                        if (++sx == p.S) { sx = 0; ++r; }
+                    }
+                }
+                if (++st == (uint32_t)p.stages) { st = 0; phs ^= 1; }
+                if (++tw_i == p.tiles_w) {
+                    tw_i = 0;
+                    if (++th_i == p.tiles_h) { th_i = 0; ++tn_i; }
                 }
             }
         }
@@ -96,22 +104,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t a_layout = umma_layout_code(p.cw * 2), b_layout = umma_layout_code(p.bw * 2);
             const uint32_t a_sbo = 8u * p.cw * 2, b_sbo = 8u * p.bw * 2;
             const uint32_t a_kstep = 16u * p.cw * 2, b_kstep = 16u * p.bw * 2;   // 16 pixel rows per MMA
-            uint32_t it = 0;
-            for (int pb = pb0; pb < pb1; ++pb, ++it) {
-                const uint32_t st = it % p.stages, phs = (it / p.stages) & 1;
+            const uint64_t a_hi = umma_smem_desc(0, (uint32_t)p.a_chunk_bytes, a_sbo, a_layout);
+            const uint64_t b_hi = umma_smem_desc(0, (uint32_t)p.b_chunk_bytes, b_sbo, b_layout);
+            const uint32_t smem_base = smem_u32(smem);
+            uint32_t st = 0, phs = 0, accumulate = 0;
+            for (int pb = pb0; pb < pb1; ++pb) {
                 mbar_wait(&full[st], phs);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + (size_t)st * p.stage_stride);
-                const uint32_t b_addr = a_addr + p.a_bytes;
+                const uint32_t a_addr = smem_base + st * (uint32_t)p.stage_stride;
+                const uint32_t b_lo = (a_addr + (uint32_t)p.a_bytes) >> 4;
                 for (int t = 0; t < mt_n; ++t) {
-                    const uint32_t at = a_addr + (uint32_t)t * p.cpt * p.a_chunk_bytes;
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const uint64_t adesc = umma_smem_desc(at + k4 * a_kstep, (uint32_t)p.a_chunk_bytes, a_sbo, a_layout);
-                        const uint64_t bdesc = umma_smem_desc(b_addr + k4 * b_kstep, (uint32_t)p.b_chunk_bytes, b_sbo, b_layout);
-                        tc_mma_f16(tmem_base + (uint32_t)t * p.Co_pad, adesc, bdesc, idesc, (it > 0 || k4 > 0) ? 1u : 0u);
-                    }
+                    const uint32_t a_lo = (a_addr + (uint32_t)t * p.cpt * p.a_chunk_bytes) >> 4;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        tc_mma_f16(tmem_base + (uint32_t)t * p.Co_pad, a_hi | (uint64_t)((a_lo + k4 * (a_kstep >> 4)) & 0x3FFFu),
+                                   b_hi | (uint64_t)((b_lo + k4 * (b_kstep >> 4)) & 0x3FFFu), idesc, accumulate | (uint32_t)(k4 > 0));
                 }
+                accumulate = 1;
                 tc_commit(&empty[st]);
+                if (++st == (uint32_t)p.stages) { st = 0; phs ^= 1; }
             }
             tc_commit(tfull);
         }
