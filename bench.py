@@ -109,6 +109,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # libraries (NCCL's version banner, warnings) must not pollute the single JSON line on stdout
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -246,7 +249,8 @@ def main():
                         "last_loss": last},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
                 "peaks": peaks}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -246,6 +246,10 @@ static int pick_tile(int N, int H, int W, int& tw, int& th, int& tn) {
     return 0;
 }
 
+// fv_conv_ring.cu: sliding-window schedule for thin full-resolution layers; -1 when not eligible
+int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
+                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, cudaStream_t stream);
+
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
@@ -278,6 +282,10 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d(const void* x, c
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: only odd square filters with same padding (R=%d S=%d pad=%d)", R, S, pad);
     if (out_mode < 0 || out_mode > 2) return fail(FV_ERR_ARG, "fv_conv2d: out_mode %d", out_mode);
     if (out_mode == FV_OUT_NCHW_F32 && residual) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: residual needs an NHWC output");
+    {
+        const int rr = conv2d_ring_try(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, (cudaStream_t)stream);
+        if (rr >= 0) return rr;
+    }
     ConvParams p{};
     p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.Co_pad = Co_pad; p.R = R; p.S = S; p.pad = pad;
     if (pick_tile(N, H, W, p.tw, p.th, p.tn))

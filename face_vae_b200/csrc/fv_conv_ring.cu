@@ -1,0 +1,310 @@
+// Sliding-window ("ring") schedule of the implicit-GEMM convolution for the full-resolution thin layers
+// (Ci <= 64, filter resident in shared memory): the layers where the plain schedule is bound by L2->SMEM traffic
+// rather than by the tensor core.
+//
+// A tile is one image-row segment of 128 pixels.  Its R x S taps read R input-row slabs of (128 + S - 1) pixels; the
+// S taps of a row are row-shifted UMMA descriptor views of the same slab (see fv_conv.cu).  Each CTA walks a
+// contiguous run of vertically adjacent tiles, so consecutive tiles share R - 1 of their R slabs: the slabs live in
+// a shared-memory ring and only ONE new slab (plus nothing for the filter, which is loaded once per CTA) is fetched
+// per tile -- the SMEM fill traffic equals the HBM traffic of the layer.  Out-of-image rows / columns are zero-filled
+// by the TMA unit as before.
+//
+// Epilogue (NHWC bf16, Co_pad <= 64): TMEM -> registers -> (+bias) -> bf16 -> swizzled shared-memory staging tile ->
+// one TMA tensor store per tile (full 128-byte lines instead of 32 scattered 16-byte stores per instruction).
+// NCHW fp32 output (the 3-channel out_conv) is stored directly: consecutive lanes are consecutive pixels.
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../include/facevae_b200.h"
+#include "fv_host.h"
+#include "fv_ptx.cuh"
+
+namespace fv {
+
+struct RingParams {
+    int N, H, W, Ci, Co, Co_pad, R, S, pad;
+    int tiles_w, num_tiles, tiles_per_cta;
+    int ring, slab_stride, slab_tx;       // slots, placement stride and TMA bytes of one slab
+    int w_off, w_slice_stride, w_tx;      // filter region offset, per-tap slice stride, total TMA bytes
+    int stage_off, stage_stride;          // epilogue staging buffers (2), 0 stride when unused
+    int bar_off;
+    int out_mode, tmem_cols;
+    const float* bias;
+    void* out;
+};
+
+static constexpr int kRingThreads = 192;
+
+template <int KB>
+__global__ void __launch_bounds__(kRingThreads, 1)
+conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmY, const RingParams p) {
+    constexpr int ROW = KB * 2;
+    constexpr int KSUB = KB / 16;
+    constexpr uint32_t LAYOUT = ROW == 128 ? 2u : (ROW == 64 ? 4u : 6u);
+    constexpr uint32_t SBO = 8u * ROW;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.bar_off);      // [ring]
+    uint64_t* empty = full + p.ring;                                      // [ring]
+    uint64_t* wbar = empty + p.ring;
+    uint64_t* tfull = wbar + 1;                                           // [2]
+    uint64_t* tempty = tfull + 2;                                         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);              // [Co_pad]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * p.tiles_per_cta;
+    const int t1 = min(t0 + p.tiles_per_cta, p.num_tiles);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+        if (p.stage_stride) tma_prefetch_desc(&tmY);
+        for (int i = 0; i < p.ring; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(wbar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    for (int c = threadIdx.x; c < p.Co_pad; c += blockDim.x) bias_s[c] = (p.bias && c < p.Co) ? p.bias[c] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile t -> column (n, w segment) = t / H, image row h = t % H: consecutive tiles are vertically adjacent
+    if (warp == 0) {
+        if (lane == 0 && t0 < t1) {
+            // filter: R*S slices of [Co_pad x KB], resident for the whole kernel
+            mbar_arrive_expect_tx(wbar, (uint32_t)p.w_tx);
+            for (int tap = 0; tap < p.R * p.S; ++tap)
+                tma_load_2d(smem + p.w_off + tap * p.w_slice_stride, &tmW, wbar, tap * p.Ci, 0);
+            uint32_t slot = 0, ph = 0;
+            int col = t0 / p.H, h = t0 - col * p.H;
+            bool fresh = true;                                   // first tile of a column: all R slabs are new
+            for (int t = t0; t < t1; ++t) {
+                const int n = col / p.tiles_w, w0 = (col - n * p.tiles_w) * 128;
+                for (int j = fresh ? 0 : p.R - 1; j < p.R; ++j) {
+                    mbar_wait(&empty[slot], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[slot], (uint32_t)p.slab_tx);
+                    tma_load_4d(smem + (size_t)slot * p.slab_stride, &tmX, &full[slot], 0, w0 - p.pad, h + j - p.pad, n);
+                    if (++slot == (uint32_t)p.ring) { slot = 0; ph ^= 1; }
+                }
+                fresh = false;
+                if (++h == p.H) { h = 0; ++col; fresh = true; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && t0 < t1) {
+            const uint32_t idesc = umma_idesc_bf16(128, p.Co_pad, 0, 0);
+            const uint64_t desc_hi = umma_smem_desc(0, 16, SBO, LAYOUT);
+            const uint32_t smem_base = smem_u32(smem);
+            const uint32_t w_base = (smem_base + (uint32_t)p.w_off) >> 4;
+            const uint32_t w_step = (uint32_t)p.w_slice_stride >> 4;
+            mbar_wait(wbar, 0);
+            // window = R consecutive ring slots starting at `first`; `wait_slot/wait_ph` track the next slab to arrive
+            uint32_t first = 0, wait_slot = 0, wait_ph = 0, tcount = 0;
+            int h = t0 % p.H;
+            bool fresh = true;
+            for (int t = t0; t < t1; ++t, ++tcount) {
+                const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+                mbar_wait(&tempty[acc], aph ^ 1);
+                const int n_new = fresh ? p.R : 1;
+                for (int i = 0; i < n_new; ++i) {                 // the new slabs of this tile have landed?
+                    mbar_wait(&full[wait_slot], wait_ph);
+                    if (++wait_slot == (uint32_t)p.ring) { wait_slot = 0; wait_ph ^= 1; }
+                }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co_pad;
+                uint32_t accumulate = 0, slot = first, wtap = w_base;
+                for (int r = 0; r < p.R; ++r) {
+                    const uint32_t a_row = (smem_base + slot * (uint32_t)p.slab_stride) >> 4;
+                    for (int s = 0; s < p.S; ++s, wtap += w_step) {
+                        const uint32_t a_lo = a_row + (uint32_t)s * (ROW >> 4);       // tap s == slab shifted by s pixel rows
+#pragma unroll
+                        for (int j = 0; j < KSUB; ++j) {
+                            tc_mma_f16(d_tmem, desc_hi | (uint64_t)((a_lo + 2 * j) & 0x3FFFu),
+                                       desc_hi | (uint64_t)((wtap + 2 * j) & 0x3FFFu), idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    if (++slot == (uint32_t)p.ring) slot = 0;
+                }
+                tc_commit(&tfull[acc]);
+                // release the slabs the next tile will not read: one when it continues this column, all R otherwise
+                const bool next_fresh = (h + 1 == p.H);
+                const int n_rel = (t + 1 < t1) ? (next_fresh ? p.R : 1) : 0;
+                for (int i = 0; i < n_rel; ++i) {
+                    tc_commit(&empty[first]);
+                    if (++first == (uint32_t)p.ring) first = 0;
+                }
+                fresh = next_fresh;
+                if (++h == p.H) h = 0;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                   // pixel within the tile == w offset
+        constexpr int EPI_BAR = 1;
+        const bool use_tma_store = p.stage_stride != 0;
+        const int out_row = p.Co_pad * 2;                // bytes per pixel of the NHWC bf16 output tile
+        // 16-byte chunk swizzle of the staging tile (must match the store tensor map: 128B / 64B / 32B swizzle)
+        const int sw_mask = out_row == 128 ? 7 : (out_row == 64 ? 3 : 1);
+        const int sw_shift = out_row == 128 ? 0 : (out_row == 64 ? 1 : 2);
+        const int sw = (row >> sw_shift) & sw_mask;
+        uint32_t tcount = 0;
+        int col = t0 / p.H, h = t0 - col * p.H;
+        for (int t = t0; t < t1; ++t, ++tcount) {
+            const int n = col / p.tiles_w, w0 = (col - n * p.tiles_w) * 128;
+            const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+            uint8_t* stage = smem + p.stage_off + (size_t)acc * p.stage_stride;
+            if (use_tma_store) {
+                // the TMA store that last read this staging buffer (two tiles ago) must have drained it
+                if (warp == 2 && lane == 0) tma_store_wait_read<1>();
+                named_bar_sync(EPI_BAR, 128);
+            }
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * (uint32_t)p.Co_pad;
+            for (int c0 = 0; c0 < p.Co_pad; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);
+                tmem_ld_wait();
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias_s[c0 + i];
+                if (p.out_mode == FV_OUT_NCHW_F32) {
+                    float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < p.Co) o[(((size_t)n * p.Co + c0 + i) * p.H + h) * p.W + w0 + row] = f[i];
+                } else if (use_tma_store) {
+                    const int j0 = c0 >> 3;              // first 16-byte chunk of this column group
+                    uint4* s0 = reinterpret_cast<uint4*>(stage + row * out_row + (((j0) ^ sw) << 4));
+                    uint4* s1 = reinterpret_cast<uint4*>(stage + row * out_row + (((j0 + 1) ^ sw) << 4));
+                    *s0 = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                    *s1 = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                } else {
+                    const size_t pix = ((size_t)n * p.H + h) * p.W + w0 + row;
+                    if (p.out_mode == FV_OUT_NHWC_BF16) {
+                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Co_pad + c0);
+                        o[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                        o[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                    } else {
+                        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Co_pad + c0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);     // accumulator drained: the issuer may start tile t + 2
+            if (use_tma_store) {
+                fence_proxy_async();                       // make the staging writes visible to the TMA unit
+                named_bar_sync(EPI_BAR, 128);
+                if (warp == 2 && lane == 0) {
+                    tma_store_4d(&tmY, stage, 0, w0, h, n);
+                    tma_store_commit();
+                }
+            }
+            if (++h == p.H) { h = 0; ++col; }
+        }
+        if (use_tma_store && warp == 2 && lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+template <int KB>
+static int launch_ring(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmY, const RingParams& p, size_t smem,
+                       int grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FV_CUDA(cudaFuncSetAttribute(conv_ring_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    conv_ring_kernel<KB><<<grid, kRingThreads, smem, stream>>>(tmX, tmW, tmY, p);
+    FV_LAUNCH_CHECK("conv_ring_kernel");
+    return FV_OK;
+}
+
+// Returns FV_OK after launching, or -1 when the configuration is not eligible (caller falls through to the generic kernel).
+int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
+                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, cudaStream_t stream) {
+    if (S < 2 || W % 128 || Ci > 64 || residual) return -1;
+    const char* env = getenv("FV_CONV_RING");
+    if (env && atoi(env) == 0) return -1;
+    const int KB = Ci, row_bytes = KB * 2;
+    RingParams p{};
+    p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.Co_pad = Co_pad; p.R = R; p.S = S; p.pad = pad;
+    p.tiles_w = W / 128;
+    p.num_tiles = N * p.tiles_w * H;
+    const int a_rows = 128 + S - 1;
+    p.slab_tx = a_rows * row_bytes;
+    p.slab_stride = (p.slab_tx + 1023) & ~1023;
+    p.ring = R + 3;
+    p.w_slice_stride = (Co_pad * row_bytes + 1023) & ~1023;
+    p.w_tx = R * S * Co_pad * row_bytes;
+    p.w_off = p.ring * p.slab_stride;
+    int off = p.w_off + R * S * p.w_slice_stride;
+    const bool tma_store = (out_mode == FV_OUT_NHWC_BF16 && Co_pad <= 64);
+    p.stage_off = off;
+    p.stage_stride = tma_store ? ((128 * Co_pad * 2 + 1023) & ~1023) : 0;
+    off += 2 * p.stage_stride;
+    p.bar_off = off;
+    const size_t smem = (size_t)off + (2 * p.ring + 8) * 8 + 16 + (size_t)Co_pad * 4 + 1024 + 64;
+    if (smem > 225 * 1024) return -1;
+    int cols = 32;
+    while (cols < 2 * Co_pad) cols <<= 1;
+    p.tmem_cols = cols;
+    p.out_mode = out_mode;
+    p.bias = bias;
+    p.out = y;
+    const int sms = num_sms();
+    p.tiles_per_cta = (p.num_tiles + sms - 1) / sms;
+    const int grid = (p.num_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+
+    CUtensorMap tmX, tmW, tmY;
+    {
+        uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)Ci * 2, (uint64_t)W * Ci * 2, (uint64_t)H * W * Ci * 2};
+        uint32_t box[4] = {(uint32_t)KB, (uint32_t)a_rows, 1, 1};
+        if (int e = encode_tmap_bf16(&tmX, x, 4, dims, str, box, row_bytes)) return e;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)R * S * Ci, (uint64_t)Co_pad};
+        uint64_t str[1] = {(uint64_t)R * S * Ci * 2};
+        uint32_t box[2] = {(uint32_t)KB, (uint32_t)Co_pad};
+        if (int e = encode_tmap_bf16(&tmW, w, 2, dims, str, box, row_bytes)) return e;
+    }
+    if (tma_store) {
+        uint64_t dims[4] = {(uint64_t)Co_pad, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)Co_pad * 2, (uint64_t)W * Co_pad * 2, (uint64_t)H * W * Co_pad * 2};
+        uint32_t box[4] = {(uint32_t)Co_pad, 128, 1, 1};
+        if (int e = encode_tmap_bf16(&tmY, y, 4, dims, str, box, Co_pad * 2)) return e;
+    } else {
+        tmY = tmX;
+    }
+    if (KB == 64) return launch_ring<64>(tmX, tmW, tmY, p, smem, grid, stream);
+    if (KB == 32) return launch_ring<32>(tmX, tmW, tmY, p, smem, grid, stream);
+    return launch_ring<16>(tmX, tmW, tmY, p, smem, grid, stream);
+}
+
+}  // namespace fv

@@ -250,3 +250,17 @@ def test_recon_loss(ops, l1):
     s = torch.tensor([3.0]).cuda()
     sc = ops.scale(g2.view(-1)[:2328].contiguous(), s, 2.0)
     torch.testing.assert_close(sc, g2.view(-1)[:2328] * 6.0, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("n,h,w,ci,co,k,out_mode", [
+    (3, 37, 256, 32, 64, 3, 0),      # column changes in the middle of a CTA's run of tiles
+    (8, 64, 256, 64, 32, 3, 0),      # several tiles per CTA, 128-byte slab rows, 64-byte output rows
+    (2, 33, 128, 16, 16, 3, 0),      # 32-byte rows in and out
+    (3, 20, 128, 32, 3, 7, 2),       # 7x7 out_conv, NCHW fp32 output
+    (3, 20, 128, 16, 32, 7, 0),      # its data gradient shape (16 -> 32 channels, 7x7)
+    (2, 16, 384, 64, 128, 3, 0),     # Co_pad > 64: direct stores from the ring kernel
+    (2, 16, 128, 32, 64, 3, 1),      # fp32 NHWC output
+])
+def test_conv_ring_schedule(ops, n, h, w, ci, co, k, out_mode):
+    """Sliding-window schedule (fv_conv_ring.cu): resident filter, one new input-row slab per tile, TMA-store epilogue."""
+    _conv_case(ops, n, h, w, ci, co, k, out_mode=out_mode, seed=40)
