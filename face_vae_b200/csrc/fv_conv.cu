@@ -102,7 +102,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int s_mmas = p.slab ? p.S : 1;              // filter taps consumed per stage
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one_sync();      // role loops stay warp-uniform; only the issue is predicated
             uint32_t st = 0, ph = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
@@ -115,10 +116,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                             mbar_wait(&empty[st], ph ^ 1);
                             uint8_t* a_dst = smem + (size_t)st * p.stage_stride;
                             uint8_t* b_dst = a_dst + p.a_off_b;
-                            mbar_arrive_expect_tx(&full[st], (uint32_t)p.tx_bytes);
-                            tma_load_4d(a_dst, &tmX, &full[st], kc * KB, ww, hh, t.n0);
+                            if (leader) {
+                                mbar_arrive_expect_tx(&full[st], (uint32_t)p.tx_bytes);
+                                tma_load_4d(a_dst, &tmX, &full[st], kc * KB, ww, hh, t.n0);
+                            }
                             for (int sm = 0; sm < s_mmas; ++sm)
-                                tma_load_2d(b_dst + sm * p.b_slice_stride, &tmW, &full[st], wtap + sm * p.Ci + kc * KB, 0);
+                                if (leader) tma_load_2d(b_dst + sm * p.b_slice_stride, &tmW, &full[st], wtap + sm * p.Ci + kc * KB, 0);
                             if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
                         }
                     }
@@ -126,7 +129,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one_sync();
             const uint32_t idesc = umma_idesc_bf16(128, p.Co_pad, 0, 0);
             const uint64_t desc_hi = umma_smem_desc(0, 16, SBO, LAYOUT);   // template: all fields but the start address
             const uint32_t smem_base = smem_u32(smem);
@@ -148,15 +152,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         const uint32_t b_lo = (b_addr + (uint32_t)sm * p.b_slice_stride) >> 4;
 #pragma unroll
                         for (int j = 0; j < KSUB; ++j) {
-                            tc_mma_f16(d_tmem, desc_hi | (uint64_t)((a_lo + 2 * j) & 0x3FFFu),
-                                       desc_hi | (uint64_t)((b_lo + 2 * j) & 0x3FFFu), idesc, accumulate);
+                            if (leader)
+                                tc_mma_f16(d_tmem, desc_hi | (uint64_t)((a_lo + 2 * j) & 0x3FFFu),
+                                           desc_hi | (uint64_t)((b_lo + 2 * j) & 0x3FFFu), idesc, accumulate);
                             accumulate = 1;
                         }
                     }
-                    tc_commit(&empty[st]);   // frees the smem stage once these MMAs have read it
+                    if (leader) tc_commit(&empty[st]);   // frees the smem stage once these MMAs have read it
                     if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
                 }
-                tc_commit(&tfull[acc]);      // accumulator complete -> epilogue
+                if (leader) tc_commit(&tfull[acc]);      // accumulator complete -> epilogue
             }
         }
     } else {

@@ -85,11 +85,12 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
     // tile t -> column (n, w segment) = t / H, image row h = t % H: consecutive tiles are vertically adjacent
     if (warp == 0) {
-        if (lane == 0 && t0 < t1) {
+        if (t0 < t1) {
+            const bool leader = elect_one_sync();
             // filter: R*S slices of [Co_pad x KB], resident for the whole kernel
-            mbar_arrive_expect_tx(wbar, (uint32_t)p.w_tx);
+            if (leader) mbar_arrive_expect_tx(wbar, (uint32_t)p.w_tx);
             for (int tap = 0; tap < p.R * p.S; ++tap)
-                tma_load_2d(smem + p.w_off + tap * p.w_slice_stride, &tmW, wbar, tap * p.Ci, 0);
+                if (leader) tma_load_2d(smem + p.w_off + tap * p.w_slice_stride, &tmW, wbar, tap * p.Ci, 0);
             uint32_t slot = 0, ph = 0;
             int col = t0 / p.H, h = t0 - col * p.H;
             bool fresh = true;                                   // first tile of a column: all R slabs are new
@@ -97,8 +98,10 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 const int n = col / p.tiles_w, w0 = (col - n * p.tiles_w) * 128;
                 for (int j = fresh ? 0 : p.R - 1; j < p.R; ++j) {
                     mbar_wait(&empty[slot], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[slot], (uint32_t)p.slab_tx);
-                    tma_load_4d(smem + (size_t)slot * p.slab_stride, &tmX, &full[slot], 0, w0 - p.pad, h + j - p.pad, n);
+                    if (leader) {
+                        mbar_arrive_expect_tx(&full[slot], (uint32_t)p.slab_tx);
+                        tma_load_4d(smem + (size_t)slot * p.slab_stride, &tmX, &full[slot], 0, w0 - p.pad, h + j - p.pad, n);
+                    }
                     if (++slot == (uint32_t)p.ring) { slot = 0; ph ^= 1; }
                 }
                 fresh = false;
@@ -106,7 +109,8 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && t0 < t1) {
+        if (t0 < t1) {
+            const bool leader = elect_one_sync();
             const uint32_t idesc = umma_idesc_bf16(128, p.Co_pad, 0, 0);
             const uint64_t desc_hi = umma_smem_desc(0, 16, SBO, LAYOUT);
             const uint32_t smem_base = smem_u32(smem);
@@ -134,19 +138,20 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                         const uint32_t a_lo = a_row + (uint32_t)s * (ROW >> 4);       // tap s == slab shifted by s pixel rows
 #pragma unroll
                         for (int j = 0; j < KSUB; ++j) {
-                            tc_mma_f16(d_tmem, desc_hi | (uint64_t)((a_lo + 2 * j) & 0x3FFFu),
-                                       desc_hi | (uint64_t)((wtap + 2 * j) & 0x3FFFu), idesc, accumulate);
+                            if (leader)
+                                tc_mma_f16(d_tmem, desc_hi | (uint64_t)((a_lo + 2 * j) & 0x3FFFu),
+                                           desc_hi | (uint64_t)((wtap + 2 * j) & 0x3FFFu), idesc, accumulate);
                             accumulate = 1;
                         }
                     }
                     if (++slot == (uint32_t)p.ring) slot = 0;
                 }
-                tc_commit(&tfull[acc]);
+                if (leader) tc_commit(&tfull[acc]);
                 // release the slabs the next tile will not read: one when it continues this column, all R otherwise
                 const bool next_fresh = (h + 1 == p.H);
                 const int n_rel = (t + 1 < t1) ? (next_fresh ? p.R : 1) : 0;
                 for (int i = 0; i < n_rel; ++i) {
-                    tc_commit(&empty[first]);
+                    if (leader) tc_commit(&empty[first]);
                     if (++first == (uint32_t)p.ring) first = 0;
                 }
                 fresh = next_fresh;

@@ -66,7 +66,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one_sync();      // role loops stay warp-uniform; only the issue is predicated
             const uint32_t tx = (uint32_t)(n_chunks * p.a_chunk_bytes + p.b_bytes);
             uint32_t st = 0, phs = 0;
             // pixel-block coordinates advance incrementally (no divisions in the steady state)
@@ -78,14 +79,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 mbar_wait(&empty[st], phs ^ 1);
                 uint8_t* a_dst = smem + (size_t)st * p.stage_stride;
                 uint8_t* b_dst = a_dst + p.a_bytes;
-                mbar_arrive_expect_tx(&full[st], tx);
+                if (leader) mbar_arrive_expect_tx(&full[st], tx);
                 for (int bc = 0; bc < p.b_chunks; ++bc)
-                    tma_load_4d(b_dst + (size_t)bc * p.b_chunk_bytes, &tmDY, &full[st], bc * p.bw, w0, h0, n0);
+                    if (leader) tma_load_4d(b_dst + (size_t)bc * p.b_chunk_bytes, &tmDY, &full[st], bc * p.bw, w0, h0, n0);
                 int tap = chunk0 / p.chunks_per_tap, cc = chunk0 - tap * p.chunks_per_tap;
                 int r = tap / p.S, sx = tap - r * p.S;
                 for (int j = 0; j < n_chunks; ++j) {
-                    tma_load_4d(a_dst + (size_t)j * p.a_chunk_bytes, &tmX, &full[st], cc * p.cw, w0 + sx - p.pad,
-                                h0 + r - p.pad, n0);
+                    if (leader)
+                        tma_load_4d(a_dst + (size_t)j * p.a_chunk_bytes, &tmX, &full[st], cc * p.cw, w0 + sx - p.pad,
+                                    h0 + r - p.pad, n0);
                     if (++cc == p.chunks_per_tap) {
                         cc = 0;
                         if (++sx == p.S) { sx = 0; ++r; }
@@ -99,7 +101,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
+            const bool leader = elect_one_sync();
             const uint32_t idesc = umma_idesc_bf16(128, p.Co_pad, 1, 1);
             const uint32_t a_layout = umma_layout_code(p.cw * 2), b_layout = umma_layout_code(p.bw * 2);
             const uint32_t a_sbo = 8u * p.cw * 2, b_sbo = 8u * p.bw * 2;
@@ -117,14 +120,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     const uint32_t a_lo = (a_addr + (uint32_t)t * p.cpt * p.a_chunk_bytes) >> 4;
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4)
-                        tc_mma_f16(tmem_base + (uint32_t)t * p.Co_pad, a_hi | (uint64_t)((a_lo + k4 * (a_kstep >> 4)) & 0x3FFFu),
+                        if (leader) tc_mma_f16(tmem_base + (uint32_t)t * p.Co_pad, a_hi | (uint64_t)((a_lo + k4 * (a_kstep >> 4)) & 0x3FFFu),
                                    b_hi | (uint64_t)((b_lo + k4 * (b_kstep >> 4)) & 0x3FFFu), idesc, accumulate | (uint32_t)(k4 > 0));
                 }
                 accumulate = 1;
-                tc_commit(&empty[st]);
+                if (leader) tc_commit(&empty[st]);
                 if (++st == (uint32_t)p.stages) { st = 0; phs ^= 1; }
             }
-            tc_commit(tfull);
+            if (leader) tc_commit(tfull);
         }
     } else {
         const int q = warp & 3;
