@@ -65,8 +65,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     constexpr uint32_t LAYOUT = ROW == 128 ? 2u : (ROW == 64 ? 4u : 6u);
     constexpr uint32_t SBO = 8u * ROW;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // align up with arithmetic on the array itself so the compiler keeps the shared address space (LDS/STS, not generic)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_stride);
     uint64_t* empty = full + p.stages;
     uint64_t* tfull = empty + p.stages;

@@ -35,7 +35,7 @@ struct RingParams {
 
 static constexpr int kRingThreads = 192;
 
-template <int KB>
+template <int KB, int S_>
 __global__ void __launch_bounds__(kRingThreads, 1)
 conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmY, const RingParams p) {
@@ -44,8 +44,9 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     constexpr uint32_t LAYOUT = ROW == 128 ? 2u : (ROW == 64 ? 4u : 6u);
     constexpr uint32_t SBO = 8u * ROW;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // align up with arithmetic on the array itself so the compiler keeps the shared address space (LDS/STS, not generic)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.bar_off);      // [ring]
     uint64_t* empty = full + p.ring;                                      // [ring]
     uint64_t* wbar = empty + p.ring;
@@ -112,9 +113,10 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (t0 < t1) {
             const bool leader = elect_one_sync();
             const uint32_t idesc = umma_idesc_bf16(128, p.Co_pad, 0, 0);
-            const uint64_t desc_hi = umma_smem_desc(0, 16, SBO, LAYOUT);
+            const uint32_t desc_hi = (uint32_t)(umma_smem_desc(0, 16, SBO, LAYOUT) >> 32);   // low word = LBO | start address
+            constexpr uint32_t LBO_LO = (16u >> 4) << 16;
             const uint32_t smem_base = smem_u32(smem);
-            const uint32_t w_base = (smem_base + (uint32_t)p.w_off) >> 4;
+            const uint32_t w_base = ((smem_base + (uint32_t)p.w_off) >> 4) | LBO_LO;
             const uint32_t w_step = (uint32_t)p.w_slice_stride >> 4;
             mbar_wait(wbar, 0);
             // window = R consecutive ring slots starting at `first`; `wait_slot/wait_ph` track the next slab to arrive
@@ -133,16 +135,17 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co_pad;
                 uint32_t accumulate = 0, slot = first, wtap = w_base;
                 for (int r = 0; r < p.R; ++r) {
-                    const uint32_t a_row = (smem_base + slot * (uint32_t)p.slab_stride) >> 4;
-                    for (int s = 0; s < p.S; ++s, wtap += w_step) {
-                        const uint32_t a_lo = a_row + (uint32_t)s * (ROW >> 4);       // tap s == slab shifted by s pixel rows
+                    const uint32_t a_row = ((smem_base + slot * (uint32_t)p.slab_stride) >> 4) | LBO_LO;
+#pragma unroll
+                    for (int s = 0; s < S_; ++s) {                                    // tap s == slab shifted by s pixel rows
 #pragma unroll
                         for (int j = 0; j < KSUB; ++j) {
                             if (leader)
-                                tc_mma_f16(d_tmem, desc_hi | (uint64_t)((a_lo + 2 * j) & 0x3FFFu),
-                                           desc_hi | (uint64_t)((wtap + 2 * j) & 0x3FFFu), idesc, accumulate);
+                                tc_mma_f16_lohi(d_tmem, a_row + (uint32_t)(s * (ROW >> 4) + 2 * j), wtap + (uint32_t)(2 * j), desc_hi, idesc,
+                                                accumulate);
                             accumulate = 1;
                         }
+                        wtap += w_step;
                     }
                     if (++slot == (uint32_t)p.ring) slot = 0;
                 }
@@ -237,15 +240,15 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
 }
 
-template <int KB>
+template <int KB, int S_>
 static int launch_ring(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmY, const RingParams& p, size_t smem,
                        int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        FV_CUDA(cudaFuncSetAttribute(conv_ring_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FV_CUDA(cudaFuncSetAttribute(conv_ring_kernel<KB, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    conv_ring_kernel<KB><<<grid, kRingThreads, smem, stream>>>(tmX, tmW, tmY, p);
+    conv_ring_kernel<KB, S_><<<grid, kRingThreads, smem, stream>>>(tmX, tmW, tmY, p);
     FV_LAUNCH_CHECK("conv_ring_kernel");
     return FV_OK;
 }
@@ -253,7 +256,7 @@ static int launch_ring(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUt
 // Returns FV_OK after launching, or -1 when the configuration is not eligible (caller falls through to the generic kernel).
 int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
                     int W, int Ci, int Co, int Co_pad, int R, int S, int pad, cudaStream_t stream) {
-    if (S < 2 || W % 128 || Ci > 64 || residual) return -1;
+    if ((S != 3 && S != 5 && S != 7) || W % 128 || Ci > 64 || residual) return -1;
     const char* env = getenv("FV_CONV_RING");
     if (env && atoi(env) == 0) return -1;
     const int KB = Ci, row_bytes = KB * 2;
@@ -307,9 +310,13 @@ int conv2d_ring_try(const void* x, const void* w, const float* bias, const void*
     } else {
         tmY = tmX;
     }
-    if (KB == 64) return launch_ring<64>(tmX, tmW, tmY, p, smem, grid, stream);
-    if (KB == 32) return launch_ring<32>(tmX, tmW, tmY, p, smem, grid, stream);
-    return launch_ring<16>(tmX, tmW, tmY, p, smem, grid, stream);
+#define FV_RING(KB_) \
+    (S == 3 ? launch_ring<KB_, 3>(tmX, tmW, tmY, p, smem, grid, stream) \
+            : (S == 5 ? launch_ring<KB_, 5>(tmX, tmW, tmY, p, smem, grid, stream) : launch_ring<KB_, 7>(tmX, tmW, tmY, p, smem, grid, stream)))
+    if (KB == 64) return FV_RING(64);
+    if (KB == 32) return FV_RING(32);
+    return FV_RING(16);
+#undef FV_RING
 }
 
 }  // namespace fv

@@ -30,8 +30,9 @@ static constexpr int kWgradThreads = 192;
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // align up with arithmetic on the array itself so the compiler keeps the shared address space (LDS/STS, not generic)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_stride);
     uint64_t* empty = full + p.stages;
     uint64_t* tfull = empty + p.stages;
