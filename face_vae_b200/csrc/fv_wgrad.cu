@@ -164,6 +164,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
 }
 
+// fv_wgrad_ring.cu: sliding-window schedule for thin full-resolution layers; -1 when not eligible
+int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
+                          cudaStream_t stream);
+
 }  // namespace fv
 
 extern "C" __attribute__((visibility("default"))) int fv_conv2d_wgrad(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad,
@@ -176,6 +180,10 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d_wgrad(const void
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: Co_pad=%d must be 16, 32, 64, 128, 192 or 256", Co_pad);
     if (R != S || (R != 1 && R != 3 && R != 5 && R != 7) || pad != (R - 1) / 2)
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: only odd square filters with same padding");
+    {
+        const int rr = conv2d_wgrad_ring_try(x, dy, dw_acc, N, H, W, Ci, Co_pad, R, S, pad, (cudaStream_t)stream);
+        if (rr >= 0) return rr;
+    }
     WgradParams p{};
     p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co_pad = Co_pad; p.R = R; p.S = S; p.pad = pad; p.taps = R * S;
     if (W >= 64) {

@@ -1,0 +1,253 @@
+// Sliding-window schedule of the weight-gradient GEMM for the thin full-resolution layers (Ci <= 64, Co_pad <= 64):
+//
+//   dW[co, (r,s), ci] = sum_pixels X[pixel + (r - pad, s - pad), ci] * dY[pixel, co]
+//
+// The plain wgrad kernel (fv_wgrad.cu) fetches one shifted activation box per filter tap and pixel block, i.e. it
+// pulls the input R*S times through L2 -> SMEM; for the 7x7 out_conv that is 49x and the kernel is L2-bound.  Here a
+// CTA walks a run of vertically adjacent 64-pixel row segments and keeps the last R input-row slabs of (64 + S - 1)
+// pixels in a shared-memory ring: per segment ONE new slab and one dY tile are fetched.  The S taps of a filter row
+// are the same slab read through MN-major UMMA descriptors whose start address is shifted by s pixel rows; the
+// 128/cw taps stacked in one 128-row M tile are consecutive shifts, expressed by a leading-dimension byte offset of
+// one pixel row.  All R * ceil(S / (128/cw)) accumulators live in TMEM for the whole run; the epilogue adds them into
+// dW_acc[Co_pad][R*S][Ci] (fp32 atomics, one pass per CTA).
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../include/facevae_b200.h"
+#include "fv_host.h"
+#include "fv_ptx.cuh"
+
+namespace fv {
+
+struct WRingParams {
+    int N, H, W, Ci, Co_pad, R, S, pad, taps;
+    int cpt, tiles_per_r, mt_total;
+    int cols_w, num_blocks, blocks_per_cta;
+    int ring, slab_stride, slab_tx;
+    int b_off, b_slots, b_stride, b_tx;
+    int bar_off, tmem_cols;
+    float* dw;
+};
+
+static constexpr int kWRingThreads = 192;
+static constexpr int kPX = 64;            // pixels (GEMM K) per block
+
+template <int CW>                          // channels per A chunk == Ci (16 / 32 / 64)
+__global__ void __launch_bounds__(kWRingThreads, 1)
+conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WRingParams p) {
+    constexpr int AROW = CW * 2;                                   // bytes per pixel row of the activation slab
+    constexpr uint32_t A_LAYOUT = AROW == 128 ? 2u : (AROW == 64 ? 4u : 6u);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.bar_off);   // [ring]   slab landed
+    uint64_t* empty = full + p.ring;                                   // [ring]   slab no longer read
+    uint64_t* bfull = empty + p.ring;                                  // [b_slots] dY tile landed
+    uint64_t* bempty = bfull + p.b_slots;                              // [b_slots]
+    uint64_t* tfull = bempty + p.b_slots;                              // accumulators complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b0 = blockIdx.x * p.blocks_per_cta;
+    const int b1 = min(b0 + p.blocks_per_cta, p.num_blocks);
+    const int brow = p.Co_pad * 2;                                     // bytes per pixel row of the dY tile
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmDY);
+        for (int i = 0; i < p.ring; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < p.b_slots; ++i) {
+            mbar_init(&bfull[i], 1);
+            mbar_init(&bempty[i], 1);
+        }
+        mbar_init(tfull, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    // block b -> column (n, 64-pixel segment) = b / H, image row h = b % H: consecutive blocks are vertically adjacent
+    if (warp == 0) {
+        if (b0 < b1) {
+            const bool leader = elect_one_sync();
+            uint32_t slot = 0, ph = 0, bs = 0, bph = 0;
+            int col = b0 / p.H, h = b0 - col * p.H;
+            bool fresh = true;
+            for (int b = b0; b < b1; ++b) {
+                const int n = col / p.cols_w, w0 = (col - n * p.cols_w) * kPX;
+                mbar_wait(&bempty[bs], bph ^ 1);
+                if (leader) {
+                    mbar_arrive_expect_tx(&bfull[bs], (uint32_t)p.b_tx);
+                    tma_load_4d(smem + p.b_off + (size_t)bs * p.b_stride, &tmDY, &bfull[bs], 0, w0, h, n);
+                }
+                if (++bs == (uint32_t)p.b_slots) { bs = 0; bph ^= 1; }
+                for (int j = fresh ? 0 : p.R - 1; j < p.R; ++j) {
+                    mbar_wait(&empty[slot], ph ^ 1);
+                    if (leader) {
+                        mbar_arrive_expect_tx(&full[slot], (uint32_t)p.slab_tx);
+                        tma_load_4d(smem + (size_t)slot * p.slab_stride, &tmX, &full[slot], 0, w0 - p.pad, h + j - p.pad, n);
+                    }
+                    if (++slot == (uint32_t)p.ring) { slot = 0; ph ^= 1; }
+                }
+                fresh = false;
+                if (++h == p.H) { h = 0; ++col; fresh = true; }
+            }
+        }
+    } else if (warp == 1) {
+        if (b0 < b1) {
+            const bool leader = elect_one_sync();
+            const uint32_t idesc = umma_idesc_bf16(128, p.Co_pad, 1, 1);           // both operands MN-major
+            const uint32_t b_layout = umma_layout_code(brow);
+            // A: chunk i of an M tile = the slab shifted by i more pixel rows -> LBO = one pixel row
+            const uint64_t a_tmpl = umma_smem_desc(0, AROW, 8u * AROW, A_LAYOUT);
+            const uint64_t b_tmpl = umma_smem_desc(0, 16, 8u * brow, b_layout);
+            const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), a_lo_base = (uint32_t)a_tmpl;
+            const uint32_t b_hi = (uint32_t)(b_tmpl >> 32), b_lo_base = (uint32_t)b_tmpl;
+            const uint32_t smem_base = smem_u32(smem);
+            const uint32_t a_kstep = (16u * AROW) >> 4, b_kstep = (16u * (uint32_t)brow) >> 4;   // 16 pixel rows per MMA
+            uint32_t first = 0, wait_slot = 0, wait_ph = 0, bs = 0, bph = 0, accumulate = 0;
+            int h = b0 % p.H;
+            bool fresh = true;
+            for (int b = b0; b < b1; ++b) {
+                const int n_new = fresh ? p.R : 1;
+                for (int i = 0; i < n_new; ++i) {
+                    mbar_wait(&full[wait_slot], wait_ph);
+                    if (++wait_slot == (uint32_t)p.ring) { wait_slot = 0; wait_ph ^= 1; }
+                }
+                mbar_wait(&bfull[bs], bph);
+                tc_fence_after();
+                const uint32_t b_lo = b_lo_base | ((smem_base + (uint32_t)p.b_off + bs * (uint32_t)p.b_stride) >> 4);
+                uint32_t slot = first, d_col = tmem_base;
+                for (int r = 0; r < p.R; ++r) {
+                    const uint32_t a_row = a_lo_base | ((smem_base + slot * (uint32_t)p.slab_stride) >> 4);
+                    for (int part = 0; part < p.tiles_per_r; ++part, d_col += (uint32_t)p.Co_pad) {
+                        const uint32_t a_lo = a_row + (uint32_t)(part * p.cpt) * (AROW >> 4);   // first tap of this M tile
+#pragma unroll
+                        for (int k4 = 0; k4 < kPX / 16; ++k4)
+                            if (leader)
+                                tc_mma_f16_lohi2(d_col, a_lo + k4 * a_kstep, a_hi, b_lo + k4 * b_kstep, b_hi, idesc,
+                                                 accumulate | (uint32_t)(k4 > 0));
+                    }
+                    if (++slot == (uint32_t)p.ring) slot = 0;
+                }
+                accumulate = 1;
+                if (leader) tc_commit(&bempty[bs]);
+                if (++bs == (uint32_t)p.b_slots) { bs = 0; bph ^= 1; }
+                const bool next_fresh = (h + 1 == p.H);
+                const int n_rel = (b + 1 < b1) ? (next_fresh ? p.R : 1) : 0;
+                for (int i = 0; i < n_rel; ++i) {
+                    if (leader) tc_commit(&empty[first]);
+                    if (++first == (uint32_t)p.ring) first = 0;
+                }
+                fresh = next_fresh;
+                if (++h == p.H) h = 0;
+            }
+            if (leader) tc_commit(tfull);
+        }
+    } else if (b0 < b1) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int chunk = row / CW, ci = row % CW;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        const size_t co_stride = (size_t)p.taps * p.Ci;
+        int mt = 0;
+        for (int r = 0; r < p.R; ++r)
+            for (int part = 0; part < p.tiles_per_r; ++part, ++mt) {
+                const int s = part * p.cpt + chunk;
+                const bool valid = s < p.S;
+                const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + (uint32_t)mt * p.Co_pad;
+                float* dst = p.dw + (size_t)(r * p.S + s) * p.Ci + ci;
+                for (int c0 = 0; c0 < p.Co_pad; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)(c0 + i) * co_stride, __uint_as_float(v[i]));
+                    }
+                }
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+template <int CW>
+static int launch_wring(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WRingParams& p, size_t smem, int grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        FV_CUDA(cudaFuncSetAttribute(conv_wgrad_ring_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    conv_wgrad_ring_kernel<CW><<<grid, kWRingThreads, smem, stream>>>(tmX, tmDY, p);
+    FV_LAUNCH_CHECK("conv_wgrad_ring_kernel");
+    return FV_OK;
+}
+
+// FV_OK after launching, -1 when not eligible (caller falls through to the generic wgrad kernel).
+int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
+                          cudaStream_t stream) {
+    if (S < 2 || W % kPX || Ci > 64 || Co_pad > 64) return -1;
+    const char* env = getenv("FV_WGRAD_RING");
+    if (env && atoi(env) == 0) return -1;
+    WRingParams p{};
+    p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co_pad = Co_pad; p.R = R; p.S = S; p.pad = pad; p.taps = R * S;
+    p.cpt = 128 / Ci;
+    p.tiles_per_r = (S + p.cpt - 1) / p.cpt;
+    p.mt_total = R * p.tiles_per_r;
+    if (p.mt_total * Co_pad > 512) return -1;
+    p.cols_w = W / kPX;
+    p.num_blocks = N * p.cols_w * H;
+    const int arow = Ci * 2, brow = Co_pad * 2;
+    p.slab_tx = (kPX + S - 1) * arow;
+    // the last (partly unused) M tile of a filter row reads up to cpt - 1 pixel rows past its slab: keep them inside the stride
+    p.slab_stride = ((kPX + S - 1 + p.cpt) * arow + 1023) & ~1023;
+    p.ring = R + 3;
+    p.b_slots = 4;
+    p.b_tx = kPX * brow;
+    p.b_stride = (p.b_tx + 1023) & ~1023;
+    p.b_off = p.ring * p.slab_stride;
+    p.bar_off = p.b_off + p.b_slots * p.b_stride;
+    const size_t smem = (size_t)p.bar_off + (2 * p.ring + 2 * p.b_slots + 2) * 8 + 16 + 1024 + 64;
+    if (smem > 225 * 1024) return -1;
+    int cols = 32;
+    while (cols < p.mt_total * Co_pad) cols <<= 1;
+    p.tmem_cols = cols;
+    p.dw = dw_acc;
+    const int sms = num_sms();
+    p.blocks_per_cta = (p.num_blocks + sms - 1) / sms;
+    const int grid = (p.num_blocks + p.blocks_per_cta - 1) / p.blocks_per_cta;
+
+    CUtensorMap tmX, tmDY;
+    {
+        uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)Ci * 2, (uint64_t)W * Ci * 2, (uint64_t)H * W * Ci * 2};
+        uint32_t box[4] = {(uint32_t)Ci, (uint32_t)(kPX + S - 1), 1, 1};
+        if (int e = encode_tmap_bf16(&tmX, x, 4, dims, str, box, arow)) return e;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)Co_pad, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)Co_pad * 2, (uint64_t)W * Co_pad * 2, (uint64_t)H * W * Co_pad * 2};
+        uint32_t box[4] = {(uint32_t)Co_pad, (uint32_t)kPX, 1, 1};
+        if (int e = encode_tmap_bf16(&tmDY, dy, 4, dims, str, box, brow)) return e;
+    }
+    if (Ci == 64) return launch_wring<64>(tmX, tmDY, p, smem, grid, stream);
+    if (Ci == 32) return launch_wring<32>(tmX, tmDY, p, smem, grid, stream);
+    return launch_wring<16>(tmX, tmDY, p, smem, grid, stream);
+}
+
+}  // namespace fv

@@ -264,3 +264,31 @@ def test_recon_loss(ops, l1):
 def test_conv_ring_schedule(ops, n, h, w, ci, co, k, out_mode):
     """Sliding-window schedule (fv_conv_ring.cu): resident filter, one new input-row slab per tile, TMA-store epilogue."""
     _conv_case(ops, n, h, w, ci, co, k, out_mode=out_mode, seed=40)
+
+
+@pytest.mark.parametrize("n,h,w,ci,co,k", [
+    (3, 37, 256, 32, 64, 3),      # enc.1-like: 3 M tiles, column changes inside a CTA's run
+    (4, 64, 128, 64, 32, 3),      # up.3-like: two taps per M tile (128-byte slab rows)
+    (3, 20, 128, 32, 3, 7),       # out_conv: 14 accumulators of 16 columns
+    (2, 33, 64, 16, 32, 3),       # eight taps per M tile (32-byte slab rows)
+    (2, 16, 192, 64, 64, 5),      # 5x5
+])
+def test_wgrad_ring_schedule(ops, n, h, w, ci, co, k):
+    """Sliding-window weight gradient (fv_wgrad_ring.cu) against autograd."""
+    from face_vae_b200.ops import pad_channels
+    x = _rand((n, ci, h, w), 50)
+    wt = _rand((co, ci, k, k), 51, -0.2, 0.2).requires_grad_(True)
+    dy = _rand((n, co, h, w), 52)
+    F.conv2d(x, wt, None, padding=(k - 1) // 2).backward(dy)
+    acc = ops.conv2d_wgrad(ops.nchw_to_nhwc(x), ops.nchw_to_nhwc(dy, pad_channels(co)), k)
+    dw = ops.wgrad_finish(acc, co, ci, k)
+    torch.cuda.synchronize()
+    err = (dw - wt.grad).abs().max().item()
+    scale = wt.grad.abs().max().item()
+    print(f"wgrad-ring ci{ci} co{co} k{k} {h}x{w}: max_err {err:.4e} absmax {scale:.4e}")
+    if err > 2e-3 * scale + 1e-5:
+        bad = ((dw - wt.grad).abs() > 2e-3 * scale + 1e-5)
+        print("   bad frac by tap:", [round(v, 2) for v in bad.float().mean(dim=(0, 1)).flatten().tolist()])
+        print("   bad frac by ci :", [round(v, 2) for v in bad.float().mean(dim=(0, 2, 3)).tolist()][:16])
+        print("   bad frac by co :", [round(v, 2) for v in bad.float().mean(dim=(1, 2, 3)).tolist()][:16])
+    assert err <= 2e-3 * scale + 1e-5, f"wgrad mismatch {err} vs {scale}"
