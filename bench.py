@@ -163,6 +163,9 @@ def main():
     barrier()
     t_end = time.perf_counter()
     launches = _lib.launch_count - l0
+    if trainer.use_cuda_graph and trainer.launches_per_step:
+        # the step is a replayed CUDA graph: the C-ABI launches were counted when it was captured
+        launches = trainer.launches_per_step * args.steps
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device="cuda")
@@ -194,10 +197,14 @@ def main():
     kernels, roofline = {}, None
     if rank == 0 or world == 1:
         pass
+    graph_mode = trainer.use_cuda_graph
+    trainer.use_cuda_graph = False                 # eager replay of the same step: one event pair per launch
+    trainer.step(*dev[0])
     _lib.profile_start()
     for i in range(args.profile_steps):
         trainer.step(*dev[i % 2])
     recs = _lib.profile_stop()
+    trainer.use_cuda_graph = graph_mode
     agg = {}
     for name, t_ms, meta in recs:
         a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "flops_exec": 0.0, "bytes": 0.0})
@@ -242,7 +249,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": f"face-vae anchor (SURVEY.md section 8) train step, batch {B} per GPU at {S}x{S}, "
                                        f"0.2*KL + 10*MSE, Adam(5e-5, betas 0.5/0.999), bf16 storage / fp32 accumulate",
-                           "global_batch": B * world, "parallelism": f"dp{world}",
+                           "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(trainer.use_cuda_graph),
                            "l2": "working set per step (activations + gradients, >3 GB) far exceeds the 126 MB L2; inputs alternate between two batches"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * S * S * 4 + B * dz * 4, "d2h_bytes_per_step": 4,

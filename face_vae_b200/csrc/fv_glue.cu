@@ -145,7 +145,21 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sum
     const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (tr < rpi) {
-        for (long long r = (long long)blockIdx.x * rpi + tr; r < P; r += (long long)gridDim.x * rpi) {
+        const long long stride = (long long)gridDim.x * rpi;
+        long long r = (long long)blockIdx.x * rpi + tr;
+        for (; r + 3 * stride < P; r += 4 * stride) {            // four independent 16-byte loads in flight per thread
+            float f[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) V8<T>::load(y + (r + u * stride) * C + tc * 8, f[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    s[k] += f[u][k];
+                    q[k] += f[u][k] * f[u][k];
+                }
+        }
+        for (; r < P; r += stride) {
             float f[8];
             V8<T>::load(y + r * C + tc * 8, f);
 #pragma unroll
@@ -326,17 +340,32 @@ __global__ void bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __r
             sc[k] = __ldg(stat + 2 * C + tc * 8 + k);
             sf[k] = __ldg(stat + 3 * C + tc * 8 + k);
         }
-        for (unsigned r = blockIdx.x * rpi + tr; r < (unsigned)P; r += gridDim.x * rpi) {
-            const unsigned w = r % (unsigned)W, t2 = r / (unsigned)W;
-            const unsigned h = t2 % (unsigned)H, n = t2 / (unsigned)H;
-            float f[8], ge[8];
-            V8<TY>::load(y + (size_t)r * C + tc * 8, f);
-            load_g<TG>(g, g_nchw, mode, n, h, w, H, W, C, tc, ge);
+        constexpr int U = 4;
+        const unsigned stride = gridDim.x * rpi, Pu = (unsigned)P;
+        for (unsigned r0 = blockIdx.x * rpi + tr; r0 < Pu; r0 += U * stride) {
+            float f[U][8], ge[U][8];
+            bool ok[U];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
-                s1[k] += dz;
-                s2[k] += dz * (f[k] - mean[k]) * invstd[k];
+            for (int u = 0; u < U; ++u) {                         // all loads first: U rows of y and g in flight
+                const unsigned r = r0 + u * stride;
+                ok[u] = r < Pu;
+                if (ok[u]) {
+                    const unsigned w = r % (unsigned)W, t2 = r / (unsigned)W;
+                    const unsigned h = t2 % (unsigned)H, n = t2 / (unsigned)H;
+                    V8<TY>::load(y + (size_t)r * C + tc * 8, f[u]);
+                    load_g<TG>(g, g_nchw, mode, n, h, w, H, W, C, tc, ge[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (ok[u]) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float dz = ge[u][k] * act_grad(fmaf(f[u][k], sc[k], sf[k]), act);
+                        s1[k] += dz;
+                        s2[k] += dz * (f[u][k] - mean[k]) * invstd[k];
+                    }
+                }
             }
         }
 #pragma unroll
@@ -385,26 +414,40 @@ __global__ void bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __re
         c1[k] = __ldg(coef + c);
         c2[k] = __ldg(coef + C + c);
     }
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const unsigned r = i / groups;
-        const unsigned w = r % (unsigned)W, t2 = r / (unsigned)W;
-        const unsigned h = t2 % (unsigned)H, n = t2 / (unsigned)H;
-        float f[8], ge[8], o[8];
-        V8<TY>::load(y + (size_t)r * C + grp * 8, f);
-        load_g<TG>(g, g_nchw, mode, n, h, w, H, W, C, grp, ge);
+    constexpr int U = 4;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+        float f[U][8], ge[U][8], a[U][8];
+        unsigned rr[U];
+        bool ok[U];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
-            const float xhat = (f[k] - mean[k]) * invstd[k];
-            o[k] = sc[k] * (dz - c1[k] - xhat * c2[k]);
+        for (int u = 0; u < U; ++u) {                             // all loads first
+            const unsigned i = i0 + u * stride;
+            ok[u] = i < total;
+            rr[u] = i / groups;
+            if (ok[u]) {
+                const unsigned r = rr[u];
+                const unsigned w = r % (unsigned)W, t2 = r / (unsigned)W;
+                const unsigned h = t2 % (unsigned)H, n = t2 / (unsigned)H;
+                V8<TY>::load(y + (size_t)r * C + grp * 8, f[u]);
+                load_g<TG>(g, g_nchw, mode, n, h, w, H, W, C, grp, ge[u]);
+                if (add) V8<__nv_bfloat16>::load(add + (size_t)r * C + grp * 8, a[u]);
+            }
         }
-        if (add) {
-            float a[8];
-            V8<__nv_bfloat16>::load(add + (size_t)r * C + grp * 8, a);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] += a[k];
+        for (int u = 0; u < U; ++u) {
+            if (ok[u]) {
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float dz = ge[u][k] * act_grad(fmaf(f[u][k], sc[k], sf[k]), act);
+                    const float xhat = (f[u][k] - mean[k]) * invstd[k];
+                    o[k] = sc[k] * (dz - c1[k] - xhat * c2[k]);
+                    if (add) o[k] += a[u][k];
+                }
+                V8<__nv_bfloat16>::store(dy + (size_t)rr[u] * C + grp * 8, o);
+            }
         }
-        V8<__nv_bfloat16>::store(dy + (size_t)r * C + grp * 8, o);
     }
 }
 

@@ -39,19 +39,38 @@ class VAEGeneratorFull(nn.Module):
 
 
 class VAETrainer:
-    """One-model version of the reference Logger's optimisation step (logger.py:52-63, 150-164)."""
+    """One-model version of the reference Logger's optimisation step (logger.py:52-63, 150-164).
+
+    ``use_cuda_graph`` (default: on for a single CUDA process, off under data parallelism or with
+    FACEVAE_CUDA_GRAPH=0): the whole step -- zero_grad, forward, backward, Adam -- is captured once per input shape into
+    a CUDA graph and replayed, which removes the ~260 per-launch host round trips of the eager step.  The captured
+    sequence is exactly the eager one (same kernels, same order, same stream semantics)."""
 
     def __init__(self, vae: FaceVAE, lr: float = 5e-5, weights: Optional[Dict[str, float]] = None, bucket_mb: float = 2.0,
-                 fused_adam: bool = True):
+                 fused_adam: bool = True, use_cuda_graph: Optional[bool] = None):
+        import os
         self.g_full = VAEGeneratorFull(vae, weights)
         self.vae = vae
         fdist.broadcast_parameters(vae)
         params = list(vae.parameters())
         on_cuda = bool(params) and params[0].is_cuda
-        self.optimizer = torch.optim.Adam(params, lr=lr, betas=(0.5, 0.999), **({"fused": True} if (fused_adam and on_cuda) else {}))
-        self.reducer = fdist.GradientReducer(params, bucket_mb) if fdist.get_world_size() > 1 else None
+        world = fdist.get_world_size()
+        if use_cuda_graph is None:
+            use_cuda_graph = on_cuda and world == 1 and os.environ.get("FACEVAE_CUDA_GRAPH", "1") != "0"
+        self.use_cuda_graph = bool(use_cuda_graph) and on_cuda and world == 1
+        kw = {}
+        if fused_adam and on_cuda:
+            kw["fused"] = True
+            if self.use_cuda_graph:
+                kw["capturable"] = True
+        self.optimizer = torch.optim.Adam(params, lr=lr, betas=(0.5, 0.999), **kw)
+        self.reducer = fdist.GradientReducer(params, bucket_mb) if world > 1 else None
+        self._graph = None
+        self._graph_key = None
+        self.launches_per_step = None            # C-ABI kernel launches inside one captured step
 
-    def step(self, d: torch.Tensor, eps: Optional[torch.Tensor] = None):
+    # -- eager ----------------------------------------------------------------------------------------------------
+    def _eager_step(self, d: torch.Tensor, eps: Optional[torch.Tensor]):
         self.optimizer.zero_grad(set_to_none=True)
         losses, generated, mu, logstd = self.g_full(d, eps, True)
         total = sum(losses.values())
@@ -60,3 +79,51 @@ class VAETrainer:
             self.reducer.finish()
         self.optimizer.step()
         return losses, generated
+
+    # -- CUDA graph -----------------------------------------------------------------------------------------------
+    def _capture(self, d: torch.Tensor, eps: torch.Tensor) -> None:
+        import copy
+        from . import _lib
+        self._static_d = d.clone()
+        self._static_eps = eps.clone()
+        # warm-up on a side stream (lazy initialisation, allocator pools) without changing the training state
+        snap_model = copy.deepcopy(self.vae.state_dict())
+        snap_opt = copy.deepcopy(self.optimizer.state_dict())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._eager_step(self._static_d, self._static_eps)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.vae.load_state_dict(snap_model)
+        self.optimizer.load_state_dict(snap_opt)
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        l0 = _lib.launch_count
+        with torch.cuda.graph(graph):
+            losses, generated, _, _ = self.g_full(self._static_d, self._static_eps, True)
+            total = sum(losses.values())
+            total.backward()
+            self.optimizer.step()
+        self.launches_per_step = _lib.launch_count - l0
+        self._graph, self._static_out = graph, (losses, generated)
+        self._graph_key = (tuple(d.shape), tuple(eps.shape))
+
+    def _graph_step(self, d: torch.Tensor, eps: Optional[torch.Tensor]):
+        if eps is None:
+            eps = torch.randn((d.shape[0], self.vae.latent_dim(d.shape[2], d.shape[3])), device=d.device)
+        eps = eps.reshape(d.shape[0], -1)
+        if self._graph is None or self._graph_key != (tuple(d.shape), tuple(eps.shape)):
+            self._capture(d.float().contiguous(), eps.float().contiguous())
+        self._static_d.copy_(d, non_blocking=True)
+        self._static_eps.copy_(eps, non_blocking=True)
+        self._graph.replay()
+        return self._static_out
+
+    def step(self, d: torch.Tensor, eps: Optional[torch.Tensor] = None):
+        """-> (loss dict {"K", "R"} already weight-multiplied, generated frames).  With CUDA graphs the returned tensors are
+        the graph's static outputs: they are overwritten by the next step."""
+        if self.use_cuda_graph and d.is_cuda:
+            return self._graph_step(d, eps)
+        return self._eager_step(d, eps)

@@ -229,3 +229,29 @@ def test_full_size_properties(fv):
         a1 = m(x[:4], False)[2]
         a2 = m(x[:4], False)[2]
     assert torch.equal(a1, a2)
+
+
+def test_cuda_graph_step_matches_eager(fv):
+    """The captured train step (VAETrainer(use_cuda_graph=True)) replays the eager sequence: same losses / weights
+    up to the bf16 run-to-run noise of the path, and the capture warm-up leaves the training state untouched."""
+    cfg = O.CFG_256
+    p = O.det_anchor_params(cfg, 0)
+    x, eps = O.det_inputs(4, 64, 64, cfg, 11)
+    x, eps = x.cuda(), eps.cuda()
+    res = {}
+    for mode in (False, True):
+        m = _load(fv.models.FaceVAE(), p)
+        tr = fv.trainer.VAETrainer(m, lr=1e-3, use_cuda_graph=mode)
+        vals = []
+        for _ in range(4):
+            losses, gen = tr.step(x, eps)
+            vals.append(sum(v.item() for v in losses.values()))
+        res[mode] = (vals, {k: v.detach().clone() for k, v in m.named_parameters()}, tr)
+    assert res[True][2].use_cuda_graph and res[True][2].launches_per_step > 100
+    v0, v1 = res[False][0], res[True][0]
+    assert abs(v0[0] - v1[0]) <= 5e-3 * abs(v0[0]), (v0, v1)        # first step: identical weights (warm-up was rolled back)
+    for a, b in zip(v0, v1):
+        assert abs(a - b) <= 2e-2 * abs(a), (v0, v1)
+    assert v1[-1] < v1[0]
+    w0, w1 = res[False][1]["out_conv.weight"], res[True][1]["out_conv.weight"]
+    assert ((w0 - w1).norm() / w0.norm()).item() < 5e-2
