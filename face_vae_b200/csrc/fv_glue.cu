@@ -44,6 +44,26 @@ template <> struct V8<float> {
     }
 };
 
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+    uint4 v;
+    __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+    }
+};
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) {
+        a = *reinterpret_cast<const float4*>(p);
+        b = *reinterpret_cast<const float4*>(p + 4);
+    }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+};
+
 __device__ __forceinline__ float act_fwd(float z, int act) {
     return act == FV_ACT_RELU ? fmaxf(z, 0.f) : (act == FV_ACT_LEAKY ? (z > 0.f ? z : 0.2f * z) : z);
 }
@@ -286,93 +306,120 @@ __global__ void bn_act_fwd_kernel(const TI* __restrict__ y, const float* __restr
 
 // ---------------------------------------------------------------- norm + act backward
 // Effective upstream gradient at the (pre-pool / pre-upsample) activation:  POOL: g/4 of the pooled pixel,
-// UP: sum of the 2x2 replicated pixels, NONE: g.  g is NHWC (TG) or NCHW fp32 when g_nchw.
-template <typename TG>
-__device__ __forceinline__ void load_g(const TG* g, int g_nchw, int mode, int n, int h, int w, int H, int W, int C,
-                                       int grp, float (&r)[8]) {
-    if (mode == FV_MODE_POOL) {
-        const int Hp = H / 2, Wp = W / 2;
-        if (g_nchw) {
+// UP: sum of the 2x2 replicated pixels, NONE: g.  g is NHWC (TG) or NCHW fp32 when GN.  MODE / GN are compile-time so
+// the unrolled main loops below carry no branches and the compiler can keep four rows of loads in flight.
+template <typename TG, int MODE, bool GN>
+struct GLoad {                                      // phase 1: issue the loads (raw registers); phase 2: convert / combine
+    static constexpr int NR = (MODE == FV_MODE_UP) ? 4 : 1;
+    Raw8<TG> raw[GN ? 1 : NR];
+    float nchw[GN ? 8 : 1];
+    __device__ __forceinline__ void issue(const TG* __restrict__ g, unsigned n, unsigned h, unsigned w, int H, int W, int C, unsigned grp) {
+        if (GN) {
             const float* gf = reinterpret_cast<const float*>(g);
+            const int Hg = MODE == FV_MODE_POOL ? H / 2 : H, Wg = MODE == FV_MODE_POOL ? W / 2 : W;
+            const unsigned hg = MODE == FV_MODE_POOL ? h / 2 : h, wg = MODE == FV_MODE_POOL ? w / 2 : w;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] = 0.25f * __ldg(gf + (((long long)n * C + grp * 8 + k) * Hp + h / 2) * Wp + w / 2);
+            for (int k = 0; k < 8; ++k) nchw[k] = __ldg(gf + (((size_t)n * C + grp * 8 + k) * Hg + hg) * Wg + wg);
+        } else if (MODE == FV_MODE_POOL) {
+            raw[0].load(g + (((size_t)n * (H / 2) + h / 2) * (W / 2) + w / 2) * C + grp * 8);
+        } else if (MODE == FV_MODE_UP) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                raw[GN ? 0 : d].load(g + (((size_t)n * 2 * H + 2 * h + (d >> 1)) * (2 * W) + 2 * w + (d & 1)) * C + grp * 8);
         } else {
-            V8<TG>::load(g + (((long long)n * Hp + h / 2) * Wp + w / 2) * C + grp * 8, r);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] *= 0.25f;
+            raw[0].load(g + (((size_t)n * H + h) * W + w) * C + grp * 8);
         }
-    } else if (mode == FV_MODE_UP) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = 0.f;
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                float f[8];
-                V8<TG>::load(g + (((long long)n * 2 * H + 2 * h + dy) * (2 * W) + 2 * w + dx) * C + grp * 8, f);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) r[k] += f[k];
-            }
-    } else if (g_nchw) {
-        const float* gf = reinterpret_cast<const float*>(g);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = __ldg(gf + (((long long)n * C + grp * 8 + k) * H + h) * W + w);
-    } else {
-        V8<TG>::load(g + (((long long)n * H + h) * W + w) * C + grp * 8, r);
     }
+    __device__ __forceinline__ void finish(float (&r)[8]) const {
+        if (GN) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = MODE == FV_MODE_POOL ? 0.25f * nchw[k] : nchw[k];
+        } else if (MODE == FV_MODE_UP) {
+            float f[4][8];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) raw[GN ? 0 : d].unpack(f[d]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = (f[0][k] + f[1][k]) + (f[2][k] + f[3][k]);
+        } else {
+            raw[0].unpack(r);
+            if (MODE == FV_MODE_POOL) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] *= 0.25f;
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ void row_to_nhw(unsigned r, int H, int W, unsigned& n, unsigned& h, unsigned& w) {
+    w = r % (unsigned)W;
+    const unsigned t2 = r / (unsigned)W;
+    h = t2 % (unsigned)H;
+    n = t2 / (unsigned)H;
 }
 
 // pass 1: sums[0..C) += sum dz, sums[C..2C) += sum dz * xhat,  dz = g_eff * act'(scale*y+shift), xhat = (y-mean)*invstd
-template <typename TY, typename TG>
-__global__ void bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
-                                         float* __restrict__ sums, int N, int H, int W, int C, int mode, int act, int g_nchw) {
+template <typename TY, typename TG, int MODE, bool GN>
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
+                         float* __restrict__ sums, int N, int H, int W, int C, int act) {
     extern __shared__ float sh[];
     const int tpr = C / 8, rpi = blockDim.x / tpr;
     const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
-    const long long P = (long long)N * H * W;
+    const unsigned P = (unsigned)N * H * W;
     float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (tr < rpi) {
-        float mean[8], invstd[8], sc[8], sf[8];
+    float mean[8], invstd[8], sc[8], sf[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            mean[k] = __ldg(stat + tc * 8 + k);
-            invstd[k] = __ldg(stat + C + tc * 8 + k);
-            sc[k] = __ldg(stat + 2 * C + tc * 8 + k);
-            sf[k] = __ldg(stat + 3 * C + tc * 8 + k);
+    for (int k = 0; k < 8; ++k) {
+        mean[k] = __ldg(stat + tc * 8 + k);
+        invstd[k] = __ldg(stat + C + tc * 8 + k);
+        sc[k] = __ldg(stat + 2 * C + tc * 8 + k);
+        sf[k] = __ldg(stat + 3 * C + tc * 8 + k);
+    }
+    constexpr int U = MODE == FV_MODE_UP ? 2 : 4;
+    const unsigned stride = gridDim.x * rpi;
+    unsigned r0 = blockIdx.x * rpi + tr;
+    for (; r0 + (U - 1) * stride < P; r0 += U * stride) {
+        Raw8<TY> yr[U];
+        GLoad<TG, MODE, GN> gl[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {                         // U rows of y and g in flight, 4 registers per 16-byte load
+            unsigned n, h, w;
+            row_to_nhw(r0 + u * stride, H, W, n, h, w);
+            yr[u].load(y + (size_t)(r0 + u * stride) * C + tc * 8);
+            gl[u].issue(g, n, h, w, H, W, C, tc);
         }
-        constexpr int U = 4;
-        const unsigned stride = gridDim.x * rpi, Pu = (unsigned)P;
-        for (unsigned r0 = blockIdx.x * rpi + tr; r0 < Pu; r0 += U * stride) {
-            float f[U][8], ge[U][8];
-            bool ok[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {                         // all loads first: U rows of y and g in flight
-                const unsigned r = r0 + u * stride;
-                ok[u] = r < Pu;
-                if (ok[u]) {
-                    const unsigned w = r % (unsigned)W, t2 = r / (unsigned)W;
-                    const unsigned h = t2 % (unsigned)H, n = t2 / (unsigned)H;
-                    V8<TY>::load(y + (size_t)r * C + tc * 8, f[u]);
-                    load_g<TG>(g, g_nchw, mode, n, h, w, H, W, C, tc, ge[u]);
-                }
-            }
+        for (int u = 0; u < U; ++u) {
+            float f[8], ge[8];
+            yr[u].unpack(f);
+            gl[u].finish(ge);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (ok[u]) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float dz = ge[u][k] * act_grad(fmaf(f[u][k], sc[k], sf[k]), act);
-                        s1[k] += dz;
-                        s2[k] += dz * (f[u][k] - mean[k]) * invstd[k];
-                    }
-                }
+            for (int k = 0; k < 8; ++k) {
+                const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
+                s1[k] += dz;
+                s2[k] += dz * (f[k] - mean[k]) * invstd[k];
             }
         }
+    }
+    for (; r0 < P; r0 += stride) {
+        unsigned n, h, w;
+        row_to_nhw(r0, H, W, n, h, w);
+        float f[8], ge[8];
+        V8<TY>::load(y + (size_t)r0 * C + tc * 8, f);
+        GLoad<TG, MODE, GN> gl;
+        gl.issue(g, n, h, w, H, W, C, tc);
+        gl.finish(ge);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            sh[tr * C + tc * 8 + k] = s1[k];
-            sh[(rpi + tr) * C + tc * 8 + k] = s2[k];
+            const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
+            s1[k] += dz;
+            s2[k] += dz * (f[k] - mean[k]) * invstd[k];
         }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        sh[tr * C + tc * 8 + k] = s1[k];
+        sh[(rpi + tr) * C + tc * 8 + k] = s2[k];
     }
     __syncthreads();
     for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
@@ -395,18 +442,20 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums_local, con
     }
 }
 
-// pass 2: dy = scale * (dz - c1 - xhat * c2) (+ add), written bf16 NHWC: the conv-output gradient fed to dgrad / wgrad
-template <typename TY, typename TG>
-__global__ void bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
-                                        const float* __restrict__ coef, const __nv_bfloat16* __restrict__ add,
-                                        __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C, int mode, int act, int g_nchw) {
-    const unsigned groups = C / 8;
-    const unsigned total = (unsigned)N * H * W * groups;
-    const unsigned grp = threadIdx.x % groups;        // constant per thread: blockDim is a multiple of groups
+// pass 2: dy = scale * (dz - c1 - xhat * c2) (+ add), written bf16 NHWC: the conv-output gradient fed to dgrad / wgrad.
+// Same thread -> (row, channel group) mapping as pass 1, so the per-channel constants sit in registers.
+template <typename TY, typename TG, int MODE, bool GN, bool ADD>
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
+                        const float* __restrict__ coef, const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dy,
+                        int N, int H, int W, int C, int act) {
+    const int tpr = C / 8, rpi = blockDim.x / tpr;
+    const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
+    const unsigned P = (unsigned)N * H * W;
     float mean[8], invstd[8], sc[8], sf[8], c1[8], c2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int c = grp * 8 + k;
+        const int c = tc * 8 + k;
         mean[k] = __ldg(stat + c);
         invstd[k] = __ldg(stat + C + c);
         sc[k] = __ldg(stat + 2 * C + c);
@@ -414,40 +463,54 @@ __global__ void bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __re
         c1[k] = __ldg(coef + c);
         c2[k] = __ldg(coef + C + c);
     }
-    constexpr int U = 4;
-    const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
-        float f[U][8], ge[U][8], a[U][8];
-        unsigned rr[U];
-        bool ok[U];
+    constexpr int U = MODE == FV_MODE_UP ? 2 : 4;
+    const unsigned stride = gridDim.x * rpi;
+    unsigned r0 = blockIdx.x * rpi + tr;
+    for (; r0 + (U - 1) * stride < P; r0 += U * stride) {
+        Raw8<TY> yr[U];
+        GLoad<TG, MODE, GN> gl[U];
+        Raw8<__nv_bfloat16> ar[ADD ? U : 1];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {                             // all loads first
-            const unsigned i = i0 + u * stride;
-            ok[u] = i < total;
-            rr[u] = i / groups;
-            if (ok[u]) {
-                const unsigned r = rr[u];
-                const unsigned w = r % (unsigned)W, t2 = r / (unsigned)W;
-                const unsigned h = t2 % (unsigned)H, n = t2 / (unsigned)H;
-                V8<TY>::load(y + (size_t)r * C + grp * 8, f[u]);
-                load_g<TG>(g, g_nchw, mode, n, h, w, H, W, C, grp, ge[u]);
-                if (add) V8<__nv_bfloat16>::load(add + (size_t)r * C + grp * 8, a[u]);
-            }
+        for (int u = 0; u < U; ++u) {
+            unsigned n, h, w;
+            row_to_nhw(r0 + u * stride, H, W, n, h, w);
+            yr[u].load(y + (size_t)(r0 + u * stride) * C + tc * 8);
+            gl[u].issue(g, n, h, w, H, W, C, tc);
+            if (ADD) ar[ADD ? u : 0].load(add + (size_t)(r0 + u * stride) * C + tc * 8);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (ok[u]) {
-                float o[8];
+            float f[8], ge[8], a[8], o[8];
+            yr[u].unpack(f);
+            gl[u].finish(ge);
+            if (ADD) ar[ADD ? u : 0].unpack(a);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float dz = ge[u][k] * act_grad(fmaf(f[u][k], sc[k], sf[k]), act);
-                    const float xhat = (f[u][k] - mean[k]) * invstd[k];
-                    o[k] = sc[k] * (dz - c1[k] - xhat * c2[k]);
-                    if (add) o[k] += a[u][k];
-                }
-                V8<__nv_bfloat16>::store(dy + (size_t)rr[u] * C + grp * 8, o);
+            for (int k = 0; k < 8; ++k) {
+                const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
+                const float xhat = (f[k] - mean[k]) * invstd[k];
+                o[k] = sc[k] * (dz - c1[k] - xhat * c2[k]);
+                if (ADD) o[k] += a[k];
             }
+            V8<__nv_bfloat16>::store(dy + (size_t)(r0 + u * stride) * C + tc * 8, o);
         }
+    }
+    for (; r0 < P; r0 += stride) {
+        unsigned n, h, w;
+        row_to_nhw(r0, H, W, n, h, w);
+        float f[8], ge[8], o[8], a[8];
+        V8<TY>::load(y + (size_t)r0 * C + tc * 8, f);
+        GLoad<TG, MODE, GN> gl;
+        gl.issue(g, n, h, w, H, W, C, tc);
+        gl.finish(ge);
+        if (ADD) V8<__nv_bfloat16>::load(add + (size_t)r0 * C + tc * 8, a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
+            const float xhat = (f[k] - mean[k]) * invstd[k];
+            o[k] = sc[k] * (dz - c1[k] - xhat * c2[k]);
+            if (ADD) o[k] += a[k];
+        }
+        V8<__nv_bfloat16>::store(dy + (size_t)r0 * C + tc * 8, o);
     }
 }
 
@@ -736,12 +799,17 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_reduce(const
     if (g_nchw && (g_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_reduce: NCHW g is fp32, no upsample");
     int grid; size_t sh;
     reduce_geometry(C, (long long)N * H * W, grid, sh);
-#define LAUNCH(TY, TG) bn_act_bwd_reduce_kernel<TY, TG><<<grid, kThreads, sh, STREAM>>>((const TY*)y, (const TG*)g, stat, sums, N, H, W, C, mode, act, g_nchw)
-    if (y_dtype == FV_DT_BF16 && g_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
-    else if (y_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, float);
-    else if (g_dtype == FV_DT_BF16) LAUNCH(float, __nv_bfloat16);
-    else LAUNCH(float, float);
-#undef LAUNCH
+#define LAUNCH3(TY, TG, M, GNF) bn_act_bwd_reduce_kernel<TY, TG, M, GNF><<<grid, kThreads, sh, STREAM>>>((const TY*)y, (const TG*)g, stat, sums, N, H, W, C, act)
+#define LAUNCH2(TY, TG) do { \
+        if (mode == FV_MODE_POOL) { if (g_nchw) LAUNCH3(TY, TG, FV_MODE_POOL, true); else LAUNCH3(TY, TG, FV_MODE_POOL, false); } \
+        else if (mode == FV_MODE_UP) LAUNCH3(TY, TG, FV_MODE_UP, false); \
+        else { if (g_nchw) LAUNCH3(TY, TG, FV_MODE_NONE, true); else LAUNCH3(TY, TG, FV_MODE_NONE, false); } } while (0)
+    if (y_dtype == FV_DT_BF16 && g_dtype == FV_DT_BF16) LAUNCH2(__nv_bfloat16, __nv_bfloat16);
+    else if (y_dtype == FV_DT_BF16) LAUNCH2(__nv_bfloat16, float);
+    else if (g_dtype == FV_DT_BF16) LAUNCH2(float, __nv_bfloat16);
+    else LAUNCH2(float, float);
+#undef LAUNCH2
+#undef LAUNCH3
     FV_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
     return FV_OK;
 }
@@ -761,13 +829,22 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_apply(const 
     if (C % 8 || 256 % (C / 8)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: C=%d must be 8 * (a divisor of 256)", C);
     if ((long long)N * H * W * (C / 8) >= (1LL << 31)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: tensor too large for 32-bit indexing");
     if (g_nchw && (g_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: NCHW g is fp32, no upsample");
-    const int grid = grid_for((long long)N * H * W * (C / 8));
-#define LAUNCH(TY, TG) bn_act_bwd_apply_kernel<TY, TG><<<grid, kThreads, 0, STREAM>>>((const TY*)y, (const TG*)g, stat, coef, (const __nv_bfloat16*)add, (__nv_bfloat16*)dy, N, H, W, C, mode, act, g_nchw)
-    if (y_dtype == FV_DT_BF16 && g_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
-    else if (y_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, float);
-    else if (g_dtype == FV_DT_BF16) LAUNCH(float, __nv_bfloat16);
-    else LAUNCH(float, float);
-#undef LAUNCH
+    if (int e = check_c8("fv_bn_act_bwd_apply", C)) return e;
+    int grid; size_t sh_unused;
+    reduce_geometry(C, (long long)N * H * W, grid, sh_unused);
+#define LAUNCH4(TY, TG, M, GNF, AD) bn_act_bwd_apply_kernel<TY, TG, M, GNF, AD><<<grid, kThreads, 0, STREAM>>>((const TY*)y, (const TG*)g, stat, coef, (const __nv_bfloat16*)add, (__nv_bfloat16*)dy, N, H, W, C, act)
+#define LAUNCH3(TY, TG, M, GNF) do { if (add) LAUNCH4(TY, TG, M, GNF, true); else LAUNCH4(TY, TG, M, GNF, false); } while (0)
+#define LAUNCH2(TY, TG) do { \
+        if (mode == FV_MODE_POOL) { if (g_nchw) LAUNCH3(TY, TG, FV_MODE_POOL, true); else LAUNCH3(TY, TG, FV_MODE_POOL, false); } \
+        else if (mode == FV_MODE_UP) LAUNCH3(TY, TG, FV_MODE_UP, false); \
+        else { if (g_nchw) LAUNCH3(TY, TG, FV_MODE_NONE, true); else LAUNCH3(TY, TG, FV_MODE_NONE, false); } } while (0)
+    if (y_dtype == FV_DT_BF16 && g_dtype == FV_DT_BF16) LAUNCH2(__nv_bfloat16, __nv_bfloat16);
+    else if (y_dtype == FV_DT_BF16) LAUNCH2(__nv_bfloat16, float);
+    else if (g_dtype == FV_DT_BF16) LAUNCH2(float, __nv_bfloat16);
+    else LAUNCH2(float, float);
+#undef LAUNCH2
+#undef LAUNCH3
+#undef LAUNCH4
     FV_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
     return FV_OK;
 }

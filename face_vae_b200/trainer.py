@@ -88,7 +88,10 @@ class VAETrainer:
         self._static_eps = eps.clone()
         # warm-up on a side stream (lazy initialisation, allocator pools) without changing the training state
         snap_model = copy.deepcopy(self.vae.state_dict())
-        snap_opt = copy.deepcopy(self.optimizer.state_dict())
+        # optimizer state must EXIST before capture (tensors created inside the capture would be re-initialised by every
+        # replay), so it is restored in place afterwards: copied back if there was state, zeroed if there was none
+        snap_opt = {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                    for p, st in self.optimizer.state.items()}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -97,7 +100,13 @@ class VAETrainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.vae.load_state_dict(snap_model)
-        self.optimizer.load_state_dict(snap_opt)
+        for p, st in self.optimizer.state.items():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    if p in snap_opt and k in snap_opt[p]:
+                        v.copy_(snap_opt[p][k])
+                    else:
+                        v.zero_()
         graph = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
         l0 = _lib.launch_count
