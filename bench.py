@@ -174,14 +174,16 @@ def main():
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end to end: pinned host -> device copy of each batch and device -> host read of the loss inside the region
+    from face_vae_b200.data import AsyncScalarLog, DevicePrefetcher
     barrier()
     t0 = time.perf_counter()
-    last = 0.0
-    for i in range(args.steps):
-        hx, he = host[i % 2]
-        x, e = hx.cuda(non_blocking=True), he.cuda(non_blocking=True)
+    log = AsyncScalarLog(args.steps)
+    # every step: its batch comes from pinned host memory (copy overlapped with the previous step on a side stream)
+    # and its loss goes back to the host (asynchronous copy into pinned memory, read after the loop)
+    for x, e in DevicePrefetcher(host[i % 2] for i in range(args.steps)):
         losses, _ = trainer.step(x, e)
-        last = float(torch.stack([v.detach() for v in losses.values()]).sum().item())
+        log.push(torch.stack([v.detach() for v in losses.values()]).sum())
+    last = float(log.values()[-1])
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:

@@ -139,8 +139,9 @@ class GradientReducer:
             self.stream.wait_stream(cur)
             with torch.cuda.stream(self.stream):
                 flat = torch.cat([g.reshape(-1) for g in grads])
-                for g in grads:
-                    g.record_stream(self.stream)
+                if not torch.cuda.is_current_stream_capturing():
+                    for g in grads:
+                        g.record_stream(self.stream)
                 work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
         else:   # gloo (CPU tests): no AVG, no streams
             flat = torch.cat([g.reshape(-1) for g in grads])

@@ -56,8 +56,10 @@ class VAETrainer:
         on_cuda = bool(params) and params[0].is_cuda
         world = fdist.get_world_size()
         if use_cuda_graph is None:
-            use_cuda_graph = on_cuda and world == 1 and os.environ.get("FACEVAE_CUDA_GRAPH", "1") != "0"
-        self.use_cuda_graph = bool(use_cuda_graph) and on_cuda and world == 1
+            use_cuda_graph = on_cuda and os.environ.get("FACEVAE_CUDA_GRAPH", "1") != "0"
+            if world > 1:   # capturing the NCCL collectives (SyncBN statistics, gradient buckets) is opt-out as well
+                use_cuda_graph = use_cuda_graph and os.environ.get("FACEVAE_CUDA_GRAPH_DDP", "1") != "0"
+        self.use_cuda_graph = bool(use_cuda_graph) and on_cuda
         kw = {}
         if fused_adam and on_cuda:
             kw["fused"] = True
@@ -114,6 +116,8 @@ class VAETrainer:
             losses, generated, _, _ = self.g_full(self._static_d, self._static_eps, True)
             total = sum(losses.values())
             total.backward()
+            if self.reducer is not None:
+                self.reducer.finish()
             self.optimizer.step()
         self.launches_per_step = _lib.launch_count - l0
         self._graph, self._static_out = graph, (losses, generated)
