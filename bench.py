@@ -261,8 +261,17 @@ def main():
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
+        # captured NCCL collectives must be released before the communicator goes away; leave without running the
+        # interpreter's teardown (a CUDA graph holding NCCL kernels can block process-group destruction)
+        trainer._graph = None
+        trainer._static_out = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
