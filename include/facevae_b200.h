@@ -102,6 +102,11 @@ int fv_recon_loss_flat(const float* a, const float* b, float* grad, float* loss_
 /* out = in * scale * (*scale_ptr) (scale_ptr may be NULL); n elements, n % 8 == 0. */
 int fv_scale(const void* in, void* out, int dtype, long long n, const float* scale_ptr, float scale, void* stream);
 
+/* ---- calibration (not on the product path) ---------------------------------------------------------------- */
+/* cycles for `iters` back-to-back tcgen05.mma (M=128, K=16, N=n_cols) on shared-memory-resident operands. */
+int fv_debug_mma_rate(int n_cols, int row_bytes, int iters, int a_distinct, int mn_major, int all_sms, long long* out_cycles_dev,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif
