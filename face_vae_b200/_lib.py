@@ -42,6 +42,7 @@ SIGNATURES = {
     "fv_recon_loss_flat": [_p, _p, _p, _p, _ll, _i, _f, _p],
     "fv_scale": [_p, _p, _i, _ll, _p, _f, _p],
     "fv_debug_mma_rate": [_i, _i, _i, _i, _i, _i, _p, _p],
+    "fv_debug_trace_set": [_p],
 }
 _STR = ("fv_last_error", "fv_version")
 

@@ -31,6 +31,7 @@ struct RingParams {
     int out_mode, tmem_cols;
     const float* bias;
     void* out;
+    long long* trace;
 };
 
 static constexpr int kRingThreads = 192;
@@ -56,6 +57,9 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);              // [Co_pad]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef FV_TRACE
+    long long* fv_trace = p.trace;
+#endif
     const int t0 = blockIdx.x * p.tiles_per_cta;
     const int t1 = min(t0 + p.tiles_per_cta, p.num_tiles);
 
@@ -98,7 +102,7 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int t = t0; t < t1; ++t) {
                 const int n = col / p.tiles_w, w0 = (col - n * p.tiles_w) * 128;
                 for (int j = fresh ? 0 : p.R - 1; j < p.R; ++j) {
-                    mbar_wait(&empty[slot], ph ^ 1);
+                    { FV_T0(tw); mbar_wait(&empty[slot], ph ^ 1); FV_TACC(0, tw); }
                     if (leader) {
                         mbar_arrive_expect_tx(&full[slot], (uint32_t)p.slab_tx);
                         tma_load_4d(smem + (size_t)slot * p.slab_stride, &tmX, &full[slot], 0, w0 - p.pad, h + j - p.pad, n);
@@ -123,15 +127,19 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             uint32_t first = 0, wait_slot = 0, wait_ph = 0, tcount = 0;
             int h = t0 % p.H;
             bool fresh = true;
+            FV_T0(t_all);
             for (int t = t0; t < t1; ++t, ++tcount) {
                 const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-                mbar_wait(&tempty[acc], aph ^ 1);
+                { FV_T0(tw); mbar_wait(&tempty[acc], aph ^ 1); FV_TACC(2, tw); }
                 const int n_new = fresh ? p.R : 1;
+                { FV_T0(tw);
                 for (int i = 0; i < n_new; ++i) {                 // the new slabs of this tile have landed?
                     mbar_wait(&full[wait_slot], wait_ph);
                     if (++wait_slot == (uint32_t)p.ring) { wait_slot = 0; wait_ph ^= 1; }
                 }
+                FV_TACC(3, tw); }
                 tc_fence_after();
+                FV_T0(t_issue);
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co_pad;
                 uint32_t accumulate = 0, slot = first, wtap = w_base;
                 for (int r = 0; r < p.R; ++r) {
@@ -149,6 +157,7 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     }
                     if (++slot == (uint32_t)p.ring) slot = 0;
                 }
+                FV_TACC(4, t_issue);
                 if (leader) tc_commit(&tfull[acc]);
                 // release the slabs the next tile will not read: one when it continues this column, all R otherwise
                 const bool next_fresh = (h + 1 == p.H);
@@ -160,6 +169,7 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 fresh = next_fresh;
                 if (++h == p.H) h = 0;
             }
+            FV_TACC(5, t_all);
         }
     } else {
         const int q = warp & 3;
@@ -182,8 +192,9 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 if (warp == 2 && lane == 0) tma_store_wait_read<1>();
                 named_bar_sync(EPI_BAR, 128);
             }
-            mbar_wait(&tfull[acc], aph);
+            { FV_T0(tw); mbar_wait(&tfull[acc], aph); if (warp == 2) FV_TACC(6, tw); }
             tc_fence_after();
+            FV_T0(t_epi);
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * (uint32_t)p.Co_pad;
             for (int c0 = 0; c0 < p.Co_pad; c0 += 16) {
                 uint32_t v[16];
@@ -227,6 +238,7 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     tma_store_commit();
                 }
             }
+            if (warp == 2) FV_TACC(7, t_epi);
             if (++h == p.H) { h = 0; ++col; }
         }
         if (use_tma_store && warp == 2 && lane == 0) tma_store_wait_all<0>();
@@ -285,6 +297,7 @@ int conv2d_ring_try(const void* x, const void* w, const float* bias, const void*
     p.out_mode = out_mode;
     p.bias = bias;
     p.out = y;
+    p.trace = trace_ptr();
     const int sms = num_sms();
     p.tiles_per_cta = (p.num_tiles + sms - 1) / sms;
     const int grid = (p.num_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;

@@ -5,6 +5,8 @@
 #include "fv_ptx.cuh"
 
 namespace fv {
+static long long* g_trace_dev = nullptr;      // device buffer of 148*8 counters registered by the caller (debug builds)
+long long* trace_ptr() { return g_trace_dev; }
 
 __global__ void __launch_bounds__(128, 1)
 mma_rate_kernel(int n_cols, int row_bytes, int iters, int a_distinct, int mn_major, long long* out_cycles) {
@@ -67,4 +69,14 @@ extern "C" __attribute__((visibility("default"))) int fv_debug_mma_rate(int n_co
     mma_rate_kernel<<<all_sms ? num_sms() : 1, 128, 98 * 1024, (cudaStream_t)stream>>>(n_cols, row_bytes, iters, a_distinct, mn_major, out_cycles_dev);
     FV_LAUNCH_CHECK("mma_rate_kernel");
     return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_debug_trace_set(long long* dev_counters) {
+#ifdef FV_TRACE
+    fv::g_trace_dev = dev_counters;
+    return 0;
+#else
+    (void)dev_counters;
+    return fv::fail(fv::FV_ERR_UNSUPPORTED, "library built without FV_TRACE");
+#endif
 }

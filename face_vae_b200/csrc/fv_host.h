@@ -24,6 +24,7 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 int num_sms();
+long long* trace_ptr();   // fv_debug.cu: device counters for FV_TRACE builds (null otherwise)
 // rank <= 5; dims innermost first; strides_bytes[i] = byte stride of dim i+1; box per dim; swizzle 0/32/64/128.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, int swizzle_bytes);

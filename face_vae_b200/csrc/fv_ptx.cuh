@@ -194,6 +194,16 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a
            (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ------------------------------------------------------------------ optional role-loop timing (debug builds of the ring kernels)
+#ifdef FV_TRACE
+// `fv_trace` (long long*, 148*8 counters in global memory, may be null) must be in scope where the macros are used
+#define FV_T0(var) const long long var = clock64()
+#define FV_TACC(slot, var) do { if (fv_trace && threadIdx.x % 32 == 0) fv_trace[(blockIdx.x % 148) * 8 + (slot)] += clock64() - (var); } while (0)
+#else
+#define FV_T0(var)
+#define FV_TACC(slot, var)
+#endif
+
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

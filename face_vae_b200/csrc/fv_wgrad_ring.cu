@@ -27,6 +27,7 @@ struct WRingParams {
     int b_off, b_slots, b_stride, b_tx;
     int bar_off, tmem_cols;
     float* dw;
+    long long* trace;
 };
 
 static constexpr int kWRingThreads = 192;
@@ -48,6 +49,9 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef FV_TRACE
+    long long* fv_trace = p.trace;
+#endif
     const int b0 = blockIdx.x * p.blocks_per_cta;
     const int b1 = min(b0 + p.blocks_per_cta, p.num_blocks);
     const int brow = p.Co_pad * 2;                                     // bytes per pixel row of the dY tile
@@ -84,14 +88,14 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             bool fresh = true;
             for (int b = b0; b < b1; ++b) {
                 const int n = col / p.cols_w, w0 = (col - n * p.cols_w) * kPX;
-                mbar_wait(&bempty[bs], bph ^ 1);
+                { FV_T0(tw); mbar_wait(&bempty[bs], bph ^ 1); FV_TACC(0, tw); }
                 if (leader) {
                     mbar_arrive_expect_tx(&bfull[bs], (uint32_t)p.b_tx);
                     tma_load_4d(smem + p.b_off + (size_t)bs * p.b_stride, &tmDY, &bfull[bs], 0, w0, h, n);
                 }
                 if (++bs == (uint32_t)p.b_slots) { bs = 0; bph ^= 1; }
                 for (int j = fresh ? 0 : p.R - 1; j < p.R; ++j) {
-                    mbar_wait(&empty[slot], ph ^ 1);
+                    { FV_T0(tw); mbar_wait(&empty[slot], ph ^ 1); FV_TACC(1, tw); }
                     if (leader) {
                         mbar_arrive_expect_tx(&full[slot], (uint32_t)p.slab_tx);
                         tma_load_4d(smem + (size_t)slot * p.slab_stride, &tmX, &full[slot], 0, w0 - p.pad, h + j - p.pad, n);
@@ -117,14 +121,18 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             uint32_t first = 0, wait_slot = 0, wait_ph = 0, bs = 0, bph = 0, accumulate = 0;
             int h = b0 % p.H;
             bool fresh = true;
+            FV_T0(t_all);
             for (int b = b0; b < b1; ++b) {
                 const int n_new = fresh ? p.R : 1;
+                { FV_T0(tw);
                 for (int i = 0; i < n_new; ++i) {
                     mbar_wait(&full[wait_slot], wait_ph);
                     if (++wait_slot == (uint32_t)p.ring) { wait_slot = 0; wait_ph ^= 1; }
                 }
-                mbar_wait(&bfull[bs], bph);
+                FV_TACC(2, tw); }
+                { FV_T0(tw); mbar_wait(&bfull[bs], bph); FV_TACC(3, tw); }
                 tc_fence_after();
+                FV_T0(t_issue);
                 const uint32_t b_lo = b_lo_base | ((smem_base + (uint32_t)p.b_off + bs * (uint32_t)p.b_stride) >> 4);
                 uint32_t slot = first, d_col = tmem_base;
                 for (int r = 0; r < p.R; ++r) {
@@ -140,6 +148,7 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     if (++slot == (uint32_t)p.ring) slot = 0;
                 }
                 accumulate = 1;
+                FV_TACC(4, t_issue);
                 if (leader) tc_commit(&bempty[bs]);
                 if (++bs == (uint32_t)p.b_slots) { bs = 0; bph ^= 1; }
                 const bool next_fresh = (h + 1 == p.H);
@@ -152,6 +161,7 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 if (++h == p.H) h = 0;
             }
             if (leader) tc_commit(tfull);
+            FV_TACC(5, t_all);
         }
     } else if (b0 < b1) {
         const int q = warp & 3;
@@ -159,6 +169,7 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         const int chunk = row / CW, ci = row % CW;
         mbar_wait(tfull, 0);
         tc_fence_after();
+        FV_T0(t_epi);
         const size_t co_stride = (size_t)p.taps * p.Ci;
         int mt = 0;
         for (int r = 0; r < p.R; ++r)
@@ -177,6 +188,7 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     }
                 }
             }
+        if (warp == 2) FV_TACC(6, t_epi);
     }
     tc_fence_before();
     __syncthreads();
@@ -228,6 +240,7 @@ int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, i
     while (cols < p.mt_total * Co_pad) cols <<= 1;
     p.tmem_cols = cols;
     p.dw = dw_acc;
+    p.trace = trace_ptr();
     const int sms = num_sms();
     p.blocks_per_cta = (p.num_blocks + sms - 1) / sms;
     const int grid = (p.num_blocks + p.blocks_per_cta - 1) / p.blocks_per_cta;

@@ -107,6 +107,10 @@ int fv_scale(const void* in, void* out, int dtype, long long n, const float* sca
 int fv_debug_mma_rate(int n_cols, int row_bytes, int iters, int a_distinct, int mn_major, int all_sms, long long* out_cycles_dev,
                       void* stream);
 
+/* role-loop cycle counters of the ring kernels: registers a device buffer of 148*8 int64 counters (libraries built with
+ * -DFV_TRACE only; NULL switches tracing off). */
+int fv_debug_trace_set(long long* dev_counters);
+
 #ifdef __cplusplus
 }
 #endif
