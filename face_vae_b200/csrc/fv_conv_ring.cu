@@ -196,47 +196,66 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             tc_fence_after();
             FV_T0(t_epi);
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * (uint32_t)p.Co_pad;
-            for (int c0 = 0; c0 < p.Co_pad; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + c0, v);
+            if (use_tma_store) {
+                // fast path (NHWC bf16, Co_pad <= 64): pull the whole accumulator row into registers with back-to-back
+                // TMEM loads and ONE wait, hand the accumulator back to the issuer immediately, then convert and stage
+                const int nc = p.Co_pad >> 4;
+                uint32_t v[4][16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < nc) tmem_ld16(taddr + c * 16, v[c]);
                 tmem_ld_wait();
-                float f[16];
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                uint8_t* srow = stage + row * out_row;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias_s[c0 + i];
-                if (p.out_mode == FV_OUT_NCHW_F32) {
-                    float* o = reinterpret_cast<float*>(p.out);
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nc) {
+                        float f[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < p.Co) o[(((size_t)n * p.Co + c0 + i) * p.H + h) * p.W + w0 + row] = f[i];
-                } else if (use_tma_store) {
-                    const int j0 = c0 >> 3;              // first 16-byte chunk of this column group
-                    uint4* s0 = reinterpret_cast<uint4*>(stage + row * out_row + (((j0) ^ sw) << 4));
-                    uint4* s1 = reinterpret_cast<uint4*>(stage + row * out_row + (((j0 + 1) ^ sw) << 4));
-                    *s0 = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                    *s1 = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
-                } else {
-                    const size_t pix = ((size_t)n * p.H + h) * p.W + w0 + row;
-                    if (p.out_mode == FV_OUT_NHWC_BF16) {
-                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Co_pad + c0);
-                        o[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                        o[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
-                    } else {
-                        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Co_pad + c0);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[c][i]) + bias_s[c * 16 + i];
+                        *reinterpret_cast<uint4*>(srow + (((2 * c) ^ sw) << 4)) =
+                            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                        *reinterpret_cast<uint4*>(srow + (((2 * c + 1) ^ sw) << 4)) =
+                            make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
                     }
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);     // accumulator drained: the issuer may start tile t + 2
-            if (use_tma_store) {
                 fence_proxy_async();                       // make the staging writes visible to the TMA unit
                 named_bar_sync(EPI_BAR, 128);
                 if (warp == 2 && lane == 0) {
                     tma_store_4d(&tmY, stage, 0, w0, h, n);
                     tma_store_commit();
                 }
+            } else {
+                for (int c0 = 0; c0 < p.Co_pad; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + c0, v);
+                    tmem_ld_wait();
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias_s[c0 + i];
+                    if (p.out_mode == FV_OUT_NCHW_F32) {
+                        float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < p.Co) o[(((size_t)n * p.Co + c0 + i) * p.H + h) * p.W + w0 + row] = f[i];
+                    } else {
+                        const size_t pix = ((size_t)n * p.H + h) * p.W + w0 + row;
+                        if (p.out_mode == FV_OUT_NHWC_BF16) {
+                            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Co_pad + c0);
+                            o[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                            o[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                        } else {
+                            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Co_pad + c0);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);     // accumulator drained: the issuer may start tile t + 2
             }
             if (warp == 2) FV_TACC(7, t_epi);
             if (++h == p.H) { h = 0; ++col; }

@@ -31,13 +31,15 @@ struct WRingParams {
 };
 
 static constexpr int kWRingThreads = 192;
-static constexpr int kPX = 64;            // pixels (GEMM K) per block
 
-template <int CW>                          // channels per A chunk == Ci (16 / 32 / 64)
+// CW: channels per A chunk == Ci (16 / 32 / 64); S_: filter size (R == S); kPX: pixels (GEMM K) per block
+template <int CW, int S_, int kPX>
 __global__ void __launch_bounds__(kWRingThreads, 1)
 conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WRingParams p) {
     constexpr int AROW = CW * 2;                                   // bytes per pixel row of the activation slab
     constexpr uint32_t A_LAYOUT = AROW == 128 ? 2u : (AROW == 64 ? 4u : 6u);
+    constexpr int CPT = 128 / CW;                                  // taps stacked in one 128-row M tile
+    constexpr int TPR = (S_ + CPT - 1) / CPT;                      // M tiles per filter row
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -134,16 +136,18 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 tc_fence_after();
                 FV_T0(t_issue);
                 const uint32_t b_lo = b_lo_base | ((smem_base + (uint32_t)p.b_off + bs * (uint32_t)p.b_stride) >> 4);
-                uint32_t slot = first, d_col = tmem_base;
-                for (int r = 0; r < p.R; ++r) {
+                uint32_t slot = first;
+#pragma unroll
+                for (int r = 0; r < S_; ++r) {
                     const uint32_t a_row = a_lo_base | ((smem_base + slot * (uint32_t)p.slab_stride) >> 4);
-                    for (int part = 0; part < p.tiles_per_r; ++part, d_col += (uint32_t)p.Co_pad) {
-                        const uint32_t a_lo = a_row + (uint32_t)(part * p.cpt) * (AROW >> 4);   // first tap of this M tile
+#pragma unroll
+                    for (int part = 0; part < TPR; ++part) {
+                        const uint32_t d_col = tmem_base + (uint32_t)((r * TPR + part) * p.Co_pad);
 #pragma unroll
                         for (int k4 = 0; k4 < kPX / 16; ++k4)
                             if (leader)
-                                tc_mma_f16_lohi2(d_col, a_lo + k4 * a_kstep, a_hi, b_lo + k4 * b_kstep, b_hi, idesc,
-                                                 accumulate | (uint32_t)(k4 > 0));
+                                tc_mma_f16_lohi2(d_col, a_row + (uint32_t)(part * CPT * (AROW >> 4)) + k4 * a_kstep, a_hi, b_lo + k4 * b_kstep,
+                                                 b_hi, idesc, accumulate | (uint32_t)(k4 > 0));
                     }
                     if (++slot == (uint32_t)p.ring) slot = 0;
                 }
@@ -198,14 +202,14 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     }
 }
 
-template <int CW>
+template <int CW, int S_, int kPX>
 static int launch_wring(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WRingParams& p, size_t smem, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        FV_CUDA(cudaFuncSetAttribute(conv_wgrad_ring_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FV_CUDA(cudaFuncSetAttribute(conv_wgrad_ring_kernel<CW, S_, kPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    conv_wgrad_ring_kernel<CW><<<grid, kWRingThreads, smem, stream>>>(tmX, tmDY, p);
+    conv_wgrad_ring_kernel<CW, S_, kPX><<<grid, kWRingThreads, smem, stream>>>(tmX, tmDY, p);
     FV_LAUNCH_CHECK("conv_wgrad_ring_kernel");
     return FV_OK;
 }
@@ -213,7 +217,8 @@ static int launch_wring(const CUtensorMap& tmX, const CUtensorMap& tmDY, const W
 // FV_OK after launching, -1 when not eligible (caller falls through to the generic wgrad kernel).
 int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
                           cudaStream_t stream) {
-    if (S < 2 || W % kPX || Ci > 64 || Co_pad > 64) return -1;
+    if ((S != 3 && S != 5 && S != 7) || R != S || W % 64 || Ci > 64 || Co_pad > 64) return -1;
+    const int kPX = (W % 128 == 0) ? 128 : 64;
     const char* env = getenv("FV_WGRAD_RING");
     if (env && atoi(env) == 0) return -1;
     WRingParams p{};
@@ -258,9 +263,13 @@ int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, i
         uint32_t box[4] = {(uint32_t)Co_pad, (uint32_t)kPX, 1, 1};
         if (int e = encode_tmap_bf16(&tmDY, dy, 4, dims, str, box, brow)) return e;
     }
-    if (Ci == 64) return launch_wring<64>(tmX, tmDY, p, smem, grid, stream);
-    if (Ci == 32) return launch_wring<32>(tmX, tmDY, p, smem, grid, stream);
-    return launch_wring<16>(tmX, tmDY, p, smem, grid, stream);
+#define FV_WR2(CW_, S__) (kPX == 128 ? launch_wring<CW_, S__, 128>(tmX, tmDY, p, smem, grid, stream) : launch_wring<CW_, S__, 64>(tmX, tmDY, p, smem, grid, stream))
+#define FV_WR(CW_) (S == 3 ? FV_WR2(CW_, 3) : (S == 5 ? FV_WR2(CW_, 5) : FV_WR2(CW_, 7)))
+    if (Ci == 64) return FV_WR(64);
+    if (Ci == 32) return FV_WR(32);
+    return FV_WR(16);
+#undef FV_WR
+#undef FV_WR2
 }
 
 }  // namespace fv
