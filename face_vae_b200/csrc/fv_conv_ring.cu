@@ -128,21 +128,28 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             int h = t0 % p.H;
             bool fresh = true;
             FV_T0(t_all);
-            for (int t = t0; t < t1; ++t, ++tcount) {
-                const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-                { FV_T0(tw); mbar_wait(&tempty[acc], aph ^ 1); FV_TACC(2, tw); }
-                const int n_new = fresh ? p.R : 1;
-                { FV_T0(tw);
-                for (int i = 0; i < n_new; ++i) {                 // the new slabs of this tile have landed?
+            // barrier waits of tile t + 1 are taken in the MIDDLE of tile t's MMAs: a completed mbarrier still costs
+            // ~150-250 cycles to observe, and the tensor pipe would otherwise drain while the issuer polls
+            auto wait_tile = [&](uint32_t tc, bool is_fresh) {
+                { FV_T0(tw); mbar_wait(&tempty[tc & 1], ((tc >> 1) & 1) ^ 1); FV_TACC(2, tw); }
+                const int n_new = is_fresh ? p.R : 1;
+                FV_T0(tw2);
+                for (int i = 0; i < n_new; ++i) {                 // the new slabs of that tile have landed?
                     mbar_wait(&full[wait_slot], wait_ph);
                     if (++wait_slot == (uint32_t)p.ring) { wait_slot = 0; wait_ph ^= 1; }
                 }
-                FV_TACC(3, tw); }
+                FV_TACC(3, tw2);
+            };
+            wait_tile(0, true);
+            for (int t = t0; t < t1; ++t, ++tcount) {
+                const uint32_t acc = tcount & 1;
+                const bool next_fresh = (h + 1 == p.H);
                 tc_fence_after();
                 FV_T0(t_issue);
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co_pad;
                 uint32_t accumulate = 0, slot = first, wtap = w_base;
-                for (int r = 0; r < p.R; ++r) {
+#pragma unroll
+                for (int r = 0; r < S_; ++r) {
                     const uint32_t a_row = ((smem_base + slot * (uint32_t)p.slab_stride) >> 4) | LBO_LO;
 #pragma unroll
                     for (int s = 0; s < S_; ++s) {                                    // tap s == slab shifted by s pixel rows
@@ -156,11 +163,12 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                         wtap += w_step;
                     }
                     if (++slot == (uint32_t)p.ring) slot = 0;
+                    if (r == (S_ - 1) / 2 && t + 1 < t1) wait_tile(tcount + 1, next_fresh);
                 }
                 FV_TACC(4, t_issue);
+                FV_T0(t_commit);
                 if (leader) tc_commit(&tfull[acc]);
                 // release the slabs the next tile will not read: one when it continues this column, all R otherwise
-                const bool next_fresh = (h + 1 == p.H);
                 const int n_rel = (t + 1 < t1) ? (next_fresh ? p.R : 1) : 0;
                 for (int i = 0; i < n_rel; ++i) {
                     if (leader) tc_commit(&empty[first]);
@@ -168,6 +176,7 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 }
                 fresh = next_fresh;
                 if (++h == p.H) h = 0;
+                FV_TACC(1, t_commit);
             }
             FV_TACC(5, t_all);
         }

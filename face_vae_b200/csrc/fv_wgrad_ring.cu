@@ -124,15 +124,24 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             int h = b0 % p.H;
             bool fresh = true;
             FV_T0(t_all);
-            for (int b = b0; b < b1; ++b) {
-                const int n_new = fresh ? p.R : 1;
-                { FV_T0(tw);
+            // the barrier waits of block b + 1 are taken in the middle of block b's MMAs (see fv_conv_ring.cu)
+            uint32_t wbs = 0, wbph = 0;
+            auto wait_block = [&](bool is_fresh) {
+                const int n_new = is_fresh ? p.R : 1;
+                FV_T0(tw);
                 for (int i = 0; i < n_new; ++i) {
                     mbar_wait(&full[wait_slot], wait_ph);
                     if (++wait_slot == (uint32_t)p.ring) { wait_slot = 0; wait_ph ^= 1; }
                 }
-                FV_TACC(2, tw); }
-                { FV_T0(tw); mbar_wait(&bfull[bs], bph); FV_TACC(3, tw); }
+                FV_TACC(2, tw);
+                FV_T0(tw2);
+                mbar_wait(&bfull[wbs], wbph);
+                if (++wbs == (uint32_t)p.b_slots) { wbs = 0; wbph ^= 1; }
+                FV_TACC(3, tw2);
+            };
+            wait_block(true);
+            for (int b = b0; b < b1; ++b) {
+                const bool next_fresh = (h + 1 == p.H);
                 tc_fence_after();
                 FV_T0(t_issue);
                 const uint32_t b_lo = b_lo_base | ((smem_base + (uint32_t)p.b_off + bs * (uint32_t)p.b_stride) >> 4);
@@ -150,12 +159,12 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                                                  b_hi, idesc, accumulate | (uint32_t)(k4 > 0));
                     }
                     if (++slot == (uint32_t)p.ring) slot = 0;
+                    if (r == (S_ - 1) / 2 && b + 1 < b1) wait_block(next_fresh);
                 }
                 accumulate = 1;
                 FV_TACC(4, t_issue);
                 if (leader) tc_commit(&bempty[bs]);
                 if (++bs == (uint32_t)p.b_slots) { bs = 0; bph ^= 1; }
-                const bool next_fresh = (h + 1 == p.H);
                 const int n_rel = (b + 1 < b1) ? (next_fresh ? p.R : 1) : 0;
                 for (int i = 0; i < n_rel; ++i) {
                     if (leader) tc_commit(&empty[first]);

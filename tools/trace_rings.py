@@ -23,7 +23,7 @@ for (ci, co, k) in [(32, 64, 3), (64, 32, 3), (32, 3, 7), (16, 32, 7)]:
     wf, wd = ops.weight_prep(w)
     tiles = n * hw * (hw // 128) / 148
     run(f"fprop ring {ci}->{co} k{k}", lambda: ops.conv2d(x, wf, None, co, k, out_mode=(2 if co == 3 else 0)),
-        ["prod_wait_empty", "", "mma_wait_tempty", "mma_wait_full", "mma_issue", "mma_total", "epi_wait_tfull", "epi_work"], tiles)
+        ["prod_wait_empty", "mma_commit", "mma_wait_tempty", "mma_wait_full", "mma_issue", "mma_total", "epi_wait_tfull", "epi_work"], tiles)
     blocks = n * hw * (hw // 64) / 148
     run(f"wgrad ring {ci}->{co} k{k}", lambda: ops.conv2d_wgrad(x, dy, k),
         ["prod_wait_bempty", "prod_wait_empty", "mma_wait_full", "mma_wait_b", "mma_issue", "mma_total", "epilogue(total)", ""], blocks)
