@@ -140,10 +140,13 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 }
                 FV_TACC(3, tw2);
             };
-            wait_tile(0, true);
+            bool waited = false;
             for (int t = t0; t < t1; ++t, ++tcount) {
                 const uint32_t acc = tcount & 1;
                 const bool next_fresh = (h + 1 == p.H);
+                // a column change needs R fresh slabs, i.e. slots this tile still occupies: that wait cannot be taken early
+                if (!waited) wait_tile(tcount, fresh);
+                waited = false;
                 tc_fence_after();
                 FV_T0(t_issue);
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co_pad;
@@ -163,7 +166,10 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                         wtap += w_step;
                     }
                     if (++slot == (uint32_t)p.ring) slot = 0;
-                    if (r == (S_ - 1) / 2 && t + 1 < t1) wait_tile(tcount + 1, next_fresh);
+                    if (r == (S_ - 1) / 2 && t + 1 < t1 && !next_fresh) {
+                        wait_tile(tcount + 1, false);
+                        waited = true;
+                    }
                 }
                 FV_TACC(4, t_issue);
                 FV_T0(t_commit);

@@ -57,7 +57,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
+        if (++spins > (1u << 22)) {
             printf("fv: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x,
                    (int)threadIdx.x, (void*)bar, parity);
             __trap();

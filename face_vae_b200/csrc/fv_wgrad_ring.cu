@@ -139,9 +139,12 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 if (++wbs == (uint32_t)p.b_slots) { wbs = 0; wbph ^= 1; }
                 FV_TACC(3, tw2);
             };
-            wait_block(true);
+            bool waited = false;
             for (int b = b0; b < b1; ++b) {
                 const bool next_fresh = (h + 1 == p.H);
+                // a column change needs R fresh slabs, i.e. slots this block still occupies: that wait cannot be taken early
+                if (!waited) wait_block(fresh);
+                waited = false;
                 tc_fence_after();
                 FV_T0(t_issue);
                 const uint32_t b_lo = b_lo_base | ((smem_base + (uint32_t)p.b_off + bs * (uint32_t)p.b_stride) >> 4);
@@ -159,7 +162,10 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                                                  b_hi, idesc, accumulate | (uint32_t)(k4 > 0));
                     }
                     if (++slot == (uint32_t)p.ring) slot = 0;
-                    if (r == (S_ - 1) / 2 && b + 1 < b1) wait_block(next_fresh);
+                    if (r == (S_ - 1) / 2 && b + 1 < b1 && !next_fresh) {
+                        wait_block(false);
+                        waited = true;
+                    }
                 }
                 accumulate = 1;
                 FV_TACC(4, t_issue);
