@@ -41,10 +41,12 @@ SIGNATURES = {
     "fv_recon_loss": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
     "fv_recon_loss_flat": [_p, _p, _p, _p, _ll, _i, _f, _p],
     "fv_scale": [_p, _p, _i, _ll, _p, _f, _p],
+    "fv_bn_finalize_xrank": [_p, _p, _i, _i, _p, _i, _d, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i, _i, _p],
     "fv_debug_mma_rate": [_i, _i, _i, _i, _i, _i, _p, _p],
     "fv_debug_trace_set": [_p],
 }
 _STR = ("fv_last_error", "fv_version")
+_LL = ("fv_xrank_buffer_floats",)
 
 _lock = threading.Lock()
 _lib = None
@@ -74,6 +76,9 @@ def load(build_if_missing: bool = True):
             fn.restype = C.c_int
         for name in _STR:
             getattr(lib, name).restype = C.c_char_p
+            getattr(lib, name).argtypes = []
+        for name in _LL:
+            getattr(lib, name).restype = C.c_longlong
             getattr(lib, name).argtypes = []
         _lib = lib
     return _lib

@@ -13,6 +13,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
+from . import xrank
 from .ops import (ACT_LEAKY, ACT_NONE, ACT_RELU, MODE_NONE, MODE_POOL, MODE_UP, OUT_NCHW_F32, OUT_NHWC_BF16,
                   OUT_NHWC_F32, pad_channels)
 
@@ -29,6 +30,16 @@ def _world() -> int:
     if _SYNC_BN and dist.is_available() and dist.is_initialized():
         return dist.get_world_size()
     return 1
+
+
+def _bn_backward_finalize(s_local, count, c, training):
+    """dgamma, dbeta (local sums) and the coupling coefficients (global sums / count)."""
+    if not training:
+        return ops.bn_bwd_finalize(s_local, torch.zeros_like(s_local), count, c)
+    xc = xrank.get() if _world() > 1 else None
+    if xc is not None:
+        return xc.finalize_bwd(s_local, count, c)
+    return ops.bn_bwd_finalize(s_local, _allreduce_sum(s_local), count, c)
 
 
 def _allreduce_sum(t: torch.Tensor) -> torch.Tensor:
@@ -91,8 +102,11 @@ def _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, e
     n, h, w, c = y.shape
     if not training:
         return ops.bn_eval_affine(gamma, beta, running_mean, running_var, eps), n * h * w
-    sums = _allreduce_sum(ops.bn_stats(y))
     count = n * h * w * _world()
+    xc = xrank.get() if _world() > 1 else None
+    if xc is not None:   # one kernel: push partial sums to all peers over NVLink, reduce, finalize
+        return xc.finalize_fwd(ops.bn_stats(y), count, gamma, beta, running_mean, running_var, momentum, eps), count
+    sums = _allreduce_sum(ops.bn_stats(y))
     return ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps), count
 
 
@@ -122,13 +136,9 @@ class ConvBNAct(torch.autograd.Function):
         ksize, post_mode, act, training, out_nchw_f32, count, co, ci = ctx.cfg
         g = g.contiguous()
         c = y.shape[3]
-        if training:
-            s_local = ops.bn_act_bwd_reduce(y, g, stat, post_mode, act, out_nchw_f32)
-            s_global = _allreduce_sum(s_local)
-        else:   # running statistics are constants: dy = scale * dz, no coupling terms
-            s_local = ops.bn_act_bwd_reduce(y, g, stat, post_mode, act, out_nchw_f32)
-            s_global = torch.zeros_like(s_local)
-        dgamma, dbeta, coef = ops.bn_bwd_finalize(s_local, s_global, count, c)
+        # eval mode: running statistics are constants, dy = scale * dz, no coupling terms
+        s_local = ops.bn_act_bwd_reduce(y, g, stat, post_mode, act, out_nchw_f32)
+        dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
         dy = ops.bn_act_bwd_apply(y, g, stat, coef, post_mode, act, None, out_nchw_f32)
         acc = ops.conv2d_wgrad(x, dy, ksize, (ci, co))
         dw = ops.wgrad_finish(acc, co, ci, ksize)
@@ -172,8 +182,7 @@ class BNActConv(torch.autograd.Function):
         da = ops.conv2d(g, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
         c = x.shape[3]
         s_local = ops.bn_act_bwd_reduce(x, da, stat, MODE_NONE, act)
-        s_global = _allreduce_sum(s_local) if training else torch.zeros_like(s_local)
-        dgamma, dbeta, coef = ops.bn_bwd_finalize(s_local, s_global, count, c)
+        dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
         dx = ops.bn_act_bwd_apply(x, da, stat, coef, MODE_NONE, act) if ctx.needs_input_grad[0] else None
         dres = g if ctx.has_res else None
         return dx, dres, dw, db, dgamma, dbeta, None, None, None, None, None, None, None

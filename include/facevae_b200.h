@@ -82,6 +82,17 @@ int fv_bn_bwd_finalize(const float* sums_local, const float* sums_global, double
 int fv_bn_act_bwd_apply(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat, const float* coef,
                         const void* add, void* dy, int N, int H, int W, int C, int mode, int act, void* stream);
 
+/* ---- cross-rank statistic exchange over NVLink peer memory, fused with the finalize kernels ------------------------
+ * Replaces the per-layer all_gather / all_reduce of SyncBatchNorm under DDP (torch/nn/modules/_functions.py:74-83,159;
+ * reference modules.py:19, logger.py:55).  peer_bufs_dev: device array of `world` pointers to the ranks' symmetric
+ * buffers (fv_xrank_buffer_floats() fp32 each, zero-initialised, mapped in every rank); epoch_ctr: device uint64,
+ * zero-initialised, private to the rank.  mode 0: out = stat[4][C] (+ running stats), mode 1: out = coef[2][C] and
+ * dgamma/dbeta from the LOCAL sums.  Every rank must issue the same sequence of calls. */
+long long fv_xrank_buffer_floats(void);
+int fv_bn_finalize_xrank(const float* sums_local, void* peer_bufs_dev, int rank, int world, void* epoch_ctr, int mode, double count,
+                         const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                         float* out, float* dgamma, float* dbeta, int accumulate, int C, void* stream);
+
 /* ---- re-parameterisation (models.py:559-561) fused with KLDivergenceLoss (losses.py:385-393) ------------- */
 /* mu/logstd: fp32 rows of Dz values, row_stride apart; z[N,Dz] = mu + exp(logstd)*eps (NULL eps => z = mu; NULL z =>
  * KL only); kl_rows[N] (caller-zeroed, may be NULL) += sum_d(-0.5 - logstd + 0.5 mu^2 + 0.5 exp(2 logstd)). */
