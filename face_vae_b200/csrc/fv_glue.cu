@@ -357,7 +357,9 @@ __device__ __forceinline__ void row_to_nhw(unsigned r, int H, int W, unsigned& n
     n = t2 / (unsigned)H;
 }
 
-// pass 1: sums[0..C) += sum dz, sums[C..2C) += sum dz * xhat,  dz = g_eff * act'(scale*y+shift), xhat = (y-mean)*invstd
+// pass 1: sums[0..C) += sum dz, sums[C..2C) += sum dz * xhat,  dz = g_eff * act'(scale*y+shift), xhat = (y-mean)*invstd.
+// The loop accumulates sum(dz) and sum(dz*y) only (xhat is affine in y), which keeps the per-thread constants down to
+// scale/shift and lets eight rows of raw 16-byte loads stay in flight.
 template <typename TY, typename TG, int MODE, bool GN>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
@@ -366,16 +368,15 @@ bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, con
     const int tpr = C / 8, rpi = blockDim.x / tpr;
     const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
     const unsigned P = (unsigned)N * H * W;
-    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    float mean[8], invstd[8], sc[8], sf[8];
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float sc[8], sf[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        mean[k] = __ldg(stat + tc * 8 + k);
-        invstd[k] = __ldg(stat + C + tc * 8 + k);
         sc[k] = __ldg(stat + 2 * C + tc * 8 + k);
         sf[k] = __ldg(stat + 3 * C + tc * 8 + k);
     }
-    constexpr int U = MODE == FV_MODE_UP ? 2 : 4;
+    constexpr bool NEED_NHW = (MODE != FV_MODE_NONE) || GN;
+    constexpr int U = MODE == FV_MODE_UP ? 2 : 8;
     const unsigned stride = gridDim.x * rpi;
     unsigned r0 = blockIdx.x * rpi + tr;
     for (; r0 + (U - 1) * stride < P; r0 += U * stride) {
@@ -383,10 +384,10 @@ bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, con
         GLoad<TG, MODE, GN> gl[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {                         // U rows of y and g in flight, 4 registers per 16-byte load
-            unsigned n, h, w;
-            row_to_nhw(r0 + u * stride, H, W, n, h, w);
+            unsigned n = 0, h = 0, w = r0 + u * stride;       // MODE_NONE, NHWC g: the row index is the g index
+            if (NEED_NHW) row_to_nhw(r0 + u * stride, H, W, n, h, w);
             yr[u].load(y + (size_t)(r0 + u * stride) * C + tc * 8);
-            gl[u].issue(g, n, h, w, H, W, C, tc);
+            gl[u].issue(g, n, h, w, NEED_NHW ? H : 1, NEED_NHW ? W : (int)P, C, tc);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -397,7 +398,7 @@ bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, con
             for (int k = 0; k < 8; ++k) {
                 const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
                 s1[k] += dz;
-                s2[k] += dz * (f[k] - mean[k]) * invstd[k];
+                sy[k] = fmaf(dz, f[k], sy[k]);
             }
         }
     }
@@ -413,13 +414,14 @@ bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, con
         for (int k = 0; k < 8; ++k) {
             const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
             s1[k] += dz;
-            s2[k] += dz * (f[k] - mean[k]) * invstd[k];
+            sy[k] = fmaf(dz, f[k], sy[k]);
         }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 8; ++k) {                             // sum dz*xhat = invstd * (sum dz*y - mean * sum dz)
+        const float mean = __ldg(stat + tc * 8 + k), invstd = __ldg(stat + C + tc * 8 + k);
         sh[tr * C + tc * 8 + k] = s1[k];
-        sh[(rpi + tr) * C + tc * 8 + k] = s2[k];
+        sh[(rpi + tr) * C + tc * 8 + k] = invstd * (sy[k] - mean * s1[k]);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
@@ -442,8 +444,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums_local, con
     }
 }
 
-// pass 2: dy = scale * (dz - c1 - xhat * c2) (+ add), written bf16 NHWC: the conv-output gradient fed to dgrad / wgrad.
-// Same thread -> (row, channel group) mapping as pass 1, so the per-channel constants sit in registers.
+// pass 2: dy = scale * (dz - c1 - xhat * c2) (+ add) = scale*dz + A + B*y with per-channel A = scale*(c2*invstd*mean - c1),
+// B = -scale*c2*invstd; written bf16 NHWC: the conv-output gradient fed to dgrad / wgrad.
 template <typename TY, typename TG, int MODE, bool GN, bool ADD>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
@@ -452,18 +454,19 @@ bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, cons
     const int tpr = C / 8, rpi = blockDim.x / tpr;
     const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
     const unsigned P = (unsigned)N * H * W;
-    float mean[8], invstd[8], sc[8], sf[8], c1[8], c2[8];
+    float sc[8], sf[8], ca[8], cb[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int c = tc * 8 + k;
-        mean[k] = __ldg(stat + c);
-        invstd[k] = __ldg(stat + C + c);
+        const float mean = __ldg(stat + c), invstd = __ldg(stat + C + c);
         sc[k] = __ldg(stat + 2 * C + c);
         sf[k] = __ldg(stat + 3 * C + c);
-        c1[k] = __ldg(coef + c);
-        c2[k] = __ldg(coef + C + c);
+        const float c1 = __ldg(coef + c), c2 = __ldg(coef + C + c);
+        ca[k] = sc[k] * (c2 * invstd * mean - c1);
+        cb[k] = -sc[k] * c2 * invstd;
     }
-    constexpr int U = MODE == FV_MODE_UP ? 2 : 4;
+    constexpr bool NEED_NHW = (MODE != FV_MODE_NONE) || GN;
+    constexpr int U = MODE == FV_MODE_UP ? 2 : (ADD ? 4 : 6);
     const unsigned stride = gridDim.x * rpi;
     unsigned r0 = blockIdx.x * rpi + tr;
     for (; r0 + (U - 1) * stride < P; r0 += U * stride) {
@@ -472,10 +475,10 @@ bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, cons
         Raw8<__nv_bfloat16> ar[ADD ? U : 1];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            unsigned n, h, w;
-            row_to_nhw(r0 + u * stride, H, W, n, h, w);
+            unsigned n = 0, h = 0, w = r0 + u * stride;
+            if (NEED_NHW) row_to_nhw(r0 + u * stride, H, W, n, h, w);
             yr[u].load(y + (size_t)(r0 + u * stride) * C + tc * 8);
-            gl[u].issue(g, n, h, w, H, W, C, tc);
+            gl[u].issue(g, n, h, w, NEED_NHW ? H : 1, NEED_NHW ? W : (int)P, C, tc);
             if (ADD) ar[ADD ? u : 0].load(add + (size_t)(r0 + u * stride) * C + tc * 8);
         }
 #pragma unroll
@@ -487,8 +490,7 @@ bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, cons
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
-                const float xhat = (f[k] - mean[k]) * invstd[k];
-                o[k] = sc[k] * (dz - c1[k] - xhat * c2[k]);
+                o[k] = fmaf(sc[k], dz, fmaf(cb[k], f[k], ca[k]));
                 if (ADD) o[k] += a[k];
             }
             V8<__nv_bfloat16>::store(dy + (size_t)(r0 + u * stride) * C + tc * 8, o);
@@ -506,8 +508,7 @@ bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, cons
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
-            const float xhat = (f[k] - mean[k]) * invstd[k];
-            o[k] = sc[k] * (dz - c1[k] - xhat * c2[k]);
+            o[k] = fmaf(sc[k], dz, fmaf(cb[k], f[k], ca[k]));
             if (ADD) o[k] += a[k];
         }
         V8<__nv_bfloat16>::store(dy + (size_t)r0 * C + tc * 8, o);

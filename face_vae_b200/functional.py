@@ -121,18 +121,19 @@ class ConvBNAct(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, ksize, post_mode, act, training,
                 out_nchw_f32, momentum, eps):
         co, ci = weight.shape[0], weight.shape[1]
-        wf, _ = ops.weight_prep(weight, True, False)
+        # both filter operands come from one pass over the fp32 master weights (the rotated copy is kept for backward)
+        wf, wd = ops.weight_prep(weight, True, x.requires_grad)
         y = ops.conv2d(x, wf, bias, co, ksize, None, OUT_NHWC_BF16, (ci, co))
         stat, count = _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, eps)
         out = ops.bn_act_fwd(y, stat, post_mode, act, torch.float32 if out_nchw_f32 else torch.bfloat16, out_nchw_f32)
-        ctx.save_for_backward(x, y, stat, weight)
+        ctx.save_for_backward(x, y, stat, weight, wd)
         ctx.cfg = (ksize, post_mode, act, training, out_nchw_f32, count, co, ci)
         ctx.has_bias = bias is not None
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, y, stat, weight = ctx.saved_tensors
+        x, y, stat, weight, wd = ctx.saved_tensors
         ksize, post_mode, act, training, out_nchw_f32, count, co, ci = ctx.cfg
         g = g.contiguous()
         c = y.shape[3]
@@ -148,7 +149,8 @@ class ConvBNAct(torch.autograd.Function):
             db = torch.zeros((co,), device=x.device, dtype=torch.float32) if training else ops.colsum(dy)[:co].clone()
         dx = None
         if ctx.needs_input_grad[0]:
-            _, wd = ops.weight_prep(weight, False, True)
+            if wd is None:
+                _, wd = ops.weight_prep(weight, False, True)
             dx = ops.conv2d(dy, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
         return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
@@ -162,9 +164,9 @@ class BNActConv(torch.autograd.Function):
         co, ci = weight.shape[0], weight.shape[1]
         stat, count = _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps)
         a = ops.bn_act_fwd(x, stat, MODE_NONE, act, torch.bfloat16)
-        wf, _ = ops.weight_prep(weight, True, False)
+        wf, wd = ops.weight_prep(weight, True, True)
         y = ops.conv2d(a, wf, bias, co, ksize, residual, OUT_NHWC_BF16, (ci, co))
-        ctx.save_for_backward(x, a, stat, weight)
+        ctx.save_for_backward(x, a, stat, weight, wd)
         ctx.cfg = (ksize, act, training, count, co, ci)
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
@@ -172,13 +174,12 @@ class BNActConv(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        x, a, stat, weight = ctx.saved_tensors
+        x, a, stat, weight, wd = ctx.saved_tensors
         ksize, act, training, count, co, ci = ctx.cfg
         g = g.contiguous()
         db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
         acc = ops.conv2d_wgrad(a, g, ksize, (ci, co))
         dw = ops.wgrad_finish(acc, co, ci, ksize)
-        _, wd = ops.weight_prep(weight, False, True)
         da = ops.conv2d(g, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
         c = x.shape[3]
         s_local = ops.bn_act_bwd_reduce(x, da, stat, MODE_NONE, act)
@@ -194,16 +195,16 @@ class ConvOnly(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, ksize, out_mode):
         co, ci = weight.shape[0], weight.shape[1]
-        wf, _ = ops.weight_prep(weight, True, False)
+        wf, wd = ops.weight_prep(weight, True, x.requires_grad)
         y = ops.conv2d(x, wf, bias, co, ksize, None, out_mode, (ci, co))
-        ctx.save_for_backward(x, weight)
+        ctx.save_for_backward(x, weight, wd)
         ctx.cfg = (ksize, out_mode, co, ci)
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, g):
-        x, weight = ctx.saved_tensors
+        x, weight, wd = ctx.saved_tensors
         ksize, out_mode, co, ci = ctx.cfg
         if out_mode == OUT_NCHW_F32:
             g = ops.nchw_to_nhwc(g.contiguous().float(), pad_channels(co))
@@ -215,7 +216,8 @@ class ConvOnly(torch.autograd.Function):
         dw = ops.wgrad_finish(acc, co, ci, ksize)
         dx = None
         if ctx.needs_input_grad[0]:
-            _, wd = ops.weight_prep(weight, False, True)
+            if wd is None:
+                _, wd = ops.weight_prep(weight, False, True)
             dx = ops.conv2d(g, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
         return dx, dw, db, None, None
 
@@ -315,11 +317,11 @@ class ConvSigmoidRecon(torch.autograd.Function):
     @staticmethod
     def forward(ctx, d, weight, bias, target, l1):
         co, ci, ksize = weight.shape[0], weight.shape[1], weight.shape[2]
-        wf, _ = ops.weight_prep(weight, True, False)
+        wf, wd = ops.weight_prep(weight, True, d.requires_grad)
         logits = ops.conv2d(d, wf, bias, co, ksize, None, OUT_NCHW_F32, (ci, co))
         e = logits.numel()
         loss, pred, _, gn = ops.recon_loss(logits, target.contiguous().float(), l1, True, 1.0 / e, True, False, True)
-        ctx.save_for_backward(d, weight, gn)
+        ctx.save_for_backward(d, weight, gn, wd)
         ctx.cfg = (ksize, co, ci)
         ctx.has_bias = bias is not None
         ctx.mark_non_differentiable(pred)
@@ -327,7 +329,7 @@ class ConvSigmoidRecon(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, _gpred, gl):
-        d, weight, gn = ctx.saved_tensors
+        d, weight, gn, wd = ctx.saved_tensors
         ksize, co, ci = ctx.cfg
         g = ops.scale(gn, gl.reshape(1).float().contiguous(), 1.0)
         db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
@@ -335,6 +337,7 @@ class ConvSigmoidRecon(torch.autograd.Function):
         dw = ops.wgrad_finish(acc, co, ci, ksize)
         dx = None
         if ctx.needs_input_grad[0]:
-            _, wd = ops.weight_prep(weight, False, True)
+            if wd is None:
+                _, wd = ops.weight_prep(weight, False, True)
             dx = ops.conv2d(g, wd, None, d.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
         return dx, dw, db, None, None
