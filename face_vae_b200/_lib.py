@@ -41,6 +41,11 @@ SIGNATURES = {
     "fv_recon_loss": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
     "fv_recon_loss_flat": [_p, _p, _p, _p, _ll, _i, _f, _p],
     "fv_scale": [_p, _p, _i, _ll, _p, _f, _p],
+    "fv_pw_moments": [_p, _p, _i, _i, _i, _p],
+    "fv_pw_prepare": [_p, _d, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _p],
+    "fv_pw_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "fv_pw_bwd_reduce": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "fv_pw_bwd_finalize": [_p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "fv_bn_finalize_xrank": [_p, _p, _i, _i, _p, _i, _d, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i, _i, _p],
     "fv_debug_mma_rate": [_i, _i, _i, _i, _i, _i, _p, _p],
     "fv_debug_trace_set": [_p],

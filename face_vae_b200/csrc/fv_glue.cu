@@ -167,17 +167,20 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sum
     if (tr < rpi) {
         const long long stride = (long long)gridDim.x * rpi;
         long long r = (long long)blockIdx.x * rpi + tr;
-        for (; r + 3 * stride < P; r += 4 * stride) {            // four independent 16-byte loads in flight per thread
-            float f[4][8];
+        for (; r + 7 * stride < P; r += 8 * stride) {            // eight independent 16-byte loads in flight per thread
+            Raw8<T> raw[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) V8<T>::load(y + (r + u * stride) * C + tc * 8, f[u]);
+            for (int u = 0; u < 8; ++u) raw[u].load(y + (r + u * stride) * C + tc * 8);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 8; ++u) {
+                float f[8];
+                raw[u].unpack(f);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    s[k] += f[u][k];
-                    q[k] += f[u][k] * f[u][k];
+                    s[k] += f[k];
+                    q[k] = fmaf(f[k], f[k], q[k]);
                 }
+            }
         }
         for (; r < P; r += stride) {
             float f[8];
@@ -245,13 +248,14 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
 // a = act(scale[c] * y + shift[c]); mode POOL averages 2x2 windows on the way out (DownBlock2D, reference
 // modules.py:59-70), mode UP replicates each pixel 2x2 (the nn.Upsample in front of UpBlock2D's conv, modules.py:78-89).
 // H, W are the INPUT spatial sizes.  Output is NHWC (TO) or, with nchw_out, NCHW fp32.
-template <typename TI, typename TO>
-__global__ void bn_act_fwd_kernel(const TI* __restrict__ y, const float* __restrict__ stat, TO* __restrict__ out,
-                                  int N, int H, int W, int C, int mode, int act, int nchw_out) {
+template <typename TI, typename TO, int MODE>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const TI* __restrict__ y, const float* __restrict__ stat, TO* __restrict__ out, int N, int H, int W, int C, int act,
+                  int nchw_out) {
     const float* scale = stat + 2 * C;
     const float* shift = stat + 3 * C;
     const unsigned groups = C / 8;
-    const unsigned Ho = mode == FV_MODE_POOL ? H / 2 : H, Wo = mode == FV_MODE_POOL ? W / 2 : W;   // iteration domain
+    const unsigned Ho = MODE == FV_MODE_POOL ? H / 2 : H, Wo = MODE == FV_MODE_POOL ? W / 2 : W;   // iteration domain
     const unsigned total = (unsigned)N * Ho * Wo * groups;
     // blockDim (256) is a multiple of groups, so a thread keeps the same channel group for its whole grid-stride walk
     const unsigned g = threadIdx.x % groups;
@@ -261,46 +265,71 @@ __global__ void bn_act_fwd_kernel(const TI* __restrict__ y, const float* __restr
         sc[k] = __ldg(scale + g * 8 + k);
         sf[k] = __ldg(shift + g * 8 + k);
     }
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    constexpr int NL = MODE == FV_MODE_POOL ? 4 : 1;          // loads per element
+    constexpr int U = MODE == FV_MODE_POOL ? 2 : 4;           // elements in flight per thread
+    auto issue = [&](unsigned i, Raw8<TI> (&raw)[NL], unsigned& n, unsigned& ho, unsigned& wo) {
         const unsigned pix = i / groups;
-        const unsigned wo = pix % Wo;
+        wo = pix % Wo;
         const unsigned t2 = pix / Wo;
-        const unsigned ho = t2 % Ho;
-        const unsigned n = t2 / Ho;
+        ho = t2 % Ho;
+        n = t2 / Ho;
+        if (MODE == FV_MODE_POOL) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                raw[MODE == FV_MODE_POOL ? d : 0].load(y + (((size_t)n * H + 2 * ho + (d >> 1)) * W + 2 * wo + (d & 1)) * C + g * 8);
+        } else {
+            raw[0].load(y + (size_t)pix * C + g * 8);
+        }
+    };
+    auto finish = [&](const Raw8<TI> (&raw)[NL], unsigned n, unsigned ho, unsigned wo) {
         float r[8];
-        if (mode == FV_MODE_POOL) {
+        if (MODE == FV_MODE_POOL) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[k] = 0.f;
 #pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
+            for (int d = 0; d < 4; ++d) {
+                float f[8];
+                raw[MODE == FV_MODE_POOL ? d : 0].unpack(f);
 #pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    float f[8];
-                    V8<TI>::load(y + (((long long)n * H + 2 * ho + dy) * W + 2 * wo + dx) * C + g * 8, f);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) r[k] += act_fwd(fmaf(f[k], sc[k], sf[k]), act);
-                }
+                for (int k = 0; k < 8; ++k) r[k] += act_fwd(fmaf(f[k], sc[k], sf[k]), act);
+            }
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[k] *= 0.25f;
         } else {
             float f[8];
-            V8<TI>::load(y + (((long long)n * H + ho) * W + wo) * C + g * 8, f);
+            raw[0].unpack(f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[k] = act_fwd(fmaf(f[k], sc[k], sf[k]), act);
         }
-        if (mode == FV_MODE_UP) {
+        if (MODE == FV_MODE_UP) {
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx)
-                    V8<TO>::store(out + (((long long)n * 2 * H + 2 * ho + dy) * (2 * W) + 2 * wo + dx) * C + g * 8, r);
+                    V8<TO>::store(out + (((size_t)n * 2 * H + 2 * ho + dy) * (2 * W) + 2 * wo + dx) * C + g * 8, r);
         } else if (nchw_out) {
             float* o = reinterpret_cast<float*>(out);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o[(((long long)n * C + g * 8 + k) * Ho + ho) * Wo + wo] = r[k];
+            for (int k = 0; k < 8; ++k) o[(((size_t)n * C + g * 8 + k) * Ho + ho) * Wo + wo] = r[k];
         } else {
-            V8<TO>::store(out + (((long long)n * Ho + ho) * Wo + wo) * C + g * 8, r);
+            V8<TO>::store(out + (((size_t)n * Ho + ho) * Wo + wo) * C + g * 8, r);
         }
+    };
+    const unsigned stride = gridDim.x * blockDim.x;
+    unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i0 + (U - 1) * stride < total; i0 += U * stride) {      // U independent elements: all loads first
+        Raw8<TI> raw[U][NL];
+        unsigned n[U], ho[U], wo[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) issue(i0 + u * stride, raw[u], n[u], ho[u], wo[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) finish(raw[u], n[u], ho[u], wo[u]);
+    }
+    for (; i0 < total; i0 += stride) {
+        Raw8<TI> raw[NL];
+        unsigned n, ho, wo;
+        issue(i0, raw, n, ho, wo);
+        finish(raw, n, ho, wo);
     }
 }
 
@@ -782,7 +811,10 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_fwd(const void* 
     if (nchw_out && (out_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: NCHW output is fp32, no upsample");
     const int Ho = mode == FV_MODE_POOL ? H / 2 : H, Wo = mode == FV_MODE_POOL ? W / 2 : W;
     const int grid = grid_for((long long)N * Ho * Wo * (C / 8));
-#define LAUNCH(TI, TO) bn_act_fwd_kernel<TI, TO><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, mode, act, nchw_out)
+#define LAUNCH(TI, TO) do { \
+        if (mode == FV_MODE_POOL) bn_act_fwd_kernel<TI, TO, FV_MODE_POOL><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, act, nchw_out); \
+        else if (mode == FV_MODE_UP) bn_act_fwd_kernel<TI, TO, FV_MODE_UP><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, act, nchw_out); \
+        else bn_act_fwd_kernel<TI, TO, FV_MODE_NONE><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, act, nchw_out); } while (0)
     if (in_dtype == FV_DT_BF16 && out_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
     else if (in_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, float);
     else if (out_dtype == FV_DT_BF16) LAUNCH(float, __nv_bfloat16);

@@ -155,6 +155,48 @@ class ConvBNAct(torch.autograd.Function):
         return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
+class PointwiseBNAct(torch.autograd.Function):
+    """SameBlock2D with <= 4 input channels in training mode, straight from the NCHW fp32 frames (the first encoder layer,
+    reference modules.py:97-108 via models.py:749): a 1x1 conv followed by batch norm is a per-pixel affine map whose
+    batch statistics follow from the input moments, so forward is `moments(x)` + one pass, backward ONE pass over (g, x)
+    with dW / dgamma / dbeta in closed form (csrc/fv_pointwise.cu).  The frames get no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, act, momentum, eps):
+        n, c, h, w = x.shape
+        co = weight.shape[0]
+        w2d = weight.reshape(co, c).contiguous()
+        fsums = ops.pw_moments(x)
+        if _world() > 1:
+            dist.all_reduce(fsums, op=dist.ReduceOp.SUM)
+        count = n * h * w * _world()
+        coef, stat = ops.pw_prepare(fsums, count, w2d, bias, gamma, beta, running_mean, running_var, momentum, eps)
+        out = ops.pw_fwd(x, coef, act)
+        ctx.save_for_backward(x, w2d, bias if bias is not None else gamma.new_zeros(0), gamma, coef, stat, fsums)
+        ctx.cfg = (act, count, bias is not None, tuple(weight.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w2d, bias, gamma, coef, stat, fsums = ctx.saved_tensors
+        act, count, has_bias, wshape = ctx.cfg
+        bsums_local = ops.pw_bwd_reduce(x, g.contiguous(), coef, act)
+        bsums = bsums_local
+        if _world() > 1:
+            bsums = bsums_local.clone()
+            dist.all_reduce(bsums, op=dist.ReduceOp.SUM)
+        b = bias if has_bias else None
+        dw, dgamma, dbeta = ops.pw_bwd_finalize(fsums, bsums, count, w2d, b, gamma, stat)
+        if _world() > 1:
+            # the closed form yields the SUM over ranks of the per-rank gradients (it is built from all-reduced sums);
+            # every rank reports 1/R of it so that the gradient all-reduce (mean over ranks) delivers exactly that sum / R,
+            # the gradient of the global-mean loss -- the same value per-rank SyncBN gradients average to
+            inv = 1.0 / _world()
+            dw, dgamma, dbeta = dw * inv, dgamma * inv, dbeta * inv
+        db = torch.zeros((wshape[0],), device=x.device, dtype=torch.float32) if has_bias else None
+        return None, dw.reshape(wshape), db, dgamma, dbeta, None, None, None, None, None
+
+
 class BNActConv(torch.autograd.Function):
     """Pattern "NAC" of _ConvBlock as used by ResBlock2D (reference modules.py:116-130): norm + act on the block
     input, then the conv; ``residual`` (NHWC bf16) is added in the conv epilogue (the ``x +`` of modules.py:125)."""

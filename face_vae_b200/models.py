@@ -67,11 +67,12 @@ class FaceVAE(nn.Module):
     # -- pieces ---------------------------------------------------------------------------------------------
     def encode_nchw(self, x: torch.Tensor) -> torch.Tensor:
         """frames [N,3,H,W] fp32 -> h [N, 2*zc, H/f, W/f] fp32 NCHW (mu | logstd kept in fp32 for the KL term)."""
-        t = as_nhwc(x)
         last = len(self.enc) - 1
+        t = x
         for i, blk in enumerate(self.enc):
             if i == 0:
-                t = blk.forward_nhwc(t)
+                # raw RGB frames: per-pixel affine fast path (statistics from the input moments), else the generic block
+                t = blk.forward_from_frames(x) if blk.pointwise_ok(x) else blk.forward_nhwc(as_nhwc(x))
             else:
                 t = blk.forward_nhwc(t, out_nchw_f32=(i == last))
         return t

@@ -197,7 +197,25 @@ class SameBlock2D(nn.Module):
     def forward_nhwc(self, x, post_mode=MODE_NONE):
         return self.layers.forward_nhwc(x, post_mode)
 
+    def pointwise_ok(self, x) -> bool:
+        """Raw NCHW fp32 frames with <= 4 channels into 32, training mode, no gradient wanted for the frames: the block is
+        a per-pixel affine map with statistics from the input moments (functional.PointwiseBNAct)."""
+        blk = self.layers
+        return (self.training and x.dim() == 4 and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+                and not x.requires_grad and x.shape[1] <= 4 and blk.in_channels == x.shape[1] and blk.out_channels == 32
+                and blk.pattern == "CNA")
+
+    def forward_from_frames(self, x):
+        """x: NCHW fp32 frames -> NHWC bf16 [N,H,W,32]."""
+        blk = self.layers
+        conv, bn = blk.conv, blk.norm
+        bn.num_batches_tracked += 1
+        return Fn.PointwiseBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, blk.act,
+                                       bn.momentum, bn.eps)
+
     def forward(self, x):
+        if self.pointwise_ok(x):
+            return as_nchw(self.forward_from_frames(x), self.out_channels)
         return as_nchw(self.forward_nhwc(as_nhwc(x)), self.out_channels)
 
 

@@ -288,3 +288,51 @@ def scale(t: torch.Tensor, scale_ptr: Optional[torch.Tensor], s: float = 1.0, ou
     out = torch.empty_like(t) if out is None else out
     call("fv_scale", t.data_ptr(), out.data_ptr(), _dt(t), t.numel(), _ptr(scale_ptr), float(s), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------ first encoder layer (C <= 4)
+def pw_moments(x: torch.Tensor) -> torch.Tensor:
+    """x NCHW fp32 [N,C,H,W], C <= 4 -> double [C + C*C]: sum x_c | sum x_c x_d."""
+    _chk(x, "x", torch.float32)
+    n, c, h, w = x.shape
+    sums = torch.zeros((c + c * c,), device=x.device, dtype=torch.float64)
+    call("fv_pw_moments", x.data_ptr(), sums.data_ptr(), n, c, h * w, _stream(), meta=_bytes(x))
+    return sums
+
+
+def pw_prepare(sums, count, w2d, bias, gamma, beta, running_mean, running_var, momentum=BN_MOMENTUM, eps=BN_EPS):
+    """-> (coef [Co, C+1] fp32: A | c, stat [2, Co]: mean_y | invstd)."""
+    co, c = w2d.shape
+    coef = torch.empty((co, c + 1), device=w2d.device, dtype=torch.float32)
+    stat = torch.empty((2, co), device=w2d.device, dtype=torch.float32)
+    call("fv_pw_prepare", sums.data_ptr(), float(count), w2d.data_ptr(), _ptr(bias), gamma.data_ptr(), beta.data_ptr(),
+         _ptr(running_mean), _ptr(running_var), momentum, eps, coef.data_ptr(), stat.data_ptr(), co, c, _stream())
+    return coef, stat
+
+
+def pw_fwd(x: torch.Tensor, coef: torch.Tensor, act: int = ACT_RELU) -> torch.Tensor:
+    n, c, h, w = x.shape
+    co = coef.shape[0]
+    out = torch.empty((n, h, w, co), device=x.device, dtype=torch.bfloat16)
+    call("fv_pw_fwd", x.data_ptr(), coef.data_ptr(), out.data_ptr(), n, c, h * w, co, act, _stream(), meta=_bytes(x, out))
+    return out
+
+
+def pw_bwd_reduce(x: torch.Tensor, g: torch.Tensor, coef: torch.Tensor, act: int = ACT_RELU) -> torch.Tensor:
+    _chk(g, "g", torch.bfloat16)
+    n, c, h, w = x.shape
+    co = coef.shape[0]
+    sums = torch.zeros((co + co * c,), device=x.device, dtype=torch.float64)
+    call("fv_pw_bwd_reduce", x.data_ptr(), g.data_ptr(), coef.data_ptr(), sums.data_ptr(), n, c, h * w, co, act, _stream(),
+         meta=_bytes(x, g))
+    return sums
+
+
+def pw_bwd_finalize(fsums, bsums, count, w2d, bias, gamma, stat):
+    co, c = w2d.shape
+    dw = torch.empty((co, c), device=w2d.device, dtype=torch.float32)
+    dgamma = torch.empty((co,), device=w2d.device, dtype=torch.float32)
+    dbeta = torch.empty((co,), device=w2d.device, dtype=torch.float32)
+    call("fv_pw_bwd_finalize", fsums.data_ptr(), bsums.data_ptr(), float(count), w2d.data_ptr(), _ptr(bias), gamma.data_ptr(),
+         stat.data_ptr(), dw.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), co, c, _stream())
+    return dw, dgamma, dbeta

@@ -82,6 +82,19 @@ int fv_bn_bwd_finalize(const float* sums_local, const float* sums_global, double
 int fv_bn_act_bwd_apply(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat, const float* coef,
                         const void* add, void* dy, int N, int H, int W, int C, int mode, int act, void* stream);
 
+/* ---- first encoder layer: SameBlock2D(C <= 4 -> 32) on raw NCHW fp32 frames (modules.py:97-108 via models.py:749) ----
+ * 1x1 conv + training-mode batch norm + ReLU is a per-pixel affine map whose statistics follow from the input moments.
+ * sums are double: forward [C + C*C] = sum x_c | sum x_c x_d; backward [Co + Co*C] = sum dz | sum dz x_c (caller-zeroed,
+ * all-reduced across ranks by the host).  coef [Co][C+1] = A | c with a = act(A x + c); stat [2][Co] = mean_y | invstd. */
+int fv_pw_moments(const float* x_nchw, double* sums, int N, int C, int HW, void* stream);
+int fv_pw_prepare(const double* sums, double count, const float* w, const float* bias, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float momentum, float eps, float* coef, float* stat, int Co, int C, void* stream);
+int fv_pw_fwd(const float* x_nchw, const float* coef, void* out_nhwc_bf16, int N, int C, int HW, int Co, int act, void* stream);
+int fv_pw_bwd_reduce(const float* x_nchw, const void* g_nhwc_bf16, const float* coef, double* sums, int N, int C, int HW, int Co, int act,
+                     void* stream);
+int fv_pw_bwd_finalize(const double* fsums, const double* bsums, double count, const float* w, const float* bias, const float* gamma,
+                       const float* stat, float* dw, float* dgamma, float* dbeta, int Co, int C, void* stream);
+
 /* ---- cross-rank statistic exchange over NVLink peer memory, fused with the finalize kernels ------------------------
  * Replaces the per-layer all_gather / all_reduce of SyncBatchNorm under DDP (torch/nn/modules/_functions.py:74-83,159;
  * reference modules.py:19, logger.py:55).  peer_bufs_dev: device array of `world` pointers to the ranks' symmetric

@@ -292,3 +292,38 @@ def test_wgrad_ring_schedule(ops, n, h, w, ci, co, k):
         print("   bad frac by ci :", [round(v, 2) for v in bad.float().mean(dim=(0, 2, 3)).tolist()][:16])
         print("   bad frac by co :", [round(v, 2) for v in bad.float().mean(dim=(1, 2, 3)).tolist()][:16])
     assert err <= 2e-3 * scale + 1e-5, f"wgrad mismatch {err} vs {scale}"
+
+
+@pytest.mark.parametrize("c", [3, 1, 4])
+def test_pointwise_first_layer(ops, c):
+    """SameBlock2D(c <= 4 -> 32) fast path (fv_pointwise.cu): statistics from input moments, closed-form parameter
+    gradients; against F.conv2d + F.batch_norm + relu in fp32."""
+    from face_vae_b200.ops import ACT_RELU
+    n, h, w, co = 3, 24, 40, 32
+    x = _rand((n, c, h, w), 60, 0.0, 1.0, False)
+    wt = _rand((co, c, 1, 1), 61, -0.6, 0.6, False).requires_grad_(True)
+    b = _rand((co,), 62, -0.2, 0.2, False).requires_grad_(True)
+    gamma = _rand((co,), 63, 0.5, 1.5, False).requires_grad_(True)
+    beta = _rand((co,), 64, -0.3, 0.3, False).requires_grad_(True)
+    rm, rv = torch.zeros(co).cuda(), torch.ones(co).cuda()
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    a = F.relu(F.batch_norm(F.conv2d(x, wt, b), rm_ref, rv_ref, gamma, beta, True, 0.1, 1e-5))
+    g = _rand(tuple(a.shape), 65)
+    a.backward(g)
+    count = n * h * w
+    fs = ops.pw_moments(x)
+    coef, stat = ops.pw_prepare(fs, count, wt.detach().reshape(co, c).contiguous(), b.detach(), gamma.detach(), beta.detach(), rm, rv)
+    out = ops.pw_fwd(x, coef, ACT_RELU)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(rm, rm_ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rv, rv_ref, rtol=1e-4, atol=1e-5)
+    _report(f"pointwise fwd c{c}", out, a.detach().permute(0, 2, 3, 1), 1e-2, 4e-3)
+    g_nhwc = g.permute(0, 2, 3, 1).contiguous().bfloat16()
+    bs = ops.pw_bwd_reduce(x, g_nhwc, coef, ACT_RELU)
+    dw, dgamma, dbeta = ops.pw_bwd_finalize(fs, bs, count, wt.detach().reshape(co, c).contiguous(), b.detach(), gamma.detach(), stat)
+    torch.cuda.synchronize()
+    for name, got, ref in (("dw", dw, wt.grad.reshape(co, c)), ("dgamma", dgamma, gamma.grad), ("dbeta", dbeta, beta.grad)):
+        err = (got - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        print(f"pointwise {name} c{c}: max_err {err:.3e} absmax {scale:.3e}")
+        assert err <= 1e-2 * scale + 1e-4, (name, err, scale)
