@@ -39,6 +39,7 @@ struct ConvParams {
     int stage_stride;
     int tx_bytes;         // bytes the TMA unit delivers per stage (what the full barrier is armed with)
     int out_mode, tmem_cols;
+    int out_cs;           // channel stride (elements) of the NHWC output / residual rows (>= Co_pad when Co is split)
     const float* bias;
     const __nv_bfloat16* residual;
     void* out;
@@ -194,7 +195,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                             if (c0 + i < p.Co) o[(((size_t)n * p.Co + c0 + i) * p.H + h) * p.W + w] = f[i];
                     } else {
                         if (p.residual) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Co_pad + c0);
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.out_cs + c0);
                             const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
                             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -204,13 +205,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                             }
                         }
                         if (p.out_mode == FV_OUT_NHWC_BF16) {
-                            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Co_pad + c0);
+                            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + c0);
                             o[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
                                               pack_bf16(f[6], f[7]));
                             o[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
                                               pack_bf16(f[14], f[15]));
                         } else {
-                            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Co_pad + c0);
+                            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cs + c0);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
                         }
@@ -275,8 +276,32 @@ static int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const Con
 
 }  // namespace fv
 
+static int conv2d_chunk(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W,
+                        int Ci, int Co, int Co_pad, int out_cs, int R, int S, int pad, void* stream);
+
+// Output channels beyond one UMMA N (256) are produced in chunks of <= 256: each chunk is an independent GEMM on a row
+// slice of the K-major filter matrix, written at its channel offset of the NHWC output (channel stride = Co_pad).
 extern "C" __attribute__((visibility("default"))) int fv_conv2d(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode,
                          int N, int H, int W, int Ci, int Co, int Co_pad, int R, int S, int pad, void* stream) {
+    using namespace fv;
+    if (Co_pad <= 256) return conv2d_chunk(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, Co_pad, R, S, pad, stream);
+    if (Co_pad % 64 || out_mode == FV_OUT_NCHW_F32)
+        return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: Co_pad=%d > 256 must be a multiple of 64 with an NHWC output", Co_pad);
+    if (!x || !w || !y) return fail(FV_ERR_ARG, "fv_conv2d: null pointer");
+    const size_t esz = out_mode == FV_OUT_NHWC_BF16 ? 2 : 4;
+    for (int c0 = 0; c0 < Co_pad; c0 += 256) {
+        const int cn = Co_pad - c0 < 256 ? Co_pad - c0 : 256;
+        const int co_real = Co - c0 < cn ? (Co - c0 > 0 ? Co - c0 : 1) : cn;
+        const int e = conv2d_chunk(x, static_cast<const char*>(w) + (size_t)c0 * R * S * Ci * 2, bias ? bias + c0 : nullptr,
+                                   residual ? static_cast<const char*>(residual) + (size_t)c0 * 2 : nullptr,
+                                   static_cast<char*>(y) + (size_t)c0 * esz, out_mode, N, H, W, Ci, co_real, cn, Co_pad, R, S, pad, stream);
+        if (e) return e;
+    }
+    return FV_OK;
+}
+
+static int conv2d_chunk(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W,
+                        int Ci, int Co, int Co_pad, int out_cs, int R, int S, int pad, void* stream) {
     using namespace fv;
     if (!x || !w || !y) return fail(FV_ERR_ARG, "fv_conv2d: null pointer");
     if (N < 1 || H < 1 || W < 1) return fail(FV_ERR_ARG, "fv_conv2d: bad shape N=%d H=%d W=%d", N, H, W);
@@ -288,7 +313,7 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d(const void* x, c
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: only odd square filters with same padding (R=%d S=%d pad=%d)", R, S, pad);
     if (out_mode < 0 || out_mode > 2) return fail(FV_ERR_ARG, "fv_conv2d: out_mode %d", out_mode);
     if (out_mode == FV_OUT_NCHW_F32 && residual) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: residual needs an NHWC output");
-    {
+    if (out_cs == Co_pad) {
         const int rr = conv2d_ring_try(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, (cudaStream_t)stream);
         if (rr >= 0) return rr;
     }
@@ -321,6 +346,7 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d(const void* x, c
     int cols = 32;
     while (cols < 2 * Co_pad) cols <<= 1;
     p.tmem_cols = cols;
+    p.out_cs = out_cs;
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.out = y;

@@ -170,8 +170,27 @@ int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, i
 
 }  // namespace fv
 
+static int wgrad_chunk(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int dy_cs, int R, int S, int pad,
+                       void* stream);
+
+// Output-channel counts beyond one UMMA N (256) are handled in chunks of <= 256 channels of dY (channel stride Co_pad).
 extern "C" __attribute__((visibility("default"))) int fv_conv2d_wgrad(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad,
                                int R, int S, int pad, void* stream) {
+    using namespace fv;
+    if (Co_pad <= 256) return wgrad_chunk(x, dy, dw_acc, N, H, W, Ci, Co_pad, Co_pad, R, S, pad, stream);
+    if (Co_pad % 64) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: Co_pad=%d > 256 must be a multiple of 64", Co_pad);
+    if (!x || !dy || !dw_acc) return fail(FV_ERR_ARG, "fv_conv2d_wgrad: null pointer");
+    for (int c0 = 0; c0 < Co_pad; c0 += 256) {
+        const int cn = Co_pad - c0 < 256 ? Co_pad - c0 : 256;
+        const int e = wgrad_chunk(x, static_cast<const char*>(dy) + (size_t)c0 * 2, dw_acc + (size_t)c0 * R * S * Ci, N, H, W, Ci, cn, Co_pad, R, S,
+                                  pad, stream);
+        if (e) return e;
+    }
+    return FV_OK;
+}
+
+static int wgrad_chunk(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int dy_cs, int R, int S, int pad,
+                       void* stream) {
     using namespace fv;
     if (!x || !dy || !dw_acc) return fail(FV_ERR_ARG, "fv_conv2d_wgrad: null pointer");
     if (Ci % 16 || Ci < 16 || (Ci > 64 && Ci % 64) || (Ci < 64 && Ci != 16 && Ci != 32))
@@ -180,7 +199,7 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d_wgrad(const void
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: Co_pad=%d must be 16, 32, 64, 128, 192 or 256", Co_pad);
     if (R != S || (R != 1 && R != 3 && R != 5 && R != 7) || pad != (R - 1) / 2)
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: only odd square filters with same padding");
-    {
+    if (dy_cs == Co_pad) {
         const int rr = conv2d_wgrad_ring_try(x, dy, dw_acc, N, H, W, Ci, Co_pad, R, S, pad, (cudaStream_t)stream);
         if (rr >= 0) return rr;
     }
@@ -243,7 +262,7 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d_wgrad(const void
     }
     {
         uint64_t dims[4] = {(uint64_t)Co_pad, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[3] = {(uint64_t)Co_pad * 2, (uint64_t)W * Co_pad * 2, (uint64_t)H * W * Co_pad * 2};
+        uint64_t str[3] = {(uint64_t)dy_cs * 2, (uint64_t)W * dy_cs * 2, (uint64_t)H * W * dy_cs * 2};
         uint32_t box[4] = {(uint32_t)p.bw, (uint32_t)p.pw, (uint32_t)p.ph, (uint32_t)p.pn};
         if (int e = encode_tmap_bf16(&tmDY, dy, 4, dims, str, box, p.bw * 2)) return e;
     }

@@ -327,3 +327,22 @@ def test_pointwise_first_layer(ops, c):
         scale = ref.abs().max().item()
         print(f"pointwise {name} c{c}: max_err {err:.3e} absmax {scale:.3e}")
         assert err <= 1e-2 * scale + 1e-4, (name, err, scale)
+
+
+@pytest.mark.parametrize("ci,co,k,h,w,n", [(512, 512, 3, 8, 8, 2), (64, 512, 1, 16, 16, 2), (512, 256, 3, 16, 16, 2), (256, 384, 3, 8, 16, 2)])
+def test_conv_more_than_256_output_channels(ops, ci, co, k, h, w, n):
+    """Co > 256 (the 512x512 'deeper' variant, BASELINE.json configs[3]): output channels are produced in chunks of one UMMA N."""
+    from face_vae_b200.ops import pad_channels
+    _conv_case(ops, n, h, w, ci, co, k, seed=70)
+    x = _rand((n, ci, h, w), 71).requires_grad_(True)
+    wt = _rand((co, ci, k, k), 72, -0.1, 0.1).requires_grad_(True)
+    dy = _rand((n, co, h, w), 73)
+    F.conv2d(x, wt, None, padding=(k - 1) // 2).backward(dy)
+    x_nhwc, dy_nhwc = ops.nchw_to_nhwc(x.detach()), ops.nchw_to_nhwc(dy, pad_channels(co))
+    _, wd = ops.weight_prep(wt.detach(), False, True)
+    dx = ops.conv2d(dy_nhwc, wd, None, pad_channels(ci), k)
+    dw = ops.wgrad_finish(ops.conv2d_wgrad(x_nhwc, dy_nhwc, k), co, ci, k)
+    torch.cuda.synchronize()
+    _report(f"dgrad ci{ci} co{co}", dx[..., :ci], x.grad.permute(0, 2, 3, 1), 2e-2, 4e-3)
+    err, scale = (dw - wt.grad).abs().max().item(), wt.grad.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-5, (err, scale)

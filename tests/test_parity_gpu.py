@@ -255,3 +255,40 @@ def test_cuda_graph_step_matches_eager(fv):
     assert v1[-1] < v1[0]
     w0, w1 = res[False][1]["out_conv.weight"], res[True][1]["out_conv.weight"]
     assert ((w0 - w1).norm() / w0.norm()).item() < 5e-2
+
+
+def test_deep_512_variant_matches_oracle(fv):
+    """BASELINE.json configs[3] architecture (down_seq (3,32,64,128,256,512,64), up to 512 channels, latent 32 channels)
+    at a size the CPU oracle finishes in seconds (batch 2, 128x128): losses per element-level tolerance, gradients bounded
+    by the bf16 yardstick of this model family."""
+    cfg = O.CFG_512
+    p = O.det_anchor_params(cfg, 2)
+    x, eps = O.det_inputs(2, 128, 128, cfg, 2)
+    ref_out, ref_grads, _, _ = O.anchor_train_grads(p, x, eps, cfg)
+    m = _load(fv.models.face_vae_512(), p)
+    assert sum(q.numel() for q in m.parameters()) == 15258819
+    out = m.forward_loss(x.cuda(), eps.cuda())
+    (cfg.w_kl * out["K"] + cfg.w_rec * out["R"]).backward()
+    torch.cuda.synchronize()
+    assert abs(out["K"].item() - ref_out["K"].item()) <= RTOL * abs(ref_out["K"].item())
+    assert abs(out["R"].item() - ref_out["R"].item()) <= RTOL * abs(ref_out["R"].item())
+    G.check_like(out["x_hat"], ref_out["x_hat"], RTOL, AFRAC, "x_hat")
+    for k, pr in m.named_parameters():
+        ref = ref_grads[k]
+        assert bool(torch.isfinite(pr.grad).all()), k
+        if ref.abs().max().item() < 1e-5:
+            continue
+        rel = ((pr.grad.cpu() - ref).norm() / ref.norm()).item()
+        assert rel <= 0.35, (k, rel)
+
+
+def test_inference_sweep_shapes(fv):
+    """BASELINE.json configs[4]: eval-mode encode -> sample -> decode at several batch sizes (running statistics)."""
+    m = fv.models.FaceVAE().cuda().eval()
+    with torch.no_grad():
+        for n in (1, 3, 16):
+            x = torch.rand((n, 3, 256, 256), device="cuda")
+            mu, ls, xh = m(x, True, torch.zeros((n, 4096), device="cuda"))
+            assert xh.shape == x.shape and mu.shape == (n, 4096) and bool(torch.isfinite(xh).all())
+            _, _, xh2 = m(x, False)
+            torch.testing.assert_close(xh, xh2, rtol=0, atol=0)        # eps = 0  <=>  z = mu
