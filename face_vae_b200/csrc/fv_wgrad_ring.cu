@@ -30,7 +30,7 @@ struct WRingParams {
     long long* trace;
 };
 
-static constexpr int kWRingThreads = 192;
+static constexpr int kWRingThreads = 224;   // producer, issuer A, 4 epilogue warps, issuer B
 
 // CW: channels per A chunk == Ci (16 / 32 / 64); S_: filter size (R == S); kPX: pixels (GEMM K) per block
 template <int CW, int S_, int kPX>
@@ -61,15 +61,16 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmDY);
+        // two issuer warps (even / odd M tiles) read every slab and every dY tile: "empty" needs both votes
         for (int i = 0; i < p.ring; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], 2);
         }
         for (int i = 0; i < p.b_slots; ++i) {
             mbar_init(&bfull[i], 1);
-            mbar_init(&bempty[i], 1);
+            mbar_init(&bempty[i], 2);
         }
-        mbar_init(tfull, 1);
+        mbar_init(tfull, 2);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -108,7 +109,10 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 if (++h == p.H) { h = 0; ++col; fresh = true; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 6) {
+        // Two issuer warps: a single warp spends ~40 % of a block on barrier observation and commits while the tensor
+        // pipe drains; with the M tiles split by parity the other warp's MMAs fill those gaps.
+        const uint32_t issuer = warp == 6 ? 1u : 0u;
         if (b0 < b1) {
             const bool leader = elect_one_sync();
             const uint32_t idesc = umma_idesc_bf16(128, p.Co_pad, 1, 1);           // both operands MN-major
@@ -157,7 +161,7 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                         const uint32_t d_col = tmem_base + (uint32_t)((r * TPR + part) * p.Co_pad);
 #pragma unroll
                         for (int k4 = 0; k4 < kPX / 16; ++k4)
-                            if (leader)
+                            if (leader && (uint32_t)((r * TPR + part) & 1) == issuer)
                                 tc_mma_f16_lohi2(d_col, a_row + (uint32_t)(part * CPT * (AROW >> 4)) + k4 * a_kstep, a_hi, b_lo + k4 * b_kstep,
                                                  b_hi, idesc, accumulate | (uint32_t)(k4 > 0));
                     }
@@ -182,7 +186,7 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             if (leader) tc_commit(tfull);
             FV_TACC(5, t_all);
         }
-    } else if (b0 < b1) {
+    } else if (b0 < b1) {       // warps 2..5
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int chunk = row / CW, ci = row % CW;
