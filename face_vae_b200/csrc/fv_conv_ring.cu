@@ -142,7 +142,7 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int t = t0; t < t1; ++t) {
                 e_end += loads_of(t);
                 if ((uint32_t)((t - t0) & 1) != issuer) continue;
-                { FV_T0(tw); mbar_wait(&tempty[issuer], (k & 1) ^ 1);       // k-th use of this issuer's accumulator FV_TACC(2, tw); }
+                { FV_T0(tw); mbar_wait(&tempty[issuer], (k & 1) ^ 1); /* k-th use of this issuer's accumulator */ FV_TACC(2, tw); }
                 { FV_T0(tw);
                 for (; waited < e_end; ++waited) mbar_wait(&full[waited % ring], (waited / ring) & 1);
                 FV_TACC(3, tw); }
