@@ -175,6 +175,10 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     const uint32_t f_next = e_end + loads_of(t + 1) + loads_of(t + 2) - R;
                     upto = f_next < vote_cap ? f_next : vote_cap;
                 }
+                // never vote for a slab this issuer has not yet seen arrive: the vote would land in the PREVIOUS phase of
+                // that slot's barrier (possibly before the other issuer released the previous occupant); it is cast after
+                // the next tile's waits instead
+                if (upto > waited) upto = waited;
                 for (; voted < upto; ++voted)
                     if (leader) tc_commit(&empty[voted % ring]);
                 ++k;
