@@ -138,6 +138,16 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             uint32_t e_end = 0;          // slabs loaded up to and including the current tile (over ALL tiles)
             uint32_t waited = 0;         // slabs whose arrival this issuer has observed
             uint32_t voted = 0;          // slabs this issuer has released
+            // slabs in front of this issuer's first window are never read by it (issuer 1 when its first tile starts a new
+            // column): release them up front.  They are first occupants of their slots, so a plain arrive hits phase 0.
+            {
+                uint32_t f_first = 0;
+                for (int u = t0; u <= t0 + (int)issuer; ++u) f_first += loads_of(u);
+                f_first -= R;
+                if (f_first > vote_cap) f_first = vote_cap;
+                for (; voted < f_first; ++voted)
+                    if (leader) mbar_arrive(&empty[voted % ring]);
+            }
             uint32_t k = 0;              // tiles this issuer has processed
             for (int t = t0; t < t1; ++t) {
                 e_end += loads_of(t);

@@ -260,6 +260,9 @@ def test_recon_loss(ops, l1):
     (3, 20, 128, 16, 32, 7, 0),      # its data gradient shape (16 -> 32 channels, 7x7)
     (2, 16, 384, 64, 128, 3, 0),     # Co_pad > 64: direct stores from the ring kernel
     (2, 16, 128, 32, 64, 3, 1),      # fp32 NHWC output
+    (75, 4, 128, 32, 3, 7, 2),       # runs of 3 tiles over columns of 4 rows: a run may START on the last row of a column
+    (75, 4, 128, 16, 32, 7, 0),      # (the second issuer's first window then lies entirely behind slabs it never reads)
+    (50, 6, 128, 64, 32, 3, 0),
 ])
 def test_conv_ring_schedule(ops, n, h, w, ci, co, k, out_mode):
     """Sliding-window schedule (fv_conv_ring.cu): resident filter, one new input-row slab per tile, TMA-store epilogue."""
