@@ -34,7 +34,7 @@ struct RingParams {
     long long* trace;
 };
 
-static constexpr int kRingThreads = 224;   // producer, issuer A, 4 epilogue warps, issuer B
+static constexpr int kRingThreads = 192;
 
 template <int KB, int S_>
 __global__ void __launch_bounds__(kRingThreads, 1)
@@ -69,7 +69,7 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (p.stage_stride) tma_prefetch_desc(&tmY);
         for (int i = 0; i < p.ring; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 2);      // both issuer warps vote
+            mbar_init(&empty[i], 1);
         }
         mbar_init(wbar, 1);
         for (int i = 0; i < 2; ++i) {
@@ -113,12 +113,8 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 if (++h == p.H) { h = 0; ++col; fresh = true; }
             }
         }
-    } else if (warp == 1 || warp == 6) {
-        // Two issuer warps take alternate tiles (each owns one TMEM accumulator buffer).  A single issuer spends ~35 % of
-        // a tile observing mbarriers and committing while the tensor pipe drains; with two, the other warp's MMAs fill
-        // those gaps.  Slabs are read by tiles of both parities, so a ring slot is recycled after BOTH issuers voted.
-        const uint32_t issuer = warp == 6 ? 1u : 0u;
-        if (t0 + (int)issuer < t1) {
+    } else if (warp == 1) {
+        if (t0 < t1) {
             const bool leader = elect_one_sync();
             const uint32_t idesc = umma_idesc_bf16(128, p.Co_pad, 0, 0);
             const uint32_t desc_hi = (uint32_t)(umma_smem_desc(0, 16, SBO, LAYOUT) >> 32);   // low word = LBO | start address
@@ -126,40 +122,35 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint32_t smem_base = smem_u32(smem);
             const uint32_t w_base = ((smem_base + (uint32_t)p.w_off) >> 4) | LBO_LO;
             const uint32_t w_step = (uint32_t)p.w_slice_stride >> 4;
-            const uint32_t ring = (uint32_t)p.ring, R = (uint32_t)p.R;
-            const int h0 = t0 % p.H;
-            // slab sequence numbers: tile u loads R slabs when it starts a column (or the run), else 1
-            auto loads_of = [&](int u) -> uint32_t { return (u == t0 || (h0 + (u - t0)) % p.H == 0) ? R : 1u; };
-            uint32_t e_total = 0;
-            for (int u = t0; u < t1; ++u) e_total += loads_of(u);
-            const uint32_t vote_cap = e_total > ring ? e_total - ring : 0;   // only slabs that get overwritten need votes
             mbar_wait(wbar, 0);
+            // window = R consecutive ring slots starting at `first`; `wait_slot/wait_ph` track the next slab to arrive
+            uint32_t first = 0, wait_slot = 0, wait_ph = 0, tcount = 0;
+            int h = t0 % p.H;
+            bool fresh = true;
             FV_T0(t_all);
-            uint32_t e_end = 0;          // slabs loaded up to and including the current tile (over ALL tiles)
-            uint32_t waited = 0;         // slabs whose arrival this issuer has observed
-            uint32_t voted = 0;          // slabs this issuer has released
-            // slabs in front of this issuer's first window are never read by it (issuer 1 when its first tile starts a new
-            // column): release them up front.  They are first occupants of their slots, so a plain arrive hits phase 0.
-            {
-                uint32_t f_first = 0;
-                for (int u = t0; u <= t0 + (int)issuer; ++u) f_first += loads_of(u);
-                f_first -= R;
-                if (f_first > vote_cap) f_first = vote_cap;
-                for (; voted < f_first; ++voted)
-                    if (leader) mbar_arrive(&empty[voted % ring]);
-            }
-            uint32_t k = 0;              // tiles this issuer has processed
-            for (int t = t0; t < t1; ++t) {
-                e_end += loads_of(t);
-                if ((uint32_t)((t - t0) & 1) != issuer) continue;
-                { FV_T0(tw); mbar_wait(&tempty[issuer], (k & 1) ^ 1); /* k-th use of this issuer's accumulator */ FV_TACC(2, tw); }
-                { FV_T0(tw);
-                for (; waited < e_end; ++waited) mbar_wait(&full[waited % ring], (waited / ring) & 1);
-                FV_TACC(3, tw); }
+            // barrier waits of tile t + 1 are taken in the MIDDLE of tile t's MMAs: a completed mbarrier still costs
+            // ~150-250 cycles to observe, and the tensor pipe would otherwise drain while the issuer polls
+            auto wait_tile = [&](uint32_t tc, bool is_fresh) {
+                { FV_T0(tw); mbar_wait(&tempty[tc & 1], ((tc >> 1) & 1) ^ 1); FV_TACC(2, tw); }
+                const int n_new = is_fresh ? p.R : 1;
+                FV_T0(tw2);
+                for (int i = 0; i < n_new; ++i) {                 // the new slabs of that tile have landed?
+                    mbar_wait(&full[wait_slot], wait_ph);
+                    if (++wait_slot == (uint32_t)p.ring) { wait_slot = 0; wait_ph ^= 1; }
+                }
+                FV_TACC(3, tw2);
+            };
+            bool waited = false;
+            for (int t = t0; t < t1; ++t, ++tcount) {
+                const uint32_t acc = tcount & 1;
+                const bool next_fresh = (h + 1 == p.H);
+                // a column change needs R fresh slabs, i.e. slots this tile still occupies: that wait cannot be taken early
+                if (!waited) wait_tile(tcount, fresh);
+                waited = false;
                 tc_fence_after();
                 FV_T0(t_issue);
-                const uint32_t d_tmem = tmem_base + issuer * (uint32_t)p.Co_pad;
-                uint32_t accumulate = 0, slot = (e_end - R) % ring, wtap = w_base;
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co_pad;
+                uint32_t accumulate = 0, slot = first, wtap = w_base;
 #pragma unroll
                 for (int r = 0; r < S_; ++r) {
                     const uint32_t a_row = ((smem_base + slot * (uint32_t)p.slab_stride) >> 4) | LBO_LO;
@@ -174,24 +165,23 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                         }
                         wtap += w_step;
                     }
-                    if (++slot == ring) slot = 0;
+                    if (++slot == (uint32_t)p.ring) slot = 0;
+                    if (r == (S_ - 1) / 2 && t + 1 < t1 && !next_fresh) {
+                        wait_tile(tcount + 1, false);
+                        waited = true;
+                    }
                 }
                 FV_TACC(4, t_issue);
                 FV_T0(t_commit);
-                if (leader) tc_commit(&tfull[issuer]);
-                // vote for the slabs this issuer will not read again: everything before its next tile's window
-                uint32_t upto = vote_cap;
-                if (t + 2 < t1) {
-                    const uint32_t f_next = e_end + loads_of(t + 1) + loads_of(t + 2) - R;
-                    upto = f_next < vote_cap ? f_next : vote_cap;
+                if (leader) tc_commit(&tfull[acc]);
+                // release the slabs the next tile will not read: one when it continues this column, all R otherwise
+                const int n_rel = (t + 1 < t1) ? (next_fresh ? p.R : 1) : 0;
+                for (int i = 0; i < n_rel; ++i) {
+                    if (leader) tc_commit(&empty[first]);
+                    if (++first == (uint32_t)p.ring) first = 0;
                 }
-                // never vote for a slab this issuer has not yet seen arrive: the vote would land in the PREVIOUS phase of
-                // that slot's barrier (possibly before the other issuer released the previous occupant); it is cast after
-                // the next tile's waits instead
-                if (upto > waited) upto = waited;
-                for (; voted < upto; ++voted)
-                    if (leader) tc_commit(&empty[voted % ring]);
-                ++k;
+                fresh = next_fresh;
+                if (++h == p.H) h = 0;
                 FV_TACC(1, t_commit);
             }
             FV_TACC(5, t_all);

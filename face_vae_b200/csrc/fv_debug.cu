@@ -39,7 +39,9 @@ mma_rate_kernel(int n_cols, int row_bytes, int iters, int a_distinct, int mn_maj
         const uint32_t a_base = smem_u32(smem) >> 4, b_base = (smem_u32(smem) + 48 * 1024) >> 4;
         const long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
-            const uint32_t a_lo = lo0 | (a_base + (a_distinct ? ((i & 3) * 2) : 0));
+            // a_distinct >= 16: additionally shift the A start address by (i % 3) pixel rows, as the slab schedule does
+            const uint32_t shift = a_distinct >= 16 ? (uint32_t)((i % 3) * (row_bytes >> 4)) : 0u;
+            const uint32_t a_lo = lo0 | (a_base + shift + (a_distinct ? ((i & 3) * 2) : 0));
             const uint32_t b_lo = lo0 | (b_base + (a_distinct ? ((i & 3) * 2) : 0));
             if (leader) tc_mma_f16_lohi(tmem_base, a_lo, b_lo, hi, idesc, i > 0);
         }
