@@ -128,7 +128,16 @@ class VAETrainer:
             eps = torch.randn((d.shape[0], self.vae.latent_dim(d.shape[2], d.shape[3])), device=d.device)
         eps = eps.reshape(d.shape[0], -1)
         if self._graph is None or self._graph_key != (tuple(d.shape), tuple(eps.shape)):
-            self._capture(d.float().contiguous(), eps.float().contiguous())
+            try:
+                self._capture(d.float().contiguous(), eps.float().contiguous())
+            except Exception as e:      # e.g. an autograd graph from an earlier eager pass is still referenced by the caller
+                import warnings
+                warnings.warn(f"face_vae_b200: CUDA-graph capture of the train step failed ({type(e).__name__}: {e}); "
+                              "continuing with eager launches")
+                self.use_cuda_graph = False
+                self._graph = None
+                torch.cuda.synchronize()
+                return self._eager_step(d, eps)
         self._static_d.copy_(d, non_blocking=True)
         self._static_eps.copy_(eps, non_blocking=True)
         self._graph.replay()
