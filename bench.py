@@ -175,9 +175,13 @@ def main():
 
     # ---- end to end: pinned host -> device copy of each batch and device -> host read of the loss inside the region
     from face_vae_b200.data import AsyncScalarLog, DevicePrefetcher
+    # set-up outside the timed region: the pinned loss buffer (cudaHostAlloc synchronises the device) and two untimed
+    # passes so that the caching allocator already holds the prefetch buffers
+    log = AsyncScalarLog(args.steps)
+    for x, e in DevicePrefetcher(host[i % 2] for i in range(2)):
+        trainer.step(x, e)
     barrier()
     t0 = time.perf_counter()
-    log = AsyncScalarLog(args.steps)
     # every step: its batch comes from pinned host memory (copy overlapped with the previous step on a side stream)
     # and its loss goes back to the host (asynchronous copy into pinned memory, read after the loop)
     for x, e in DevicePrefetcher(host[i % 2] for i in range(args.steps)):
