@@ -178,13 +178,14 @@ def main():
     # set-up outside the timed region: the pinned loss buffer (cudaHostAlloc synchronises the device) and two untimed
     # passes so that the caching allocator already holds the prefetch buffers
     log = AsyncScalarLog(args.steps)
-    for x, e in DevicePrefetcher(host[i % 2] for i in range(2)):
+    prefetch = DevicePrefetcher()
+    for x, e in prefetch.over(host[i % 2] for i in range(3)):
         trainer.step(x, e)
     barrier()
     t0 = time.perf_counter()
     # every step: its batch comes from pinned host memory (copy overlapped with the previous step on a side stream)
     # and its loss goes back to the host (asynchronous copy into pinned memory, read after the loop)
-    for x, e in DevicePrefetcher(host[i % 2] for i in range(args.steps)):
+    for x, e in prefetch.over(host[i % 2] for i in range(args.steps)):
         losses, _ = trainer.step(x, e)
         log.push(torch.stack([v.detach() for v in losses.values()]).sum())
     last = float(log.values()[-1])
@@ -231,10 +232,15 @@ def main():
             k["gbs"] = a["bytes"] / (a["ms"] * 1e-3) / 1e9
             k["frac_hbm"] = k["gbs"] / peaks["hbm"]
         kernels[name] = k
-    conv = agg.get("fv_conv2d")
-    if conv and conv["ms"] > 0:
+    # forward + data-gradient convolutions: the generic implicit-GEMM / ring kernels and the tap-folded out_conv kernels
+    conv = {"ms": 0.0, "flops": 0.0, "launches": 0}
+    for nm in ("fv_conv2d", "fv_outconv_fwd", "fv_outconv_dgrad"):
+        if nm in agg:
+            for k in conv:
+                conv[k] += agg[nm][k]
+    if conv["ms"] > 0:
         ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
-        roofline = {"kernel": "conv_igemm_kernel (fv_conv2d: forward + data-gradient convolutions)", "bound": "tensor",
+        roofline = {"kernel": "conv_igemm_kernel / conv_ring_kernel / fold_conv_kernel (all forward + data-gradient convolutions of the step)", "bound": "tensor",
                     "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
                     "frac_of_burst_peak": ach / peaks["bf16"], "peak_source": peaks["source"] + " (sustained: timed inside the step)",
                     "avg_launch_ms": conv["ms"] / conv["launches"], "launches_per_step": conv["launches"] / args.profile_steps,

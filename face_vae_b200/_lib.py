@@ -29,6 +29,10 @@ SIGNATURES = {
     "fv_conv2d_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "fv_wgrad_finish": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_colsum": [_p, _p, _ll, _i, _p],
+    "fv_outconv_prep": [_p, _p, _p, _i, _i, _p],
+    "fv_outconv_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
+    "fv_outconv_dgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "fv_outconv_wgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "fv_bn_stats": [_p, _i, _p, _ll, _i, _p],
     "fv_bn_finalize": [_p, _d, _p, _p, _p, _p, _f, _f, _p, _i, _p],
     "fv_bn_eval_affine": [_p, _p, _p, _p, _f, _p, _i, _p],
@@ -52,6 +56,7 @@ SIGNATURES = {
 }
 _STR = ("fv_last_error", "fv_version")
 _LL = ("fv_xrank_buffer_floats",)
+_PLAIN_INT = {"fv_outconv_supported": [_i, _i, _i, _i, _i, _i, _i]}   # predicates: the return value is the answer
 
 _lock = threading.Lock()
 _lib = None
@@ -85,6 +90,9 @@ def load(build_if_missing: bool = True):
         for name in _LL:
             getattr(lib, name).restype = C.c_longlong
             getattr(lib, name).argtypes = []
+        for name, args in _PLAIN_INT.items():
+            getattr(lib, name).restype = C.c_int
+            getattr(lib, name).argtypes = args
         _lib = lib
     return _lib
 

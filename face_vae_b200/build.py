@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfacevae_b200.so")
-SOURCES = ["fv_host.cu", "fv_glue.cu", "fv_conv.cu", "fv_conv_ring.cu", "fv_wgrad.cu", "fv_wgrad_ring.cu", "fv_xrank.cu", "fv_pointwise.cu", "fv_debug.cu"]
+SOURCES = ["fv_host.cu", "fv_glue.cu", "fv_conv.cu", "fv_conv_ring.cu", "fv_wgrad.cu", "fv_wgrad_ring.cu", "fv_xrank.cu", "fv_pointwise.cu", "fv_outconv.cu", "fv_debug.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
 if os.environ.get("FV_TRACE"):                       # role-loop cycle counters in the ring kernels (debug only)

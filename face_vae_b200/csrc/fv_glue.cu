@@ -12,9 +12,12 @@ namespace fv {
 
 static constexpr int kThreads = 256;
 
+// Grids are ONE resident wave (num_sms x blocks that fit on an SM at the kernel's register count) of grid-stride blocks:
+// a block's life is a few dependent latency rounds (per-channel constants, the loads, the block reduction + atomics), so
+// several short waves multiply that fixed cost -- 18 us for a 4 MB tensor at 8 blocks per SM in the round-1 profile.
 static inline int grid_for(long long work_items, int per_block = kThreads, int waves = 8) {
     long long b = (work_items + per_block - 1) / per_block;
-    long long cap = (long long)num_sms() * waves;
+    long long cap = (long long)num_sms() * (b > (long long)num_sms() * 64 ? 8 : waves);
     if (b > cap) b = cap;
     if (b < 1) b = 1;
     return (int)b;
@@ -48,6 +51,7 @@ template <typename T> struct Raw8;
 template <> struct Raw8<__nv_bfloat16> {
     uint4 v;
     __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void zero() { v = make_uint4(0u, 0u, 0u, 0u); }
     __device__ __forceinline__ void unpack(float (&f)[8]) const {
         f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
         f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
@@ -59,6 +63,7 @@ template <> struct Raw8<float> {
         a = *reinterpret_cast<const float4*>(p);
         b = *reinterpret_cast<const float4*>(p + 4);
     }
+    __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
     __device__ __forceinline__ void unpack(float (&f)[8]) const {
         f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
     }
@@ -167,10 +172,13 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sum
     if (tr < rpi) {
         const long long stride = (long long)gridDim.x * rpi;
         long long r = (long long)blockIdx.x * rpi + tr;
-        for (; r + 7 * stride < P; r += 8 * stride) {            // eight independent 16-byte loads in flight per thread
+        for (; r < P; r += 8 * stride) {            // eight independent 16-byte loads in flight per thread (rows past the end: zeros)
             Raw8<T> raw[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) raw[u].load(y + (r + u * stride) * C + tc * 8);
+            for (int u = 0; u < 8; ++u) {
+                if (r + u * stride < P) raw[u].load(y + (r + u * stride) * C + tc * 8);
+                else raw[u].zero();
+            }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 float f[8];
@@ -180,15 +188,6 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sum
                     s[k] += f[k];
                     q[k] = fmaf(f[k], f[k], q[k]);
                 }
-            }
-        }
-        for (; r < P; r += stride) {
-            float f[8];
-            V8<T>::load(y + r * C + tc * 8, f);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                s[k] += f[k];
-                q[k] += f[k] * f[k];
             }
         }
 #pragma unroll
@@ -317,19 +316,21 @@ bn_act_fwd_kernel(const TI* __restrict__ y, const float* __restrict__ stat, TO* 
     };
     const unsigned stride = gridDim.x * blockDim.x;
     unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i0 + (U - 1) * stride < total; i0 += U * stride) {      // U independent elements: all loads first
+    for (; i0 < total; i0 += U * stride) {      // U independent elements: all loads first (elements past the end skipped)
         Raw8<TI> raw[U][NL];
         unsigned n[U], ho[U], wo[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) issue(i0 + u * stride, raw[u], n[u], ho[u], wo[u]);
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * stride < total) issue(i0 + u * stride, raw[u], n[u], ho[u], wo[u]);
+            else {
 #pragma unroll
-        for (int u = 0; u < U; ++u) finish(raw[u], n[u], ho[u], wo[u]);
-    }
-    for (; i0 < total; i0 += stride) {
-        Raw8<TI> raw[NL];
-        unsigned n, ho, wo;
-        issue(i0, raw, n, ho, wo);
-        finish(raw, n, ho, wo);
+                for (int d = 0; d < NL; ++d) raw[u][d].zero();
+                n[u] = ho[u] = wo[u] = 0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (i0 + u * stride < total) finish(raw[u], n[u], ho[u], wo[u]);
     }
 }
 
@@ -358,6 +359,12 @@ struct GLoad {                                      // phase 1: issue the loads 
         } else {
             raw[0].load(g + (((size_t)n * H + h) * W + w) * C + grp * 8);
         }
+    }
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int d = 0; d < (GN ? 1 : NR); ++d) raw[d].zero();
+#pragma unroll
+        for (int k = 0; k < (GN ? 8 : 1); ++k) nchw[k] = 0.f;
     }
     __device__ __forceinline__ void finish(float (&r)[8]) const {
         if (GN) {
@@ -408,15 +415,21 @@ bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, con
     constexpr int U = MODE == FV_MODE_UP ? 2 : 8;
     const unsigned stride = gridDim.x * rpi;
     unsigned r0 = blockIdx.x * rpi + tr;
-    for (; r0 + (U - 1) * stride < P; r0 += U * stride) {
+    for (; r0 < P; r0 += U * stride) {
         Raw8<TY> yr[U];
         GLoad<TG, MODE, GN> gl[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {                         // U rows of y and g in flight, 4 registers per 16-byte load
-            unsigned n = 0, h = 0, w = r0 + u * stride;       // MODE_NONE, NHWC g: the row index is the g index
-            if (NEED_NHW) row_to_nhw(r0 + u * stride, H, W, n, h, w);
-            yr[u].load(y + (size_t)(r0 + u * stride) * C + tc * 8);
-            gl[u].issue(g, n, h, w, NEED_NHW ? H : 1, NEED_NHW ? W : (int)P, C, tc);
+            const unsigned row = r0 + u * stride;             // rows past the end load nothing and contribute zero (g = 0)
+            if (row < P) {
+                unsigned n = 0, h = 0, w = row;               // MODE_NONE, NHWC g: the row index is the g index
+                if (NEED_NHW) row_to_nhw(row, H, W, n, h, w);
+                yr[u].load(y + (size_t)row * C + tc * 8);
+                gl[u].issue(g, n, h, w, NEED_NHW ? H : 1, NEED_NHW ? W : (int)P, C, tc);
+            } else {
+                yr[u].zero();
+                gl[u].zero();
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -429,21 +442,6 @@ bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, con
                 s1[k] += dz;
                 sy[k] = fmaf(dz, f[k], sy[k]);
             }
-        }
-    }
-    for (; r0 < P; r0 += stride) {
-        unsigned n, h, w;
-        row_to_nhw(r0, H, W, n, h, w);
-        float f[8], ge[8];
-        V8<TY>::load(y + (size_t)r0 * C + tc * 8, f);
-        GLoad<TG, MODE, GN> gl;
-        gl.issue(g, n, h, w, H, W, C, tc);
-        gl.finish(ge);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
-            s1[k] += dz;
-            sy[k] = fmaf(dz, f[k], sy[k]);
         }
     }
 #pragma unroll
@@ -498,17 +496,24 @@ bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, cons
     constexpr int U = MODE == FV_MODE_UP ? 2 : (ADD ? 4 : 6);
     const unsigned stride = gridDim.x * rpi;
     unsigned r0 = blockIdx.x * rpi + tr;
-    for (; r0 + (U - 1) * stride < P; r0 += U * stride) {
+    for (; r0 < P; r0 += U * stride) {
         Raw8<TY> yr[U];
         GLoad<TG, MODE, GN> gl[U];
         Raw8<__nv_bfloat16> ar[ADD ? U : 1];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            unsigned n = 0, h = 0, w = r0 + u * stride;
-            if (NEED_NHW) row_to_nhw(r0 + u * stride, H, W, n, h, w);
-            yr[u].load(y + (size_t)(r0 + u * stride) * C + tc * 8);
-            gl[u].issue(g, n, h, w, NEED_NHW ? H : 1, NEED_NHW ? W : (int)P, C, tc);
-            if (ADD) ar[ADD ? u : 0].load(add + (size_t)(r0 + u * stride) * C + tc * 8);
+            const unsigned row = r0 + u * stride;
+            if (row < P) {
+                unsigned n = 0, h = 0, w = row;
+                if (NEED_NHW) row_to_nhw(row, H, W, n, h, w);
+                yr[u].load(y + (size_t)row * C + tc * 8);
+                gl[u].issue(g, n, h, w, NEED_NHW ? H : 1, NEED_NHW ? W : (int)P, C, tc);
+                if (ADD) ar[ADD ? u : 0].load(add + (size_t)row * C + tc * 8);
+            } else {
+                yr[u].zero();
+                gl[u].zero();
+                if (ADD) ar[ADD ? u : 0].zero();
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -522,25 +527,8 @@ bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, cons
                 o[k] = fmaf(sc[k], dz, fmaf(cb[k], f[k], ca[k]));
                 if (ADD) o[k] += a[k];
             }
-            V8<__nv_bfloat16>::store(dy + (size_t)(r0 + u * stride) * C + tc * 8, o);
+            if (r0 + u * stride < P) V8<__nv_bfloat16>::store(dy + (size_t)(r0 + u * stride) * C + tc * 8, o);
         }
-    }
-    for (; r0 < P; r0 += stride) {
-        unsigned n, h, w;
-        row_to_nhw(r0, H, W, n, h, w);
-        float f[8], ge[8], o[8], a[8];
-        V8<TY>::load(y + (size_t)r0 * C + tc * 8, f);
-        GLoad<TG, MODE, GN> gl;
-        gl.issue(g, n, h, w, H, W, C, tc);
-        gl.finish(ge);
-        if (ADD) V8<__nv_bfloat16>::load(add + (size_t)r0 * C + tc * 8, a);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float dz = ge[k] * act_grad(fmaf(f[k], sc[k], sf[k]), act);
-            o[k] = fmaf(sc[k], dz, fmaf(cb[k], f[k], ca[k]));
-            if (ADD) o[k] += a[k];
-        }
-        V8<__nv_bfloat16>::store(dy + (size_t)r0 * C + tc * 8, o);
     }
 }
 
@@ -764,10 +752,12 @@ extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const floa
     return FV_OK;
 }
 
-static int reduce_geometry(int C, long long P, int& grid, size_t& shmem) {
+static int reduce_geometry(int C, long long P, int& grid, size_t& shmem, int resident = 2) {
     const int rpi = kThreads / (C / 8) > 0 ? kThreads / (C / 8) : 1;
     long long blocks = (P + rpi - 1) / rpi;
-    const long long cap = (long long)num_sms() * 8;
+    // small tensors: one resident wave (the fixed per-block cost dominates); large tensors: 8 blocks per SM -- measured
+    // ~5 % faster there than a single wave (more independent streams keep DRAM busier through block start / tail phases)
+    const long long cap = (long long)num_sms() * (blocks > (long long)num_sms() * 64 ? 8 : resident);
     grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
     shmem = (size_t)2 * rpi * C * sizeof(float);
     return rpi;
@@ -777,7 +767,7 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_stats(const void* y,
     if (!y || !sums) return fail(FV_ERR_ARG, "fv_bn_stats: null pointer");
     if (int e = check_c8("fv_bn_stats", C)) return e;
     int grid; size_t sh;
-    reduce_geometry(C, P, grid, sh);
+    reduce_geometry(C, P, grid, sh, 4);            // 51 registers: four 256-thread blocks per SM
     if (dtype == FV_DT_BF16)
         bn_stats_kernel<__nv_bfloat16><<<grid, kThreads, sh, STREAM>>>((const __nv_bfloat16*)y, sums, P, C);
     else
@@ -810,7 +800,7 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_fwd(const void* 
     if (mode == FV_MODE_POOL && ((H | W) & 1)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: pooling needs even H, W");
     if (nchw_out && (out_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: NCHW output is fp32, no upsample");
     const int Ho = mode == FV_MODE_POOL ? H / 2 : H, Wo = mode == FV_MODE_POOL ? W / 2 : W;
-    const int grid = grid_for((long long)N * Ho * Wo * (C / 8));
+    const int grid = grid_for((long long)N * Ho * Wo * (C / 8), kThreads, 3);   // 79 registers: three blocks per SM
 #define LAUNCH(TI, TO) do { \
         if (mode == FV_MODE_POOL) bn_act_fwd_kernel<TI, TO, FV_MODE_POOL><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, act, nchw_out); \
         else if (mode == FV_MODE_UP) bn_act_fwd_kernel<TI, TO, FV_MODE_UP><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, act, nchw_out); \

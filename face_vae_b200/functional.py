@@ -351,29 +351,60 @@ class ReconLossFlat(torch.autograd.Function):
         return (out if ctx.needs_input_grad[0] else None), (-out if ctx.needs_input_grad[1] else None), None
 
 
+def _outconv_fold_ok(d: torch.Tensor, weight: torch.Tensor) -> bool:
+    import os
+    if os.environ.get("FACEVAE_OUTCONV_FOLD", "1") == "0":
+        return False
+    n, h, w, cp = d.shape
+    co, ci, k = weight.shape[0], weight.shape[1], weight.shape[2]
+    return ci == cp and weight.shape[2] == weight.shape[3] and ops.outconv_supported(n, h, w, cp, co, k)
+
+
 class ConvSigmoidRecon(torch.autograd.Function):
     """out_conv (7x7, reference models.py:1099) -> sigmoid (models.py:1110) -> ReconLoss against the target frame
-    (losses.py:396-403, trainer.py:314), fused: the loss kernel also emits d(loss)/d(logits) as the NHWC bf16 tensor the
-    conv's dgrad / wgrad consume.  Returns (x_hat NCHW fp32, mean loss)."""
+    (losses.py:396-403, trainer.py:314), fused.  Full-resolution shapes (W = 128 / 256) run the tap-folded kernels of
+    csrc/fv_outconv.cu: ONE forward kernel produces x_hat, the loss sum, the compact gradient d(loss)/d(logits) and the
+    bias gradient; dgrad / wgrad consume the compact gradient and apply the upstream scalar in their epilogues.  Other
+    shapes: generic conv + loss kernel (the loss kernel emits the NHWC bf16 gradient the generic dgrad / wgrad consume).
+    Returns (x_hat NCHW fp32, mean loss)."""
 
     @staticmethod
     def forward(ctx, d, weight, bias, target, l1):
         co, ci, ksize = weight.shape[0], weight.shape[1], weight.shape[2]
+        ctx.cfg = (ksize, co, ci)
+        ctx.has_bias = bias is not None
+        ctx.fold = _outconv_fold_ok(d, weight)
+        if ctx.fold:
+            wq, wdq = ops.outconv_prep(weight, True, d.requires_grad)
+            e = d.shape[0] * co * d.shape[1] * d.shape[2]
+            out = ops.outconv_fwd(d, wq, bias, co, target=target.contiguous().float(), l1=l1, gscale=1.0 / e)
+            ctx.save_for_backward(d, weight, out["g4"], wdq, out["gsum"])
+            ctx.mark_non_differentiable(out["pred"])
+            return out["pred"], out["loss_sum"][0] / e
         wf, wd = ops.weight_prep(weight, True, d.requires_grad)
         logits = ops.conv2d(d, wf, bias, co, ksize, None, OUT_NCHW_F32, (ci, co))
         e = logits.numel()
         loss, pred, _, gn = ops.recon_loss(logits, target.contiguous().float(), l1, True, 1.0 / e, True, False, True)
         ctx.save_for_backward(d, weight, gn, wd)
-        ctx.cfg = (ksize, co, ci)
-        ctx.has_bias = bias is not None
         ctx.mark_non_differentiable(pred)
         return pred, loss[0] / e
 
     @staticmethod
     def backward(ctx, _gpred, gl):
-        d, weight, gn, wd = ctx.saved_tensors
         ksize, co, ci = ctx.cfg
-        g = ops.scale(gn, gl.reshape(1).float().contiguous(), 1.0)
+        gl = gl.reshape(1).float().contiguous()
+        if ctx.fold:
+            d, weight, g4, wdq, gsum = ctx.saved_tensors
+            db = gsum * gl if ctx.has_bias else None
+            dw = ops.outconv_wgrad(d, g4, gl, co)
+            dx = None
+            if ctx.needs_input_grad[0]:
+                if wdq is None:
+                    _, wdq = ops.outconv_prep(weight, False, True)
+                dx = ops.outconv_dgrad(g4, wdq, gl, co)
+            return dx, dw, db, None, None
+        d, weight, gn, wd = ctx.saved_tensors
+        g = ops.scale(gn, gl, 1.0)
         db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
         acc = ops.conv2d_wgrad(d, g, ksize, (ci, co))
         dw = ops.wgrad_finish(acc, co, ci, ksize)

@@ -156,6 +156,74 @@ def colsum(y: torch.Tensor) -> torch.Tensor:
     return sums
 
 
+# ------------------------------------------------------------------------------------------------ out_conv (7x7, 32 -> <= 4)
+def outconv_supported(n: int, h: int, w: int, ci: int, co: int, k: int) -> bool:
+    """Shapes the tap-folded out_conv kernels (csrc/fv_outconv.cu) take; everything else goes through conv2d."""
+    return bool(_lib.load().fv_outconv_supported(n, h, w, ci, co, k, k))
+
+
+def outconv_prep(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = True):
+    """nn.Conv2d weight [Co,32,7,7] fp32 -> (wq, wdq) bf16 [7,32,32] folded operands of the forward / data-gradient GEMMs."""
+    _chk(w, "weight", torch.float32)
+    co, ci = w.shape[0], w.shape[1]
+    wq = torch.empty((7, 32, 32), device=w.device, dtype=torch.bfloat16) if want_fwd else None
+    wdq = torch.empty((7, 32, 32), device=w.device, dtype=torch.bfloat16) if want_dgrad else None
+    call("fv_outconv_prep", w.data_ptr(), _ptr(wq), _ptr(wdq), co, ci, _stream())
+    return wq, wdq
+
+
+def outconv_fwd(x: torch.Tensor, wq: torch.Tensor, bias: Optional[torch.Tensor], co: int, target: Optional[torch.Tensor] = None,
+                l1: bool = False, use_sigmoid: bool = True, gscale: float = 1.0, want_logits: Optional[bool] = None,
+                want_pred: bool = True):
+    """x NHWC bf16 [N,H,W,32] -> dict(logits, pred, g4, loss_sum, gsum); the loss entries need ``target`` (NCHW fp32)."""
+    _chk(x, "x", torch.bfloat16)
+    _chk(wq, "wq", torch.bfloat16)
+    n, h, w, ci = x.shape
+    fused = target is not None
+    if want_logits is None:
+        want_logits = not fused
+    dev = x.device
+    logits = torch.empty((n, co, h, w), device=dev, dtype=torch.float32) if want_logits else None
+    pred = g4 = acc = None
+    if fused:
+        _chk(target, "target", torch.float32)
+        if tuple(target.shape) != (n, co, h, w):
+            raise _lib.FaceVaeError("outconv_fwd: target shape mismatch")
+        pred = torch.empty((n, co, h, w), device=dev, dtype=torch.float32) if want_pred else None
+        g4 = torch.empty((n, h, w, 4), device=dev, dtype=torch.bfloat16)
+        acc = torch.zeros((8,), device=dev, dtype=torch.float32)         # [0]: loss sum, [4:8]: gradient sums per channel
+    if bias is not None:
+        _chk(bias, "bias", torch.float32)
+    meta = _conv_meta(n, h, w, ci, 32, 7, (ci, co))
+    call("fv_outconv_fwd", x.data_ptr(), wq.data_ptr(), _ptr(bias), _ptr(logits), _ptr(target), _ptr(pred), _ptr(g4),
+         _ptr(acc), None if acc is None else acc[4:].data_ptr(), n, h, w, ci, co, int(l1), int(use_sigmoid), float(gscale),
+         _stream(), meta=meta)
+    return {"logits": logits, "pred": pred, "g4": g4, "loss_sum": None if acc is None else acc[:1],
+            "gsum": None if acc is None else acc[4:4 + co]}
+
+
+def outconv_dgrad(g4: torch.Tensor, wdq: torch.Tensor, scale_ptr: Optional[torch.Tensor], co: int) -> torch.Tensor:
+    _chk(g4, "g4", torch.bfloat16)
+    n, h, w, c4 = g4.shape
+    if c4 != 4:
+        raise _lib.FaceVaeError("outconv_dgrad: g4 must be [N,H,W,4]")
+    dx = torch.empty((n, h, w, 32), device=g4.device, dtype=torch.bfloat16)
+    call("fv_outconv_dgrad", g4.data_ptr(), wdq.data_ptr(), _ptr(scale_ptr), dx.data_ptr(), n, h, w, 32, co, _stream(),
+         meta=_conv_meta(n, h, w, 32, 32, 7, (co, 32)))
+    return dx
+
+
+def outconv_wgrad(x: torch.Tensor, g4: torch.Tensor, scale_ptr: Optional[torch.Tensor], co: int) -> torch.Tensor:
+    """-> dw fp32 [co, 32, 7, 7] (nn.Conv2d layout)."""
+    _chk(x, "x", torch.bfloat16)
+    _chk(g4, "g4", torch.bfloat16)
+    n, h, w, ci = x.shape
+    dw = torch.zeros((co, ci, 7, 7), device=x.device, dtype=torch.float32)
+    call("fv_outconv_wgrad", x.data_ptr(), g4.data_ptr(), _ptr(scale_ptr), dw.data_ptr(), n, h, w, ci, co, _stream(),
+         meta=_conv_meta(n, h, w, ci, 32, 7, (ci, co)))
+    return dw
+
+
 # ------------------------------------------------------------------------------------------------ batch norm glue
 def bn_stats(y: torch.Tensor) -> torch.Tensor:
     _chk(y, "y")

@@ -56,6 +56,27 @@ int fv_wgrad_finish(const float* dw_acc, float* grad, int Co, int Ci, int R, int
 /* sums[C] (caller-zeroed) += per-channel sums over P rows of an NHWC bf16 tensor: the bias gradient. */
 int fv_colsum(const void* y, float* sums, long long P, int C, void* stream);
 
+/* ---- out_conv: nn.Conv2d(32, 3, 7, padding 3) (models.py:1099) -> torch.sigmoid (models.py:1110) -> ReconLoss
+ *      (losses.py:396-403, trainer.py:314), tap-folded tcgen05 schedule (csrc/fv_outconv.cu).  Shapes: 7x7 filter,
+ *      Ci = 32, Co <= 4, W = 128 or 256 (fv_outconv_supported() != 0); other shapes use fv_conv2d. ----------------- */
+int fv_outconv_supported(int N, int H, int W, int Ci, int Co, int R, int S);
+/* weight [Co,Ci,7,7] fp32 -> wq bf16 [7][32][32] (forward operand: rows (s,co), K = ci) and wdq bf16 [7][32][32]
+ * (data-gradient operand: rows ci, K = (s',co), taps rotated).  Either may be NULL. */
+int fv_outconv_prep(const float* w, void* wq, void* wdq, int Co, int Ci, void* stream);
+/* x: NHWC bf16 [N,H,W,32].  logits (NCHW fp32 [N,Co,H,W], optional when target is given) = conv(x) + bias.  With
+ * target (NCHW fp32) the epilogue also produces pred = sigmoid(logits) (optional), loss_sum[1] += sum l(pred - target)
+ * (caller-zeroed), g4 = bf16 [N,H,W,4]: gscale * dloss/dlogits (channels Co..3 zero) and gsum[4] += its per-channel sums
+ * (caller-zeroed: the bias gradient). */
+int fv_outconv_fwd(const void* x, const void* wq, const float* bias, float* logits, const float* target, float* pred, void* g4,
+                   float* loss_sum, float* gsum, int N, int H, int W, int Ci, int Co, int l1, int use_sigmoid, float gscale,
+                   void* stream);
+/* dx NHWC bf16 [N,H,W,32] = (*scale_ptr) * conv_transpose(g4, w) (scale_ptr may be NULL); g4 as written by fv_outconv_fwd. */
+int fv_outconv_dgrad(const void* g4, const void* wdq, const float* scale_ptr, void* dx, int N, int H, int W, int Ci, int Co,
+                     void* stream);
+/* dw [Co,32,7,7] fp32 (nn.Conv2d layout, caller-zeroed) += (*scale_ptr) * sum_pixels x[pixel + tap] * g4[pixel]. */
+int fv_outconv_wgrad(const void* x, const void* g4, const float* scale_ptr, float* dw, int N, int H, int W, int Ci, int Co,
+                     void* stream);
+
 /* ---- nn.SyncBatchNorm (modules.py:19) + ReLU/LeakyReLU (modules.py:27,29) + AvgPool2d (modules.py:62,70) /
  *      nn.Upsample (modules.py:81,89) ---------------------------------------------------------------------- */
 /* sums[0..C) += sum y, sums[C..2C) += sum y^2 over P = N*H*W rows (caller-zeroed; all-reduced across ranks by the

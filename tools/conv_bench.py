@@ -55,6 +55,17 @@ def main():
             res["dgrad"] = timeit(lambda: ops.conv2d(dy, wd, None, cip, k), a.iters, flush)
         if "wgrad" in a.what:
             res["wgrad"] = timeit(lambda: ops.conv2d_wgrad(x, dy, k), a.iters, flush)
+        if name == "out" and ops.outconv_supported(n, hw, hw, cip, co, k):
+            # the product path of this layer: tap-folded kernels (forward with the fused sigmoid + loss epilogue)
+            wq, wdq = ops.outconv_prep(w)
+            tgt = torch.rand((n, co, hw, hw), device="cuda")
+            g4 = (torch.randn((n, hw, hw, 4), device="cuda") * 0.01).bfloat16()
+            one = torch.ones((1,), device="cuda")
+            rf = {"fwd": timeit(lambda: ops.outconv_fwd(xf, wq, None, co, target=tgt, gscale=1e-6), a.iters, flush) if (xf := x) is not None else 0,
+                  "dgrad": timeit(lambda: ops.outconv_dgrad(g4, wdq, one, co), a.iters, flush),
+                  "wgrad": timeit(lambda: ops.outconv_wgrad(x, g4, one, co), a.iters, flush)}
+            print(f"{'out/gen':7s} {ci:4d} {co:4d} {k} {hw:4d} | " + " | ".join(f"{res[key]:8.3f} {flops / res[key] / 1e9:7.1f}" for key in ("fwd", "dgrad", "wgrad") if key in res), flush=True)
+            res = rf
         cells = []
         for key in ("fwd", "dgrad", "wgrad"):
             if key in res:
