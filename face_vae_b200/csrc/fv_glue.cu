@@ -3,6 +3,7 @@
 // fused with the KL reduction, and the reconstruction loss fused with its gradient.  Every kernel is a single
 // coalesced, 16-byte-vectorised pass (8 channels per thread in NHWC), sized in multiples of the SM count.
 #include <cmath>
+#include <type_traits>
 
 #include "../../include/facevae_b200.h"
 #include "fv_host.h"
@@ -145,6 +146,30 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* _
     }
 }
 
+// the same for a table of layers (blockIdx.y = layer): one launch per step instead of one per convolution
+__global__ void weight_prep_batched_kernel(const fv_prep_desc* __restrict__ table) {
+    const fv_prep_desc d = table[blockIdx.y];
+    const float* __restrict__ w = d.w;
+    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(d.wf);
+    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(d.wd);
+    const unsigned taps = d.R * d.S, cip = d.Ci_pad, cop = d.Co_pad;
+    const unsigned nf = cop * taps * cip;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) {
+        if (wf) {
+            const unsigned ci = i % cip, t2 = i / cip;
+            const unsigned tap = t2 % taps, co = t2 / taps;
+            const float v = (co < (unsigned)d.Co && ci < (unsigned)d.Ci) ? __ldg(w + (co * d.Ci + ci) * taps + tap) : 0.f;
+            wf[i] = __float2bfloat16(v);
+        }
+        if (wd) {
+            const unsigned co = i % cop, t2 = i / cop;
+            const unsigned tap = t2 % taps, ci = t2 / taps;
+            const float v = (co < (unsigned)d.Co && ci < (unsigned)d.Ci) ? __ldg(w + (co * d.Ci + ci) * taps + (taps - 1 - tap)) : 0.f;
+            wd[i] = __float2bfloat16(v);
+        }
+    }
+}
+
 // dWacc fp32 [Co_pad][taps][Ci_pad] -> grad fp32 [Co][Ci][R][S]
 __global__ void wgrad_finish_kernel(const float* __restrict__ acc, float* __restrict__ grad, int Co, int Ci, int taps,
                                     int Ci_pad, int accumulate) {
@@ -172,11 +197,14 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sum
     if (tr < rpi) {
         const long long stride = (long long)gridDim.x * rpi;
         long long r = (long long)blockIdx.x * rpi + tr;
-        for (; r < P; r += 8 * stride) {            // eight independent 16-byte loads in flight per thread (rows past the end: zeros)
+        // eight independent 16-byte loads in flight per thread; the main loop is unpredicated (conditional loads cost ~10 %
+        // of the bandwidth), the last partial batch is issued in one predicated batch (rows past the end: zeros)
+        auto batch = [&](long long rb, auto tag) {
+            constexpr bool PRED = decltype(tag)::value;
             Raw8<T> raw[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                if (r + u * stride < P) raw[u].load(y + (r + u * stride) * C + tc * 8);
+                if (!PRED || rb + u * stride < P) raw[u].load(y + (rb + u * stride) * C + tc * 8);
                 else raw[u].zero();
             }
 #pragma unroll
@@ -189,7 +217,9 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sum
                     q[k] = fmaf(f[k], f[k], q[k]);
                 }
             }
-        }
+        };
+        for (; r + 7 * stride < P; r += 8 * stride) batch(r, std::false_type{});
+        if (r < P) batch(r, std::true_type{});
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             sh[tr * C + tc * 8 + k] = s[k];
@@ -316,12 +346,13 @@ bn_act_fwd_kernel(const TI* __restrict__ y, const float* __restrict__ stat, TO* 
     };
     const unsigned stride = gridDim.x * blockDim.x;
     unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i0 < total; i0 += U * stride) {      // U independent elements: all loads first (elements past the end skipped)
+    auto batch = [&](unsigned ib, auto tag) {      // U independent elements: all loads first
+        constexpr bool PRED = decltype(tag)::value;
         Raw8<TI> raw[U][NL];
         unsigned n[U], ho[U], wo[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (i0 + u * stride < total) issue(i0 + u * stride, raw[u], n[u], ho[u], wo[u]);
+            if (!PRED || ib + u * stride < total) issue(ib + u * stride, raw[u], n[u], ho[u], wo[u]);
             else {
 #pragma unroll
                 for (int d = 0; d < NL; ++d) raw[u][d].zero();
@@ -330,8 +361,10 @@ bn_act_fwd_kernel(const TI* __restrict__ y, const float* __restrict__ stat, TO* 
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (i0 + u * stride < total) finish(raw[u], n[u], ho[u], wo[u]);
-    }
+            if (!PRED || ib + u * stride < total) finish(raw[u], n[u], ho[u], wo[u]);
+    };
+    for (; i0 + (U - 1) * stride < total; i0 += U * stride) batch(i0, std::false_type{});
+    if (i0 < total) batch(i0, std::true_type{});
 }
 
 // ---------------------------------------------------------------- norm + act backward
@@ -415,13 +448,14 @@ bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, con
     constexpr int U = MODE == FV_MODE_UP ? 2 : 8;
     const unsigned stride = gridDim.x * rpi;
     unsigned r0 = blockIdx.x * rpi + tr;
-    for (; r0 < P; r0 += U * stride) {
+    auto batch = [&](unsigned rb, auto tag) {
+        constexpr bool PRED = decltype(tag)::value;
         Raw8<TY> yr[U];
         GLoad<TG, MODE, GN> gl[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {                         // U rows of y and g in flight, 4 registers per 16-byte load
-            const unsigned row = r0 + u * stride;             // rows past the end load nothing and contribute zero (g = 0)
-            if (row < P) {
+            const unsigned row = rb + u * stride;             // (tail batch) rows past the end load nothing: g = 0
+            if (!PRED || row < P) {
                 unsigned n = 0, h = 0, w = row;               // MODE_NONE, NHWC g: the row index is the g index
                 if (NEED_NHW) row_to_nhw(row, H, W, n, h, w);
                 yr[u].load(y + (size_t)row * C + tc * 8);
@@ -443,7 +477,9 @@ bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, con
                 sy[k] = fmaf(dz, f[k], sy[k]);
             }
         }
-    }
+    };
+    for (; r0 + (U - 1) * stride < P; r0 += U * stride) batch(r0, std::false_type{});
+    if (r0 < P) batch(r0, std::true_type{});
 #pragma unroll
     for (int k = 0; k < 8; ++k) {                             // sum dz*xhat = invstd * (sum dz*y - mean * sum dz)
         const float mean = __ldg(stat + tc * 8 + k), invstd = __ldg(stat + C + tc * 8 + k);
@@ -496,14 +532,15 @@ bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, cons
     constexpr int U = MODE == FV_MODE_UP ? 2 : (ADD ? 4 : 6);
     const unsigned stride = gridDim.x * rpi;
     unsigned r0 = blockIdx.x * rpi + tr;
-    for (; r0 < P; r0 += U * stride) {
+    auto batch = [&](unsigned rb, auto tag) {
+        constexpr bool PRED = decltype(tag)::value;
         Raw8<TY> yr[U];
         GLoad<TG, MODE, GN> gl[U];
         Raw8<__nv_bfloat16> ar[ADD ? U : 1];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const unsigned row = r0 + u * stride;
-            if (row < P) {
+            const unsigned row = rb + u * stride;
+            if (!PRED || row < P) {
                 unsigned n = 0, h = 0, w = row;
                 if (NEED_NHW) row_to_nhw(row, H, W, n, h, w);
                 yr[u].load(y + (size_t)row * C + tc * 8);
@@ -527,9 +564,11 @@ bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, cons
                 o[k] = fmaf(sc[k], dz, fmaf(cb[k], f[k], ca[k]));
                 if (ADD) o[k] += a[k];
             }
-            if (r0 + u * stride < P) V8<__nv_bfloat16>::store(dy + (size_t)(r0 + u * stride) * C + tc * 8, o);
+            if (!PRED || rb + u * stride < P) V8<__nv_bfloat16>::store(dy + (size_t)(rb + u * stride) * C + tc * 8, o);
         }
-    }
+    };
+    for (; r0 + (U - 1) * stride < P; r0 += U * stride) batch(r0, std::false_type{});
+    if (r0 < P) batch(r0, std::true_type{});
 }
 
 // per-channel column sums of an NHWC bf16 tensor (bias gradient of a conv that does not feed a batch norm)
@@ -745,6 +784,17 @@ extern "C" __attribute__((visibility("default"))) int fv_weight_prep(const float
     return FV_OK;
 }
 
+extern "C" __attribute__((visibility("default"))) int fv_weight_prep_batched(const fv_prep_desc* table_dev, int n_layers, long long max_items, void* stream) {
+    if (!table_dev || n_layers < 1 || max_items < 1) return fail(FV_ERR_ARG, "fv_weight_prep_batched: bad arguments");
+    if (max_items >= (1LL << 31)) return fail(FV_ERR_UNSUPPORTED, "fv_weight_prep_batched: filter too large for 32-bit indexing");
+    long long bx = (max_items + kThreads * 2 - 1) / (kThreads * 2);
+    const long long cap = (long long)num_sms() * 8 / n_layers + 1;      // the whole table: about one resident wave
+    if (bx > cap) bx = cap;
+    weight_prep_batched_kernel<<<dim3((unsigned)bx, (unsigned)n_layers), kThreads, 0, STREAM>>>(table_dev);
+    FV_LAUNCH_CHECK("weight_prep_batched_kernel");
+    return FV_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const float* acc, float* grad, int Co, int Ci, int R, int S, int Ci_pad, int accumulate, void* stream) {
     if (!acc || !grad) return fail(FV_ERR_ARG, "fv_wgrad_finish: null pointer");
     wgrad_finish_kernel<<<grid_for((long long)Co * Ci * R * S), kThreads, 0, STREAM>>>(acc, grad, Co, Ci, R * S, Ci_pad, accumulate);
@@ -752,12 +802,15 @@ extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const floa
     return FV_OK;
 }
 
-static int reduce_geometry(int C, long long P, int& grid, size_t& shmem, int resident = 2) {
+static int reduce_geometry(int C, long long P, int& grid, size_t& shmem, int resident = 2, int rows_per_thread = 16) {
     const int rpi = kThreads / (C / 8) > 0 ? kThreads / (C / 8) : 1;
-    long long blocks = (P + rpi - 1) / rpi;
-    // small tensors: one resident wave (the fixed per-block cost dominates); large tensors: 8 blocks per SM -- measured
-    // ~5 % faster there than a single wave (more independent streams keep DRAM busier through block start / tail phases)
-    const long long cap = (long long)num_sms() * (blocks > (long long)num_sms() * 64 ? 8 : resident);
+    // Reductions end every block with a shared-memory pass and 2C global atomics: at least 16 rows per thread, so that a
+    // small tensor does not pay for a thousand blocks' worth of atomics on the same 2C addresses (14 us for 4 MB in round
+    // 1).  Small tensors: at most one resident wave (the fixed per-block cost dominates); large tensors: 8 blocks per SM,
+    // measured ~5 % faster there than a single wave.
+    const long long row_blocks = (P + rpi - 1) / rpi;
+    long long blocks = (row_blocks + rows_per_thread - 1) / rows_per_thread;
+    const long long cap = (long long)num_sms() * (row_blocks > (long long)num_sms() * 64 ? 8 : resident);
     grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
     shmem = (size_t)2 * rpi * C * sizeof(float);
     return rpi;
@@ -854,7 +907,7 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_apply(const 
     if (g_nchw && (g_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: NCHW g is fp32, no upsample");
     if (int e = check_c8("fv_bn_act_bwd_apply", C)) return e;
     int grid; size_t sh_unused;
-    reduce_geometry(C, (long long)N * H * W, grid, sh_unused);
+    reduce_geometry(C, (long long)N * H * W, grid, sh_unused, 2, 4);   // no block tail here: one batch of rows per thread
 #define LAUNCH4(TY, TG, M, GNF, AD) bn_act_bwd_apply_kernel<TY, TG, M, GNF, AD><<<grid, kThreads, 0, STREAM>>>((const TY*)y, (const TG*)g, stat, coef, (const __nv_bfloat16*)add, (__nv_bfloat16*)dy, N, H, W, C, act)
 #define LAUNCH3(TY, TG, M, GNF) do { if (add) LAUNCH4(TY, TG, M, GNF, true); else LAUNCH4(TY, TG, M, GNF, false); } while (0)
 #define LAUNCH2(TY, TG) do { \

@@ -53,6 +53,110 @@ def _chk(t: torch.Tensor, name: str, dtype=None):
     return t
 
 
+# ------------------------------------------------------------------------------------------------ per-step scope
+class _ZeroArena:
+    """Caller-zeroed scratch (statistic sums, weight-gradient accumulators, loss sums) for one train step: one buffer,
+    ONE memset at the start of the step, bump-allocated 256-byte-aligned slices -- instead of ~45 torch.zeros launches.
+    Slices are only valid until the next step starts; everything the kernels accumulate there is consumed inside the step."""
+
+    def __init__(self):
+        self.buf = None
+        self.offset = 0
+        self.need = 0
+        self.active = False
+
+    def begin(self, device):
+        want = max(self.need, 1 << 20)
+        if self.buf is None or self.buf.device != device or self.buf.numel() < want:
+            self.buf = torch.empty((int(want * 1.25) + 4096,), dtype=torch.uint8, device=device)
+        self.buf.zero_()          # the whole buffer: slices of a later, larger step must be clean as well (one memset)
+        self.offset = 0
+        self.need = 0
+        self.active = True
+
+    def take(self, shape, dtype, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = (n * torch.empty((), dtype=dtype).element_size() + 255) // 256 * 256
+        self.need += nbytes
+        if not self.active or self.buf is None or self.buf.device != device or self.offset + nbytes > self.buf.numel():
+            return None
+        view = self.buf[self.offset:self.offset + nbytes].view(dtype)[:n].view(shape)
+        self.offset += nbytes
+        return view
+
+
+_arena = _ZeroArena()
+
+
+def _zeros(shape, device, dtype=torch.float32) -> torch.Tensor:
+    t = _arena.take(tuple(shape), dtype, device) if _arena.active else None
+    return torch.zeros(shape, device=device, dtype=dtype) if t is None else t
+
+
+class _PrepCache:
+    """bf16 filter operands of every convolution of a model, produced by one batched launch per step."""
+
+    def __init__(self):
+        self.key = None
+        self.map = {}
+        self.table = None
+        self.max_items = 0
+        self.valid = False
+
+    def build(self, weights):
+        import numpy as np
+        dev = weights[0].device
+        rec = np.zeros((len(weights),), dtype=np.dtype([("w", "<u8"), ("wf", "<u8"), ("wd", "<u8"), ("dims", "<i4", (6,))]))
+        self.map = {}
+        self.max_items = 0
+        for i, w in enumerate(weights):
+            co, ci, r, s_ = w.shape
+            cop, cip = pad_channels(co), pad_channels(ci)
+            wf = torch.empty((cop, r * s_, cip), device=dev, dtype=torch.bfloat16)
+            wd = torch.empty((cip, r * s_, cop), device=dev, dtype=torch.bfloat16)
+            rec[i] = (w.data_ptr(), wf.data_ptr(), wd.data_ptr(), (co, ci, r, s_, cop, cip))
+            self.map[w.data_ptr()] = (wf, wd)
+            self.max_items = max(self.max_items, cop * cip * r * s_)
+        self.table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)
+        self.key = tuple(w.data_ptr() for w in weights)
+
+    def run(self, weights):
+        key = tuple(w.data_ptr() for w in weights)
+        if key != self.key:
+            self.build(weights)
+        call("fv_weight_prep_batched", self.table.data_ptr(), len(weights), self.max_items, _stream())
+        self.valid = True
+
+
+_prep = _PrepCache()
+
+
+class step_scope:
+    """``with ops.step_scope(model):`` around forward + backward of one train step (VAETrainer does this): the scratch
+    the kernels accumulate into comes from one arena zeroed by a single memset, and the bf16 filter operands of all
+    convolutions come from one batched launch.  Outside the scope every op allocates / prepares for itself."""
+
+    def __init__(self, module: Optional[torch.nn.Module] = None):
+        self.module = module
+
+    def __enter__(self):
+        weights = []
+        if self.module is not None:
+            weights = [p for p in self.module.parameters() if p.dim() == 4 and p.is_cuda and p.dtype == torch.float32
+                       and p.is_contiguous()]
+        if weights:
+            _arena.begin(weights[0].device)
+            _prep.run(weights)
+        return self
+
+    def __exit__(self, *exc):
+        _arena.active = False
+        _prep.valid = False
+        return False
+
+
 # ------------------------------------------------------------------------------------------------ layout
 def nchw_to_nhwc(x: torch.Tensor, cp: Optional[int] = None, dtype=torch.bfloat16) -> torch.Tensor:
     _chk(x, "x", torch.float32)
@@ -92,6 +196,10 @@ def weight_prep(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = True
                 ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
     """nn.Conv2d weight [Co,Ci,R,S] fp32 -> (wf [Co_pad,R*S,Ci_pad], wd [Ci_pad,R*S,Co_pad]) bf16."""
     _chk(w, "weight", torch.float32)
+    if _prep.valid:
+        hit = _prep.map.get(w.data_ptr())
+        if hit is not None:                      # prepared by this step's batched launch (ops.step_scope)
+            return (hit[0] if want_fwd else None), (hit[1] if want_dgrad else None)
     co, ci, r, s = w.shape
     cop, cip = pad_channels(co), pad_channels(ci)
     wf = torch.empty((cop, r * s, cip), device=w.device, dtype=torch.bfloat16) if want_fwd else None
@@ -133,7 +241,7 @@ def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, real_dims=None) 
     cop = dy.shape[3]
     if tuple(dy.shape[:3]) != (n, h, w):
         raise _lib.FaceVaeError("conv2d_wgrad: x / dy shape mismatch")
-    acc = torch.zeros((cop, ksize * ksize, ci), device=x.device, dtype=torch.float32)
+    acc = _zeros((cop, ksize * ksize, ci), x.device)
     call("fv_conv2d_wgrad", x.data_ptr(), dy.data_ptr(), acc.data_ptr(), n, h, w, ci, cop, ksize, ksize,
          (ksize - 1) // 2, _stream(), meta=_conv_meta(n, h, w, ci, cop, ksize, real_dims))
     return acc
@@ -151,7 +259,7 @@ def wgrad_finish(acc: torch.Tensor, co: int, ci: int, ksize: int, grad: Optional
 def colsum(y: torch.Tensor) -> torch.Tensor:
     _chk(y, "y", torch.bfloat16)
     c = y.shape[-1]
-    sums = torch.zeros((c,), device=y.device, dtype=torch.float32)
+    sums = _zeros((c,), y.device)
     call("fv_colsum", y.data_ptr(), sums.data_ptr(), y.numel() // c, c, _stream())
     return sums
 
@@ -191,7 +299,7 @@ def outconv_fwd(x: torch.Tensor, wq: torch.Tensor, bias: Optional[torch.Tensor],
             raise _lib.FaceVaeError("outconv_fwd: target shape mismatch")
         pred = torch.empty((n, co, h, w), device=dev, dtype=torch.float32) if want_pred else None
         g4 = torch.empty((n, h, w, 4), device=dev, dtype=torch.bfloat16)
-        acc = torch.zeros((8,), device=dev, dtype=torch.float32)         # [0]: loss sum, [4:8]: gradient sums per channel
+        acc = _zeros((8,), dev)         # [0]: loss sum, [4:8]: gradient sums per channel
     if bias is not None:
         _chk(bias, "bias", torch.float32)
     meta = _conv_meta(n, h, w, ci, 32, 7, (ci, co))
@@ -218,7 +326,7 @@ def outconv_wgrad(x: torch.Tensor, g4: torch.Tensor, scale_ptr: Optional[torch.T
     _chk(x, "x", torch.bfloat16)
     _chk(g4, "g4", torch.bfloat16)
     n, h, w, ci = x.shape
-    dw = torch.zeros((co, ci, 7, 7), device=x.device, dtype=torch.float32)
+    dw = torch.zeros((co, ci, 7, 7), device=x.device, dtype=torch.float32)   # becomes .grad: not arena memory
     call("fv_outconv_wgrad", x.data_ptr(), g4.data_ptr(), _ptr(scale_ptr), dw.data_ptr(), n, h, w, ci, co, _stream(),
          meta=_conv_meta(n, h, w, ci, 32, 7, (ci, co)))
     return dw
@@ -228,7 +336,7 @@ def outconv_wgrad(x: torch.Tensor, g4: torch.Tensor, scale_ptr: Optional[torch.T
 def bn_stats(y: torch.Tensor) -> torch.Tensor:
     _chk(y, "y")
     c = y.shape[-1]
-    sums = torch.zeros((2 * c,), device=y.device, dtype=torch.float32)
+    sums = _zeros((2 * c,), y.device)
     call("fv_bn_stats", y.data_ptr(), _dt(y), sums.data_ptr(), y.numel() // c, c, _stream(), meta=_bytes(y))
     return sums
 
@@ -268,7 +376,7 @@ def bn_act_bwd_reduce(y: torch.Tensor, g: torch.Tensor, stat: torch.Tensor, mode
     _chk(y, "y")
     _chk(g, "g")
     n, h, w, c = y.shape
-    sums = torch.zeros((2 * c,), device=y.device, dtype=torch.float32)
+    sums = _zeros((2 * c,), y.device)
     call("fv_bn_act_bwd_reduce", y.data_ptr(), _dt(y), g.data_ptr(), _dt(g), int(g_nchw), stat.data_ptr(),
          sums.data_ptr(), n, h, w, c, mode, act, _stream(), meta=_bytes(y, g))
     return sums
@@ -305,7 +413,7 @@ def reparam_kl_fwd(mu: torch.Tensor, logstd: torch.Tensor, eps: Optional[torch.T
     if mu.stride(1) != 1 or logstd.stride(1) != 1 or mu.stride(0) != logstd.stride(0):
         raise _lib.FaceVaeError("reparam_kl_fwd: mu/logstd must be row views with a common row stride")
     z = torch.empty((n, dz), device=mu.device, dtype=torch.float32) if want_z else None
-    kl = torch.zeros((n,), device=mu.device, dtype=torch.float32) if want_kl else None
+    kl = _zeros((n,), mu.device) if want_kl else None
     if eps is not None:
         _chk(eps, "eps", torch.float32)
     call("fv_reparam_kl_fwd", mu.data_ptr(), logstd.data_ptr(), mu.stride(0), _ptr(eps), _ptr(z), _ptr(kl), n, dz,
@@ -332,7 +440,7 @@ def recon_loss(logits: torch.Tensor, target: torch.Tensor, l1: bool = False, use
     _chk(target, "target", torch.float32)
     n, c, h, w = logits.shape
     cp = pad_channels(c)
-    loss = torch.zeros((1,), device=logits.device, dtype=torch.float32)
+    loss = _zeros((1,), logits.device)
     pred = torch.empty_like(logits) if want_pred else None
     gf = torch.empty_like(logits) if want_grad_f32 else None
     gn = torch.empty((n, h, w, cp), device=logits.device, dtype=torch.bfloat16) if want_grad_nhwc else None
@@ -344,7 +452,7 @@ def recon_loss(logits: torch.Tensor, target: torch.Tensor, l1: bool = False, use
 def recon_loss_flat(a: torch.Tensor, b: torch.Tensor, l1: bool = False, gscale: float = 1.0, want_grad: bool = True):
     _chk(a, "a", torch.float32)
     _chk(b, "b", torch.float32)
-    loss = torch.zeros((1,), device=a.device, dtype=torch.float32)
+    loss = _zeros((1,), a.device)
     grad = torch.empty_like(a) if want_grad else None
     call("fv_recon_loss_flat", a.data_ptr(), b.data_ptr(), _ptr(grad), loss.data_ptr(), a.numel(), int(l1), float(gscale),
          _stream())
@@ -363,7 +471,7 @@ def pw_moments(x: torch.Tensor) -> torch.Tensor:
     """x NCHW fp32 [N,C,H,W], C <= 4 -> double [C + C*C]: sum x_c | sum x_c x_d."""
     _chk(x, "x", torch.float32)
     n, c, h, w = x.shape
-    sums = torch.zeros((c + c * c,), device=x.device, dtype=torch.float64)
+    sums = _zeros((c + c * c,), x.device, torch.float64)
     call("fv_pw_moments", x.data_ptr(), sums.data_ptr(), n, c, h * w, _stream(), meta=_bytes(x))
     return sums
 
@@ -390,7 +498,7 @@ def pw_bwd_reduce(x: torch.Tensor, g: torch.Tensor, coef: torch.Tensor, act: int
     _chk(g, "g", torch.bfloat16)
     n, c, h, w = x.shape
     co = coef.shape[0]
-    sums = torch.zeros((co + co * c,), device=x.device, dtype=torch.float64)
+    sums = _zeros((co + co * c,), x.device, torch.float64)
     call("fv_pw_bwd_reduce", x.data_ptr(), g.data_ptr(), coef.data_ptr(), sums.data_ptr(), n, c, h * w, co, act, _stream(),
          meta=_bytes(x, g))
     return sums

@@ -73,10 +73,12 @@ class VAETrainer:
 
     # -- eager ----------------------------------------------------------------------------------------------------
     def _eager_step(self, d: torch.Tensor, eps: Optional[torch.Tensor]):
+        from . import ops
         self.optimizer.zero_grad(set_to_none=True)
-        losses, generated, mu, logstd = self.g_full(d, eps, True)
-        total = sum(losses.values())
-        total.backward()
+        with ops.step_scope(self.vae):          # one memset for all accumulators, one launch for all filter operands
+            losses, generated, mu, logstd = self.g_full(d, eps, True)
+            total = sum(losses.values())
+            total.backward()
         if self.reducer is not None:
             self.reducer.finish()
         self.optimizer.step()
@@ -112,10 +114,12 @@ class VAETrainer:
         graph = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
         l0 = _lib.launch_count
+        from . import ops
         with torch.cuda.graph(graph):
-            losses, generated, _, _ = self.g_full(self._static_d, self._static_eps, True)
-            total = sum(losses.values())
-            total.backward()
+            with ops.step_scope(self.vae):
+                losses, generated, _, _ = self.g_full(self._static_d, self._static_eps, True)
+                total = sum(losses.values())
+                total.backward()
             if self.reducer is not None:
                 self.reducer.finish()
             self.optimizer.step()

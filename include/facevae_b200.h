@@ -41,6 +41,15 @@ int fv_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int N, int C, in
 /* nn.Conv2d weight [Co,Ci,R,S] fp32 -> wf bf16 [Co_pad][R*S][Ci_pad] (forward operand) and
  * wd bf16 [Ci_pad][R*S][Co_pad], taps rotated 180 degrees (data-gradient operand).  Either may be NULL. */
 int fv_weight_prep(const float* w, void* wf, void* wd, int Co, int Ci, int R, int S, int Co_pad, int Ci_pad, void* stream);
+/* The same for a table of layers in ONE launch (device array of n_layers descriptors; max_items = the largest
+ * Co_pad*R*S*Ci_pad in the table): the per-step filter preparation of a whole network. */
+typedef struct {
+    const float* w;
+    void* wf;
+    void* wd;
+    int Co, Ci, R, S, Co_pad, Ci_pad;
+} fv_prep_desc;
+int fv_weight_prep_batched(const fv_prep_desc* table_dev, int n_layers, long long max_items, void* stream);
 /* y = conv(x, wf) + bias (+ residual); stride 1, odd square filter, pad = (R-1)/2.  tcgen05 implicit GEMM.
  * x: NHWC bf16 [N,H,W,Ci] (Ci = 16, 32 or a multiple of 64); wf: [Co_pad][R*S][Ci]; bias: fp32 [Co] or NULL;
  * residual: NHWC bf16 [N,H,W,Co_pad] or NULL (the `x +` of ResBlock2D, modules.py:124-125);

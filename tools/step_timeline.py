@@ -86,6 +86,16 @@ def main():
           f"idle gaps {gaps / 1e3 / a.steps:.3f}, records/step {len(evs) / a.steps:.0f}")
     for name, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{c / a.steps:6.1f} x {us / c:8.2f} us = {us / a.steps / 1e3:7.3f} ms/step  {name}")
+    # per-launch durations (last traced step, launch order) of the multi-launch kernels
+    per = len(evs) // a.steps
+    last = evs[-per:]
+    seq = collections.OrderedDict()
+    for e in last:
+        seq.setdefault(e.name[:60], []).append(e.time_range.end - e.time_range.start)
+    print("\nper-launch us (last step, launch order):")
+    for name, ds in seq.items():
+        if 3 <= len(ds) <= 30 and "fv::" in name:
+            print(f"  {name:60s} " + " ".join(f"{d:.0f}" for d in ds))
 
 
 if __name__ == "__main__":
