@@ -40,6 +40,8 @@ struct ConvParams {
     int tx_bytes;         // bytes the TMA unit delivers per stage (what the full barrier is armed with)
     int out_mode, tmem_cols;
     int out_cs;           // channel stride (elements) of the NHWC output / residual rows (>= Co_pad when Co is split)
+    int co_parts, Nc;     // output channels split over co_parts CTAs per pixel tile (layers with fewer tiles than SMs): Nc = Co_pad / co_parts
+    int num_vtiles;       // num_tiles * co_parts
     const float* bias;
     const __nv_bfloat16* residual;
     void* out;
@@ -107,7 +109,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         {
             const bool leader = elect_one_sync();      // role loops stay warp-uniform; only the issue is predicated
             uint32_t st = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+                const int part = vt / p.num_tiles, tile = vt - part * p.num_tiles;
+                const int co0 = part * p.Nc;
                 const TileCoord t = decode_tile(p, tile);
                 for (int r = 0; r < p.R; ++r) {
                     const int hh = t.h0 + r - p.pad;
@@ -123,7 +127,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                                 tma_load_4d(a_dst, &tmX, &full[st], kc * KB, ww, hh, t.n0);
                             }
                             for (int sm = 0; sm < s_mmas; ++sm)
-                                if (leader) tma_load_2d(b_dst + sm * p.b_slice_stride, &tmW, &full[st], wtap + sm * p.Ci + kc * KB, 0);
+                                if (leader) tma_load_2d(b_dst + sm * p.b_slice_stride, &tmW, &full[st], wtap + sm * p.Ci + kc * KB, co0);
                             if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
                         }
                     }
@@ -133,16 +137,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     } else if (warp == 1) {
         {
             const bool leader = elect_one_sync();
-            const uint32_t idesc = umma_idesc_bf16(128, p.Co_pad, 0, 0);
+            const uint32_t idesc = umma_idesc_bf16(128, p.Nc, 0, 0);
             const uint64_t desc_hi = umma_smem_desc(0, 16, SBO, LAYOUT);   // template: all fields but the start address
             const uint32_t smem_base = smem_u32(smem);
             const int groups = p.R * s_loads * p.kc_blocks;
             uint32_t st = 0, ph = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+            for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
                 mbar_wait(&tempty[acc], aph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co_pad;
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Nc;
                 uint32_t accumulate = 0;
                 for (int g = 0; g < groups; ++g) {
                     mbar_wait(&full[st], ph);
@@ -171,18 +175,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int row = q * 32 + lane;       // tile row == pixel within the tile
         const int w_l = row % p.tw, h_l = (row / p.tw) % p.th, n_l = row / (p.tw * p.th);
         uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+        for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x, ++tcount) {
+            const int part = vt / p.num_tiles, tile = vt - part * p.num_tiles;
+            const int co0 = part * p.Nc;
             const TileCoord t = decode_tile(p, tile);
             const int w = t.w0 + w_l, h = t.h0 + h_l, n = t.n0 + n_l;
             const bool valid = n < p.N;
             const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * (uint32_t)p.Co_pad;
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * (uint32_t)p.Nc;
             const size_t pix = ((size_t)n * p.H + h) * p.W + w;
-            for (int c0 = 0; c0 < p.Co_pad; c0 += 16) {
+            for (int cl = 0; cl < p.Nc; cl += 16) {
+                const int c0 = co0 + cl;                       // global output channel of column cl
                 uint32_t v[16];
-                tmem_ld16(taddr + c0, v);
+                tmem_ld16(taddr + cl, v);
                 tmem_ld_wait();
                 if (valid) {
                     float f[16];
@@ -331,9 +338,17 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
     const int a_rows = p.slab ? p.tw + S - 1 : 128;
     const int b_slices = p.slab ? S : 1;
     p.a_off_b = (a_rows * row_bytes + 1023) & ~1023;
-    p.b_slice_stride = (Co_pad * row_bytes + 1023) & ~1023;
+    // fewer pixel tiles than half the SMs (the 16x16 ResBlock2D layers: 64 tiles): split the output channels over 2-4 CTAs
+    // per tile -- each streams only its slice of the filter, and twice / four times as many SMs work
+    p.co_parts = 1;
+    while (p.co_parts < 4 && p.num_tiles * p.co_parts * 2 <= num_sms() && Co_pad % (p.co_parts * 2 * 64) == 0 &&
+           out_mode != FV_OUT_NCHW_F32 && env_int("FV_CONV_COSPLIT", 1))
+        p.co_parts *= 2;
+    p.Nc = Co_pad / p.co_parts;
+    p.num_vtiles = p.num_tiles * p.co_parts;
+    p.b_slice_stride = (p.Nc * row_bytes + 1023) & ~1023;
     p.stage_stride = p.a_off_b + p.b_slice_stride * b_slices;
-    p.tx_bytes = a_rows * row_bytes + b_slices * Co_pad * row_bytes;
+    p.tx_bytes = a_rows * row_bytes + b_slices * p.Nc * row_bytes;
     const int groups = R * (p.slab ? 1 : S) * p.kc_blocks;
     int stages = (196 * 1024) / p.stage_stride;
     if (stages > 8) stages = 8;
@@ -344,7 +359,7 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
     p.stages = stages;
     p.out_mode = out_mode;
     int cols = 32;
-    while (cols < 2 * Co_pad) cols <<= 1;
+    while (cols < 2 * p.Nc) cols <<= 1;
     p.tmem_cols = cols;
     p.out_cs = out_cs;
     p.bias = bias;
@@ -361,11 +376,11 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
     {
         uint64_t dims[2] = {(uint64_t)R * S * Ci, (uint64_t)Co_pad};
         uint64_t str[1] = {(uint64_t)R * S * Ci * 2};
-        uint32_t box[2] = {(uint32_t)KB, (uint32_t)Co_pad};
+        uint32_t box[2] = {(uint32_t)KB, (uint32_t)p.Nc};
         if (int e = encode_tmap_bf16(&tmW, w, 2, dims, str, box, row_bytes)) return e;
     }
     const size_t smem = (size_t)p.stages * p.stage_stride + 1024 + 256 + (size_t)Co_pad * 4 + 64;
-    const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    const int grid = p.num_vtiles < num_sms() ? p.num_vtiles : num_sms();
     cudaStream_t s = (cudaStream_t)stream;
     if (KB == 64) return launch_conv<64>(tmX, tmW, p, smem, grid, s);
     if (KB == 32) return launch_conv<32>(tmX, tmW, p, smem, grid, s);

@@ -146,31 +146,44 @@ pw_bwd_reduce_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
         for (int c = 0; c <= C; ++c) acc[co][c] = 0.f;
     const long long P = (long long)N * HW;
     const long long stride = (long long)gridDim.x * (blockDim.x / 2);
-    for (long long p = blockIdx.x * (long long)(blockDim.x / 2) + (threadIdx.x >> 1); p < P; p += stride) {
-        const int n = (int)(p / HW), hw = (int)(p % HW);
-        float v[C];
+    // two pixels per thread and iteration, all loads issued before the arithmetic (one pixel in flight per thread left the
+    // kernel at 2 TB/s: 44 bytes per thread cannot cover the HBM latency)
+    constexpr int UP = 2;
+    for (long long p0 = blockIdx.x * (long long)(blockDim.x / 2) + (threadIdx.x >> 1); p0 < P; p0 += UP * stride) {
+        float v[UP][C];
+        uint4 raw[UP][CH / 8];
+        bool ok[UP];
 #pragma unroll
-        for (int c = 0; c < C; ++c) v[c] = __ldg(x + ((long long)n * C + c) * HW + hw);
-        const uint4* gp = reinterpret_cast<const uint4*>(g + p * CO + half * CH);
-        uint4 raw[CH / 8];
+        for (int u = 0; u < UP; ++u) {
+            const long long p = p0 + u * stride;
+            ok[u] = p < P;
+            const long long pc = ok[u] ? p : p0;
+            const int n = (int)(pc / HW), hw = (int)(pc % HW);
 #pragma unroll
-        for (int grp = 0; grp < CH / 8; ++grp) raw[grp] = __ldg(gp + grp);
+            for (int c = 0; c < C; ++c) v[u][c] = __ldg(x + ((long long)n * C + c) * HW + hw);
+            const uint4* gp = reinterpret_cast<const uint4*>(g + pc * CO + half * CH);
 #pragma unroll
-        for (int grp = 0; grp < CH / 8; ++grp) {
-            const float gg[8] = {bf16_lo(raw[grp].x), bf16_hi(raw[grp].x), bf16_lo(raw[grp].y), bf16_hi(raw[grp].y),
-                                 bf16_lo(raw[grp].z), bf16_hi(raw[grp].z), bf16_lo(raw[grp].w), bf16_hi(raw[grp].w)};
+            for (int grp = 0; grp < CH / 8; ++grp) raw[u][grp] = ok[u] ? __ldg(gp + grp) : make_uint4(0u, 0u, 0u, 0u);
+        }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int col = grp * 8 + k;
-                const float* cc = cs + (half * CH + col) * (C + 1);
-                float z = cc[C];
+        for (int u = 0; u < UP; ++u) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) z = fmaf(cc[c], v[c], z);
-                const float d = act == FV_ACT_RELU ? (z > 0.f ? 1.f : 0.f) : (act == FV_ACT_LEAKY ? (z > 0.f ? 1.f : 0.2f) : 1.f);
-                const float dz = gg[k] * d;
-                acc[col][C] += dz;
+            for (int grp = 0; grp < CH / 8; ++grp) {
+                const float gg[8] = {bf16_lo(raw[u][grp].x), bf16_hi(raw[u][grp].x), bf16_lo(raw[u][grp].y), bf16_hi(raw[u][grp].y),
+                                     bf16_lo(raw[u][grp].z), bf16_hi(raw[u][grp].z), bf16_lo(raw[u][grp].w), bf16_hi(raw[u][grp].w)};
 #pragma unroll
-                for (int c = 0; c < C; ++c) acc[col][c] = fmaf(dz, v[c], acc[col][c]);
+                for (int k = 0; k < 8; ++k) {
+                    const int col = grp * 8 + k;
+                    const float* cc = cs + (half * CH + col) * (C + 1);
+                    float z = cc[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) z = fmaf(cc[c], v[u][c], z);
+                    const float d = act == FV_ACT_RELU ? (z > 0.f ? 1.f : 0.f) : (act == FV_ACT_LEAKY ? (z > 0.f ? 1.f : 0.2f) : 1.f);
+                    const float dz = gg[k] * d;               // a pixel past the end carries g = 0
+                    acc[col][C] += dz;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[col][c] = fmaf(dz, v[u][c], acc[col][c]);
+                }
             }
         }
     }

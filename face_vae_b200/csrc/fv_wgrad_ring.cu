@@ -27,6 +27,9 @@ struct WRingParams {
     int b_off, b_slots, b_stride, b_tx;
     int bar_off, tmem_cols;
     float* dw;
+    // D[(tap t, ci), co] -> dw[ci + t * st + co * sb]: st = total input channels, sb = taps * st (dw already points at this
+    // launch's channel chunk when the wide operand is walked in chunks of 64)
+    long long st, sb;
     long long* trace;
 };
 
@@ -193,21 +196,21 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         mbar_wait(tfull, 0);
         tc_fence_after();
         FV_T0(t_epi);
-        const size_t co_stride = (size_t)p.taps * p.Ci;
         int mt = 0;
         for (int r = 0; r < p.R; ++r)
             for (int part = 0; part < p.tiles_per_r; ++part, ++mt) {
                 const int s = part * p.cpt + chunk;
                 const bool valid = s < p.S;
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + (uint32_t)mt * p.Co_pad;
-                float* dst = p.dw + (size_t)(r * p.S + s) * p.Ci + ci;
+                const int t = r * p.S + s;
+                float* dst = p.dw + ci + (size_t)t * p.st;
                 for (int c0 = 0; c0 < p.Co_pad; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c0, v);
                     tmem_ld_wait();
                     if (valid) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)(c0 + i) * co_stride, __uint_as_float(v[i]));
+                        for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)(c0 + i) * p.sb, __uint_as_float(v[i]));
                     }
                 }
             }
@@ -234,8 +237,10 @@ static int launch_wring(const CUtensorMap& tmX, const CUtensorMap& tmDY, const W
 }
 
 // FV_OK after launching, -1 when not eligible (caller falls through to the generic wgrad kernel).
-int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
-                          cudaStream_t stream) {
+// x / dy: NHWC operands of which Ci <= 64 / Co_pad <= 64 channels starting at the pointers are used; x_cs / dy_cs = their channel
+// strides in elements.  Output mapping: WRingParams.
+int conv2d_wgrad_ring_ex(const void* x, int x_cs, const void* dy, int dy_cs, float* dw_acc, long long st, long long sb, int N, int H,
+                         int W, int Ci, int Co_pad, int R, int S, int pad, cudaStream_t stream) {
     if ((S != 3 && S != 5 && S != 7) || R != S || W % 64 || Ci > 64 || Co_pad > 64) return -1;
     const int kPX = (W % 128 == 0) ? 128 : 64;
     const char* env = getenv("FV_WGRAD_RING");
@@ -264,6 +269,7 @@ int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, i
     while (cols < p.mt_total * Co_pad) cols <<= 1;
     p.tmem_cols = cols;
     p.dw = dw_acc;
+    p.st = st; p.sb = sb;
     p.trace = trace_ptr();
     const int sms = num_sms();
     p.blocks_per_cta = (p.num_blocks + sms - 1) / sms;
@@ -272,13 +278,13 @@ int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, i
     CUtensorMap tmX, tmDY;
     {
         uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[3] = {(uint64_t)Ci * 2, (uint64_t)W * Ci * 2, (uint64_t)H * W * Ci * 2};
+        uint64_t str[3] = {(uint64_t)x_cs * 2, (uint64_t)W * x_cs * 2, (uint64_t)H * W * x_cs * 2};
         uint32_t box[4] = {(uint32_t)Ci, (uint32_t)(kPX + S - 1), 1, 1};
         if (int e = encode_tmap_bf16(&tmX, x, 4, dims, str, box, arow)) return e;
     }
     {
         uint64_t dims[4] = {(uint64_t)Co_pad, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[3] = {(uint64_t)Co_pad * 2, (uint64_t)W * Co_pad * 2, (uint64_t)H * W * Co_pad * 2};
+        uint64_t str[3] = {(uint64_t)dy_cs * 2, (uint64_t)W * dy_cs * 2, (uint64_t)H * W * dy_cs * 2};
         uint32_t box[4] = {(uint32_t)Co_pad, (uint32_t)kPX, 1, 1};
         if (int e = encode_tmap_bf16(&tmDY, dy, 4, dims, str, box, brow)) return e;
     }
@@ -289,6 +295,34 @@ int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, i
     return FV_WR(16);
 #undef FV_WR
 #undef FV_WR2
+}
+
+// dW_acc[Co_pad][R*S][Ci] += ...   Ring schedule whenever one of the two channel counts is <= 64: the other operand is walked
+// in chunks of 64 channels, one launch per chunk (each pass re-reads the narrow operand).
+int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
+                          cudaStream_t stream) {
+    const long long taps = (long long)R * S;
+    if (Ci <= 64 && Co_pad <= 64)
+        return conv2d_wgrad_ring_ex(x, Ci, dy, Co_pad, dw_acc, Ci, taps * Ci, N, H, W, Ci, Co_pad, R, S, pad, stream);
+    const char* env = getenv("FV_WGRAD_RING_WIDE");
+    if (env && atoi(env) == 0) return -1;
+    if (Ci <= 64 && Co_pad % 64 == 0 && Co_pad <= 256) {                    // dY in chunks of 64 channels
+        for (int c0 = 0; c0 < Co_pad; c0 += 64) {
+            const int e = conv2d_wgrad_ring_ex(x, Ci, static_cast<const char*>(dy) + (size_t)c0 * 2, Co_pad, dw_acc + (size_t)c0 * taps * Ci, Ci,
+                                               taps * Ci, N, H, W, Ci, 64, R, S, pad, stream);
+            if (e) return e;                                                 // -1 on the first chunk: nothing launched yet
+        }
+        return FV_OK;
+    }
+    if (Co_pad <= 64 && Ci % 64 == 0 && Ci <= 256) {                        // x in chunks of 64 channels
+        for (int c0 = 0; c0 < Ci; c0 += 64) {
+            const int e = conv2d_wgrad_ring_ex(static_cast<const char*>(x) + (size_t)c0 * 2, Ci, dy, Co_pad, dw_acc + c0, Ci, taps * Ci, N, H, W,
+                                               64, Co_pad, R, S, pad, stream);
+            if (e) return e;
+        }
+        return FV_OK;
+    }
+    return -1;
 }
 
 }  // namespace fv

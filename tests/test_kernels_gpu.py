@@ -105,6 +105,13 @@ def test_conv_residual_and_f32_out(ops):
     _conv_case(ops, 2, 16, 16, 64, 32, 3, out_mode=OUT_NHWC_F32)
 
 
+@pytest.mark.parametrize("n,h,w,ci,co,res", [(8, 16, 16, 256, 256, True), (2, 16, 16, 256, 256, False), (4, 16, 32, 128, 128, False),
+                                             (3, 8, 8, 256, 192, True)])
+def test_conv_output_channel_split(ops, n, h, w, ci, co, res):
+    """Layers with fewer pixel tiles than half the SMs split the output channels over 2-4 CTAs per tile."""
+    _conv_case(ops, n, h, w, ci, co, 3, residual=res, seed=60)
+
+
 def test_conv_many_tiles_persistent(ops):
     # more tiles than SMs: exercises the persistent loop, TMEM double buffering and mbarrier phase wrap-around
     _conv_case(ops, 8, 64, 128, 32, 64, 3)
@@ -275,6 +282,10 @@ def test_conv_ring_schedule(ops, n, h, w, ci, co, k, out_mode):
     (3, 20, 128, 32, 3, 7),       # out_conv: 14 accumulators of 16 columns
     (2, 33, 64, 16, 32, 3),       # eight taps per M tile (32-byte slab rows)
     (2, 16, 192, 64, 64, 5),      # 5x5
+    (2, 24, 128, 64, 128, 3),     # enc.2-like: dY walked in two 64-channel chunks
+    (2, 24, 128, 128, 64, 3),     # up.2-like: x walked in two 64-channel chunks
+    (1, 10, 64, 32, 192, 3),      # three dY chunks, 32-channel slabs
+    (1, 10, 64, 256, 32, 3),      # four x chunks, dY padded to 32 channels
 ])
 def test_wgrad_ring_schedule(ops, n, h, w, ci, co, k):
     """Sliding-window weight gradient (fv_wgrad_ring.cu) against autograd."""
