@@ -28,6 +28,18 @@
 
 namespace fv {
 
+// Role-loop timing for FV_TRACE builds: cycle deltas accumulate in REGISTERS and are flushed once when the role ends (the
+// generic FV_TACC does a global read-modify-write per sample, ~300 cycles each, which swamps loops of ~1000 cycles).
+#ifdef FV_TRACE
+#define FVR_DECL long long fvr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define FVR_ACC(slot, var) fvr_acc[slot] += clock64() - (var)
+#define FVR_FLUSH(ptr) do { if ((ptr) && threadIdx.x % 32 == 0) { for (int i_ = 0; i_ < 8; ++i_) if (fvr_acc[i_]) atomicAdd((unsigned long long*)&(ptr)[(blockIdx.x % 148) * 8 + i_], (unsigned long long)fvr_acc[i_]); } } while (0)
+#else
+#define FVR_DECL
+#define FVR_ACC(slot, var)
+#define FVR_FLUSH(ptr)
+#endif
+
 static constexpr int kFR = 7;            // filter rows == filter columns
 static constexpr int kFC = 32;           // channels of the wide side (Ci of the forward conv) == record width
 static constexpr int kRowB = kFC * 2;    // bytes per pixel row of a slab / record (one 64-byte swizzle span)
@@ -37,7 +49,7 @@ static constexpr int kAcc = 4;           // TMEM accumulator buffers (64 columns
 struct FoldParams {
     int N, H, W, halves, Co, NQ, QS;
     int rows_total, rows_per_cta, ring, slab_bytes;
-    int w_off, q_off, bar_off;
+    int w_off, q_off, t_off, bar_off;
     // forward epilogue
     const float* bias;
     float* logits;                  // NCHW fp32 (optional when the loss is fused)
@@ -53,7 +65,7 @@ struct FoldParams {
     __nv_bfloat16* dx;
     const float* scale_ptr;
     long long* trace;
-    int dbg;                        // FV_FOLD_DEBUG bit mask (timing experiments only): 1 no MMAs, 2 no epilogue work, 4 no slab fill
+    int dbg;                        // FV_FOLD_DEBUG bit mask (tools/fold_experiments.py only): 1 no MMAs, 2 no epilogue work, 4 no slab fill
 };
 
 __device__ __forceinline__ uint32_t swz64(uint32_t byte_addr) {          // 64-byte swizzle: 16-byte chunk ^= address bits [7,9)
@@ -84,18 +96,19 @@ __device__ __forceinline__ void rec_store(const Rec& r, uint32_t rec_addr) {    
 
 // MODE 0: forward (slabs by TMA, shifted-sum epilogue).  MODE 1: data gradient (slabs = records built by warps 10..17).
 template <int MODE>
-__global__ void __launch_bounds__(MODE == 0 ? 320 : 576, 1)
+__global__ void __launch_bounds__(MODE == 0 ? 352 : 608, 1)
 fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const FoldParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.bar_off);
     uint64_t* empty = full + p.ring;
     uint64_t* tfull = empty + p.ring;
-    uint64_t* tempty = tfull + kAcc;
-    uint64_t* wfull = tempty + kAcc;
+    uint64_t* tempty = tfull + 2 * kAcc;                 // [kAcc][2 halves]
+    uint64_t* wfull = tempty + 2 * kAcc;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
     float* Qs = reinterpret_cast<float*>(smem + p.q_off);
 
+    constexpr int kIssuerB = MODE == 0 ? 10 : 18;       // second MMA issuer warp (the last warp of the CTA)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g0 = blockIdx.x * p.rows_per_cta;
     const int g1 = min(g0 + p.rows_per_cta, p.rows_total);
@@ -108,11 +121,11 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_prefetch_desc(&tmW);
         for (int i = 0; i < p.ring; ++i) {
             mbar_init(&full[i], MODE == 0 ? 1 : 32);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], p.halves);              // one vote per issuer warp
         }
-        for (int i = 0; i < kAcc; ++i) {
+        for (int i = 0; i < 2 * kAcc; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4 * p.halves);
+            mbar_init(&tempty[i], 4);
         }
         mbar_init(wfull, 1);
         fence_mbar_init();
@@ -144,7 +157,7 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int n = g / p.H, y = g - n * p.H;
                 const bool fresh = (g == g0) || (y == 0);
                 for (int j = fresh ? 0 : kFR - 1; j < kFR; ++j) {
-                    { FV_T0(tw); mbar_wait(&empty[slot], ph ^ 1); FV_TACC(0, tw); }
+                    mbar_wait(&empty[slot], ph ^ 1);
                     if (leader) {
                         if (p.dbg & 4) {
                             mbar_arrive(&full[slot]);
@@ -157,81 +170,77 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
-    } else if (warp == 1) {
-        const bool leader = elect_one_sync();
-        const uint32_t idesc = umma_idesc_bf16(128, 32, 0, 0);
-        const uint64_t tmpl = umma_smem_desc(0, 16, 8u * kRowB, 4u);          // K-major, 64-byte swizzle
-        const uint32_t desc_hi = (uint32_t)(tmpl >> 32), lo_base = (uint32_t)tmpl;
-        const uint32_t smem_base = smem_u32(smem);
-        const uint32_t w_lo = lo_base | ((smem_base + (uint32_t)p.w_off) >> 4);
-        uint32_t first = 0, wslot = 0, wph = 0, tcount = 0;
-        mbar_wait(wfull, 0);
-        FV_T0(t_all);
-        for (int g = g0; g < g1; ++g, ++tcount) {
-            const int y = g % p.H;
-            const bool fresh = (g == g0) || (y == 0);
-            const bool next_fresh = (g + 1 == g1) || (y + 1 == p.H);
-            if (fresh) first = wslot;
-            {
-                FV_T0(tw);
-                for (int i = fresh ? 0 : kFR - 1; i < kFR; ++i) {
-                    mbar_wait(&full[wslot], wph);
-                    if (++wslot == (uint32_t)p.ring) { wslot = 0; wph ^= 1; }
-                }
-                FV_TACC(1, tw);
-            }
-            const uint32_t acc = tcount % kAcc, aph = (tcount / kAcc) & 1;
-            { FV_T0(tw); mbar_wait(&tempty[acc], aph ^ 1); FV_TACC(2, tw); }
-            tc_fence_after();
-            FV_T0(t_issue);
-            // all descriptor words first, then ONE predicated block of back-to-back MMAs: a per-MMA address computation
-            // in front of every tcgen05.mma is a serial IMAD -> R2UR -> uniform-ALU chain of ~50 cycles (ncu, round 1)
-            uint32_t a_lo[kFR];
-            {
-                uint32_t slot = first;
-#pragma unroll
-                for (int r = 0; r < kFR; ++r) {
-                    a_lo[r] = lo_base | ((smem_base + slot * (uint32_t)p.slab_bytes) >> 4);
-                    if (++slot == (uint32_t)p.ring) slot = 0;
-                }
-            }
-            const uint32_t d_tmem = tmem_base + acc * 64u;
-            if (leader && (p.dbg & 8)) {               // timing experiment: 12 of the 28 MMAs
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        tc_mma_f16_lohi(d_tmem, a_lo[r] + 2 * k, w_lo + (uint32_t)(r * ((32 * kRowB) >> 4) + 2 * k), desc_hi, idesc, (uint32_t)(r | k));
-                        tc_mma_f16_lohi(d_tmem + 32u, a_lo[r] + (uint32_t)((128 * kRowB) >> 4) + 2 * k,
-                                        w_lo + (uint32_t)(r * ((32 * kRowB) >> 4) + 2 * k), desc_hi, idesc, (uint32_t)(r | k));
+    } else if (warp == 1 || warp == kIssuerB) {
+        // Two MMA issuer warps, one per 128-pixel half of the row.  The issuing thread is blocked for the ~45 cycles of
+        // every tcgen05.mma (tools/fold_experiments.py: time is linear in the MMA count, with the per-row bookkeeping --
+        // barrier waits, descriptor words, commits, ~600-1000 cycles -- purely additive), so a single issuer leaves the
+        // tensor pipe idle during its bookkeeping; with two, one warp's MMAs run during the other's bookkeeping.
+        const uint32_t ih = warp == 1 ? 0u : 1u;
+        if ((int)ih < p.halves) {
+            const bool leader = elect_one_sync();
+            const uint32_t idesc = umma_idesc_bf16(128, 32, 0, 0);
+            const uint64_t tmpl = umma_smem_desc(0, 16, 8u * kRowB, 4u);          // K-major, 64-byte swizzle
+            const uint32_t desc_hi = (uint32_t)(tmpl >> 32), lo_base = (uint32_t)tmpl;
+            const uint32_t smem_base = smem_u32(smem);
+            const uint32_t w_lo = lo_base | ((smem_base + (uint32_t)p.w_off) >> 4);
+            const uint32_t a_half = ih * (uint32_t)((128 * kRowB) >> 4);
+            uint32_t first = 0, wslot = 0, wph = 0, tcount = 0;
+            int y = g0 % p.H;
+            FVR_DECL;
+            mbar_wait(wfull, 0);
+            FV_T0(t_all);
+            for (int g = g0; g < g1; ++g, ++tcount) {
+                const bool fresh = (g == g0) || (y == 0);
+                const bool next_fresh = (g + 1 == g1) || (y + 1 == p.H);
+                if (++y == p.H) y = 0;
+                if (fresh) first = wslot;
+                {
+                    FV_T0(tw);
+                    for (int i = fresh ? 0 : kFR - 1; i < kFR; ++i) {
+                        mbar_wait(&full[wslot], wph);
+                        if (++wslot == (uint32_t)p.ring) { wslot = 0; wph ^= 1; }
                     }
-            } else if (leader && !(p.dbg & 1)) {
+                    if (ih == 0) FVR_ACC(1, tw);
+                }
+                const uint32_t acc = tcount % kAcc, aph = (tcount / kAcc) & 1;
+                { FV_T0(tw); mbar_wait(&tempty[acc * 2 + ih], aph ^ 1); if (ih == 0) FVR_ACC(2, tw); }
+                tc_fence_after();
+                FV_T0(t_desc);
+                // all descriptor words first, then ONE predicated block of back-to-back MMAs: a per-MMA address computation
+                // in front of every tcgen05.mma is a serial IMAD -> R2UR -> uniform-ALU chain of ~50 cycles (ncu, round 1)
+                uint32_t a_lo[kFR];
+                {
+                    uint32_t slot = first;
 #pragma unroll
-                for (int r = 0; r < kFR; ++r)
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        tc_mma_f16_lohi(d_tmem, a_lo[r] + 2 * k, w_lo + (uint32_t)(r * ((32 * kRowB) >> 4) + 2 * k), desc_hi, idesc,
-                                        (uint32_t)(r | k));
-                if (p.halves == 2) {
+                    for (int r = 0; r < kFR; ++r) {
+                        a_lo[r] = (lo_base | ((smem_base + slot * (uint32_t)p.slab_bytes) >> 4)) + a_half;
+                        if (++slot == (uint32_t)p.ring) slot = 0;
+                    }
+                }
+                const uint32_t d_tmem = tmem_base + acc * 64u + ih * 32u;
+                if (ih == 0) FVR_ACC(6, t_desc);
+                FV_T0(t_issue);
+                if (leader && !(p.dbg & 1)) {
 #pragma unroll
                     for (int r = 0; r < kFR; ++r)
 #pragma unroll
                         for (int k = 0; k < 2; ++k)
-                            tc_mma_f16_lohi(d_tmem + 32u, a_lo[r] + (uint32_t)((128 * kRowB) >> 4) + 2 * k,
-                                            w_lo + (uint32_t)(r * ((32 * kRowB) >> 4) + 2 * k), desc_hi, idesc, (uint32_t)(r | k));
+                            tc_mma_f16_lohi(d_tmem, a_lo[r] + 2 * k, w_lo + (uint32_t)(r * ((32 * kRowB) >> 4) + 2 * k), desc_hi, idesc,
+                                            (uint32_t)(r | k));
                 }
+                if (ih == 0) FVR_ACC(3, t_issue);
+                FV_T0(t_commit);
+                if (leader) tc_commit(&tfull[acc * 2 + ih]);
+                const int n_rel = next_fresh ? kFR : 1;
+                for (int i = 0; i < n_rel; ++i) {
+                    if (leader) tc_commit(&empty[first]);
+                    if (++first == (uint32_t)p.ring) first = 0;
+                }
+                if (ih == 0) FVR_ACC(4, t_commit);
             }
-            FV_TACC(3, t_issue);
-            FV_T0(t_commit);
-            if (leader) tc_commit(&tfull[acc]);
-            const int n_rel = next_fresh ? kFR : 1;
-            for (int i = 0; i < n_rel; ++i) {
-                if (leader) tc_commit(&empty[first]);
-                if (++first == (uint32_t)p.ring) first = 0;
-            }
-            FV_TACC(4, t_commit);
+            if (ih == 0) FVR_ACC(5, t_all);
+            FVR_FLUSH(p.trace);
         }
-        FV_TACC(5, t_all);
     } else if (warp < 10) {
         const int q = warp & 3, h = (warp - 2) >> 2;
         if (h < p.halves) {
@@ -246,43 +255,34 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float dscale = (MODE == 1 && p.scale_ptr) ? __ldg(p.scale_ptr) : 1.f;
             const int nthr = 128 * p.halves;
             const size_t plane = (size_t)p.H * p.W;
-            // the targets of row g + 1 are loaded while row g is processed (an epilogue warp has nothing else to hide the
-            // HBM latency behind: its work per row is a few hundred instructions)
-            float t_next[4] = {0.f, 0.f, 0.f, 0.f};
-            auto load_targets = [&](int gg) {
-                const int nn = gg / p.H, yy = gg - nn * p.H;
-                const float* tp = p.target + (size_t)nn * p.Co * plane + (size_t)yy * p.W + u;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (c < p.Co) t_next[c] = __ldg(tp + c * plane);
-            };
-            // ... and pulled into L2 four rows ahead (one 128-byte line per warp and channel), so that the register prefetch
-            // above sees L2 latency, which is shorter than a row; without it the loads cost more than the convolution
-            auto prefetch_targets = [&](int gg) {
-                if (lane == 0 && gg < g1) {
+            // The targets of a row are fetched three rows ahead with cp.async into a per-thread slot of shared memory.  Register
+            // prefetching does not work here: however far ahead the loads are issued (1, 2 and 4 rows were measured), the
+            // warp ends up waiting a full memory latency per row -- with six scoreboards per warp the long-lived load shares
+            // one with the row's own tcgen05.ld / LDS traffic and is waited on at its next reuse.  cp.async completion is
+            // tracked per thread by commit groups instead.
+            constexpr int kTRows = 3;
+            float* Ts = reinterpret_cast<float*>(smem + p.t_off);
+            const bool fused = MODE == 0 && p.target != nullptr;
+            auto fetch_targets = [&](int gg, int slot) {
+                if (fused && gg < g1 && !(p.dbg & 32)) {
                     const int nn = gg / p.H, yy = gg - nn * p.H;
                     const float* tp = p.target + (size_t)nn * p.Co * plane + (size_t)yy * p.W + u;
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
-                        if (c < p.Co) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + c * plane));
+                        if (c < p.Co)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(Ts + (slot * p.Co + c) * p.W + u)),
+                                         "l"(tp + c * plane)
+                                         : "memory");
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");          // one group per row, empty or not
             };
-            if (MODE == 0 && p.target && g0 < g1) {
-                load_targets(g0);
-                for (int i = 1; i < 4; ++i) prefetch_targets(g0 + i);
-            }
+            if (fused)
+                for (int i = 0; i < kTRows; ++i) fetch_targets(g0 + i, i);
             uint32_t tcount = 0;
+            float t_cur[4] = {0.f, 0.f, 0.f, 0.f};
             for (int g = g0; g < g1; ++g, ++tcount) {
                 const uint32_t acc = tcount % kAcc, aph = (tcount / kAcc) & 1;
-                float t_cur[4] = {t_next[0], t_next[1], t_next[2], t_next[3]};
-                if (MODE == 0 && p.target) {
-                    if (g + 1 < g1) load_targets(g + 1);
-                    prefetch_targets(g + 4);
-                }
-                FV_T0(t_ew);
-                mbar_wait(&tfull[acc], aph);
-                if (warp == 2) FV_TACC(6, t_ew);
-                FV_T0(t_epi);
+                mbar_wait(&tfull[acc * 2 + h], aph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * 64u + (uint32_t)h * 32u;
                 uint32_t v0[16], v1[16];
@@ -291,7 +291,7 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) mbar_arrive(&tempty[acc * 2 + h]);
                 if (p.dbg & 2) continue;
                 if (MODE == 1) {
                     // one pixel = 64 contiguous bytes per thread: two 256-bit stores (full 32-byte sectors; 16-byte stores at a
@@ -331,10 +331,16 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (c < p.Co) p.logits[idx0 + c * plane] = o[c];
                     }
                     if (p.target) {
+                        const int tslot = (int)(tcount % kTRows);
+                        asm volatile("cp.async.wait_group %0;" ::"n"(kTRows - 1) : "memory");     // this row's group has landed
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (c < p.Co) t_cur[c] = Ts[(tslot * p.Co + c) * p.W + u];
+                        fetch_targets(g + kTRows, tslot);                                       // refill the slot just consumed
                         float gd4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            if (c >= p.Co) continue;
+                            if (c < p.Co) {
                             const float t = t_cur[c];
                             const float sg = p.use_sigmoid ? 1.f / (1.f + __expf(-o[c])) : o[c];
                             const float d = sg - t;
@@ -342,16 +348,16 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             float gd = p.l1 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : 2.f * d;
                             if (p.use_sigmoid) gd *= sg * (1.f - sg);
                             gd *= p.gscale;
-                            if (p.pred) p.pred[idx0 + c * plane] = sg;
+                            if (p.pred && !(p.dbg & 64)) p.pred[idx0 + c * plane] = sg;
                             gd4[c] = gd;
                             gs[c] += gd;
+                            }
                         }
-                        if (p.g4)
+                        if (p.g4 && !(p.dbg & 64))
                             *reinterpret_cast<uint2*>(p.g4 + ((size_t)g * p.W + u) * 4) =
                                 make_uint2(pack_bf16(gd4[0], gd4[1]), pack_bf16(gd4[2], gd4[3]));
                     }
                 }
-                if (warp == 2) FV_TACC(7, t_epi);
             }
             if (MODE == 0 && p.target) {
                 loss_acc = warp_sum(loss_acc);
@@ -365,7 +371,7 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
         }
-    } else if (MODE == 1) {
+    } else if (MODE == 1 && warp < 18) {
         // record builders (warps 10..17): the forward producer's slab sequence, slab k built by warp k % 8, so that up to
         // (ring - 7) slabs are in flight; the global loads of a slab are issued before the wait for its slot
         const uint32_t bw = (uint32_t)(warp - 10);
@@ -389,7 +395,7 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     Rec ra[2], rb[2];
                     rec_load(ra[0], row4, row_ok, lane, p.W);
                     rec_load(ra[1], row4, row_ok, lane + 32, p.W);
-                    { FV_T0(tw); mbar_wait(&empty[slot], ph ^ 1); if (bw == 0) FV_TACC(0, tw); }
+                    mbar_wait(&empty[slot], ph ^ 1);
                     for (int u0 = 0; u0 < p.W; u0 += 128) {                 // 4 records per lane and pass, double-buffered
                         rec_load(rb[0], row4, row_ok, u0 + 64 + lane, p.W);
                         rec_load(rb[1], row4, row_ok, u0 + 96 + lane, p.W);
@@ -432,9 +438,10 @@ struct FoldWgradParams {
     float* dw;                     // [Co][32][7][7] fp32, caller-zeroed
     const float* scale_ptr;
     long long* trace;
+    int dbg;                       // FV_FOLD_DEBUG (tools/fold_experiments.py only): 1 no MMAs, 4 no record build, 8 no slab loads
 };
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(352, 1)
 fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -456,13 +463,13 @@ fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams
         tma_prefetch_desc(&tmX);
         for (int i = 0; i < kWSlots; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], 2);                     // one vote per issuer warp
         }
         for (int i = 0; i < kRecSlots; ++i) {
             mbar_init(&rfull[i], 32);
-            mbar_init(&rempty[i], 1);
+            mbar_init(&rempty[i], 2);
         }
-        mbar_init(tfull, 1);
+        mbar_init(tfull, 2);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -490,15 +497,21 @@ fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams
             int n, h, y0, T;
             decode(unit, n, h, y0, T);
             for (int i = 0; i < T + 6; ++i) {
-                { FV_T0(tw); mbar_wait(&empty[i], ((phmask >> i) & 1u) ^ 1u); FV_TACC(0, tw); }
+                mbar_wait(&empty[i], ((phmask >> i) & 1u) ^ 1u);
                 phmask ^= 1u << i;
                 if (leader) {
-                    mbar_arrive_expect_tx(&full[i], (uint32_t)kWSlab);
-                    tma_load_4d(smem + (size_t)i * kWSlab, &tmX, &full[i], 0, h * 128, y0 - 3 + i, n);
+                    if (p.dbg & 8) {
+                        mbar_arrive(&full[i]);
+                    } else {
+                        mbar_arrive_expect_tx(&full[i], (uint32_t)kWSlab);
+                        tma_load_4d(smem + (size_t)i * kWSlab, &tmX, &full[i], 0, h * 128, y0 - 3 + i, n);
+                    }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 10) {
+        // two issuer warps, one per M tile (filter rows 0-3 / 4-6): see fold_conv_kernel
+        const uint32_t mt = warp == 1 ? 0u : 1u;
         if (u0 < u1) {
             const bool leader = elect_one_sync();
             const uint32_t idesc = umma_idesc_bf16(128, 32, 1, 1);                       // both operands MN-major
@@ -509,6 +522,7 @@ fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams
             const uint32_t smem_base = smem_u32(smem);
             constexpr uint32_t kstep = (16u * kRowB) >> 4;                                // 16 pixels per MMA
             uint32_t phmask = 0, rs = 0, rph = 0, accumulate = 0;
+            FVR_DECL;
             FV_T0(t_all);
             for (int unit = u0; unit < u1; ++unit) {
                 int n, h, y0, T;
@@ -520,23 +534,21 @@ fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams
                             mbar_wait(&full[i], (phmask >> i) & 1u);
                             phmask ^= 1u << i;
                         }
-                        FV_TACC(1, tw);
+                        if (mt == 0) FVR_ACC(1, tw);
                     }
-                    { FV_T0(tw); mbar_wait(&rfull[rs], rph); FV_TACC(2, tw); }
+                    { FV_T0(tw); mbar_wait(&rfull[rs], rph); if (mt == 0) FVR_ACC(2, tw); }
                     tc_fence_after();
                     FV_T0(t_issue);
                     const uint32_t b_lo = b_lo_base | ((smem_base + (uint32_t)p.rec_off + rs * (uint32_t)kWSlab) >> 4);
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        const uint32_t a_lo = a_lo_base | ((smem_base + (uint32_t)(j + 4 * mt) * (uint32_t)kWSlab) >> 4);
+                    const uint32_t a_lo = a_lo_base | ((smem_base + ((uint32_t)j + 4u * mt) * (uint32_t)kWSlab) >> 4);
+                    if (leader && !(p.dbg & 1)) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
-                            if (leader)
-                                tc_mma_f16_lohi2(tmem_base + (uint32_t)mt * 32u, a_lo + k * kstep, a_hi, b_lo + k * kstep, b_hi, idesc,
-                                                 accumulate | (uint32_t)(k > 0));
+                            tc_mma_f16_lohi2(tmem_base + mt * 32u, a_lo + k * kstep, a_hi, b_lo + k * kstep, b_hi, idesc,
+                                             accumulate | (uint32_t)(k > 0));
                     }
                     accumulate = 1;
-                    FV_TACC(3, t_issue);
+                    if (mt == 0) FVR_ACC(3, t_issue);
                     FV_T0(t_commit);
                     if (leader) tc_commit(&rempty[rs]);
                     if (++rs == kRecSlots) { rs = 0; rph ^= 1; }
@@ -544,11 +556,12 @@ fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams
                     if (j == T - 1)
                         for (int i = T; i < T + 6; ++i)
                             if (leader) tc_commit(&empty[i]);
-                    FV_TACC(4, t_commit);
+                    if (mt == 0) FVR_ACC(4, t_commit);
                 }
             }
             if (leader) tc_commit(tfull);
-            FV_TACC(5, t_all);
+            if (mt == 0) FVR_ACC(5, t_all);
+            FVR_FLUSH(p.trace);
         }
     } else if (warp < 6) {
         if (u0 < u1) {
@@ -556,7 +569,6 @@ fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams
             const float sc = p.scale_ptr ? __ldg(p.scale_ptr) : 1.f;
             mbar_wait(tfull, 0);
             tc_fence_after();
-            FV_T0(t_epi);
             for (int mt = 0; mt < 2; ++mt) {
                 const int r = 4 * mt + q;
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + (uint32_t)mt * 32u;
@@ -575,9 +587,8 @@ fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams
                     }
                 }
             }
-            if (warp == 2) FV_TACC(6, t_epi);
         }
-    } else {
+    } else if (warp < 10) {
         // record builders (warps 6..9): the records of output row k (in processing order) are built by warp k % 4, four
         // records per lane, with all global loads issued before the wait for the slot
         const uint32_t bw = (uint32_t)(warp - 6);
@@ -590,12 +601,16 @@ fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams
                 if ((k & 3u) == bw) {
                     const __nv_bfloat16* row4 = p.dy4 + ((size_t)n * p.H + y0 + j) * p.W * 4;
                     Rec r[4];
+                    if (!(p.dbg & 4)) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) rec_load(r[i], row4, true, h * 128 + 32 * i + lane, p.W);
-                    { FV_T0(tw); mbar_wait(&rempty[rs], rph ^ 1); if (bw == 0) FV_TACC(7, tw); }
+                        for (int i = 0; i < 4; ++i) rec_load(r[i], row4, true, h * 128 + 32 * i + lane, p.W);
+                    }
+                    mbar_wait(&rempty[rs], rph ^ 1);
                     const uint32_t base = smem_base + (uint32_t)p.rec_off + rs * (uint32_t)kWSlab;
+                    if (!(p.dbg & 4)) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) rec_store(r[i], base + (uint32_t)(32 * i + lane) * kRowB);
+                        for (int i = 0; i < 4; ++i) rec_store(r[i], base + (uint32_t)(32 * i + lane) * kRowB);
+                    }
                     fence_proxy_async();
                     mbar_arrive(&rfull[rs]);
                 }
@@ -649,13 +664,15 @@ static int fold_geometry(FoldParams& p, int N, int H, int W, int mode) {
     p.rows_per_cta = (p.rows_total + sms - 1) / sms;
     p.slab_bytes = W * kRowB;
     const int q_bytes = mode == 0 ? (((W + 6) * p.QS * 4 + 1023) & ~1023) : 0;
-    int ring = (212 * 1024 - kWBytes - q_bytes) / p.slab_bytes;
+    const int t_bytes = (mode == 0 && p.target) ? 3 * p.Co * W * 4 : 0;          // cp.async staging of three target rows
+    int ring = (221 * 1024 - kWBytes - q_bytes - t_bytes) / p.slab_bytes;
     if (ring > 16) ring = 16;
     if (ring < kFR + 1) return -1;
     p.ring = ring;
     p.w_off = ring * p.slab_bytes;
     p.q_off = p.w_off + kWBytes;
-    p.bar_off = p.q_off + q_bytes;
+    p.t_off = p.q_off + q_bytes;
+    p.bar_off = p.t_off + t_bytes;
     return (p.rows_total + p.rows_per_cta - 1) / p.rows_per_cta;
 }
 
@@ -695,6 +712,7 @@ extern "C" __attribute__((visibility("default"))) int fv_outconv_fwd(const void*
         return fail(FV_ERR_UNSUPPORTED, "fv_outconv_fwd: needs a 7x7 filter, Ci = 32, Co <= 4, W = 128 or 256 (got Ci=%d Co=%d W=%d)", Ci, Co, W);
     FoldParams p{};
     p.Co = Co; p.NQ = kFR * Co; p.QS = p.NQ | 1;
+    p.target = target;                           // sizes the target staging area
     const int grid = fold_geometry(p, N, H, W, 0);
     if (grid < 1) return fail(FV_ERR_INTERNAL, "fv_outconv_fwd: shared-memory budget");
     p.bias = bias; p.logits = logits; p.target = target; p.pred = pred; p.g4 = (__nv_bfloat16*)g4; p.loss_sum = loss_sum; p.gsum = gsum;
@@ -707,13 +725,13 @@ extern "C" __attribute__((visibility("default"))) int fv_outconv_fwd(const void*
         if (int e = encode_tmap_bf16(&tmA, x, 4, dims, str, box, kRowB)) return e;
     }
     if (int e = encode_w(&tmW, wq)) return e;
-    const size_t smem = (size_t)p.bar_off + (2 * p.ring + 2 * kAcc + 1) * 8 + 16 + 1024 + 64;
+    const size_t smem = (size_t)p.bar_off + (2 * p.ring + 4 * kAcc + 1) * 8 + 16 + 1024 + 64;
     static bool attr_set = false;
     if (!attr_set) {
         FV_CUDA(cudaFuncSetAttribute(fold_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    fold_conv_kernel<0><<<grid, 320, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
+    fold_conv_kernel<0><<<grid, 352, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
     FV_LAUNCH_CHECK("fold_conv_kernel<fwd>");
     return FV_OK;
 }
@@ -730,13 +748,13 @@ extern "C" __attribute__((visibility("default"))) int fv_outconv_dgrad(const voi
     p.dy4 = (const __nv_bfloat16*)dy4; p.dx = (__nv_bfloat16*)dx; p.scale_ptr = scale_ptr; p.trace = trace_ptr();
     CUtensorMap tmW;
     if (int e = encode_w(&tmW, wdq)) return e;
-    const size_t smem = (size_t)p.bar_off + (2 * p.ring + 2 * kAcc + 1) * 8 + 16 + 1024 + 64;
+    const size_t smem = (size_t)p.bar_off + (2 * p.ring + 4 * kAcc + 1) * 8 + 16 + 1024 + 64;
     static bool attr_set = false;
     if (!attr_set) {
         FV_CUDA(cudaFuncSetAttribute(fold_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    fold_conv_kernel<1><<<grid, 576, smem, (cudaStream_t)stream>>>(tmW, tmW, p);
+    fold_conv_kernel<1><<<grid, 608, smem, (cudaStream_t)stream>>>(tmW, tmW, p);
     FV_LAUNCH_CHECK("fold_conv_kernel<dgrad>");
     return FV_OK;
 }
@@ -756,6 +774,7 @@ extern "C" __attribute__((visibility("default"))) int fv_outconv_wgrad(const voi
     p.rec_off = kWSlots * kWSlab;
     p.bar_off = p.rec_off + kRecSlots * kWSlab;
     p.dy4 = (const __nv_bfloat16*)dy4; p.dw = dw; p.scale_ptr = scale_ptr; p.trace = trace_ptr();
+    { const char* v = getenv("FV_FOLD_DEBUG"); p.dbg = v ? atoi(v) : 0; }
     CUtensorMap tmX;
     {
         uint64_t dims[4] = {(uint64_t)kFC, (uint64_t)W, (uint64_t)H, (uint64_t)N};
@@ -769,7 +788,7 @@ extern "C" __attribute__((visibility("default"))) int fv_outconv_wgrad(const voi
         FV_CUDA(cudaFuncSetAttribute(fold_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    fold_wgrad_kernel<<<grid, 320, smem, (cudaStream_t)stream>>>(tmX, p);
+    fold_wgrad_kernel<<<grid, 352, smem, (cudaStream_t)stream>>>(tmX, p);
     FV_LAUNCH_CHECK("fold_wgrad_kernel");
     return FV_OK;
 }

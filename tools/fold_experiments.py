@@ -22,7 +22,11 @@ def timeit(fn, iters=5):
         ts.append(e0.elapsed_time(e1))
     ts.sort()
     return ts[len(ts) // 2] * 1e3
-for dbg in (0, 6, 7, 14, 8):
+for dbg in ():
+    os.environ["FV_FOLD_DEBUG"] = str(dbg)
+    d = timeit(lambda: ops.outconv_wgrad(x, g4, one, co))
+    print(f"wgrad dbg {dbg} (noMMA {dbg & 1} noBuild {(dbg >> 2) & 1} noSlabLoad {(dbg >> 3) & 1}): {d:6.1f} us", flush=True)
+for dbg in (0, 32):
     os.environ["FV_FOLD_DEBUG"] = str(dbg)
     a = timeit(lambda: ops.outconv_fwd(x, wq, None, co, target=tgt, gscale=1e-6))
     b = timeit(lambda: ops.outconv_fwd(x, wq, None, co))

@@ -22,9 +22,14 @@ tgt = torch.rand((n, co, hw, hw), device="cuda")
 g4 = (torch.randn((n, hw, hw, 4), device="cuda") * 0.01).bfloat16()
 one = torch.ones((1,), device="cuda")
 rows = n * hw / 148
-names = ["prod_wait_empty", "mma_wait_full", "mma_wait_tempty", "mma_issue", "mma_commit", "mma_total", "epi_wait_tfull", "epi_work"]
+names = ["", "mma_wait_full", "mma_wait_tempty", "mma_issue", "mma_commit", "mma_total", "mma_desc", ""]
 run("fold fwd + loss", lambda: ops.outconv_fwd(x, wq, None, co, target=tgt, gscale=1e-6), names, rows)
 run("fold fwd plain ", lambda: ops.outconv_fwd(x, wq, None, co), names, rows)
 run("fold dgrad     ", lambda: ops.outconv_dgrad(g4, wdq, one, co), names, rows)
 run("fold wgrad     ", lambda: ops.outconv_wgrad(x, g4, one, co),
-    ["prod_wait_empty", "mma_wait_full", "mma_wait_rfull", "mma_issue", "mma_commit", "mma_total", "epilogue(total)", "build_wait_rempty"], 2 * rows)
+    ["", "mma_wait_full", "mma_wait_rfull", "mma_issue", "mma_commit", "mma_total", "", ""], 2 * rows)
+import os
+for dbg in (7, 13):
+    os.environ["FV_FOLD_DEBUG"] = str(dbg)
+    run(f"dbg {dbg} fold fwd plain ", lambda: ops.outconv_fwd(x, wq, None, co), names, rows)
+    run(f"dbg {dbg} fold wgrad     ", lambda: ops.outconv_wgrad(x, g4, one, co), ["", "mma_wait_full", "mma_wait_rfull", "mma_issue", "mma_commit", "mma_total", "", ""], 2 * rows)
