@@ -211,16 +211,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                                 f[2 * i + 1] += bf16_hi(rr[i]);
                             }
                         }
+                        // 256-bit stores: a thread owns 32 (bf16) / 64 (fp32) contiguous bytes of its pixel row; 16-byte
+                        // stores at a row-sized lane stride reach L2 as half-written sectors (2x write traffic in ncu)
                         if (p.out_mode == FV_OUT_NHWC_BF16) {
-                            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + c0);
-                            o[0] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
-                                              pack_bf16(f[6], f[7]));
-                            o[1] = make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]),
-                                              pack_bf16(f[14], f[15]));
-                        } else {
-                            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.out_cs + c0);
+                            uint32_t wv[8];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) o[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                            for (int i = 0; i < 8; ++i) wv[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+                            st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + c0, wv);
+                        } else {
+                            uint32_t wv[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) wv[i] = __float_as_uint(f[i]);
+                            float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cs + c0;
+                            st_global_256(o, wv);
+                            st_global_256(o + 8, wv + 8);
                         }
                     }
                 }
