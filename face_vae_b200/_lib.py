@@ -27,6 +27,7 @@ SIGNATURES = {
     "fv_weight_prep": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_weight_prep_batched": [_p, _i, _ll, _p],
     "fv_conv2d": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "fv_conv2d_stats": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
     "fv_conv2d_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "fv_wgrad_finish": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_colsum": [_p, _p, _ll, _i, _p],

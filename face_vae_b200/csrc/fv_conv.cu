@@ -45,6 +45,8 @@ struct ConvParams {
     const float* bias;
     const __nv_bfloat16* residual;
     void* out;
+    float* stats;         // optional [2][stats_c]: per-channel sum / sum of squares of the stored output (fused fv_bn_stats)
+    int stats_c;
 };
 
 static constexpr int kConvThreads = 192;
@@ -77,6 +79,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);      // [Co_pad]
+    float* stat_s = bias_s + p.Co_pad;                            // [2][Co_pad] CTA-level statistic accumulators (when p.stats)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -98,6 +101,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tmem_relinquish();
     }
     for (int c = threadIdx.x; c < p.Co_pad; c += blockDim.x) bias_s[c] = (p.bias && c < p.Co) ? p.bias[c] : 0.f;
+    if (p.stats)
+        for (int c = threadIdx.x; c < 2 * p.Co_pad; c += blockDim.x) stat_s[c] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -191,8 +196,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 uint32_t v[16];
                 tmem_ld16(taddr + cl, v);
                 tmem_ld_wait();
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = 0.f;          // rows past the batch contribute nothing to the statistics
                 if (valid) {
-                    float f[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias_s[c0 + i];
                     if (p.out_mode == FV_OUT_NCHW_F32) {
@@ -218,6 +225,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
                             for (int i = 0; i < 8; ++i) wv[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
                             st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + c0, wv);
+                            if (p.stats) {                       // statistics of the values as stored (bf16-rounded)
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    f[2 * i] = bf16_lo(wv[i]);
+                                    f[2 * i + 1] = bf16_hi(wv[i]);
+                                }
+                            }
                         } else {
                             uint32_t wv[16];
 #pragma unroll
@@ -228,10 +242,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         }
                     }
                 }
+                if (p.stats) {                                    // warp-uniform: all 32 lanes take part in the shuffles
+                    float fq[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) fq[i] = f[i] * f[i];
+                    const float cs = warp_colsum16(f, lane), cq = warp_colsum16(fq, lane);
+                    if (!(lane & 1)) {
+                        atomicAdd(stat_s + c0 + ((lane >> 1) & 15), cs);
+                        atomicAdd(stat_s + p.Co_pad + c0 + ((lane >> 1) & 15), cq);
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if (p.stats) {                                   // CTA totals -> global, one atomic per channel and CTA
+            named_bar_sync(1, 128);
+            for (int c = threadIdx.x - 64; c < 2 * p.Co_pad; c += 128) {
+                const float v = stat_s[c];
+                if (v != 0.f) atomicAdd(p.stats + (c < p.Co_pad ? c : p.stats_c + c - p.Co_pad), v);
+            }
         }
     }
 
@@ -266,7 +297,7 @@ static int pick_tile(int N, int H, int W, int& tw, int& th, int& tn) {
 
 // fv_conv_ring.cu: sliding-window schedule for thin full-resolution layers; -1 when not eligible
 int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
-                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, cudaStream_t stream);
+                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, cudaStream_t stream);
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -288,14 +319,31 @@ static int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const Con
 }  // namespace fv
 
 static int conv2d_chunk(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W,
-                        int Ci, int Co, int Co_pad, int out_cs, int R, int S, int pad, void* stream);
+                        int Ci, int Co, int Co_pad, int out_cs, int R, int S, int pad, float* stats, void* stream);
+static int conv2d_any(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W, int Ci,
+                      int Co, int Co_pad, int R, int S, int pad, float* stats, void* stream);
 
 // Output channels beyond one UMMA N (256) are produced in chunks of <= 256: each chunk is an independent GEMM on a row
 // slice of the K-major filter matrix, written at its channel offset of the NHWC output (channel stride = Co_pad).
 extern "C" __attribute__((visibility("default"))) int fv_conv2d(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode,
                          int N, int H, int W, int Ci, int Co, int Co_pad, int R, int S, int pad, void* stream) {
+    return conv2d_any(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, nullptr, stream);
+}
+
+// The same with the batch-norm statistics of the output fused into the epilogue: stats[0..Co_pad) += sum_pixels y,
+// stats[Co_pad..2 Co_pad) += sum_pixels y^2 of the values as stored (caller-zeroed; NHWC outputs only).
+extern "C" __attribute__((visibility("default"))) int fv_conv2d_stats(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                               int out_mode, int N, int H, int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats,
+                               void* stream) {
+    if (!stats) return fv::fail(fv::FV_ERR_ARG, "fv_conv2d_stats: null stats pointer");
+    if (out_mode == FV_OUT_NCHW_F32) return fv::fail(fv::FV_ERR_UNSUPPORTED, "fv_conv2d_stats: NHWC outputs only");
+    return conv2d_any(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, stats, stream);
+}
+
+static int conv2d_any(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W, int Ci,
+                      int Co, int Co_pad, int R, int S, int pad, float* stats, void* stream) {
     using namespace fv;
-    if (Co_pad <= 256) return conv2d_chunk(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, Co_pad, R, S, pad, stream);
+    if (Co_pad <= 256) return conv2d_chunk(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, Co_pad, R, S, pad, stats, stream);
     if (Co_pad % 64 || out_mode == FV_OUT_NCHW_F32)
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: Co_pad=%d > 256 must be a multiple of 64 with an NHWC output", Co_pad);
     if (!x || !w || !y) return fail(FV_ERR_ARG, "fv_conv2d: null pointer");
@@ -305,14 +353,15 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d(const void* x, c
         const int co_real = Co - c0 < cn ? (Co - c0 > 0 ? Co - c0 : 1) : cn;
         const int e = conv2d_chunk(x, static_cast<const char*>(w) + (size_t)c0 * R * S * Ci * 2, bias ? bias + c0 : nullptr,
                                    residual ? static_cast<const char*>(residual) + (size_t)c0 * 2 : nullptr,
-                                   static_cast<char*>(y) + (size_t)c0 * esz, out_mode, N, H, W, Ci, co_real, cn, Co_pad, R, S, pad, stream);
+                                   static_cast<char*>(y) + (size_t)c0 * esz, out_mode, N, H, W, Ci, co_real, cn, Co_pad, R, S, pad,
+                                   stats ? stats + c0 : nullptr, stream);
         if (e) return e;
     }
     return FV_OK;
 }
 
 static int conv2d_chunk(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W,
-                        int Ci, int Co, int Co_pad, int out_cs, int R, int S, int pad, void* stream) {
+                        int Ci, int Co, int Co_pad, int out_cs, int R, int S, int pad, float* stats, void* stream) {
     using namespace fv;
     if (!x || !w || !y) return fail(FV_ERR_ARG, "fv_conv2d: null pointer");
     if (N < 1 || H < 1 || W < 1) return fail(FV_ERR_ARG, "fv_conv2d: bad shape N=%d H=%d W=%d", N, H, W);
@@ -324,9 +373,16 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: only odd square filters with same padding (R=%d S=%d pad=%d)", R, S, pad);
     if (out_mode < 0 || out_mode > 2) return fail(FV_ERR_ARG, "fv_conv2d: out_mode %d", out_mode);
     if (out_mode == FV_OUT_NCHW_F32 && residual) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: residual needs an NHWC output");
+    // Fused statistics cost the epilogue ~250 cycles per 16 output channels and tile (a transposing shuffle butterfly +
+    // shared-memory atomics); where that is not hidden behind the tile's MMAs the statistics come from a separate
+    // fv_bn_stats pass over y instead (measured: ring kernel with 64 channels +70 %, enc.2-like N = 128 / K = 576 tiles +75 %,
+    // while 32-channel ring tiles and the K >= 1152 layers hide it).
+    const int y_dtype = out_mode == FV_OUT_NHWC_BF16 ? FV_DT_BF16 : FV_DT_F32;
     if (out_cs == Co_pad) {
-        const int rr = conv2d_ring_try(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, (cudaStream_t)stream);
-        if (rr >= 0) return rr;
+        float* ring_stats = (stats && Co_pad <= 32 && env_int("FV_CONV_FUSE_STATS", 1)) ? stats : nullptr;
+        const int rr = conv2d_ring_try(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, ring_stats, out_cs, (cudaStream_t)stream);
+        if (rr > 0) return rr;
+        if (rr == 0) return (stats && !ring_stats) ? fv_bn_stats(y, y_dtype, stats, (long long)N * H * W, Co_pad, stream) : FV_OK;
     }
     ConvParams p{};
     p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.Co_pad = Co_pad; p.R = R; p.S = S; p.pad = pad;
@@ -369,6 +425,10 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.out = y;
+    const long long mma_cycles = (long long)R * S * (Ci / 16) * (p.Nc / 2 > 32 + p.Nc / 4 ? p.Nc / 2 : 32 + p.Nc / 4);
+    const bool fuse_stats = stats && (out_cs != Co_pad || (10 * mma_cycles >= 34 * (p.Nc / 16) * 250 && env_int("FV_CONV_FUSE_STATS", 1)));
+    p.stats = fuse_stats ? stats : nullptr;
+    p.stats_c = out_cs;                          // the statistic block is [2][total Co_pad] also when Co is walked in chunks
 
     CUtensorMap tmX, tmW;
     {
@@ -383,10 +443,10 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
         uint32_t box[2] = {(uint32_t)KB, (uint32_t)p.Nc};
         if (int e = encode_tmap_bf16(&tmW, w, 2, dims, str, box, row_bytes)) return e;
     }
-    const size_t smem = (size_t)p.stages * p.stage_stride + 1024 + 256 + (size_t)Co_pad * 4 + 64;
+    const size_t smem = (size_t)p.stages * p.stage_stride + 1024 + 256 + (size_t)Co_pad * 12 + 64;
     const int grid = p.num_vtiles < num_sms() ? p.num_vtiles : num_sms();
     cudaStream_t s = (cudaStream_t)stream;
-    if (KB == 64) return launch_conv<64>(tmX, tmW, p, smem, grid, s);
-    if (KB == 32) return launch_conv<32>(tmX, tmW, p, smem, grid, s);
-    return launch_conv<16>(tmX, tmW, p, smem, grid, s);
+    const int e = KB == 64 ? launch_conv<64>(tmX, tmW, p, smem, grid, s) : (KB == 32 ? launch_conv<32>(tmX, tmW, p, smem, grid, s) : launch_conv<16>(tmX, tmW, p, smem, grid, s));
+    if (e || !stats || fuse_stats) return e;
+    return fv_bn_stats(y, y_dtype, stats, (long long)N * H * W, Co_pad, stream);
 }

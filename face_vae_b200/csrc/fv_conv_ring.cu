@@ -31,6 +31,8 @@ struct RingParams {
     int out_mode, tmem_cols;
     const float* bias;
     void* out;
+    float* stats;                         // optional [2][stats_c]: per-channel sum and sum of squares of the stored output
+    int stats_c;
     long long* trace;
 };
 
@@ -198,6 +200,10 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int sw = (row >> sw_shift) & sw_mask;
         uint32_t tcount = 0;
         int col = t0 / p.H, h = t0 - col * p.H;
+        // batch-norm statistics of the stored (bf16-rounded) output, fused: per-lane partial column sums live in
+        // registers across the CTA's tiles (lane l <-> channel 16 c + ((l >> 1) & 15) of chunk c), one atomic per lane pair
+        // and chunk at the end -- replaces a full re-read of the output by fv_bn_stats
+        float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
         for (int t = t0; t < t1; ++t, ++tcount) {
             const int n = col / p.tiles_w, w0 = (col - n * p.tiles_w) * 128;
             const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
@@ -230,10 +236,23 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                         float f[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[c][i]) + bias_s[c * 16 + i];
-                        *reinterpret_cast<uint4*>(srow + (((2 * c) ^ sw) << 4)) =
-                            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                        *reinterpret_cast<uint4*>(srow + (((2 * c + 1) ^ sw) << 4)) =
-                            make_uint4(pack_bf16(f[8], f[9]), pack_bf16(f[10], f[11]), pack_bf16(f[12], f[13]), pack_bf16(f[14], f[15]));
+                        uint32_t wv[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) wv[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+                        *reinterpret_cast<uint4*>(srow + (((2 * c) ^ sw) << 4)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                        *reinterpret_cast<uint4*>(srow + (((2 * c + 1) ^ sw) << 4)) = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+                        if (p.stats) {
+                            float fr[16], fq[16];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                fr[2 * i] = bf16_lo(wv[i]);
+                                fr[2 * i + 1] = bf16_hi(wv[i]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) fq[i] = fr[i] * fr[i];
+                            st_s[c] += warp_colsum16(fr, lane);
+                            st_q[c] += warp_colsum16(fq, lane);
+                        }
                     }
                 }
                 fence_proxy_async();                       // make the staging writes visible to the TMA unit
@@ -276,6 +295,14 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (++h == p.H) { h = 0; ++col; }
         }
         if (use_tma_store && warp == 2 && lane == 0) tma_store_wait_all<0>();
+        if (p.stats && use_tma_store && !(lane & 1)) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < (p.Co_pad >> 4)) {
+                    atomicAdd(p.stats + c * 16 + ((lane >> 1) & 15), st_s[c]);
+                    atomicAdd(p.stats + p.stats_c + c * 16 + ((lane >> 1) & 15), st_q[c]);
+                }
+        }
     }
 
     tc_fence_before();
@@ -301,8 +328,9 @@ static int launch_ring(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUt
 
 // Returns FV_OK after launching, or -1 when the configuration is not eligible (caller falls through to the generic kernel).
 int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
-                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, cudaStream_t stream) {
+                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, cudaStream_t stream) {
     if ((S != 3 && S != 5 && S != 7) || W % 128 || Ci > 64 || residual) return -1;
+    if (stats && !(out_mode == FV_OUT_NHWC_BF16 && Co_pad <= 64)) return -1;      // fused statistics: staged-store epilogue only
     const char* env = getenv("FV_CONV_RING");
     if (env && atoi(env) == 0) return -1;
     const int KB = Ci, row_bytes = KB * 2;
@@ -331,6 +359,8 @@ int conv2d_ring_try(const void* x, const void* w, const float* bias, const void*
     p.out_mode = out_mode;
     p.bias = bias;
     p.out = y;
+    p.stats = stats;
+    p.stats_c = stats_c;
     p.trace = trace_ptr();
     const int sms = num_sms();
     p.tiles_per_cta = (p.num_tiles + sms - 1) / sms;

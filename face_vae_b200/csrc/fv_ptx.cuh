@@ -205,6 +205,21 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a
 #endif
 
 // ------------------------------------------------------------------ misc
+// Column sums over the 32 lanes of a warp for 16 values per lane (a 32 x 16 tile, lane = row): a transposing butterfly
+// that halves the number of columns a lane keeps at every exchange (8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5).
+// Returns the 32-lane total of column ((lane >> 1) & 15); lanes 2k and 2k + 1 hold the same column.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (h16 ? v[j + 8] : v[j]) + __shfl_xor_sync(0xffffffffu, h16 ? v[j] : v[j + 8], 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = (h8 ? a[j + 4] : a[j]) + __shfl_xor_sync(0xffffffffu, h8 ? a[j] : a[j + 4], 8);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) c[j] = (h4 ? b[j + 2] : b[j]) + __shfl_xor_sync(0xffffffffu, h4 ? b[j] : b[j + 2], 4);
+    float d = (h2 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, h2 ? c[0] : c[1], 2);
+    return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -18,6 +18,8 @@ from .ops import (ACT_LEAKY, ACT_NONE, ACT_RELU, MODE_NONE, MODE_POOL, MODE_UP, 
                   OUT_NHWC_F32, pad_channels)
 
 _SYNC_BN = True
+import os as _os
+_FUSE_STATS = _os.environ.get("FACEVAE_FUSE_BN_STATS", "1") != "0"
 
 
 def set_sync_bn(enabled: bool) -> None:
@@ -97,16 +99,19 @@ class Upsample2x(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------------- conv blocks
-def _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, eps):
-    """Returns the [4, C] stat block (mean, invstd, scale, shift) and the global element count per channel."""
+def _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, eps, sums=None):
+    """Returns the [4, C] stat block (mean, invstd, scale, shift) and the global element count per channel.
+    ``sums``: local [sum | sum of squares] already produced by the conv epilogue (otherwise one fv_bn_stats pass over y)."""
     n, h, w, c = y.shape
     if not training:
         return ops.bn_eval_affine(gamma, beta, running_mean, running_var, eps), n * h * w
     count = n * h * w * _world()
+    if sums is None:
+        sums = ops.bn_stats(y)
     xc = xrank.get() if _world() > 1 else None
     if xc is not None:   # one kernel: push partial sums to all peers over NVLink, reduce, finalize
-        return xc.finalize_fwd(ops.bn_stats(y), count, gamma, beta, running_mean, running_var, momentum, eps), count
-    sums = _allreduce_sum(ops.bn_stats(y))
+        return xc.finalize_fwd(sums, count, gamma, beta, running_mean, running_var, momentum, eps), count
+    sums = _allreduce_sum(sums)
     return ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps), count
 
 
@@ -123,8 +128,12 @@ class ConvBNAct(torch.autograd.Function):
         co, ci = weight.shape[0], weight.shape[1]
         # both filter operands come from one pass over the fp32 master weights (the rotated copy is kept for backward)
         wf, wd = ops.weight_prep(weight, True, x.requires_grad)
-        y = ops.conv2d(x, wf, bias, co, ksize, None, OUT_NHWC_BF16, (ci, co))
-        stat, count = _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, eps)
+        sums = None
+        if training and _FUSE_STATS:      # the conv epilogue also produces the batch-norm sums of y (no second pass over y)
+            y, sums = ops.conv2d(x, wf, bias, co, ksize, None, OUT_NHWC_BF16, (ci, co), want_stats=True)
+        else:
+            y = ops.conv2d(x, wf, bias, co, ksize, None, OUT_NHWC_BF16, (ci, co))
+        stat, count = _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, eps, sums)
         out = ops.bn_act_fwd(y, stat, post_mode, act, torch.float32 if out_nchw_f32 else torch.bfloat16, out_nchw_f32)
         ctx.save_for_backward(x, y, stat, weight, wd)
         ctx.cfg = (ksize, post_mode, act, training, out_nchw_f32, count, co, ci)

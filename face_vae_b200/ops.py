@@ -209,8 +209,9 @@ def weight_prep(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = True
 
 
 def conv2d(x: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], co: int, ksize: int,
-           residual: Optional[torch.Tensor] = None, out_mode: int = OUT_NHWC_BF16, real_dims=None) -> torch.Tensor:
-    """x NHWC bf16 [N,H,W,Ci]; wf [Co_pad, k*k, Ci] bf16 -> y (NHWC [N,H,W,Co_pad] or NCHW fp32 [N,co,H,W])."""
+           residual: Optional[torch.Tensor] = None, out_mode: int = OUT_NHWC_BF16, real_dims=None, want_stats: bool = False):
+    """x NHWC bf16 [N,H,W,Ci]; wf [Co_pad, k*k, Ci] bf16 -> y (NHWC [N,H,W,Co_pad] or NCHW fp32 [N,co,H,W]).
+    ``want_stats``: also return the batch-norm sums [2*Co_pad] (sum | sum of squares) of y, produced by the conv epilogue."""
     _chk(x, "x", torch.bfloat16)
     _chk(wf, "wf", torch.bfloat16)
     n, h, w, ci = x.shape
@@ -228,6 +229,11 @@ def conv2d(x: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], co: 
         _chk(residual, "residual", torch.bfloat16)
         if tuple(residual.shape) != (n, h, w, cop):
             raise _lib.FaceVaeError("conv2d: residual shape mismatch")
+    if want_stats:
+        sums = _zeros((2 * cop,), x.device)
+        call("fv_conv2d_stats", x.data_ptr(), wf.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), out_mode, n, h, w, ci, co,
+             cop, ksize, ksize, (ksize - 1) // 2, sums.data_ptr(), _stream(), meta=_conv_meta(n, h, w, ci, cop, ksize, real_dims))
+        return y, sums
     call("fv_conv2d", x.data_ptr(), wf.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), out_mode, n, h, w, ci, co,
          cop, ksize, ksize, (ksize - 1) // 2, _stream(), meta=_conv_meta(n, h, w, ci, cop, ksize, real_dims))
     return y

@@ -57,6 +57,11 @@ int fv_weight_prep_batched(const fv_prep_desc* table_dev, int n_layers, long lon
  * The data gradient is the same call with x := dY, wf := wd, (Ci, Co, Co_pad) := (Co_pad, Ci, Ci_pad). */
 int fv_conv2d(const void* x, const void* wf, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W,
               int Ci, int Co, int Co_pad, int R, int S, int pad, void* stream);
+/* fv_conv2d with the statistic pass of the following batch norm fused into the epilogue (replaces a separate fv_bn_stats
+ * read of y): stats[0..Co_pad) += sum_pixels y, stats[Co_pad..2*Co_pad) += sum_pixels y^2 over the values as stored
+ * (caller-zeroed fp32; NHWC output modes only). */
+int fv_conv2d_stats(const void* x, const void* wf, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
+                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, void* stream);
 /* dw_acc[Co_pad][R*S][Ci] (fp32, caller-zeroed) += sum_pixels x[pixel + tap] * dy[pixel]; tcgen05, split over pixels. */
 int fv_conv2d_wgrad(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
                     void* stream);

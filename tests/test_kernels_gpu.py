@@ -112,6 +112,35 @@ def test_conv_output_channel_split(ops, n, h, w, ci, co, res):
     _conv_case(ops, n, h, w, ci, co, 3, residual=res, seed=60)
 
 
+@pytest.mark.parametrize("n,h,w,ci,co,k", [
+    (3, 37, 256, 32, 64, 3),      # ring kernel (staged-store epilogue), per-lane register accumulators
+    (2, 20, 128, 64, 32, 3),      # ring kernel, 32 output channels
+    (2, 16, 128, 64, 128, 3),     # implicit GEMM, slab schedule
+    (4, 16, 16, 256, 256, 3),     # output channels split over CTAs
+    (5, 4, 4, 128, 64, 3),        # tiles spanning several images, masked tail rows
+    (2, 8, 8, 64, 512, 1),        # more than 256 output channels: two launches into one statistic block
+    (2, 16, 32, 3, 32, 1),        # padded input channels
+])
+def test_conv_fused_bn_statistics(ops, n, h, w, ci, co, k):
+    """fv_conv2d_stats: the epilogue's per-channel sum / sum of squares against fv_bn_stats on the stored output (fp32, rtol 1e-4)."""
+    from face_vae_b200.ops import pad_channels
+    x = _rand((n, ci, h, w), 70)
+    wt = _rand((co, ci, k, k), 71, -1.0 / math.sqrt(ci * k * k), 1.0 / math.sqrt(ci * k * k))
+    b = _rand((co,), 72, bf16_exact=False)
+    wf, _ = ops.weight_prep(wt, True, False)
+    xn = ops.nchw_to_nhwc(x)
+    y, sums = ops.conv2d(xn, wf, b, co, k, want_stats=True)
+    y_ref = ops.conv2d(xn, wf, b, co, k)
+    ref = ops.bn_stats(y_ref)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
+    cp = pad_channels(co)
+    yf = y.float().reshape(-1, cp)
+    exact = torch.cat([yf.sum(0), (yf * yf).sum(0)])
+    _report(f"fused stats n{n} {h}x{w} ci{ci} co{co}", sums.reshape(1, 1, 1, -1), exact.reshape(1, 1, 1, -1), 1e-4, 1e-5)
+    _report("bn_stats kernel", ref.reshape(1, 1, 1, -1), exact.reshape(1, 1, 1, -1), 1e-4, 1e-5)
+
+
 def test_conv_many_tiles_persistent(ops):
     # more tiles than SMs: exercises the persistent loop, TMEM double buffering and mbarrier phase wrap-around
     _conv_case(ops, 8, 64, 128, 32, 64, 3)
