@@ -214,13 +214,16 @@ def main():
     trainer.use_cuda_graph = graph_mode
     agg = {}
     for name, t_ms, meta in recs:
-        a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "flops_exec": 0.0, "bytes": 0.0})
+        a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "flops_exec": 0.0, "bytes": 0.0, "big_bytes": 0.0, "big_ms": 0.0})
         a["launches"] += 1
         a["ms"] += t_ms
         if meta:
             a["flops"] += meta.get("flops", 0.0)
             a["flops_exec"] += meta.get("flops_exec", 0.0)
             a["bytes"] += meta.get("bytes", 0.0)
+            if meta.get("bytes", 0.0) >= 64e6:        # launches that move >= 64 MB: bandwidth-bound, not launch / latency-bound
+                a["big_bytes"] += meta["bytes"]
+                a["big_ms"] += t_ms
     total_ms = sum(a["ms"] for a in agg.values()) or 1.0
     for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
         k = {"launches_per_step": a["launches"] / args.profile_steps, "ms_per_step": a["ms"] / args.profile_steps,
@@ -231,10 +234,13 @@ def main():
         if a["bytes"]:
             k["gbs"] = a["bytes"] / (a["ms"] * 1e-3) / 1e9
             k["frac_hbm"] = k["gbs"] / peaks["hbm"]
+            if a["big_ms"]:
+                k["gbs_launches_over_64MB"] = a["big_bytes"] / (a["big_ms"] * 1e-3) / 1e9
+                k["frac_hbm_launches_over_64MB"] = k["gbs_launches_over_64MB"] / peaks["hbm"]
         kernels[name] = k
     # forward + data-gradient convolutions: the generic implicit-GEMM / ring kernels and the tap-folded out_conv kernels
     conv = {"ms": 0.0, "flops": 0.0, "launches": 0}
-    for nm in ("fv_conv2d", "fv_outconv_fwd", "fv_outconv_dgrad"):
+    for nm in ("fv_conv2d", "fv_conv2d_stats", "fv_outconv_fwd", "fv_outconv_dgrad"):
         if nm in agg:
             for k in conv:
                 conv[k] += agg[nm][k]

@@ -58,7 +58,7 @@ SIGNATURES = {
 }
 _STR = ("fv_last_error", "fv_version")
 _LL = ("fv_xrank_buffer_floats",)
-_PLAIN_INT = {"fv_outconv_supported": [_i, _i, _i, _i, _i, _i, _i]}   # predicates: the return value is the answer
+_PLAIN_INT = {"fv_outconv_supported": [_i, _i, _i, _i, _i, _i, _i], "fv_conv2d_fuses_stats": [_i, _i, _i, _i, _i, _i, _i, _i, _i]}   # predicates: the return value is the answer
 
 _lock = threading.Lock()
 _lib = None

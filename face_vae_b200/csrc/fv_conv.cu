@@ -295,7 +295,26 @@ static int pick_tile(int N, int H, int W, int& tw, int& th, int& tn) {
     return 0;
 }
 
+static int env_int(const char* name, int dflt);
+
+// Fused statistics cost the epilogue ~250 cycles per 16 output channels and tile (a transposing shuffle butterfly +
+// shared-memory atomics); they are fused only where the tile's MMAs hide that (measured: ring kernel with 64 channels +70 %,
+// enc.2-like N = 128 / K = 576 tiles +75 %, while 32-channel ring tiles and the K >= 1152 layers hide it).
+static bool igemm_fuses_stats(int Ci, int Nc, int R, int S) {
+    const long long mma_cycles = (long long)R * S * (Ci / 16) * (Nc / 2 > 32 + Nc / 4 ? Nc / 2 : 32 + Nc / 4);
+    return 10 * mma_cycles >= 34LL * (Nc / 16) * 250 && env_int("FV_CONV_FUSE_STATS", 1);
+}
+static int igemm_co_parts(int num_tiles, int Co_pad, int out_mode) {
+    int parts = 1;
+    while (parts < 4 && num_tiles * parts * 2 <= num_sms() && Co_pad % (parts * 2 * 64) == 0 && out_mode != FV_OUT_NCHW_F32 &&
+           env_int("FV_CONV_COSPLIT", 1))
+        parts *= 2;
+    return parts;
+}
+static bool ring_fuses_stats(int out_mode, int Co_pad) { return out_mode == FV_OUT_NHWC_BF16 && Co_pad <= 32 && env_int("FV_CONV_FUSE_STATS", 1); }
+
 // fv_conv_ring.cu: sliding-window schedule for thin full-resolution layers; -1 when not eligible
+int conv2d_ring_eligible(int out_mode, int H, int W, int Ci, int Co_pad, int R, int S, bool residual);
 int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
                     int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, cudaStream_t stream);
 
@@ -303,6 +322,22 @@ static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
 }
+}  // namespace fv
+
+// 1 when fv_conv2d_stats produces the statistics inside the convolution's epilogue for this shape, 0 when it runs a separate
+// fv_bn_stats pass over y (a host that times kernels individually can then issue the two calls itself).
+extern "C" __attribute__((visibility("default"))) int fv_conv2d_fuses_stats(int out_mode, int N, int H, int W, int Ci, int Co_pad, int R, int S,
+                                                                           int has_residual) {
+    using namespace fv;
+    if (out_mode == FV_OUT_NCHW_F32) return 0;
+    if (Co_pad > 256) return 1;
+    if (conv2d_ring_eligible(out_mode, H, W, Ci, Co_pad, R, S, has_residual != 0)) return ring_fuses_stats(out_mode, Co_pad) ? 1 : 0;
+    int tw = 0, th = 0, tn = 0;
+    if (pick_tile(N, H, W, tw, th, tn)) return 0;
+    const int num_tiles = (W / tw) * (H / th) * ((N + tn - 1) / tn);
+    return igemm_fuses_stats(Ci, Co_pad / igemm_co_parts(num_tiles, Co_pad, out_mode), R, S) ? 1 : 0;
+}
+namespace fv {
 
 template <int KB>
 static int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const ConvParams& p, size_t smem, int grid, cudaStream_t stream) {
@@ -373,13 +408,10 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: only odd square filters with same padding (R=%d S=%d pad=%d)", R, S, pad);
     if (out_mode < 0 || out_mode > 2) return fail(FV_ERR_ARG, "fv_conv2d: out_mode %d", out_mode);
     if (out_mode == FV_OUT_NCHW_F32 && residual) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: residual needs an NHWC output");
-    // Fused statistics cost the epilogue ~250 cycles per 16 output channels and tile (a transposing shuffle butterfly +
-    // shared-memory atomics); where that is not hidden behind the tile's MMAs the statistics come from a separate
-    // fv_bn_stats pass over y instead (measured: ring kernel with 64 channels +70 %, enc.2-like N = 128 / K = 576 tiles +75 %,
-    // while 32-channel ring tiles and the K >= 1152 layers hide it).
+    // statistics: fused into the epilogue where that is hidden (see igemm_fuses_stats), a separate fv_bn_stats pass otherwise
     const int y_dtype = out_mode == FV_OUT_NHWC_BF16 ? FV_DT_BF16 : FV_DT_F32;
     if (out_cs == Co_pad) {
-        float* ring_stats = (stats && Co_pad <= 32 && env_int("FV_CONV_FUSE_STATS", 1)) ? stats : nullptr;
+        float* ring_stats = (stats && ring_fuses_stats(out_mode, Co_pad)) ? stats : nullptr;
         const int rr = conv2d_ring_try(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, ring_stats, out_cs, (cudaStream_t)stream);
         if (rr > 0) return rr;
         if (rr == 0) return (stats && !ring_stats) ? fv_bn_stats(y, y_dtype, stats, (long long)N * H * W, Co_pad, stream) : FV_OK;
@@ -400,10 +432,7 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
     p.a_off_b = (a_rows * row_bytes + 1023) & ~1023;
     // fewer pixel tiles than half the SMs (the 16x16 ResBlock2D layers: 64 tiles): split the output channels over 2-4 CTAs
     // per tile -- each streams only its slice of the filter, and twice / four times as many SMs work
-    p.co_parts = 1;
-    while (p.co_parts < 4 && p.num_tiles * p.co_parts * 2 <= num_sms() && Co_pad % (p.co_parts * 2 * 64) == 0 &&
-           out_mode != FV_OUT_NCHW_F32 && env_int("FV_CONV_COSPLIT", 1))
-        p.co_parts *= 2;
+    p.co_parts = igemm_co_parts(p.num_tiles, Co_pad, out_mode);
     p.Nc = Co_pad / p.co_parts;
     p.num_vtiles = p.num_tiles * p.co_parts;
     p.b_slice_stride = (p.Nc * row_bytes + 1023) & ~1023;
@@ -425,8 +454,7 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
     p.bias = bias;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.out = y;
-    const long long mma_cycles = (long long)R * S * (Ci / 16) * (p.Nc / 2 > 32 + p.Nc / 4 ? p.Nc / 2 : 32 + p.Nc / 4);
-    const bool fuse_stats = stats && (out_cs != Co_pad || (10 * mma_cycles >= 34 * (p.Nc / 16) * 250 && env_int("FV_CONV_FUSE_STATS", 1)));
+    const bool fuse_stats = stats && (out_cs != Co_pad || igemm_fuses_stats(Ci, p.Nc, R, S));
     p.stats = fuse_stats ? stats : nullptr;
     p.stats_c = out_cs;                          // the statistic block is [2][total Co_pad] also when Co is walked in chunks
 

@@ -327,6 +327,20 @@ static int launch_ring(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUt
 }
 
 // Returns FV_OK after launching, or -1 when the configuration is not eligible (caller falls through to the generic kernel).
+// 1 when conv2d_ring_try takes this shape (same conditions, no launch)
+int conv2d_ring_eligible(int out_mode, int H, int W, int Ci, int Co_pad, int R, int S, bool residual) {
+    if ((S != 3 && S != 5 && S != 7) || R != S || W % 128 || Ci > 64 || residual) return 0;
+    const char* env = getenv("FV_CONV_RING");
+    if (env && atoi(env) == 0) return 0;
+    const int row_bytes = Ci * 2;
+    const int slab_stride = ((128 + S - 1) * row_bytes + 1023) & ~1023;
+    int off = (R + 3) * slab_stride + R * S * ((Co_pad * row_bytes + 1023) & ~1023);
+    if (out_mode == FV_OUT_NHWC_BF16 && Co_pad <= 64) off += 2 * ((128 * Co_pad * 2 + 1023) & ~1023);
+    const size_t smem = (size_t)off + (2 * (R + 3) + 8) * 8 + 16 + (size_t)Co_pad * 4 + 1024 + 64;
+    (void)H;
+    return smem <= 225 * 1024 ? 1 : 0;
+}
+
 int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
                     int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, cudaStream_t stream) {
     if ((S != 3 && S != 5 && S != 7) || W % 128 || Ci > 64 || residual) return -1;

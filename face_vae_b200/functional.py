@@ -246,8 +246,15 @@ class ConvOnly(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, ksize, out_mode):
         co, ci = weight.shape[0], weight.shape[1]
-        wf, wd = ops.weight_prep(weight, True, x.requires_grad)
-        y = ops.conv2d(x, wf, bias, co, ksize, None, out_mode, (ci, co))
+        if out_mode == OUT_NCHW_F32 and _outconv_fold_ok(x, weight):
+            # full-resolution 7x7 output convolution (inference / eval path): tap-folded forward kernel; the backward below
+            # prepares its own operands for the generic kernels when it is ever needed
+            wq, _ = ops.outconv_prep(weight, True, False)
+            y = ops.outconv_fwd(x, wq, bias, co)["logits"]
+            wd = None
+        else:
+            wf, wd = ops.weight_prep(weight, True, x.requires_grad)
+            y = ops.conv2d(x, wf, bias, co, ksize, None, out_mode, (ci, co))
         ctx.save_for_backward(x, weight, wd)
         ctx.cfg = (ksize, out_mode, co, ci)
         ctx.has_bias = bias is not None

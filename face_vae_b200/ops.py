@@ -229,6 +229,11 @@ def conv2d(x: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], co: 
         _chk(residual, "residual", torch.bfloat16)
         if tuple(residual.shape) != (n, h, w, cop):
             raise _lib.FaceVaeError("conv2d: residual shape mismatch")
+    if want_stats and not _lib.load().fv_conv2d_fuses_stats(out_mode, n, h, w, ci, cop, ksize, ksize, int(residual is not None)):
+        # the library would run a separate statistic pass for this shape: issue the two calls here (timed individually)
+        call("fv_conv2d", x.data_ptr(), wf.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), out_mode, n, h, w, ci, co,
+             cop, ksize, ksize, (ksize - 1) // 2, _stream(), meta=_conv_meta(n, h, w, ci, cop, ksize, real_dims))
+        return y, bn_stats(y)
     if want_stats:
         sums = _zeros((2 * cop,), x.device)
         call("fv_conv2d_stats", x.data_ptr(), wf.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), out_mode, n, h, w, ci, co,
@@ -309,6 +314,7 @@ def outconv_fwd(x: torch.Tensor, wq: torch.Tensor, bias: Optional[torch.Tensor],
     if bias is not None:
         _chk(bias, "bias", torch.float32)
     meta = _conv_meta(n, h, w, ci, 32, 7, (ci, co))
+    meta.update(_bytes(x, logits, target, pred, g4))
     call("fv_outconv_fwd", x.data_ptr(), wq.data_ptr(), _ptr(bias), _ptr(logits), _ptr(target), _ptr(pred), _ptr(g4),
          _ptr(acc), None if acc is None else acc[4:].data_ptr(), n, h, w, ci, co, int(l1), int(use_sigmoid), float(gscale),
          _stream(), meta=meta)

@@ -62,6 +62,9 @@ int fv_conv2d(const void* x, const void* wf, const float* bias, const void* resi
  * (caller-zeroed fp32; NHWC output modes only). */
 int fv_conv2d_stats(const void* x, const void* wf, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
                     int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, void* stream);
+/* 1 when fv_conv2d_stats fuses the statistics into the epilogue for this shape, 0 when it runs a separate fv_bn_stats pass
+ * over y (fusing costs the epilogue ~250 cycles per 16 channels and tile; it is done only where the tile's MMAs hide it). */
+int fv_conv2d_fuses_stats(int out_mode, int N, int H, int W, int Ci, int Co_pad, int R, int S, int has_residual);
 /* dw_acc[Co_pad][R*S][Ci] (fp32, caller-zeroed) += sum_pixels x[pixel + tap] * dy[pixel]; tcgen05, split over pixels. */
 int fv_conv2d_wgrad(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
                     void* stream);

@@ -175,6 +175,29 @@ def test_outconv_full_size_against_generic_kernels(ops):
     _close("full wgrad", dw, dw_ref, 2e-3, 1e-3)
 
 
+def test_model_eval_forward_uses_fold_and_matches_generic_path(ops):
+    """Inference path (encode -> sample -> decode, eval mode): folded out_conv forward vs the generic kernel."""
+    from face_vae_b200.models import FaceVAE
+    from face_vae_b200 import _lib
+    torch.manual_seed(4)
+    model = FaceVAE().cuda().eval()
+    x = torch.rand((2, 3, 128, 128), device="cuda")
+    old = os.environ.get("FACEVAE_OUTCONV_FOLD")
+    res = {}
+    try:
+        for fold in ("1", "0"):
+            os.environ["FACEVAE_OUTCONV_FOLD"] = fold
+            with torch.no_grad():
+                res[fold] = model(x, False)[2].clone()
+    finally:
+        if old is None:
+            os.environ.pop("FACEVAE_OUTCONV_FOLD", None)
+        else:
+            os.environ["FACEVAE_OUTCONV_FOLD"] = old
+    torch.cuda.synchronize()
+    _close("eval x_hat", res["1"], res["0"], 1e-4, 1e-5)      # eval mode is deterministic: kernel-level agreement
+
+
 def test_model_step_fold_matches_generic_path(ops):
     """One train step of the anchor model at 128x128: folded out_conv path vs the generic kernels (same weights, inputs)."""
     from face_vae_b200.models import FaceVAE
