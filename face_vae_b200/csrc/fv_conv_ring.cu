@@ -150,6 +150,13 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 if (!waited) wait_tile(tcount, fresh);
                 waited = false;
                 tc_fence_after();
+                // non-blocking probes of tile t + 1's barriers, issued before this tile's MMAs and consumed in their middle:
+                // the mbarrier round trip overlaps the (blocking) MMA issue instead of stalling between two MMAs
+                uint32_t probe_te = 0, probe_full = 0;
+                if (t + 1 < t1 && !next_fresh) {
+                    probe_te = mbar_test_wait(&tempty[(tcount + 1) & 1], (((tcount + 1) >> 1) & 1) ^ 1);
+                    probe_full = mbar_test_wait(&full[wait_slot], wait_ph);
+                }
                 FV_T0(t_issue);
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co_pad;
                 uint32_t accumulate = 0, slot = first, wtap = w_base;
@@ -169,7 +176,9 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     }
                     if (++slot == (uint32_t)p.ring) slot = 0;
                     if (r == (S_ - 1) / 2 && t + 1 < t1 && !next_fresh) {
-                        wait_tile(tcount + 1, false);
+                        if (!probe_te) mbar_wait(&tempty[(tcount + 1) & 1], (((tcount + 1) >> 1) & 1) ^ 1);
+                        if (!probe_full) mbar_wait(&full[wait_slot], wait_ph);
+                        if (++wait_slot == (uint32_t)p.ring) { wait_slot = 0; wait_ph ^= 1; }
                         waited = true;
                     }
                 }

@@ -185,6 +185,7 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t w_lo = lo_base | ((smem_base + (uint32_t)p.w_off) >> 4);
             const uint32_t a_half = ih * (uint32_t)((128 * kRowB) >> 4);
             uint32_t first = 0, wslot = 0, wph = 0, tcount = 0;
+            uint32_t probe_full = 0, probe_te = 0;       // the next row's barriers, probed before this row's MMAs were issued
             int y = g0 % p.H;
             FVR_DECL;
             mbar_wait(wfull, 0);
@@ -197,14 +198,21 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 {
                     FV_T0(tw);
                     for (int i = fresh ? 0 : kFR - 1; i < kFR; ++i) {
-                        mbar_wait(&full[wslot], wph);
+                        if (fresh || !probe_full) mbar_wait(&full[wslot], wph);
                         if (++wslot == (uint32_t)p.ring) { wslot = 0; wph ^= 1; }
                     }
                     if (ih == 0) FVR_ACC(1, tw);
                 }
                 const uint32_t acc = tcount % kAcc, aph = (tcount / kAcc) & 1;
-                { FV_T0(tw); mbar_wait(&tempty[acc * 2 + ih], aph ^ 1); if (ih == 0) FVR_ACC(2, tw); }
+                { FV_T0(tw); if (!probe_te) mbar_wait(&tempty[acc * 2 + ih], aph ^ 1); if (ih == 0) FVR_ACC(2, tw); }
                 tc_fence_after();
+                // probe the NEXT row's barriers now: the results are consumed after this row's MMAs have been issued
+                probe_full = probe_te = 0;
+                if (g + 1 < g1) {
+                    const uint32_t nacc = (tcount + 1) % kAcc, naph = ((tcount + 1) / kAcc) & 1;
+                    if (!next_fresh) probe_full = mbar_test_wait(&full[wslot], wph);
+                    probe_te = mbar_test_wait(&tempty[nacc * 2 + ih], naph ^ 1);
+                }
                 FV_T0(t_desc);
                 // all descriptor words first, then ONE predicated block of back-to-back MMAs: a per-MMA address computation
                 // in front of every tcgen05.mma is a serial IMAD -> R2UR -> uniform-ALU chain of ~50 cycles (ncu, round 1)
@@ -522,6 +530,7 @@ fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams
             const uint32_t smem_base = smem_u32(smem);
             constexpr uint32_t kstep = (16u * kRowB) >> 4;                                // 16 pixels per MMA
             uint32_t phmask = 0, rs = 0, rph = 0, accumulate = 0;
+            uint32_t probe_full = 0, probe_rf = 0;       // the next row's barriers, probed before this row's MMAs were issued
             FVR_DECL;
             FV_T0(t_all);
             for (int unit = u0; unit < u1; ++unit) {
@@ -531,13 +540,24 @@ fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams
                     {
                         FV_T0(tw);
                         for (int i = (j == 0 ? 0 : j + 6); i <= j + 6; ++i) {
-                            mbar_wait(&full[i], (phmask >> i) & 1u);
+                            if (j == 0 || !probe_full) mbar_wait(&full[i], (phmask >> i) & 1u);
                             phmask ^= 1u << i;
                         }
                         if (mt == 0) FVR_ACC(1, tw);
                     }
-                    { FV_T0(tw); mbar_wait(&rfull[rs], rph); if (mt == 0) FVR_ACC(2, tw); }
+                    { FV_T0(tw); if (!probe_rf) mbar_wait(&rfull[rs], rph); if (mt == 0) FVR_ACC(2, tw); }
                     tc_fence_after();
+                    // probe the NEXT row's barriers now: the results are consumed after this row's MMAs have been issued
+                    probe_full = probe_rf = 0;
+                    {
+                        const uint32_t nrs = rs + 1 == kRecSlots ? 0u : rs + 1, nrph = rs + 1 == kRecSlots ? rph ^ 1u : rph;
+                        if (j + 1 < T) {
+                            probe_full = mbar_test_wait(&full[j + 7], (phmask >> (j + 7)) & 1u);
+                            probe_rf = mbar_test_wait(&rfull[nrs], nrph);
+                        } else if (unit + 1 < u1) {
+                            probe_rf = mbar_test_wait(&rfull[nrs], nrph);
+                        }
+                    }
                     FV_T0(t_issue);
                     const uint32_t b_lo = b_lo_base | ((smem_base + (uint32_t)p.rec_off + rs * (uint32_t)kWSlab) >> 4);
                     const uint32_t a_lo = a_lo_base | ((smem_base + ((uint32_t)j + 4u * mt) * (uint32_t)kWSlab) >> 4);

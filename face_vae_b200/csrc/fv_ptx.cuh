@@ -53,6 +53,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
         : "memory");
     return ok;
 }
+// Non-blocking probe (never suspends the thread): issued BEFORE a batch of tcgen05.mma and consumed after it, the ~150-300
+// cycles an mbarrier round trip costs the issuing warp are hidden behind the (blocking) MMA issue.
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
 // Bounded wait: a protocol bug becomes a trap (reported as a launch failure) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;

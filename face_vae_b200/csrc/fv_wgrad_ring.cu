@@ -153,6 +153,12 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 if (!waited) wait_block(fresh);
                 waited = false;
                 tc_fence_after();
+                // non-blocking probes of block b + 1's barriers before this block's MMAs, consumed in their middle (fv_conv_ring.cu)
+                uint32_t probe_full = 0, probe_b = 0;
+                if (b + 1 < b1 && !next_fresh) {
+                    probe_full = mbar_test_wait(&full[wait_slot], wait_ph);
+                    probe_b = mbar_test_wait(&bfull[wbs], wbph);
+                }
                 FV_T0(t_issue);
                 const uint32_t b_lo = b_lo_base | ((smem_base + (uint32_t)p.b_off + bs * (uint32_t)p.b_stride) >> 4);
                 uint32_t slot = first;
@@ -170,7 +176,10 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                     }
                     if (++slot == (uint32_t)p.ring) slot = 0;
                     if (r == (S_ - 1) / 2 && b + 1 < b1 && !next_fresh) {
-                        wait_block(false);
+                        if (!probe_full) mbar_wait(&full[wait_slot], wait_ph);
+                        if (++wait_slot == (uint32_t)p.ring) { wait_slot = 0; wait_ph ^= 1; }
+                        if (!probe_b) mbar_wait(&bfull[wbs], wbph);
+                        if (++wbs == (uint32_t)p.b_slots) { wbs = 0; wbph ^= 1; }
                         waited = true;
                     }
                 }

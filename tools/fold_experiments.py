@@ -26,7 +26,7 @@ for dbg in ():
     os.environ["FV_FOLD_DEBUG"] = str(dbg)
     d = timeit(lambda: ops.outconv_wgrad(x, g4, one, co))
     print(f"wgrad dbg {dbg} (noMMA {dbg & 1} noBuild {(dbg >> 2) & 1} noSlabLoad {(dbg >> 3) & 1}): {d:6.1f} us", flush=True)
-for dbg in (0, 32):
+for dbg in (0,):
     os.environ["FV_FOLD_DEBUG"] = str(dbg)
     a = timeit(lambda: ops.outconv_fwd(x, wq, None, co, target=tgt, gscale=1e-6))
     b = timeit(lambda: ops.outconv_fwd(x, wq, None, co))
