@@ -39,6 +39,8 @@ SIGNATURES = {
     "fv_bn_finalize": [_p, _d, _p, _p, _p, _p, _f, _f, _p, _i, _p],
     "fv_bn_eval_affine": [_p, _p, _p, _p, _f, _p, _i, _p],
     "fv_bn_act_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "fv_bn_act_fwd_fin": [_p, _i, _p, _d, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "fv_bn_act_bwd_apply_fin": [_p, _i, _p, _i, _i, _p, _p, _d, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_bn_act_bwd_reduce": [_p, _i, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_bn_bwd_finalize": [_p, _p, _d, _p, _p, _p, _i, _i, _p],
     "fv_bn_act_bwd_apply": [_p, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

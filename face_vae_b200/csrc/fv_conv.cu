@@ -147,6 +147,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t smem_base = smem_u32(smem);
             const int groups = p.R * s_loads * p.kc_blocks;
             uint32_t st = 0, ph = 0, tcount = 0;
+            // `probe`: the NEXT stage's full barrier, tested (non-blocking) before the current stage's MMAs are issued and
+            // consumed after them -- an mbarrier round trip costs the issuing warp 150-300 cycles even when the phase is
+            // complete, and the (blocking) issue of 4-12 MMAs per stage hides it
+            uint32_t probe = 0;
             for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x, ++tcount) {
                 const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
                 mbar_wait(&tempty[acc], aph ^ 1);
@@ -154,8 +158,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Nc;
                 uint32_t accumulate = 0;
                 for (int g = 0; g < groups; ++g) {
-                    mbar_wait(&full[st], ph);
+                    if (!probe) mbar_wait(&full[st], ph);
                     tc_fence_after();
+                    {
+                        const uint32_t nst = st + 1 == (uint32_t)p.stages ? 0u : st + 1, nph = st + 1 == (uint32_t)p.stages ? ph ^ 1u : ph;
+                        probe = mbar_test_wait(&full[nst], nph);
+                    }
                     const uint32_t a_addr = smem_base + st * (uint32_t)p.stage_stride;
                     const uint32_t b_addr = a_addr + (uint32_t)p.a_off_b;
                     for (int sm = 0; sm < s_mmas; ++sm) {

@@ -277,10 +277,23 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
 // a = act(scale[c] * y + shift[c]); mode POOL averages 2x2 windows on the way out (DownBlock2D, reference
 // modules.py:59-70), mode UP replicates each pixel 2x2 (the nn.Upsample in front of UpBlock2D's conv, modules.py:78-89).
 // H, W are the INPUT spatial sizes.  Output is NHWC (TO) or, with nchw_out, NCHW fp32.
+// With fin.sums the kernel finalizes the statistics itself (what bn_finalize_kernel does: every thread derives scale / shift
+// of its 8 channels from the sums; block 0 also writes the [4][C] stat block kept for backward and updates the running
+// statistics), which removes one tiny launch per batch-norm layer from the step.
+struct BnFin {
+    const float* sums;      // [2][C] sum | sum of squares, or null: use the finished stat block
+    double count;
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    float momentum, eps;
+    float* stat_out;        // [4][C]
+};
 template <typename TI, typename TO, int MODE>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const TI* __restrict__ y, const float* __restrict__ stat, TO* __restrict__ out, int N, int H, int W, int C, int act,
-                  int nchw_out) {
+                  int nchw_out, const BnFin fin) {
     const float* scale = stat + 2 * C;
     const float* shift = stat + 3 * C;
     const unsigned groups = C / 8;
@@ -289,10 +302,38 @@ bn_act_fwd_kernel(const TI* __restrict__ y, const float* __restrict__ stat, TO* 
     // blockDim (256) is a multiple of groups, so a thread keeps the same channel group for its whole grid-stride walk
     const unsigned g = threadIdx.x % groups;
     float sc[8], sf[8];
+    if (fin.sums) {
+        const bool writer = blockIdx.x == 0 && threadIdx.x < groups;      // one thread per channel group writes the results
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        sc[k] = __ldg(scale + g * 8 + k);
-        sf[k] = __ldg(shift + g * 8 + k);
+        for (int k = 0; k < 8; ++k) {
+            const int c = g * 8 + k;
+            // no fp64 division / square root here (every thread of the grid runs this, and fp64 is a trickle on this part):
+            // double only for the cancellation-prone E[y^2] - mean^2, the rest in fp32
+            const double inv_count = 1.0 / fin.count;            // uniform: one division per thread, hoisted by the compiler
+            const double mean = (double)__ldg(fin.sums + c) * inv_count;
+            double var = fma((double)__ldg(fin.sums + C + c), inv_count, -mean * mean);
+            if (var < 0) var = 0;
+            const float invstd = 1.0f / sqrtf((float)var + fin.eps);
+            sc[k] = __ldg(fin.gamma + c) * invstd;
+            sf[k] = __ldg(fin.beta + c) - (float)mean * sc[k];
+            if (writer) {
+                fin.stat_out[c] = (float)mean;
+                fin.stat_out[C + c] = invstd;
+                fin.stat_out[2 * C + c] = sc[k];
+                fin.stat_out[3 * C + c] = sf[k];
+                if (fin.running_mean) {
+                    const double unbiased = fin.count > 1 ? var * fin.count / (fin.count - 1) : var;
+                    fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * (float)mean;
+                    fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (float)unbiased;
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            sc[k] = __ldg(scale + g * 8 + k);
+            sf[k] = __ldg(shift + g * 8 + k);
+        }
     }
     constexpr int NL = MODE == FV_MODE_POOL ? 4 : 1;          // loads per element
     constexpr int U = MODE == FV_MODE_POOL ? 2 : 4;           // elements in flight per thread
@@ -509,11 +550,15 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums_local, con
 
 // pass 2: dy = scale * (dz - c1 - xhat * c2) (+ add) = scale*dz + A + B*y with per-channel A = scale*(c2*invstd*mean - c1),
 // B = -scale*c2*invstd; written bf16 NHWC: the conv-output gradient fed to dgrad / wgrad.
+// With fin_sums (the backward sums of pass 1) the coupling coefficients are derived here (sums / count) and block 0 writes
+// dgamma / dbeta: the work of bn_bwd_finalize_kernel without its launch (single-process training; with several ranks the
+// cross-rank exchange kernel produces coef).
 template <typename TY, typename TG, int MODE, bool GN, bool ADD>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
                         const float* __restrict__ coef, const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dy,
-                        int N, int H, int W, int C, int act) {
+                        int N, int H, int W, int C, int act, const float* __restrict__ fin_sums, double fin_count,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int tpr = C / 8, rpi = blockDim.x / tpr;
     const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
     const unsigned P = (unsigned)N * H * W;
@@ -524,7 +569,20 @@ bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, cons
         const float mean = __ldg(stat + c), invstd = __ldg(stat + C + c);
         sc[k] = __ldg(stat + 2 * C + c);
         sf[k] = __ldg(stat + 3 * C + c);
-        const float c1 = __ldg(coef + c), c2 = __ldg(coef + C + c);
+        float c1, c2;
+        if (fin_sums) {
+            const float s1 = __ldg(fin_sums + c), s2 = __ldg(fin_sums + C + c);
+            const float inv_count = (float)(1.0 / fin_count);
+            c1 = s1 * inv_count;
+            c2 = s2 * inv_count;
+            if (blockIdx.x == 0 && tr == 0) {                    // one thread per channel group
+                if (dbeta) dbeta[c] = s1;
+                if (dgamma) dgamma[c] = s2;
+            }
+        } else {
+            c1 = __ldg(coef + c);
+            c2 = __ldg(coef + C + c);
+        }
         ca[k] = sc[k] * (c2 * invstd * mean - c1);
         cb[k] = -sc[k] * c2 * invstd;
     }
@@ -845,8 +903,26 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_eval_affine(const fl
     return FV_OK;
 }
 
+static int bn_act_fwd_impl(const void* y, int in_dtype, const float* stat, void* out, int out_dtype, int nchw_out, int N, int H, int W, int C,
+                           int mode, int act, const BnFin& fin, void* stream);
+
 extern "C" __attribute__((visibility("default"))) int fv_bn_act_fwd(const void* y, int in_dtype, const float* stat, void* out, int out_dtype, int nchw_out, int N, int H,
                              int W, int C, int mode, int act, void* stream) {
+    if (!stat) return fail(FV_ERR_ARG, "fv_bn_act_fwd: null pointer");
+    BnFin fin{};
+    return bn_act_fwd_impl(y, in_dtype, stat, out, out_dtype, nchw_out, N, H, W, C, mode, act, fin, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bn_act_fwd_fin(const void* y, int in_dtype, const float* sums, double count, const float* gamma,
+                                 const float* beta, float* running_mean, float* running_var, float momentum, float eps, float* stat_out,
+                                 void* out, int out_dtype, int nchw_out, int N, int H, int W, int C, int mode, int act, void* stream) {
+    if (!sums || !gamma || !beta || !stat_out || count <= 0) return fail(FV_ERR_ARG, "fv_bn_act_fwd_fin: bad arguments");
+    BnFin fin{sums, count, gamma, beta, running_mean, running_var, momentum, eps, stat_out};
+    return bn_act_fwd_impl(y, in_dtype, stat_out, out, out_dtype, nchw_out, N, H, W, C, mode, act, fin, stream);
+}
+
+static int bn_act_fwd_impl(const void* y, int in_dtype, const float* stat, void* out, int out_dtype, int nchw_out, int N, int H, int W, int C,
+                           int mode, int act, const BnFin& fin, void* stream) {
     if (!y || !stat || !out) return fail(FV_ERR_ARG, "fv_bn_act_fwd: null pointer");
     if (C % 8 || 256 % (C / 8)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: C=%d must be 8 * (a divisor of 256)", C);
     if ((long long)N * H * W * (C / 8) >= (1LL << 31)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_fwd: tensor too large for 32-bit indexing");
@@ -855,9 +931,9 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_fwd(const void* 
     const int Ho = mode == FV_MODE_POOL ? H / 2 : H, Wo = mode == FV_MODE_POOL ? W / 2 : W;
     const int grid = grid_for((long long)N * Ho * Wo * (C / 8), kThreads, 3);   // 79 registers: three blocks per SM
 #define LAUNCH(TI, TO) do { \
-        if (mode == FV_MODE_POOL) bn_act_fwd_kernel<TI, TO, FV_MODE_POOL><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, act, nchw_out); \
-        else if (mode == FV_MODE_UP) bn_act_fwd_kernel<TI, TO, FV_MODE_UP><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, act, nchw_out); \
-        else bn_act_fwd_kernel<TI, TO, FV_MODE_NONE><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, act, nchw_out); } while (0)
+        if (mode == FV_MODE_POOL) bn_act_fwd_kernel<TI, TO, FV_MODE_POOL><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, act, nchw_out, fin); \
+        else if (mode == FV_MODE_UP) bn_act_fwd_kernel<TI, TO, FV_MODE_UP><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, act, nchw_out, fin); \
+        else bn_act_fwd_kernel<TI, TO, FV_MODE_NONE><<<grid, kThreads, 0, STREAM>>>((const TI*)y, stat, (TO*)out, N, H, W, C, act, nchw_out, fin); } while (0)
     if (in_dtype == FV_DT_BF16 && out_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
     else if (in_dtype == FV_DT_BF16) LAUNCH(__nv_bfloat16, float);
     else if (out_dtype == FV_DT_BF16) LAUNCH(float, __nv_bfloat16);
@@ -898,9 +974,27 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_bwd_finalize(const f
     return FV_OK;
 }
 
+static int bn_act_bwd_apply_impl(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat, const float* coef,
+                                 const void* add, void* dy, int N, int H, int W, int C, int mode, int act, const float* fin_sums, double fin_count,
+                                 float* dgamma, float* dbeta, void* stream);
+
 extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_apply(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat,
                                    const float* coef, const void* add, void* dy, int N, int H, int W, int C, int mode, int act,
                                    void* stream) {
+    if (!coef) return fail(FV_ERR_ARG, "fv_bn_act_bwd_apply: null pointer");
+    return bn_act_bwd_apply_impl(y, y_dtype, g, g_dtype, g_nchw, stat, coef, add, dy, N, H, W, C, mode, act, nullptr, 1.0, nullptr, nullptr, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_apply_fin(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat,
+                                       const float* sums, double count, float* dgamma, float* dbeta, const void* add, void* dy, int N,
+                                       int H, int W, int C, int mode, int act, void* stream) {
+    if (!sums || count <= 0) return fail(FV_ERR_ARG, "fv_bn_act_bwd_apply_fin: bad arguments");
+    return bn_act_bwd_apply_impl(y, y_dtype, g, g_dtype, g_nchw, stat, sums, add, dy, N, H, W, C, mode, act, sums, count, dgamma, dbeta, stream);
+}
+
+static int bn_act_bwd_apply_impl(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat, const float* coef,
+                                 const void* add, void* dy, int N, int H, int W, int C, int mode, int act, const float* fin_sums, double fin_count,
+                                 float* dgamma, float* dbeta, void* stream) {
     if (!y || !g || !stat || !coef || !dy) return fail(FV_ERR_ARG, "fv_bn_act_bwd_apply: null pointer");
     if (C % 8 || 256 % (C / 8)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: C=%d must be 8 * (a divisor of 256)", C);
     if ((long long)N * H * W * (C / 8) >= (1LL << 31)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_apply: tensor too large for 32-bit indexing");
@@ -908,7 +1002,7 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_apply(const 
     if (int e = check_c8("fv_bn_act_bwd_apply", C)) return e;
     int grid; size_t sh_unused;
     reduce_geometry(C, (long long)N * H * W, grid, sh_unused, 2, 4);   // no block tail here: one batch of rows per thread
-#define LAUNCH4(TY, TG, M, GNF, AD) bn_act_bwd_apply_kernel<TY, TG, M, GNF, AD><<<grid, kThreads, 0, STREAM>>>((const TY*)y, (const TG*)g, stat, coef, (const __nv_bfloat16*)add, (__nv_bfloat16*)dy, N, H, W, C, act)
+#define LAUNCH4(TY, TG, M, GNF, AD) bn_act_bwd_apply_kernel<TY, TG, M, GNF, AD><<<grid, kThreads, 0, STREAM>>>((const TY*)y, (const TG*)g, stat, coef, (const __nv_bfloat16*)add, (__nv_bfloat16*)dy, N, H, W, C, act, fin_sums, fin_count, dgamma, dbeta)
 #define LAUNCH3(TY, TG, M, GNF) do { if (add) LAUNCH4(TY, TG, M, GNF, true); else LAUNCH4(TY, TG, M, GNF, false); } while (0)
 #define LAUNCH2(TY, TG) do { \
         if (mode == FV_MODE_POOL) { if (g_nchw) LAUNCH3(TY, TG, FV_MODE_POOL, true); else LAUNCH3(TY, TG, FV_MODE_POOL, false); } \

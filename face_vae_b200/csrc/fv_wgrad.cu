@@ -111,10 +111,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint64_t a_hi = umma_smem_desc(0, (uint32_t)p.a_chunk_bytes, a_sbo, a_layout);
             const uint64_t b_hi = umma_smem_desc(0, (uint32_t)p.b_chunk_bytes, b_sbo, b_layout);
             const uint32_t smem_base = smem_u32(smem);
-            uint32_t st = 0, phs = 0, accumulate = 0;
+            uint32_t st = 0, phs = 0, accumulate = 0, probe = 0;   // probe: next stage's barrier, tested before this stage's MMAs
             for (int pb = pb0; pb < pb1; ++pb) {
-                mbar_wait(&full[st], phs);
+                if (!probe) mbar_wait(&full[st], phs);
                 tc_fence_after();
+                {
+                    const uint32_t nst = st + 1 == (uint32_t)p.stages ? 0u : st + 1, nph = st + 1 == (uint32_t)p.stages ? phs ^ 1u : phs;
+                    probe = mbar_test_wait(&full[nst], nph);
+                }
                 const uint32_t a_addr = smem_base + st * (uint32_t)p.stage_stride;
                 const uint32_t b_lo = (a_addr + (uint32_t)p.a_bytes) >> 4;
                 for (int t = 0; t < mt_n; ++t) {

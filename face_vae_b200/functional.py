@@ -20,6 +20,12 @@ from .ops import (ACT_LEAKY, ACT_NONE, ACT_RELU, MODE_NONE, MODE_POOL, MODE_UP, 
 _SYNC_BN = True
 import os as _os
 _FUSE_STATS = _os.environ.get("FACEVAE_FUSE_BN_STATS", "1") != "0"
+_FUSE_FIN = _os.environ.get("FACEVAE_FUSE_BN_FINALIZE", "1") != "0"
+
+
+def _fin_fused(training: bool) -> bool:
+    """Single-process training: the statistic finalize steps run inside the norm+act kernels (no cross-rank exchange needed)."""
+    return training and _FUSE_FIN and _world() == 1
 
 
 def set_sync_bn(enabled: bool) -> None:
@@ -133,8 +139,14 @@ class ConvBNAct(torch.autograd.Function):
             y, sums = ops.conv2d(x, wf, bias, co, ksize, None, OUT_NHWC_BF16, (ci, co), want_stats=True)
         else:
             y = ops.conv2d(x, wf, bias, co, ksize, None, OUT_NHWC_BF16, (ci, co))
-        stat, count = _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, eps, sums)
-        out = ops.bn_act_fwd(y, stat, post_mode, act, torch.float32 if out_nchw_f32 else torch.bfloat16, out_nchw_f32)
+        out_dtype = torch.float32 if out_nchw_f32 else torch.bfloat16
+        if _fin_fused(training):
+            count = y.shape[0] * y.shape[1] * y.shape[2]
+            out, stat = ops.bn_act_fwd_fin(y, sums if sums is not None else ops.bn_stats(y), count, gamma, beta, running_mean,
+                                           running_var, post_mode, act, out_dtype, out_nchw_f32, momentum, eps)
+        else:
+            stat, count = _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, eps, sums)
+            out = ops.bn_act_fwd(y, stat, post_mode, act, out_dtype, out_nchw_f32)
         ctx.save_for_backward(x, y, stat, weight, wd)
         ctx.cfg = (ksize, post_mode, act, training, out_nchw_f32, count, co, ci)
         ctx.has_bias = bias is not None
@@ -148,8 +160,11 @@ class ConvBNAct(torch.autograd.Function):
         c = y.shape[3]
         # eval mode: running statistics are constants, dy = scale * dz, no coupling terms
         s_local = ops.bn_act_bwd_reduce(y, g, stat, post_mode, act, out_nchw_f32)
-        dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
-        dy = ops.bn_act_bwd_apply(y, g, stat, coef, post_mode, act, None, out_nchw_f32)
+        if _fin_fused(training):
+            dy, dgamma, dbeta = ops.bn_act_bwd_apply_fin(y, g, stat, s_local, count, post_mode, act, None, out_nchw_f32)
+        else:
+            dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
+            dy = ops.bn_act_bwd_apply(y, g, stat, coef, post_mode, act, None, out_nchw_f32)
         acc = ops.conv2d_wgrad(x, dy, ksize, (ci, co))
         dw = ops.wgrad_finish(acc, co, ci, ksize)
         db = None
@@ -213,8 +228,13 @@ class BNActConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, residual, weight, bias, gamma, beta, running_mean, running_var, ksize, act, training, momentum, eps):
         co, ci = weight.shape[0], weight.shape[1]
-        stat, count = _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps)
-        a = ops.bn_act_fwd(x, stat, MODE_NONE, act, torch.bfloat16)
+        if _fin_fused(training):
+            count = x.shape[0] * x.shape[1] * x.shape[2]
+            a, stat = ops.bn_act_fwd_fin(x, ops.bn_stats(x), count, gamma, beta, running_mean, running_var, MODE_NONE, act,
+                                         torch.bfloat16, False, momentum, eps)
+        else:
+            stat, count = _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps)
+            a = ops.bn_act_fwd(x, stat, MODE_NONE, act, torch.bfloat16)
         wf, wd = ops.weight_prep(weight, True, True)
         y = ops.conv2d(a, wf, bias, co, ksize, residual, OUT_NHWC_BF16, (ci, co))
         ctx.save_for_backward(x, a, stat, weight, wd)
@@ -234,8 +254,11 @@ class BNActConv(torch.autograd.Function):
         da = ops.conv2d(g, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
         c = x.shape[3]
         s_local = ops.bn_act_bwd_reduce(x, da, stat, MODE_NONE, act)
-        dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
-        dx = ops.bn_act_bwd_apply(x, da, stat, coef, MODE_NONE, act) if ctx.needs_input_grad[0] else None
+        if _fin_fused(training):
+            dx, dgamma, dbeta = ops.bn_act_bwd_apply_fin(x, da, stat, s_local, count, MODE_NONE, act)
+        else:
+            dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
+            dx = ops.bn_act_bwd_apply(x, da, stat, coef, MODE_NONE, act) if ctx.needs_input_grad[0] else None
         dres = g if ctx.has_res else None
         return dx, dres, dw, db, dgamma, dbeta, None, None, None, None, None, None, None
 

@@ -14,6 +14,7 @@ import torch
 from torch import nn
 
 from . import functional as Fn
+from . import ops
 from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, MODE_NONE, MODE_POOL, MODE_UP, OUT_NHWC_BF16, pad_channels
 
 BN_EPS = 1e-5
@@ -132,7 +133,7 @@ class ConvBlock2D(nn.Module):
     def forward_nhwc(self, x, post_mode=MODE_NONE, residual=None, out_nchw_f32=False):
         conv, bn = self.conv, self.norm
         if self.training:
-            bn.num_batches_tracked += 1
+            ops.bump_counter(bn.num_batches_tracked)
         if self.pattern in ("CNA", "CN"):
             return Fn.ConvBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                       self.kernel_size, post_mode, self.act, self.training, out_nchw_f32, bn.momentum, bn.eps)
@@ -209,7 +210,7 @@ class SameBlock2D(nn.Module):
         """x: NCHW fp32 frames -> NHWC bf16 [N,H,W,32]."""
         blk = self.layers
         conv, bn = blk.conv, blk.norm
-        bn.num_batches_tracked += 1
+        ops.bump_counter(bn.num_batches_tracked)
         return Fn.PointwiseBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, blk.act,
                                        bn.momentum, bn.eps)
 

@@ -133,6 +133,17 @@ class _PrepCache:
 _prep = _PrepCache()
 
 
+_pending_counters = []
+
+
+def bump_counter(t: torch.Tensor) -> None:
+    """num_batches_tracked += 1: inside a step scope the increments of all layers are issued as ONE multi-tensor launch."""
+    if _arena.active:
+        _pending_counters.append(t)
+    else:
+        t += 1
+
+
 class step_scope:
     """``with ops.step_scope(model):`` around forward + backward of one train step (VAETrainer does this): the scratch
     the kernels accumulate into comes from one arena zeroed by a single memset, and the bf16 filter operands of all
@@ -154,6 +165,9 @@ class step_scope:
     def __exit__(self, *exc):
         _arena.active = False
         _prep.valid = False
+        if _pending_counters:
+            torch._foreach_add_(list(_pending_counters), 1)
+            _pending_counters.clear()
         return False
 
 
@@ -381,6 +395,37 @@ def bn_act_fwd(y: torch.Tensor, stat: torch.Tensor, mode: int = MODE_NONE, act: 
     call("fv_bn_act_fwd", y.data_ptr(), _dt(y), stat.data_ptr(), out.data_ptr(), _dt(out), int(nchw_out), n, h, w, c,
          mode, act, _stream(), meta=_bytes(y, out))
     return out
+
+
+def bn_act_fwd_fin(y: torch.Tensor, sums: torch.Tensor, count: float, gamma, beta, running_mean, running_var, mode: int = MODE_NONE,
+                   act: int = ACT_RELU, out_dtype=torch.bfloat16, nchw_out: bool = False, momentum: float = BN_MOMENTUM,
+                   eps: float = BN_EPS):
+    """bn_finalize + bn_act_fwd in one launch -> (out, stat [4, C])."""
+    _chk(y, "y")
+    n, h, w, c = y.shape
+    ho, wo = (h // 2, w // 2) if mode == MODE_POOL else ((2 * h, 2 * w) if mode == MODE_UP else (h, w))
+    shape = (n, c, ho, wo) if nchw_out else (n, ho, wo, c)
+    out = torch.empty(shape, device=y.device, dtype=out_dtype)
+    stat = torch.empty((4, c), device=y.device, dtype=torch.float32)
+    call("fv_bn_act_fwd_fin", y.data_ptr(), _dt(y), sums.data_ptr(), float(count), gamma.data_ptr(), beta.data_ptr(),
+         _ptr(running_mean), _ptr(running_var), momentum, eps, stat.data_ptr(), out.data_ptr(), _dt(out), int(nchw_out), n, h, w, c,
+         mode, act, _stream(), meta=_bytes(y, out))
+    return out, stat
+
+
+def bn_act_bwd_apply_fin(y: torch.Tensor, g: torch.Tensor, stat: torch.Tensor, sums: torch.Tensor, count: float, mode: int, act: int,
+                         add: Optional[torch.Tensor] = None, g_nchw: bool = False):
+    """bn_bwd_finalize + bn_act_bwd_apply in one launch -> (dy, dgamma, dbeta)."""
+    n, h, w, c = y.shape
+    dy = torch.empty((n, h, w, c), device=y.device, dtype=torch.bfloat16)
+    dgamma = torch.empty((c,), device=y.device, dtype=torch.float32)
+    dbeta = torch.empty((c,), device=y.device, dtype=torch.float32)
+    if add is not None:
+        _chk(add, "add", torch.bfloat16)
+    call("fv_bn_act_bwd_apply_fin", y.data_ptr(), _dt(y), g.data_ptr(), _dt(g), int(g_nchw), stat.data_ptr(), sums.data_ptr(),
+         float(count), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(add), dy.data_ptr(), n, h, w, c, mode, act, _stream(),
+         meta=_bytes(y, g, add, dy))
+    return dy, dgamma, dbeta
 
 
 def bn_act_bwd_reduce(y: torch.Tensor, g: torch.Tensor, stat: torch.Tensor, mode: int, act: int,

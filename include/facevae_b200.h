@@ -109,6 +109,11 @@ int fv_bn_eval_affine(const float* gamma, const float* beta, const float* runnin
 /* out = [pool2x2 | up2x]( act(scale*y + shift) ).  H, W are the input sizes.  out: NHWC (bf16/fp32) or NCHW fp32. */
 int fv_bn_act_fwd(const void* y, int in_dtype, const float* stat, void* out, int out_dtype, int nchw_out, int N, int H, int W,
                   int C, int mode, int act, void* stream);
+/* fv_bn_finalize + fv_bn_act_fwd in one launch (single-process training): every block derives scale / shift from the sums,
+ * block 0 writes stat_out[4][C] (kept for backward) and updates the running statistics. */
+int fv_bn_act_fwd_fin(const void* y, int in_dtype, const float* sums, double count, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float momentum, float eps, float* stat_out, void* out, int out_dtype,
+                      int nchw_out, int N, int H, int W, int C, int mode, int act, void* stream);
 /* backward pass 1: sums[0..C) += sum dz, sums[C..2C) += sum dz*xhat (caller-zeroed; all-reduced across ranks like
  * torch/nn/modules/_functions.py:144-159).  g is the gradient of the block output (pooled / up-sampled domain). */
 int fv_bn_act_bwd_reduce(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat, float* sums,
@@ -119,6 +124,12 @@ int fv_bn_bwd_finalize(const float* sums_local, const float* sums_global, double
 /* backward pass 2: dy = scale*(dz - coef0 - xhat*coef1) (+ add), bf16 NHWC: the conv-output gradient. */
 int fv_bn_act_bwd_apply(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat, const float* coef,
                         const void* add, void* dy, int N, int H, int W, int C, int mode, int act, void* stream);
+
+/* fv_bn_bwd_finalize + fv_bn_act_bwd_apply in one launch (single-process training): coef = sums / count is derived in the
+ * kernel, block 0 writes dgamma = sums[C..2C), dbeta = sums[0..C) (either may be NULL). */
+int fv_bn_act_bwd_apply_fin(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat, const float* sums,
+                            double count, float* dgamma, float* dbeta, const void* add, void* dy, int N, int H, int W, int C, int mode,
+                            int act, void* stream);
 
 /* ---- first encoder layer: SameBlock2D(C <= 4 -> 32) on raw NCHW fp32 frames (modules.py:97-108 via models.py:749) ----
  * 1x1 conv + training-mode batch norm + ReLU is a per-pixel affine map whose statistics follow from the input moments.
