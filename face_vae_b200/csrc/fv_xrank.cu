@@ -4,11 +4,16 @@
 // [sum_dy, sum_dy_xmu] per layer in backward (torch/nn/modules/_functions.py:39-83,144-159; reference modules.py:19,
 // logger.py:55): 26 latency-bound collectives per step on the critical path of the anchor model.  Here each exchange is
 // ONE single-block kernel: every rank pushes its 2C partial sums straight into a slot of every peer's symmetric buffer
-// (st.global on NVLink-mapped pointers), publishes an epoch flag (st.release.sys), spins until all peers' flags carry
-// the epoch (ld.acquire.sys), adds the R rows and -- in the same kernel -- produces what the next kernel needs: the
+// (stores on NVLink-mapped pointers), waits until all peers' rows have landed in its own buffer, adds the R rows in rank
+// order (bitwise identical on every rank) and -- in the same kernel -- produces what the next kernel needs: the
 // [mean, invstd, scale, shift] block + running-stat update (forward) or dgamma/dbeta + the two coupling coefficients
-// (backward).  The epoch lives in device memory and advances by one per launch on every rank, so the launch sequence
-// can be captured in a CUDA graph and replayed.
+// (backward).
+// Protocol: every element travels as ONE 8-byte store {value, epoch tag}; the receiver polls the element itself until the
+// tag carries the current epoch (the low-latency scheme of NCCL's LL protocol).  There is no separate flag, hence no
+// system-scope fence between data and flag: the first version (data, __threadfence_system, flag) paid an extra NVLink round
+// trip per exchange.  The epoch lives in device memory and advances by one per launch on every rank, so the launch
+// sequence can be captured in a CUDA graph and replayed; a ring of slots keeps a fast rank's next exchange from
+// overwriting rows a slow rank is still reading (a rank can start exchange e + 2 only after every peer has finished e).
 #include <cstdio>
 
 #include "../../include/facevae_b200.h"
@@ -17,24 +22,24 @@
 
 namespace fv {
 
-static constexpr int kXSlots = 8;          // ring of exchange slots (a rank is never more than one exchange ahead)
-static constexpr int kXRow = 1024;         // floats per (slot, rank) row: 2 * C_max
+static constexpr int kXSlots = 8;          // ring of exchange slots
+static constexpr int kXRow = 1024;         // elements per (slot, rank) row: 2 * C_max
 static constexpr int kXMaxWorld = 16;
-// symmetric buffer layout (floats): [flags: kXSlots * kXMaxWorld uint32][pad to 1024][rows: kXSlots * kXMaxWorld * kXRow]
-static constexpr size_t kXFlagsFloats = 1024;
+// symmetric buffer layout: rows[kXSlots][kXMaxWorld][kXRow] of {float value, uint32 epoch} (8 bytes each), zero-initialised
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_tagged_sys(unsigned long long* p, float v, uint32_t tag) {
+    asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void ld_tagged_sys(const unsigned long long* p, float& v, uint32_t& tag) {
+    uint32_t a, b;
+    asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+    v = __uint_as_float(a);
+    tag = b;
 }
 
 // mode 0: forward finalize, mode 1: backward finalize
 __global__ void __launch_bounds__(256, 1)
-bn_xrank_kernel(const float* __restrict__ local, float* const* __restrict__ peer_bufs, int rank, int world,
+bn_xrank_kernel(const float* __restrict__ local, unsigned long long* const* __restrict__ peer_bufs, int rank, int world,
                 unsigned long long* __restrict__ epoch_ctr, int C, int mode, double count,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
                 float momentum, float eps, float* __restrict__ out /* fwd: stat[4][C]; bwd: coef[2][C] */,
@@ -45,32 +50,29 @@ bn_xrank_kernel(const float* __restrict__ local, float* const* __restrict__ peer
     if (threadIdx.x == 0) epoch_s = (uint32_t)(atomicAdd(epoch_ctr, 1ULL) + 1ULL);
     __syncthreads();
     const uint32_t epoch = epoch_s;
-    const int slot = (int)(epoch % kXSlots);
-    // push my partial sums into row (slot, rank) of every peer (and of myself)
+    const size_t slot_base = (size_t)(epoch % kXSlots) * kXMaxWorld * kXRow;
+    // push my partial sums, tagged with the epoch, into row (slot, rank) of every peer (and of myself)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float v = local[i];
-        for (int p = 0; p < world; ++p) peer_bufs[p][kXFlagsFloats + ((size_t)slot * kXMaxWorld + rank) * kXRow + i] = v;
+        for (int p = 0; p < world; ++p) st_tagged_sys(peer_bufs[p] + slot_base + (size_t)rank * kXRow + i, v, epoch);
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < world)
-        st_release_sys(reinterpret_cast<uint32_t*>(peer_bufs[threadIdx.x]) + slot * kXMaxWorld + rank, epoch);
-    // wait until every rank's row for this epoch has landed in MY buffer
-    float* mine = peer_bufs[rank];
-    if (threadIdx.x < world) {
-        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine) + slot * kXMaxWorld + threadIdx.x;
-        uint32_t spins = 0;
-        while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
-            if (++spins > (1u << 24)) {
-                printf("fv: cross-rank BN exchange timed out (rank %d waiting for rank %d, epoch %u)\n", rank, (int)threadIdx.x, epoch);
-                __trap();
-            }
-        }
-    }
-    __syncthreads();
+    // gather: poll every element of every rank's row in MY buffer until it carries this epoch; fixed summation order
+    const unsigned long long* mine = peer_bufs[rank] + slot_base;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         float a = 0.f;
-        for (int p = 0; p < world; ++p) a += __ldcg(mine + kXFlagsFloats + ((size_t)slot * kXMaxWorld + p) * kXRow + i);
+        for (int p = 0; p < world; ++p) {
+            float v;
+            uint32_t tag, spins = 0;
+            ld_tagged_sys(mine + (size_t)p * kXRow + i, v, tag);
+            while (tag != epoch) {
+                if (++spins > (1u << 24)) {
+                    printf("fv: cross-rank BN exchange timed out (rank %d waiting for rank %d, epoch %u)\n", rank, p, epoch);
+                    __trap();
+                }
+                ld_tagged_sys(mine + (size_t)p * kXRow + i, v, tag);
+            }
+            a += v;
+        }
         tot[i] = a;
     }
     __syncthreads();
@@ -103,7 +105,7 @@ bn_xrank_kernel(const float* __restrict__ local, float* const* __restrict__ peer
 }  // namespace fv
 
 extern "C" __attribute__((visibility("default"))) long long fv_xrank_buffer_floats(void) {
-    return (long long)(fv::kXFlagsFloats + (size_t)fv::kXSlots * fv::kXMaxWorld * fv::kXRow);
+    return (long long)(2 * (size_t)fv::kXSlots * fv::kXMaxWorld * fv::kXRow);      // 8-byte tagged elements
 }
 
 extern "C" __attribute__((visibility("default"))) int fv_bn_finalize_xrank(const float* sums_local, void* peer_bufs_dev, int rank, int world,
@@ -116,7 +118,7 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_finalize_xrank(const
     if (world < 1 || world > kXMaxWorld || rank < 0 || rank >= world) return fail(FV_ERR_ARG, "fv_bn_finalize_xrank: rank %d / world %d", rank, world);
     if (2 * C > kXRow) return fail(FV_ERR_UNSUPPORTED, "fv_bn_finalize_xrank: C=%d exceeds %d", C, kXRow / 2);
     if (mode == 0 && (!gamma || !beta)) return fail(FV_ERR_ARG, "fv_bn_finalize_xrank: gamma/beta required in forward mode");
-    bn_xrank_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums_local, reinterpret_cast<float* const*>(peer_bufs_dev), rank, world,
+    bn_xrank_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums_local, reinterpret_cast<unsigned long long* const*>(peer_bufs_dev), rank, world,
                                                          reinterpret_cast<unsigned long long*>(epoch_ctr), C, mode, count, gamma, beta,
                                                          running_mean, running_var, momentum, eps, out, dgamma, dbeta, accumulate);
     FV_LAUNCH_CHECK("bn_xrank_kernel");
