@@ -105,6 +105,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--deep", action="store_true", help="512x512-deep variant (BASELINE.json configs[3]; use with --size 512 --batch 8)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -132,7 +133,11 @@ def main():
     B, S = args.batch, args.size
 
     torch.manual_seed(0)                               # identical initial weights on every rank
-    model = FaceVAE().cuda().train()
+    if args.deep:
+        from face_vae_b200.models import face_vae_512
+        model = face_vae_512().cuda().train()
+    else:
+        model = FaceVAE().cuda().train()
     trainer = VAETrainer(model)
     dz = model.latent_dim(S, S)
     g = torch.Generator().manual_seed(1 + rank)        # reference seed rule (distributed.py:10)
@@ -265,7 +270,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": f"face-vae anchor (SURVEY.md section 8) train step, batch {B} per GPU at {S}x{S}, "
+                "config": {"workload": f"face-vae {'512-deep variant' if args.deep else 'anchor'} (SURVEY.md section 8) train step, batch {B} per GPU at {S}x{S}, "
                                        f"0.2*KL + 10*MSE, Adam(5e-5, betas 0.5/0.999), bf16 storage / fp32 accumulate",
                            "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(trainer.use_cuda_graph),
                            "l2": "working set per step (activations + gradients, >3 GB) far exceeds the 126 MB L2; inputs alternate between two batches"},

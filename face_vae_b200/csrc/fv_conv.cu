@@ -434,16 +434,18 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
     const int row_bytes = KB * 2;
     p.kc_blocks = Ci / KB;
     // slab schedule: one activation box per filter row, taps = shifted descriptor views (row-segment tiles only)
-    p.slab = (S > 1 && p.th == 1 && p.tn == 1) ? env_int("FV_CONV_SLAB", 1) : 0;
-    const int a_rows = p.slab ? p.tw + S - 1 : 128;
-    const int b_slices = p.slab ? S : 1;
-    p.a_off_b = (a_rows * row_bytes + 1023) & ~1023;
     // fewer pixel tiles than half the SMs (the 16x16 ResBlock2D layers: 64 tiles): split the output channels over 2-4 CTAs
     // per tile -- each streams only its slice of the filter, and twice / four times as many SMs work
     p.co_parts = igemm_co_parts(p.num_tiles, Co_pad, out_mode);
     p.Nc = Co_pad / p.co_parts;
     p.num_vtiles = p.num_tiles * p.co_parts;
     p.b_slice_stride = (p.Nc * row_bytes + 1023) & ~1023;
+    p.slab = (S > 1 && p.th == 1 && p.tn == 1) ? env_int("FV_CONV_SLAB", 1) : 0;
+    // a slab stage carries S filter slices: with 256 output channels and a 128-byte K block it no longer fits twice -> tap schedule
+    if (p.slab && 2 * ((((p.tw + S - 1) * row_bytes + 1023) & ~1023) + p.b_slice_stride * S) > 200 * 1024) p.slab = 0;
+    const int a_rows = p.slab ? p.tw + S - 1 : 128;
+    const int b_slices = p.slab ? S : 1;
+    p.a_off_b = (a_rows * row_bytes + 1023) & ~1023;
     p.stage_stride = p.a_off_b + p.b_slice_stride * b_slices;
     p.tx_bytes = a_rows * row_bytes + b_slices * p.Nc * row_bytes;
     const int groups = R * (p.slab ? 1 : S) * p.kc_blocks;

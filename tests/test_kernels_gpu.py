@@ -141,6 +141,12 @@ def test_conv_fused_bn_statistics(ops, n, h, w, ci, co, k):
     _report("bn_stats kernel", ref.reshape(1, 1, 1, -1), exact.reshape(1, 1, 1, -1), 1e-4, 1e-5)
 
 
+def test_conv_wide_row_tiles_with_256_output_channels(ops):
+    # 512-deep variant at 512x512: 128 -> 256 channels on 128-pixel row tiles (the slab stage does not fit twice: tap schedule)
+    _conv_case(ops, 1, 6, 128, 128, 256, 3, seed=80)
+    _conv_case(ops, 1, 4, 256, 64, 256, 3, seed=81)
+
+
 def test_conv_many_tiles_persistent(ops):
     # more tiles than SMs: exercises the persistent loop, TMEM double buffering and mbarrier phase wrap-around
     _conv_case(ops, 8, 64, 128, 32, 64, 3)

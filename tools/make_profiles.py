@@ -89,6 +89,9 @@ copy("bench_ref.json", f"{tag}_bench_reference_cpu.json")
 copy("bench_2gpu.json", f"{tag}_bench_2gpu.json")
 copy("bench_8gpu.json", f"{tag}_bench_8gpu.json")
 copy("timeline3.txt", f"{tag}_step_timeline.txt")
+copy("torch_gpu_baseline.json", f"{tag}_torch_cudnn_baseline_b200.json")
+copy("bench_512deep.json", f"{tag}_bench_512deep_1gpu.json")
+copy("infer_sweep2.txt", f"{tag}_inference_sweep.txt")
 copy("trace_outconv2.txt", f"{tag}_trace_outconv.txt")
 for i, name in enumerate(sorted(f for f in os.listdir(out) if f.startswith("fold_experiments"))):
     with open(os.path.join(prof, f"{tag}_fold_experiments.txt"), "a" if i else "w") as fh:
