@@ -860,7 +860,7 @@ extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const floa
     return FV_OK;
 }
 
-static int reduce_geometry(int C, long long P, int& grid, size_t& shmem, int resident = 2, int rows_per_thread = 16) {
+static int reduce_geometry(int C, long long P, int& grid, size_t& shmem, int resident = 2, int rows_per_thread = 16, int big_waves = 8) {
     const int rpi = kThreads / (C / 8) > 0 ? kThreads / (C / 8) : 1;
     // Reductions end every block with a shared-memory pass and 2C global atomics: at least 16 rows per thread, so that a
     // small tensor does not pay for a thousand blocks' worth of atomics on the same 2C addresses (14 us for 4 MB in round
@@ -868,7 +868,7 @@ static int reduce_geometry(int C, long long P, int& grid, size_t& shmem, int res
     // measured ~5 % faster there than a single wave.
     const long long row_blocks = (P + rpi - 1) / rpi;
     long long blocks = (row_blocks + rows_per_thread - 1) / rows_per_thread;
-    const long long cap = (long long)num_sms() * (row_blocks > (long long)num_sms() * 64 ? 8 : resident);
+    const long long cap = (long long)num_sms() * (row_blocks > (long long)num_sms() * 64 ? big_waves : resident);
     grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
     shmem = (size_t)2 * rpi * C * sizeof(float);
     return rpi;
@@ -950,7 +950,9 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_reduce(const
     if ((long long)N * H * W >= (1LL << 31)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_reduce: tensor too large for 32-bit indexing");
     if (g_nchw && (g_dtype != FV_DT_F32 || mode == FV_MODE_UP)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_reduce: NCHW g is fp32, no upsample");
     int grid; size_t sh;
-    reduce_geometry(C, (long long)N * H * W, grid, sh);
+    // one resident wave also for large tensors: every block ends with 2C atomics on the same addresses (1184 blocks x 128
+    // channels = 150 k serialised atomics cost more than the second wave's tail gains)
+    reduce_geometry(C, (long long)N * H * W, grid, sh, 2, 16, 2);
 #define LAUNCH3(TY, TG, M, GNF) bn_act_bwd_reduce_kernel<TY, TG, M, GNF><<<grid, kThreads, sh, STREAM>>>((const TY*)y, (const TG*)g, stat, sums, N, H, W, C, act)
 #define LAUNCH2(TY, TG) do { \
         if (mode == FV_MODE_POOL) { if (g_nchw) LAUNCH3(TY, TG, FV_MODE_POOL, true); else LAUNCH3(TY, TG, FV_MODE_POOL, false); } \
