@@ -785,6 +785,37 @@ __global__ void recon_loss_flat_kernel(const float* __restrict__ a, const float*
     }
 }
 
+// Adam (torch.optim.Adam semantics without amsgrad / weight decay, reference logger.py:60) over a table of tensors in ONE
+// launch: blockIdx.y = tensor, grid-stride over its elements.  `step` is the step count AFTER this update, read from
+// device memory so that the launch can be captured in a CUDA graph.
+__global__ void adam_multi_kernel(const fv_adam_desc* __restrict__ table, float lr, float beta1, float beta2, float eps,
+                                  const float* __restrict__ step) {
+    const fv_adam_desc d = table[blockIdx.y];
+    const float t = __ldg(step);
+    const float bc1 = 1.f - powf(beta1, t), bc2 = 1.f - powf(beta2, t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    const long long n4 = d.n / 4;
+    const bool vec = ((reinterpret_cast<uintptr_t>(d.p) | reinterpret_cast<uintptr_t>(d.g) | reinterpret_cast<uintptr_t>(d.m) |
+                       reinterpret_cast<uintptr_t>(d.v)) & 15) == 0;
+    auto upd = [&](float& p, float g, float& m, float& v) {
+        m = beta1 * m + (1.f - beta1) * g;
+        v = beta2 * v + (1.f - beta2) * g * g;
+        p -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
+    };
+    if (vec) {
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+            float4 p = reinterpret_cast<float4*>(d.p)[i], m = reinterpret_cast<float4*>(d.m)[i], v = reinterpret_cast<float4*>(d.v)[i];
+            const float4 g = __ldg(reinterpret_cast<const float4*>(d.g) + i);
+            upd(p.x, g.x, m.x, v.x); upd(p.y, g.y, m.y, v.y); upd(p.z, g.z, m.z, v.z); upd(p.w, g.w, m.w, v.w);
+            reinterpret_cast<float4*>(d.p)[i] = p;
+            reinterpret_cast<float4*>(d.m)[i] = m;
+            reinterpret_cast<float4*>(d.v)[i] = v;
+        }
+    }
+    for (long long i = (vec ? n4 * 4 : 0) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.n; i += (long long)gridDim.x * blockDim.x)
+        upd(d.p[i], d.g[i], d.m[i], d.v[i]);
+}
+
 // out[i] = in[i] * scale_ptr[0] * scale  (chain rule for a scalar upstream gradient living on the device)
 template <typename T>
 __global__ void scale_kernel(const T* __restrict__ in, T* __restrict__ out, long long n8, const float* __restrict__ scale_ptr,
@@ -1075,6 +1106,18 @@ extern "C" __attribute__((visibility("default"))) int fv_recon_loss_flat(const f
         return fail(FV_ERR_ARG, "fv_recon_loss_flat: pointers must be 16-byte aligned");
     recon_loss_flat_kernel<<<grid_for(E / 4 + 1), kThreads, 0, STREAM>>>(a, b, grad, loss_sum, E, l1, gscale);
     FV_LAUNCH_CHECK("recon_loss_flat_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_adam_multi(const fv_adam_desc* table_dev, int n_tensors, long long max_n, float lr, float beta1,
+                                                                  float beta2, float eps, const float* step_dev, void* stream) {
+    if (!table_dev || !step_dev || n_tensors < 1 || max_n < 1) return fail(FV_ERR_ARG, "fv_adam_multi: bad arguments");
+    long long bx = (max_n / 4 + kThreads * 2 - 1) / (kThreads * 2);
+    const long long cap = (long long)num_sms() * 16 / n_tensors + 1;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    adam_multi_kernel<<<dim3((unsigned)bx, (unsigned)n_tensors), kThreads, 0, STREAM>>>(table_dev, lr, beta1, beta2, eps, step_dev);
+    FV_LAUNCH_CHECK("adam_multi_kernel");
     return FV_OK;
 }
 

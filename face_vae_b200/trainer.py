@@ -61,11 +61,15 @@ class VAETrainer:
                 use_cuda_graph = use_cuda_graph and os.environ.get("FACEVAE_CUDA_GRAPH_DDP", "1") != "0"
         self.use_cuda_graph = bool(use_cuda_graph) and on_cuda
         kw = {}
-        if fused_adam and on_cuda:
-            kw["fused"] = True
-            if self.use_cuda_graph:
-                kw["capturable"] = True
-        self.optimizer = torch.optim.Adam(params, lr=lr, betas=(0.5, 0.999), **kw)
+        if fused_adam and on_cuda and os.environ.get("FACEVAE_FUSED_ADAM", "1") != "0":
+            from .optim import FusedAdam              # one multi-tensor launch, device-resident step count (graph-capturable)
+            self.optimizer = FusedAdam(params, lr=lr, betas=(0.5, 0.999))
+        else:
+            if fused_adam and on_cuda:
+                kw["fused"] = True
+                if self.use_cuda_graph:
+                    kw["capturable"] = True
+            self.optimizer = torch.optim.Adam(params, lr=lr, betas=(0.5, 0.999), **kw)
         self.reducer = fdist.GradientReducer(params, bucket_mb) if world > 1 else None
         self._graph = None
         self._graph_key = None

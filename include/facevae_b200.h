@@ -175,6 +175,19 @@ int fv_recon_loss_flat(const float* a, const float* b, float* grad, float* loss_
 /* out = in * scale * (*scale_ptr) (scale_ptr may be NULL); n elements, n % 8 == 0. */
 int fv_scale(const void* in, void* out, int dtype, long long n, const float* scale_ptr, float scale, void* stream);
 
+/* ---- optimiser step of Logger.step (logger.py:60,160: Adam lr 5e-5, betas (0.5, 0.999)) ------------------------------------
+ * torch.optim.Adam semantics (no amsgrad, no weight decay) over a device table of n_tensors descriptors in ONE launch;
+ * *step_dev = the step count after this update (fp32, device memory: graph-capturable); max_n = the largest element count. */
+typedef struct {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    long long n;
+} fv_adam_desc;
+int fv_adam_multi(const fv_adam_desc* table_dev, int n_tensors, long long max_n, float lr, float beta1, float beta2, float eps,
+                  const float* step_dev, void* stream);
+
 /* ---- calibration (not on the product path) ---------------------------------------------------------------- */
 /* cycles for `iters` back-to-back tcgen05.mma (M=128, K=16, N=n_cols) on shared-memory-resident operands. */
 int fv_debug_mma_rate(int n_cols, int row_bytes, int iters, int a_distinct, int mn_major, int all_sms, long long* out_cycles_dev,

@@ -147,6 +147,29 @@ def test_conv_wide_row_tiles_with_256_output_channels(ops):
     _conv_case(ops, 1, 4, 256, 64, 256, 3, seed=81)
 
 
+def test_fused_adam_matches_torch_adam(ops):
+    """fv_adam_multi (one launch over a tensor table) against torch.optim.Adam, three steps, odd sizes and a tail."""
+    from face_vae_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(64, 32, 3, 3), (257,), (3, 32, 7, 7), (1,), (256, 256, 3, 3), (33, 5)]
+    pa = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = FusedAdam(pa, lr=5e-5, betas=(0.5, 0.999))
+    ob = torch.optim.Adam(pb, lr=5e-5, betas=(0.5, 0.999))
+    for it in range(3):
+        for a, b in zip(pa, pb):
+            g = torch.randn_like(a) * (10.0 ** (it - 1))
+            a.grad, b.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+    torch.cuda.synchronize()
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=1e-6, atol=2e-7), (a - b).abs().max().item()
+    for a, b in zip(pa, pb):
+        assert torch.allclose(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"], rtol=1e-5, atol=1e-12)   # a few ulp: FMA contraction
+        assert float(oa.state[a]["step"]) == 3.0
+
+
 def test_conv_many_tiles_persistent(ops):
     # more tiles than SMs: exercises the persistent loop, TMEM double buffering and mbarrier phase wrap-around
     _conv_case(ops, 8, 64, 128, 32, 64, 3)
