@@ -48,7 +48,7 @@ SIGNATURES = {
     "fv_reparam_kl_bwd": [_p, _p, _ll, _p, _p, _p, _p, _f, _p, _p, _p, _ll, _i, _i, _p],
     "fv_recon_loss": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
     "fv_recon_loss_flat": [_p, _p, _p, _p, _ll, _i, _f, _p],
-    "fv_adam_multi": [_p, _i, _ll, _f, _f, _f, _f, _p, _p],
+    "fv_adam_multi": [_p, _i, _ll, _f, _d, _d, _f, _p, _p],
     "fv_scale": [_p, _p, _i, _ll, _p, _f, _p],
     "fv_pw_moments": [_p, _p, _i, _i, _i, _p],
     "fv_pw_prepare": [_p, _d, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _p],

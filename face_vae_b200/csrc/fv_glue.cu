@@ -788,18 +788,26 @@ __global__ void recon_loss_flat_kernel(const float* __restrict__ a, const float*
 // Adam (torch.optim.Adam semantics without amsgrad / weight decay, reference logger.py:60) over a table of tensors in ONE
 // launch: blockIdx.y = tensor, grid-stride over its elements.  `step` is the step count AFTER this update, read from
 // device memory so that the launch can be captured in a CUDA graph.
-__global__ void adam_multi_kernel(const fv_adam_desc* __restrict__ table, float lr, float beta1, float beta2, float eps,
+__global__ void adam_multi_kernel(const fv_adam_desc* __restrict__ table, float lr, double beta1_d, double beta2_d, float eps,
                                   const float* __restrict__ step) {
     const fv_adam_desc d = table[blockIdx.y];
-    const float t = __ldg(step);
-    const float bc1 = 1.f - powf(beta1, t), bc2 = 1.f - powf(beta2, t);
-    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    // coefficients as torch.optim.Adam forms them: 1 - beta and the bias corrections 1 - beta^t in double (0.999f is 4.7e-5
+    // away from 0.999 relative to 1 - beta), once per block
+    __shared__ float coef[2];
+    if (threadIdx.x == 0) {
+        const double t = (double)__ldg(step);
+        coef[0] = (float)((double)lr / (1.0 - pow(beta1_d, t)));
+        coef[1] = (float)(1.0 / sqrt(1.0 - pow(beta2_d, t)));
+    }
+    __syncthreads();
+    const float beta1 = (float)beta1_d, beta2 = (float)beta2_d, omb1 = (float)(1.0 - beta1_d), omb2 = (float)(1.0 - beta2_d);
+    const float step_size = coef[0], inv_sqrt_bc2 = coef[1];
     const long long n4 = d.n / 4;
     const bool vec = ((reinterpret_cast<uintptr_t>(d.p) | reinterpret_cast<uintptr_t>(d.g) | reinterpret_cast<uintptr_t>(d.m) |
                        reinterpret_cast<uintptr_t>(d.v)) & 15) == 0;
     auto upd = [&](float& p, float g, float& m, float& v) {
-        m = beta1 * m + (1.f - beta1) * g;
-        v = beta2 * v + (1.f - beta2) * g * g;
+        m = beta1 * m + omb1 * g;
+        v = beta2 * v + omb2 * g * g;
         p -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
     };
     if (vec) {
@@ -1109,8 +1117,8 @@ extern "C" __attribute__((visibility("default"))) int fv_recon_loss_flat(const f
     return FV_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int fv_adam_multi(const fv_adam_desc* table_dev, int n_tensors, long long max_n, float lr, float beta1,
-                                                                  float beta2, float eps, const float* step_dev, void* stream) {
+extern "C" __attribute__((visibility("default"))) int fv_adam_multi(const fv_adam_desc* table_dev, int n_tensors, long long max_n, float lr, double beta1,
+                                                                  double beta2, float eps, const float* step_dev, void* stream) {
     if (!table_dev || !step_dev || n_tensors < 1 || max_n < 1) return fail(FV_ERR_ARG, "fv_adam_multi: bad arguments");
     long long bx = (max_n / 4 + kThreads * 2 - 1) / (kThreads * 2);
     const long long cap = (long long)num_sms() * 16 / n_tensors + 1;

@@ -185,7 +185,7 @@ typedef struct {
     float* v;
     long long n;
 } fv_adam_desc;
-int fv_adam_multi(const fv_adam_desc* table_dev, int n_tensors, long long max_n, float lr, float beta1, float beta2, float eps,
+int fv_adam_multi(const fv_adam_desc* table_dev, int n_tensors, long long max_n, float lr, double beta1, double beta2, float eps,
                   const float* step_dev, void* stream);
 
 /* ---- calibration (not on the product path) ---------------------------------------------------------------- */
