@@ -1,0 +1,86 @@
+"""Host-side logic that needs no GPU: shape predicates of the C ABI, argument checking of the newer entry points, the
+per-step scratch arena, and the optimiser's refusal of CPU tensors (the package has no CPU compute path)."""
+import ctypes
+
+import pytest
+import torch
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from face_vae_b200 import _lib
+    return _lib.load()
+
+
+def test_outconv_shape_predicate(lib):
+    ok = lib.fv_outconv_supported
+    assert ok(32, 256, 256, 32, 3, 7, 7) == 1          # BASELINE.json configs[1]: batch 32 at 256x256
+    assert ok(8, 128, 128, 32, 4, 7, 7) == 1
+    assert ok(8, 64, 64, 32, 3, 7, 7) == 0             # W = 64: generic kernels (the CPU-anchor size of the parity tests)
+    assert ok(8, 512, 512, 32, 3, 7, 7) == 0           # W = 512: generic kernels
+    assert ok(8, 256, 256, 64, 3, 7, 7) == 0           # 64 input channels
+    assert ok(8, 256, 256, 32, 5, 7, 7) == 0           # more than 4 output channels
+    assert ok(8, 256, 256, 32, 3, 3, 3) == 0           # not a 7x7 filter
+
+
+def test_conv_stats_fusion_predicate_on_the_anchor_layers(lib):
+    """Which layers of the anchor produce their batch-norm sums in the conv epilogue: the 32-channel ring
+    layer and the K >= 1152 layers; the 64-channel ring layer and the K = 576 / N = 128 layer keep a separate pass."""
+    f = lambda ci, co, hw: lib.fv_conv2d_fuses_stats(0, 32, hw, hw, ci, co, 3, 3, 0)
+    assert f(64, 32, 256) == 1 and f(256, 256, 32) == 1 and f(256, 128, 64) == 1 and f(128, 64, 128) == 1 and f(256, 32, 32) == 1
+    assert f(32, 64, 256) == 0 and f(64, 128, 128) == 0 and f(128, 256, 64) == 0
+    assert lib.fv_conv2d_fuses_stats(2, 32, 64, 64, 128, 256, 3, 3, 0) == 0        # NCHW fp32 output: never
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_gpu(lib):
+    assert lib.fv_outconv_fwd(None, None, None, None, None, None, None, None, None, 1, 8, 128, 32, 3, 0, 1, 1.0, None) != 0
+    assert b"null pointer" in lib.fv_last_error()
+    assert lib.fv_outconv_dgrad(None, None, None, None, 1, 8, 128, 32, 3, None) != 0
+    assert lib.fv_outconv_wgrad(None, None, None, None, 1, 8, 128, 32, 3, None) != 0
+    assert lib.fv_outconv_prep(None, None, None, 3, 32, None) != 0
+    assert lib.fv_conv2d_stats(None, None, None, None, None, 0, 1, 8, 8, 16, 16, 16, 3, 3, 1, None, None) != 0
+    assert lib.fv_weight_prep_batched(None, 1, 10, None) != 0
+    assert lib.fv_adam_multi(None, 1, 10, 1e-3, 0.9, 0.999, 1e-8, None, None) != 0
+    assert lib.fv_bn_act_fwd_fin(None, 0, None, 1.0, None, None, None, None, 0.1, 1e-5, None, None, 0, 0, 1, 8, 8, 16, 0, 1, None) != 0
+    assert lib.fv_bn_act_bwd_apply_fin(None, 0, None, 0, 0, None, None, 1.0, None, None, None, None, 1, 8, 8, 16, 0, 1, None) != 0
+
+
+def test_zero_arena_hands_out_clean_aligned_slices():
+    from face_vae_b200 import ops
+    arena = ops._ZeroArena()
+    dev = torch.device("cpu")
+    assert arena.take((4,), torch.float32, dev) is None                  # outside a step: the caller allocates for itself
+    arena.begin(dev)
+    a = arena.take((3, 5), torch.float32, dev)
+    b = arena.take((7,), torch.float64, dev)
+    assert a.shape == (3, 5) and b.dtype == torch.float64 and float(a.abs().sum()) == 0.0 and float(b.abs().sum()) == 0.0
+    assert (b.data_ptr() - a.data_ptr()) % 256 == 0 and b.data_ptr() != a.data_ptr()
+    a.fill_(3.0)
+    b.fill_(5.0)
+    need = arena.need
+    arena.begin(dev)                                                      # next step: same offsets, zeroed again
+    a2 = arena.take((3, 5), torch.float32, dev)
+    assert a2.data_ptr() == a.data_ptr() and float(a2.abs().sum()) == 0.0 and need > 0
+    n_big = arena.buf.numel()
+    assert arena.take((n_big,), torch.float32, dev) is None              # does not fit: the caller falls back to torch.zeros ...
+    arena.begin(dev)                                                      # ... and the arena has grown for the next step
+    assert arena.buf.numel() >= 4 * n_big
+    assert arena.take((n_big,), torch.float32, dev) is not None
+
+
+def test_fused_adam_refuses_cpu_tensors():
+    from face_vae_b200 import _lib
+    from face_vae_b200.optim import FusedAdam
+    p = torch.zeros(4, requires_grad=True)
+    p.grad = torch.ones(4)
+    opt = FusedAdam([p], lr=1e-3)
+    with pytest.raises(_lib.FaceVaeError):
+        opt.step()
+
+
+def test_ops_refuse_cpu_tensors():
+    from face_vae_b200 import _lib, ops
+    with pytest.raises(_lib.FaceVaeError):
+        ops.bn_stats(torch.zeros((1, 2, 2, 16)))
+    with pytest.raises(_lib.FaceVaeError):
+        ops.outconv_prep(torch.zeros((3, 32, 7, 7)))
