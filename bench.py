@@ -256,6 +256,12 @@ def main():
                     "frac_of_burst_peak": ach / peaks["bf16"], "peak_source": peaks["source"] + " (sustained: timed inside the step)",
                     "avg_launch_ms": conv["ms"] / conv["launches"], "launches_per_step": conv["launches"] / args.profile_steps,
                     "traffic": None}
+        # DRAM bytes per launch of these kernels from the committed ncu launch list of this command (profiles/)
+        tpath = os.path.join(ROOT, "profiles", "r01_final_conv_traffic.json")
+        if os.path.exists(tpath) and B == 32 and S == 256 and not args.deep:
+            t = json.load(open(tpath))
+            roofline["traffic"] = t["bytes_per_launch"]
+            roofline["traffic_source"] = "profiles/r01_final_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per launch)"
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
