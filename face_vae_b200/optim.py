@@ -45,6 +45,9 @@ class FusedAdam(torch.optim.Optimizer):
                         not p.grad.is_contiguous():
                     raise _lib.FaceVaeError("FusedAdam: contiguous fp32 CUDA parameters and gradients only (no CPU path)")
             states = [self._init_state(p) for p in ps]
+            for p, st in zip(ps, states):          # state loaded from a torch.optim.Adam checkpoint: python / CPU step counts
+                if not torch.is_tensor(st["step"]) or st["step"].device != p.device or st["step"].dtype != torch.float32:
+                    st["step"] = torch.tensor(float(st["step"]), dtype=torch.float32, device=p.device)
             steps = [st["step"] for st in states]
             torch._foreach_add_(steps, 1.0)
             key = (gi,) + tuple((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr())

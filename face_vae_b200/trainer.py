@@ -151,6 +151,25 @@ class VAETrainer:
         self._graph.replay()
         return self._static_out
 
+    # -- checkpoints (reference Logger.save_cpk / load_cpk, logger.py:93-115) ---------------------------------------------
+    def checkpoint(self, name: str = "vae", epoch: int = 0) -> dict:
+        """The reference's checkpoint dict for one model: {name: state_dict, "optimizer_" + name: ..., "epoch": epoch}."""
+        return {name: self.vae.state_dict(), "optimizer_" + name: self.optimizer.state_dict(), "epoch": epoch}
+
+    def save_cpk(self, path: str, name: str = "vae", epoch: int = 0) -> None:
+        if fdist.is_master():
+            torch.save(self.checkpoint(name, epoch), path)
+
+    def load_cpk(self, path_or_dict, name: str = "vae") -> int:
+        """Loads model and optimiser state written by save_cpk or by the reference's Logger; -> the epoch to resume at
+        (checkpoint epoch + 1, logger.py:115).  A captured CUDA graph is dropped: the optimiser state tensors are new."""
+        ckp = path_or_dict if isinstance(path_or_dict, dict) else torch.load(path_or_dict, map_location=torch.device("cpu"))
+        self.vae.load_state_dict(ckp[name])
+        self.optimizer.load_state_dict(ckp["optimizer_" + name])
+        self._graph = None
+        self._graph_key = None
+        return int(ckp["epoch"]) + 1
+
     def step(self, d: torch.Tensor, eps: Optional[torch.Tensor] = None):
         """-> (loss dict {"K", "R"} already weight-multiplied, generated frames).  With CUDA graphs the returned tensors are
         the graph's static outputs: they are overwritten by the next step."""

@@ -84,3 +84,33 @@ def test_ops_refuse_cpu_tensors():
         ops.bn_stats(torch.zeros((1, 2, 2, 16)))
     with pytest.raises(_lib.FaceVaeError):
         ops.outconv_prep(torch.zeros((3, 32, 7, 7)))
+
+
+def test_checkpoint_format_and_optimizer_state_interchange(tmp_path):
+    """Reference Logger checkpoint layout (logger.py:93-115) and FusedAdam <-> torch.optim.Adam state dicts (host side only)."""
+    from face_vae_b200.models import FaceVAE
+    from face_vae_b200.optim import FusedAdam
+    from face_vae_b200.trainer import VAETrainer
+    torch.manual_seed(0)
+    tr = VAETrainer(FaceVAE())                              # CPU parameters: construction and (de)serialisation need no GPU
+    for p in tr.vae.parameters():                           # give the optimiser some state, as after a few steps
+        p.grad = torch.full_like(p, 1e-3)
+    tr.optimizer.step()
+    path = tmp_path / "00000007-checkpoint.pth.tar"
+    tr.save_cpk(str(path), "vae", epoch=7)
+    ckp = torch.load(str(path), map_location="cpu")
+    assert set(ckp) == {"vae", "optimizer_vae", "epoch"} and ckp["epoch"] == 7
+    assert "enc.0.layers.layers.0.weight" in ckp["vae"] or any(k.endswith("layers.0.weight") for k in ckp["vae"])
+    tr2 = VAETrainer(FaceVAE())
+    assert tr2.load_cpk(str(path), "vae") == 8
+    for a, b in zip(tr.vae.state_dict().values(), tr2.vae.state_dict().values()):
+        assert torch.equal(a, b)
+    # the same optimiser state loads into FusedAdam (and its state dict back into torch.optim.Adam)
+    params = list(tr2.vae.parameters())
+    fa = FusedAdam(params, lr=5e-5, betas=(0.5, 0.999))
+    fa.load_state_dict(ckp["optimizer_vae"])
+    st = fa.state[params[0]]
+    assert set(st) >= {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 1.0
+    ta = torch.optim.Adam(params, lr=5e-5, betas=(0.5, 0.999))
+    ta.load_state_dict(fa.state_dict())
+    assert torch.equal(ta.state[params[0]]["exp_avg"], tr.optimizer.state[next(iter(tr.vae.parameters()))]["exp_avg"])
