@@ -26,42 +26,55 @@ SIGNATURES = {
     "fv_nhwc_to_nchw": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_weight_prep": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_weight_prep_batched": [_p, _i, _ll, _p],
+    "fv_weight_prep_up": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "fv_weight_prep_s2": [_p, _p, _p, _i, _i, _i, _i, _p],
     "fv_conv2d": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
-    "fv_conv2d_stats": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p],
-    "fv_conv2d_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
-    "fv_wgrad_finish": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
-    "fv_colsum": [_p, _p, _ll, _i, _p],
+    "fv_conv2d_stats": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+    "fv_conv2d_x2": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+    "fv_conv2d_s2": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+    "fv_conv2d_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "fv_conv2d_wgrad_x2": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_conv2d_wgrad_s2": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_wgrad_finish": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "fv_wgrad_finish_up": [_p, _i, _p, _i, _i, _i, _i, _i, _p],
+    "fv_slab_sum": [_p, _i, _ll, _p, _ll, _i, _p],
+    "fv_colsum": [_p, _p, _ll, _i, _p, _p],
     "fv_outconv_prep": [_p, _p, _p, _i, _i, _p],
-    "fv_outconv_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
+    "fv_outconv_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p],
     "fv_outconv_dgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
-    "fv_outconv_wgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
-    "fv_bn_stats": [_p, _i, _p, _ll, _i, _p],
+    "fv_outconv_wgrad": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_bn_stats": [_p, _i, _p, _ll, _i, _p, _p],
     "fv_bn_finalize": [_p, _d, _p, _p, _p, _p, _f, _f, _p, _i, _p],
     "fv_bn_eval_affine": [_p, _p, _p, _p, _f, _p, _i, _p],
     "fv_bn_act_fwd": [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "fv_bn_act_fwd_fin": [_p, _i, _p, _d, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "fv_bn_act_bwd_apply_fin": [_p, _i, _p, _i, _i, _p, _p, _d, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
-    "fv_bn_act_bwd_reduce": [_p, _i, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_bn_act_bwd_reduce": [_p, _i, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "fv_bn_bwd_finalize": [_p, _p, _d, _p, _p, _p, _i, _i, _p],
     "fv_bn_act_bwd_apply": [_p, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_reparam_kl_fwd": [_p, _p, _ll, _p, _p, _p, _i, _i, _p],
     "fv_reparam_kl_bwd": [_p, _p, _ll, _p, _p, _p, _p, _f, _p, _p, _p, _ll, _i, _i, _p],
-    "fv_recon_loss": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p],
-    "fv_recon_loss_flat": [_p, _p, _p, _p, _ll, _i, _f, _p],
+    "fv_recon_loss": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p],
+    "fv_recon_loss_flat": [_p, _p, _p, _p, _ll, _i, _f, _p, _p],
     "fv_adam_multi": [_p, _i, _ll, _f, _d, _d, _f, _p, _p],
     "fv_scale": [_p, _p, _i, _ll, _p, _f, _p],
-    "fv_pw_moments": [_p, _p, _i, _i, _i, _p],
+    "fv_pw_moments": [_p, _p, _i, _i, _i, _p, _p],
     "fv_pw_prepare": [_p, _d, _p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _p],
     "fv_pw_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _p],
-    "fv_pw_bwd_reduce": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "fv_pw_bwd_reduce": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
     "fv_pw_bwd_finalize": [_p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "fv_bn_finalize_xrank": [_p, _p, _i, _i, _p, _i, _d, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i, _i, _p],
     "fv_debug_mma_rate": [_i, _i, _i, _i, _i, _i, _p, _p],
     "fv_debug_trace_set": [_p],
 }
 _STR = ("fv_last_error", "fv_version")
-_LL = ("fv_xrank_buffer_floats",)
-_PLAIN_INT = {"fv_outconv_supported": [_i, _i, _i, _i, _i, _i, _i], "fv_conv2d_fuses_stats": [_i, _i, _i, _i, _i, _i, _i, _i, _i]}   # predicates: the return value is the answer
+_LL = ("fv_xrank_buffer_floats", "fv_reduce_ws_bytes")
+# predicates / planning queries: the return value is the answer
+_PLAIN_INT = {"fv_outconv_supported": [_i, _i, _i, _i, _i, _i, _i], "fv_conv2d_fuses_stats": [_i, _i, _i, _i, _i, _i, _i, _i, _i],
+              "fv_conv2d_wgrad_splits": [_i, _i, _i, _i, _i, _i, _i, _i],
+              "fv_conv2d_geom_fuses_stats": [_i, _i, _i, _i, _i, _i, _i], "fv_outconv_wgrad_splits": [_i, _i, _i],
+              "fv_reparam_kl_parts": [_i, _i], "fv_abi_version": []}
+ABI_VERSION = 2            # include/facevae_b200.h FV_ABI_VERSION
 
 _lock = threading.Lock()
 _lib = None
@@ -79,12 +92,19 @@ def load(build_if_missing: bool = True):
     with _lock:
         if _lib is not None:
             return _lib
+        from . import build as _build
         if not os.path.exists(LIB_PATH):
             if not build_if_missing:
                 raise FaceVaeError(f"{LIB_PATH} is missing; run `python -m face_vae_b200.build` (needs nvcc)")
-            from . import build as _build
             _build.build()
+        elif build_if_missing and _build.stale() and _build.have_nvcc():
+            _build.build()            # sources changed since the library was built: never bind new signatures to an old binary
         lib = C.CDLL(LIB_PATH)
+        lib.fv_abi_version.restype = C.c_int
+        lib.fv_abi_version.argtypes = []
+        if lib.fv_abi_version() != ABI_VERSION:
+            raise FaceVaeError(f"{LIB_PATH} has ABI version {lib.fv_abi_version()}, this package binds version {ABI_VERSION}: "
+                               "rebuild with `python -m face_vae_b200.build --force`")
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = args

@@ -1,52 +1,71 @@
-// Implicit-GEMM 2-D convolution (stride 1, "same" padding) for sm_100a: NHWC bf16 in, fp32 accumulate in TMEM.
+// Implicit-GEMM 2-D convolution for sm_100a: NHWC bf16 in, fp32 accumulate in TMEM.  Three geometries share one kernel:
 //
-//   Y[pixel, co] = sum_{r,s,ci} X[pixel + (r - pad, s - pad), ci] * Wt[co, (r*S + s)*Ci + ci]     (+ bias, + residual)
+//   SAME : Y[p, co] = sum_{r,s,ci} X[p + (r - pad, s - pad), ci] * Wt[co, (r*S + s)*Ci + ci]     stride 1, odd filter, "same" padding
+//          -- the nn.Conv2d inside the reference's _ConvBlock (reference modules.py:15,32), forward, and (called with the
+//          rotated / transposed filter of fv_weight_prep) its data gradient;
+//   X2   : nearest 2x up-sampling followed by a 3x3 "same" convolution (UpBlock2D, reference modules.py:78-89) WITHOUT the
+//          up-sampled tensor: output pixel (2i + a, 2j + b) only ever sees a 2x2 neighbourhood of the coarse input, so the
+//          layer is four 2x2 convolutions ("phases" (a, b)) on the coarse grid whose filters are sums of the 3x3 taps
+//          (fv_weight_prep_up) -- 16 tap-GEMMs per coarse pixel instead of 36 and a 4x smaller input to read.  The same
+//          schedule is the data gradient of a 4x4 stride-2 convolution;
+//   S2   : 4x4 stride-2 pad-1 convolution (Conv2dELR as used by EFE_conv6, reference models_utils.py:632-744,
+//          models.py:845-852) and -- with summed, mirrored taps -- the data gradient of X2 (it folds the 2x2 sum of the
+//          up-sampling backward into the GEMM).  The fine NHWC tensor [N,2H,2W,C] is addressed through a 5-D tensor map
+//          (2C, W, 2, H, N): tap (r, s) is a box at row parity a, channel offset b*C, coarse offset (dh, dw).
 //
-// GEMM view: M = N*H*W pixels (128 per tile), N = Co_pad (one UMMA N, <= 256), K = R*S*Ci.  Replaces the
-// nn.Conv2d inside the reference's _ConvBlock (reference modules.py:15,32) -- forward, and (called with the
-// rotated/transposed filter produced by fv_weight_prep) its data gradient.
+// GEMM view: M = pixels of the tiling grid (128 per tile), N = Co_pad (one UMMA N, <= 256), K = taps * Ci.
 //
 // Structure (one persistent CTA per SM, 6 warps):
-//   warp 0  : TMA producer.  Activations come through a 4-D tensor map over (C, W, H, N); pixels outside the image
-//             are zero-filled by the TMA unit, so padding costs no memory and no branches.  Two load schedules:
-//               tap mode  : one box (KB ch, tw, th, tn) per filter tap, at (kc, w0 + s - pad, h0 + r - pad, n0);
-//               slab mode : (tiles that are one image-row segment, th == tn == 1) one box (KB ch, tw + S - 1) per
-//                           filter ROW; the S taps of that row are the same shared-memory slab read through UMMA
-//                           descriptors whose start address is shifted by s pixel rows -- S x fewer bytes through
-//                           L2 -> SMEM and S x fewer TMA transactions.
-//             The matching [Co_pad x KB] slices of the K-major filter matrix come through a 2-D map.
-//   warp 1  : one thread issues tcgen05.mma (UMMA 128 x Co_pad x 16, bf16 -> fp32) into one of two TMEM
-//             accumulator buffers and commits to the stage / accumulator mbarriers.
+//   warp 0  : TMA producer.  Activations come through a 5-D tensor map; pixels outside the image are zero-filled by the
+//             TMA unit, so padding costs no memory and no branches.  A "group" is one activation box plus the filter
+//             slices it feeds: one filter tap (tap schedule: box (KB ch, tw, th, tn)), or -- SAME geometry with row-segment
+//             tiles -- one filter ROW (slab schedule: box (KB ch, tw + S - 1); the S taps of that row are the same
+//             shared-memory slab read through UMMA descriptors whose start address is shifted by s pixel rows).  Box
+//             coordinates come from a per-(phase, group) table in the kernel parameters.
+//   warp 1  : one thread issues tcgen05.mma (UMMA 128 x Nc x 16, bf16 -> fp32) into one of two TMEM accumulator
+//             buffers and commits to the stage / accumulator mbarriers.
 //   warps 2-5: epilogue.  tcgen05.ld their TMEM lane quarter (row = pixel), add bias / residual, convert and store
-//             (NHWC bf16, NHWC fp32 or NCHW fp32); overlapped with the next tile's MMAs via the second buffer.
-// The single-thread producer / issuer loops carry no divisions: stage index and phase advance incrementally and the
-// UMMA descriptors are formed by 32-bit adds on a precomputed template.
+//             (NHWC bf16, NHWC fp32 or NCHW fp32); overlapped with the next tile's MMAs via the second buffer.  Optional
+//             fused batch-norm statistics of the stored values, reduced across CTAs in a fixed order (fv_reduce.cuh).
 #include <cstdio>
 #include <cstdlib>
 
 #include "../../include/facevae_b200.h"
 #include "fv_host.h"
 #include "fv_ptx.cuh"
+#include "fv_reduce.cuh"
 
 namespace fv {
 
+enum : int { CONV_SAME = 0, CONV_X2 = 1, CONV_S2 = 2 };
+
 struct ConvParams {
-    int N, H, W, Ci, Co, Co_pad, R, S, pad;
+    int N, H, W;            // tiling grid (X2 / S2: the COARSE resolution)
+    int Ci, Co, Co_pad;
+    int Ho, Wo, osy, osx;   // output image size and pixel stride: tile pixel (h, w) of phase ph -> (h*osy + oy[ph], w*osx + ox[ph])
     int tw, th, tn, tiles_w, tiles_h, tiles_n, num_tiles;
-    int kc_blocks, stages, slab;
-    int a_off_b;          // byte offset of the filter slices inside a stage (activation region, rounded to 1 KB)
-    int b_slice_stride;   // placement stride of one [Co_pad x KB] filter slice (rounded to 1 KB)
+    int kc_blocks, stages;
+    int groups;             // TMA groups per (phase, tile)
+    int nsub;               // filter taps per group (slab schedule: S, tap schedule: 1)
+    int nph;                // output phases: 1, or 4 (X2)
+    int a_off_b;            // byte offset of the filter slices inside a stage (activation region, rounded to 1 KB)
+    int b_slice_stride;     // placement stride of one [Nc x KB] filter slice (rounded to 1 KB)
     int stage_stride;
-    int tx_bytes;         // bytes the TMA unit delivers per stage (what the full barrier is armed with)
+    int tx_bytes;           // bytes the TMA unit delivers per stage (what the full barrier is armed with)
     int out_mode, tmem_cols;
-    int out_cs;           // channel stride (elements) of the NHWC output / residual rows (>= Co_pad when Co is split)
-    int co_parts, Nc;     // output channels split over co_parts CTAs per pixel tile (layers with fewer tiles than SMs): Nc = Co_pad / co_parts
-    int num_vtiles;       // num_tiles * co_parts
+    int out_cs;             // channel stride (elements) of the NHWC output / residual rows
+    int co_base;            // first output channel of this launch inside the out_cs-wide rows (Co_pad > 256 is walked in chunks)
+    int w_rows_per_phase;   // rows of the filter matrix per phase (= total Co_pad of the layer)
+    int co_parts, Nc;       // output channels split over co_parts CTAs per pixel tile (few tiles): Nc = Co_pad / co_parts
+    int num_vtiles;         // nph * co_parts * num_tiles
     const float* bias;
     const __nv_bfloat16* residual;
     void* out;
-    float* stats;         // optional [2][stats_c]: per-channel sum / sum of squares of the stored output (fused fv_bn_stats)
+    float* stats;           // optional [2][stats_c]: per-channel sum / sum of squares of the stored output (fused fv_bn_stats)
     int stats_c;
+    void* red_ws;           // fv_reduce.cuh workspace (with stats)
+    short4 tap[64];         // per (phase, group): x = channel offset, y = dw, z = row parity / 0, w = dh of the activation box
+    signed char oy[4], ox[4];
 };
 
 static constexpr int kConvThreads = 192;
@@ -61,10 +80,18 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
     const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
     return {tw_i * p.tw, th_i * p.th, tn_i * p.tn};
 }
+// virtual tile -> (phase, output-channel part, pixel tile); consecutive CTAs work on the same filter slice
+__device__ __forceinline__ void decode_vtile(const ConvParams& p, int vt, int& ph, int& part, int& tile) {
+    const int per_ph = p.num_tiles * p.co_parts;
+    ph = vt / per_ph;
+    const int rem = vt - ph * per_ph;
+    part = rem / p.num_tiles;
+    tile = rem - part * p.num_tiles;
+}
 
 template <int KB>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ ConvParams p) {
     constexpr int ROW = KB * 2;                       // bytes per pixel row of a K block == swizzle span
     constexpr int KSUB = KB / 16;                     // UMMA K steps per K block
     constexpr uint32_t LAYOUT = ROW == 128 ? 2u : (ROW == 64 ? 4u : 6u);
@@ -78,8 +105,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint64_t* tfull = empty + p.stages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    int* red_flag = reinterpret_cast<int*>(tmem_slot + 2);
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);      // [Co_pad]
-    float* stat_s = bias_s + p.Co_pad;                            // [2][Co_pad] CTA-level statistic accumulators (when p.stats)
+    float* stat_w = bias_s + p.Co_pad;                            // [4 epilogue warps][2][Co_pad] (when p.stats)
+    float* stat_blk = stat_w + 8 * p.Co_pad;                      // [2][Co_pad] this CTA's totals
+    float* stat_tot = stat_blk + 2 * p.Co_pad;                    // [2][Co_pad] grid totals (in the last CTA)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -102,39 +132,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
     for (int c = threadIdx.x; c < p.Co_pad; c += blockDim.x) bias_s[c] = (p.bias && c < p.Co) ? p.bias[c] : 0.f;
     if (p.stats)
-        for (int c = threadIdx.x; c < 2 * p.Co_pad; c += blockDim.x) stat_s[c] = 0.f;
+        for (int c = threadIdx.x; c < 8 * p.Co_pad; c += blockDim.x) stat_w[c] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int s_loads = p.slab ? 1 : p.S;             // activation boxes per (r, kc) group
-    const int s_mmas = p.slab ? p.S : 1;              // filter taps consumed per stage
 
     if (warp == 0) {
         {
             const bool leader = elect_one_sync();      // role loops stay warp-uniform; only the issue is predicated
             uint32_t st = 0, ph = 0;
             for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
-                const int part = vt / p.num_tiles, tile = vt - part * p.num_tiles;
-                const int co0 = part * p.Nc;
+                int phase, part, tile;
+                decode_vtile(p, vt, phase, part, tile);
+                const int wrow = phase * p.w_rows_per_phase + p.co_base + part * p.Nc;   // first row of this CTA's filter slice
                 const TileCoord t = decode_tile(p, tile);
-                for (int r = 0; r < p.R; ++r) {
-                    const int hh = t.h0 + r - p.pad;
-                    for (int sl = 0; sl < s_loads; ++sl) {
-                        const int ww = t.w0 + sl - p.pad;                 // slab mode: sl == 0, the box is S - 1 pixels wider
-                        const int wtap = (r * p.S + sl) * p.Ci;           // first filter column of this stage
-                        for (int kc = 0; kc < p.kc_blocks; ++kc) {
-                            mbar_wait(&empty[st], ph ^ 1);
-                            uint8_t* a_dst = smem + (size_t)st * p.stage_stride;
-                            uint8_t* b_dst = a_dst + p.a_off_b;
-                            if (leader) {
-                                mbar_arrive_expect_tx(&full[st], (uint32_t)p.tx_bytes);
-                                tma_load_4d(a_dst, &tmX, &full[st], kc * KB, ww, hh, t.n0);
-                            }
-                            for (int sm = 0; sm < s_mmas; ++sm)
-                                if (leader) tma_load_2d(b_dst + sm * p.b_slice_stride, &tmW, &full[st], wtap + sm * p.Ci + kc * KB, co0);
-                            if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
+                for (int g = 0; g < p.groups; ++g) {
+                    const short4 tp = p.tap[phase * p.groups + g];
+                    const int wtap = g * p.nsub * p.Ci;                   // first filter column of this group
+                    for (int kc = 0; kc < p.kc_blocks; ++kc) {
+                        mbar_wait(&empty[st], ph ^ 1);
+                        uint8_t* a_dst = smem + (size_t)st * p.stage_stride;
+                        uint8_t* b_dst = a_dst + p.a_off_b;
+                        if (leader) {
+                            mbar_arrive_expect_tx(&full[st], (uint32_t)p.tx_bytes);
+                            tma_load_5d(a_dst, &tmX, &full[st], kc * KB + tp.x, t.w0 + tp.y, tp.z, t.h0 + tp.w, t.n0);
                         }
+                        for (int sm = 0; sm < p.nsub; ++sm)
+                            if (leader) tma_load_2d(b_dst + sm * p.b_slice_stride, &tmW, &full[st], wtap + sm * p.Ci + kc * KB, wrow);
+                        if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
                     }
                 }
             }
@@ -145,7 +171,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t idesc = umma_idesc_bf16(128, p.Nc, 0, 0);
             const uint64_t desc_hi = umma_smem_desc(0, 16, SBO, LAYOUT);   // template: all fields but the start address
             const uint32_t smem_base = smem_u32(smem);
-            const int groups = p.R * s_loads * p.kc_blocks;
+            const int groups = p.groups * p.kc_blocks;
             uint32_t st = 0, ph = 0, tcount = 0;
             // `probe`: the NEXT stage's full barrier, tested (non-blocking) before the current stage's MMAs are issued and
             // consumed after them -- an mbarrier round trip costs the issuing warp 150-300 cycles even when the phase is
@@ -166,7 +192,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     }
                     const uint32_t a_addr = smem_base + st * (uint32_t)p.stage_stride;
                     const uint32_t b_addr = a_addr + (uint32_t)p.a_off_b;
-                    for (int sm = 0; sm < s_mmas; ++sm) {
+                    for (int sm = 0; sm < p.nsub; ++sm) {
                         const uint32_t a_lo = (a_addr + (uint32_t)sm * ROW) >> 4;   // slab: tap sm == slab shifted by sm pixel rows
                         const uint32_t b_lo = (b_addr + (uint32_t)sm * p.b_slice_stride) >> 4;
 #pragma unroll
@@ -187,20 +213,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int q = warp & 3;              // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;       // tile row == pixel within the tile
         const int w_l = row % p.tw, h_l = (row / p.tw) % p.th, n_l = row / (p.tw * p.th);
+        float* my_stat = stat_w + q * 2 * p.Co_pad;      // this warp's accumulators: lane pair k <-> channel 16 c + k, plain adds
         uint32_t tcount = 0;
         for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x, ++tcount) {
-            const int part = vt / p.num_tiles, tile = vt - part * p.num_tiles;
+            int phase, part, tile;
+            decode_vtile(p, vt, phase, part, tile);
             const int co0 = part * p.Nc;
             const TileCoord t = decode_tile(p, tile);
             const int w = t.w0 + w_l, h = t.h0 + h_l, n = t.n0 + n_l;
+            const int oh = h * p.osy + p.oy[phase], ow = w * p.osx + p.ox[phase];
             const bool valid = n < p.N;
             const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * (uint32_t)p.Nc;
-            const size_t pix = ((size_t)n * p.H + h) * p.W + w;
+            const size_t pix = ((size_t)n * p.Ho + oh) * p.Wo + ow;
             for (int cl = 0; cl < p.Nc; cl += 16) {
-                const int c0 = co0 + cl;                       // global output channel of column cl
+                const int c0 = co0 + cl;                       // output channel of column cl within this launch's chunk
                 uint32_t v[16];
                 tmem_ld16(taddr + cl, v);
                 tmem_ld_wait();
@@ -214,10 +243,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (c0 + i < p.Co) o[(((size_t)n * p.Co + c0 + i) * p.H + h) * p.W + w] = f[i];
+                            if (c0 + i < p.Co) o[(((size_t)n * p.Co + c0 + i) * p.Ho + oh) * p.Wo + ow] = f[i];
                     } else {
+                        const size_t eoff = pix * p.out_cs + p.co_base + c0;
                         if (p.residual) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.out_cs + c0);
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + eoff);
                             const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
                             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -232,7 +262,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                             uint32_t wv[8];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) wv[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
-                            st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_cs + c0, wv);
+                            st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + eoff, wv);
                             if (p.stats) {                       // statistics of the values as stored (bf16-rounded)
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
@@ -244,7 +274,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                             uint32_t wv[16];
 #pragma unroll
                             for (int i = 0; i < 16; ++i) wv[i] = __float_as_uint(f[i]);
-                            float* o = reinterpret_cast<float*>(p.out) + pix * p.out_cs + c0;
+                            float* o = reinterpret_cast<float*>(p.out) + eoff;
                             st_global_256(o, wv);
                             st_global_256(o + 8, wv + 8);
                         }
@@ -255,9 +285,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 16; ++i) fq[i] = f[i] * f[i];
                     const float cs = warp_colsum16(f, lane), cq = warp_colsum16(fq, lane);
-                    if (!(lane & 1)) {
-                        atomicAdd(stat_s + c0 + ((lane >> 1) & 15), cs);
-                        atomicAdd(stat_s + p.Co_pad + c0 + ((lane >> 1) & 15), cq);
+                    if (!(lane & 1)) {                            // one owner lane per (warp, channel): no atomics, fixed order
+                        my_stat[c0 + ((lane >> 1) & 15)] += cs;
+                        my_stat[p.Co_pad + c0 + ((lane >> 1) & 15)] += cq;
                     }
                 }
             }
@@ -265,12 +295,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
         }
-        if (p.stats) {                                   // CTA totals -> global, one atomic per channel and CTA
+        if (p.stats) {                                   // warps in order -> CTA totals -> CTAs in order (fv_reduce.cuh)
+            const int tid = threadIdx.x - 64, n2 = 2 * p.Co_pad;
             named_bar_sync(1, 128);
-            for (int c = threadIdx.x - 64; c < 2 * p.Co_pad; c += 128) {
-                const float v = stat_s[c];
-                if (v != 0.f) atomicAdd(p.stats + (c < p.Co_pad ? c : p.stats_c + c - p.Co_pad), v);
-            }
+            for (int c = tid; c < n2; c += 128) stat_blk[c] = ((stat_w[c] + stat_w[n2 + c]) + stat_w[2 * n2 + c]) + stat_w[3 * n2 + c];
+            named_bar_sync(1, 128);
+            if (det_reduce<float>(p.red_ws, n2, gridDim.x, blockIdx.x, stat_blk, stat_tot, tid, 128, NamedSync{1, 128}, red_flag))
+                for (int c = tid; c < n2; c += 128) p.stats[(c < p.Co_pad ? c : p.stats_c + c - p.Co_pad) + p.co_base] = stat_tot[c];
         }
     }
 
@@ -303,13 +334,16 @@ static int pick_tile(int N, int H, int W, int& tw, int& th, int& tn) {
     return 0;
 }
 
-static int env_int(const char* name, int dflt);
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
 
 // Fused statistics cost the epilogue ~250 cycles per 16 output channels and tile (a transposing shuffle butterfly +
-// shared-memory atomics); they are fused only where the tile's MMAs hide that (measured: ring kernel with 64 channels +70 %,
+// shared-memory adds); they are fused only where the tile's MMAs hide that (measured: ring kernel with 64 channels +70 %,
 // enc.2-like N = 128 / K = 576 tiles +75 %, while 32-channel ring tiles and the K >= 1152 layers hide it).
-static bool igemm_fuses_stats(int Ci, int Nc, int R, int S) {
-    const long long mma_cycles = (long long)R * S * (Ci / 16) * (Nc / 2 > 32 + Nc / 4 ? Nc / 2 : 32 + Nc / 4);
+static bool igemm_fuses_stats(int Ci, int Nc, int taps) {
+    const long long mma_cycles = (long long)taps * (Ci / 16) * (Nc / 2 > 32 + Nc / 4 ? Nc / 2 : 32 + Nc / 4);
     return 10 * mma_cycles >= 34LL * (Nc / 16) * 250 && env_int("FV_CONV_FUSE_STATS", 1);
 }
 static int igemm_co_parts(int num_tiles, int Co_pad, int out_mode) {
@@ -324,12 +358,8 @@ static bool ring_fuses_stats(int out_mode, int Co_pad) { return out_mode == FV_O
 // fv_conv_ring.cu: sliding-window schedule for thin full-resolution layers; -1 when not eligible
 int conv2d_ring_eligible(int out_mode, int H, int W, int Ci, int Co_pad, int R, int S, bool residual);
 int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
-                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, cudaStream_t stream);
+                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, void* red_ws, cudaStream_t stream);
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
 }  // namespace fv
 
 // 1 when fv_conv2d_stats produces the statistics inside the convolution's epilogue for this shape, 0 when it runs a separate
@@ -343,7 +373,18 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d_fuses_stats(int 
     int tw = 0, th = 0, tn = 0;
     if (pick_tile(N, H, W, tw, th, tn)) return 0;
     const int num_tiles = (W / tw) * (H / th) * ((N + tn - 1) / tn);
-    return igemm_fuses_stats(Ci, Co_pad / igemm_co_parts(num_tiles, Co_pad, out_mode), R, S) ? 1 : 0;
+    return igemm_fuses_stats(Ci, Co_pad / igemm_co_parts(num_tiles, Co_pad, out_mode), R * S) ? 1 : 0;
+}
+// the same question for the x2 (kind 1) / s2 (kind 2) geometries; H, W = the coarse tiling grid
+extern "C" __attribute__((visibility("default"))) int fv_conv2d_geom_fuses_stats(int kind, int out_mode, int N, int H, int W, int Ci, int Co_pad) {
+    using namespace fv;
+    if (out_mode == FV_OUT_NCHW_F32 || (kind != CONV_X2 && kind != CONV_S2)) return 0;
+    if (Co_pad > 256) return 1;
+    int tw = 0, th = 0, tn = 0;
+    if (pick_tile(N, H, W, tw, th, tn)) return 0;
+    const int nph = kind == CONV_X2 ? 4 : 1;
+    const int num_tiles = (W / tw) * (H / th) * ((N + tn - 1) / tn);
+    return igemm_fuses_stats(Ci, Co_pad / igemm_co_parts(num_tiles * nph, Co_pad, out_mode), kind == CONV_X2 ? 4 : 16) ? 1 : 0;
 }
 namespace fv {
 
@@ -359,73 +400,57 @@ static int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const Con
     return FV_OK;
 }
 
-}  // namespace fv
+struct ConvCall {
+    int kind;                       // CONV_SAME / CONV_X2 / CONV_S2
+    const void* x; const void* w; const float* bias; const void* residual; void* y;
+    int out_mode, N, H, W;          // H, W: the tiling grid (X2 / S2: coarse resolution)
+    int Ci, Co, Co_pad, R, S, pad;
+    float* stats; void* red_ws; void* stream;
+};
 
-static int conv2d_chunk(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W,
-                        int Ci, int Co, int Co_pad, int out_cs, int R, int S, int pad, float* stats, void* stream);
-static int conv2d_any(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W, int Ci,
-                      int Co, int Co_pad, int R, int S, int pad, float* stats, void* stream);
+static int conv_chunk(const ConvCall& c, int co_base, int Co_chunk, int Co_real);
 
 // Output channels beyond one UMMA N (256) are produced in chunks of <= 256: each chunk is an independent GEMM on a row
 // slice of the K-major filter matrix, written at its channel offset of the NHWC output (channel stride = Co_pad).
-extern "C" __attribute__((visibility("default"))) int fv_conv2d(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode,
-                         int N, int H, int W, int Ci, int Co, int Co_pad, int R, int S, int pad, void* stream) {
-    return conv2d_any(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, nullptr, stream);
-}
-
-// The same with the batch-norm statistics of the output fused into the epilogue: stats[0..Co_pad) += sum_pixels y,
-// stats[Co_pad..2 Co_pad) += sum_pixels y^2 of the values as stored (caller-zeroed; NHWC outputs only).
-extern "C" __attribute__((visibility("default"))) int fv_conv2d_stats(const void* x, const void* w, const float* bias, const void* residual, void* y,
-                               int out_mode, int N, int H, int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats,
-                               void* stream) {
-    if (!stats) return fv::fail(fv::FV_ERR_ARG, "fv_conv2d_stats: null stats pointer");
-    if (out_mode == FV_OUT_NCHW_F32) return fv::fail(fv::FV_ERR_UNSUPPORTED, "fv_conv2d_stats: NHWC outputs only");
-    return conv2d_any(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, stats, stream);
-}
-
-static int conv2d_any(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W, int Ci,
-                      int Co, int Co_pad, int R, int S, int pad, float* stats, void* stream) {
-    using namespace fv;
-    if (Co_pad <= 256) return conv2d_chunk(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, Co_pad, R, S, pad, stats, stream);
-    if (Co_pad % 64 || out_mode == FV_OUT_NCHW_F32)
-        return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: Co_pad=%d > 256 must be a multiple of 64 with an NHWC output", Co_pad);
-    if (!x || !w || !y) return fail(FV_ERR_ARG, "fv_conv2d: null pointer");
-    const size_t esz = out_mode == FV_OUT_NHWC_BF16 ? 2 : 4;
-    for (int c0 = 0; c0 < Co_pad; c0 += 256) {
-        const int cn = Co_pad - c0 < 256 ? Co_pad - c0 : 256;
-        const int co_real = Co - c0 < cn ? (Co - c0 > 0 ? Co - c0 : 1) : cn;
-        const int e = conv2d_chunk(x, static_cast<const char*>(w) + (size_t)c0 * R * S * Ci * 2, bias ? bias + c0 : nullptr,
-                                   residual ? static_cast<const char*>(residual) + (size_t)c0 * 2 : nullptr,
-                                   static_cast<char*>(y) + (size_t)c0 * esz, out_mode, N, H, W, Ci, co_real, cn, Co_pad, R, S, pad,
-                                   stats ? stats + c0 : nullptr, stream);
-        if (e) return e;
+static int conv_any(const ConvCall& c) {
+    if (!c.x || !c.w || !c.y) return fail(FV_ERR_ARG, "fv_conv2d: null pointer");
+    if (c.stats && !c.red_ws) return fail(FV_ERR_ARG, "fv_conv2d: statistics need the reduction workspace (fv_reduce_ws_bytes)");
+    if (c.Co_pad <= 256) return conv_chunk(c, 0, c.Co_pad, c.Co);
+    if (c.Co_pad % 64 || c.out_mode == FV_OUT_NCHW_F32)
+        return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: Co_pad=%d > 256 must be a multiple of 64 with an NHWC output", c.Co_pad);
+    for (int c0 = 0; c0 < c.Co_pad; c0 += 256) {
+        const int cn = c.Co_pad - c0 < 256 ? c.Co_pad - c0 : 256;
+        const int co_real = c.Co - c0 < cn ? (c.Co - c0 > 0 ? c.Co - c0 : 1) : cn;
+        if (int e = conv_chunk(c, c0, cn, co_real)) return e;
     }
     return FV_OK;
 }
 
-static int conv2d_chunk(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W,
-                        int Ci, int Co, int Co_pad, int out_cs, int R, int S, int pad, float* stats, void* stream) {
-    using namespace fv;
-    if (!x || !w || !y) return fail(FV_ERR_ARG, "fv_conv2d: null pointer");
+static int conv_chunk(const ConvCall& c, int co_base, int Co_pad, int Co) {
+    const int N = c.N, H = c.H, W = c.W, Ci = c.Ci, R = c.R, S = c.S, pad = c.pad, out_mode = c.out_mode, out_cs = c.Co_pad;
     if (N < 1 || H < 1 || W < 1) return fail(FV_ERR_ARG, "fv_conv2d: bad shape N=%d H=%d W=%d", N, H, W);
     if (Ci % 16 || Ci < 16 || (Ci > 64 && Ci % 64) || (Ci < 64 && Ci != 16 && Ci != 32))
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: Ci=%d must be 16, 32 or a multiple of 64 (pad the channels)", Ci);
     if (Co_pad % 16 || Co_pad < 16 || Co_pad > 256 || Co < 1 || Co > Co_pad)
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: Co=%d Co_pad=%d (Co_pad must be a multiple of 16 in [16,256])", Co, Co_pad);
-    if (R != S || (R != 1 && R != 3 && R != 5 && R != 7) || pad != (R - 1) / 2)
+    if (c.kind == CONV_SAME && (R != S || (R != 1 && R != 3 && R != 5 && R != 7) || pad != (R - 1) / 2))
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: only odd square filters with same padding (R=%d S=%d pad=%d)", R, S, pad);
     if (out_mode < 0 || out_mode > 2) return fail(FV_ERR_ARG, "fv_conv2d: out_mode %d", out_mode);
-    if (out_mode == FV_OUT_NCHW_F32 && residual) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: residual needs an NHWC output");
+    if (out_mode == FV_OUT_NCHW_F32 && c.residual) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: residual needs an NHWC output");
+    float* stats = c.stats;
+    cudaStream_t s = (cudaStream_t)c.stream;
+    const int osy = c.kind == CONV_X2 ? 2 : 1, Ho = H * osy, Wo = W * osy;
     // statistics: fused into the epilogue where that is hidden (see igemm_fuses_stats), a separate fv_bn_stats pass otherwise
     const int y_dtype = out_mode == FV_OUT_NHWC_BF16 ? FV_DT_BF16 : FV_DT_F32;
-    if (out_cs == Co_pad) {
+    if (c.kind == CONV_SAME && out_cs == Co_pad) {
         float* ring_stats = (stats && ring_fuses_stats(out_mode, Co_pad)) ? stats : nullptr;
-        const int rr = conv2d_ring_try(x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, ring_stats, out_cs, (cudaStream_t)stream);
+        const int rr = conv2d_ring_try(c.x, c.w, c.bias, c.residual, c.y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, ring_stats, out_cs, c.red_ws, s);
         if (rr > 0) return rr;
-        if (rr == 0) return (stats && !ring_stats) ? fv_bn_stats(y, y_dtype, stats, (long long)N * H * W, Co_pad, stream) : FV_OK;
+        if (rr == 0) return (stats && !ring_stats) ? fv_bn_stats(c.y, y_dtype, stats, (long long)N * H * W, Co_pad, c.red_ws, c.stream) : FV_OK;
     }
     ConvParams p{};
-    p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.Co_pad = Co_pad; p.R = R; p.S = S; p.pad = pad;
+    p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.Co_pad = Co_pad;
+    p.Ho = Ho; p.Wo = Wo; p.osy = osy; p.osx = osy;
     if (pick_tile(N, H, W, p.tw, p.th, p.tn))
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: H=%d W=%d not tileable (W multiple of 128, or W,H powers of two)", H, W);
     p.tiles_w = W / p.tw; p.tiles_h = H / p.th; p.tiles_n = (N + p.tn - 1) / p.tn;
@@ -433,22 +458,50 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
     const int KB = Ci >= 64 ? 64 : Ci;
     const int row_bytes = KB * 2;
     p.kc_blocks = Ci / KB;
-    // slab schedule: one activation box per filter row, taps = shifted descriptor views (row-segment tiles only)
+    p.nph = c.kind == CONV_X2 ? 4 : 1;
     // fewer pixel tiles than half the SMs (the 16x16 ResBlock2D layers: 64 tiles): split the output channels over 2-4 CTAs
     // per tile -- each streams only its slice of the filter, and twice / four times as many SMs work
-    p.co_parts = igemm_co_parts(p.num_tiles, Co_pad, out_mode);
+    p.co_parts = igemm_co_parts(p.num_tiles * p.nph, Co_pad, out_mode);
     p.Nc = Co_pad / p.co_parts;
-    p.num_vtiles = p.num_tiles * p.co_parts;
+    p.num_vtiles = p.num_tiles * p.co_parts * p.nph;
     p.b_slice_stride = (p.Nc * row_bytes + 1023) & ~1023;
-    p.slab = (S > 1 && p.th == 1 && p.tn == 1) ? env_int("FV_CONV_SLAB", 1) : 0;
+    // slab schedule: one activation box per filter row, taps = shifted descriptor views (row-segment tiles of SAME convs only)
+    int slab = (c.kind == CONV_SAME && S > 1 && p.th == 1 && p.tn == 1) ? env_int("FV_CONV_SLAB", 1) : 0;
     // a slab stage carries S filter slices: with 256 output channels and a 128-byte K block it no longer fits twice -> tap schedule
-    if (p.slab && 2 * ((((p.tw + S - 1) * row_bytes + 1023) & ~1023) + p.b_slice_stride * S) > 200 * 1024) p.slab = 0;
-    const int a_rows = p.slab ? p.tw + S - 1 : 128;
-    const int b_slices = p.slab ? S : 1;
+    if (slab && 2 * ((((p.tw + S - 1) * row_bytes + 1023) & ~1023) + p.b_slice_stride * S) > 200 * 1024) slab = 0;
+    int taps = R * S;
+    if (c.kind == CONV_X2) taps = 4;
+    if (c.kind == CONV_S2) taps = 16;
+    p.nsub = slab ? S : 1;
+    p.groups = slab ? R : taps;
+    if (p.nph * p.groups > 64) return fail(FV_ERR_INTERNAL, "fv_conv2d: tap table overflow");
+    for (int ph = 0; ph < p.nph; ++ph) {
+        const int a = ph >> 1, b = ph & 1;
+        p.oy[ph] = (signed char)(c.kind == CONV_X2 ? a : 0);
+        p.ox[ph] = (signed char)(c.kind == CONV_X2 ? b : 0);
+        for (int g = 0; g < p.groups; ++g) {
+            short4 t = make_short4(0, 0, 0, 0);
+            if (c.kind == CONV_SAME) {
+                const int r = slab ? g : g / S, sx = slab ? 0 : g % S;
+                t.y = (short)(sx - pad); t.w = (short)(r - pad);
+            } else if (c.kind == CONV_X2) {        // phase (a, b), tap (u, v): coarse pixel (i + u - 1 + a, j + v - 1 + b)
+                const int u = g >> 1, v = g & 1;
+                t.y = (short)(v - 1 + b); t.w = (short)(u - 1 + a);
+            } else {                               // S2 tap (r4, s4): fine pixel (2i + r4 - 1, 2j + s4 - 1) = parity + coarse offset
+                const int r4 = g >> 2, s4 = g & 3;
+                const int fr = r4 - 1, fc = s4 - 1;
+                const int dh = fr < 0 ? -1 : fr / 2, dw = fc < 0 ? -1 : fc / 2;
+                t.w = (short)dh; t.z = (short)(fr - 2 * dh);
+                t.y = (short)dw; t.x = (short)((fc - 2 * dw) * Ci);
+            }
+            p.tap[ph * p.groups + g] = t;
+        }
+    }
+    const int a_rows = slab ? p.tw + S - 1 : 128;
     p.a_off_b = (a_rows * row_bytes + 1023) & ~1023;
-    p.stage_stride = p.a_off_b + p.b_slice_stride * b_slices;
-    p.tx_bytes = a_rows * row_bytes + b_slices * p.Nc * row_bytes;
-    const int groups = R * (p.slab ? 1 : S) * p.kc_blocks;
+    p.stage_stride = p.a_off_b + p.b_slice_stride * p.nsub;
+    p.tx_bytes = a_rows * row_bytes + p.nsub * p.Nc * row_bytes;
+    const int groups = p.groups * p.kc_blocks;
     int stages = (196 * 1024) / p.stage_stride;
     if (stages > 8) stages = 8;
     if (stages > groups) stages = groups;
@@ -461,30 +514,74 @@ static int conv2d_chunk(const void* x, const void* w, const float* bias, const v
     while (cols < 2 * p.Nc) cols <<= 1;
     p.tmem_cols = cols;
     p.out_cs = out_cs;
-    p.bias = bias;
-    p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
-    p.out = y;
-    const bool fuse_stats = stats && (out_cs != Co_pad || igemm_fuses_stats(Ci, p.Nc, R, S));
+    p.co_base = co_base;
+    p.w_rows_per_phase = out_cs;
+    p.bias = c.bias ? c.bias + co_base : nullptr;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(c.residual);
+    p.out = c.y;
+    const bool fuse_stats = stats && (out_cs != Co_pad || igemm_fuses_stats(Ci, p.Nc, taps));
     p.stats = fuse_stats ? stats : nullptr;
     p.stats_c = out_cs;                          // the statistic block is [2][total Co_pad] also when Co is walked in chunks
+    p.red_ws = c.red_ws;
 
     CUtensorMap tmX, tmW;
     {
-        uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[3] = {(uint64_t)Ci * 2, (uint64_t)W * Ci * 2, (uint64_t)H * W * Ci * 2};
-        uint32_t box[4] = {(uint32_t)KB, (uint32_t)(p.slab ? p.tw + S - 1 : p.tw), (uint32_t)p.th, (uint32_t)p.tn};
-        if (int e = encode_tmap_bf16(&tmX, x, 4, dims, str, box, row_bytes)) return e;
+        // (channels, W, row parity, H, N): SAME / X2 read the tensor as it is (parity dimension of extent 1); S2 reads the fine
+        // tensor [N, 2H, 2W, Ci] as (2 Ci, W, 2, H, N) -- column parity folded into the channel coordinate
+        const uint64_t fw = c.kind == CONV_S2 ? 2 : 1;
+        uint64_t dims[5] = {(uint64_t)Ci * fw, (uint64_t)W, fw, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {(uint64_t)Ci * fw * 2, (uint64_t)W * fw * Ci * 2, (uint64_t)W * fw * Ci * 2 * fw, (uint64_t)H * fw * W * fw * Ci * 2};
+        uint32_t box[5] = {(uint32_t)KB, (uint32_t)(slab ? p.tw + S - 1 : p.tw), 1, (uint32_t)p.th, (uint32_t)p.tn};
+        if (int e = encode_tmap_bf16(&tmX, c.x, 5, dims, str, box, row_bytes)) return e;
     }
     {
-        uint64_t dims[2] = {(uint64_t)R * S * Ci, (uint64_t)Co_pad};
-        uint64_t str[1] = {(uint64_t)R * S * Ci * 2};
+        uint64_t dims[2] = {(uint64_t)taps * Ci, (uint64_t)out_cs * p.nph};
+        uint64_t str[1] = {(uint64_t)taps * Ci * 2};
         uint32_t box[2] = {(uint32_t)KB, (uint32_t)p.Nc};
-        if (int e = encode_tmap_bf16(&tmW, w, 2, dims, str, box, row_bytes)) return e;
+        if (int e = encode_tmap_bf16(&tmW, c.w, 2, dims, str, box, row_bytes)) return e;
     }
-    const size_t smem = (size_t)p.stages * p.stage_stride + 1024 + 256 + (size_t)Co_pad * 12 + 64;
+    const size_t smem = (size_t)p.stages * p.stage_stride + 1024 + 256 + (size_t)Co_pad * 52 + 64;
     const int grid = p.num_vtiles < num_sms() ? p.num_vtiles : num_sms();
-    cudaStream_t s = (cudaStream_t)stream;
     const int e = KB == 64 ? launch_conv<64>(tmX, tmW, p, smem, grid, s) : (KB == 32 ? launch_conv<32>(tmX, tmW, p, smem, grid, s) : launch_conv<16>(tmX, tmW, p, smem, grid, s));
     if (e || !stats || fuse_stats) return e;
-    return fv_bn_stats(y, y_dtype, stats, (long long)N * H * W, Co_pad, stream);
+    return fv_bn_stats(c.y, y_dtype, stats, (long long)N * Ho * Wo, Co_pad, c.red_ws, c.stream);
+}
+
+}  // namespace fv
+
+using namespace fv;
+
+extern "C" __attribute__((visibility("default"))) int fv_conv2d(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode,
+                         int N, int H, int W, int Ci, int Co, int Co_pad, int R, int S, int pad, void* stream) {
+    ConvCall c{CONV_SAME, x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, nullptr, nullptr, stream};
+    return conv_any(c);
+}
+
+// The same with the batch-norm statistics of the output fused into the epilogue: stats[0..Co_pad) = sum_pixels y,
+// stats[Co_pad..2 Co_pad) = sum_pixels y^2 of the values as stored (written, not accumulated; NHWC outputs only).
+extern "C" __attribute__((visibility("default"))) int fv_conv2d_stats(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                               int out_mode, int N, int H, int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats,
+                               void* red_ws, void* stream) {
+    if (!stats) return fail(FV_ERR_ARG, "fv_conv2d_stats: null stats pointer");
+    if (out_mode == FV_OUT_NCHW_F32) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_stats: NHWC outputs only");
+    ConvCall c{CONV_SAME, x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, stats, red_ws, stream};
+    return conv_any(c);
+}
+
+// x [N,H,W,Ci] -> y [N,2H,2W,Co_pad]: nearest 2x up-sampling + 3x3 "same" convolution as four 2x2 phase convolutions on the
+// coarse grid (wp = [4][Co_pad][4*Ci] from fv_weight_prep_up), or the data gradient of a 4x4 stride-2 convolution.
+extern "C" __attribute__((visibility("default"))) int fv_conv2d_x2(const void* x, const void* wp, const float* bias, void* y, int out_mode, int N, int H, int W,
+                                                                 int Ci, int Co, int Co_pad, float* stats, void* red_ws, void* stream) {
+    if (stats && out_mode == FV_OUT_NCHW_F32) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_x2: statistics need an NHWC output");
+    ConvCall c{CONV_X2, x, wp, bias, nullptr, y, out_mode, N, H, W, Ci, Co, Co_pad, 2, 2, 0, stats, red_ws, stream};
+    return conv_any(c);
+}
+
+// x [N,2H,2W,Ci] -> y [N,H,W,Co_pad]: 4x4 stride-2 pad-1 convolution (w = [Co_pad][16*Ci], taps row-major), or -- with the
+// summed, mirrored taps of fv_weight_prep_up -- the data gradient of fv_conv2d_x2 (up-sampling backward folded in).
+extern "C" __attribute__((visibility("default"))) int fv_conv2d_s2(const void* x, const void* w, const float* bias, void* y, int out_mode, int N, int H, int W,
+                                                                 int Ci, int Co, int Co_pad, float* stats, void* red_ws, void* stream) {
+    if (stats && out_mode == FV_OUT_NCHW_F32) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_s2: statistics need an NHWC output");
+    ConvCall c{CONV_S2, x, w, bias, nullptr, y, out_mode, N, H, W, Ci, Co, Co_pad, 4, 4, 1, stats, red_ws, stream};
+    return conv_any(c);
 }

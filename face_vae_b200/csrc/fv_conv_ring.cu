@@ -18,6 +18,7 @@
 #include "../../include/facevae_b200.h"
 #include "fv_host.h"
 #include "fv_ptx.cuh"
+#include "fv_reduce.cuh"
 
 namespace fv {
 
@@ -33,6 +34,7 @@ struct RingParams {
     void* out;
     float* stats;                         // optional [2][stats_c]: per-channel sum and sum of squares of the stored output
     int stats_c;
+    void* red_ws;                         // fv_reduce.cuh workspace (with stats)
     long long* trace;
 };
 
@@ -56,7 +58,11 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint64_t* tfull = wbar + 1;                                           // [2]
     uint64_t* tempty = tfull + 2;                                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    int* red_flag = reinterpret_cast<int*>(tmem_slot + 2);
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);              // [Co_pad]
+    float* stat_w = bias_s + p.Co_pad;                                    // [4 epilogue warps][2][Co_pad] (when p.stats)
+    float* stat_blk = stat_w + 8 * p.Co_pad;                              // [2][Co_pad] CTA totals
+    float* stat_tot = stat_blk + 2 * p.Co_pad;                            // [2][Co_pad] grid totals (last CTA)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef FV_TRACE
@@ -304,13 +310,21 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (++h == p.H) { h = 0; ++col; }
         }
         if (use_tma_store && warp == 2 && lane == 0) tma_store_wait_all<0>();
-        if (p.stats && use_tma_store && !(lane & 1)) {
+        if (p.stats && use_tma_store) {            // lanes -> warp slots -> warps in order -> CTAs in order (fv_reduce.cuh): reproducible
+            const int tid = threadIdx.x - 64, n2 = 2 * p.Co_pad;
+            if (!(lane & 1)) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (c < (p.Co_pad >> 4)) {
-                    atomicAdd(p.stats + c * 16 + ((lane >> 1) & 15), st_s[c]);
-                    atomicAdd(p.stats + p.stats_c + c * 16 + ((lane >> 1) & 15), st_q[c]);
-                }
+                for (int c = 0; c < 4; ++c)
+                    if (c < (p.Co_pad >> 4)) {
+                        stat_w[q * n2 + c * 16 + ((lane >> 1) & 15)] = st_s[c];
+                        stat_w[q * n2 + p.Co_pad + c * 16 + ((lane >> 1) & 15)] = st_q[c];
+                    }
+            }
+            named_bar_sync(EPI_BAR, 128);
+            for (int c = tid; c < n2; c += 128) stat_blk[c] = ((stat_w[c] + stat_w[n2 + c]) + stat_w[2 * n2 + c]) + stat_w[3 * n2 + c];
+            named_bar_sync(EPI_BAR, 128);
+            if (det_reduce<float>(p.red_ws, n2, gridDim.x, blockIdx.x, stat_blk, stat_tot, tid, 128, NamedSync{EPI_BAR, 128}, red_flag))
+                for (int c = tid; c < n2; c += 128) p.stats[c < p.Co_pad ? c : p.stats_c + c - p.Co_pad] = stat_tot[c];
         }
     }
 
@@ -345,13 +359,13 @@ int conv2d_ring_eligible(int out_mode, int H, int W, int Ci, int Co_pad, int R, 
     const int slab_stride = ((128 + S - 1) * row_bytes + 1023) & ~1023;
     int off = (R + 3) * slab_stride + R * S * ((Co_pad * row_bytes + 1023) & ~1023);
     if (out_mode == FV_OUT_NHWC_BF16 && Co_pad <= 64) off += 2 * ((128 * Co_pad * 2 + 1023) & ~1023);
-    const size_t smem = (size_t)off + (2 * (R + 3) + 8) * 8 + 16 + (size_t)Co_pad * 4 + 1024 + 64;
+    const size_t smem = (size_t)off + (2 * (R + 3) + 8) * 8 + 16 + (size_t)Co_pad * 52 + 1024 + 64;
     (void)H;
     return smem <= 225 * 1024 ? 1 : 0;
 }
 
 int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
-                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, cudaStream_t stream) {
+                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, void* red_ws, cudaStream_t stream) {
     if ((S != 3 && S != 5 && S != 7) || W % 128 || Ci > 64 || residual) return -1;
     if (stats && !(out_mode == FV_OUT_NHWC_BF16 && Co_pad <= 64)) return -1;      // fused statistics: staged-store epilogue only
     const char* env = getenv("FV_CONV_RING");
@@ -374,7 +388,7 @@ int conv2d_ring_try(const void* x, const void* w, const float* bias, const void*
     p.stage_stride = tma_store ? ((128 * Co_pad * 2 + 1023) & ~1023) : 0;
     off += 2 * p.stage_stride;
     p.bar_off = off;
-    const size_t smem = (size_t)off + (2 * p.ring + 8) * 8 + 16 + (size_t)Co_pad * 4 + 1024 + 64;
+    const size_t smem = (size_t)off + (2 * p.ring + 8) * 8 + 16 + (size_t)Co_pad * 52 + 1024 + 64;
     if (smem > 225 * 1024) return -1;
     int cols = 32;
     while (cols < 2 * Co_pad) cols <<= 1;
@@ -384,6 +398,7 @@ int conv2d_ring_try(const void* x, const void* w, const float* bias, const void*
     p.out = y;
     p.stats = stats;
     p.stats_c = stats_c;
+    p.red_ws = red_ws;
     p.trace = trace_ptr();
     const int sms = num_sms();
     p.tiles_per_cta = (p.num_tiles + sms - 1) / sms;

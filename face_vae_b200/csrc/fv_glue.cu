@@ -8,6 +8,7 @@
 #include "../../include/facevae_b200.h"
 #include "fv_host.h"
 #include "fv_ptx.cuh"
+#include "fv_reduce.cuh"
 
 namespace fv {
 
@@ -146,50 +147,200 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, __nv_bfloat16* _
     }
 }
 
-// the same for a table of layers (blockIdx.y = layer): one launch per step instead of one per convolution
+// the same for a table of layers (blockIdx.y = layer): one launch per step instead of one per convolution.  kind 0: plain
+// convolution (wf | wd), 1: up-sampling 3x3 convolution (wx2 | ws2, weight_prep_up_kernel), 2: 4x4 stride-2 convolution
+// (wf | wx2, weight_prep_s2_kernel).
+__device__ __forceinline__ void up_rows(int a, int u, int& r0, int& r1);
+__device__ __forceinline__ float up_tap_sum(const float* __restrict__ w9, int a, int u, int b, int v) {
+    int r0, r1, s0, s1;
+    up_rows(a, u, r0, r1);
+    up_rows(b, v, s0, s1);
+    float acc = 0.f;
+    for (int r = r0; r <= r1; ++r)
+        for (int s_ = s0; s_ <= s1; ++s_) acc += __ldg(w9 + r * 3 + s_);
+    return acc;
+}
 __global__ void weight_prep_batched_kernel(const fv_prep_desc* __restrict__ table) {
     const fv_prep_desc d = table[blockIdx.y];
     const float* __restrict__ w = d.w;
-    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(d.wf);
-    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(d.wd);
-    const unsigned taps = d.R * d.S, cip = d.Ci_pad, cop = d.Co_pad;
+    __nv_bfloat16* o0 = static_cast<__nv_bfloat16*>(d.wf);
+    __nv_bfloat16* o1 = static_cast<__nv_bfloat16*>(d.wd);
+    const unsigned taps = d.kind == 0 ? d.R * d.S : 16, cip = d.Ci_pad, cop = d.Co_pad;
     const unsigned nf = cop * taps * cip;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) {
-        if (wf) {
-            const unsigned ci = i % cip, t2 = i / cip;
-            const unsigned tap = t2 % taps, co = t2 / taps;
-            const float v = (co < (unsigned)d.Co && ci < (unsigned)d.Ci) ? __ldg(w + (co * d.Ci + ci) * taps + tap) : 0.f;
-            wf[i] = __float2bfloat16(v);
-        }
-        if (wd) {
-            const unsigned co = i % cop, t2 = i / cop;
-            const unsigned tap = t2 % taps, ci = t2 / taps;
-            const float v = (co < (unsigned)d.Co && ci < (unsigned)d.Ci) ? __ldg(w + (co * d.Ci + ci) * taps + (taps - 1 - tap)) : 0.f;
-            wd[i] = __float2bfloat16(v);
+        if (d.kind == 0) {
+            if (o0) {
+                const unsigned ci = i % cip, t2 = i / cip;
+                const unsigned tap = t2 % taps, co = t2 / taps;
+                const float v = (co < (unsigned)d.Co && ci < (unsigned)d.Ci) ? __ldg(w + (co * d.Ci + ci) * taps + tap) : 0.f;
+                o0[i] = __float2bfloat16(v);
+            }
+            if (o1) {
+                const unsigned co = i % cop, t2 = i / cop;
+                const unsigned tap = t2 % taps, ci = t2 / taps;
+                const float v = (co < (unsigned)d.Co && ci < (unsigned)d.Ci) ? __ldg(w + (co * d.Ci + ci) * taps + (taps - 1 - tap)) : 0.f;
+                o1[i] = __float2bfloat16(v);
+            }
+        } else if (d.kind == 1) {
+            if (o0) {                                      // wx2 [4 phases][Co_pad][4 taps][Ci_pad]
+                const unsigned ci = i % cip, tap = (i / cip) % 4, co = (i / (4 * cip)) % cop, ph = i / (4 * cip * cop);
+                const float v = (co < (unsigned)d.Co && ci < (unsigned)d.Ci) ? up_tap_sum(w + (co * d.Ci + ci) * 9, ph >> 1, tap >> 1, ph & 1, tap & 1) : 0.f;
+                o0[i] = __float2bfloat16(v);
+            }
+            if (o1) {                                      // ws2 [Ci_pad][16 taps][Co_pad]
+                const unsigned co = i % cop, t16 = (i / cop) % 16, ci = i / (16 * cop);
+                const unsigned r4 = t16 >> 2, s4 = t16 & 3;
+                const float v = (co < (unsigned)d.Co && ci < (unsigned)d.Ci)
+                                    ? up_tap_sum(w + (co * d.Ci + ci) * 9, (r4 & 1) ? 0 : 1, r4 < 2 ? 1 : 0, (s4 & 1) ? 0 : 1, s4 < 2 ? 1 : 0) : 0.f;
+                o1[i] = __float2bfloat16(v);
+            }
+        } else {
+            if (o0) {                                      // wf [Co_pad][16][Ci_pad]
+                const unsigned ci = i % cip, tap = (i / cip) % 16, co = i / (16 * cip);
+                o0[i] = __float2bfloat16((co < (unsigned)d.Co && ci < (unsigned)d.Ci) ? __ldg(w + (co * d.Ci + ci) * 16 + tap) : 0.f);
+            }
+            if (o1) {                                      // wx2 [4 phases][Ci_pad][4 taps][Co_pad]
+                const unsigned co = i % cop, tap = (i / cop) % 4, ci = (i / (4 * cop)) % cip, ph = i / (4 * cop * cip);
+                const unsigned r4 = 3 - 2 * (tap >> 1) - (ph >> 1), s4 = 3 - 2 * (tap & 1) - (ph & 1);
+                o1[i] = __float2bfloat16((co < (unsigned)d.Co && ci < (unsigned)d.Ci) ? __ldg(w + (co * d.Ci + ci) * 16 + r4 * 4 + s4) : 0.f);
+            }
         }
     }
 }
 
-// dWacc fp32 [Co_pad][taps][Ci_pad] -> grad fp32 [Co][Ci][R][S]
-__global__ void wgrad_finish_kernel(const float* __restrict__ acc, float* __restrict__ grad, int Co, int Ci, int taps,
-                                    int Ci_pad, int accumulate) {
+// dW partials fp32 [splits][Co_pad][taps][Ci_pad] (one slab per pixel split of the weight-gradient kernels, plain stores) ->
+// grad fp32 [Co][Ci][R][S]: the splits are added in split order (reproducible; replaces red.global.add into one buffer).
+__global__ void wgrad_finish_kernel(const float* __restrict__ part, float* __restrict__ grad, int Co, int Ci, int taps,
+                                    int Ci_pad, int accumulate, int splits, long long split_stride) {
     const long long total = (long long)Co * Ci * taps;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int tap = (int)(i % taps);
         const int ci = (int)((i / taps) % Ci);
         const int co = (int)(i / ((long long)taps * Ci));
-        const float v = acc[((long long)co * taps + tap) * Ci_pad + ci];
+        const float* src = part + ((long long)co * taps + tap) * Ci_pad + ci;
+        float v = 0.f;
+        int sp = 0;
+        for (; sp + 4 <= splits; sp += 4) {                  // four independent loads in flight, added in split order
+            const float a0 = __ldg(src + (sp + 0) * split_stride), a1 = __ldg(src + (sp + 1) * split_stride),
+                        a2 = __ldg(src + (sp + 2) * split_stride), a3 = __ldg(src + (sp + 3) * split_stride);
+            v += a0; v += a1; v += a2; v += a3;
+        }
+        for (; sp < splits; ++sp) v += __ldg(src + sp * split_stride);
         grad[i] = accumulate ? grad[i] + v : v;
     }
 }
 
+// out[i] (+)= sum_s part[s][i] in slab order (the tap-folded out_conv weight gradient writes one slab per CTA)
+__global__ void slab_sum_kernel(const float* __restrict__ part, int slabs, long long stride, float* __restrict__ out, long long n, int accumulate) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        int sp = 0;
+        for (; sp + 4 <= slabs; sp += 4) {
+            const float a0 = __ldg(part + (sp + 0) * stride + i), a1 = __ldg(part + (sp + 1) * stride + i), a2 = __ldg(part + (sp + 2) * stride + i),
+                        a3 = __ldg(part + (sp + 3) * stride + i);
+            v += a0; v += a1; v += a2; v += a3;
+        }
+        for (; sp < slabs; ++sp) v += __ldg(part + sp * stride + i);
+        out[i] = accumulate ? out[i] + v : v;
+    }
+}
+
+// ---- filters of the up-sampling convolution (UpBlock2D: nearest x2 + 3x3, reference modules.py:78-89) ------------------------
+// Output pixel (2i + a, 2j + b) reads the coarse pixels (i + u - 1 + a, j + v - 1 + b), u, v in {0, 1}; the 3x3 taps that land
+// on coarse tap u of phase a are  a = 0: u = 0 <- {r = 0}, u = 1 <- {1, 2};  a = 1: u = 0 <- {0, 1}, u = 1 <- {2}.
+__device__ __forceinline__ void up_rows(int a, int u, int& r0, int& r1) {      // inclusive range of 3x3 rows
+    if (a == 0) { r0 = u == 0 ? 0 : 1; r1 = u == 0 ? 0 : 2; }
+    else        { r0 = u == 0 ? 0 : 2; r1 = u == 0 ? 1 : 2; }
+}
+// w fp32 [Co][Ci][3][3] -> wx2 bf16 [4 phases][Co_pad][4 taps (u, v)][Ci_pad] (forward operand of fv_conv2d_x2: sums of taps in
+// fp32, rounded once) and ws2 bf16 [Ci_pad][16 taps (r4, s4)][Co_pad] (operand of fv_conv2d_s2 for the data gradient: the
+// fine pixel (2i + r4 - 1, 2j + s4 - 1) of dY meets phase a, tap u with r4 = 3 - 2u - a).
+__global__ void weight_prep_up_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wx2, __nv_bfloat16* __restrict__ ws2,
+                                      int Co, int Ci, int Co_pad, int Ci_pad) {
+    const long long n = 16LL * Co_pad * Ci_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (wx2) {
+            const int ci = (int)(i % Ci_pad);
+            const int tap = (int)((i / Ci_pad) % 4);
+            const int co = (int)((i / (4LL * Ci_pad)) % Co_pad);
+            const int ph = (int)(i / (4LL * Ci_pad * Co_pad));
+            wx2[i] = __float2bfloat16((co < Co && ci < Ci) ? up_tap_sum(w + ((long long)co * Ci + ci) * 9, ph >> 1, tap >> 1, ph & 1, tap & 1) : 0.f);
+        }
+        if (ws2) {
+            const int co = (int)(i % Co_pad);
+            const int t16 = (int)((i / Co_pad) % 16);
+            const int ci = (int)(i / (16LL * Co_pad));
+            // r4 = 3 - 2u - a  <=>  (a, u) = (1,1), (0,1), (1,0), (0,0) for r4 = 0..3
+            const int r4 = t16 >> 2, s4 = t16 & 3;
+            ws2[i] = __float2bfloat16((co < Co && ci < Ci)
+                                          ? up_tap_sum(w + ((long long)co * Ci + ci) * 9, (r4 & 1) ? 0 : 1, r4 < 2 ? 1 : 0, (s4 & 1) ? 0 : 1, s4 < 2 ? 1 : 0)
+                                          : 0.f);
+        }
+    }
+}
+
+// partial slabs of fv_conv2d_wgrad_x2 [splits][4 phases][Co_pad][4 taps][Ci_pad] -> grad fp32 [Co][Ci][3][3]:
+// dW[r][s] = sum over the (phase, tap) pairs whose coarse tap contains (r, s); splits added in order inside each term.
+__global__ void wgrad_finish_up_kernel(const float* __restrict__ part, float* __restrict__ grad, int Co, int Ci, int Co_pad, int Ci_pad,
+                                       int accumulate, int splits, long long split_stride) {
+    const long long total = (long long)Co * Ci * 9;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int s_ = (int)(i % 3), r = (int)((i / 3) % 3);
+        const int ci = (int)((i / 9) % Ci);
+        const int co = (int)(i / (9LL * Ci));
+        float v = 0.f;
+        for (int a = 0; a < 2; ++a)
+            for (int u = 0; u < 2; ++u) {
+                int r0, r1;
+                up_rows(a, u, r0, r1);
+                if (r < r0 || r > r1) continue;
+                for (int b = 0; b < 2; ++b)
+                    for (int vv = 0; vv < 2; ++vv) {
+                        int s0, s1;
+                        up_rows(b, vv, s0, s1);
+                        if (s_ < s0 || s_ > s1) continue;
+                        const float* src = part + ((((long long)(a * 2 + b) * Co_pad + co) * 4 + (u * 2 + vv)) * Ci_pad + ci);
+                        float t = 0.f;
+                        for (int sp = 0; sp < splits; ++sp) t += __ldg(src + sp * split_stride);
+                        v += t;
+                    }
+            }
+        grad[i] = accumulate ? grad[i] + v : v;
+    }
+}
+
+// ---- filters of the 4x4 stride-2 convolution (Conv2dELR as used by EFE_conv6, reference models_utils.py:632-744) ---------------
+// w fp32 [Co][Ci][4][4] -> wf bf16 [Co_pad][16][Ci_pad] (fv_conv2d_s2 operand) and wx2 bf16 [4 phases][Ci_pad][4 taps][Co_pad]
+// (fv_conv2d_x2 operand of the data gradient: phase (a, b), tap (u, v) <- filter tap (3 - 2u - a, 3 - 2v - b)).
+__global__ void weight_prep_s2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wx2,
+                                      int Co, int Ci, int Co_pad, int Ci_pad) {
+    const long long n = 16LL * Co_pad * Ci_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (wf) {
+            const int ci = (int)(i % Ci_pad);
+            const int tap = (int)((i / Ci_pad) % 16);
+            const int co = (int)(i / (16LL * Ci_pad));
+            wf[i] = __float2bfloat16((co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * 16 + tap] : 0.f);
+        }
+        if (wx2) {
+            const int co = (int)(i % Co_pad);
+            const int tap = (int)((i / Co_pad) % 4);
+            const int ci = (int)((i / (4LL * Co_pad)) % Ci_pad);
+            const int ph = (int)(i / (4LL * Co_pad * Ci_pad));
+            const int r4 = 3 - 2 * (tap >> 1) - (ph >> 1), s4 = 3 - 2 * (tap & 1) - (ph & 1);
+            wx2[i] = __float2bfloat16((co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * 16 + r4 * 4 + s4] : 0.f);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- batch-norm statistics
-// sums[0..C) += sum_p y[p,c], sums[C..2C) += sum_p y[p,c]^2 over P rows of an NHWC tensor (channel stride C).
+// sums[0..C) = sum_p y[p,c], sums[C..2C) = sum_p y[p,c]^2 over P rows of an NHWC tensor (channel stride C).
 // blockDim = 256; a block covers rows_per_iter = 256 / (C/8) rows per step; cross-row reduction through shared memory,
-// then one atomicAdd per channel per block.
+// then the deterministic cross-block reduction of fv_reduce.cuh (fixed summation order: bitwise reproducible).
 template <typename T>
-__global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sums, long long P, int C) {
-    extern __shared__ float sh[];   // [2][rows_per_iter][C]
+__global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sums, long long P, int C, void* ws) {
+    extern __shared__ float sh[];   // [2][rows_per_iter][C] | block vector [2C] | totals [2C]
+    __shared__ int red_flag;
     const int tpr = C / 8;                       // threads per row
     const int rpi = blockDim.x / tpr;            // rows per iteration
     const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
@@ -227,12 +378,17 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sum
         }
     }
     __syncthreads();
+    float* blk = sh + 2 * rpi * C;
+    float* tot = blk + 2 * C;
     for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
         const int which = c / C, ch = c % C;
         float a = 0.f;
         for (int r = 0; r < rpi; ++r) a += sh[(which * rpi + r) * C + ch];
-        atomicAdd(sums + c, a);
+        blk[c] = a;
     }
+    __syncthreads();
+    if (det_reduce<float>(ws, 2 * C, gridDim.x, blockIdx.x, blk, tot, threadIdx.x, blockDim.x, BlockSync{}, &red_flag))
+        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sums[c] = tot[c];
 }
 
 // mean / invstd / folded scale+shift from the (possibly cross-rank reduced) sums; running-stat update with the
@@ -473,8 +629,9 @@ __device__ __forceinline__ void row_to_nhw(unsigned r, int H, int W, unsigned& n
 template <typename TY, typename TG, int MODE, bool GN>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
-                         float* __restrict__ sums, int N, int H, int W, int C, int act) {
-    extern __shared__ float sh[];
+                         float* __restrict__ sums, int N, int H, int W, int C, int act, void* ws) {
+    extern __shared__ float sh[];   // [2][rows_per_iter][C] | block vector [2C] | totals [2C]
+    __shared__ int red_flag;
     const int tpr = C / 8, rpi = blockDim.x / tpr;
     const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
     const unsigned P = (unsigned)N * H * W;
@@ -528,12 +685,17 @@ bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, con
         sh[(rpi + tr) * C + tc * 8 + k] = invstd * (sy[k] - mean * s1[k]);
     }
     __syncthreads();
+    float* blk = sh + 2 * rpi * C;
+    float* tot = blk + 2 * C;
     for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
         const int which = c / C, ch = c % C;
         float a = 0.f;
         for (int r = 0; r < rpi; ++r) a += sh[(which * rpi + r) * C + ch];
-        atomicAdd(sums + c, a);
+        blk[c] = a;
     }
+    __syncthreads();
+    if (det_reduce<float>(ws, 2 * C, gridDim.x, blockIdx.x, blk, tot, threadIdx.x, blockDim.x, BlockSync{}, &red_flag))
+        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sums[c] = tot[c];
 }
 
 // dgamma += s2, dbeta += s1 (local sums: autograd's gradient all-reduce averages them later); coef = (cross-rank) sums / count
@@ -630,8 +792,9 @@ bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, cons
 }
 
 // per-channel column sums of an NHWC bf16 tensor (bias gradient of a conv that does not feed a batch norm)
-__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ sums, long long P, int C) {
-    extern __shared__ float sh[];
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ sums, long long P, int C, void* ws) {
+    extern __shared__ float sh[];   // [rows_per_iter][C] | block vector [C] | totals [C]
+    __shared__ int red_flag;
     const int tpr = C / 8, rpi = blockDim.x / tpr;
     const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -646,20 +809,27 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ y, float* __rest
         for (int k = 0; k < 8; ++k) sh[tr * C + tc * 8 + k] = s[k];
     }
     __syncthreads();
+    float* blk = sh + rpi * C;
+    float* tot = blk + C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float a = 0.f;
         for (int r = 0; r < rpi; ++r) a += sh[r * C + c];
-        atomicAdd(sums + c, a);
+        blk[c] = a;
     }
+    __syncthreads();
+    if (det_reduce<float>(ws, C, gridDim.x, blockIdx.x, blk, tot, threadIdx.x, blockDim.x, BlockSync{}, &red_flag))
+        for (int c = threadIdx.x; c < C; c += blockDim.x) sums[c] = tot[c];
 }
 
 // ---------------------------------------------------------------- re-parameterisation + KL
 // h = [N][2*Dz] fp32 (mu | logstd, the NCHW flatten of the encoder output; reference models.py:559-560),
-// z = mu + exp(logstd) * eps (models.py:561), kl_rows[n] = sum_d(-0.5 - ls + 0.5 mu^2 + 0.5 exp(2 ls)) (losses.py:392).
-// One block row per sample chunk; warp-shuffle reduction, one atomicAdd per warp.
+// z = mu + exp(logstd) * eps (models.py:561), sum_blocks kl_part[n][.] = sum_d(-0.5 - ls + 0.5 mu^2 + 0.5 exp(2 ls)) (losses.py:392).
+// One block row per sample chunk, float4 loads; warp-shuffle reduction, the warps of a block combined in warp order, one
+// partial per block written to kl_part[n][blockIdx.x] (the caller adds the few partials of a row: no atomics, reproducible).
 __global__ void reparam_kl_fwd_kernel(const float* __restrict__ mu_p, const float* __restrict__ ls_p, long long row_stride,
-                                      const float* __restrict__ eps, float* __restrict__ z, float* __restrict__ kl_rows,
+                                      const float* __restrict__ eps, float* __restrict__ z, float* __restrict__ kl_part,
                                       int Dz) {
+    __shared__ float red[32];
     const int n = blockIdx.y;
     const float4* mu4 = reinterpret_cast<const float4*>(mu_p + (long long)n * row_stride);
     const float4* ls4 = reinterpret_cast<const float4*>(ls_p + (long long)n * row_stride);
@@ -668,7 +838,7 @@ __global__ void reparam_kl_fwd_kernel(const float* __restrict__ mu_p, const floa
     float acc = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Dz / 4; i += gridDim.x * blockDim.x) {
         const float4 m = __ldg(mu4 + i), l = __ldg(ls4 + i);
-        const float sx = __expf(l.x), sy = __expf(l.y), sz = __expf(l.z), sw = __expf(l.w);
+        const float sx = expf(l.x), sy = expf(l.y), sz = expf(l.z), sw = expf(l.w);
         if (z4) {
             float4 e = e4 ? __ldg(e4 + i) : make_float4(0, 0, 0, 0);
             z4[i] = make_float4(fmaf(sx, e.x, m.x), fmaf(sy, e.y, m.y), fmaf(sz, e.z, m.z), fmaf(sw, e.w, m.w));
@@ -676,9 +846,15 @@ __global__ void reparam_kl_fwd_kernel(const float* __restrict__ mu_p, const floa
         acc += (-0.5f - l.x + 0.5f * m.x * m.x + 0.5f * sx * sx) + (-0.5f - l.y + 0.5f * m.y * m.y + 0.5f * sy * sy) +
                (-0.5f - l.z + 0.5f * m.z * m.z + 0.5f * sz * sz) + (-0.5f - l.w + 0.5f * m.w * m.w + 0.5f * sw * sw);
     }
-    if (kl_rows) {
+    if (kl_part) {
         acc = warp_sum(acc);
-        if ((threadIdx.x & 31) == 0) atomicAdd(kl_rows + n, acc);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float v = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w];
+            kl_part[(long long)n * gridDim.x + blockIdx.x] = v;
+        }
     }
 }
 
@@ -691,16 +867,24 @@ __global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu_p, const floa
                                       float* __restrict__ dls, long long out_stride, int Dz) {
     const int n = blockIdx.y;
     const float ks = kscale_ptr ? kscale * __ldg(kscale_ptr) : kscale;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Dz; i += gridDim.x * blockDim.x) {
-        const float m = mu_p[(long long)n * row_stride + i], l = ls_p[(long long)n * row_stride + i];
-        const float s = __expf(l);
-        const float g = dz ? dz[(long long)n * Dz + i] : 0.f;
-        const float e = eps ? eps[(long long)n * Dz + i] : 0.f;
-        float a = g + ks * m, b = g * e * s + ks * (s * s - 1.f);
-        if (dmu_ext) a += dmu_ext[(long long)n * Dz + i];
-        if (dls_ext) b += dls_ext[(long long)n * Dz + i];
-        dmu[(long long)n * out_stride + i] = a;
-        dls[(long long)n * out_stride + i] = b;
+    // float4 everywhere: Dz % 4 == 0 and 16-byte aligned rows are checked by the host entry point
+    const float4* mu4 = reinterpret_cast<const float4*>(mu_p + (long long)n * row_stride);
+    const float4* ls4 = reinterpret_cast<const float4*>(ls_p + (long long)n * row_stride);
+    const float4* e4 = eps ? reinterpret_cast<const float4*>(eps + (long long)n * Dz) : nullptr;
+    const float4* g4 = dz ? reinterpret_cast<const float4*>(dz + (long long)n * Dz) : nullptr;
+    const float4* xm4 = dmu_ext ? reinterpret_cast<const float4*>(dmu_ext + (long long)n * Dz) : nullptr;
+    const float4* xl4 = dls_ext ? reinterpret_cast<const float4*>(dls_ext + (long long)n * Dz) : nullptr;
+    float4* om4 = reinterpret_cast<float4*>(dmu + (long long)n * out_stride);
+    float4* ol4 = reinterpret_cast<float4*>(dls + (long long)n * out_stride);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Dz / 4; i += gridDim.x * blockDim.x) {
+        const float4 m = __ldg(mu4 + i), l = __ldg(ls4 + i);
+        const float4 g = g4 ? __ldg(g4 + i) : zero4, e = e4 ? __ldg(e4 + i) : zero4;
+        const float4 xm = xm4 ? __ldg(xm4 + i) : zero4, xl = xl4 ? __ldg(xl4 + i) : zero4;
+        const float sx = expf(l.x), sy = expf(l.y), sz = expf(l.z), sw = expf(l.w);
+        om4[i] = make_float4(g.x + ks * m.x + xm.x, g.y + ks * m.y + xm.y, g.z + ks * m.z + xm.z, g.w + ks * m.w + xm.w);
+        ol4[i] = make_float4(g.x * e.x * sx + ks * (sx * sx - 1.f) + xl.x, g.y * e.y * sy + ks * (sy * sy - 1.f) + xl.y,
+                             g.z * e.z * sz + ks * (sz * sz - 1.f) + xl.z, g.w * e.w * sw + ks * (sw * sw - 1.f) + xl.w);
     }
 }
 
@@ -711,8 +895,9 @@ __global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu_p, const floa
 // Block reduce: warp shuffle -> shared -> one atomicAdd per block.
 __global__ void recon_loss_kernel(const float* __restrict__ logits, const float* __restrict__ target, float* __restrict__ pred_out,
                                   float* __restrict__ grad_f32, __nv_bfloat16* __restrict__ grad_nhwc, float* __restrict__ loss_sum,
-                                  int N, int C, int HW, int Cp, int l1, int use_sigmoid, float gscale) {
-    __shared__ float red[32];
+                                  int N, int C, int HW, int Cp, int l1, int use_sigmoid, float gscale, void* ws) {
+    __shared__ float red[34];
+    __shared__ int red_flag;
     float acc = 0.f;
     const long long P = (long long)N * HW;
     for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < P; pix += (long long)gridDim.x * blockDim.x) {
@@ -723,7 +908,7 @@ __global__ void recon_loss_kernel(const float* __restrict__ logits, const float*
         for (int c = 0; c < C; ++c) {
             const long long idx = ((long long)n * C + c) * HW + hw;
             const float o = __ldg(logits + idx), t = __ldg(target + idx);
-            const float s = use_sigmoid ? 1.f / (1.f + __expf(-o)) : o;
+            const float s = use_sigmoid ? 1.f / (1.f + expf(-o)) : o;
             const float d = s - t;
             acc += l1 ? fabsf(d) : d * d;
             float gd = l1 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : 2.f * d;
@@ -745,17 +930,21 @@ __global__ void recon_loss_kernel(const float* __restrict__ logits, const float*
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-        v = warp_sum(v);
-        if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+    if (threadIdx.x == 0) {                      // warps in order, then blocks in order (fv_reduce.cuh): reproducible
+        float v = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w];
+        red[32] = v;
     }
+    __syncthreads();
+    if (det_reduce<float>(ws, 1, gridDim.x, blockIdx.x, red + 32, red + 33, threadIdx.x, blockDim.x, BlockSync{}, &red_flag))
+        if (threadIdx.x == 0) loss_sum[0] = red[33];
 }
 
 // flat variant for arbitrary same-shape fp32 tensors (the drop-in ReconLoss()((a, b))): float4 vectorised
 __global__ void recon_loss_flat_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ grad,
-                                       float* __restrict__ loss_sum, long long E, int l1, float gscale) {
-    __shared__ float red[32];
+                                       float* __restrict__ loss_sum, long long E, int l1, float gscale, void* ws) {
+    __shared__ float red[34];
+    __shared__ int red_flag;
     float acc = 0.f;
     const long long E4 = E / 4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < E4; i += (long long)gridDim.x * blockDim.x) {
@@ -778,11 +967,14 @@ __global__ void recon_loss_flat_kernel(const float* __restrict__ a, const float*
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-        v = warp_sum(v);
-        if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+    if (threadIdx.x == 0) {                      // warps in order, then blocks in order (fv_reduce.cuh): reproducible
+        float v = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w];
+        red[32] = v;
     }
+    __syncthreads();
+    if (det_reduce<float>(ws, 1, gridDim.x, blockIdx.x, red + 32, red + 33, threadIdx.x, blockDim.x, BlockSync{}, &red_flag))
+        if (threadIdx.x == 0) loss_sum[0] = red[33];
 }
 
 // Adam (torch.optim.Adam semantics without amsgrad / weight decay, reference logger.py:60) over a table of tensors in ONE
@@ -892,11 +1084,54 @@ extern "C" __attribute__((visibility("default"))) int fv_weight_prep_batched(con
     return FV_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const float* acc, float* grad, int Co, int Ci, int R, int S, int Ci_pad, int accumulate, void* stream) {
-    if (!acc || !grad) return fail(FV_ERR_ARG, "fv_wgrad_finish: null pointer");
-    wgrad_finish_kernel<<<grid_for((long long)Co * Ci * R * S), kThreads, 0, STREAM>>>(acc, grad, Co, Ci, R * S, Ci_pad, accumulate);
+extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const float* part, int splits, float* grad, int Co, int Ci, int R, int S, int Co_pad,
+                                                                    int Ci_pad, int accumulate, void* stream) {
+    if (!part || !grad || splits < 1) return fail(FV_ERR_ARG, "fv_wgrad_finish: bad arguments");
+    wgrad_finish_kernel<<<grid_for((long long)Co * Ci * R * S), kThreads, 0, STREAM>>>(part, grad, Co, Ci, R * S, Ci_pad, accumulate, splits,
+                                                                                        (long long)Co_pad * R * S * Ci_pad);
     FV_LAUNCH_CHECK("wgrad_finish_kernel");
     return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_slab_sum(const float* part, int slabs, long long slab_stride, float* out, long long n, int accumulate,
+                                                                void* stream) {
+    if (!part || !out || slabs < 1 || n < 1) return fail(FV_ERR_ARG, "fv_slab_sum: bad arguments");
+    slab_sum_kernel<<<grid_for(n), kThreads, 0, STREAM>>>(part, slabs, slab_stride, out, n, accumulate);
+    FV_LAUNCH_CHECK("slab_sum_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_weight_prep_up(const float* w, void* wx2, void* ws2, int Co, int Ci, int Co_pad, int Ci_pad, void* stream) {
+    if (!w || (!wx2 && !ws2) || Co_pad < Co || Ci_pad < Ci) return fail(FV_ERR_ARG, "fv_weight_prep_up: bad arguments");
+    weight_prep_up_kernel<<<grid_for(16LL * Co_pad * Ci_pad), kThreads, 0, STREAM>>>(w, (__nv_bfloat16*)wx2, (__nv_bfloat16*)ws2, Co, Ci, Co_pad, Ci_pad);
+    FV_LAUNCH_CHECK("weight_prep_up_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_weight_prep_s2(const float* w, void* wf, void* wx2, int Co, int Ci, int Co_pad, int Ci_pad, void* stream) {
+    if (!w || (!wf && !wx2) || Co_pad < Co || Ci_pad < Ci) return fail(FV_ERR_ARG, "fv_weight_prep_s2: bad arguments");
+    weight_prep_s2_kernel<<<grid_for(16LL * Co_pad * Ci_pad), kThreads, 0, STREAM>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wx2, Co, Ci, Co_pad, Ci_pad);
+    FV_LAUNCH_CHECK("weight_prep_s2_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish_up(const float* part, int splits, float* grad, int Co, int Ci, int Co_pad, int Ci_pad,
+                                                                       int accumulate, void* stream) {
+    if (!part || !grad || splits < 1) return fail(FV_ERR_ARG, "fv_wgrad_finish_up: bad arguments");
+    wgrad_finish_up_kernel<<<grid_for((long long)Co * Ci * 9), kThreads, 0, STREAM>>>(part, grad, Co, Ci, Co_pad, Ci_pad, accumulate, splits,
+                                                                                       16LL * Co_pad * Ci_pad);
+    FV_LAUNCH_CHECK("wgrad_finish_up_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) long long fv_reduce_ws_bytes(void) {
+    return (long long)det_reduce_ws_bytes(kRedGroup * kRedMaxGroups, 1024, sizeof(float));
+}
+static int check_ws(const char* who, const void* ws, int grid, int n_elems, int elem_size) {
+    if (!ws) return fail(FV_ERR_ARG, "%s: null reduction workspace (fv_reduce_ws_bytes() bytes, zero-initialised once)", who);
+    if (grid > kRedGroup * kRedMaxGroups || (long long)n_elems * elem_size > 4096)
+        return fail(FV_ERR_INTERNAL, "%s: reduction of %d x %d-byte elements over %d blocks exceeds the workspace layout", who, n_elems, elem_size, grid);
+    return 0;
 }
 
 static int reduce_geometry(int C, long long P, int& grid, size_t& shmem, int resident = 2, int rows_per_thread = 16, int big_waves = 8) {
@@ -909,19 +1144,20 @@ static int reduce_geometry(int C, long long P, int& grid, size_t& shmem, int res
     long long blocks = (row_blocks + rows_per_thread - 1) / rows_per_thread;
     const long long cap = (long long)num_sms() * (row_blocks > (long long)num_sms() * 64 ? big_waves : resident);
     grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
-    shmem = (size_t)2 * rpi * C * sizeof(float);
+    shmem = ((size_t)2 * rpi * C + 4 * (size_t)C) * sizeof(float);   // row partials | block vector [2C] | totals [2C]
     return rpi;
 }
 
-extern "C" __attribute__((visibility("default"))) int fv_bn_stats(const void* y, int dtype, float* sums, long long P, int C, void* stream) {
+extern "C" __attribute__((visibility("default"))) int fv_bn_stats(const void* y, int dtype, float* sums, long long P, int C, void* ws, void* stream) {
     if (!y || !sums) return fail(FV_ERR_ARG, "fv_bn_stats: null pointer");
     if (int e = check_c8("fv_bn_stats", C)) return e;
     int grid; size_t sh;
     reduce_geometry(C, P, grid, sh, 4);            // 51 registers: four 256-thread blocks per SM
+    if (int e = check_ws("fv_bn_stats", ws, grid, 2 * C, 4)) return e;
     if (dtype == FV_DT_BF16)
-        bn_stats_kernel<__nv_bfloat16><<<grid, kThreads, sh, STREAM>>>((const __nv_bfloat16*)y, sums, P, C);
+        bn_stats_kernel<__nv_bfloat16><<<grid, kThreads, sh, STREAM>>>((const __nv_bfloat16*)y, sums, P, C, ws);
     else
-        bn_stats_kernel<float><<<grid, kThreads, sh, STREAM>>>((const float*)y, sums, P, C);
+        bn_stats_kernel<float><<<grid, kThreads, sh, STREAM>>>((const float*)y, sums, P, C, ws);
     FV_LAUNCH_CHECK("bn_stats_kernel");
     return FV_OK;
 }
@@ -983,7 +1219,7 @@ static int bn_act_fwd_impl(const void* y, int in_dtype, const float* stat, void*
 }
 
 extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_reduce(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat,
-                                    float* sums, int N, int H, int W, int C, int mode, int act, void* stream) {
+                                    float* sums, int N, int H, int W, int C, int mode, int act, void* ws, void* stream) {
     if (!y || !g || !stat || !sums) return fail(FV_ERR_ARG, "fv_bn_act_bwd_reduce: null pointer");
     if (int e = check_c8("fv_bn_act_bwd_reduce", C)) return e;
     if ((long long)N * H * W >= (1LL << 31)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_reduce: tensor too large for 32-bit indexing");
@@ -992,7 +1228,8 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_reduce(const
     // one resident wave also for large tensors: every block ends with 2C atomics on the same addresses (1184 blocks x 128
     // channels = 150 k serialised atomics cost more than the second wave's tail gains)
     reduce_geometry(C, (long long)N * H * W, grid, sh, 2, 16, 2);
-#define LAUNCH3(TY, TG, M, GNF) bn_act_bwd_reduce_kernel<TY, TG, M, GNF><<<grid, kThreads, sh, STREAM>>>((const TY*)y, (const TG*)g, stat, sums, N, H, W, C, act)
+    if (int e = check_ws("fv_bn_act_bwd_reduce", ws, grid, 2 * C, 4)) return e;
+#define LAUNCH3(TY, TG, M, GNF) bn_act_bwd_reduce_kernel<TY, TG, M, GNF><<<grid, kThreads, sh, STREAM>>>((const TY*)y, (const TG*)g, stat, sums, N, H, W, C, act, ws)
 #define LAUNCH2(TY, TG) do { \
         if (mode == FV_MODE_POOL) { if (g_nchw) LAUNCH3(TY, TG, FV_MODE_POOL, true); else LAUNCH3(TY, TG, FV_MODE_POOL, false); } \
         else if (mode == FV_MODE_UP) LAUNCH3(TY, TG, FV_MODE_UP, false); \
@@ -1060,24 +1297,34 @@ static int bn_act_bwd_apply_impl(const void* y, int y_dtype, const void* g, int 
     return FV_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int fv_colsum(const void* y, float* sums, long long P, int C, void* stream) {
+extern "C" __attribute__((visibility("default"))) int fv_colsum(const void* y, float* sums, long long P, int C, void* ws, void* stream) {
     if (!y || !sums) return fail(FV_ERR_ARG, "fv_colsum: null pointer");
     if (int e = check_c8("fv_colsum", C)) return e;
     int grid; size_t sh;
     reduce_geometry(C, P, grid, sh);
-    colsum_kernel<<<grid, kThreads, sh / 2, STREAM>>>((const __nv_bfloat16*)y, sums, P, C);
+    if (int e = check_ws("fv_colsum", ws, grid, C, 4)) return e;
+    colsum_kernel<<<grid, kThreads, sh, STREAM>>>((const __nv_bfloat16*)y, sums, P, C, ws);
     FV_LAUNCH_CHECK("colsum_kernel");
     return FV_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int fv_reparam_kl_fwd(const float* mu, const float* logstd, long long row_stride, const float* eps, float* z,
-                                 float* kl_rows, int N, int Dz, void* stream) {
-    if (!mu || !logstd || Dz % 4 || N < 1) return fail(FV_ERR_ARG, "fv_reparam_kl_fwd: bad arguments (Dz=%d must be a multiple of 4)", Dz);
+static int reparam_blocks(int N, int Dz) {
     int bx = (Dz / 4 + kThreads - 1) / kThreads;
     const int cap = (num_sms() * 8 + N - 1) / N;
     if (bx > cap) bx = cap;
-    if (bx < 1) bx = 1;
-    reparam_kl_fwd_kernel<<<dim3(bx, N), kThreads, 0, STREAM>>>(mu, logstd, row_stride, eps, z, kl_rows, Dz);
+    return bx < 1 ? 1 : bx;
+}
+// partial KL sums per row that fv_reparam_kl_fwd writes (kl_part has N * this many floats)
+extern "C" __attribute__((visibility("default"))) int fv_reparam_kl_parts(int N, int Dz) { return (N < 1 || Dz < 4) ? 1 : reparam_blocks(N, Dz); }
+
+static bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
+
+extern "C" __attribute__((visibility("default"))) int fv_reparam_kl_fwd(const float* mu, const float* logstd, long long row_stride, const float* eps, float* z,
+                                 float* kl_part, int N, int Dz, void* stream) {
+    if (!mu || !logstd || Dz % 4 || N < 1) return fail(FV_ERR_ARG, "fv_reparam_kl_fwd: bad arguments (Dz=%d must be a multiple of 4)", Dz);
+    if (row_stride % 4 || misaligned16(mu) || misaligned16(logstd) || misaligned16(eps) || misaligned16(z))
+        return fail(FV_ERR_ARG, "fv_reparam_kl_fwd: rows must be 16-byte aligned");
+    reparam_kl_fwd_kernel<<<dim3(reparam_blocks(N, Dz), N), kThreads, 0, STREAM>>>(mu, logstd, row_stride, eps, z, kl_part, Dz);
     FV_LAUNCH_CHECK("reparam_kl_fwd_kernel");
     return FV_OK;
 }
@@ -1085,34 +1332,37 @@ extern "C" __attribute__((visibility("default"))) int fv_reparam_kl_fwd(const fl
 extern "C" __attribute__((visibility("default"))) int fv_reparam_kl_bwd(const float* mu, const float* logstd, long long row_stride, const float* eps, const float* dz,
                                  const float* dmu_ext, const float* dls_ext, float kscale, const float* kscale_ptr, float* dmu,
                                  float* dls, long long out_stride, int N, int Dz, void* stream) {
-    if (!mu || !logstd || !dmu || !dls || N < 1) return fail(FV_ERR_ARG, "fv_reparam_kl_bwd: bad arguments");
-    int bx = (Dz + kThreads - 1) / kThreads;
-    const int cap = (num_sms() * 8 + N - 1) / N;
-    if (bx > cap) bx = cap;
-    if (bx < 1) bx = 1;
-    reparam_kl_bwd_kernel<<<dim3(bx, N), kThreads, 0, STREAM>>>(mu, logstd, row_stride, eps, dz, dmu_ext, dls_ext, kscale, kscale_ptr,
-                                                                dmu, dls, out_stride, Dz);
+    if (!mu || !logstd || !dmu || !dls || N < 1 || Dz % 4) return fail(FV_ERR_ARG, "fv_reparam_kl_bwd: bad arguments (Dz=%d must be a multiple of 4)", Dz);
+    if (row_stride % 4 || out_stride % 4 || misaligned16(mu) || misaligned16(logstd) || misaligned16(eps) || misaligned16(dz) ||
+        misaligned16(dmu_ext) || misaligned16(dls_ext) || misaligned16(dmu) || misaligned16(dls))
+        return fail(FV_ERR_ARG, "fv_reparam_kl_bwd: rows must be 16-byte aligned");
+    reparam_kl_bwd_kernel<<<dim3(reparam_blocks(N, Dz), N), kThreads, 0, STREAM>>>(mu, logstd, row_stride, eps, dz, dmu_ext, dls_ext, kscale, kscale_ptr,
+                                                                                 dmu, dls, out_stride, Dz);
     FV_LAUNCH_CHECK("reparam_kl_bwd_kernel");
     return FV_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int fv_recon_loss(const float* logits, const float* target, float* pred_out, float* grad_f32, void* grad_nhwc,
                              float* loss_sum, int N, int C, int H, int W, int Cp, int l1, int use_sigmoid, float gscale,
-                             void* stream) {
+                             void* ws, void* stream) {
     if (!logits || !target || !loss_sum) return fail(FV_ERR_ARG, "fv_recon_loss: null pointer");
     if (grad_nhwc && (Cp % 8 || Cp < C || C > 16)) return fail(FV_ERR_UNSUPPORTED, "fv_recon_loss: NHWC gradient needs C <= 16 <= Cp, Cp %% 8 == 0");
-    recon_loss_kernel<<<grid_for((long long)N * H * W), kThreads, 0, STREAM>>>(logits, target, pred_out, grad_f32, (__nv_bfloat16*)grad_nhwc,
-                                                                             loss_sum, N, C, H * W, Cp, l1, use_sigmoid, gscale);
+    const int grid = grid_for((long long)N * H * W);
+    if (int e = check_ws("fv_recon_loss", ws, grid, 1, 4)) return e;
+    recon_loss_kernel<<<grid, kThreads, 0, STREAM>>>(logits, target, pred_out, grad_f32, (__nv_bfloat16*)grad_nhwc, loss_sum, N, C, H * W, Cp, l1,
+                                                     use_sigmoid, gscale, ws);
     FV_LAUNCH_CHECK("recon_loss_kernel");
     return FV_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int fv_recon_loss_flat(const float* a, const float* b, float* grad, float* loss_sum, long long E, int l1, float gscale,
-                                  void* stream) {
+                                  void* ws, void* stream) {
     if (!a || !b || !loss_sum || E < 1) return fail(FV_ERR_ARG, "fv_recon_loss_flat: bad arguments");
     if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(grad)) & 15)
         return fail(FV_ERR_ARG, "fv_recon_loss_flat: pointers must be 16-byte aligned");
-    recon_loss_flat_kernel<<<grid_for(E / 4 + 1), kThreads, 0, STREAM>>>(a, b, grad, loss_sum, E, l1, gscale);
+    const int grid = grid_for(E / 4 + 1);
+    if (int e = check_ws("fv_recon_loss_flat", ws, grid, 1, 4)) return e;
+    recon_loss_flat_kernel<<<grid, kThreads, 0, STREAM>>>(a, b, grad, loss_sum, E, l1, gscale, ws);
     FV_LAUNCH_CHECK("recon_loss_flat_kernel");
     return FV_OK;
 }

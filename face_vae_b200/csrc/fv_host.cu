@@ -84,7 +84,9 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 }  // namespace fv
 
 extern "C" __attribute__((visibility("default"))) const char* fv_last_error(void) { return fv::g_err; }
-extern "C" __attribute__((visibility("default"))) const char* fv_version(void) { return "face_vae_b200 0.1 (sm_100a)"; }
+extern "C" __attribute__((visibility("default"))) const char* fv_version(void) { return "face_vae_b200 0.2 (sm_100a)"; }
+// bumped whenever an exported signature changes: the ctypes binding refuses a library built from other sources
+extern "C" __attribute__((visibility("default"))) int fv_abi_version(void) { return FV_ABI_VERSION; }
 extern "C" __attribute__((visibility("default"))) int fv_device_ok(void) {
     int dev = 0;
     cudaDeviceProp p;

@@ -25,6 +25,7 @@
 #include "../../include/facevae_b200.h"
 #include "fv_host.h"
 #include "fv_ptx.cuh"
+#include "fv_reduce.cuh"
 
 namespace fv {
 
@@ -56,8 +57,9 @@ struct FoldParams {
     const float* target;            // NCHW fp32: non-null fuses sigmoid + loss + gradient
     float* pred;                    // NCHW fp32
     __nv_bfloat16* g4;              // [N,H,W,4] bf16: gscale * dloss/dlogits
-    float* loss_sum;                // [1]
+    float* loss_sum;                // [1]   (written: grid total in a fixed summation order)
     float* gsum;                    // [4]: per-channel sums of the gradient (bias gradient)
+    void* red_ws;                   // fv_reduce.cuh workspace (with target)
     int l1, use_sigmoid;
     float gscale;
     // dgrad
@@ -107,6 +109,9 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* wfull = tempty + 2 * kAcc;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
     float* Qs = reinterpret_cast<float*>(smem + p.q_off);
+    __shared__ float fred[8][8];                         // per epilogue warp: loss | - | - | - | gradient sums x4
+    __shared__ float fblk[8], ftot[8];
+    __shared__ int fflag;
 
     constexpr int kIssuerB = MODE == 0 ? 10 : 18;       // second MMA issuer warp (the last warp of the CTA)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -350,7 +355,7 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int c = 0; c < 4; ++c) {
                             if (c < p.Co) {
                             const float t = t_cur[c];
-                            const float sg = p.use_sigmoid ? 1.f / (1.f + __expf(-o[c])) : o[c];
+                            const float sg = p.use_sigmoid ? 1.f / (1.f + expf(-o[c])) : o[c];
                             const float d = sg - t;
                             loss_acc += p.l1 ? fabsf(d) : d * d;
                             float gd = p.l1 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : 2.f * d;
@@ -367,17 +372,19 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
             }
-            if (MODE == 0 && p.target) {
+            if (MODE == 0 && p.target) {                 // per-warp partials; combined in warp order at the end of the kernel
                 loss_acc = warp_sum(loss_acc);
-                if (lane == 0) atomicAdd(p.loss_sum, loss_acc);
-                if (p.gsum) {
+                if (lane == 0) fred[warp - 2][0] = loss_acc;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float t = warp_sum(gs[c]);
-                        if (lane == 0 && c < p.Co) atomicAdd(p.gsum + c, t);
-                    }
+                for (int c = 0; c < 4; ++c) {
+                    const float t = warp_sum(gs[c]);
+                    if (lane == 0) fred[warp - 2][4 + c] = c < p.Co ? t : 0.f;
                 }
             }
+        } else if (MODE == 0 && lane == 0) {
+            fred[warp - 2][0] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) fred[warp - 2][4 + c] = 0.f;
         }
     } else if (MODE == 1 && warp < 18) {
         // record builders (warps 10..17): the forward producer's slab sequence, slab k built by warp k % 8, so that up to
@@ -430,6 +437,19 @@ fold_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         tmem_dealloc(tmem_base, 64 * kAcc);
     }
+    if (MODE == 0 && p.target) {                         // warps in order -> CTA totals -> CTAs in order (fv_reduce.cuh): reproducible
+        if (threadIdx.x < 8) {
+            float a = 0.f;
+            if (threadIdx.x == 0 || threadIdx.x >= 4)
+                for (int w = 0; w < 8; ++w) a += fred[w][threadIdx.x];
+            fblk[threadIdx.x] = a;
+        }
+        __syncthreads();
+        if (det_reduce<float>(p.red_ws, 8, gridDim.x, blockIdx.x, fblk, ftot, threadIdx.x, blockDim.x, BlockSync{}, &fflag)) {
+            if (threadIdx.x == 0) p.loss_sum[0] = ftot[0];
+            if (p.gsum && threadIdx.x >= 4 && threadIdx.x < 4 + p.Co) p.gsum[threadIdx.x - 4] = ftot[threadIdx.x];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
@@ -443,7 +463,8 @@ struct FoldWgradParams {
     int wins_per_col, units_total, units_per_cta;
     int rec_off, bar_off;
     const __nv_bfloat16* dy4;
-    float* dw;                     // [Co][32][7][7] fp32, caller-zeroed
+    float* dw;                     // [CTAs][Co][32][7][7] fp32 partial slabs (stored; fv_slab_sum adds them in CTA order)
+    long long slab_stride;
     const float* scale_ptr;
     long long* trace;
     int dbg;                       // FV_FOLD_DEBUG (tools/fold_experiments.py only): 1 no MMAs, 4 no record build, 8 no slab loads
@@ -602,7 +623,7 @@ fold_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const FoldWgradParams
                         const int sp = k >> 2, co = k & 3;
                         if (co < p.Co) {
                             const float v = __uint_as_float(k < 16 ? v0[k & 15] : v1[k & 15]) * sc;
-                            atomicAdd(p.dw + (((size_t)co * kFC + lane) * kFR + r) * kFR + (6 - sp), v);
+                            p.dw[(size_t)blockIdx.x * p.slab_stride + (((size_t)co * kFC + lane) * kFR + r) * kFR + (6 - sp)] = v;
                         }
                     }
                 }
@@ -725,9 +746,9 @@ extern "C" __attribute__((visibility("default"))) int fv_outconv_prep(const floa
 
 extern "C" __attribute__((visibility("default"))) int fv_outconv_fwd(const void* x, const void* wq, const float* bias, float* logits, const float* target,
                                                                     float* pred, void* g4, float* loss_sum, float* gsum, int N, int H, int W,
-                                                                    int Ci, int Co, int l1, int use_sigmoid, float gscale, void* stream) {
+                                                                    int Ci, int Co, int l1, int use_sigmoid, float gscale, void* red_ws, void* stream) {
     if (!x || !wq || (!logits && !target)) return fail(FV_ERR_ARG, "fv_outconv_fwd: null pointer");
-    if (target && !loss_sum) return fail(FV_ERR_ARG, "fv_outconv_fwd: the fused loss needs loss_sum");
+    if (target && (!loss_sum || !red_ws)) return fail(FV_ERR_ARG, "fv_outconv_fwd: the fused loss needs loss_sum and the reduction workspace");
     if (!fold_shape_ok(N, H, W, Ci, Co, kFR, kFR))
         return fail(FV_ERR_UNSUPPORTED, "fv_outconv_fwd: needs a 7x7 filter, Ci = 32, Co <= 4, W = 128 or 256 (got Ci=%d Co=%d W=%d)", Ci, Co, W);
     FoldParams p{};
@@ -735,7 +756,7 @@ extern "C" __attribute__((visibility("default"))) int fv_outconv_fwd(const void*
     p.target = target;                           // sizes the target staging area
     const int grid = fold_geometry(p, N, H, W, 0);
     if (grid < 1) return fail(FV_ERR_INTERNAL, "fv_outconv_fwd: shared-memory budget");
-    p.bias = bias; p.logits = logits; p.target = target; p.pred = pred; p.g4 = (__nv_bfloat16*)g4; p.loss_sum = loss_sum; p.gsum = gsum;
+    p.bias = bias; p.logits = logits; p.target = target; p.pred = pred; p.g4 = (__nv_bfloat16*)g4; p.loss_sum = loss_sum; p.gsum = gsum; p.red_ws = red_ws;
     p.l1 = l1; p.use_sigmoid = use_sigmoid; p.gscale = gscale; p.trace = trace_ptr();
     CUtensorMap tmA, tmW;
     {
@@ -779,21 +800,31 @@ extern "C" __attribute__((visibility("default"))) int fv_outconv_dgrad(const voi
     return FV_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int fv_outconv_wgrad(const void* x, const void* dy4, const float* scale_ptr, float* dw, int N, int H, int W,
-                                                                      int Ci, int Co, void* stream) {
-    if (!x || !dy4 || !dw) return fail(FV_ERR_ARG, "fv_outconv_wgrad: null pointer");
+static int fold_wgrad_grid(int N, int H, int W, int& units_total, int& units_per_cta) {
+    units_total = N * (W / 128) * ((H + kWT - 1) / kWT);
+    const int sms = fold_ctas();
+    units_per_cta = (units_total + sms - 1) / sms;
+    return (units_total + units_per_cta - 1) / units_per_cta;
+}
+// partial slabs ([Co][32][7][7] floats each) fv_outconv_wgrad writes for this shape
+extern "C" __attribute__((visibility("default"))) int fv_outconv_wgrad_splits(int N, int H, int W) {
+    int a, b;
+    return (N < 1 || H < 1 || (W != 128 && W != 256)) ? 0 : fold_wgrad_grid(N, H, W, a, b);
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_outconv_wgrad(const void* x, const void* dy4, const float* scale_ptr, float* part, int splits, int N,
+                                                                      int H, int W, int Ci, int Co, void* stream) {
+    if (!x || !dy4 || !part) return fail(FV_ERR_ARG, "fv_outconv_wgrad: null pointer");
     if (!fold_shape_ok(N, H, W, Ci, Co, kFR, kFR))
         return fail(FV_ERR_UNSUPPORTED, "fv_outconv_wgrad: needs a 7x7 filter, Ci = 32, Co <= 4, W = 128 or 256 (got Ci=%d Co=%d W=%d)", Ci, Co, W);
     FoldWgradParams p{};
     p.N = N; p.H = H; p.W = W; p.halves = W / 128; p.Co = Co;
     p.wins_per_col = (H + kWT - 1) / kWT;
-    p.units_total = N * p.halves * p.wins_per_col;
-    const int sms = fold_ctas();
-    p.units_per_cta = (p.units_total + sms - 1) / sms;
-    const int grid = (p.units_total + p.units_per_cta - 1) / p.units_per_cta;
+    const int grid = fold_wgrad_grid(N, H, W, p.units_total, p.units_per_cta);
+    if (grid != splits) return fail(FV_ERR_ARG, "fv_outconv_wgrad: splits=%d does not match fv_outconv_wgrad_splits() = %d", splits, grid);
     p.rec_off = kWSlots * kWSlab;
     p.bar_off = p.rec_off + kRecSlots * kWSlab;
-    p.dy4 = (const __nv_bfloat16*)dy4; p.dw = dw; p.scale_ptr = scale_ptr; p.trace = trace_ptr();
+    p.dy4 = (const __nv_bfloat16*)dy4; p.dw = part; p.slab_stride = (long long)Co * kFC * kFR * kFR; p.scale_ptr = scale_ptr; p.trace = trace_ptr();
     { const char* v = getenv("FV_FOLD_DEBUG"); p.dbg = v ? atoi(v) : 0; }
     CUtensorMap tmX;
     {

@@ -8,11 +8,12 @@
 //   forward  = moments of x (9 numbers, one pass over 25 MB) + one pass  a = relu(A x + c)  writing NHWC bf16;
 //   backward = ONE pass over (g, x) accumulating sum(dz) and sum(dz * x) per output channel (128 numbers); dW, dgamma,
 //              dbeta follow in closed form (the BN coupling terms need only those sums and the input moments).
-// All sums are accumulated in double (atomicAdd on doubles, a few thousand per launch) and all-reduced by the host
-// across data-parallel ranks like every other batch-norm statistic.
+// All sums are accumulated in double, combined across blocks in a fixed order (fv_reduce.cuh: bitwise reproducible) and
+// all-reduced by the host across data-parallel ranks like every other batch-norm statistic.
 #include "../../include/facevae_b200.h"
 #include "fv_host.h"
 #include "fv_ptx.cuh"
+#include "fv_reduce.cuh"
 
 namespace fv {
 
@@ -25,10 +26,12 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-// sums[0..C) = sum_p x_c ; sums[C + c*C + d] = sum_p x_c x_d
+// sums[0..C) = sum_p x_c ; sums[C + c*C + d] = sum_p x_c x_d   (written, not accumulated)
 template <int C>
-__global__ void pw_moments_kernel(const float* __restrict__ x, double* __restrict__ sums, int N, int HW) {
+__global__ void pw_moments_kernel(const float* __restrict__ x, double* __restrict__ sums, int N, int HW, void* ws) {
     __shared__ double red[kPwThreads / 32][C + C * C];
+    __shared__ double blk[C + C * C], tot[C + C * C];
+    __shared__ int red_flag;
     float s[C], q[C][C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -64,8 +67,11 @@ __global__ void pw_moments_kernel(const float* __restrict__ x, double* __restric
     if (threadIdx.x < C + C * C) {
         double a = 0;
         for (int w = 0; w < kPwThreads / 32; ++w) a += red[w][threadIdx.x];
-        atomicAdd(sums + threadIdx.x, a);
+        blk[threadIdx.x] = a;
     }
+    __syncthreads();
+    if (det_reduce<double>(ws, C + C * C, gridDim.x, blockIdx.x, blk, tot, threadIdx.x, blockDim.x, BlockSync{}, &red_flag))
+        if (threadIdx.x < C + C * C) sums[threadIdx.x] = tot[threadIdx.x];
 }
 
 // coef[co][0..C) = A = gamma*invstd*W, coef[co][C] = c = beta - gamma*invstd*(W mean_x); stat[0][co] = mean_y, stat[1][co] = invstd
@@ -127,15 +133,17 @@ __global__ void pw_fwd_kernel(const float* __restrict__ x, const float* __restri
     }
 }
 
-// sums[co] += sum_p dz[p,co];  sums[CO + co*C + c] += sum_p dz[p,co] * x[p,c];   dz = g * act'(A x + c).
+// sums[co] = sum_p dz[p,co];  sums[CO + co*C + c] = sum_p dz[p,co] * x[p,c];   dz = g * act'(A x + c).
 // Two threads per pixel (16 output channels each) keep the partial sums at 64 registers so two blocks fit per SM.
 template <int C, int CO>
 __global__ void __launch_bounds__(kPwThreads, 2)
 pw_bwd_reduce_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ g, const float* __restrict__ coef,
-                     double* __restrict__ sums, int N, int HW, int act) {
+                     double* __restrict__ sums, int N, int HW, int act, void* ws) {
     constexpr int CH = CO / 2;                                   // channels per thread
     __shared__ float cs[CO * (C + 1)];
     __shared__ float red[kPwThreads / 32][2][CH * (C + 1)];
+    __shared__ double blk[CO * (C + 1)], tot[CO * (C + 1)];
+    __shared__ int red_flag;
     for (int i = threadIdx.x; i < CO * (C + 1); i += blockDim.x) cs[i] = coef[i];
     __syncthreads();
     const int half = threadIdx.x & 1;
@@ -204,8 +212,11 @@ pw_bwd_reduce_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
         const int h = co / CH, col = co % CH;
         double a = 0;
         for (int w = 0; w < kPwThreads / 32; ++w) a += (double)red[w][h][col * (C + 1) + c];
-        atomicAdd(sums + (c == C ? co : CO + co * C + c), a);
+        blk[c == C ? co : CO + co * C + c] = a;
     }
+    __syncthreads();
+    if (det_reduce<double>(ws, CO * (C + 1), gridDim.x, blockIdx.x, blk, tot, threadIdx.x, blockDim.x, BlockSync{}, &red_flag))
+        for (int i = threadIdx.x; i < CO * (C + 1); i += blockDim.x) sums[i] = tot[i];
 }
 
 // closed-form parameter gradients from the forward moments (fs) and the backward sums (bs); see the header comment
@@ -243,13 +254,13 @@ using namespace fv;
 #define PW_DISPATCH_C(C_, EXPR3, EXPR4, EXPR1, EXPR2) \
     switch (C_) { case 1: EXPR1; break; case 2: EXPR2; break; case 3: EXPR3; break; default: EXPR4; break; }
 
-extern "C" __attribute__((visibility("default"))) int fv_pw_moments(const float* x, double* sums, int N, int C, int HW, void* stream) {
-    if (!x || !sums || C < 1 || C > kPwMaxC) return fail(FV_ERR_ARG, "fv_pw_moments: C=%d must be 1..%d", C, kPwMaxC);
+extern "C" __attribute__((visibility("default"))) int fv_pw_moments(const float* x, double* sums, int N, int C, int HW, void* ws, void* stream) {
+    if (!x || !sums || !ws || C < 1 || C > kPwMaxC) return fail(FV_ERR_ARG, "fv_pw_moments: C=%d must be 1..%d", C, kPwMaxC);
     const int grid = pw_grid((long long)N * HW);
-    PW_DISPATCH_C(C, (pw_moments_kernel<3><<<grid, kPwThreads, 0, STREAM>>>(x, sums, N, HW)),
-                  (pw_moments_kernel<4><<<grid, kPwThreads, 0, STREAM>>>(x, sums, N, HW)),
-                  (pw_moments_kernel<1><<<grid, kPwThreads, 0, STREAM>>>(x, sums, N, HW)),
-                  (pw_moments_kernel<2><<<grid, kPwThreads, 0, STREAM>>>(x, sums, N, HW)));
+    PW_DISPATCH_C(C, (pw_moments_kernel<3><<<grid, kPwThreads, 0, STREAM>>>(x, sums, N, HW, ws)),
+                  (pw_moments_kernel<4><<<grid, kPwThreads, 0, STREAM>>>(x, sums, N, HW, ws)),
+                  (pw_moments_kernel<1><<<grid, kPwThreads, 0, STREAM>>>(x, sums, N, HW, ws)),
+                  (pw_moments_kernel<2><<<grid, kPwThreads, 0, STREAM>>>(x, sums, N, HW, ws)));
     FV_LAUNCH_CHECK("pw_moments_kernel");
     return FV_OK;
 }
@@ -279,15 +290,15 @@ extern "C" __attribute__((visibility("default"))) int fv_pw_fwd(const float* x, 
 }
 
 extern "C" __attribute__((visibility("default"))) int fv_pw_bwd_reduce(const float* x, const void* g, const float* coef, double* sums, int N, int C,
-                                                                     int HW, int Co, int act, void* stream) {
-    if (!x || !g || !coef || !sums) return fail(FV_ERR_ARG, "fv_pw_bwd_reduce: null pointer");
+                                                                     int HW, int Co, int act, void* ws, void* stream) {
+    if (!x || !g || !coef || !sums || !ws) return fail(FV_ERR_ARG, "fv_pw_bwd_reduce: null pointer");
     if (Co != 32 || C < 1 || C > kPwMaxC) return fail(FV_ERR_UNSUPPORTED, "fv_pw_bwd_reduce: supports C in 1..4 and Co = 32 (got %d -> %d)", C, Co);
     const int grid = pw_grid((long long)N * HW);
     const __nv_bfloat16* gp = (const __nv_bfloat16*)g;
-    PW_DISPATCH_C(C, (pw_bwd_reduce_kernel<3, 32><<<grid, kPwThreads, 0, STREAM>>>(x, gp, coef, sums, N, HW, act)),
-                  (pw_bwd_reduce_kernel<4, 32><<<grid, kPwThreads, 0, STREAM>>>(x, gp, coef, sums, N, HW, act)),
-                  (pw_bwd_reduce_kernel<1, 32><<<grid, kPwThreads, 0, STREAM>>>(x, gp, coef, sums, N, HW, act)),
-                  (pw_bwd_reduce_kernel<2, 32><<<grid, kPwThreads, 0, STREAM>>>(x, gp, coef, sums, N, HW, act)));
+    PW_DISPATCH_C(C, (pw_bwd_reduce_kernel<3, 32><<<grid, kPwThreads, 0, STREAM>>>(x, gp, coef, sums, N, HW, act, ws)),
+                  (pw_bwd_reduce_kernel<4, 32><<<grid, kPwThreads, 0, STREAM>>>(x, gp, coef, sums, N, HW, act, ws)),
+                  (pw_bwd_reduce_kernel<1, 32><<<grid, kPwThreads, 0, STREAM>>>(x, gp, coef, sums, N, HW, act, ws)),
+                  (pw_bwd_reduce_kernel<2, 32><<<grid, kPwThreads, 0, STREAM>>>(x, gp, coef, sums, N, HW, act, ws)));
     FV_LAUNCH_CHECK("pw_bwd_reduce_kernel");
     return FV_OK;
 }

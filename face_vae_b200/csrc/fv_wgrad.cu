@@ -1,14 +1,20 @@
-// Weight gradient of the stride-1 "same" convolution as a tcgen05 GEMM with the pixels as the K dimension:
+// Weight gradient of the convolutions of fv_conv.cu as a tcgen05 GEMM with the pixels as the K dimension:
 //
-//   dW[co, tap, ci] = sum_pixels  X[pixel + tap_offset, ci] * dY[pixel, co]
+//   SAME : dW[co, tap, ci] = sum_pixels X[pixel + tap_offset, ci] * dY[pixel, co]
+//   X2   : dWp[phase][co, tap, ci] = sum_{coarse pixels} X[(i, j) + tap_offset(phase, tap), ci] * dY[(2i + a, 2j + b), co]
+//          (the four 2x2 phase filters of the up-sampling convolution; fv_wgrad_finish_up folds them back into the 3x3 filter)
+//   S2   : dW[co, (r4, s4), ci] = sum_{coarse pixels} X[(2i + r4 - 1, 2j + s4 - 1), ci] * dY[(i, j), co]
 //
 // Both operands are NHWC, i.e. the contraction index (pixel) is the slow index in memory, so they are fed to the
 // tensor core as MN-major operands straight from TMA boxes (no transpose pass):
 //   A (M side) = shifted input windows.  One 128-row M tile stacks 128/cw chunks of cw = min(Ci,64) channels, each
 //                chunk being one (filter tap, channel chunk) pair, so thin layers (Ci = 16/32/64) still fill M = 128.
 //   B (N side) = dY, N = Co_pad.
-//   D[(tap,ci), co] accumulates in TMEM over this CTA's share of the pixels (split-K across CTAs); the epilogue adds
-//   it into the fp32 buffer dWacc[Co_pad][taps][Ci] with red.global.add.f32.
+// The tensor on the FINE grid (dY for X2, X for S2) is read through the 5-D view (2C, W, 2, H, N) of fv_conv.cu: a box at row
+// parity a and channel offset b*C is the stride-2 sub-lattice (2i + a, 2j + b).
+//   D[(tap,ci), co] accumulates in TMEM over this CTA's share of the pixels (split-K across CTAs); every split STORES its
+//   partial into its own slab of the workspace [splits][...]; fv_wgrad_finish adds the slabs in split order (reproducible --
+//   round 1 used red.global.add.f32 into one buffer, whose arrival order changed the last bits from run to run).
 // Replaces the wgrad half of aten::convolution_backward behind nn.Conv2d (reference modules.py:15,32).
 #include "../../include/facevae_b200.h"
 #include "fv_host.h"
@@ -16,20 +22,26 @@
 
 namespace fv {
 
+enum : int { CONV_SAME = 0, CONV_X2 = 1, CONV_S2 = 2 };
+
 struct WgradParams {
-    int N, H, W, Ci, Co_pad, R, S, pad, taps;
+    int N, H, W, Ci, Co_pad, taps, nph;
     int pw, ph, pn, tiles_w, tiles_h, tiles_n, num_pb;   // 64-pixel K blocks
     int cw, cpt, chunks_per_tap, total_chunks;           // A chunking
     int bw, b_chunks;                                    // B chunking
     int mt_total, mt_per_group, groups, splits, pb_per_split;
     int a_chunk_bytes, b_chunk_bytes, a_bytes, b_bytes, stage_stride, stages, tmem_cols;
-    float* dw;
+    float* dw;                                           // partial slabs
+    long long split_stride, phase_stride, co_stride;     // elements; D[(tap, ci), co] -> dw[split][phase][co*co_stride + tap*Ci_total + ci]
+    int ci_total;
+    short4 tapA[64];                                     // per (phase, tap): x = channel offset, y = dw, z = row parity, w = dh of the A box
+    short4 tapB[4];                                      // per phase: x = channel offset, z = row parity of the dY box
 };
 
 static constexpr int kWgradThreads = 192;
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
-conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ WgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // align up with arithmetic on the array itself so the compiler keeps the shared address space (LDS/STS, not generic)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -39,7 +51,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int group = blockIdx.x % p.groups, split = blockIdx.x / p.groups;
+    const int per_phase = p.groups * p.splits;
+    const int phase = blockIdx.x / per_phase, brem = blockIdx.x - phase * per_phase;
+    const int group = brem % p.groups, split = brem / p.groups;
     const int mt0 = group * p.mt_per_group;
     const int mt_n = min(p.mt_per_group, p.mt_total - mt0);
     const int chunk0 = mt0 * p.cpt;
@@ -70,6 +84,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         {
             const bool leader = elect_one_sync();      // role loops stay warp-uniform; only the issue is predicated
             const uint32_t tx = (uint32_t)(n_chunks * p.a_chunk_bytes + p.b_bytes);
+            const short4 tb = p.tapB[phase];
             uint32_t st = 0, phs = 0;
             // pixel-block coordinates advance incrementally (no divisions in the steady state)
             int tn_i = pb0 / (p.tiles_w * p.tiles_h);
@@ -82,17 +97,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 uint8_t* b_dst = a_dst + p.a_bytes;
                 if (leader) mbar_arrive_expect_tx(&full[st], tx);
                 for (int bc = 0; bc < p.b_chunks; ++bc)
-                    if (leader) tma_load_4d(b_dst + (size_t)bc * p.b_chunk_bytes, &tmDY, &full[st], bc * p.bw, w0, h0, n0);
+                    if (leader) tma_load_5d(b_dst + (size_t)bc * p.b_chunk_bytes, &tmDY, &full[st], tb.x + bc * p.bw, w0, tb.z, h0, n0);
                 int tap = chunk0 / p.chunks_per_tap, cc = chunk0 - tap * p.chunks_per_tap;
-                int r = tap / p.S, sx = tap - r * p.S;
                 for (int j = 0; j < n_chunks; ++j) {
+                    const short4 ta = p.tapA[phase * p.taps + tap];
                     if (leader)
-                        tma_load_4d(a_dst + (size_t)j * p.a_chunk_bytes, &tmX, &full[st], cc * p.cw, w0 + sx - p.pad,
-                                    h0 + r - p.pad, n0);
-                    if (++cc == p.chunks_per_tap) {
-                        cc = 0;
-                        if (++sx == p.S) { sx = 0; ++r; }
-                    }
+                        tma_load_5d(a_dst + (size_t)j * p.a_chunk_bytes, &tmX, &full[st], ta.x + cc * p.cw, w0 + ta.y, ta.z, h0 + ta.w, n0);
+                    if (++cc == p.chunks_per_tap) { cc = 0; ++tap; }
                 }
                 if (++st == (uint32_t)p.stages) { st = 0; phs ^= 1; }
                 if (++tw_i == p.tiles_w) {
@@ -140,21 +151,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (pb1 > pb0) {
             mbar_wait(tfull, 0);
             tc_fence_after();
+            float* slab = p.dw + (size_t)split * p.split_stride + (size_t)phase * p.phase_stride;
             for (int t = 0; t < mt_n; ++t) {
                 const int cj = chunk0 + t * p.cpt + row / p.cw;
                 const bool valid = cj < p.total_chunks;
                 const int tap = cj / p.chunks_per_tap, cc = cj - tap * p.chunks_per_tap;
                 const int ci = cc * p.cw + row % p.cw;
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + (uint32_t)t * p.Co_pad;
-                float* dst = p.dw + (size_t)tap * p.Ci + ci;
-                const size_t co_stride = (size_t)p.taps * p.Ci;
+                float* dst = slab + (size_t)tap * p.ci_total + ci;
                 for (int c0 = 0; c0 < p.Co_pad; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c0, v);
                     tmem_ld_wait();
                     if (valid) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)(c0 + i) * co_stride, __uint_as_float(v[i]));
+                        for (int i = 0; i < 16; ++i) dst[(size_t)(c0 + i) * p.co_stride] = __uint_as_float(v[i]);   // lanes = consecutive ci: coalesced
                     }
                 }
             }
@@ -168,62 +179,35 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
 }
 
-// fv_wgrad_ring.cu: sliding-window schedule for thin full-resolution layers; -1 when not eligible
-int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
-                          cudaStream_t stream);
+// fv_wgrad_ring.cu: sliding-window schedule for thin full-resolution layers
+int conv2d_wgrad_ring_splits(int N, int H, int W, int Ci, int Co_pad, int R, int S);     // 0 when not eligible
+int conv2d_wgrad_ring_try(const void* x, const void* dy, float* part, long long split_stride, int N, int H, int W, int Ci, int Co_pad, int R,
+                          int S, int pad, cudaStream_t stream);
 
-}  // namespace fv
-
-static int wgrad_chunk(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int dy_cs, int R, int S, int pad,
-                       void* stream);
-
-// Output-channel counts beyond one UMMA N (256) are handled in chunks of <= 256 channels of dY (channel stride Co_pad).
-extern "C" __attribute__((visibility("default"))) int fv_conv2d_wgrad(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad,
-                               int R, int S, int pad, void* stream) {
-    using namespace fv;
-    if (Co_pad <= 256) return wgrad_chunk(x, dy, dw_acc, N, H, W, Ci, Co_pad, Co_pad, R, S, pad, stream);
-    if (Co_pad % 64) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: Co_pad=%d > 256 must be a multiple of 64", Co_pad);
-    if (!x || !dy || !dw_acc) return fail(FV_ERR_ARG, "fv_conv2d_wgrad: null pointer");
-    for (int c0 = 0; c0 < Co_pad; c0 += 256) {
-        const int cn = Co_pad - c0 < 256 ? Co_pad - c0 : 256;
-        const int e = wgrad_chunk(x, static_cast<const char*>(dy) + (size_t)c0 * 2, dw_acc + (size_t)c0 * R * S * Ci, N, H, W, Ci, cn, Co_pad, R, S,
-                                  pad, stream);
-        if (e) return e;
+static int pick_pixel_block(int H, int W, int& pw, int& ph, int& pn) {
+    if (W >= 64) {
+        if (W % 64) return 1;
+        pw = 64; ph = 1; pn = 1;
+        return 0;
     }
-    return FV_OK;
+    if (W < 1 || (W & (W - 1))) return 1;
+    pw = W;
+    const int rest = 64 / W;
+    if (H >= rest) {
+        if (H % rest) return 1;
+        ph = rest; pn = 1;
+    } else {
+        if (H & (H - 1)) return 1;
+        ph = H; pn = rest / H;
+    }
+    return 0;
 }
 
-static int wgrad_chunk(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int dy_cs, int R, int S, int pad,
-                       void* stream) {
-    using namespace fv;
-    if (!x || !dy || !dw_acc) return fail(FV_ERR_ARG, "fv_conv2d_wgrad: null pointer");
-    if (Ci % 16 || Ci < 16 || (Ci > 64 && Ci % 64) || (Ci < 64 && Ci != 16 && Ci != 32))
-        return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: Ci=%d must be 16, 32 or a multiple of 64", Ci);
-    if (Co_pad % 16 || Co_pad < 16 || Co_pad > 256 || (Co_pad > 64 && Co_pad % 64) || (Co_pad < 64 && Co_pad != 16 && Co_pad != 32))
-        return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: Co_pad=%d must be 16, 32, 64, 128, 192 or 256", Co_pad);
-    if (R != S || (R != 1 && R != 3 && R != 5 && R != 7) || pad != (R - 1) / 2)
-        return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: only odd square filters with same padding");
-    if (dy_cs == Co_pad) {
-        const int rr = conv2d_wgrad_ring_try(x, dy, dw_acc, N, H, W, Ci, Co_pad, R, S, pad, (cudaStream_t)stream);
-        if (rr >= 0) return rr;
-    }
-    WgradParams p{};
-    p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co_pad = Co_pad; p.R = R; p.S = S; p.pad = pad; p.taps = R * S;
-    if (W >= 64) {
-        if (W % 64) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: W=%d must be a multiple of 64 or a power of two", W);
-        p.pw = 64; p.ph = 1; p.pn = 1;
-    } else {
-        if (W & (W - 1)) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: W=%d must be a power of two", W);
-        p.pw = W;
-        int rest = 64 / W;
-        if (H >= rest) {
-            if (H % rest) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: H=%d not divisible by %d", H, rest);
-            p.ph = rest; p.pn = 1;
-        } else {
-            if (H & (H - 1)) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: H=%d must be a power of two", H);
-            p.ph = H; p.pn = rest / H;
-        }
-    }
+// geometry of the generic kernel for one chunk of <= 256 output channels: M-tile groups and pixel splits
+static int plan_generic(int kind, int N, int H, int W, int Ci, int Co_pad, int taps, WgradParams& p) {
+    p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co_pad = Co_pad; p.taps = taps;
+    p.nph = kind == CONV_X2 ? 4 : 1;
+    if (pick_pixel_block(H, W, p.pw, p.ph, p.pn)) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: H=%d W=%d not tileable (W multiple of 64 or powers of two)", H, W);
     p.tiles_w = W / p.pw; p.tiles_h = H / p.ph; p.tiles_n = (N + p.pn - 1) / p.pn;
     p.num_pb = p.tiles_w * p.tiles_h * p.tiles_n;
     p.cw = Ci >= 64 ? 64 : Ci;
@@ -238,11 +222,47 @@ static int wgrad_chunk(const void* x, const void* dy, float* dw_acc, int N, int 
     p.groups = (p.mt_total + mt_max - 1) / mt_max;
     p.mt_per_group = (p.mt_total + p.groups - 1) / p.groups;
     p.groups = (p.mt_total + p.mt_per_group - 1) / p.mt_per_group;
-    int splits = num_sms() / p.groups;
+    int splits = num_sms() / (p.groups * p.nph);
     if (splits < 1) splits = 1;
     if (splits > p.num_pb) splits = p.num_pb;
     p.pb_per_split = (p.num_pb + splits - 1) / splits;
     p.splits = (p.num_pb + p.pb_per_split - 1) / p.pb_per_split;
+    return FV_OK;
+}
+
+static int check_channels(int Ci, int Co_pad) {
+    if (Ci % 16 || Ci < 16 || (Ci > 64 && Ci % 64) || (Ci < 64 && Ci != 16 && Ci != 32))
+        return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: Ci=%d must be 16, 32 or a multiple of 64", Ci);
+    if (Co_pad % 16 || Co_pad < 16 || (Co_pad > 64 && Co_pad % 64) || (Co_pad < 64 && Co_pad != 16 && Co_pad != 32))
+        return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: Co_pad=%d must be 16, 32 or a multiple of 64", Co_pad);
+    return FV_OK;
+}
+
+// number of partial slabs the launch for this shape writes (the caller allocates splits * slab elements and hands the count to
+// fv_wgrad_finish); kind: 0 same, 1 x2, 2 s2.  0 on unsupported shapes (the launch itself reports the reason).
+static int wgrad_splits(int kind, int N, int H, int W, int Ci, int Co_pad, int R, int S) {
+    if (check_channels(Ci, Co_pad)) return 0;
+    if (kind == CONV_SAME) {
+        const int rs = conv2d_wgrad_ring_splits(N, H, W, Ci, Co_pad, R, S);
+        if (rs > 0) return rs;
+    }
+    int splits = 0;
+    for (int c0 = 0; c0 < Co_pad; c0 += 256) {      // all chunks of a layer share the pixel split (same grid geometry)
+        WgradParams p{};
+        const int cn = Co_pad - c0 < 256 ? Co_pad - c0 : 256;
+        if (plan_generic(kind, N, H, W, Ci, cn, kind == CONV_X2 ? 4 : (kind == CONV_S2 ? 16 : R * S), p)) return 0;
+        if (p.splits > splits) splits = p.splits;
+    }
+    return splits;
+}
+
+static int wgrad_chunk(int kind, const void* x, const void* dy, float* part, long long split_stride, int N, int H, int W, int Ci, int Co_pad,
+                       int dy_cs, int dy_c0, int R, int S, int pad, int splits_expected, void* stream) {
+    WgradParams p{};
+    const int taps = kind == CONV_X2 ? 4 : (kind == CONV_S2 ? 16 : R * S);
+    if (int e = plan_generic(kind, N, H, W, Ci, Co_pad, taps, p)) return e;
+    if (p.splits != splits_expected) return fail(FV_ERR_INTERNAL, "fv_conv2d_wgrad: the channel chunks of this layer disagree on the pixel split");
+    if (p.nph * taps > 64) return fail(FV_ERR_INTERNAL, "fv_conv2d_wgrad: tap table overflow");
     p.a_chunk_bytes = 64 * p.cw * 2;
     p.b_chunk_bytes = 64 * p.bw * 2;
     p.a_bytes = p.mt_per_group * p.cpt * p.a_chunk_bytes;
@@ -255,20 +275,45 @@ static int wgrad_chunk(const void* x, const void* dy, float* dw_acc, int N, int 
     int cols = 32;
     while (cols < p.mt_per_group * Co_pad) cols <<= 1;
     p.tmem_cols = cols;
-    p.dw = dw_acc;
+    p.dw = part + (size_t)dy_c0 * taps * Ci;            // this chunk's output channels inside every slab / phase block
+    p.split_stride = split_stride;
+    p.phase_stride = (long long)dy_cs * taps * Ci;
+    p.co_stride = (long long)taps * Ci;
+    p.ci_total = Ci;
+    for (int ph = 0; ph < p.nph; ++ph) {
+        const int a = ph >> 1, b = ph & 1;
+        p.tapB[ph] = make_short4((short)(kind == CONV_X2 ? b * dy_cs + dy_c0 : dy_c0), 0, (short)(kind == CONV_X2 ? a : 0), 0);
+        for (int t = 0; t < taps; ++t) {
+            short4 ta = make_short4(0, 0, 0, 0);
+            if (kind == CONV_SAME) {
+                ta.y = (short)(t % S - pad); ta.w = (short)(t / S - pad);
+            } else if (kind == CONV_X2) {
+                const int u = t >> 1, v = t & 1;
+                ta.y = (short)(v - 1 + b); ta.w = (short)(u - 1 + a);
+            } else {
+                const int fr = (t >> 2) - 1, fc = (t & 3) - 1;
+                const int dh = fr < 0 ? -1 : fr / 2, dwc = fc < 0 ? -1 : fc / 2;
+                ta.w = (short)dh; ta.z = (short)(fr - 2 * dh);
+                ta.y = (short)dwc; ta.x = (short)((fc - 2 * dwc) * Ci);
+            }
+            p.tapA[ph * taps + t] = ta;
+        }
+    }
 
     CUtensorMap tmX, tmDY;
     {
-        uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[3] = {(uint64_t)Ci * 2, (uint64_t)W * Ci * 2, (uint64_t)H * W * Ci * 2};
-        uint32_t box[4] = {(uint32_t)p.cw, (uint32_t)p.pw, (uint32_t)p.ph, (uint32_t)p.pn};
-        if (int e = encode_tmap_bf16(&tmX, x, 4, dims, str, box, p.cw * 2)) return e;
+        const uint64_t fx = kind == CONV_S2 ? 2 : 1;       // X on the fine grid (S2): the 5-D parity view
+        uint64_t dims[5] = {(uint64_t)Ci * fx, (uint64_t)W, fx, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {(uint64_t)Ci * fx * 2, (uint64_t)W * fx * Ci * 2, (uint64_t)W * fx * Ci * 2 * fx, (uint64_t)H * fx * W * fx * Ci * 2};
+        uint32_t box[5] = {(uint32_t)p.cw, (uint32_t)p.pw, 1, (uint32_t)p.ph, (uint32_t)p.pn};
+        if (int e = encode_tmap_bf16(&tmX, x, 5, dims, str, box, p.cw * 2)) return e;
     }
     {
-        uint64_t dims[4] = {(uint64_t)Co_pad, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[3] = {(uint64_t)dy_cs * 2, (uint64_t)W * dy_cs * 2, (uint64_t)H * W * dy_cs * 2};
-        uint32_t box[4] = {(uint32_t)p.bw, (uint32_t)p.pw, (uint32_t)p.ph, (uint32_t)p.pn};
-        if (int e = encode_tmap_bf16(&tmDY, dy, 4, dims, str, box, p.bw * 2)) return e;
+        const uint64_t fy = kind == CONV_X2 ? 2 : 1;       // dY on the fine grid (X2)
+        uint64_t dims[5] = {(uint64_t)dy_cs * fy, (uint64_t)W, fy, (uint64_t)H, (uint64_t)N};
+        uint64_t str[4] = {(uint64_t)dy_cs * fy * 2, (uint64_t)W * fy * dy_cs * 2, (uint64_t)W * fy * dy_cs * 2 * fy, (uint64_t)H * fy * W * fy * dy_cs * 2};
+        uint32_t box[5] = {(uint32_t)p.bw, (uint32_t)p.pw, 1, (uint32_t)p.ph, (uint32_t)p.pn};
+        if (int e = encode_tmap_bf16(&tmDY, dy, 5, dims, str, box, p.bw * 2)) return e;
     }
     const size_t smem = (size_t)p.stages * p.stage_stride + 1024 + 512;
     static bool attr_set = false;
@@ -276,7 +321,57 @@ static int wgrad_chunk(const void* x, const void* dy, float* dw_acc, int N, int 
         FV_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    conv_wgrad_kernel<<<p.groups * p.splits, kWgradThreads, smem, (cudaStream_t)stream>>>(tmX, tmDY, p);
+    conv_wgrad_kernel<<<p.nph * p.groups * p.splits, kWgradThreads, smem, (cudaStream_t)stream>>>(tmX, tmDY, p);
     FV_LAUNCH_CHECK("conv_wgrad_kernel");
     return FV_OK;
+}
+
+static int wgrad_any(int kind, const void* x, const void* dy, float* part, int splits, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
+                     void* stream) {
+    if (!x || !dy || !part) return fail(FV_ERR_ARG, "fv_conv2d_wgrad: null pointer");
+    if (int e = check_channels(Ci, Co_pad)) return e;
+    if (kind == CONV_SAME && (R != S || (R != 1 && R != 3 && R != 5 && R != 7) || pad != (R - 1) / 2))
+        return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_wgrad: only odd square filters with same padding");
+    const int taps = kind == CONV_X2 ? 4 : (kind == CONV_S2 ? 16 : R * S);
+    const int nph = kind == CONV_X2 ? 4 : 1;
+    if (splits != wgrad_splits(kind, N, H, W, Ci, Co_pad, R, S))
+        return fail(FV_ERR_ARG, "fv_conv2d_wgrad: splits=%d does not match fv_conv2d_wgrad_splits() for this shape", splits);
+    const long long split_stride = (long long)nph * Co_pad * taps * Ci;
+    if (kind == CONV_SAME) {
+        const int rr = conv2d_wgrad_ring_try(x, dy, part, split_stride, N, H, W, Ci, Co_pad, R, S, pad, (cudaStream_t)stream);
+        if (rr >= 0) return rr;
+    }
+    // output-channel counts beyond one UMMA N (256) are handled in chunks of <= 256 channels of dY
+    for (int c0 = 0; c0 < Co_pad; c0 += 256) {
+        const int cn = Co_pad - c0 < 256 ? Co_pad - c0 : 256;
+        if (int e = wgrad_chunk(kind, x, dy, part, split_stride, N, H, W, Ci, cn, Co_pad, c0, R, S, pad, splits, stream)) return e;
+    }
+    return FV_OK;
+}
+
+}  // namespace fv
+
+using namespace fv;
+
+// kind: 0 = stride-1 "same" (R x S), 1 = x2 (up-sampling conv, four 2x2 phases), 2 = s2 (4x4 stride 2).  H, W: the tiling grid
+// (x2 / s2: coarse resolution).
+extern "C" __attribute__((visibility("default"))) int fv_conv2d_wgrad_splits(int kind, int N, int H, int W, int Ci, int Co_pad, int R, int S) {
+    return wgrad_splits(kind, N, H, W, Ci, Co_pad, R, S);
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_conv2d_wgrad(const void* x, const void* dy, float* part, int splits, int N, int H, int W, int Ci,
+                                                                    int Co_pad, int R, int S, int pad, void* stream) {
+    return wgrad_any(CONV_SAME, x, dy, part, splits, N, H, W, Ci, Co_pad, R, S, pad, stream);
+}
+
+// x [N,H,W,Ci] coarse, dy [N,2H,2W,Co_pad] fine -> part [splits][4 phases][Co_pad][4 taps][Ci]
+extern "C" __attribute__((visibility("default"))) int fv_conv2d_wgrad_x2(const void* x, const void* dy, float* part, int splits, int N, int H, int W, int Ci,
+                                                                       int Co_pad, void* stream) {
+    return wgrad_any(CONV_X2, x, dy, part, splits, N, H, W, Ci, Co_pad, 2, 2, 0, stream);
+}
+
+// x [N,2H,2W,Ci] fine, dy [N,H,W,Co_pad] coarse -> part [splits][Co_pad][16 taps][Ci]
+extern "C" __attribute__((visibility("default"))) int fv_conv2d_wgrad_s2(const void* x, const void* dy, float* part, int splits, int N, int H, int W, int Ci,
+                                                                       int Co_pad, void* stream) {
+    return wgrad_any(CONV_S2, x, dy, part, splits, N, H, W, Ci, Co_pad, 4, 4, 1, stream);
 }

@@ -8,8 +8,8 @@
 // pixels in a shared-memory ring: per segment ONE new slab and one dY tile are fetched.  The S taps of a filter row
 // are the same slab read through MN-major UMMA descriptors whose start address is shifted by s pixel rows; the
 // 128/cw taps stacked in one 128-row M tile are consecutive shifts, expressed by a leading-dimension byte offset of
-// one pixel row.  All R * ceil(S / (128/cw)) accumulators live in TMEM for the whole run; the epilogue adds them into
-// dW_acc[Co_pad][R*S][Ci] (fp32 atomics, one pass per CTA).
+// one pixel row.  All R * ceil(S / (128/cw)) accumulators live in TMEM for the whole run; the epilogue STORES them into this
+// CTA's slab of the workspace [CTAs][Co_pad][R*S][Ci]; fv_wgrad_finish adds the slabs in CTA order (reproducible).
 #include <cstdio>
 #include <cstdlib>
 
@@ -27,7 +27,8 @@ struct WRingParams {
     int b_off, b_slots, b_stride, b_tx;
     int bar_off, tmem_cols;
     float* dw;
-    // D[(tap t, ci), co] -> dw[ci + t * st + co * sb]: st = total input channels, sb = taps * st (dw already points at this
+    long long split_stride;   // elements between the slabs of consecutive CTAs
+    // D[(tap t, ci), co] -> dw[cta * split_stride + ci + t * st + co * sb]: st = total input channels, sb = taps * st (dw already points at this
     // launch's channel chunk when the wide operand is walked in chunks of 64)
     long long st, sb;
     long long* trace;
@@ -212,14 +213,14 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 const bool valid = s < p.S;
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + (uint32_t)mt * p.Co_pad;
                 const int t = r * p.S + s;
-                float* dst = p.dw + ci + (size_t)t * p.st;
+                float* dst = p.dw + (size_t)blockIdx.x * p.split_stride + ci + (size_t)t * p.st;
                 for (int c0 = 0; c0 < p.Co_pad; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + c0, v);
                     tmem_ld_wait();
                     if (valid) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)(c0 + i) * p.sb, __uint_as_float(v[i]));
+                        for (int i = 0; i < 16; ++i) dst[(size_t)(c0 + i) * p.sb] = __uint_as_float(v[i]);
                     }
                 }
             }
@@ -248,12 +249,25 @@ static int launch_wring(const CUtensorMap& tmX, const CUtensorMap& tmDY, const W
 // FV_OK after launching, -1 when not eligible (caller falls through to the generic wgrad kernel).
 // x / dy: NHWC operands of which Ci <= 64 / Co_pad <= 64 channels starting at the pointers are used; x_cs / dy_cs = their channel
 // strides in elements.  Output mapping: WRingParams.
-int conv2d_wgrad_ring_ex(const void* x, int x_cs, const void* dy, int dy_cs, float* dw_acc, long long st, long long sb, int N, int H,
-                         int W, int Ci, int Co_pad, int R, int S, int pad, cudaStream_t stream) {
-    if ((S != 3 && S != 5 && S != 7) || R != S || W % 64 || Ci > 64 || Co_pad > 64) return -1;
-    const int kPX = (W % 128 == 0) ? 128 : 64;
+static int wring_grid(int N, int H, int W, int kPX) {
+    const int num_blocks = N * (W / kPX) * H, sms = num_sms();
+    const int per = (num_blocks + sms - 1) / sms;
+    return (num_blocks + per - 1) / per;
+}
+static bool wring_shape_ok(int W, int Ci, int Co_pad, int R, int S) {
+    if ((S != 3 && S != 5 && S != 7) || R != S || W % 64 || Ci > 64 || Co_pad > 64) return false;
+    const int cpt = 128 / Ci, kPX = (W % 128 == 0) ? 128 : 64;
+    if (R * ((S + cpt - 1) / cpt) * Co_pad > 512) return false;
+    const int slab_stride = ((kPX + S - 1 + cpt) * Ci * 2 + 1023) & ~1023, b_stride = (kPX * Co_pad * 2 + 1023) & ~1023;
+    const size_t smem = (size_t)(R + 3) * slab_stride + 4 * b_stride + (2 * (R + 3) + 2 * 4 + 2) * 8 + 16 + 1024 + 64;
     const char* env = getenv("FV_WGRAD_RING");
-    if (env && atoi(env) == 0) return -1;
+    return smem <= 225 * 1024 && !(env && atoi(env) == 0);
+}
+
+int conv2d_wgrad_ring_ex(const void* x, int x_cs, const void* dy, int dy_cs, float* dw_acc, long long split_stride, long long st, long long sb, int N,
+                         int H, int W, int Ci, int Co_pad, int R, int S, int pad, cudaStream_t stream) {
+    if (!wring_shape_ok(W, Ci, Co_pad, R, S)) return -1;
+    const int kPX = (W % 128 == 0) ? 128 : 64;
     WRingParams p{};
     p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co_pad = Co_pad; p.R = R; p.S = S; p.pad = pad; p.taps = R * S;
     p.cpt = 128 / Ci;
@@ -278,6 +292,7 @@ int conv2d_wgrad_ring_ex(const void* x, int x_cs, const void* dy, int dy_cs, flo
     while (cols < p.mt_total * Co_pad) cols <<= 1;
     p.tmem_cols = cols;
     p.dw = dw_acc;
+    p.split_stride = split_stride;
     p.st = st; p.sb = sb;
     p.trace = trace_ptr();
     const int sms = num_sms();
@@ -306,32 +321,44 @@ int conv2d_wgrad_ring_ex(const void* x, int x_cs, const void* dy, int dy_cs, flo
 #undef FV_WR2
 }
 
-// dW_acc[Co_pad][R*S][Ci] += ...   Ring schedule whenever one of the two channel counts is <= 64: the other operand is walked
-// in chunks of 64 channels, one launch per chunk (each pass re-reads the narrow operand).
-int conv2d_wgrad_ring_try(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
-                          cudaStream_t stream) {
-    const long long taps = (long long)R * S;
-    if (Ci <= 64 && Co_pad <= 64)
-        return conv2d_wgrad_ring_ex(x, Ci, dy, Co_pad, dw_acc, Ci, taps * Ci, N, H, W, Ci, Co_pad, R, S, pad, stream);
+// Which schedule a shape gets: 1 both channel counts <= 64, 2 dY walked in chunks of 64, 3 x walked in chunks of 64, 0 none.
+static int wring_mode(int W, int Ci, int Co_pad, int R, int S) {
+    if (Ci <= 64 && Co_pad <= 64) return wring_shape_ok(W, Ci, Co_pad, R, S) ? 1 : 0;
     const char* env = getenv("FV_WGRAD_RING_WIDE");
-    if (env && atoi(env) == 0) return -1;
-    if (Ci <= 64 && Co_pad % 64 == 0 && Co_pad <= 256) {                    // dY in chunks of 64 channels
+    if (env && atoi(env) == 0) return 0;
+    if (Ci <= 64 && Co_pad % 64 == 0 && Co_pad <= 256) return wring_shape_ok(W, Ci, 64, R, S) ? 2 : 0;
+    if (Co_pad <= 64 && Ci % 64 == 0 && Ci <= 256) return wring_shape_ok(W, 64, Co_pad, R, S) ? 3 : 0;
+    return 0;
+}
+
+// number of partial slabs (= CTAs) the ring schedule writes for this shape; 0 when it does not take the shape
+int conv2d_wgrad_ring_splits(int N, int H, int W, int Ci, int Co_pad, int R, int S) {
+    if (!wring_mode(W, Ci, Co_pad, R, S)) return 0;
+    return wring_grid(N, H, W, (W % 128 == 0) ? 128 : 64);
+}
+
+// part[cta][Co_pad][R*S][Ci] = this CTA's share.  Ring schedule whenever one of the two channel counts is <= 64: the other
+// operand is walked in chunks of 64 channels, one launch per chunk (each pass re-reads the narrow operand).
+int conv2d_wgrad_ring_try(const void* x, const void* dy, float* part, long long split_stride, int N, int H, int W, int Ci, int Co_pad, int R, int S,
+                          int pad, cudaStream_t stream) {
+    const long long taps = (long long)R * S;
+    const int mode = wring_mode(W, Ci, Co_pad, R, S);
+    if (mode == 0) return -1;
+    if (mode == 1) return conv2d_wgrad_ring_ex(x, Ci, dy, Co_pad, part, split_stride, Ci, taps * Ci, N, H, W, Ci, Co_pad, R, S, pad, stream);
+    if (mode == 2) {                                                         // dY in chunks of 64 channels
         for (int c0 = 0; c0 < Co_pad; c0 += 64) {
-            const int e = conv2d_wgrad_ring_ex(x, Ci, static_cast<const char*>(dy) + (size_t)c0 * 2, Co_pad, dw_acc + (size_t)c0 * taps * Ci, Ci,
-                                               taps * Ci, N, H, W, Ci, 64, R, S, pad, stream);
-            if (e) return e;                                                 // -1 on the first chunk: nothing launched yet
+            const int e = conv2d_wgrad_ring_ex(x, Ci, static_cast<const char*>(dy) + (size_t)c0 * 2, Co_pad, part + (size_t)c0 * taps * Ci, split_stride,
+                                               Ci, taps * Ci, N, H, W, Ci, 64, R, S, pad, stream);
+            if (e) return e < 0 ? fail(FV_ERR_INTERNAL, "fv_conv2d_wgrad: ring schedule refused a chunk it had accepted") : e;
         }
         return FV_OK;
     }
-    if (Co_pad <= 64 && Ci % 64 == 0 && Ci <= 256) {                        // x in chunks of 64 channels
-        for (int c0 = 0; c0 < Ci; c0 += 64) {
-            const int e = conv2d_wgrad_ring_ex(static_cast<const char*>(x) + (size_t)c0 * 2, Ci, dy, Co_pad, dw_acc + c0, Ci, taps * Ci, N, H, W,
-                                               64, Co_pad, R, S, pad, stream);
-            if (e) return e;
-        }
-        return FV_OK;
+    for (int c0 = 0; c0 < Ci; c0 += 64) {                                    // x in chunks of 64 channels
+        const int e = conv2d_wgrad_ring_ex(static_cast<const char*>(x) + (size_t)c0 * 2, Ci, dy, Co_pad, part + c0, split_stride, Ci, taps * Ci, N, H, W,
+                                           64, Co_pad, R, S, pad, stream);
+        if (e) return e < 0 ? fail(FV_ERR_INTERNAL, "fv_conv2d_wgrad: ring schedule refused a chunk it had accepted") : e;
     }
-    return -1;
+    return FV_OK;
 }
 
 }  // namespace fv

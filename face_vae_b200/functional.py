@@ -121,24 +121,63 @@ def _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, e
     return ops.bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, eps), count
 
 
+GEOM_SAME, GEOM_UP = 0, 1
+
+
+def _conv_forward(geom, x, weight, bias, ksize, want_stats, residual=None):
+    """-> (y, sums | None, operand for the data gradient).  GEOM_UP: nearest 2x up-sampling + 3x3 conv as four 2x2 phase
+    convolutions on the coarse input (csrc/fv_conv.cu, X2) -- the up-sampled tensor never exists."""
+    co, ci = weight.shape[0], weight.shape[1]
+    if geom == GEOM_UP:
+        wx2, ws2 = ops.weight_prep_up(weight, True, x.requires_grad)
+        if want_stats:
+            y, sums = ops.conv2d_x2(x, wx2, bias, co, OUT_NHWC_BF16, (ci, co), want_stats=True)
+        else:
+            y, sums = ops.conv2d_x2(x, wx2, bias, co, OUT_NHWC_BF16, (ci, co)), None
+        return y, sums, ws2
+    wf, wd = ops.weight_prep(weight, True, x.requires_grad)
+    if want_stats:      # the conv epilogue also produces the batch-norm sums of y where that is hidden (no second pass over y)
+        y, sums = ops.conv2d(x, wf, bias, co, ksize, residual, OUT_NHWC_BF16, (ci, co), want_stats=True)
+    else:
+        y, sums = ops.conv2d(x, wf, bias, co, ksize, residual, OUT_NHWC_BF16, (ci, co)), None
+    return y, sums, wd
+
+
+def _conv_backward(geom, x, dy, weight, wd, ksize, need_dx):
+    """-> (dx | None, dw) for y = conv(x, weight) in geometry ``geom``; dy: NHWC bf16 gradient of y."""
+    co, ci = weight.shape[0], weight.shape[1]
+    if geom == GEOM_UP:
+        dw = ops.wgrad_finish_up(ops.conv2d_wgrad_x2(x, dy, (ci, co)), co, ci)
+        dx = None
+        if need_dx:
+            if wd is None:
+                _, wd = ops.weight_prep_up(weight, False, True)
+            # 4x4 stride-2 convolution of dY with the summed, mirrored taps: the 2x2 sum of the up-sampling backward is inside
+            dx = ops.conv2d_s2(dy, wd, None, x.shape[3], OUT_NHWC_BF16, (co, ci), alg_taps=36)
+        return dx, dw
+    dw = ops.wgrad_finish(ops.conv2d_wgrad(x, dy, ksize, (ci, co)), co, ci, ksize)
+    dx = None
+    if need_dx:
+        if wd is None:
+            _, wd = ops.weight_prep(weight, False, True)
+        dx = ops.conv2d(dy, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
+    return dx, dw
+
+
 class ConvBNAct(torch.autograd.Function):
     """Pattern "CNA" of _ConvBlock (reference modules.py:8-42) plus the block's own pooling (DownBlock2D,
-    modules.py:59-70) or the *next* block's up-sampling (UpBlock2D, modules.py:78-89) folded into the norm+act pass.
+    modules.py:59-70) folded into the norm+act pass, or (``geom`` = GEOM_UP) UpBlock2D's up-sampling folded into the
+    convolution itself (modules.py:78-89).
 
     x: NHWC bf16 [N,H,W,Ci_pad].  Returns NHWC (bf16 / fp32) or NCHW fp32 per ``out_nchw_f32``.
     """
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, ksize, post_mode, act, training,
-                out_nchw_f32, momentum, eps):
+                out_nchw_f32, momentum, eps, geom=GEOM_SAME):
         co, ci = weight.shape[0], weight.shape[1]
-        # both filter operands come from one pass over the fp32 master weights (the rotated copy is kept for backward)
-        wf, wd = ops.weight_prep(weight, True, x.requires_grad)
-        sums = None
-        if training and _FUSE_STATS:      # the conv epilogue also produces the batch-norm sums of y (no second pass over y)
-            y, sums = ops.conv2d(x, wf, bias, co, ksize, None, OUT_NHWC_BF16, (ci, co), want_stats=True)
-        else:
-            y = ops.conv2d(x, wf, bias, co, ksize, None, OUT_NHWC_BF16, (ci, co))
+        # both filter operands come from one pass over the fp32 master weights (the dgrad operand is kept for backward)
+        y, sums, wd = _conv_forward(geom, x, weight, bias, ksize, training and _FUSE_STATS)
         out_dtype = torch.float32 if out_nchw_f32 else torch.bfloat16
         if _fin_fused(training):
             count = y.shape[0] * y.shape[1] * y.shape[2]
@@ -148,14 +187,14 @@ class ConvBNAct(torch.autograd.Function):
             stat, count = _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, eps, sums)
             out = ops.bn_act_fwd(y, stat, post_mode, act, out_dtype, out_nchw_f32)
         ctx.save_for_backward(x, y, stat, weight, wd)
-        ctx.cfg = (ksize, post_mode, act, training, out_nchw_f32, count, co, ci)
+        ctx.cfg = (ksize, post_mode, act, training, out_nchw_f32, count, co, ci, geom)
         ctx.has_bias = bias is not None
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, y, stat, weight, wd = ctx.saved_tensors
-        ksize, post_mode, act, training, out_nchw_f32, count, co, ci = ctx.cfg
+        ksize, post_mode, act, training, out_nchw_f32, count, co, ci, geom = ctx.cfg
         g = g.contiguous()
         c = y.shape[3]
         # eval mode: running statistics are constants, dy = scale * dz, no coupling terms
@@ -165,18 +204,12 @@ class ConvBNAct(torch.autograd.Function):
         else:
             dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
             dy = ops.bn_act_bwd_apply(y, g, stat, coef, post_mode, act, None, out_nchw_f32)
-        acc = ops.conv2d_wgrad(x, dy, ksize, (ci, co))
-        dw = ops.wgrad_finish(acc, co, ci, ksize)
+        dx, dw = _conv_backward(geom, x, dy, weight, wd, ksize, ctx.needs_input_grad[0])
         db = None
         if ctx.has_bias:
             # a bias in front of a (training-mode) batch norm has zero gradient analytically; eval mode: real sum
             db = torch.zeros((co,), device=x.device, dtype=torch.float32) if training else ops.colsum(dy)[:co].clone()
-        dx = None
-        if ctx.needs_input_grad[0]:
-            if wd is None:
-                _, wd = ops.weight_prep(weight, False, True)
-            dx = ops.conv2d(dy, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
-        return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None, None
+        return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
 
 
 class PointwiseBNAct(torch.autograd.Function):
@@ -249,9 +282,7 @@ class BNActConv(torch.autograd.Function):
         ksize, act, training, count, co, ci = ctx.cfg
         g = g.contiguous()
         db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
-        acc = ops.conv2d_wgrad(a, g, ksize, (ci, co))
-        dw = ops.wgrad_finish(acc, co, ci, ksize)
-        da = ops.conv2d(g, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
+        da, dw = _conv_backward(GEOM_SAME, a, g, weight, wd, ksize, True)
         c = x.shape[3]
         s_local = ops.bn_act_bwd_reduce(x, da, stat, MODE_NONE, act)
         if _fin_fused(training):
@@ -293,13 +324,7 @@ class ConvOnly(torch.autograd.Function):
             g = g.to(torch.bfloat16)
         g = g.contiguous()
         db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
-        acc = ops.conv2d_wgrad(x, g, ksize, (ci, co))
-        dw = ops.wgrad_finish(acc, co, ci, ksize)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            if wd is None:
-                _, wd = ops.weight_prep(weight, False, True)
-            dx = ops.conv2d(g, wd, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
+        dx, dw = _conv_backward(GEOM_SAME, x, g, weight, wd, ksize, ctx.needs_input_grad[0])
         return dx, dw, db, None, None
 
 
@@ -445,11 +470,5 @@ class ConvSigmoidRecon(torch.autograd.Function):
         d, weight, gn, wd = ctx.saved_tensors
         g = ops.scale(gn, gl, 1.0)
         db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
-        acc = ops.conv2d_wgrad(d, g, ksize, (ci, co))
-        dw = ops.wgrad_finish(acc, co, ci, ksize)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            if wd is None:
-                _, wd = ops.weight_prep(weight, False, True)
-            dx = ops.conv2d(g, wd, None, d.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
+        dx, dw = _conv_backward(GEOM_SAME, d, g, weight, wd, ksize, ctx.needs_input_grad[0])
         return dx, dw, db, None, None

@@ -58,6 +58,7 @@ class FaceVAE(nn.Module):
         self.res = nn.Sequential(*[ResBlock2D(u[0], use_weight_norm) for _ in range(n_res)])
         self.up = nn.Sequential(*[UpBlock2D(u[i], u[i + 1], use_weight_norm) for i in range(len(u) - 1)])
         self.out_conv = Conv2d(u[-1], 3, 7, 1, 3)
+        self.out_conv.prep_kind = -1 if u[-1] == 32 else 0     # the tap-folded out_conv kernels prepare their own operands
         self.n_down = len(d) - 2
 
     def latent_dim(self, h: int, w: int) -> int:
@@ -83,11 +84,8 @@ class FaceVAE(nn.Module):
         t = Fn.ConvOnly.apply(t, self.mid_conv.weight, self.mid_conv.bias, 1, OUT_NHWC_BF16)
         for blk in self.res:
             t = blk.forward_nhwc(t)
-        t = Fn.Upsample2x.apply(t)
-        n_up = len(self.up)
-        for i, blk in enumerate(self.up):
-            # this block's norm+act pass also writes the 2x up-sampled tensor the next UpBlock2D starts with
-            t = blk.forward_nhwc(t, pre_upsampled=True, post_mode=MODE_UP if i + 1 < n_up else MODE_NONE)
+        for blk in self.up:
+            t = blk.forward_nhwc(t)        # up-sampling folded into the convolution: no 4x tensor between the blocks
         return t
 
     # -- public ---------------------------------------------------------------------------------------------

@@ -130,13 +130,20 @@ class ConvBlock2D(nn.Module):
     def norm(self) -> _BatchNormParams:
         return self.layers[self.pattern.index("N")]
 
-    def forward_nhwc(self, x, post_mode=MODE_NONE, residual=None, out_nchw_f32=False):
+    def forward_nhwc(self, x, post_mode=MODE_NONE, residual=None, out_nchw_f32=False, upsample_input=False):
+        """``upsample_input``: the conv reads the nearest-2x up-sampled x (UpBlock2D) -- computed on the coarse grid by the
+        phase-decomposed kernel, the up-sampled tensor is never written."""
         conv, bn = self.conv, self.norm
         if self.training:
             ops.bump_counter(bn.num_batches_tracked)
         if self.pattern in ("CNA", "CN"):
+            geom = Fn.GEOM_UP if upsample_input else Fn.GEOM_SAME
+            if upsample_input and self.kernel_size != 3:
+                raise NotImplementedError("the fused up-sampling convolution is 3x3 (UpBlock2D)")
             return Fn.ConvBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                      self.kernel_size, post_mode, self.act, self.training, out_nchw_f32, bn.momentum, bn.eps)
+                                      self.kernel_size, post_mode, self.act, self.training, out_nchw_f32, bn.momentum, bn.eps, geom)
+        if upsample_input:
+            raise NotImplementedError("NAC blocks have no fused up-sampling")
         if post_mode != MODE_NONE or out_nchw_f32:
             raise NotImplementedError("NAC blocks have no fused pool/upsample")
         return Fn.BNActConv.apply(x, residual, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
@@ -170,18 +177,20 @@ class DownBlock2D(nn.Module):
 
 
 class UpBlock2D(nn.Module):
-    """reference modules.py:78-89: Upsample(x2, nearest) -> CNA 3x3 s1 p1.  ``forward_nhwc(pre_upsampled=True)`` lets
-    a producer that already wrote the 2x-replicated tensor (fused into its own norm+act pass) skip the copy."""
+    """reference modules.py:78-89: Upsample(x2, nearest) -> CNA 3x3 s1 p1.  The up-sampling is folded into the convolution:
+    every output pixel (2i + a, 2j + b) sees a 2x2 neighbourhood of the coarse input, so the layer runs as four 2x2 phase
+    convolutions on the coarse grid (csrc/fv_conv.cu, X2 geometry) and the 4x larger tensor is never written or re-read;
+    backward likewise (data gradient = a 4x4 stride-2 convolution of dY, which contains the 2x2 sum of the up-sampling
+    backward).  ``pre_upsampled=True`` takes an input that already is at the output resolution (plain CNA block)."""
 
     def __init__(self, in_channels, out_channels, use_weight_norm):
         super().__init__()
         self.layers = nn.Sequential(_Up(), ConvBlock2D("CNA", in_channels, out_channels, 3, 1, 1, use_weight_norm))
+        self.layers[1].conv.prep_kind = ops.PREP_UP        # ops.step_scope prepares the phase filters for this weight
         self.out_channels = out_channels
 
     def forward_nhwc(self, x, pre_upsampled=False, post_mode=MODE_NONE):
-        if not pre_upsampled:
-            x = Fn.Upsample2x.apply(x)
-        return self.layers[1].forward_nhwc(x, post_mode)
+        return self.layers[1].forward_nhwc(x, post_mode, upsample_input=not pre_upsampled)
 
     def forward(self, x):
         return as_nchw(self.forward_nhwc(as_nhwc(x)), self.out_channels)

@@ -53,46 +53,24 @@ def _chk(t: torch.Tensor, name: str, dtype=None):
     return t
 
 
+# ------------------------------------------------------------------------------------------------ reduction workspace
+_red_ws_cache = {}
+
+
+def _red_ws() -> int:
+    """Device pointer of the reduction scratch for the CURRENT stream (include/facevae_b200.h, `red_ws`): one buffer per
+    (device, stream), zero-initialised once -- the kernels leave its ticket words zero again.  Kernels on one stream run in
+    order, so they can share it; another stream gets its own."""
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    buf = _red_ws_cache.get(key)
+    if buf is None:
+        buf = torch.zeros((int(_lib.load().fv_reduce_ws_bytes()),), dtype=torch.uint8, device="cuda")
+        _red_ws_cache[key] = buf
+    return buf.data_ptr()
+
+
 # ------------------------------------------------------------------------------------------------ per-step scope
-class _ZeroArena:
-    """Caller-zeroed scratch (statistic sums, weight-gradient accumulators, loss sums) for one train step: one buffer,
-    ONE memset at the start of the step, bump-allocated 256-byte-aligned slices -- instead of ~45 torch.zeros launches.
-    Slices are only valid until the next step starts; everything the kernels accumulate there is consumed inside the step."""
-
-    def __init__(self):
-        self.buf = None
-        self.offset = 0
-        self.need = 0
-        self.active = False
-
-    def begin(self, device):
-        want = max(self.need, 1 << 20)
-        if self.buf is None or self.buf.device != device or self.buf.numel() < want:
-            self.buf = torch.empty((int(want * 1.25) + 4096,), dtype=torch.uint8, device=device)
-        self.buf.zero_()          # the whole buffer: slices of a later, larger step must be clean as well (one memset)
-        self.offset = 0
-        self.need = 0
-        self.active = True
-
-    def take(self, shape, dtype, device):
-        n = 1
-        for d in shape:
-            n *= int(d)
-        nbytes = (n * torch.empty((), dtype=dtype).element_size() + 255) // 256 * 256
-        self.need += nbytes
-        if not self.active or self.buf is None or self.buf.device != device or self.offset + nbytes > self.buf.numel():
-            return None
-        view = self.buf[self.offset:self.offset + nbytes].view(dtype)[:n].view(shape)
-        self.offset += nbytes
-        return view
-
-
-_arena = _ZeroArena()
-
-
-def _zeros(shape, device, dtype=torch.float32) -> torch.Tensor:
-    t = _arena.take(tuple(shape), dtype, device) if _arena.active else None
-    return torch.zeros(shape, device=device, dtype=dtype) if t is None else t
+PREP_PLAIN, PREP_UP, PREP_S2 = 0, 1, 2      # fv_prep_desc.kind
 
 
 class _PrepCache:
@@ -100,30 +78,45 @@ class _PrepCache:
 
     def __init__(self):
         self.key = None
-        self.map = {}
+        self.map = {}          # plain convolutions: weight ptr -> (wf, wd)
+        self.map_up = {}       # up-sampling 3x3 convolutions: weight ptr -> (wx2, ws2)
+        self.map_s2 = {}       # 4x4 stride-2 convolutions: weight ptr -> (wf, wx2)
         self.table = None
         self.max_items = 0
         self.valid = False
 
     def build(self, weights):
         import numpy as np
-        dev = weights[0].device
-        rec = np.zeros((len(weights),), dtype=np.dtype([("w", "<u8"), ("wf", "<u8"), ("wd", "<u8"), ("dims", "<i4", (6,))]))
-        self.map = {}
+        dev = weights[0][0].device
+        rec = np.zeros((len(weights),), dtype=np.dtype([("w", "<u8"), ("o0", "<u8"), ("o1", "<u8"), ("dims", "<i4", (6,)),
+                                                        ("kind", "<i4"), ("reserved", "<i4")]))
+        self.map, self.map_up, self.map_s2 = {}, {}, {}
         self.max_items = 0
-        for i, w in enumerate(weights):
+        for i, (w, kind) in enumerate(weights):
             co, ci, r, s_ = w.shape
             cop, cip = pad_channels(co), pad_channels(ci)
-            wf = torch.empty((cop, r * s_, cip), device=dev, dtype=torch.bfloat16)
-            wd = torch.empty((cip, r * s_, cop), device=dev, dtype=torch.bfloat16)
-            rec[i] = (w.data_ptr(), wf.data_ptr(), wd.data_ptr(), (co, ci, r, s_, cop, cip))
-            self.map[w.data_ptr()] = (wf, wd)
-            self.max_items = max(self.max_items, cop * cip * r * s_)
+            if kind == PREP_UP:
+                o0 = torch.empty((4, cop, 4, cip), device=dev, dtype=torch.bfloat16)
+                o1 = torch.empty((cip, 16, cop), device=dev, dtype=torch.bfloat16)
+                self.map_up[w.data_ptr()] = (o0, o1)
+                items = 16 * cop * cip
+            elif kind == PREP_S2:
+                o0 = torch.empty((cop, 16, cip), device=dev, dtype=torch.bfloat16)
+                o1 = torch.empty((4, cip, 4, cop), device=dev, dtype=torch.bfloat16)
+                self.map_s2[w.data_ptr()] = (o0, o1)
+                items = 16 * cop * cip
+            else:
+                o0 = torch.empty((cop, r * s_, cip), device=dev, dtype=torch.bfloat16)
+                o1 = torch.empty((cip, r * s_, cop), device=dev, dtype=torch.bfloat16)
+                self.map[w.data_ptr()] = (o0, o1)
+                items = cop * cip * r * s_
+            rec[i] = (w.data_ptr(), o0.data_ptr(), o1.data_ptr(), (co, ci, r, s_, cop, cip), kind, 0)
+            self.max_items = max(self.max_items, items)
         self.table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)
-        self.key = tuple(w.data_ptr() for w in weights)
+        self.key = tuple((w.data_ptr(), kind) for w, kind in weights)
 
     def run(self, weights):
-        key = tuple(w.data_ptr() for w in weights)
+        key = tuple((w.data_ptr(), kind) for w, kind in weights)
         if key != self.key:
             self.build(weights)
         call("fv_weight_prep_batched", self.table.data_ptr(), len(weights), self.max_items, _stream())
@@ -131,39 +124,51 @@ class _PrepCache:
 
 
 _prep = _PrepCache()
-
-
+_scope_active = False
 _pending_counters = []
 
 
 def bump_counter(t: torch.Tensor) -> None:
     """num_batches_tracked += 1: inside a step scope the increments of all layers are issued as ONE multi-tensor launch."""
-    if _arena.active:
+    if _scope_active:
         _pending_counters.append(t)
     else:
         t += 1
 
 
 class step_scope:
-    """``with ops.step_scope(model):`` around forward + backward of one train step (VAETrainer does this): the scratch
-    the kernels accumulate into comes from one arena zeroed by a single memset, and the bf16 filter operands of all
-    convolutions come from one batched launch.  Outside the scope every op allocates / prepares for itself."""
+    """``with ops.step_scope(model):`` around forward + backward of one train step (VAETrainer does this): the bf16 filter
+    operands of all convolutions come from ONE batched launch (a device table of layer descriptors; modules tag their
+    4-d weights with ``prep_kind``: plain, up-sampling 3x3, 4x4 stride-2) and the batch counters are bumped by one
+    multi-tensor launch.  Outside the scope every op prepares for itself.  (Round 1 also zeroed an arena of accumulators
+    here; every reduction now WRITES its result -- fv_reduce.cuh -- so nothing needs zeroing.)"""
 
     def __init__(self, module: Optional[torch.nn.Module] = None):
         self.module = module
 
     def __enter__(self):
+        global _scope_active
         weights = []
         if self.module is not None:
-            weights = [p for p in self.module.parameters() if p.dim() == 4 and p.is_cuda and p.dtype == torch.float32
-                       and p.is_contiguous()]
+            for m in self.module.modules():
+                w = getattr(m, "weight", None)
+                if isinstance(w, torch.nn.Parameter) and w.dim() == 4 and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous():
+                    kind = int(getattr(m, "prep_kind", PREP_PLAIN))
+                    if kind < 0:                 # the module prepares its own operands (tap-folded out_conv)
+                        continue
+                    if kind == PREP_UP and tuple(w.shape[2:]) != (3, 3):
+                        kind = PREP_PLAIN
+                    if kind == PREP_S2 and tuple(w.shape[2:]) != (4, 4):
+                        continue
+                    weights.append((w, kind))
         if weights:
-            _arena.begin(weights[0].device)
             _prep.run(weights)
+        _scope_active = True
         return self
 
     def __exit__(self, *exc):
-        _arena.active = False
+        global _scope_active
+        _scope_active = False
         _prep.valid = False
         if _pending_counters:
             torch._foreach_add_(list(_pending_counters), 1)
@@ -249,9 +254,9 @@ def conv2d(x: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], co: 
              cop, ksize, ksize, (ksize - 1) // 2, _stream(), meta=_conv_meta(n, h, w, ci, cop, ksize, real_dims))
         return y, bn_stats(y)
     if want_stats:
-        sums = _zeros((2 * cop,), x.device)
+        sums = torch.empty((2 * cop,), device=x.device, dtype=torch.float32)
         call("fv_conv2d_stats", x.data_ptr(), wf.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), out_mode, n, h, w, ci, co,
-             cop, ksize, ksize, (ksize - 1) // 2, sums.data_ptr(), _stream(), meta=_conv_meta(n, h, w, ci, cop, ksize, real_dims))
+             cop, ksize, ksize, (ksize - 1) // 2, sums.data_ptr(), _red_ws(), _stream(), meta=_conv_meta(n, h, w, ci, cop, ksize, real_dims))
         return y, sums
     call("fv_conv2d", x.data_ptr(), wf.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), out_mode, n, h, w, ci, co,
          cop, ksize, ksize, (ksize - 1) // 2, _stream(), meta=_conv_meta(n, h, w, ci, cop, ksize, real_dims))
@@ -259,33 +264,168 @@ def conv2d(x: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], co: 
 
 
 def conv2d_wgrad(x: torch.Tensor, dy: torch.Tensor, ksize: int, real_dims=None) -> torch.Tensor:
-    """x NHWC bf16 [N,H,W,Ci], dy NHWC bf16 [N,H,W,Co_pad] -> dw_acc fp32 [Co_pad, k*k, Ci]."""
+    """x NHWC bf16 [N,H,W,Ci], dy NHWC bf16 [N,H,W,Co_pad] -> partial slabs fp32 [splits, Co_pad, k*k, Ci] (one per pixel split
+    of the kernel; ``wgrad_finish`` adds them in a fixed order)."""
     _chk(x, "x", torch.bfloat16)
     _chk(dy, "dy", torch.bfloat16)
     n, h, w, ci = x.shape
     cop = dy.shape[3]
     if tuple(dy.shape[:3]) != (n, h, w):
         raise _lib.FaceVaeError("conv2d_wgrad: x / dy shape mismatch")
-    acc = _zeros((cop, ksize * ksize, ci), x.device)
-    call("fv_conv2d_wgrad", x.data_ptr(), dy.data_ptr(), acc.data_ptr(), n, h, w, ci, cop, ksize, ksize,
+    splits = int(_lib.load().fv_conv2d_wgrad_splits(0, n, h, w, ci, cop, ksize, ksize))
+    part = torch.empty((max(splits, 1), cop, ksize * ksize, ci), device=x.device, dtype=torch.float32)
+    call("fv_conv2d_wgrad", x.data_ptr(), dy.data_ptr(), part.data_ptr(), splits, n, h, w, ci, cop, ksize, ksize,
          (ksize - 1) // 2, _stream(), meta=_conv_meta(n, h, w, ci, cop, ksize, real_dims))
-    return acc
+    return part
 
 
-def wgrad_finish(acc: torch.Tensor, co: int, ci: int, ksize: int, grad: Optional[torch.Tensor] = None) -> torch.Tensor:
+def wgrad_finish(part: torch.Tensor, co: int, ci: int, ksize: int, grad: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """partial slabs [splits, Co_pad, k*k, Ci_pad] -> nn.Conv2d layout gradient [co, ci, k, k] fp32."""
     accumulate = grad is not None
     if grad is None:
-        grad = torch.empty((co, ci, ksize, ksize), device=acc.device, dtype=torch.float32)
-    call("fv_wgrad_finish", acc.data_ptr(), _chk(grad, "grad", torch.float32).data_ptr(), co, ci, ksize, ksize,
-         acc.shape[2], int(accumulate), _stream())
+        grad = torch.empty((co, ci, ksize, ksize), device=part.device, dtype=torch.float32)
+    call("fv_wgrad_finish", part.data_ptr(), part.shape[0], _chk(grad, "grad", torch.float32).data_ptr(), co, ci, ksize, ksize,
+         part.shape[1], part.shape[3], int(accumulate), _stream())
     return grad
+
+
+# ------------------------------------------------------------------------------------------------ up-sampling / stride-2 convolutions
+def _conv_meta_x2(n, h, w, ci, cop, real_dims, exec_taps, alg_taps):
+    """(h, w) = coarse grid.  Executed FLOPs: exec_taps MACs per coarse pixel and channel pair; algorithmic FLOPs: what the
+    reference's formulation costs (alg_taps per coarse pixel: 36 for up-sample + 3x3, 16 for the 4x4 stride-2 conv)."""
+    rci, rco = real_dims if real_dims is not None else (ci, cop)
+    return {"shape": (n, h, w, ci, cop, exec_taps), "flops_exec": 2.0 * n * h * w * ci * cop * exec_taps,
+            "flops": 2.0 * n * h * w * rci * rco * alg_taps}
+
+
+def weight_prep_up(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = True):
+    """nn.Conv2d weight [Co,Ci,3,3] of an UpBlock2D conv -> (wx2 [4, Co_pad, 4, Ci_pad], ws2 [Ci_pad, 16, Co_pad]) bf16."""
+    _chk(w, "weight", torch.float32)
+    if _prep.valid:
+        hit = _prep.map_up.get(w.data_ptr())
+        if hit is not None:                      # prepared by this step's batched launch (ops.step_scope)
+            return (hit[0] if want_fwd else None), (hit[1] if want_dgrad else None)
+    co, ci, r, s = w.shape
+    if r != 3 or s != 3:
+        raise _lib.FaceVaeError("weight_prep_up: the up-sampling convolution is 3x3")
+    cop, cip = pad_channels(co), pad_channels(ci)
+    wx2 = torch.empty((4, cop, 4, cip), device=w.device, dtype=torch.bfloat16) if want_fwd else None
+    ws2 = torch.empty((cip, 16, cop), device=w.device, dtype=torch.bfloat16) if want_dgrad else None
+    call("fv_weight_prep_up", w.data_ptr(), _ptr(wx2), _ptr(ws2), co, ci, cop, cip, _stream())
+    return wx2, ws2
+
+
+def weight_prep_s2(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = True):
+    """weight [Co,Ci,4,4] of a 4x4 stride-2 conv -> (wf [Co_pad, 16, Ci_pad], wx2 [4, Ci_pad, 4, Co_pad]) bf16."""
+    _chk(w, "weight", torch.float32)
+    if _prep.valid:
+        hit = _prep.map_s2.get(w.data_ptr())
+        if hit is not None:
+            return (hit[0] if want_fwd else None), (hit[1] if want_dgrad else None)
+    co, ci, r, s = w.shape
+    if r != 4 or s != 4:
+        raise _lib.FaceVaeError("weight_prep_s2: the stride-2 convolution is 4x4")
+    cop, cip = pad_channels(co), pad_channels(ci)
+    wf = torch.empty((cop, 16, cip), device=w.device, dtype=torch.bfloat16) if want_fwd else None
+    wx2 = torch.empty((4, cip, 4, cop), device=w.device, dtype=torch.bfloat16) if want_dgrad else None
+    call("fv_weight_prep_s2", w.data_ptr(), _ptr(wf), _ptr(wx2), co, ci, cop, cip, _stream())
+    return wf, wx2
+
+
+def conv2d_x2(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], co: int, out_mode: int = OUT_NHWC_BF16,
+              real_dims=None, want_stats: bool = False, alg_taps: int = 36):
+    """x NHWC bf16 [N,H,W,Ci] -> y [N,2H,2W,Co_pad]: four 2x2 phase convolutions, wp [4, Co_pad, 4, Ci] (UpBlock2D's
+    up-sample + 3x3 conv without the up-sampled tensor; also the data gradient of ``conv2d_s2``)."""
+    _chk(x, "x", torch.bfloat16)
+    _chk(wp, "wp", torch.bfloat16)
+    n, h, w, ci = x.shape
+    if wp.dim() != 4 or wp.shape[0] != 4 or wp.shape[2] != 4 or wp.shape[3] != ci:
+        raise _lib.FaceVaeError(f"conv2d_x2: filter {tuple(wp.shape)} does not match input channels {ci}")
+    cop = wp.shape[1]
+    if out_mode == OUT_NCHW_F32:
+        y = torch.empty((n, co, 2 * h, 2 * w), device=x.device, dtype=torch.float32)
+    else:
+        y = torch.empty((n, 2 * h, 2 * w, cop), device=x.device, dtype=torch.bfloat16 if out_mode == OUT_NHWC_BF16 else torch.float32)
+    fused = want_stats and bool(_lib.load().fv_conv2d_geom_fuses_stats(1, out_mode, n, h, w, ci, cop))
+    sums = torch.empty((2 * cop,), device=x.device, dtype=torch.float32) if fused else None
+    call("fv_conv2d_x2", x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), out_mode, n, h, w, ci, co, cop, _ptr(sums),
+         _red_ws() if fused else None, _stream(), meta=_conv_meta_x2(n, h, w, ci, cop, real_dims, 16, alg_taps))
+    if want_stats and not fused:      # the library would run a separate statistic pass: issue it here (timed on its own)
+        sums = bn_stats(y)
+    return (y, sums) if want_stats else y
+
+
+def conv2d_s2(x: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], co: int, out_mode: int = OUT_NHWC_BF16,
+              real_dims=None, want_stats: bool = False, alg_taps: int = 16):
+    """x NHWC bf16 [N,2H,2W,Ci] -> y [N,H,W,Co_pad]: 4x4 stride-2 pad-1 convolution, wf [Co_pad, 16, Ci] (Conv2dELR of
+    EFE_conv6; with ``weight_prep_up``'s ws2 the data gradient of ``conv2d_x2``)."""
+    _chk(x, "x", torch.bfloat16)
+    _chk(wf, "wf", torch.bfloat16)
+    n, h2, w2, ci = x.shape
+    if h2 % 2 or w2 % 2:
+        raise _lib.FaceVaeError("conv2d_s2: even input sizes only")
+    h, w = h2 // 2, w2 // 2
+    if wf.dim() != 3 or wf.shape[1] != 16 or wf.shape[2] != ci:
+        raise _lib.FaceVaeError(f"conv2d_s2: filter {tuple(wf.shape)} does not match input channels {ci}")
+    cop = wf.shape[0]
+    if out_mode == OUT_NCHW_F32:
+        y = torch.empty((n, co, h, w), device=x.device, dtype=torch.float32)
+    else:
+        y = torch.empty((n, h, w, cop), device=x.device, dtype=torch.bfloat16 if out_mode == OUT_NHWC_BF16 else torch.float32)
+    fused = want_stats and bool(_lib.load().fv_conv2d_geom_fuses_stats(2, out_mode, n, h, w, ci, cop))
+    sums = torch.empty((2 * cop,), device=x.device, dtype=torch.float32) if fused else None
+    call("fv_conv2d_s2", x.data_ptr(), wf.data_ptr(), _ptr(bias), y.data_ptr(), out_mode, n, h, w, ci, co, cop, _ptr(sums),
+         _red_ws() if fused else None, _stream(), meta=_conv_meta_x2(n, h, w, ci, cop, real_dims, 16, alg_taps))
+    if want_stats and not fused:
+        sums = bn_stats(y)
+    return (y, sums) if want_stats else y
+
+
+def conv2d_wgrad_x2(x: torch.Tensor, dy: torch.Tensor, real_dims=None) -> torch.Tensor:
+    """x coarse [N,H,W,Ci], dy fine [N,2H,2W,Co_pad] -> partial slabs [splits, 4, Co_pad, 4, Ci] of the phase filters."""
+    _chk(x, "x", torch.bfloat16)
+    _chk(dy, "dy", torch.bfloat16)
+    n, h, w, ci = x.shape
+    cop = dy.shape[3]
+    if tuple(dy.shape[:3]) != (n, 2 * h, 2 * w):
+        raise _lib.FaceVaeError("conv2d_wgrad_x2: x / dy shape mismatch")
+    splits = int(_lib.load().fv_conv2d_wgrad_splits(1, n, h, w, ci, cop, 2, 2))
+    part = torch.empty((max(splits, 1), 4, cop, 4, ci), device=x.device, dtype=torch.float32)
+    call("fv_conv2d_wgrad_x2", x.data_ptr(), dy.data_ptr(), part.data_ptr(), splits, n, h, w, ci, cop, _stream(),
+         meta=_conv_meta_x2(n, h, w, ci, cop, real_dims, 16, 36))
+    return part
+
+
+def wgrad_finish_up(part: torch.Tensor, co: int, ci: int, grad: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """phase slabs [splits, 4, Co_pad, 4, Ci_pad] -> gradient of the 3x3 filter [co, ci, 3, 3] fp32."""
+    accumulate = grad is not None
+    if grad is None:
+        grad = torch.empty((co, ci, 3, 3), device=part.device, dtype=torch.float32)
+    call("fv_wgrad_finish_up", part.data_ptr(), part.shape[0], _chk(grad, "grad", torch.float32).data_ptr(), co, ci, part.shape[2],
+         part.shape[4], int(accumulate), _stream())
+    return grad
+
+
+def conv2d_wgrad_s2(x: torch.Tensor, dy: torch.Tensor, real_dims=None) -> torch.Tensor:
+    """x fine [N,2H,2W,Ci], dy coarse [N,H,W,Co_pad] -> partial slabs [splits, Co_pad, 16, Ci] (``wgrad_finish(ksize=4)``)."""
+    _chk(x, "x", torch.bfloat16)
+    _chk(dy, "dy", torch.bfloat16)
+    n, h, w, cop = dy.shape
+    ci = x.shape[3]
+    if tuple(x.shape[:3]) != (n, 2 * h, 2 * w):
+        raise _lib.FaceVaeError("conv2d_wgrad_s2: x / dy shape mismatch")
+    splits = int(_lib.load().fv_conv2d_wgrad_splits(2, n, h, w, ci, cop, 4, 4))
+    part = torch.empty((max(splits, 1), cop, 16, ci), device=x.device, dtype=torch.float32)
+    call("fv_conv2d_wgrad_s2", x.data_ptr(), dy.data_ptr(), part.data_ptr(), splits, n, h, w, ci, cop, _stream(),
+         meta=_conv_meta_x2(n, h, w, ci, cop, real_dims, 16, 16))
+    return part
 
 
 def colsum(y: torch.Tensor) -> torch.Tensor:
     _chk(y, "y", torch.bfloat16)
     c = y.shape[-1]
-    sums = _zeros((c,), y.device)
-    call("fv_colsum", y.data_ptr(), sums.data_ptr(), y.numel() // c, c, _stream())
+    sums = torch.empty((c,), device=y.device, dtype=torch.float32)
+    call("fv_colsum", y.data_ptr(), sums.data_ptr(), y.numel() // c, c, _red_ws(), _stream())
     return sums
 
 
@@ -324,14 +464,14 @@ def outconv_fwd(x: torch.Tensor, wq: torch.Tensor, bias: Optional[torch.Tensor],
             raise _lib.FaceVaeError("outconv_fwd: target shape mismatch")
         pred = torch.empty((n, co, h, w), device=dev, dtype=torch.float32) if want_pred else None
         g4 = torch.empty((n, h, w, 4), device=dev, dtype=torch.bfloat16)
-        acc = _zeros((8,), dev)         # [0]: loss sum, [4:8]: gradient sums per channel
+        acc = torch.empty((8,), device=dev, dtype=torch.float32)         # [0]: loss sum, [4:8]: gradient sums per channel
     if bias is not None:
         _chk(bias, "bias", torch.float32)
     meta = _conv_meta(n, h, w, ci, 32, 7, (ci, co))
     meta.update(_bytes(x, logits, target, pred, g4))
     call("fv_outconv_fwd", x.data_ptr(), wq.data_ptr(), _ptr(bias), _ptr(logits), _ptr(target), _ptr(pred), _ptr(g4),
          _ptr(acc), None if acc is None else acc[4:].data_ptr(), n, h, w, ci, co, int(l1), int(use_sigmoid), float(gscale),
-         _stream(), meta=meta)
+         _red_ws() if fused else None, _stream(), meta=meta)
     return {"logits": logits, "pred": pred, "g4": g4, "loss_sum": None if acc is None else acc[:1],
             "gsum": None if acc is None else acc[4:4 + co]}
 
@@ -348,13 +488,16 @@ def outconv_dgrad(g4: torch.Tensor, wdq: torch.Tensor, scale_ptr: Optional[torch
 
 
 def outconv_wgrad(x: torch.Tensor, g4: torch.Tensor, scale_ptr: Optional[torch.Tensor], co: int) -> torch.Tensor:
-    """-> dw fp32 [co, 32, 7, 7] (nn.Conv2d layout)."""
+    """-> dw fp32 [co, 32, 7, 7] (nn.Conv2d layout): per-CTA slabs from the tensor-core kernel, added in CTA order."""
     _chk(x, "x", torch.bfloat16)
     _chk(g4, "g4", torch.bfloat16)
     n, h, w, ci = x.shape
-    dw = torch.zeros((co, ci, 7, 7), device=x.device, dtype=torch.float32)   # becomes .grad: not arena memory
-    call("fv_outconv_wgrad", x.data_ptr(), g4.data_ptr(), _ptr(scale_ptr), dw.data_ptr(), n, h, w, ci, co, _stream(),
+    splits = int(_lib.load().fv_outconv_wgrad_splits(n, h, w))
+    part = torch.empty((max(splits, 1), co, ci, 7, 7), device=x.device, dtype=torch.float32)
+    call("fv_outconv_wgrad", x.data_ptr(), g4.data_ptr(), _ptr(scale_ptr), part.data_ptr(), splits, n, h, w, ci, co, _stream(),
          meta=_conv_meta(n, h, w, ci, 32, 7, (ci, co)))
+    dw = torch.empty((co, ci, 7, 7), device=x.device, dtype=torch.float32)
+    call("fv_slab_sum", part.data_ptr(), splits, co * ci * 49, dw.data_ptr(), co * ci * 49, 0, _stream())
     return dw
 
 
@@ -362,8 +505,8 @@ def outconv_wgrad(x: torch.Tensor, g4: torch.Tensor, scale_ptr: Optional[torch.T
 def bn_stats(y: torch.Tensor) -> torch.Tensor:
     _chk(y, "y")
     c = y.shape[-1]
-    sums = _zeros((2 * c,), y.device)
-    call("fv_bn_stats", y.data_ptr(), _dt(y), sums.data_ptr(), y.numel() // c, c, _stream(), meta=_bytes(y))
+    sums = torch.empty((2 * c,), device=y.device, dtype=torch.float32)
+    call("fv_bn_stats", y.data_ptr(), _dt(y), sums.data_ptr(), y.numel() // c, c, _red_ws(), _stream(), meta=_bytes(y))
     return sums
 
 
@@ -433,9 +576,9 @@ def bn_act_bwd_reduce(y: torch.Tensor, g: torch.Tensor, stat: torch.Tensor, mode
     _chk(y, "y")
     _chk(g, "g")
     n, h, w, c = y.shape
-    sums = _zeros((2 * c,), y.device)
+    sums = torch.empty((2 * c,), device=y.device, dtype=torch.float32)
     call("fv_bn_act_bwd_reduce", y.data_ptr(), _dt(y), g.data_ptr(), _dt(g), int(g_nchw), stat.data_ptr(),
-         sums.data_ptr(), n, h, w, c, mode, act, _stream(), meta=_bytes(y, g))
+         sums.data_ptr(), n, h, w, c, mode, act, _red_ws(), _stream(), meta=_bytes(y, g))
     return sums
 
 
@@ -465,12 +608,14 @@ def bn_act_bwd_apply(y: torch.Tensor, g: torch.Tensor, stat: torch.Tensor, coef:
 # ------------------------------------------------------------------------------------------------ VAE bottleneck + losses
 def reparam_kl_fwd(mu: torch.Tensor, logstd: torch.Tensor, eps: Optional[torch.Tensor], want_z: bool = True,
                    want_kl: bool = True):
-    """mu / logstd: fp32 [N, Dz] row views (unit inner stride, common row stride).  Returns (z [N,Dz] | None, kl_rows [N] | None)."""
+    """mu / logstd: fp32 [N, Dz] row views (unit inner stride, common row stride).  Returns (z [N,Dz] | None, kl partial sums
+    [N, P] | None -- ``.sum()`` of it is the KL sum over all samples and latent dimensions)."""
     n, dz = mu.shape
     if mu.stride(1) != 1 or logstd.stride(1) != 1 or mu.stride(0) != logstd.stride(0):
         raise _lib.FaceVaeError("reparam_kl_fwd: mu/logstd must be row views with a common row stride")
     z = torch.empty((n, dz), device=mu.device, dtype=torch.float32) if want_z else None
-    kl = _zeros((n,), mu.device) if want_kl else None
+    # per-block partial sums [N, P]; the (few) partials are added by the caller in a fixed order (no atomics)
+    kl = torch.empty((n, int(_lib.load().fv_reparam_kl_parts(n, dz))), device=mu.device, dtype=torch.float32) if want_kl else None
     if eps is not None:
         _chk(eps, "eps", torch.float32)
     call("fv_reparam_kl_fwd", mu.data_ptr(), logstd.data_ptr(), mu.stride(0), _ptr(eps), _ptr(z), _ptr(kl), n, dz,
@@ -497,22 +642,22 @@ def recon_loss(logits: torch.Tensor, target: torch.Tensor, l1: bool = False, use
     _chk(target, "target", torch.float32)
     n, c, h, w = logits.shape
     cp = pad_channels(c)
-    loss = _zeros((1,), logits.device)
+    loss = torch.empty((1,), device=logits.device, dtype=torch.float32)
     pred = torch.empty_like(logits) if want_pred else None
     gf = torch.empty_like(logits) if want_grad_f32 else None
     gn = torch.empty((n, h, w, cp), device=logits.device, dtype=torch.bfloat16) if want_grad_nhwc else None
     call("fv_recon_loss", logits.data_ptr(), target.data_ptr(), _ptr(pred), _ptr(gf), _ptr(gn), loss.data_ptr(), n, c, h,
-         w, cp, int(l1), int(use_sigmoid), float(gscale), _stream(), meta=_bytes(logits, target, pred, gf, gn))
+         w, cp, int(l1), int(use_sigmoid), float(gscale), _red_ws(), _stream(), meta=_bytes(logits, target, pred, gf, gn))
     return loss, pred, gf, gn
 
 
 def recon_loss_flat(a: torch.Tensor, b: torch.Tensor, l1: bool = False, gscale: float = 1.0, want_grad: bool = True):
     _chk(a, "a", torch.float32)
     _chk(b, "b", torch.float32)
-    loss = _zeros((1,), a.device)
+    loss = torch.empty((1,), device=a.device, dtype=torch.float32)
     grad = torch.empty_like(a) if want_grad else None
     call("fv_recon_loss_flat", a.data_ptr(), b.data_ptr(), _ptr(grad), loss.data_ptr(), a.numel(), int(l1), float(gscale),
-         _stream())
+         _red_ws(), _stream(), meta=_bytes(a, b, grad))
     return loss, grad
 
 
@@ -528,8 +673,8 @@ def pw_moments(x: torch.Tensor) -> torch.Tensor:
     """x NCHW fp32 [N,C,H,W], C <= 4 -> double [C + C*C]: sum x_c | sum x_c x_d."""
     _chk(x, "x", torch.float32)
     n, c, h, w = x.shape
-    sums = _zeros((c + c * c,), x.device, torch.float64)
-    call("fv_pw_moments", x.data_ptr(), sums.data_ptr(), n, c, h * w, _stream(), meta=_bytes(x))
+    sums = torch.empty((c + c * c,), device=x.device, dtype=torch.float64)
+    call("fv_pw_moments", x.data_ptr(), sums.data_ptr(), n, c, h * w, _red_ws(), _stream(), meta=_bytes(x))
     return sums
 
 
@@ -555,8 +700,8 @@ def pw_bwd_reduce(x: torch.Tensor, g: torch.Tensor, coef: torch.Tensor, act: int
     _chk(g, "g", torch.bfloat16)
     n, c, h, w = x.shape
     co = coef.shape[0]
-    sums = _zeros((co + co * c,), x.device, torch.float64)
-    call("fv_pw_bwd_reduce", x.data_ptr(), g.data_ptr(), coef.data_ptr(), sums.data_ptr(), n, c, h * w, co, act, _stream(),
+    sums = torch.empty((co + co * c,), device=x.device, dtype=torch.float64)
+    call("fv_pw_bwd_reduce", x.data_ptr(), g.data_ptr(), coef.data_ptr(), sums.data_ptr(), n, c, h * w, co, act, _red_ws(), _stream(),
          meta=_bytes(x, g))
     return sums
 

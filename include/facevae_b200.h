@@ -12,6 +12,10 @@
  *   - return 0 on success, non-zero on failure (bad shape / unsupported configuration / CUDA error); the message
  *     is available from fv_last_error() (thread-local).  Nothing is thrown, nothing falls back to another path;
  *   - the library never allocates, frees or retains caller memory;
+ *   - sums over pixels (batch-norm statistics, bias / weight gradients, losses) are combined in a FIXED order, so every entry
+ *     point is bitwise reproducible from run to run.  Entry points that reduce across thread blocks take `red_ws`: a scratch
+ *     buffer of fv_reduce_ws_bytes() bytes whose first 512 bytes are zero before the first use (the kernels leave them zero
+ *     again), private to one stream at a time; outputs of such reductions are WRITTEN, not accumulated;
  *   - activations are NHWC ("channels last") bf16 or fp32 with the channel count padded to a multiple of 16
  *     (Cp / Ci / Co_pad below); the NCHW fp32 tensors of the reference API are converted at the edges.
  */
@@ -25,8 +29,10 @@ enum { FV_OUT_NHWC_BF16 = 0, FV_OUT_NHWC_F32 = 1, FV_OUT_NCHW_F32 = 2 };
 enum { FV_MODE_NONE = 0, FV_MODE_POOL = 1, FV_MODE_UP = 2 };   /* fused 2x2 avg-pool / nearest 2x up-sample */
 enum { FV_ACT_NONE = 0, FV_ACT_RELU = 1, FV_ACT_LEAKY = 2 };   /* LeakyReLU slope 0.2 (reference modules.py:29) */
 
+#define FV_ABI_VERSION 2   /* bumped with every signature change; fv_abi_version() returns the value the library was built with */
 const char* fv_last_error(void);
 const char* fv_version(void);
+int fv_abi_version(void);
 int fv_device_ok(void);   /* 0 iff the current device is sm_10x */
 
 /* ---- layout at the edges of the path -------------------------------------------------------------------- */
@@ -45,9 +51,10 @@ int fv_weight_prep(const float* w, void* wf, void* wd, int Co, int Ci, int R, in
  * Co_pad*R*S*Ci_pad in the table): the per-step filter preparation of a whole network. */
 typedef struct {
     const float* w;
-    void* wf;
-    void* wd;
+    void* wf;                 /* kind 0: wf;  kind 1 (fv_weight_prep_up): wx2;  kind 2 (fv_weight_prep_s2): wf */
+    void* wd;                 /* kind 0: wd;  kind 1: ws2;                      kind 2: wx2 */
     int Co, Ci, R, S, Co_pad, Ci_pad;
+    int kind, reserved;
 } fv_prep_desc;
 int fv_weight_prep_batched(const fv_prep_desc* table_dev, int n_layers, long long max_items, void* stream);
 /* y = conv(x, wf) + bias (+ residual); stride 1, odd square filter, pad = (R-1)/2.  tcgen05 implicit GEMM.
@@ -57,21 +64,56 @@ int fv_weight_prep_batched(const fv_prep_desc* table_dev, int n_layers, long lon
  * The data gradient is the same call with x := dY, wf := wd, (Ci, Co, Co_pad) := (Co_pad, Ci, Ci_pad). */
 int fv_conv2d(const void* x, const void* wf, const float* bias, const void* residual, void* y, int out_mode, int N, int H, int W,
               int Ci, int Co, int Co_pad, int R, int S, int pad, void* stream);
+/* bytes of the reduction scratch every `red_ws` parameter below expects (see Conventions) */
+long long fv_reduce_ws_bytes(void);
 /* fv_conv2d with the statistic pass of the following batch norm fused into the epilogue (replaces a separate fv_bn_stats
- * read of y): stats[0..Co_pad) += sum_pixels y, stats[Co_pad..2*Co_pad) += sum_pixels y^2 over the values as stored
- * (caller-zeroed fp32; NHWC output modes only). */
+ * read of y): stats[0..Co_pad) = sum_pixels y, stats[Co_pad..2*Co_pad) = sum_pixels y^2 over the values as stored
+ * (fp32; NHWC output modes only). */
 int fv_conv2d_stats(const void* x, const void* wf, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
-                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, void* stream);
+                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, void* red_ws, void* stream);
 /* 1 when fv_conv2d_stats fuses the statistics into the epilogue for this shape, 0 when it runs a separate fv_bn_stats pass
  * over y (fusing costs the epilogue ~250 cycles per 16 channels and tile; it is done only where the tile's MMAs hide it). */
 int fv_conv2d_fuses_stats(int out_mode, int N, int H, int W, int Ci, int Co_pad, int R, int S, int has_residual);
-/* dw_acc[Co_pad][R*S][Ci] (fp32, caller-zeroed) += sum_pixels x[pixel + tap] * dy[pixel]; tcgen05, split over pixels. */
-int fv_conv2d_wgrad(const void* x, const void* dy, float* dw_acc, int N, int H, int W, int Ci, int Co_pad, int R, int S, int pad,
+/* the same question for fv_conv2d_x2 (kind 1) / fv_conv2d_s2 (kind 2); H, W = the coarse grid */
+int fv_conv2d_geom_fuses_stats(int kind, int out_mode, int N, int H, int W, int Ci, int Co_pad);
+/* Weight gradient, tcgen05, split over pixels: part[split][Co_pad][R*S][Ci] (fp32) = this split's share of
+ * sum_pixels x[pixel + tap] * dy[pixel]; splits = fv_conv2d_wgrad_splits(0, ...) slabs are written (plain stores). */
+int fv_conv2d_wgrad_splits(int kind /* 0 same, 1 x2, 2 s2 */, int N, int H, int W, int Ci, int Co_pad, int R, int S);
+int fv_conv2d_wgrad(const void* x, const void* dy, float* part, int splits, int N, int H, int W, int Ci, int Co_pad, int R, int S,
+                    int pad, void* stream);
+/* slabs added in split order -> nn.Conv2d layout grad [Co,Ci,R,S] fp32 (accumulate != 0 adds, as autograd does into .grad). */
+int fv_wgrad_finish(const float* part, int splits, float* grad, int Co, int Ci, int R, int S, int Co_pad, int Ci_pad, int accumulate,
                     void* stream);
-/* dw_acc -> nn.Conv2d layout grad [Co,Ci,R,S] fp32 (accumulate != 0 adds, as autograd does into .grad). */
-int fv_wgrad_finish(const float* dw_acc, float* grad, int Co, int Ci, int R, int S, int Ci_pad, int accumulate, void* stream);
-/* sums[C] (caller-zeroed) += per-channel sums over P rows of an NHWC bf16 tensor: the bias gradient. */
-int fv_colsum(const void* y, float* sums, long long P, int C, void* stream);
+/* sums[C] = per-channel sums over P rows of an NHWC bf16 tensor: the bias gradient. */
+int fv_colsum(const void* y, float* sums, long long P, int C, void* red_ws, void* stream);
+/* out[n] (+)= sum over `slabs` partial vectors, slab_stride elements apart, in slab order. */
+int fv_slab_sum(const float* part, int slabs, long long slab_stride, float* out, long long n, int accumulate, void* stream);
+
+/* ---- UpBlock2D's nn.Upsample(x2, nearest) + 3x3 conv (modules.py:78-89) WITHOUT the up-sampled tensor, and the 4x4 stride-2
+ *      convolution of Conv2dELR / EFE_conv6.efe_encoder (models_utils.py:632-744, models.py:845-852).  Output pixel
+ *      (2i + a, 2j + b) of the up-sampled conv sees only the coarse pixels (i + u - 1 + a, j + v - 1 + b), u, v in {0, 1}: four
+ *      2x2 "phase" convolutions on the coarse grid with summed taps (2.25x fewer MACs, 4x smaller input).  Its data gradient
+ *      is a 4x4 stride-2 convolution of dY (the 2x2 sum of the up-sampling backward folded in), and vice versa. ----------- */
+/* w [Co,Ci,3,3] fp32 -> wx2 bf16 [4][Co_pad][4][Ci_pad] (fv_conv2d_x2) and ws2 bf16 [Ci_pad][16][Co_pad] (fv_conv2d_s2 computing
+ * the data gradient).  Either may be NULL. */
+int fv_weight_prep_up(const float* w, void* wx2, void* ws2, int Co, int Ci, int Co_pad, int Ci_pad, void* stream);
+/* w [Co,Ci,4,4] fp32 -> wf bf16 [Co_pad][16][Ci_pad] (fv_conv2d_s2) and wx2 bf16 [4][Ci_pad][4][Co_pad] (fv_conv2d_x2 computing
+ * the data gradient).  Either may be NULL. */
+int fv_weight_prep_s2(const float* w, void* wf, void* wx2, int Co, int Ci, int Co_pad, int Ci_pad, void* stream);
+/* x NHWC bf16 [N,H,W,Ci] -> y [N,2H,2W,Co_pad] (out_mode as fv_conv2d) = bias + four 2x2 phase convolutions with
+ * wp = [4][Co_pad][4*Ci].  stats (optional, NHWC outputs): [2][Co_pad] sum / sum of squares of y, needs red_ws. */
+int fv_conv2d_x2(const void* x, const void* wp, const float* bias, void* y, int out_mode, int N, int H, int W, int Ci, int Co,
+                 int Co_pad, float* stats, void* red_ws, void* stream);
+/* x NHWC bf16 [N,2H,2W,Ci] -> y [N,H,W,Co_pad] = bias + 4x4 stride-2 pad-1 convolution with w = [Co_pad][16*Ci]. */
+int fv_conv2d_s2(const void* x, const void* w, const float* bias, void* y, int out_mode, int N, int H, int W, int Ci, int Co,
+                 int Co_pad, float* stats, void* red_ws, void* stream);
+/* x [N,H,W,Ci] coarse, dy [N,2H,2W,Co_pad] fine -> part[split][4][Co_pad][4][Ci]; splits = fv_conv2d_wgrad_splits(1, ...). */
+int fv_conv2d_wgrad_x2(const void* x, const void* dy, float* part, int splits, int N, int H, int W, int Ci, int Co_pad, void* stream);
+/* x [N,2H,2W,Ci] fine, dy [N,H,W,Co_pad] coarse -> part[split][Co_pad][16][Ci]; splits = fv_conv2d_wgrad_splits(2, ...);
+ * fv_wgrad_finish(R = S = 4) completes it. */
+int fv_conv2d_wgrad_s2(const void* x, const void* dy, float* part, int splits, int N, int H, int W, int Ci, int Co_pad, void* stream);
+/* phase slabs of fv_conv2d_wgrad_x2 -> grad [Co,Ci,3,3] fp32 of the 3x3 filter. */
+int fv_wgrad_finish_up(const float* part, int splits, float* grad, int Co, int Ci, int Co_pad, int Ci_pad, int accumulate, void* stream);
 
 /* ---- out_conv: nn.Conv2d(32, 3, 7, padding 3) (models.py:1099) -> torch.sigmoid (models.py:1110) -> ReconLoss
  *      (losses.py:396-403, trainer.py:314), tap-folded tcgen05 schedule (csrc/fv_outconv.cu).  Shapes: 7x7 filter,
@@ -81,24 +123,26 @@ int fv_outconv_supported(int N, int H, int W, int Ci, int Co, int R, int S);
  * (data-gradient operand: rows ci, K = (s',co), taps rotated).  Either may be NULL. */
 int fv_outconv_prep(const float* w, void* wq, void* wdq, int Co, int Ci, void* stream);
 /* x: NHWC bf16 [N,H,W,32].  logits (NCHW fp32 [N,Co,H,W], optional when target is given) = conv(x) + bias.  With
- * target (NCHW fp32) the epilogue also produces pred = sigmoid(logits) (optional), loss_sum[1] += sum l(pred - target)
- * (caller-zeroed), g4 = bf16 [N,H,W,4]: gscale * dloss/dlogits (channels Co..3 zero) and gsum[4] += its per-channel sums
- * (caller-zeroed: the bias gradient). */
+ * target (NCHW fp32) the epilogue also produces pred = sigmoid(logits) (optional), loss_sum[1] = sum l(pred - target),
+ * g4 = bf16 [N,H,W,4]: gscale * dloss/dlogits (channels Co..3 zero) and gsum[Co] = its per-channel sums (the bias gradient);
+ * the fused loss needs red_ws. */
 int fv_outconv_fwd(const void* x, const void* wq, const float* bias, float* logits, const float* target, float* pred, void* g4,
                    float* loss_sum, float* gsum, int N, int H, int W, int Ci, int Co, int l1, int use_sigmoid, float gscale,
-                   void* stream);
+                   void* red_ws, void* stream);
 /* dx NHWC bf16 [N,H,W,32] = (*scale_ptr) * conv_transpose(g4, w) (scale_ptr may be NULL); g4 as written by fv_outconv_fwd. */
 int fv_outconv_dgrad(const void* g4, const void* wdq, const float* scale_ptr, void* dx, int N, int H, int W, int Ci, int Co,
                      void* stream);
-/* dw [Co,32,7,7] fp32 (nn.Conv2d layout, caller-zeroed) += (*scale_ptr) * sum_pixels x[pixel + tap] * g4[pixel]. */
-int fv_outconv_wgrad(const void* x, const void* g4, const float* scale_ptr, float* dw, int N, int H, int W, int Ci, int Co,
-                     void* stream);
+/* part[split][Co,32,7,7] fp32 (nn.Conv2d layout per slab) = this CTA's share of (*scale_ptr) * sum_pixels x[pixel + tap] *
+ * g4[pixel]; splits = fv_outconv_wgrad_splits(N, H, W); fv_slab_sum adds the slabs. */
+int fv_outconv_wgrad_splits(int N, int H, int W);
+int fv_outconv_wgrad(const void* x, const void* g4, const float* scale_ptr, float* part, int splits, int N, int H, int W, int Ci,
+                     int Co, void* stream);
 
 /* ---- nn.SyncBatchNorm (modules.py:19) + ReLU/LeakyReLU (modules.py:27,29) + AvgPool2d (modules.py:62,70) /
  *      nn.Upsample (modules.py:81,89) ---------------------------------------------------------------------- */
-/* sums[0..C) += sum y, sums[C..2C) += sum y^2 over P = N*H*W rows (caller-zeroed; all-reduced across ranks by the
- * host before fv_bn_finalize -- the stat exchange of torch/nn/modules/_functions.py:39-83). */
-int fv_bn_stats(const void* y, int dtype, float* sums, long long P, int C, void* stream);
+/* sums[0..C) = sum y, sums[C..2C) = sum y^2 over P = N*H*W rows (all-reduced across ranks by the host before
+ * fv_bn_finalize -- the stat exchange of torch/nn/modules/_functions.py:39-83). */
+int fv_bn_stats(const void* y, int dtype, float* sums, long long P, int C, void* red_ws, void* stream);
 /* stat[4][C] = mean, invstd (biased variance, eps), scale = gamma*invstd, shift = beta - mean*scale; updates
  * running_mean / running_var (unbiased variance, momentum) when given. */
 int fv_bn_finalize(const float* sums, double count, const float* gamma, const float* beta, float* running_mean,
@@ -114,10 +158,10 @@ int fv_bn_act_fwd(const void* y, int in_dtype, const float* stat, void* out, int
 int fv_bn_act_fwd_fin(const void* y, int in_dtype, const float* sums, double count, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, float momentum, float eps, float* stat_out, void* out, int out_dtype,
                       int nchw_out, int N, int H, int W, int C, int mode, int act, void* stream);
-/* backward pass 1: sums[0..C) += sum dz, sums[C..2C) += sum dz*xhat (caller-zeroed; all-reduced across ranks like
+/* backward pass 1: sums[0..C) = sum dz, sums[C..2C) = sum dz*xhat (all-reduced across ranks like
  * torch/nn/modules/_functions.py:144-159).  g is the gradient of the block output (pooled / up-sampled domain). */
 int fv_bn_act_bwd_reduce(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat, float* sums,
-                         int N, int H, int W, int C, int mode, int act, void* stream);
+                         int N, int H, int W, int C, int mode, int act, void* red_ws, void* stream);
 /* dgamma/dbeta (+)= local sums; coef[2][C] = global sums / count. */
 int fv_bn_bwd_finalize(const float* sums_local, const float* sums_global, double count, float* dgamma, float* dbeta, float* coef,
                        int C, int accumulate, void* stream);
@@ -133,14 +177,14 @@ int fv_bn_act_bwd_apply_fin(const void* y, int y_dtype, const void* g, int g_dty
 
 /* ---- first encoder layer: SameBlock2D(C <= 4 -> 32) on raw NCHW fp32 frames (modules.py:97-108 via models.py:749) ----
  * 1x1 conv + training-mode batch norm + ReLU is a per-pixel affine map whose statistics follow from the input moments.
- * sums are double: forward [C + C*C] = sum x_c | sum x_c x_d; backward [Co + Co*C] = sum dz | sum dz x_c (caller-zeroed,
+ * sums are double: forward [C + C*C] = sum x_c | sum x_c x_d; backward [Co + Co*C] = sum dz | sum dz x_c (written;
  * all-reduced across ranks by the host).  coef [Co][C+1] = A | c with a = act(A x + c); stat [2][Co] = mean_y | invstd. */
-int fv_pw_moments(const float* x_nchw, double* sums, int N, int C, int HW, void* stream);
+int fv_pw_moments(const float* x_nchw, double* sums, int N, int C, int HW, void* red_ws, void* stream);
 int fv_pw_prepare(const double* sums, double count, const float* w, const float* bias, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, float momentum, float eps, float* coef, float* stat, int Co, int C, void* stream);
 int fv_pw_fwd(const float* x_nchw, const float* coef, void* out_nhwc_bf16, int N, int C, int HW, int Co, int act, void* stream);
 int fv_pw_bwd_reduce(const float* x_nchw, const void* g_nhwc_bf16, const float* coef, double* sums, int N, int C, int HW, int Co, int act,
-                     void* stream);
+                     void* red_ws, void* stream);
 int fv_pw_bwd_finalize(const double* fsums, const double* bsums, double count, const float* w, const float* bias, const float* gamma,
                        const float* stat, float* dw, float* dgamma, float* dbeta, int Co, int C, void* stream);
 
@@ -156,9 +200,11 @@ int fv_bn_finalize_xrank(const float* sums_local, void* peer_bufs_dev, int rank,
                          float* out, float* dgamma, float* dbeta, int accumulate, int C, void* stream);
 
 /* ---- re-parameterisation (models.py:559-561) fused with KLDivergenceLoss (losses.py:385-393) ------------- */
-/* mu/logstd: fp32 rows of Dz values, row_stride apart; z[N,Dz] = mu + exp(logstd)*eps (NULL eps => z = mu; NULL z =>
- * KL only); kl_rows[N] (caller-zeroed, may be NULL) += sum_d(-0.5 - logstd + 0.5 mu^2 + 0.5 exp(2 logstd)). */
-int fv_reparam_kl_fwd(const float* mu, const float* logstd, long long row_stride, const float* eps, float* z, float* kl_rows,
+/* mu/logstd: fp32 rows of Dz values (Dz % 4 == 0, 16-byte aligned), row_stride apart; z[N,Dz] = mu + exp(logstd)*eps (NULL
+ * eps => z = mu; NULL z => KL only); kl_part[N][P] (may be NULL), P = fv_reparam_kl_parts(N, Dz): per-block partial sums of
+ * sum_d(-0.5 - logstd + 0.5 mu^2 + 0.5 exp(2 logstd)) -- the caller adds the P partials of a row (no atomics). */
+int fv_reparam_kl_parts(int N, int Dz);
+int fv_reparam_kl_fwd(const float* mu, const float* logstd, long long row_stride, const float* eps, float* z, float* kl_part,
                       int N, int Dz, void* stream);
 /* dmu = dz + k*mu (+dmu_ext); dlogstd = dz*eps*exp(logstd) + k*(exp(2 logstd)-1) (+dls_ext); k = kscale * (*kscale_ptr). */
 int fv_reparam_kl_bwd(const float* mu, const float* logstd, long long row_stride, const float* eps, const float* dz,
@@ -166,12 +212,13 @@ int fv_reparam_kl_bwd(const float* mu, const float* logstd, long long row_stride
                       long long out_stride, int N, int Dz, void* stream);
 
 /* ---- ReconLoss / nn.MSELoss (losses.py:396-403), nn.L1Loss (losses.py:128), torch.sigmoid (models.py:1110) - */
-/* NCHW fp32 logits/target [N,C,H,W]; loss_sum (caller-zeroed) += sum l(pred - target); optional outputs: pred
+/* NCHW fp32 logits/target [N,C,H,W]; loss_sum[1] = sum l(pred - target); optional outputs: pred
  * (= sigmoid(logits) when use_sigmoid), gradient w.r.t. logits times gscale as fp32 NCHW and/or bf16 NHWC [N,H,W,Cp]. */
 int fv_recon_loss(const float* logits, const float* target, float* pred_out, float* grad_f32, void* grad_nhwc, float* loss_sum,
-                  int N, int C, int H, int W, int Cp, int l1, int use_sigmoid, float gscale, void* stream);
-/* same-shape flat fp32 tensors a, b of E elements: loss_sum += sum l(a-b); grad (optional) = gscale * dl/da. */
-int fv_recon_loss_flat(const float* a, const float* b, float* grad, float* loss_sum, long long E, int l1, float gscale, void* stream);
+                  int N, int C, int H, int W, int Cp, int l1, int use_sigmoid, float gscale, void* red_ws, void* stream);
+/* same-shape flat fp32 tensors a, b of E elements: loss_sum[1] = sum l(a-b); grad (optional) = gscale * dl/da. */
+int fv_recon_loss_flat(const float* a, const float* b, float* grad, float* loss_sum, long long E, int l1, float gscale, void* red_ws,
+                       void* stream);
 /* out = in * scale * (*scale_ptr) (scale_ptr may be NULL); n elements, n % 8 == 0. */
 int fv_scale(const void* in, void* out, int dtype, long long n, const float* scale_ptr, float scale, void* stream);
 

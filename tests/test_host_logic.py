@@ -1,5 +1,5 @@
-"""Host-side logic that needs no GPU: shape predicates of the C ABI, argument checking of the newer entry points, the
-per-step scratch arena, and the optimiser's refusal of CPU tensors (the package has no CPU compute path)."""
+"""Host-side logic that needs no GPU: shape predicates and planning queries of the C ABI, argument checking of the entry
+points, the per-step scope, and the optimiser's refusal of CPU tensors (the package has no CPU compute path)."""
 import ctypes
 
 import pytest
@@ -33,39 +33,69 @@ def test_conv_stats_fusion_predicate_on_the_anchor_layers(lib):
 
 
 def test_new_entry_points_reject_bad_arguments_without_a_gpu(lib):
-    assert lib.fv_outconv_fwd(None, None, None, None, None, None, None, None, None, 1, 8, 128, 32, 3, 0, 1, 1.0, None) != 0
+    assert lib.fv_outconv_fwd(None, None, None, None, None, None, None, None, None, 1, 8, 128, 32, 3, 0, 1, 1.0, None, None) != 0
     assert b"null pointer" in lib.fv_last_error()
     assert lib.fv_outconv_dgrad(None, None, None, None, 1, 8, 128, 32, 3, None) != 0
-    assert lib.fv_outconv_wgrad(None, None, None, None, 1, 8, 128, 32, 3, None) != 0
+    assert lib.fv_outconv_wgrad(None, None, None, None, 1, 1, 8, 128, 32, 3, None) != 0
     assert lib.fv_outconv_prep(None, None, None, 3, 32, None) != 0
-    assert lib.fv_conv2d_stats(None, None, None, None, None, 0, 1, 8, 8, 16, 16, 16, 3, 3, 1, None, None) != 0
+    assert lib.fv_conv2d_stats(None, None, None, None, None, 0, 1, 8, 8, 16, 16, 16, 3, 3, 1, None, None, None) != 0
+    assert lib.fv_conv2d_x2(None, None, None, None, 0, 1, 8, 8, 16, 16, 16, None, None, None) != 0
+    assert lib.fv_conv2d_s2(None, None, None, None, 0, 1, 8, 8, 16, 16, 16, None, None, None) != 0
+    assert lib.fv_conv2d_wgrad(None, None, None, 1, 1, 8, 8, 16, 16, 3, 3, 1, None) != 0
+    assert lib.fv_conv2d_wgrad_x2(None, None, None, 1, 1, 8, 8, 16, 16, None) != 0
+    assert lib.fv_conv2d_wgrad_s2(None, None, None, 1, 1, 8, 8, 16, 16, None) != 0
+    assert lib.fv_wgrad_finish(None, 1, None, 16, 16, 3, 3, 16, 16, 0, None) != 0
+    assert lib.fv_wgrad_finish_up(None, 1, None, 16, 16, 16, 16, 0, None) != 0
+    assert lib.fv_weight_prep_up(None, None, None, 16, 16, 16, 16, None) != 0
+    assert lib.fv_weight_prep_s2(None, None, None, 16, 16, 16, 16, None) != 0
+    assert lib.fv_slab_sum(None, 1, 10, None, 10, 0, None) != 0
     assert lib.fv_weight_prep_batched(None, 1, 10, None) != 0
     assert lib.fv_adam_multi(None, 1, 10, 1e-3, 0.9, 0.999, 1e-8, None, None) != 0
     assert lib.fv_bn_act_fwd_fin(None, 0, None, 1.0, None, None, None, None, 0.1, 1e-5, None, None, 0, 0, 1, 8, 8, 16, 0, 1, None) != 0
     assert lib.fv_bn_act_bwd_apply_fin(None, 0, None, 0, 0, None, None, 1.0, None, None, None, None, 1, 8, 8, 16, 0, 1, None) != 0
+    # reductions refuse to run without their workspace (include/facevae_b200.h, `red_ws`)
+    one = ctypes.c_void_p(16)            # any non-null address: the checks fire before anything is dereferenced
+    assert lib.fv_bn_stats(one, 0, one, 64, 16, None, None) != 0 and b"workspace" in lib.fv_last_error()
+    assert lib.fv_colsum(one, one, 64, 16, None, None) != 0
+    assert lib.fv_recon_loss_flat(one, one, None, one, 64, 0, 1.0, None, None) != 0
 
 
-def test_zero_arena_hands_out_clean_aligned_slices():
+def test_reduction_workspace_and_split_planning(lib):
+    """Sizes the host allocates from: the reduction scratch and the number of partial slabs of the weight-gradient kernels
+    (deterministic: one slab per pixel split, added in split order by fv_wgrad_finish)."""
+    assert lib.fv_reduce_ws_bytes() >= 512 + 2048 * 1024 * 4
+    assert lib.fv_abi_version() == 2
+    sp = lib.fv_conv2d_wgrad_splits
+    # thin full-resolution layer (enc.1, 32 -> 64 at 256x256): ring schedule, one slab per CTA
+    assert 1 <= sp(0, 32, 256, 256, 32, 64, 3, 3) <= 148
+    # wide layer: generic schedule, groups x splits <= SM count
+    assert 1 <= sp(0, 32, 16, 16, 256, 256, 3, 3) <= 148
+    # up-sampling conv (x2 geometry, four phases) and the 4x4 stride-2 conv
+    assert 1 <= sp(1, 32, 32, 32, 256, 128, 2, 2) <= 37 and 1 <= sp(2, 32, 32, 32, 64, 128, 4, 4) <= 148
+    assert sp(0, 1, 8, 8, 24, 16, 3, 3) == 0            # unsupported channel count: the launch reports why
+    assert lib.fv_outconv_wgrad_splits(32, 256, 256) >= 1 and lib.fv_outconv_wgrad_splits(32, 64, 64) == 0
+    assert lib.fv_reparam_kl_parts(32, 4096) >= 1
+    # statistics of the x2 / s2 geometries: never for NCHW outputs
+    assert lib.fv_conv2d_geom_fuses_stats(1, 2, 32, 64, 64, 128, 64) == 0
+    assert lib.fv_conv2d_geom_fuses_stats(1, 0, 32, 16, 16, 256, 256) in (0, 1)
+
+
+def test_step_scope_collects_tagged_weights():
+    """ops.step_scope walks the module tree for 4-d weights and their ``prep_kind`` tag (plain / up-sampling / own prep);
+    with CPU parameters nothing is launched (the package has no CPU path) and the scope still batches the counters."""
     from face_vae_b200 import ops
-    arena = ops._ZeroArena()
-    dev = torch.device("cpu")
-    assert arena.take((4,), torch.float32, dev) is None                  # outside a step: the caller allocates for itself
-    arena.begin(dev)
-    a = arena.take((3, 5), torch.float32, dev)
-    b = arena.take((7,), torch.float64, dev)
-    assert a.shape == (3, 5) and b.dtype == torch.float64 and float(a.abs().sum()) == 0.0 and float(b.abs().sum()) == 0.0
-    assert (b.data_ptr() - a.data_ptr()) % 256 == 0 and b.data_ptr() != a.data_ptr()
-    a.fill_(3.0)
-    b.fill_(5.0)
-    need = arena.need
-    arena.begin(dev)                                                      # next step: same offsets, zeroed again
-    a2 = arena.take((3, 5), torch.float32, dev)
-    assert a2.data_ptr() == a.data_ptr() and float(a2.abs().sum()) == 0.0 and need > 0
-    n_big = arena.buf.numel()
-    assert arena.take((n_big,), torch.float32, dev) is None              # does not fit: the caller falls back to torch.zeros ...
-    arena.begin(dev)                                                      # ... and the arena has grown for the next step
-    assert arena.buf.numel() >= 4 * n_big
-    assert arena.take((n_big,), torch.float32, dev) is not None
+    from face_vae_b200.models import FaceVAE
+    m = FaceVAE()
+    kinds = {name: getattr(mod, "prep_kind", 0) for name, mod in m.named_modules() if getattr(getattr(mod, "weight", None), "dim", lambda: 0)() == 4}
+    assert kinds["up.0.layers.1.layers.0"] == ops.PREP_UP and kinds["enc.1.layers.0.layers.0"] == ops.PREP_PLAIN
+    assert kinds["out_conv"] == -1
+    t = torch.zeros((), dtype=torch.long)
+    with ops.step_scope(m):
+        ops.bump_counter(t)
+        assert int(t) == 0                # deferred to the end of the scope
+    assert int(t) == 1
+    ops.bump_counter(t)
+    assert int(t) == 2
 
 
 def test_fused_adam_refuses_cpu_tensors():
