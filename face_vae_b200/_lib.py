@@ -64,6 +64,7 @@ SIGNATURES = {
     "fv_pw_bwd_reduce": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
     "fv_pw_bwd_finalize": [_p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "fv_bn_finalize_xrank": [_p, _p, _i, _i, _p, _i, _d, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i, _i, _p],
+    "fv_bn_finalize_xrank_emulate": [_p, _p, _i, _p, _i, _d, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i, _i, _p],
     "fv_debug_mma_rate": [_i, _i, _i, _i, _i, _i, _p, _p],
     "fv_debug_trace_set": [_p],
 }

@@ -21,6 +21,7 @@ int fail(int code, const char* fmt, ...) {
 }
 
 int cuda_fail(cudaError_t e, const char* what) {
+    (void)cudaGetLastError();      // reported here: do not leave it behind for the next entry point's launch check
     return fail(FV_ERR_CUDA, "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
 }
 

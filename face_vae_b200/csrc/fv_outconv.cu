@@ -769,7 +769,9 @@ extern "C" __attribute__((visibility("default"))) int fv_outconv_fwd(const void*
     const size_t smem = (size_t)p.bar_off + (2 * p.ring + 4 * kAcc + 1) * 8 + 16 + 1024 + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        FV_CUDA(cudaFuncSetAttribute(fold_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cudaFuncAttributes fa;                      // the opt-in limit covers static + dynamic shared memory
+        FV_CUDA(cudaFuncGetAttributes(&fa, fold_conv_kernel<0>));
+        FV_CUDA(cudaFuncSetAttribute(fold_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
         attr_set = true;
     }
     fold_conv_kernel<0><<<grid, 352, smem, (cudaStream_t)stream>>>(tmA, tmW, p);
@@ -792,7 +794,9 @@ extern "C" __attribute__((visibility("default"))) int fv_outconv_dgrad(const voi
     const size_t smem = (size_t)p.bar_off + (2 * p.ring + 4 * kAcc + 1) * 8 + 16 + 1024 + 64;
     static bool attr_set = false;
     if (!attr_set) {
-        FV_CUDA(cudaFuncSetAttribute(fold_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cudaFuncAttributes fa;                      // the opt-in limit covers static + dynamic shared memory
+        FV_CUDA(cudaFuncGetAttributes(&fa, fold_conv_kernel<1>));
+        FV_CUDA(cudaFuncSetAttribute(fold_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
         attr_set = true;
     }
     fold_conv_kernel<1><<<grid, 608, smem, (cudaStream_t)stream>>>(tmW, tmW, p);

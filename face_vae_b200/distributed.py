@@ -88,12 +88,21 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
 class GradientReducer:
     """Bucketed mean all-reduce of parameter gradients, overlapped with backward.
 
-    Parameters are packed into buckets of ~``bucket_mb`` in reverse registration order (the order backward produces
-    them).  A post-accumulate-grad hook counts ready parameters; when a bucket completes, its gradients are flattened
-    and all-reduced (AVG) asynchronously on a side stream.  ``finish()`` waits and scatters the results back.
+    All gradients live in ONE flat fp32 buffer laid out in reverse registration order (the order backward produces them);
+    a bucket is a contiguous ~``bucket_mb`` slice of it.  A post-accumulate-grad hook counts ready parameters; when a
+    bucket completes, its gradients are moved into their slots with one multi-tensor copy, ``p.grad`` is re-pointed at the
+    slot views, and the slice is all-reduced IN PLACE on a side stream (NCCL, ``ReduceOp.AVG``) while backward continues.
+    ``finish()`` only joins the side stream: there is no flatten (``torch.cat``) and no copy back, and the optimiser reads
+    the averaged gradients straight from the flat buffer.
     Equivalent to DDP's reducer (the reference wraps every sub-model in DistributedDataParallel, logger.py:55) with
     smaller buckets: the default 25 MiB cap puts this 15 MB model in essentially one bucket, i.e. no overlap.
+
+    Stream discipline (round-1 ADVICE, high): the collective is issued synchronously *on the side stream*, i.e. the side
+    stream itself is ordered after NCCL's completion, and the compute stream joins the side stream in ``finish()`` --
+    nothing reads a bucket that NCCL may still be writing, in eager mode as well as under CUDA-graph capture.
     """
+
+    ALIGN = 64          # floats: slots start on 256-byte boundaries (vectorised optimiser loads)
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_mb: float = 2.0, process_group=None):
         self.group = process_group
@@ -111,11 +120,23 @@ class GradientReducer:
         if cur:
             self.buckets.append(cur)
         self._bucket_of = {}
+        self._slot = {}
+        self._range = []
+        off = 0
+        layout = []
         for bi, b in enumerate(self.buckets):
+            start = off
             for p in b:
                 self._bucket_of[id(p)] = bi
+                layout.append((p, off))
+                off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            self._range.append((start, off))
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros((max(off, 1),), dtype=torch.float32, device=dev)     # padding stays zero
+        for p, o in layout:
+            self._slot[id(p)] = self.flat[o:o + p.numel()].view(p.shape)
         self._pending = [len(b) for b in self.buckets]
-        self._inflight = []
+        self._launched = [False] * len(self.buckets)
         self._handles = []
         self.stream: Optional[torch.cuda.Stream] = None
         self.launched = 0
@@ -131,62 +152,45 @@ class GradientReducer:
 
     def _launch(self, bi: int) -> None:
         bucket = self.buckets[bi]
-        grads = [p.grad for p in bucket]
-        if grads[0].is_cuda:
+        lo, hi = self._range[bi]
+        # gather this bucket's gradients into their slots (one multi-tensor copy on the compute stream, right behind the
+        # kernels that produced them) and make the slots the parameters' .grad
+        src = [p.grad for p in bucket if p.grad is not None and p.grad.data_ptr() != self._slot[id(p)].data_ptr()]
+        dst = [self._slot[id(p)] for p in bucket if p.grad is not None and p.grad.data_ptr() != self._slot[id(p)].data_ptr()]
+        if src:
+            torch._foreach_copy_(dst, src)
+        for p in bucket:
+            if p.grad is None:                       # received no gradient this step: contributes zeros
+                self._slot[id(p)].zero_()
+            p.grad = self._slot[id(p)]
+        piece = self.flat[lo:hi]
+        if piece.is_cuda:
             if self.stream is None:
                 self.stream = torch.cuda.Stream()
-            cur = torch.cuda.current_stream()
-            self.stream.wait_stream(cur)
+            self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                flat = torch.cat([g.reshape(-1) for g in grads])
-                if not torch.cuda.is_current_stream_capturing():
-                    for g in grads:
-                        g.record_stream(self.stream)
-                work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+                # synchronous call = the SIDE stream waits for the collective; the host does not block
+                dist.all_reduce(piece, op=dist.ReduceOp.AVG, group=self.group)
         else:   # gloo (CPU tests): no AVG, no streams
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._inflight.append((bi, flat, work))
+            dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=self.group)
+            piece /= self.world
+        self._launched[bi] = True
         self.launched += 1
 
     def finish(self) -> None:
-        """Call after backward(): waits for every bucket and writes the averaged gradients back into ``.grad``."""
+        """Call after backward(): launches the buckets whose parameters received no gradient this step and joins the side
+        stream, after which every ``p.grad`` (a view of the flat buffer) holds the gradient averaged over the ranks."""
         if self.world == 1:
             return
-        for bi, n in enumerate(self._pending):     # buckets with parameters that received no gradient this step
-            if n > 0:
-                for p in self.buckets[bi]:
-                    if p.grad is None:
-                        p.grad = torch.zeros_like(p)
+        for bi in range(len(self.buckets)):
+            if not self._launched[bi]:
                 self._launch(bi)
-        for bi, flat, work in self._inflight:
-            work.wait()
-            bucket = self.buckets[bi]
-            ctx = torch.cuda.stream(self.stream) if (flat.is_cuda and self.stream is not None) else _null()
-            with ctx:
-                if not flat.is_cuda:
-                    flat /= self.world
-                off = 0
-                views = []
-                for p in bucket:
-                    n = p.numel()
-                    views.append(flat[off:off + n].view_as(p.grad))
-                    off += n
-                torch._foreach_copy_([p.grad for p in bucket], views)
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
-        self._inflight.clear()
         self._pending = [len(b) for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
 
     def remove(self) -> None:
         for h in self._handles:
             h.remove()
         self._handles.clear()
-
-
-class _null:
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *a):
-        return False

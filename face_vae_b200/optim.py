@@ -20,7 +20,11 @@ class FusedAdam(torch.optim.Optimizer):
         # descriptor tables: one set for eager steps and one for steps recorded into a CUDA graph (the graph's memcpy node reads
         # its pinned source again at every replay, so an eager step in between must not overwrite it)
         self._bufs = {}
-        self._max_n = 1
+        self._check_steps = False
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._check_steps = True
 
     def _init_state(self, p):
         st = self.state[p]
@@ -48,26 +52,42 @@ class FusedAdam(torch.optim.Optimizer):
             for p, st in zip(ps, states):          # state loaded from a torch.optim.Adam checkpoint: python / CPU step counts
                 if not torch.is_tensor(st["step"]) or st["step"].device != p.device or st["step"].dtype != torch.float32:
                     st["step"] = torch.tensor(float(st["step"]), dtype=torch.float32, device=p.device)
+            # one bias correction per launch: all tensors of a group are assumed to share their step count (they do when
+            # every parameter receives a gradient every step, which holds for this model; torch.optim.Adam state that
+            # disagrees is refused rather than silently mis-corrected -- checked only when state was loaded from outside)
             steps = [st["step"] for st in states]
+            if self._check_steps:
+                vals = {float(t) for t in steps}
+                if len(vals) > 1:
+                    raise _lib.FaceVaeError(f"FusedAdam: parameters of one group have different step counts {sorted(vals)}")
+                self._check_steps = False
             torch._foreach_add_(steps, 1.0)
-            key = (gi,) + tuple((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr())
-                                for p, st in zip(ps, states))
+            key = tuple((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr())
+                        for p, st in zip(ps, states))
+            # descriptor tables are per (parameter group, mode): a graph's memcpy node re-reads its pinned source at every
+            # replay, so eager steps and other groups must never write to it
             mode = "capture" if torch.cuda.is_current_stream_capturing() else "eager"
             nbytes = 40 * len(ps)
-            if not self._bufs or self._bufs["eager"]["host"].numel() != nbytes:
-                self._bufs = {m: {"host": torch.empty(nbytes, dtype=torch.uint8).pin_memory(),
-                                  "table": torch.empty(nbytes, dtype=torch.uint8, device=ps[0].device), "key": None}
-                              for m in ("eager", "capture")}
-            buf = self._bufs[mode]
+            buf = self._bufs.get((gi, mode))
+            if buf is None or buf["host"].numel() != nbytes:
+                buf = {"host": torch.empty(nbytes, dtype=torch.uint8).pin_memory(),
+                       "table": torch.empty(nbytes, dtype=torch.uint8, device=ps[0].device), "key": None, "copied": None,
+                       "max_n": 1}
+                self._bufs[(gi, mode)] = buf
             if key != buf["key"]:
                 rec = np.zeros((len(ps),), dtype=np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8")]))
                 for i, (p, st) in enumerate(zip(ps, states)):
                     rec[i] = (p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel())
+                if buf["copied"] is not None:
+                    buf["copied"].synchronize()          # the previous step's async H2D copy has read the pinned table
                 buf["host"].copy_(torch.from_numpy(rec.view(np.uint8).copy()))
                 buf["table"].copy_(buf["host"], non_blocking=True)   # stream-ordered (a memcpy node under graph capture)
-                self._max_n = max(p.numel() for p in ps)
+                if mode == "eager":
+                    buf["copied"] = torch.cuda.Event()
+                    buf["copied"].record()
+                buf["max_n"] = max(p.numel() for p in ps)
                 buf["key"] = key
             b1, b2 = group["betas"]
-            _lib.call("fv_adam_multi", buf["table"].data_ptr(), len(ps), self._max_n, float(group["lr"]), float(b1), float(b2),
+            _lib.call("fv_adam_multi", buf["table"].data_ptr(), len(ps), buf["max_n"], float(group["lr"]), float(b1), float(b2),
                       float(group["eps"]), steps[0].data_ptr(), torch.cuda.current_stream().cuda_stream)
         return loss

@@ -73,6 +73,7 @@ class VAETrainer:
         self.reducer = fdist.GradientReducer(params, bucket_mb) if world > 1 else None
         self._graph = None
         self._graph_key = None
+        self._cap_stream = None
         self.launches_per_step = None            # C-ABI kernel launches inside one captured step
 
     # -- eager ----------------------------------------------------------------------------------------------------
@@ -100,7 +101,12 @@ class VAETrainer:
         # replay), so it is restored in place afterwards: copied back if there was state, zeroed if there was none
         snap_opt = {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
                     for p, st in self.optimizer.state.items()}
-        side = torch.cuda.Stream()
+        # warm-up AND capture run on one dedicated stream, so that everything keyed by stream (the reduction workspace of
+        # ops._red_ws, the NCCL side stream's dependencies) already exists when the capture starts: nothing is allocated
+        # or zero-initialised inside the graph
+        if self._cap_stream is None:
+            self._cap_stream = torch.cuda.Stream()
+        side = self._cap_stream
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
@@ -112,14 +118,15 @@ class VAETrainer:
             for k, v in st.items():
                 if torch.is_tensor(v):
                     if p in snap_opt and k in snap_opt[p]:
-                        v.copy_(snap_opt[p][k])
+                        old = snap_opt[p][k]
+                        v.copy_(old) if torch.is_tensor(old) else v.fill_(float(old))   # a loaded checkpoint may hold python numbers
                     else:
                         v.zero_()
         graph = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
         l0 = _lib.launch_count
         from . import ops
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=self._cap_stream):
             with ops.step_scope(self.vae):
                 losses, generated, _, _ = self.g_full(self._static_d, self._static_eps, True)
                 total = sum(losses.values())

@@ -198,6 +198,13 @@ long long fv_xrank_buffer_floats(void);
 int fv_bn_finalize_xrank(const float* sums_local, void* peer_bufs_dev, int rank, int world, void* epoch_ctr, int mode, double count,
                          const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                          float* out, float* dgamma, float* dbeta, int accumulate, int C, void* stream);
+/* The same exchange with all `world` ranks emulated as the blocks of ONE cooperative launch on one GPU (block r = rank r):
+ * every per-rank array is the concatenation of the ranks' arrays; peer_bufs_dev points at `world` local buffers.  For the
+ * single-GPU parity test of the protocol (waiting kernels must be co-resident, which separate launches do not guarantee).
+ * A peer that never arrives is reported after FACEVAE_XRANK_TIMEOUT_S seconds of wall clock (default 600). */
+int fv_bn_finalize_xrank_emulate(const float* sums_local, void* peer_bufs_dev, int world, void* epoch_ctr, int mode, double count,
+                                 const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
+                                 float eps, float* out, float* dgamma, float* dbeta, int accumulate, int C, void* stream);
 
 /* ---- re-parameterisation (models.py:559-561) fused with KLDivergenceLoss (losses.py:385-393) ------------- */
 /* mu/logstd: fp32 rows of Dz values (Dz % 4 == 0, 16-byte aligned), row_stride apart; z[N,Dz] = mu + exp(logstd)*eps (NULL

@@ -1,0 +1,217 @@
+"""Layer-by-layer parity of the whole model at tight tolerance ("teacher forcing").
+
+End to end, a bf16 network cannot match an fp32 run of the reference to 2e-2 on its gradients -- ReLU masks decided on
+rounded pre-activations flip, for the reference's own bf16 autocast exactly as for this path -- so the
+end-to-end gradient check (test_parity_gpu.py) is bounded by the reference-autocast yardstick.  What CAN be tight is every
+layer on its own: the CUDA model is run block by block with the autograd graph cut between blocks; each block's input,
+upstream gradient, output, input gradient and parameter gradients are recorded; and the same block is evaluated on the CPU
+by oracle/emulate.py -- the reference's formulas (pinned against the unmodified reference classes in
+test_oracle_golden.py) with bf16 storage roundings at the points where the CUDA path stores bf16 -- on the CUDA path's own
+input and upstream gradient.  Whatever differs is then accumulation order plus isolated one-ulp roundings:
+
+    forward activations   per element  rtol 2e-2 (+ 4e-3 of the tensor's max)      [north_star: 2e-2]
+    gradients (dx, params) relative L2 <= 2e-2 per tensor (observed ~1e-3)          [north_star: 2e-2]
+    KL / fp32 quantities   rtol 1e-4;  running statistics rtol 1e-4
+
+A wrong 1/world factor, a missing BN coupling term or a mis-indexed tap in ANY layer's forward or backward shows up here
+as a >= 5 % error in that layer, at the CPU-anchor size and at BASELINE.json's batch 32 at 256x256."""
+import pytest
+import torch
+
+from oracle import emulate as E
+from oracle import facevae_oracle as O
+from tests import goldenlib as G
+
+pytestmark = pytest.mark.gpu
+
+FWD_RTOL, FWD_AFRAC = 2e-2, 4e-3
+GRAD_L2 = 2e-2
+
+
+@pytest.fixture(scope="module")
+def fv():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import face_vae_b200.functional as Fn
+    import face_vae_b200.models as MO
+    from face_vae_b200 import _lib, ops
+    _lib.call("fv_device_ok")
+
+    class NS:
+        functional, models, o = Fn, MO, ops
+    return NS
+
+
+def _nchw(t, c=None):
+    """NHWC bf16 / NCHW fp32 device tensor -> NCHW fp32 on the CPU (first c channels)."""
+    if t.dtype == torch.bfloat16:
+        t = t.float().permute(0, 3, 1, 2)
+    t = t.detach().float().cpu().contiguous()
+    return t if c is None else t[:, :c].contiguous()
+
+
+def _rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _check_fwd(name, got, ref):
+    G.check_like(got, ref, FWD_RTOL, FWD_AFRAC, name)
+
+
+def _check_grad(name, got, ref, report, scale=None):
+    """``scale``: magnitude of the block's weight gradient.  A conv bias in front of a training-mode batch norm has an
+    analytically zero gradient (the reference's autograd leaves fp32 noise of ~1e-7 of the weight gradient there, the CUDA
+    path returns exact zeros): such tensors are only required to stay at noise level."""
+    if scale is not None and float(ref.abs().max()) <= 1e-4 * scale:
+        assert float(got.abs().max()) <= 2e-3 * scale, (name, float(got.abs().max()), scale)
+        return
+    r = _rel_l2(got, ref)
+    report.append((r, name))
+    assert r <= GRAD_L2, f"{name}: relative L2 {r:.3e} > {GRAD_L2}"
+
+
+def _leaf_params(p, prefix):
+    sub = {}
+    for k, v in p.items():
+        if k.startswith(prefix):
+            sub[k] = v.clone() if "running" in k else v.clone().requires_grad_(True)
+    return sub
+
+
+def _run_layerwise(fv, cfg, n, hw, base):
+    Fn, ops = fv.functional, fv.o
+    from face_vae_b200.ops import OUT_NHWC_BF16
+    p = O.det_anchor_params(cfg, base)
+    x_cpu, eps_cpu = O.det_inputs(n, hw, hw, cfg, base)
+    m = fv.models.FaceVAE(cfg.down_seq, cfg.up_seq, cfg.n_res)
+    sd = m.state_dict()
+    for k, v in p.items():
+        sd[k] = v.clone()
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    x, eps = x_cpu.cuda(), eps_cpu.cuda()
+
+    # ------------------------------------------------------------------ CUDA: forward block by block, graph cut between blocks
+    recs = []                                   # (name, input leaf, output)
+    last = len(m.enc) - 1
+    out = m.enc[0].forward_from_frames(x)
+    recs.append(("enc.0", x, out))
+    for i in range(1, last + 1):
+        inp = out.detach().requires_grad_(True)
+        out = m.enc[i].forward_nhwc(inp, out_nchw_f32=(i == last))
+        recs.append((f"enc.{i}", inp, out))
+    h = out.detach().requires_grad_(True)       # fp32 NCHW (mu | logstd)
+    b, c2, hh, ww = h.shape
+    dz = cfg.zc * hh * ww
+    z, kl = Fn.ReparamKL.apply(h.view(b, 2 * dz), eps)
+    recs.append(("vae", h, (z, kl)))
+    zin = z.detach().view(b, cfg.zc, hh, ww).requires_grad_(True)
+    out = Fn.ConvOnly.apply(Fn.ToNHWC.apply(zin), m.mid_conv.weight, m.mid_conv.bias, 1, OUT_NHWC_BF16)
+    recs.append(("mid_conv", zin, out))
+    for r, blk in enumerate(m.res):
+        inp = out.detach().requires_grad_(True)
+        out = blk.forward_nhwc(inp)
+        recs.append((f"res.{r}", inp, out))
+    for i, blk in enumerate(m.up):
+        inp = out.detach().requires_grad_(True)
+        out = blk.forward_nhwc(inp)
+        recs.append((f"up.{i}", inp, out))
+    dl = out.detach().requires_grad_(True)
+    x_hat, rec = Fn.ConvSigmoidRecon.apply(dl, m.out_conv.weight, m.out_conv.bias, x, False)
+    recs.append(("out_conv", dl, (x_hat, rec)))
+    # ------------------------------------------------------------------ CUDA: backward block by block
+    gouts = {}
+    (cfg.w_rec * rec).backward()
+    g_next = dl.grad
+    for name, inp, outp in reversed(recs[:-1]):
+        gouts[name] = g_next
+        if name == "vae":
+            torch.autograd.backward([outp[0], outp[1]], [g_next.reshape(b, dz).contiguous(), torch.tensor(cfg.w_kl, device="cuda")])
+        else:
+            outp.backward(g_next)
+        g_next = inp.grad
+    torch.cuda.synchronize()
+    grads = {k: v.grad.detach().cpu() for k, v in m.named_parameters()}
+    bufs = {k: v.detach().cpu() for k, v in m.named_buffers()}
+
+    # ------------------------------------------------------------------ CPU: the same blocks through the emulation
+    report = []
+    prec = E.BF16
+    folded = ops.outconv_supported(n, hw, hw, cfg.up_seq[-1], 3, 7)
+    n_enc = len(cfg.down_seq) - 1
+    for name, inp, outp in recs:
+        upd = {}
+        if name.startswith("enc."):
+            i = int(name.split(".")[1])
+            prefix = "enc.0.layers.layers." if i == 0 else f"enc.{i}.layers.0.layers."
+            lp = _leaf_params(p, prefix)
+            xin = (x_cpu if i == 0 else _nchw(inp, cfg.down_seq[i])).requires_grad_(i > 0)
+            y = E.cna_block(xin, lp, prefix, 1 if i == 0 else 3, prec, post="none" if i == 0 else "pool", out_fp32=(i == n_enc - 1),
+                            updates=upd, first_layer_pointwise=(i == 0))
+            y.backward(_nchw(gouts[name], cfg.down_seq[i + 1]))
+            _check_fwd(name + " out", _nchw(outp, cfg.down_seq[i + 1]), y.detach())
+        elif name == "vae":
+            hin = _nchw(inp).requires_grad_(True)
+            mu, ls, zz = O.reparameterise(hin, eps_cpu, True, cfg.zc)
+            K = O.kl_divergence(mu, ls)
+            torch.autograd.backward([zz, K], [_nchw(gouts[name]), torch.tensor(cfg.w_kl)])
+            torch.testing.assert_close(outp[0].detach().cpu().view_as(zz), zz.detach(), rtol=1e-5, atol=1e-5)
+            assert abs(outp[1].item() - K.item()) <= 1e-4 * abs(K.item()), (outp[1].item(), K.item())      # KL: rtol 1e-4
+            torch.testing.assert_close(inp.grad.cpu(), hin.grad, rtol=1e-4, atol=1e-7)
+            continue
+        elif name == "mid_conv":
+            lp = _leaf_params(p, "mid_conv.")
+            xin = _nchw(inp).requires_grad_(True)
+            y = E.mid_conv(xin, lp, prec)
+            y.backward(_nchw(gouts[name], cfg.up_seq[0]))
+            _check_fwd(name + " out", _nchw(outp, cfg.up_seq[0]), y.detach())
+        elif name.startswith("res."):
+            lp = _leaf_params(p, name + ".")
+            xin = _nchw(inp, cfg.up_seq[0]).requires_grad_(True)
+            y = E.res_block(xin, lp, name + ".", prec, updates=upd)
+            y.backward(_nchw(gouts[name], cfg.up_seq[0]))
+            _check_fwd(name + " out", _nchw(outp, cfg.up_seq[0]), y.detach())
+        elif name.startswith("up."):
+            i = int(name.split(".")[1])
+            prefix = f"up.{i}.layers.1.layers."
+            lp = _leaf_params(p, prefix)
+            xin = _nchw(inp, cfg.up_seq[i]).requires_grad_(True)
+            y = E.cna_block(xin, lp, prefix, 3, prec, upsample=True, updates=upd)
+            y.backward(_nchw(gouts[name], cfg.up_seq[i + 1]))
+            _check_fwd(name + " out", _nchw(outp, cfg.up_seq[i + 1]), y.detach())
+        else:                                    # out_conv + sigmoid + reconstruction loss
+            lp = _leaf_params(p, "out_conv.")
+            xin = _nchw(inp, cfg.up_seq[-1]).requires_grad_(True)
+            xh, R, _ = E.out_conv_loss(xin, x_cpu, lp, prec, cfg.w_rec, folded)
+            (cfg.w_rec * R).backward()
+            assert abs(outp[1].item() - R.item()) <= 1e-3 * abs(R.item()), (outp[1].item(), R.item())
+            _check_fwd(name + " x_hat", outp[0].detach().cpu(), xh.detach())
+        if xin.requires_grad:
+            c_in = xin.shape[1]
+            _check_grad(name + " dx", _nchw(inp.grad, c_in), xin.grad, report)
+        wscale = max(float(v.grad.abs().max()) for k, v in lp.items() if v.requires_grad and v.dim() == 4)
+        for k, v in lp.items():
+            if v.requires_grad:
+                _check_grad(k, grads[k], v.grad, report, wscale)
+        for k, v in upd.items():                  # running statistics: fp32 quantities, rtol 1e-4
+            torch.testing.assert_close(bufs[k], v.detach(), rtol=1e-4, atol=1e-6)
+    report.sort(reverse=True)
+    print(f"layer-wise parity n={n} {hw}x{hw}: largest gradient relative L2:", [(f"{r:.2e}", k) for r, k in report[:5]])
+    return report
+
+
+def test_layerwise_parity_cpu_anchor_size(fv):
+    """BASELINE.json configs[0]: batch 4 at 64x64."""
+    _run_layerwise(fv, O.CFG_256, 4, 64, 0)
+
+
+def test_layerwise_parity_batch32_256(fv):
+    """BASELINE.json configs[1]: batch 32 at 256x256 -- the ring kernels, the folded out_conv kernels, the output-channel split
+    and the persistent 148-CTA schedules only run at this size."""
+    _run_layerwise(fv, O.CFG_256, 32, 256, 7)
+
+
+def test_layerwise_parity_512_deep(fv):
+    """BASELINE.json configs[3] architecture (512 channels, 64-channel latent) at 128x128, batch 4."""
+    _run_layerwise(fv, O.CFG_512, 4, 128, 2)
