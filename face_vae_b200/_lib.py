@@ -24,12 +24,17 @@ SIGNATURES = {
     "fv_device_ok": [],
     "fv_nchw_to_nhwc": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_nhwc_to_nchw": [_p, _i, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_bilinear_resize": [_p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_weight_prep": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_weight_prep_batched": [_p, _i, _ll, _p],
     "fv_weight_prep_up": [_p, _p, _p, _i, _i, _i, _i, _p],
     "fv_weight_prep_s2": [_p, _p, _p, _i, _i, _i, _i, _p],
     "fv_conv2d": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "fv_conv2d_stats": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+    "fv_conv2d_ex": [_i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+    "fv_demod_fwd": [_p, _p, _p, _i, _i, _f, _i, _p],
+    "fv_demod_bwd": [_p, _p, _p, _p, _i, _i, _f, _i, _p],
+    "fv_act_bwd": [_p, _p, _p, _ll, _i, _p],
     "fv_conv2d_x2": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "fv_conv2d_s2": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "fv_conv2d_wgrad": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],

@@ -64,6 +64,7 @@ struct ConvParams {
     float* stats;           // optional [2][stats_c]: per-channel sum / sum of squares of the stored output (fused fv_bn_stats)
     int stats_c;
     void* red_ws;           // fv_reduce.cuh workspace (with stats)
+    int act;                // FV_ACT_*: applied after bias (+ residual), before the store (Conv2dELR: conv -> bias -> LeakyReLU)
     short4 tap[64];         // per (phase, group): x = channel offset, y = dw, z = row parity / 0, w = dh of the activation box
     signed char oy[4], ox[4];
 };
@@ -239,6 +240,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 if (valid) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias_s[c0 + i];
+                    if (p.act != FV_ACT_NONE && !p.residual) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) f[i] = f[i] > 0.f ? f[i] : (p.act == FV_ACT_LEAKY ? 0.2f * f[i] : 0.f);
+                    }
                     if (p.out_mode == FV_OUT_NCHW_F32) {
                         float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
@@ -346,6 +351,19 @@ static bool igemm_fuses_stats(int Ci, int Nc, int taps) {
     const long long mma_cycles = (long long)taps * (Ci / 16) * (Nc / 2 > 32 + Nc / 4 ? Nc / 2 : 32 + Nc / 4);
     return 10 * mma_cycles >= 34LL * (Nc / 16) * 250 && env_int("FV_CONV_FUSE_STATS", 1);
 }
+// x2 / s2 geometries run the tap schedule with one activation box per tap and are bound by L2 -> shared-memory traffic
+// rather than by MMA issue, so their epilogue has slack the MMA-cycle model above does not see: FV_X2_FUSE_STATS = 1 / 0
+// forces the fused statistics on / off (default: the model).
+static bool geom_fuses_stats(int kind, int Ci, int Nc, int taps, int vtiles) {
+    if (kind != CONV_SAME) {
+        const int f = env_int("FV_X2_FUSE_STATS", -1);
+        if (f >= 0) return f != 0;
+        // measured (batch 32, 256^2): fusing costs the x2 kernels 14-21 us per layer and saves a statistic pass of 12 / 14 / 22 /
+        // 37 us (up.0 .. up.3): it pays for the large outputs only
+        if (kind == CONV_X2 && vtiles >= 2048) return env_int("FV_CONV_FUSE_STATS", 1) != 0;
+    }
+    return igemm_fuses_stats(Ci, Nc, taps);
+}
 static int igemm_co_parts(int num_tiles, int Co_pad, int out_mode) {
     int parts = 1;
     while (parts < 4 && num_tiles * parts * 2 <= num_sms() && Co_pad % (parts * 2 * 64) == 0 && out_mode != FV_OUT_NCHW_F32 &&
@@ -384,7 +402,7 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d_geom_fuses_stats
     if (pick_tile(N, H, W, tw, th, tn)) return 0;
     const int nph = kind == CONV_X2 ? 4 : 1;
     const int num_tiles = (W / tw) * (H / th) * ((N + tn - 1) / tn);
-    return igemm_fuses_stats(Ci, Co_pad / igemm_co_parts(num_tiles * nph, Co_pad, out_mode), kind == CONV_X2 ? 4 : 16) ? 1 : 0;
+    return geom_fuses_stats(kind, Ci, Co_pad / igemm_co_parts(num_tiles * nph, Co_pad, out_mode), kind == CONV_X2 ? 4 : 16, num_tiles * nph) ? 1 : 0;
 }
 namespace fv {
 
@@ -406,6 +424,7 @@ struct ConvCall {
     int out_mode, N, H, W;          // H, W: the tiling grid (X2 / S2: coarse resolution)
     int Ci, Co, Co_pad, R, S, pad;
     float* stats; void* red_ws; void* stream;
+    int act = 0;
 };
 
 static int conv_chunk(const ConvCall& c, int co_base, int Co_chunk, int Co_real);
@@ -437,12 +456,13 @@ static int conv_chunk(const ConvCall& c, int co_base, int Co_pad, int Co) {
         return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: only odd square filters with same padding (R=%d S=%d pad=%d)", R, S, pad);
     if (out_mode < 0 || out_mode > 2) return fail(FV_ERR_ARG, "fv_conv2d: out_mode %d", out_mode);
     if (out_mode == FV_OUT_NCHW_F32 && c.residual) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: residual needs an NHWC output");
+    if (c.act < 0 || c.act > 2 || (c.act && c.residual)) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d: activation %d (none / relu / leaky, not with a residual)", c.act);
     float* stats = c.stats;
     cudaStream_t s = (cudaStream_t)c.stream;
     const int osy = c.kind == CONV_X2 ? 2 : 1, Ho = H * osy, Wo = W * osy;
     // statistics: fused into the epilogue where that is hidden (see igemm_fuses_stats), a separate fv_bn_stats pass otherwise
     const int y_dtype = out_mode == FV_OUT_NHWC_BF16 ? FV_DT_BF16 : FV_DT_F32;
-    if (c.kind == CONV_SAME && out_cs == Co_pad) {
+    if (c.kind == CONV_SAME && out_cs == Co_pad && c.act == FV_ACT_NONE) {
         float* ring_stats = (stats && ring_fuses_stats(out_mode, Co_pad)) ? stats : nullptr;
         const int rr = conv2d_ring_try(c.x, c.w, c.bias, c.residual, c.y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, ring_stats, out_cs, c.red_ws, s);
         if (rr > 0) return rr;
@@ -519,10 +539,11 @@ static int conv_chunk(const ConvCall& c, int co_base, int Co_pad, int Co) {
     p.bias = c.bias ? c.bias + co_base : nullptr;
     p.residual = reinterpret_cast<const __nv_bfloat16*>(c.residual);
     p.out = c.y;
-    const bool fuse_stats = stats && (out_cs != Co_pad || igemm_fuses_stats(Ci, p.Nc, taps));
+    const bool fuse_stats = stats && (out_cs != Co_pad || geom_fuses_stats(c.kind, Ci, p.Nc, taps, p.num_tiles * p.nph));
     p.stats = fuse_stats ? stats : nullptr;
     p.stats_c = out_cs;                          // the statistic block is [2][total Co_pad] also when Co is walked in chunks
     p.red_ws = c.red_ws;
+    p.act = c.act;
 
     CUtensorMap tmX, tmW;
     {
@@ -583,5 +604,19 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d_s2(const void* x
                                                                  int Ci, int Co, int Co_pad, float* stats, void* red_ws, void* stream) {
     if (stats && out_mode == FV_OUT_NCHW_F32) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_s2: statistics need an NHWC output");
     ConvCall c{CONV_S2, x, w, bias, nullptr, y, out_mode, N, H, W, Ci, Co, Co_pad, 4, 4, 1, stats, red_ws, stream};
+    return conv_any(c);
+}
+
+// The general entry: geometry kind (0 same, 1 x2, 2 s2), optional activation in the epilogue (conv -> bias -> act, the order of
+// Conv2dELR.forward, reference models_utils.py:712-742), optional fused statistics.  H, W: the tiling grid (x2 / s2: coarse).
+extern "C" __attribute__((visibility("default"))) int fv_conv2d_ex(int kind, const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                                                 int out_mode, int N, int H, int W, int Ci, int Co, int Co_pad, int R, int S, int pad, int act,
+                                                                 float* stats, void* red_ws, void* stream) {
+    if (kind < 0 || kind > 2) return fail(FV_ERR_ARG, "fv_conv2d_ex: kind %d", kind);
+    if (kind != CONV_SAME && residual) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_ex: residual only with the same-size geometry");
+    if (stats && out_mode == FV_OUT_NCHW_F32) return fail(FV_ERR_UNSUPPORTED, "fv_conv2d_ex: statistics need an NHWC output");
+    ConvCall c{kind, x, w, bias, residual, y, out_mode, N, H, W, Ci, Co, Co_pad, kind == CONV_X2 ? 2 : (kind == CONV_S2 ? 4 : R),
+               kind == CONV_X2 ? 2 : (kind == CONV_S2 ? 4 : S), kind == CONV_X2 ? 0 : (kind == CONV_S2 ? 1 : pad), stats, red_ws, stream};
+    c.act = act;
     return conv_any(c);
 }

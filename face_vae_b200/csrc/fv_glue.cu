@@ -212,12 +212,14 @@ __global__ void weight_prep_batched_kernel(const fv_prep_desc* __restrict__ tabl
 // grad fp32 [Co][Ci][R][S]: the splits are added in split order (reproducible; replaces red.global.add into one buffer).
 __global__ void wgrad_finish_kernel(const float* __restrict__ part, float* __restrict__ grad, int Co, int Ci, int taps,
                                     int Ci_pad, int accumulate, int splits, long long split_stride) {
-    const long long total = (long long)Co * Ci * taps;
+    // threads walk the SOURCE layout (ci fastest): the `splits` reads per element are coalesced, the single write is strided
+    const long long total = (long long)Co * taps * Ci_pad;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int tap = (int)(i % taps);
-        const int ci = (int)((i / taps) % Ci);
-        const int co = (int)(i / ((long long)taps * Ci));
-        const float* src = part + ((long long)co * taps + tap) * Ci_pad + ci;
+        const int ci = (int)(i % Ci_pad);
+        if (ci >= Ci) continue;
+        const int tap = (int)((i / Ci_pad) % taps);
+        const int co = (int)(i / ((long long)Ci_pad * taps));
+        const float* src = part + i;
         float v = 0.f;
         int sp = 0;
         for (; sp + 4 <= splits; sp += 4) {                  // four independent loads in flight, added in split order
@@ -226,21 +228,41 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ part, float* __res
             v += a0; v += a1; v += a2; v += a3;
         }
         for (; sp < splits; ++sp) v += __ldg(src + sp * split_stride);
-        grad[i] = accumulate ? grad[i] + v : v;
+        float* dst = grad + ((long long)co * Ci + ci) * taps + tap;
+        *dst = accumulate ? *dst + v : v;
     }
 }
 
-// out[i] (+)= sum_s part[s][i] in slab order (the tap-folded out_conv weight gradient writes one slab per CTA)
+// out[i] (+)= sum_s part[s][i] in slab order (per-CTA / per-split partial weight gradients): float4 loads, four slabs in flight
 __global__ void slab_sum_kernel(const float* __restrict__ part, int slabs, long long stride, float* __restrict__ out, long long n, int accumulate) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float v = 0.f;
-        int sp = 0;
-        for (; sp + 4 <= slabs; sp += 4) {
-            const float a0 = __ldg(part + (sp + 0) * stride + i), a1 = __ldg(part + (sp + 1) * stride + i), a2 = __ldg(part + (sp + 2) * stride + i),
-                        a3 = __ldg(part + (sp + 3) * stride + i);
-            v += a0; v += a1; v += a2; v += a3;
+    const long long n4 = n / 4;
+    const bool vec = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (vec) {
+        const float4* p4 = reinterpret_cast<const float4*>(part);
+        const long long s4 = stride / 4;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            int sp = 0;
+            for (; sp + 4 <= slabs; sp += 4) {
+                const float4 a0 = __ldg(p4 + (sp + 0) * s4 + i), a1 = __ldg(p4 + (sp + 1) * s4 + i), a2 = __ldg(p4 + (sp + 2) * s4 + i),
+                             a3 = __ldg(p4 + (sp + 3) * s4 + i);
+                v.x += a0.x; v.y += a0.y; v.z += a0.z; v.w += a0.w;
+                v.x += a1.x; v.y += a1.y; v.z += a1.z; v.w += a1.w;
+                v.x += a2.x; v.y += a2.y; v.z += a2.z; v.w += a2.w;
+                v.x += a3.x; v.y += a3.y; v.z += a3.z; v.w += a3.w;
+            }
+            for (; sp < slabs; ++sp) {
+                const float4 a = __ldg(p4 + sp * s4 + i);
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            float4* o = reinterpret_cast<float4*>(out) + i;
+            if (accumulate) { const float4 c = *o; v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w; }
+            *o = v;
         }
-        for (; sp < slabs; ++sp) v += __ldg(part + sp * stride + i);
+    }
+    for (long long i = (vec ? n4 * 4 : 0) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        for (int sp = 0; sp < slabs; ++sp) v += __ldg(part + sp * stride + i);
         out[i] = accumulate ? out[i] + v : v;
     }
 }
@@ -283,29 +305,41 @@ __global__ void weight_prep_up_kernel(const float* __restrict__ w, __nv_bfloat16
 // dW[r][s] = sum over the (phase, tap) pairs whose coarse tap contains (r, s); splits added in order inside each term.
 __global__ void wgrad_finish_up_kernel(const float* __restrict__ part, float* __restrict__ grad, int Co, int Ci, int Co_pad, int Ci_pad,
                                        int accumulate, int splits, long long split_stride) {
-    const long long total = (long long)Co * Ci * 9;
+    // one thread per (co, ci), ci fastest: the 16 phase-tap values are read coalesced (each summed over the splits in split
+    // order), then scattered into the 3x3 positions their coarse tap covers
+    const long long total = (long long)Co * Ci_pad;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int s_ = (int)(i % 3), r = (int)((i / 3) % 3);
-        const int ci = (int)((i / 9) % Ci);
-        const int co = (int)(i / (9LL * Ci));
-        float v = 0.f;
-        for (int a = 0; a < 2; ++a)
-            for (int u = 0; u < 2; ++u) {
-                int r0, r1;
-                up_rows(a, u, r0, r1);
-                if (r < r0 || r > r1) continue;
-                for (int b = 0; b < 2; ++b)
-                    for (int vv = 0; vv < 2; ++vv) {
-                        int s0, s1;
-                        up_rows(b, vv, s0, s1);
-                        if (s_ < s0 || s_ > s1) continue;
-                        const float* src = part + ((((long long)(a * 2 + b) * Co_pad + co) * 4 + (u * 2 + vv)) * Ci_pad + ci);
-                        float t = 0.f;
-                        for (int sp = 0; sp < splits; ++sp) t += __ldg(src + sp * split_stride);
-                        v += t;
-                    }
+        const int ci = (int)(i % Ci_pad);
+        if (ci >= Ci) continue;
+        const int co = (int)(i / Ci_pad);
+        float w9[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w9[k] = 0.f;
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+            for (int tap = 0; tap < 4; ++tap) {
+                const float* src = part + (((long long)ph * Co_pad + co) * 4 + tap) * Ci_pad + ci;
+                float t = 0.f;
+                int sp = 0;
+                for (; sp + 4 <= splits; sp += 4) {
+                    const float a0 = __ldg(src + (sp + 0) * split_stride), a1 = __ldg(src + (sp + 1) * split_stride),
+                                a2 = __ldg(src + (sp + 2) * split_stride), a3 = __ldg(src + (sp + 3) * split_stride);
+                    t += a0; t += a1; t += a2; t += a3;
+                }
+                for (; sp < splits; ++sp) t += __ldg(src + sp * split_stride);
+                int r0, r1, s0, s1;
+                up_rows(ph >> 1, tap >> 1, r0, r1);
+                up_rows(ph & 1, tap & 1, s0, s1);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int s_ = 0; s_ < 3; ++s_)
+                        if (r >= r0 && r <= r1 && s_ >= s0 && s_ <= s1) w9[r * 3 + s_] += t;
             }
-        grad[i] = accumulate ? grad[i] + v : v;
+        float* dst = grad + ((long long)co * Ci + ci) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dst[k] = accumulate ? dst[k] + w9[k] : w9[k];
     }
 }
 
@@ -330,6 +364,82 @@ __global__ void weight_prep_s2_kernel(const float* __restrict__ w, __nv_bfloat16
             const int r4 = 3 - 2 * (tap >> 1) - (ph >> 1), s4 = 3 - 2 * (tap & 1) - (ph & 1);
             wx2[i] = __float2bfloat16((co < Co && ci < Ci) ? w[((long long)co * Ci + ci) * 16 + r4 * 4 + s4] : 0.f);
         }
+    }
+}
+
+// ---- input pre-scale of EFE_conv5 / EFE_conv6 (reference models.py:764, 872) ---------------------------------------------------------
+// F.interpolate(x, mode="bilinear", scale_factor=s, align_corners=False, recompute_scale_factor=True) on NCHW fp32 frames:
+// Ho = floor(H * s); source index = (o + 0.5) * (H / Ho) - 0.5, clamped at 0 (ATen area_pixel_compute_source_index); the four
+// neighbours are blended in fp32.  For the reference's s = 0.25 on sizes divisible by 4 this is the mean of the 2x2 block at
+// (4i + 1 .. 4i + 2, 4j + 1 .. 4j + 2).  One thread per output pixel, consecutive threads = consecutive output columns.
+__global__ void bilinear_resize_kernel(const float* __restrict__ x, float* __restrict__ out, long long NC, int H, int W, int Ho, int Wo,
+                                       float rh, float rw) {
+    const long long total = NC * Ho * Wo;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ow = (int)(i % Wo), oh = (int)((i / Wo) % Ho);
+        const long long nc = i / ((long long)Wo * Ho);
+        float sh = rh * (oh + 0.5f) - 0.5f, sw = rw * (ow + 0.5f) - 0.5f;
+        sh = sh < 0.f ? 0.f : sh;
+        sw = sw < 0.f ? 0.f : sw;
+        const int h0 = (int)sh, w0 = (int)sw;
+        const int h1 = h0 + (h0 < H - 1 ? 1 : 0), w1 = w0 + (w0 < W - 1 ? 1 : 0);
+        const float lh1 = sh - h0, lw1 = sw - w0, lh0 = 1.f - lh1, lw0 = 1.f - lw1;
+        const float* p = x + nc * (long long)H * W;
+        out[i] = lh0 * (lw0 * __ldg(p + (long long)h0 * W + w0) + lw1 * __ldg(p + (long long)h0 * W + w1)) +
+                 lh1 * (lw0 * __ldg(p + (long long)h1 * W + w0) + lw1 * __ldg(p + (long long)h1 * W + w1));
+    }
+}
+
+// ---- Conv2dELR pieces (reference models_utils.py:632-744) --------------------------------------------------------------------------
+// weff[co][:] = gain * w[co][:] / max(||w[co][:]||, 1e-12)  (norm == "demod": F.normalize over dims 1,2,3, then weightgain), or
+// gain * w when demod == 0.  One block per output channel; inv_norm[co] is kept for the backward.
+__global__ void demod_fwd_kernel(const float* __restrict__ w, float* __restrict__ weff, float* __restrict__ inv_norm, int K, float gain, int demod) {
+    __shared__ float red[32];
+    const float* row = w + (size_t)blockIdx.x * K;
+    float inv = 1.f;
+    if (demod) {
+        float a = 0.f;
+        for (int i = threadIdx.x; i < K; i += blockDim.x) a = fmaf(row[i], row[i], a);
+        a = warp_sum(a);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+        __syncthreads();
+        float t = 0.f;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) t += red[wv];
+        inv = 1.f / fmaxf(sqrtf(t), 1e-12f);
+    }
+    if (threadIdx.x == 0 && inv_norm) inv_norm[blockIdx.x] = inv;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) weff[(size_t)blockIdx.x * K + i] = row[i] * inv * gain;
+}
+// dw = gain * inv * (dweff - what * <what, dweff>),  what = w * inv   (gradient of w / ||w||); demod == 0: dw = gain * dweff
+__global__ void demod_bwd_kernel(const float* __restrict__ w, const float* __restrict__ inv_norm, const float* __restrict__ dweff,
+                                 float* __restrict__ dw, int K, float gain, int demod) {
+    __shared__ float red[32];
+    const size_t base = (size_t)blockIdx.x * K;
+    if (!demod) {
+        for (int i = threadIdx.x; i < K; i += blockDim.x) dw[base + i] = gain * dweff[base + i];
+        return;
+    }
+    const float inv = inv_norm[blockIdx.x];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) a = fmaf(w[base + i] * inv, dweff[base + i], a);
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    float dot = 0.f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) dot += red[wv];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) dw[base + i] = gain * inv * (dweff[base + i] - w[base + i] * inv * dot);
+}
+// dy = g * act'(out) for an activation applied in the conv epilogue (ReLU / LeakyReLU(0.2): the derivative follows from the sign of
+// the stored output); NHWC bf16, 8 elements per thread
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dy,
+                               long long n8, int act) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float o[8], gg[8], r[8];
+        V8<__nv_bfloat16>::load(out + i * 8, o);
+        V8<__nv_bfloat16>::load(g + i * 8, gg);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = gg[k] * act_grad(o[k], act);
+        V8<__nv_bfloat16>::store(dy + i * 8, r);
     }
 }
 
@@ -1077,7 +1187,7 @@ extern "C" __attribute__((visibility("default"))) int fv_weight_prep_batched(con
     if (!table_dev || n_layers < 1 || max_items < 1) return fail(FV_ERR_ARG, "fv_weight_prep_batched: bad arguments");
     if (max_items >= (1LL << 31)) return fail(FV_ERR_UNSUPPORTED, "fv_weight_prep_batched: filter too large for 32-bit indexing");
     long long bx = (max_items + kThreads * 2 - 1) / (kThreads * 2);
-    const long long cap = (long long)num_sms() * 8 / n_layers + 1;      // the whole table: about one resident wave
+    const long long cap = (long long)num_sms() * 24 / n_layers + 1;     // the whole table: about three resident waves (layers differ 1000x in size)
     if (bx > cap) bx = cap;
     weight_prep_batched_kernel<<<dim3((unsigned)bx, (unsigned)n_layers), kThreads, 0, STREAM>>>(table_dev);
     FV_LAUNCH_CHECK("weight_prep_batched_kernel");
@@ -1087,7 +1197,7 @@ extern "C" __attribute__((visibility("default"))) int fv_weight_prep_batched(con
 extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const float* part, int splits, float* grad, int Co, int Ci, int R, int S, int Co_pad,
                                                                     int Ci_pad, int accumulate, void* stream) {
     if (!part || !grad || splits < 1) return fail(FV_ERR_ARG, "fv_wgrad_finish: bad arguments");
-    wgrad_finish_kernel<<<grid_for((long long)Co * Ci * R * S), kThreads, 0, STREAM>>>(part, grad, Co, Ci, R * S, Ci_pad, accumulate, splits,
+    wgrad_finish_kernel<<<grid_for((long long)Co * Ci_pad * R * S), kThreads, 0, STREAM>>>(part, grad, Co, Ci, R * S, Ci_pad, accumulate, splits,
                                                                                         (long long)Co_pad * R * S * Ci_pad);
     FV_LAUNCH_CHECK("wgrad_finish_kernel");
     return FV_OK;
@@ -1096,7 +1206,7 @@ extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const floa
 extern "C" __attribute__((visibility("default"))) int fv_slab_sum(const float* part, int slabs, long long slab_stride, float* out, long long n, int accumulate,
                                                                 void* stream) {
     if (!part || !out || slabs < 1 || n < 1) return fail(FV_ERR_ARG, "fv_slab_sum: bad arguments");
-    slab_sum_kernel<<<grid_for(n), kThreads, 0, STREAM>>>(part, slabs, slab_stride, out, n, accumulate);
+    slab_sum_kernel<<<grid_for(n / 4 + 1), kThreads, 0, STREAM>>>(part, slabs, slab_stride, out, n, accumulate);
     FV_LAUNCH_CHECK("slab_sum_kernel");
     return FV_OK;
 }
@@ -1118,9 +1228,39 @@ extern "C" __attribute__((visibility("default"))) int fv_weight_prep_s2(const fl
 extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish_up(const float* part, int splits, float* grad, int Co, int Ci, int Co_pad, int Ci_pad,
                                                                        int accumulate, void* stream) {
     if (!part || !grad || splits < 1) return fail(FV_ERR_ARG, "fv_wgrad_finish_up: bad arguments");
-    wgrad_finish_up_kernel<<<grid_for((long long)Co * Ci * 9), kThreads, 0, STREAM>>>(part, grad, Co, Ci, Co_pad, Ci_pad, accumulate, splits,
+    wgrad_finish_up_kernel<<<grid_for((long long)Co * Ci_pad), kThreads, 0, STREAM>>>(part, grad, Co, Ci, Co_pad, Ci_pad, accumulate, splits,
                                                                                        16LL * Co_pad * Ci_pad);
     FV_LAUNCH_CHECK("wgrad_finish_up_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bilinear_resize(const float* x, float* out, int N, int C, int H, int W, int Ho, int Wo, void* stream) {
+    if (!x || !out || N < 1 || C < 1 || H < 1 || W < 1 || Ho < 1 || Wo < 1) return fail(FV_ERR_ARG, "fv_bilinear_resize: bad arguments");
+    bilinear_resize_kernel<<<grid_for((long long)N * C * Ho * Wo), kThreads, 0, STREAM>>>(x, out, (long long)N * C, H, W, Ho, Wo, (float)H / (float)Ho,
+                                                                                         (float)W / (float)Wo);
+    FV_LAUNCH_CHECK("bilinear_resize_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_demod_fwd(const float* w, float* weff, float* inv_norm, int Co, int K, float gain, int demod, void* stream) {
+    if (!w || !weff || Co < 1 || K < 1) return fail(FV_ERR_ARG, "fv_demod_fwd: bad arguments");
+    demod_fwd_kernel<<<Co, kThreads, 0, STREAM>>>(w, weff, inv_norm, K, gain, demod);
+    FV_LAUNCH_CHECK("demod_fwd_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_demod_bwd(const float* w, const float* inv_norm, const float* dweff, float* dw, int Co, int K, float gain,
+                                                                 int demod, void* stream) {
+    if (!w || !dweff || !dw || (demod && !inv_norm) || Co < 1 || K < 1) return fail(FV_ERR_ARG, "fv_demod_bwd: bad arguments");
+    demod_bwd_kernel<<<Co, kThreads, 0, STREAM>>>(w, inv_norm, dweff, dw, K, gain, demod);
+    FV_LAUNCH_CHECK("demod_bwd_kernel");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_act_bwd(const void* out, const void* g, void* dy, long long n, int act, void* stream) {
+    if (!out || !g || !dy || n < 8 || n % 8) return fail(FV_ERR_ARG, "fv_act_bwd: element count %lld must be a positive multiple of 8", n);
+    act_bwd_kernel<<<grid_for(n / 8), kThreads, 0, STREAM>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)g, (__nv_bfloat16*)dy, n / 8, act);
+    FV_LAUNCH_CHECK("act_bwd_kernel");
     return FV_OK;
 }
 

@@ -2,7 +2,7 @@
 //
 // fp32 atomics add in arrival order, so two runs of the same step differed in the last bits of every batch-norm sum; bf16
 // rounding and ReLU masks amplify that to percent-level differences of the encoder gradients (round-1 VERDICT, weak #1).
-// Here every block stores its partial vector, the LAST block of each group of 32 blocks (ticket counter) adds the group's
+// Here every block stores its partial vector, the LAST block of each group of 64 blocks (ticket counter) adds the group's
 // rows in block order, and the last group to finish adds the group rows in group order: a fixed summation tree for a
 // given grid, i.e. bitwise-reproducible results, at the price of ~1-2 us at the tail of the kernel.  The block that ends up
 // with the totals continues with whatever follows (statistic finalize, cross-rank exchange), which is what used to be a
@@ -16,8 +16,8 @@
 
 namespace fv {
 
-static constexpr int kRedGroup = 32;          // blocks per first-level group
-static constexpr int kRedMaxGroups = 64;      // => grids of up to 2048 blocks
+static constexpr int kRedGroup = 64;          // blocks per first-level group (grids of <= 64 blocks: one level)
+static constexpr int kRedMaxGroups = 32;      // => grids of up to 2048 blocks
 static constexpr int kRedTicketBytes = 512;   // word 0: finished groups; word 1 + g: finished blocks of group g
 
 __host__ __device__ inline size_t det_reduce_ws_bytes(int max_blocks, int n, int elem_size) {
@@ -50,22 +50,30 @@ __device__ __forceinline__ bool det_reduce(void* ws, int n, int nb, int b, const
     T* part2 = reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + kRedTicketBytes);
     T* part = part2 + (size_t)kRedMaxGroups * n;
     for (int c = tid; c < n; c += nthr) part[(size_t)b * n + c] = my[c];
-    __threadfence();
+    // release / acquire through ONE thread: the barrier orders every thread's stores before thread 0's gpu-scope fence
+    // (fences are cumulative), and thread 0's fence after the ticket orders the other blocks' stores before the barrier
+    // that lets this block's threads read them (with L2 loads) -- a fence per thread costs ~1 us per level
     sync();
     const int grp = b / kRedGroup, g0 = grp * kRedGroup;
     const int gsz = nb - g0 < kRedGroup ? nb - g0 : kRedGroup;
     const int ngroups = (nb + kRedGroup - 1) / kRedGroup;
-    if (tid == 0) *flag = (atomicAdd(&tickets[1 + grp], 1u) == (unsigned)(gsz - 1));
+    if (tid == 0) {
+        __threadfence();
+        *flag = (atomicAdd(&tickets[1 + grp], 1u) == (unsigned)(gsz - 1));
+        __threadfence();
+    }
     sync();
     if (!*flag) return false;
-    __threadfence();
     for (int c = tid; c < n; c += nthr) {
-        T v[kRedGroup];
+        T a = T(0);
+        for (int j0 = 0; j0 < kRedGroup; j0 += 32) {           // 32 independent L2 loads in flight, added in block order
+            if (j0 >= gsz) break;
+            T v[32];
 #pragma unroll
-        for (int j = 0; j < kRedGroup; ++j) v[j] = j < gsz ? ld_l2(part + (size_t)(g0 + j) * n + c) : T(0);
-        T a = v[0];
+            for (int j = 0; j < 32; ++j) v[j] = j0 + j < gsz ? ld_l2(part + (size_t)(g0 + j0 + j) * n + c) : T(0);
 #pragma unroll
-        for (int j = 1; j < kRedGroup; ++j) a += v[j];
+            for (int j = 0; j < 32; ++j) a += v[j];
+        }
         if (ngroups == 1) tot[c] = a;
         else part2[(size_t)grp * n + c] = a;
     }
@@ -74,12 +82,14 @@ __device__ __forceinline__ bool det_reduce(void* ws, int n, int nb, int b, const
         if (tid == 0) tickets[1] = 0u;
         return true;
     }
-    __threadfence();
     sync();
-    if (tid == 0) *flag = (atomicAdd(&tickets[0], 1u) == (unsigned)(ngroups - 1));
+    if (tid == 0) {
+        __threadfence();
+        *flag = (atomicAdd(&tickets[0], 1u) == (unsigned)(ngroups - 1));
+        __threadfence();
+    }
     sync();
     if (!*flag) return false;
-    __threadfence();
     for (int c = tid; c < n; c += nthr) {
         T a = T(0);
         for (int g = 0; g < ngroups; g += 16) {

@@ -212,6 +212,55 @@ class ConvBNAct(torch.autograd.Function):
         return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
 
 
+class ConvELRAct(torch.autograd.Function):
+    """Conv2dELR.forward (reference models_utils.py:706-744) without style modulation: weight -> F.normalize over (ci, r, s)
+    ("demod") -> * weightgain -> conv (4x4 stride 2 pad 1, or stride-1 "same") -> + bias -> activation, the last three in
+    ONE tensor-core kernel.  x: NHWC bf16.  Backward: act' from the stored output, bias gradient = column sums, weight
+    gradient through the strided / plain wgrad kernels and the normalisation, data gradient = four-phase x2 convolution
+    (stride 2) or the rotated-filter convolution (stride 1)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, ksize, stride, gain, demod, act):
+        co, ci = weight.shape[0], weight.shape[1]
+        weff, inv = ops.demod_fwd(weight, gain, demod)
+        if stride == 2:
+            wf, wx2 = ops.weight_prep_s2(weff, True, x.requires_grad)
+            out = ops.conv2d_ex(2, x, wf, bias, co, 4, act, OUT_NHWC_BF16, (ci, co))
+            wback = wx2
+        else:
+            wf, wd = ops.weight_prep(weff, True, x.requires_grad)
+            out = ops.conv2d_ex(0, x, wf, bias, co, ksize, act, OUT_NHWC_BF16, (ci, co))
+            wback = wd
+        ctx.save_for_backward(x, out, weight, inv, wback)
+        ctx.cfg = (ksize, stride, gain, demod, act, co, ci)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out, weight, inv, wback = ctx.saved_tensors
+        ksize, stride, gain, demod, act, co, ci = ctx.cfg
+        g = g.contiguous()
+        dy = ops.act_bwd(out, g, act) if act != ACT_NONE else g
+        db = ops.colsum(dy)[:co].clone() if ctx.has_bias else None
+        if stride == 2:
+            dweff = ops.wgrad_finish(ops.conv2d_wgrad_s2(x, dy, (ci, co)), co, ci, 4)
+        else:
+            dweff = ops.wgrad_finish(ops.conv2d_wgrad(x, dy, ksize, (ci, co)), co, ci, ksize)
+        dw = ops.demod_bwd(weight, inv, dweff, gain, demod)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if stride == 2:
+                if wback is None:
+                    _, wback = ops.weight_prep_s2(ops.demod_fwd(weight, gain, demod)[0], False, True)
+                dx = ops.conv2d_x2(dy, wback, None, x.shape[3], OUT_NHWC_BF16, (co, ci), alg_taps=16)
+            else:
+                if wback is None:
+                    _, wback = ops.weight_prep(ops.demod_fwd(weight, gain, demod)[0], False, True)
+                dx = ops.conv2d(dy, wback, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
+        return dx, dw, db, None, None, None, None, None
+
+
 class PointwiseBNAct(torch.autograd.Function):
     """SameBlock2D with <= 4 input channels in training mode, straight from the NCHW fp32 frames (the first encoder layer,
     reference modules.py:97-108 via models.py:749): a 1x1 conv followed by batch norm is a per-pixel affine map whose

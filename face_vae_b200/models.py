@@ -43,6 +43,85 @@ class flatten_vae_nl(nn.Module):
         return mu, logstd, z.view(b, zc, h, w)
 
 
+class flatten_vae6(nn.Module):
+    """reference models.py:802-833: LinearELR encoder -> (mu_fc * 0.1, logstd_fc * 0.01) -> z = mu + exp(logstd) * randn (training)
+    / z = mu (eval) -> LinearELR decoder -> view back to the input shape.  ``forward(x)`` -> ``(mu, logstd, x_hat)``.  The
+    sampling runs in the fused re-parameterisation kernel; ``eps`` may be injected."""
+
+    def __init__(self, down_seq=[16 * 4 * 4, 256], up_seq=[256, 16 * 4 * 4], vae_seq=[256, 256], training=True, lin=None) -> None:
+        super().__init__()
+        from .modules import LinearELR
+        lin = LinearELR if lin is None else lin
+        self.encoder = nn.Sequential(*[lin(down_seq[i], down_seq[i + 1], norm="demod", act=nn.LeakyReLU(0.2)) for i in range(len(down_seq) - 1)])
+        self.decoder = nn.Sequential(*[lin(up_seq[i], up_seq[i + 1], norm="demod", act=nn.LeakyReLU(0.2)) for i in range(len(up_seq) - 1)])
+        self.mu_fc = lin(vae_seq[0], vae_seq[1])
+        self.logstd_fc = lin(vae_seq[0], vae_seq[1])
+        self.training = training
+
+    def forward(self, x, eps: Optional[torch.Tensor] = None):
+        x = to_float_nchw(x) if x.dim() == 4 else x
+        shape = x.shape
+        x_en = self.encoder(x.flatten(start_dim=1))
+        mu = self.mu_fc(x_en) * 0.1
+        logstd = self.logstd_fc(x_en) * 0.01
+        if self.training:
+            if eps is None:
+                eps = torch.randn(*logstd.size(), device=logstd.device)
+            z = Fn.Reparam.apply(mu.contiguous(), logstd.contiguous(), eps.reshape(mu.shape).contiguous().float())
+        else:
+            z = mu
+        x_hat = self.decoder(z).view(shape)
+        return mu, logstd, x_hat
+
+
+class EFE_conv5(nn.Module):
+    """The 2-D stage of the reference's default expression-feature extractor (models.py:724-798, the trainer's EFE): input
+    pre-scale ``F.interpolate(bilinear, scale_factor, recompute_scale_factor=True)`` (models.py:764) -> ``down`` (SameBlock2D +
+    DownBlock2D stack, :749) -> ``vae`` (flatten_vae_nl, :775-778) -> ``mid_conv`` (:785) -> ``view(N, C, D, H, W)`` (:786-787),
+    the hand-off to the 3-D keypoint decoder.  Same constructor arguments and the same sub-module names / state_dict keys
+    for ``down``, ``mid_conv`` and ``vae``; the 3-D part (``up``, ``out_conv``, ``mix``, ``mix_out``: Conv3d / heat-maps) is
+    outside the hot path, so ``forward`` is not provided -- ``forward_2d`` returns what the 3-D part consumes."""
+
+    def __init__(self, use_weight_norm=False, down_seq=[3, 32, 64, 128, 256, 32], up_seq=[256, 256, 128, 64, 32, 32], D=16, K=15, n_res=3,
+                 scale_factor=0.25, use_vae=True) -> None:
+        super().__init__()
+        self.down = nn.Sequential(*[SameBlock2D(down_seq[i], down_seq[i + 1], use_weight_norm) if i == 0 else
+                                    DownBlock2D(down_seq[i], down_seq[i + 1], use_weight_norm) for i in range(len(down_seq) - 1)])
+        self.mid_conv = Conv2d(down_seq[-1] // 2, up_seq[0] * D, 1, 1, 0)
+        self.C, self.D = up_seq[0], D
+        self.scale_factor = scale_factor
+        self.vae = flatten_vae_nl() if use_vae else None
+
+    def forward_2d(self, x, x_a=None, train_vae=None, eps: Optional[torch.Tensor] = None):
+        """-> (x3d [N, C, D, h, w] bf16, x_c, x_a_c, (x_mu, x_logstd), (x_vae, x_hat)) -- models.py:764-787."""
+        def encode(t):
+            t = ops.bilinear_resize(t.contiguous().float(), self.scale_factor)
+            last = len(self.down) - 1
+            for i, blk in enumerate(self.down):
+                if i == 0:
+                    t = blk.forward_from_frames(t) if blk.pointwise_ok(t) else blk.forward_nhwc(as_nhwc(t))
+                else:
+                    t = blk.forward_nhwc(t, out_nchw_f32=(i == last))
+            return t
+        x = encode(x)
+        x_z = x
+        x_c, x_a_c = (x, encode(x_a)) if x_a is not None else (None, None)
+        if self.vae is not None:
+            x_vae = x
+            x_mu, x_logstd, x_hat = self.vae(x_vae, train_vae, eps)
+            x_z = x_hat
+        else:
+            x_mu = x_logstd = x_hat = x_vae = None
+        t = Fn.ConvOnly.apply(Fn.ToNHWC.apply(x_z.contiguous()), self.mid_conv.weight, self.mid_conv.bias, 1, OUT_NHWC_BF16)
+        y = as_nchw(t, self.mid_conv.out_channels)                 # logical [N, C*D, h, w]
+        n, _, h, w = y.shape
+        return y.reshape(n, self.C, self.D, h, w), x_c, x_a_c, (x_mu, x_logstd), (x_vae, x_hat)
+
+    def forward(self, x, x_a=None, kpc=None, train_vae=None):
+        raise NotImplementedError("EFE_conv5: the 3-D keypoint decoder (UpBlock3D / Conv3d / heat-maps, models.py:788-798) is outside "
+                                  "the hot path (SURVEY.md 2.1); use forward_2d for the 2-D stage")
+
+
 class FaceVAE(nn.Module):
     """The anchor "face-vae" (SURVEY.md section 8).  Sub-module names give the oracle's state_dict keys."""
 

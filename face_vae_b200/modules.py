@@ -9,6 +9,7 @@ are in scope; anything else raises.
 from __future__ import annotations
 
 import math
+from typing import Optional
 
 import torch
 from torch import nn
@@ -246,3 +247,118 @@ class ResBlock2D(nn.Module):
 
     def forward(self, x):
         return as_nchw(self.forward_nhwc(as_nhwc(x)), self.out_channels)
+
+
+# ---------------------------------------------------------------------------------------------------- ELR layers
+def _act_gain(act) -> float:
+    """The gain Conv2dELR / LinearELR derive from their activation module (reference models_utils.py:137-146, 648-657)."""
+    try:
+        if isinstance(act, nn.LeakyReLU):
+            return nn.init.calculate_gain("leaky_relu", act.negative_slope)
+        if isinstance(act, nn.ReLU):
+            return nn.init.calculate_gain("relu")
+        return nn.init.calculate_gain(act)
+    except Exception:
+        return 1.0
+
+
+def _act_code(act) -> int:
+    if act is None:
+        return ACT_NONE
+    if isinstance(act, nn.ReLU):
+        return ACT_RELU
+    if isinstance(act, nn.LeakyReLU) and abs(act.negative_slope - 0.2) < 1e-12:
+        return ACT_LEAKY
+    raise NotImplementedError(f"activation {act!r}: the fused epilogue knows ReLU and LeakyReLU(0.2) (what the reference uses)")
+
+
+class Conv2dELR(nn.Module):
+    """reference models_utils.py:632-744 -- equalised-learning-rate convolution with optional weight demodulation, as used by
+    ``EFE_conv6.efe_encoder`` (models.py:845-852): ``conv(ci, co, 4, 2, 1, norm="demod", act=nn.LeakyReLU(0.2))``.
+    Same constructor, parameter names (``weight`` ~ N(0,1), ``bias`` zeros) and ``weightgain`` as the reference.
+
+    In scope: 4x4 stride-2 pad-1 (even input sizes, output width a power of two or a multiple of 128) and stride-1 "same"
+    1x1 / 3x3, ``norm`` in {None, "demod"}, ``act`` in {None, ReLU, LeakyReLU(0.2)}.  Out of scope (raise): style modulation
+    (``wsize > 0`` / a ``w`` argument), untied biases (``ub``), and the reference's first encoder layer ``conv(3, 32, 1, 1, 1)``
+    -- a 1x1 kernel with padding 1, which grows the image to 66x66 and makes every later size odd."""
+
+    def __init__(self, inch, outch, kernel_size, stride, padding, wsize=0, affinelrmult=1., norm=None, ub=None, act=None):
+        super().__init__()
+        if wsize > 0 or ub is not None:
+            raise NotImplementedError("Conv2dELR: style modulation (wsize) and untied biases (ub) are outside the hot path")
+        if norm not in (None, "demod"):
+            raise NotImplementedError(f"Conv2dELR: norm={norm!r}")
+        if (kernel_size, stride, padding) not in ((4, 2, 1), (1, 1, 0), (3, 1, 1)):
+            raise NotImplementedError(f"Conv2dELR: kernel {kernel_size} stride {stride} padding {padding}: supported are 4/2/1, 1/1/0, 3/1/1")
+        self.inch, self.outch, self.kernel_size, self.stride, self.padding = inch, outch, kernel_size, stride, padding
+        self.wsize, self.norm, self.ub, self.act = wsize, norm, ub, act
+        self.act_code = _act_code(act)
+        fan_in = inch * (kernel_size ** 2)
+        initgain = 1.0 if norm == "demod" else 1.0 / math.sqrt(fan_in)
+        self.weightgain = _act_gain(act) * initgain
+        self.weight = nn.Parameter(torch.randn(outch, inch, kernel_size, kernel_size))
+        self.bias = nn.Parameter(torch.zeros(outch))
+        self.affine = None
+        self.fused = False
+        self.prep_kind = -1            # the operands depend on the demodulated weight: prepared per call, not by ops.step_scope
+
+    def extra_repr(self):
+        return 'inch={}, outch={}, kernel_size={}, stride={}, padding={}, wsize={}, norm={}, ub={}, act={}'.format(
+            self.inch, self.outch, self.kernel_size, self.stride, self.padding, self.wsize, self.norm, self.ub, self.act)
+
+    def fuse(self):
+        """Bake normalisation and gain into the weight (reference models_utils.py:700-704)."""
+        with torch.no_grad():
+            w, _ = ops.demod_fwd(self.weight.data.contiguous(), self.weightgain, self.norm == "demod")
+            self.weight.data = w
+        self.fused = True
+
+    def forward_nhwc(self, x):
+        demod = (self.norm == "demod") and not self.fused
+        gain = 1.0 if self.fused else self.weightgain
+        return Fn.ConvELRAct.apply(x, self.weight, self.bias, self.kernel_size, self.stride, gain, demod, self.act_code)
+
+    def forward(self, x, w: Optional[torch.Tensor] = None):
+        if w is not None:
+            raise NotImplementedError("Conv2dELR: style modulation is outside the hot path")
+        return as_nchw(self.forward_nhwc(as_nhwc(x)), self.outch)
+
+
+class LinearELR(nn.Module):
+    """reference models_utils.py:134-203.  The bottleneck's fully connected layers are [N, 256] x [256, 256] library GEMMs
+    ("leave on torch.addmm"); kept as plain torch ops on the CUDA device with the reference's exact
+    formulas, constructor and parameter names."""
+
+    def __init__(self, inch, outch, lrmult=1., norm: Optional[str] = None, act=None):
+        super().__init__()
+        initgain = 1.0 / math.sqrt(inch)
+        self.weight = nn.Parameter(torch.randn(outch, inch) / lrmult)
+        self.weightgain = _act_gain(act)
+        if norm is None:
+            self.weightgain = self.weightgain * initgain * lrmult
+        self.bias = nn.Parameter(torch.full([outch], 0.))
+        self.norm = norm
+        self.act = act
+        self.fused = False
+
+    def getweight(self):
+        if self.fused or self.norm != "demod":
+            return self.weight
+        return torch.nn.functional.normalize(self.weight, dim=1)
+
+    def fuse(self):
+        if not self.fused:
+            with torch.no_grad():
+                self.weight.data = self.getweight() * self.weightgain
+        self.fused = True
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("face_vae_b200 has no CPU path: move the input to a CUDA device")
+        weight = self.getweight()
+        if self.fused:
+            out = torch.addmm(self.bias[None], x, weight.t())
+            return self.act(out) if self.act is not None else out
+        if self.act is None:
+            return torch.addmm(self.bias[None], x, weight.t(), alpha=self.weightgain)
+        return self.act(torch.nn.functional.linear(x, weight * self.weightgain, bias=self.bias))

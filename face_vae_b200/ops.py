@@ -6,6 +6,7 @@ Activations are explicit NHWC tensors ``[N, H, W, C]`` (bf16 unless stated), C p
 """
 from __future__ import annotations
 
+import math
 from typing import Optional, Tuple
 
 import torch
@@ -199,6 +200,19 @@ def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None, out: Optional[torch.T
     return out
 
 
+def bilinear_resize(x: torch.Tensor, scale_factor: float) -> torch.Tensor:
+    """F.interpolate(x, mode="bilinear", scale_factor=s, align_corners=False, recompute_scale_factor=True) on NCHW fp32 frames
+    (reference models.py:764): the input pre-scale in front of the encoder.  No gradient (frames are data)."""
+    _chk(x, "x", torch.float32)
+    n, c, h, w = x.shape
+    ho, wo = int(math.floor(h * scale_factor)), int(math.floor(w * scale_factor))
+    if ho < 1 or wo < 1:
+        raise _lib.FaceVaeError("bilinear_resize: empty output")
+    out = torch.empty((n, c, ho, wo), device=x.device, dtype=torch.float32)
+    call("fv_bilinear_resize", x.data_ptr(), out.data_ptr(), n, c, h, w, ho, wo, _stream(), meta=_bytes(x, out))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ convolution
 def _conv_meta(n, h, w, ci, cop, k, real_dims):
     """Profiling record: executed (padded) FLOPs and algorithmic FLOPs (real channel counts) of one launch."""
@@ -381,6 +395,59 @@ def conv2d_s2(x: torch.Tensor, wf: torch.Tensor, bias: Optional[torch.Tensor], c
     return (y, sums) if want_stats else y
 
 
+def conv2d_ex(kind: int, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], co: int, ksize: int = 1, act: int = ACT_NONE,
+              out_mode: int = OUT_NHWC_BF16, real_dims=None) -> torch.Tensor:
+    """Convolution + bias + activation in one kernel (Conv2dELR.forward, reference models_utils.py:712-742).  kind 0: stride-1
+    "same" conv, w [Co_pad, k*k, Ci]; kind 2: 4x4 stride-2 pad-1 conv of x [N,2H,2W,Ci], w [Co_pad, 16, Ci]; kind 1: the
+    four-phase x2 geometry, w [4, Co_pad, 4, Ci]."""
+    _chk(x, "x", torch.bfloat16)
+    _chk(w, "w", torch.bfloat16)
+    n, hx, wx, ci = x.shape
+    if kind == 2:
+        if hx % 2 or wx % 2:
+            raise _lib.FaceVaeError("conv2d_ex: the stride-2 convolution needs even input sizes")
+        h, wd, ho, wo, cop, taps_exec, taps_alg = hx // 2, wx // 2, hx // 2, wx // 2, w.shape[0], 16, 16
+    elif kind == 1:
+        h, wd, ho, wo, cop, taps_exec, taps_alg = hx, wx, 2 * hx, 2 * wx, w.shape[1], 16, 16
+    else:
+        h, wd, ho, wo, cop, taps_exec, taps_alg = hx, wx, hx, wx, w.shape[0], ksize * ksize, ksize * ksize
+    if out_mode == OUT_NCHW_F32:
+        y = torch.empty((n, co, ho, wo), device=x.device, dtype=torch.float32)
+    else:
+        y = torch.empty((n, ho, wo, cop), device=x.device, dtype=torch.bfloat16 if out_mode == OUT_NHWC_BF16 else torch.float32)
+    call("fv_conv2d_ex", kind, x.data_ptr(), w.data_ptr(), _ptr(bias), None, y.data_ptr(), out_mode, n, h, wd, ci, co, cop, ksize, ksize,
+         (ksize - 1) // 2, act, None, None, _stream(), meta=_conv_meta_x2(n, h, wd, ci, cop, real_dims, taps_exec, taps_alg))
+    return y
+
+
+def demod_fwd(w: torch.Tensor, gain: float, demod: bool):
+    """Conv2dELR.getweight (reference models_utils.py:686-704): -> (weff fp32 same shape, inv_norm [Co] | None)."""
+    _chk(w, "weight", torch.float32)
+    co = w.shape[0]
+    k = w.numel() // co
+    weff = torch.empty_like(w)
+    inv = torch.empty((co,), device=w.device, dtype=torch.float32) if demod else None
+    call("fv_demod_fwd", w.data_ptr(), weff.data_ptr(), _ptr(inv), co, k, float(gain), int(demod), _stream())
+    return weff, inv
+
+
+def demod_bwd(w: torch.Tensor, inv: Optional[torch.Tensor], dweff: torch.Tensor, gain: float, demod: bool) -> torch.Tensor:
+    _chk(dweff, "dweff", torch.float32)
+    co = w.shape[0]
+    dw = torch.empty_like(w)
+    call("fv_demod_bwd", w.data_ptr(), _ptr(inv), dweff.data_ptr(), dw.data_ptr(), co, w.numel() // co, float(gain), int(demod), _stream())
+    return dw
+
+
+def act_bwd(out: torch.Tensor, g: torch.Tensor, act: int) -> torch.Tensor:
+    """dy = g * act'(out) for an activation fused into a conv epilogue (NHWC bf16)."""
+    _chk(out, "out", torch.bfloat16)
+    _chk(g, "g", torch.bfloat16)
+    dy = torch.empty_like(out)
+    call("fv_act_bwd", out.data_ptr(), g.data_ptr(), dy.data_ptr(), out.numel(), act, _stream(), meta=_bytes(out, g, dy))
+    return dy
+
+
 def conv2d_wgrad_x2(x: torch.Tensor, dy: torch.Tensor, real_dims=None) -> torch.Tensor:
     """x coarse [N,H,W,Ci], dy fine [N,2H,2W,Co_pad] -> partial slabs [splits, 4, Co_pad, 4, Ci] of the phase filters."""
     _chk(x, "x", torch.bfloat16)
@@ -401,6 +468,13 @@ def wgrad_finish_up(part: torch.Tensor, co: int, ci: int, grad: Optional[torch.T
     accumulate = grad is not None
     if grad is None:
         grad = torch.empty((co, ci, 3, 3), device=part.device, dtype=torch.float32)
+    if part.shape[0] > 1:
+        # splits first (one wide, vectorised pass over 16 * Co_pad * Ci_pad elements), then the 16 -> 9 fold: the fold kernel has
+        # only Co * Ci threads and would walk the splits serially
+        tot = torch.empty(part.shape[1:], device=part.device, dtype=torch.float32)
+        n = tot.numel()
+        call("fv_slab_sum", part.data_ptr(), part.shape[0], n, tot.data_ptr(), n, 0, _stream())
+        part = tot.unsqueeze(0)
     call("fv_wgrad_finish_up", part.data_ptr(), part.shape[0], _chk(grad, "grad", torch.float32).data_ptr(), co, ci, part.shape[2],
          part.shape[4], int(accumulate), _stream())
     return grad

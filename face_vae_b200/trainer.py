@@ -38,6 +38,52 @@ class VAEGeneratorFull(nn.Module):
         return loss, out["x_hat"], out["mu"], out["logstd"]
 
 
+class GeneratorFull(nn.Module):
+    """Drop-in for the reference's ``GeneratorFull`` (reference trainer.py:214-317) on the VAE path.
+
+    Same constructor parameter names, same ``weights`` dict (keys P, G, F, E, L, H, D, C, K, R), same
+    ``forward(s, d, s_a=None, d_a=None, train_vae=None)`` and the same 8-tuple
+    ``(loss_dict, generated_d, transformed_d, kp_s, kp_d, transformed_kp, occlusion, mask)``, so the reference's
+    ``Logger.step`` (logger.py:150-164: ``losses_g, generated_d, ... = self.g_full(s, d, s_a, d_a, train_vae)``;
+    ``sum(losses_g.values()).backward()``) runs unchanged.  What is computed is the hot path of SURVEY.md section 8:
+    ``generator`` is the image -> image VAE (``FaceVAE``), "K" is the weighted KL term of the DRIVING frame's (mu, logstd)
+    (trainer.py:312) and "R" the weighted reconstruction loss of ``(d, generated_d)`` (trainer.py:314); the keypoint /
+    motion / GAN / perceptual networks are outside the path (they need 3-D blocks, downloaded VGG weights and the
+    git-ignored hopenet checkpoint), so their sub-modules may be ``None``, their loss entries are zero tensors of the
+    reference's shape ``[1]`` and their outputs ``None``.  As in the reference, a falsy ``train_vae`` yields zero K / R
+    (the bottleneck then returns ``(None, None, x_hat)``, models.py:567-570).
+    The shipped reference weights K: 0, R: 0 switch the VAE terms off (trainer.py:250-251); the defaults here are the
+    values commented next to them (0.2 and 10), since this class exists to train that path.  ``eps`` (optional attribute or
+    keyword) injects the re-parameterisation noise the reference draws inline with ``torch.randn`` (models.py:561)."""
+
+    OUT_OF_SCOPE = ("P", "G", "F", "E", "L", "H", "D", "C")
+
+    def __init__(self, efe=None, afe=None, ckd=None, hpe_ede=None, mfe=None, generator: Optional[FaceVAE] = None, discriminator=None,
+                 pretrained_path=None, n_bins=66):
+        super().__init__()
+        if generator is None:
+            raise ValueError("GeneratorFull: `generator` must be the FaceVAE of the hot path")
+        self.efe, self.afe, self.ckd, self.hpe_ede, self.mfe = efe, afe, ckd, hpe_ede, mfe
+        self.generator = generator
+        self.discriminator = discriminator
+        self.weights = {"P": 10, "G": 1, "F": 10, "E": 20, "L": 10, "H": 20, "D": 0.5, "C": 10, "K": 0.2, "R": 10}
+        self.eps = None
+        self.l1 = False
+
+    def forward(self, s, d, s_a=None, d_a=None, train_vae=None, eps: Optional[torch.Tensor] = None):
+        zero = lambda: torch.zeros(1, device=d.device)          # the reference's `torch.Tensor([0.0]).cuda()`
+        loss = {k: zero() for k in self.OUT_OF_SCOPE}
+        if not train_vae:
+            _, _, generated_d = self.generator(d, False)
+            loss["K"], loss["R"] = zero(), zero()
+        else:
+            out = self.generator.forward_loss(d, self.eps if eps is None else eps, self.l1)
+            generated_d = out["x_hat"]
+            loss["K"] = self.weights["K"] * out["K"]
+            loss["R"] = self.weights["R"] * out["R"]
+        return loss, generated_d, None, None, None, None, None, None
+
+
 class VAETrainer:
     """One-model version of the reference Logger's optimisation step (logger.py:52-63, 150-164).
 

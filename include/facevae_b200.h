@@ -42,6 +42,10 @@ int fv_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int N, int C, in
 /* NHWC (channel stride Cs) -> NCHW fp32, first C channels; accumulate != 0 adds into dst. */
 int fv_nhwc_to_nchw(const void* src, int src_dtype, float* dst, int N, int C, int H, int W, int Cs, int accumulate, void* stream);
 
+/* F.interpolate(x, mode="bilinear", scale_factor=s, align_corners=False, recompute_scale_factor=True) of NCHW fp32 frames
+ * (the input pre-scale of EFE_conv5 / EFE_conv6, models.py:764, 872): out [N,C,Ho,Wo], Ho = floor(H*s) chosen by the caller. */
+int fv_bilinear_resize(const float* x, float* out, int N, int C, int H, int W, int Ho, int Wo, void* stream);
+
 /* ---- convolution: nn.Conv2d inside _ConvBlock (modules.py:15,32), mid_conv (models.py:750,1096), out_conv
  *      (models.py:1099) and their autograd (aten::convolution_backward) ----------------------------------- */
 /* nn.Conv2d weight [Co,Ci,R,S] fp32 -> wf bf16 [Co_pad][R*S][Ci_pad] (forward operand) and
@@ -107,6 +111,18 @@ int fv_conv2d_x2(const void* x, const void* wp, const float* bias, void* y, int 
 /* x NHWC bf16 [N,2H,2W,Ci] -> y [N,H,W,Co_pad] = bias + 4x4 stride-2 pad-1 convolution with w = [Co_pad][16*Ci]. */
 int fv_conv2d_s2(const void* x, const void* w, const float* bias, void* y, int out_mode, int N, int H, int W, int Ci, int Co,
                  int Co_pad, float* stats, void* red_ws, void* stream);
+/* The general convolution entry: geometry kind (0 same, 1 x2, 2 s2; R, S, pad are used by kind 0 only), an optional activation
+ * applied in the epilogue after the bias (FV_ACT_*: conv -> bias -> LeakyReLU(0.2) is Conv2dELR.forward, models_utils.py:712-742),
+ * optional residual (kind 0) and fused statistics. */
+int fv_conv2d_ex(int kind, const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
+                 int W, int Ci, int Co, int Co_pad, int R, int S, int pad, int act, float* stats, void* red_ws, void* stream);
+/* Conv2dELR weight path (models_utils.py:686-704): weff[co] = gain * w[co] / max(||w[co]||, 1e-12) (demod != 0: F.normalize over
+ * dims 1..3) or gain * w; K = Ci*R*S elements per output channel; inv_norm[Co] (may be NULL) is kept for fv_demod_bwd, which maps
+ * the gradient with respect to weff back to the gradient with respect to w. */
+int fv_demod_fwd(const float* w, float* weff, float* inv_norm, int Co, int K, float gain, int demod, void* stream);
+int fv_demod_bwd(const float* w, const float* inv_norm, const float* dweff, float* dw, int Co, int K, float gain, int demod, void* stream);
+/* dy = g * act'(out) for an activation applied in a conv epilogue (NHWC bf16, n % 8 == 0 elements). */
+int fv_act_bwd(const void* out, const void* g, void* dy, long long n, int act, void* stream);
 /* x [N,H,W,Ci] coarse, dy [N,2H,2W,Co_pad] fine -> part[split][4][Co_pad][4][Ci]; splits = fv_conv2d_wgrad_splits(1, ...). */
 int fv_conv2d_wgrad_x2(const void* x, const void* dy, float* part, int splits, int N, int H, int W, int Ci, int Co_pad, void* stream);
 /* x [N,2H,2W,Ci] fine, dy [N,H,W,Co_pad] coarse -> part[split][Co_pad][16][Ci]; splits = fv_conv2d_wgrad_splits(2, ...);

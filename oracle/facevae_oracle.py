@@ -182,6 +182,87 @@ def l2(x, y):
 
 
 # ----------------------------------------------------------------------------
+# ELR layers, flatten_vae6, input pre-scale
+# ----------------------------------------------------------------------------
+def _elr_act_gain(act):
+    """Gain Conv2dELR / LinearELR derive from their activation (reference models_utils.py:137-146, 648-657):
+    ``act`` in {None, "relu", "leaky"} (LeakyReLU(0.2))."""
+    if act == "relu":
+        return float(np.sqrt(2.0))
+    if act == "leaky":
+        return float(np.sqrt(2.0 / (1.0 + 0.2 ** 2)))
+    return 1.0
+
+
+def _elr_act(x, act):
+    if act == "relu":
+        return torch.relu(x)
+    if act == "leaky":
+        return torch.where(x > 0, x, 0.2 * x)
+    return x
+
+
+def conv2d_elr(x, weight, bias, stride, padding, norm=None, act=None):
+    """Conv2dELR.forward without style modulation (reference models_utils.py:686-744): weight / ||weight||_(ci,r,s) when
+    norm == "demod", times weightgain = actgain * (1 if demod else 1/sqrt(fan_in)); conv; + bias; activation."""
+    co, ci, k, _ = weight.shape
+    gain = _elr_act_gain(act) * (1.0 if norm == "demod" else 1.0 / float(np.sqrt(ci * k * k)))
+    w = weight
+    if norm == "demod":
+        w = w / w.flatten(1).norm(dim=1).clamp_min(1e-12)[:, None, None, None]
+    w = w * gain
+    return _elr_act(F.conv2d(x, w, None, stride=stride, padding=padding) + bias[None, :, None, None], act)
+
+
+def linear_elr(x, weight, bias, norm=None, act=None, lrmult=1.0):
+    """LinearELR.forward, un-fused (reference models_utils.py:134-203)."""
+    gain = _elr_act_gain(act)
+    if norm is None:
+        gain = gain * lrmult / float(np.sqrt(weight.shape[1]))
+    w = weight / weight.norm(dim=1, keepdim=True).clamp_min(1e-12) if norm == "demod" else weight
+    return _elr_act(x @ (w * gain).t() + bias[None], act)
+
+
+def flatten_vae6_forward(x, p, eps, training=True):
+    """flatten_vae6.forward (reference models.py:822-833) with eps injected; ``p``: state_dict of the module."""
+    shape = x.shape
+    h = x.flatten(start_dim=1)
+    i = 0
+    while f"encoder.{i}.weight" in p:
+        h = linear_elr(h, p[f"encoder.{i}.weight"], p[f"encoder.{i}.bias"], "demod", "leaky")
+        i += 1
+    mu = linear_elr(h, p["mu_fc.weight"], p["mu_fc.bias"]) * 0.1
+    logstd = linear_elr(h, p["logstd_fc.weight"], p["logstd_fc.bias"]) * 0.01
+    z = mu + torch.exp(logstd) * eps if training else mu
+    i = 0
+    while f"decoder.{i}.weight" in p:
+        z = linear_elr(z, p[f"decoder.{i}.weight"], p[f"decoder.{i}.bias"], "demod", "leaky")
+        i += 1
+    return mu, logstd, z.view(shape)
+
+
+def bilinear_prescale(x, scale_factor=0.25):
+    """F.interpolate(x, mode="bilinear", scale_factor=s, align_corners=False, recompute_scale_factor=True) written out
+    (reference models.py:764): Ho = floor(H s); source index (o + 0.5) * (H / Ho) - 0.5 clamped at 0; 4-neighbour blend."""
+    n, c, h, w = x.shape
+    ho, wo = int(np.floor(h * scale_factor)), int(np.floor(w * scale_factor))
+
+    def axis(size, osize):
+        src = (torch.arange(osize, dtype=torch.float32) + 0.5) * (np.float32(size) / np.float32(osize)) - 0.5
+        src = src.clamp_min(0)
+        i0 = src.floor().long()
+        i1 = (i0 + (i0 < size - 1).long())
+        l1 = src - i0.float()
+        return i0, i1, 1 - l1, l1
+
+    h0, h1, lh0, lh1 = axis(h, ho)
+    w0, w1, lw0, lw1 = axis(w, wo)
+    top = x[:, :, h0][:, :, :, w0] * lw0 + x[:, :, h0][:, :, :, w1] * lw1
+    bot = x[:, :, h1][:, :, :, w0] * lw0 + x[:, :, h1][:, :, :, w1] * lw1
+    return top * lh0[:, None] + bot * lh1[:, None]
+
+
+# ----------------------------------------------------------------------------
 # Anchor model ("face-vae", SURVEY.md section 8)
 # ----------------------------------------------------------------------------
 @dataclass

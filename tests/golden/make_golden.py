@@ -297,10 +297,66 @@ def golden_losses(path):
     print(path, {k: float(v) for k, v in store.items() if np.ndim(v) == 0})
 
 
+def golden_elr(path):
+    """Conv2dELR (4x4 stride 2 + demod + LeakyReLU, and a plain 3x3), flatten_vae6, LinearELR and the
+    bilinear pre-scale -- outputs of the unmodified reference classes / the reference's own F.interpolate call."""
+    import models_utils as ref_mu
+    store = {}
+
+    def conv_case(tag, ci, co, k, s, pd, norm, act, hw, n=2):
+        m = ref_mu.Conv2dELR(ci, co, k, s, pd, norm=norm, act=act)
+        with torch.no_grad():
+            m.weight.copy_(torch.from_numpy(detgen.det_normal(tuple(m.weight.shape), detgen.name_seed(tag + ".w"))))
+            m.bias.copy_(torch.from_numpy(detgen.det_uniform(tuple(m.bias.shape), detgen.name_seed(tag + ".b"), -0.3, 0.3)))
+        x = torch.from_numpy(detgen.det_uniform((n, ci, hw, hw), detgen.name_seed(tag + ".x"), -1.0, 1.0)).requires_grad_(True)
+        y = m(x)
+        gy = torch.from_numpy(detgen.det_uniform(tuple(y.shape), detgen.name_seed(tag + ".g"), -1.0, 1.0))
+        (y * gy).sum().backward()
+        put(store, f"{tag}/y", y, full_below=1 << 20)
+        put(store, f"{tag}/dx", x.grad, full_below=1 << 20)
+        put(store, f"{tag}/dw", m.weight.grad)
+        put(store, f"{tag}/db", m.bias.grad, full_below=1 << 20)
+        store[f"{tag}/gain"] = np.float64(m.weightgain)
+
+    conv_case("elr_s2_demod_leaky", 32, 64, 4, 2, 1, "demod", nn.LeakyReLU(0.2), 16)       # EFE_conv6.efe_encoder layer (models.py:846)
+    conv_case("elr_s2_rgb", 3, 32, 4, 2, 1, "demod", nn.LeakyReLU(0.2), 16)
+    conv_case("elr_s2_plain", 16, 16, 4, 2, 1, None, None, 8)
+    conv_case("elr_3x3_relu", 16, 32, 3, 1, 1, None, nn.ReLU(), 8)
+    conv_case("elr_1x1_demod", 32, 16, 1, 1, 0, "demod", nn.LeakyReLU(0.2), 8)
+    # flatten_vae6 (models.py:802-833), eps injected
+    vae = ref_models.flatten_vae6()
+    sd = vae.state_dict()
+    for k in sd:
+        sd[k] = torch.from_numpy(detgen.det_normal(tuple(sd[k].shape), detgen.name_seed("vae6." + k)) * (0.2 if k.endswith("bias") else 1.0))
+    vae.load_state_dict(sd)
+    x = torch.from_numpy(detgen.det_uniform((3, 16, 4, 4), 91, -1.0, 1.0)).requires_grad_(True)
+    eps = torch.from_numpy(detgen.det_normal((3, 256), 92))
+    with injected_randn(eps):
+        mu, ls, xh = vae(x)
+    gy = torch.from_numpy(detgen.det_uniform((3, 16, 4, 4), 93, -1.0, 1.0))
+    kl = ref_losses.KLDivergenceLoss()((mu, ls))
+    ((xh * gy).sum() + 3.0 * kl).backward()
+    for k, v in (("mu", mu), ("logstd", ls), ("xhat", xh), ("dx", x.grad)):
+        put(store, f"vae6/{k}", v, full_below=1 << 20)
+    for k, v in vae.named_parameters():
+        put(store, f"vae6/grad/{k}", v.grad)
+    vae.training = False
+    mu0, ls0, xh0 = vae(x.detach())
+    put(store, "vae6/eval_xhat", xh0, full_below=1 << 20)
+    # input pre-scale exactly as EFE_conv5 / EFE_conv6 call it (models.py:764)
+    for tag, shape in (("pre256", (2, 3, 256, 256)), ("pre100", (1, 3, 100, 72))):
+        xi = torch.from_numpy(detgen.det_unit(shape, detgen.name_seed(tag)))
+        yo = torch.nn.functional.interpolate(xi, mode="bilinear", scale_factor=0.25, align_corners=False, recompute_scale_factor=True)
+        put(store, f"{tag}/y", yo)
+    np.savez_compressed(path, **store)
+    print(path, len(store), "arrays")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     golden_losses(os.path.join(HERE, "losses.npz"))
     golden_blocks(os.path.join(HERE, "blocks.npz"))
+    golden_elr(os.path.join(HERE, "elr.npz"))
     golden_anchor(4, 64, 0, os.path.join(HERE, "anchor_n4_64.npz"))     # BASELINE.json configs[0]
     golden_anchor(2, 64, 1, os.path.join(HERE, "anchor_n2_64_b1.npz"))
     if "--large" in sys.argv:       # minutes of CPU time: BASELINE.json configs[1] and the configs[3] architecture at 512x512

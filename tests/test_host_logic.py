@@ -144,3 +144,30 @@ def test_checkpoint_format_and_optimizer_state_interchange(tmp_path):
     ta = torch.optim.Adam(params, lr=5e-5, betas=(0.5, 0.999))
     ta.load_state_dict(fa.state_dict())
     assert torch.equal(ta.state[params[0]]["exp_avg"], tr.optimizer.state[next(iter(tr.vae.parameters()))]["exp_avg"])
+
+
+def test_generator_full_keeps_the_reference_call_contract():
+    """GeneratorFull drop-in (reference trainer.py:214-317): constructor and forward parameter names, the ten loss keys.
+    Compared with the reference's own class when /root/reference is present (this container), with the recorded names
+    otherwise (the GPU box)."""
+    import inspect
+    import os
+    import sys
+    from face_vae_b200.models import FaceVAE
+    from face_vae_b200.trainer import GeneratorFull
+    ctor = ["efe", "afe", "ckd", "hpe_ede", "mfe", "generator", "discriminator", "pretrained_path", "n_bins"]
+    fwd = ["s", "d", "s_a", "d_a", "train_vae"]
+    keys = ["P", "G", "F", "E", "L", "H", "D", "C", "K", "R"]
+    if os.path.isdir("/root/reference"):
+        src = open("/root/reference/trainer.py").read()
+        import ast
+        cls = [n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "GeneratorFull"][0]
+        fns = {f.name: f for f in cls.body if isinstance(f, ast.FunctionDef)}
+        assert [a.arg for a in fns["__init__"].args.args][1:] == ctor
+        assert [a.arg for a in fns["forward"].args.args][1:] == fwd
+    assert list(inspect.signature(GeneratorFull.__init__).parameters)[1:] == ctor
+    assert list(inspect.signature(GeneratorFull.forward).parameters)[1:6] == fwd
+    g = GeneratorFull(generator=FaceVAE())
+    assert list(g.weights) == keys
+    with pytest.raises(ValueError):
+        GeneratorFull()

@@ -59,12 +59,13 @@ def _check_fwd(name, got, ref):
     G.check_like(got, ref, FWD_RTOL, FWD_AFRAC, name)
 
 
-def _check_grad(name, got, ref, report, scale=None):
-    """``scale``: magnitude of the block's weight gradient.  A conv bias in front of a training-mode batch norm has an
-    analytically zero gradient (the reference's autograd leaves fp32 noise of ~1e-7 of the weight gradient there, the CUDA
-    path returns exact zeros): such tensors are only required to stay at noise level."""
-    if scale is not None and float(ref.abs().max()) <= 1e-4 * scale:
-        assert float(got.abs().max()) <= 2e-3 * scale, (name, float(got.abs().max()), scale)
+def _check_grad(name, got, ref, report, scale=None, analytic_zero=False):
+    """``analytic_zero``: a conv bias in front of a training-mode batch norm.  Its gradient is zero analytically; the CUDA
+    path returns zeros, autograd (reference and emulation alike) returns the sum of the rounding noise of dy -- both must
+    stay at noise level relative to the block's weight gradient (``scale``)."""
+    if analytic_zero:
+        assert float(got.abs().max()) <= 5e-2 * scale, (name, float(got.abs().max()), scale)
+        assert float(ref.abs().max()) <= 5e-2 * scale, (name, float(ref.abs().max()), scale)
         return
     r = _rel_l2(got, ref)
     report.append((r, name))
@@ -191,11 +192,16 @@ def _run_layerwise(fv, cfg, n, hw, base):
             c_in = xin.shape[1]
             _check_grad(name + " dx", _nchw(inp.grad, c_in), xin.grad, report)
         wscale = max(float(v.grad.abs().max()) for k, v in lp.items() if v.requires_grad and v.dim() == 4)
+        cna = name.startswith("enc.") or name.startswith("up.")
         for k, v in lp.items():
             if v.requires_grad:
-                _check_grad(k, grads[k], v.grad, report, wscale)
-        for k, v in upd.items():                  # running statistics: fp32 quantities, rtol 1e-4
-            torch.testing.assert_close(bufs[k], v.detach(), rtol=1e-4, atol=1e-6)
+                # biases of convs whose output feeds a training-mode batch norm: CNA blocks, and the FIRST conv of a ResBlock2D
+                # (its output goes straight into the second half's norm): sum(dy) = 0 analytically, what is left is the sum of
+                # bf16 rounding noise, a cancellation-dominated number that only has to stay small
+                zero = (cna and k.endswith("layers.0.bias")) or (name.startswith("res.") and k.endswith("layers.0.layers.2.bias"))
+                _check_grad(k, grads[k], v.grad, report, wscale, analytic_zero=zero)
+        for k, v in upd.items():                  # running statistics: fp32 quantities, 1e-4 (of the vector's scale for means near zero)
+            torch.testing.assert_close(bufs[k], v.detach(), rtol=1e-4, atol=1e-4 * float(v.detach().abs().max()))
     report.sort(reverse=True)
     print(f"layer-wise parity n={n} {hw}x{hw}: largest gradient relative L2:", [(f"{r:.2e}", k) for r, k in report[:5]])
     return report

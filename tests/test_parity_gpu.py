@@ -77,8 +77,9 @@ def test_block_matches_reference_golden(fv, tag):
 
 def _check_grad(g, name, t, slack=1.5, floor=1e-2, zero_tol=1e-3):
     """Gradients: relative L2 against the fp32 golden no worse than slack x the reference's own bf16-autocast deviation
-    (+ floor); analytically-zero gradients (bias of a conv feeding a batch norm) must stay ~0."""
-    if float(g[f"{name}/absmax"]) < 1e-5:
+    (+ floor); analytically-zero gradients (bias of a conv feeding a batch norm: fp32 noise in the golden, whose "yardstick"
+    is meaningless) must stay ~0."""
+    if float(g[f"{name}/absmax"]) < 1e-5 or (name.endswith("layers.0.bias") and (".enc." in "." + name or ".up." in "." + name)):
         assert float(t.detach().abs().max()) <= zero_tol, (name, float(t.detach().abs().max()))   # bf16 rounding noise only
         return 0.0, 0.0
     return G.check_vs_yardstick(g, name, t, slack, floor)
@@ -89,13 +90,19 @@ def _anchor(fv, cfg, base):
     return _load(m, O.det_anchor_params(cfg, base))
 
 
-@pytest.mark.parametrize("fixture,n,base", [("anchor_n4_64.npz", 4, 0), ("anchor_n2_64_b1.npz", 2, 1)])
-def test_anchor_matches_reference_golden(fv, fixture, n, base):
-    """BASELINE.json configs[0]: batch 4 at 64x64 -- forward activations, losses, gradients, running stats."""
+@pytest.mark.parametrize("fixture,n,hw,base,cfg", [
+    ("anchor_n4_64.npz", 4, 64, 0, O.CFG_256),              # BASELINE.json configs[0]: batch 4 at 64x64
+    ("anchor_n2_64_b1.npz", 2, 64, 1, O.CFG_256),
+    ("anchor_n32_256.npz", 32, 256, 7, O.CFG_256),          # configs[1]: batch 32 at 256x256 (ring / folded / persistent schedules)
+    ("anchor512_n2_512.npz", 2, 512, 2, O.CFG_512),         # configs[3] architecture at 512x512
+])
+def test_anchor_matches_reference_golden(fv, fixture, n, hw, base, cfg):
+    """End to end against the unmodified reference classes (fp32): forward activations, losses per element within 2e-2;
+    every parameter gradient within 1.25 x the reference's OWN bf16-autocast deviation from its fp32 self (+ 5e-3) -- the
+    tight per-layer gradient check is tests/test_layerwise_gpu.py; running statistics."""
     g = G.load(fixture)
-    cfg = O.CFG_256
     m = _anchor(fv, cfg, base)
-    x, eps = O.det_inputs(n, 64, 64, cfg, base)
+    x, eps = O.det_inputs(n, hw, hw, cfg, base)
     x, eps = x.cuda(), eps.cuda()
     out = m.forward_loss(x, eps)
     loss = cfg.w_kl * out["K"] + cfg.w_rec * out["R"]
@@ -109,12 +116,14 @@ def test_anchor_matches_reference_golden(fv, fixture, n, base):
     G.check(g, "out/logstd", out["logstd"], RTOL, AFRAC)
     G.check(g, "out/x_hat", out["x_hat"], RTOL, AFRAC)
     worst = {}
+    scale = max(float(g[f"grad/{k}/absmax"]) for k, _ in m.named_parameters())
     for k, p in m.named_parameters():
-        worst[k] = _check_grad(g, f"grad/{k}", p.grad)
+        worst[k] = _check_grad(g, f"grad/{k}", p.grad, slack=1.25, floor=5e-3, zero_tol=2e-3 * scale)
     for k, b in m.named_buffers():
         if k.endswith("running_mean") or k.endswith("running_var"):
             G.check(g, f"buf/{k}", b, 1e-2, 1e-2)
-    print("largest grad rel-L2 (ours, reference-autocast yardstick):", sorted(worst.items(), key=lambda kv: -kv[1][0])[:3])
+    top = sorted(worst.items(), key=lambda kv: -kv[1][0])[:3]
+    print(f"{fixture}: largest grad rel-L2 (ours, reference-autocast yardstick):", [(k, f"{a:.3f}", f"{b:.3f}") for k, (a, b) in top])
 
 
 def test_anchor_modular_forward_matches_fused(fv):
@@ -292,3 +301,68 @@ def test_inference_sweep_shapes(fv):
             assert xh.shape == x.shape and mu.shape == (n, 4096) and bool(torch.isfinite(xh).all())
             _, _, xh2 = m(x, False)
             torch.testing.assert_close(xh, xh2, rtol=0, atol=0)        # eps = 0  <=>  z = mu
+
+
+def test_loss_modules_match_reference_golden(fv):
+    """The nn.Module classes themselves (KLDivergenceLoss, ReconLoss, flatten_vae_nl: reference losses.py:385-403,
+    models.py:525-570) against tests/golden/losses.npz -- outputs of the unmodified reference classes -- at rtol 1e-4."""
+    g = G.load("losses.npz")
+    L, MO = fv.losses, fv.models
+    kl, rec = L.KLDivergenceLoss(), L.ReconLoss()
+    for tag, (mv, sv) in {"zero": (0.0, 0.0), "mu1": (1.0, 0.0), "ls1": (0.0, 1.0), "lsm1": (0.0, -1.0)}.items():
+        got = kl((torch.full((4, 256), mv, device="cuda"), torch.full((4, 256), sv, device="cuda"))).item()
+        assert abs(got - float(g[f"kl/{tag}"])) <= 1e-4 * abs(float(g[f"kl/{tag}"])) + 1e-7, (tag, got)
+    i = torch.arange(1024, dtype=torch.float32, device="cuda").view(4, 256)
+    mu = torch.sin(0.01 * i).requires_grad_(True)
+    ls = (0.5 * torch.cos(0.013 * i)).requires_grad_(True)
+    v = kl((mu, ls))
+    v.backward()
+    assert abs(v.item() - float(g["kl/sincos"])) <= 1e-4 * float(g["kl/sincos"])
+    np.testing.assert_allclose(mu.grad.cpu().numpy(), g["kl/sincos_dmu"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(ls.grad.cpu().numpy(), g["kl/sincos_dlogstd"], rtol=1e-4, atol=1e-8)
+    a = torch.sin(0.1 * torch.arange(384, dtype=torch.float32, device="cuda")).view(2, 3, 8, 8).requires_grad_(True)
+    b = torch.cos(0.07 * torch.arange(384, dtype=torch.float32, device="cuda")).view(2, 3, 8, 8)
+    r = rec((a, b))
+    r.backward()
+    assert abs(r.item() - float(g["rec/mse"])) <= 1e-4 * float(g["rec/mse"])
+    np.testing.assert_allclose(a.grad.cpu().numpy(), g["rec/mse_da"], rtol=1e-4, atol=1e-9)
+    assert abs(L.ReconLoss(l1=True)((a.detach(), b)).item() - float(g["rec/l1"])) <= 1e-4 * float(g["rec/l1"])
+    np.testing.assert_allclose(L.l1(a.detach(), b).cpu().numpy(), g["rec/l1_elem"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(L.l2(a.detach(), b).cpu().numpy(), g["rec/l2_elem"], rtol=1e-6, atol=1e-7)
+    vae = MO.flatten_vae_nl()
+    x = torch.from_numpy(detgen.det_uniform((3, 32, 4, 4), 77, 0.0, 2.0)).cuda()
+    eps = torch.from_numpy(detgen.det_normal((3, 256), 78)).cuda()
+    m0, s0, xh0 = vae(x, False)
+    assert m0 is None and s0 is None and np.array_equal(xh0.cpu().numpy(), g["vae/eval_xhat"])      # eval: z == mu exactly
+    m1, s1, xh1 = vae(x, True, eps)
+    np.testing.assert_allclose(m1.cpu().numpy(), g["vae/train_mu"], rtol=0, atol=0)
+    np.testing.assert_allclose(s1.cpu().numpy(), g["vae/train_logstd"], rtol=0, atol=0)
+    np.testing.assert_allclose(xh1.cpu().numpy(), g["vae/train_xhat"], rtol=1e-5, atol=1e-5)
+
+
+def test_generator_full_drop_in(fv):
+    """GeneratorFull (reference trainer.py:214-317 call contract) on the VAE path: same numbers as the fused forward_loss,
+    ten loss keys with the out-of-scope entries zero, 8-tuple, zero K / R when train_vae is falsy; the reference Logger's
+    step skeleton (logger.py:150-164) runs on it."""
+    cfg = O.CFG_256
+    m = _anchor(fv, cfg, 0)
+    x, eps = O.det_inputs(2, 64, 64, cfg, 3)
+    x, eps = x.cuda(), eps.cuda()
+    out = m.forward_loss(x, eps)
+    g_full = fv.trainer.GeneratorFull(generator=m)
+    g_full.eps = eps
+    res = g_full(x, x, None, None, True)
+    assert len(res) == 8 and all(r is None for r in res[2:])
+    losses, generated = res[0], res[1]
+    assert list(losses) == ["P", "G", "F", "E", "L", "H", "D", "C", "K", "R"]
+    assert all(float(losses[k]) == 0.0 for k in "PGFELHDC")
+    assert torch.equal(generated, out["x_hat"])                                  # deterministic kernels: same bits
+    assert float(losses["K"]) == 0.2 * float(out["K"]) or abs(float(losses["K"]) - 0.2 * float(out["K"])) < 1e-7
+    assert abs(float(losses["R"]) - 10 * float(out["R"])) < 1e-6
+    opt = torch.optim.Adam(m.parameters(), lr=5e-5, betas=(0.5, 0.999))            # logger.py:60
+    opt.zero_grad()
+    sum(losses.values()).backward()                                              # logger.py:160-161
+    opt.step()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+    off = g_full(x, x, None, None, False)
+    assert float(off[0]["K"]) == 0.0 and float(off[0]["R"]) == 0.0 and off[1].shape == x.shape
