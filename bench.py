@@ -94,6 +94,106 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+CONV_KERNELS = ("conv_igemm_kernel", "conv_ring_kernel", "conv_wgrad_kernel", "conv_wgrad_ring_kernel", "fold_conv_kernel", "fold_wgrad_kernel",
+                "wgrad_finish_kernel", "wgrad_finish_up_kernel", "slab_sum_kernel")
+
+
+def _in_graph_shares(torch, trainer, dev, replays=3):
+    """Per-kernel device time inside the replayed CUDA graph (CUPTI activity records through torch.profiler).  Only SHARES are
+    used: absolute times under a profiler are never reported as bench values."""
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(replays):
+            trainer.step(*dev[i % 2])
+        torch.cuda.synchronize()
+    per = {}
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            d = per.setdefault(ev.name, [0, 0.0])
+            d[0] += 1
+            d[1] += float(ev.time_range.end - ev.time_range.start)
+    total = sum(v[1] for v in per.values()) or 1.0
+    conv = sum(v[1] for k, v in per.items() if any(c in k for c in CONV_KERNELS))
+    top = sorted(per.items(), key=lambda kv: -kv[1][1])[:24]
+    return {"conv_share": conv / total,
+            "kernels": {k[:96]: {"launches_per_step": v[0] / replays, "share_of_kernel_time": v[1] / total} for k, v in top}}
+
+
+def _glue_roofline(torch, peaks):
+    """north_star: "fused loss / KL kernels at >= 70 % of HBM bandwidth" -- the reconstruction-loss (+ sigmoid + gradient) and
+    re-parameterisation + KL kernels timed alone at a bandwidth-bound size (the inference sweep's batch 1024 for the loss, 8192
+    samples for the latent: inputs far larger than the 126 MB L2), CUDA events, median of 10 after 3 warm-ups."""
+    from face_vae_b200 import ops
+    out = {}
+
+    def timed(fn, nbytes):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        t = statistics.median(ts)
+        gbs = nbytes / (t * 1e-3) / 1e9
+        return {"ms": t, "bytes": nbytes, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"], "bound": "hbm"}
+
+    n, c, h, w = 1024, 3, 256, 256
+    logits = torch.randn((n, c, h, w), device="cuda")
+    target = torch.rand((n, c, h, w), device="cuda")
+    e = logits.numel()
+    # sigmoid + MSE + gradient: reads logits and target, writes the fp32 gradient (12 bytes per element, SURVEY.md 8d)
+    out["fv_recon_loss (sigmoid + MSE + gradient, fp32 in / fp32 grad)"] = timed(
+        lambda: ops.recon_loss(logits, target, False, True, 1.0 / e, False, True, False), 12.0 * e)
+    out["fv_recon_loss_flat (ReconLoss()((a, b)) + gradient)"] = timed(lambda: ops.recon_loss_flat(logits, target, False, 1.0 / e, True), 12.0 * e)
+    del logits, target
+    nz, dz = 8192, 4096
+    hlat = torch.rand((nz, 2 * dz), device="cuda")
+    eps = torch.randn((nz, dz), device="cuda")
+    mu, ls = hlat[:, :dz], hlat[:, dz:]
+    out["fv_reparam_kl_fwd (z + KL partial sums)"] = timed(lambda: ops.reparam_kl_fwd(mu, ls, eps, True, True), 16.0 * nz * dz)
+    dzt = torch.randn((nz, dz), device="cuda")
+    buf = torch.empty((nz, 2 * dz), device="cuda")
+    # reads mu, logstd, eps, dz; writes dmu, dlogstd
+    out["fv_reparam_kl_bwd"] = timed(lambda: ops.reparam_kl_bwd(mu, ls, eps, dzt, None, None, 1e-6, None, buf), 24.0 * nz * dz)
+    return out
+
+
+def run_inference(args, torch, _lib, real_stdout, peaks, warmup):
+    """BASELINE.json configs[4]: eval-mode encode -> sample -> decode (running statistics, no backward) at one batch size."""
+    from face_vae_b200.models import FaceVAE
+    torch.manual_seed(0)
+    model = FaceVAE().cuda().eval()
+    B, S = args.batch, args.size
+    dz = model.latent_dim(S, S)
+    xs = [torch.rand((B, 3, S, S), device="cuda") for _ in range(2)]
+    eps = torch.randn((B, dz), device="cuda")
+    l0 = _lib.launch_count
+    with torch.no_grad():
+        for i in range(warmup):
+            model(xs[i % 2], True, eps)
+        torch.cuda.synchronize()
+        per_step = (_lib.launch_count - l0) // max(warmup, 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            model(xs[i % 2], True, eps)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    line = {"metric": "inference images/sec at 256x256 (encode -> sample -> decode)", "value": B / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"face-vae anchor eval-mode encode -> sample -> decode, batch {B} at {S}x{S} (BASELINE.json configs[4])",
+                       "l2": "two alternating input batches"},
+            "gpu_launches": per_step * args.steps, "latency_ms": ms, "peaks": peaks}
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -106,6 +206,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--deep", action="store_true", help="512x512-deep variant (BASELINE.json configs[3]; use with --size 512 --batch 8)")
+    ap.add_argument("--global-batch", type=int, default=0, help="fixed global batch split over the ranks (BASELINE.json configs[2]: 256 at "
+                    "2/4/8 GPUs -> strong scaling); overrides --batch")
+    ap.add_argument("--infer", action="store_true", help="BASELINE.json configs[4]: eval-mode encode -> sample -> decode at --batch (no backward)")
+    ap.add_argument("--no-glue-roofline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -130,7 +234,13 @@ def main():
     _lib.call("fv_device_ok")
     peaks = _peaks()
     warmup = max(args.warmup, 3)
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} ranks")
+        args.batch = args.global_batch // world
     B, S = args.batch, args.size
+    if args.infer:
+        return run_inference(args, torch, _lib, real_stdout, peaks, warmup)
 
     torch.manual_seed(0)                               # identical initial weights on every rank
     if args.deep:
@@ -243,25 +353,61 @@ def main():
                 k["gbs_launches_over_64MB"] = a["big_bytes"] / (a["big_ms"] * 1e-3) / 1e9
                 k["frac_hbm_launches_over_64MB"] = k["gbs_launches_over_64MB"] / peaks["hbm"]
         kernels[name] = k
-    # forward + data-gradient convolutions: the generic implicit-GEMM / ring kernels and the tap-folded out_conv kernels
-    conv = {"ms": 0.0, "flops": 0.0, "launches": 0}
-    for nm in ("fv_conv2d", "fv_conv2d_stats", "fv_outconv_fwd", "fv_outconv_dgrad"):
+    # ---- roofline of the convolutions: ALL of them -- forward, data gradient and weight gradient, the generic / ring / x2 / s2
+    # kernels, the tap-folded out_conv kernels and the passes that finish the weight gradients (their time counts, they add no
+    # FLOPs).  Algorithmic FLOPs = 2*N*H*W*Ci*Co*k*k per pass of the reference's formulation; the up-sampling
+    # convolutions EXECUTE 2.25x fewer (four 2x2 phases instead of a 3x3 on the 4x larger image) -- both figures are given.
+    CONV = ("fv_conv2d", "fv_conv2d_stats", "fv_conv2d_x2", "fv_conv2d_s2", "fv_conv2d_ex", "fv_conv2d_wgrad", "fv_conv2d_wgrad_x2",
+            "fv_conv2d_wgrad_s2", "fv_outconv_fwd", "fv_outconv_dgrad", "fv_outconv_wgrad", "fv_wgrad_finish", "fv_wgrad_finish_up", "fv_slab_sum")
+    conv = {"ms": 0.0, "flops": 0.0, "flops_exec": 0.0, "launches": 0}
+    for nm in CONV:
         if nm in agg:
             for k in conv:
                 conv[k] += agg[nm][k]
+    # the same split measured INSIDE the replayed CUDA graph (CUPTI activity records of three replays): the eager event-pair
+    # pass above inflates every launch by its host gap, so the in-graph SHARE of the convolutions times the device-timed step
+    # (measured without any profiler, above) is the better estimate of their time in the real step
+    in_graph = None
+    if trainer.use_cuda_graph:
+        try:
+            in_graph = _in_graph_shares(torch, trainer, dev)
+        except Exception as e:                      # profiler unavailable: keep the event-pair numbers only
+            in_graph = {"error": f"{type(e).__name__}: {e}"}
     if conv["ms"] > 0:
-        ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
-        roofline = {"kernel": "conv_igemm_kernel / conv_ring_kernel / fold_conv_kernel (all forward + data-gradient convolutions of the step)", "bound": "tensor",
-                    "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
-                    "frac_of_burst_peak": ach / peaks["bf16"], "peak_source": peaks["source"] + " (sustained: timed inside the step)",
-                    "avg_launch_ms": conv["ms"] / conv["launches"], "launches_per_step": conv["launches"] / args.profile_steps,
-                    "traffic": None}
+        per_step_ms = conv["ms"] / args.profile_steps
+        flops_step = conv["flops"] / args.profile_steps
+        ach = flops_step / (per_step_ms * 1e-3) / 1e12
+        at_max = clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"] and "sw_power_cap" not in clocks.get("reasons", [])
+        peak = peaks["bf16"] if at_max else peaks["bf16_sustained"]
+        roofline = {"kernel": "all convolution kernels of the step: conv_igemm (same / x2 / s2), conv_ring, conv_wgrad, conv_wgrad_ring, fold_conv, "
+                              "fold_wgrad + the weight-gradient finish passes (forward, data gradient AND weight gradient)",
+                    "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "peak_source": peaks["source"] + (" burst (SM clock at max, no power cap during the timed region)" if at_max else
+                                                      " sustained (SM clock below max or power cap active during the timed region)"),
+                    "frac_of_burst_peak": ach / peaks["bf16"], "frac_of_sustained_peak": ach / peaks["bf16_sustained"],
+                    "timing": "CUDA events around every launch of an eager replay of the step, on the launching stream",
+                    "algorithmic_tflop_per_step": flops_step / 1e12, "executed_tflop_per_step": conv["flops_exec"] / args.profile_steps / 1e12,
+                    "achieved_executed": conv["flops_exec"] / args.profile_steps / (per_step_ms * 1e-3) / 1e12,
+                    "ms_per_step": per_step_ms, "avg_launch_ms": conv["ms"] / conv["launches"],
+                    "launches_per_step": conv["launches"] / args.profile_steps, "traffic": None}
+        if in_graph and "conv_share" in in_graph:
+            ms_in = in_graph["conv_share"] * (ms / args.steps)
+            roofline["in_graph"] = {"conv_share_of_kernel_time": in_graph["conv_share"], "conv_ms_per_step": ms_in,
+                                    "achieved": flops_step / (ms_in * 1e-3) / 1e12, "frac": flops_step / (ms_in * 1e-3) / 1e12 / peak,
+                                    "how": "share of the convolution kernels in the CUPTI kernel time of three graph replays x the device-timed step"}
+        elif in_graph:
+            roofline["in_graph"] = in_graph
         # DRAM bytes per launch of these kernels from the committed ncu launch list of this command (profiles/)
-        tpath = os.path.join(ROOT, "profiles", "r01_final_conv_traffic.json")
-        if os.path.exists(tpath) and B == 32 and S == 256 and not args.deep:
-            t = json.load(open(tpath))
-            roofline["traffic"] = t["bytes_per_launch"]
-            roofline["traffic_source"] = "profiles/r01_final_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per launch)"
+        for tname in ("r02_conv_traffic.json", "r01_final_conv_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath) and B == 32 and S == 256 and not args.deep:
+                t = json.load(open(tpath))
+                roofline["traffic"] = t["bytes_per_launch"]
+                roofline["traffic_source"] = f"profiles/{tname} (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per launch)"
+                break
+    glue = None
+    if rank == 0 and not args.no_glue_roofline:
+        glue = _glue_roofline(torch, peaks)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
@@ -283,8 +429,11 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * S * S * 4 + B * dz * 4, "d2h_bytes_per_step": 4,
                         "last_loss": last},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels,
-                "peaks": peaks}
+                "gpu_launches": launches, "roofline": roofline, "roofline_glue": glue, "cpu_baseline": cpu, "kernels": kernels,
+                "in_graph_kernels": (in_graph or {}).get("kernels"), "peaks": peaks}
+        if args.global_batch:
+            line["scaling"] = "strong"
+            line["config"]["workload"] += f" (global batch {args.global_batch} split over {world} GPUs)"
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:

@@ -902,7 +902,7 @@ bn_act_bwd_apply_kernel(const TY* __restrict__ y, const TG* __restrict__ g, cons
 }
 
 // per-channel column sums of an NHWC bf16 tensor (bias gradient of a conv that does not feed a batch norm)
-__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ sums, long long P, int C, void* ws) {
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ sums, long long P, int C, long long ld, void* ws) {
     extern __shared__ float sh[];   // [rows_per_iter][C] | block vector [C] | totals [C]
     __shared__ int red_flag;
     const int tpr = C / 8, rpi = blockDim.x / tpr;
@@ -911,7 +911,7 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ y, float* __rest
     if (tr < rpi) {
         for (long long r = (long long)blockIdx.x * rpi + tr; r < P; r += (long long)gridDim.x * rpi) {
             float f[8];
-            V8<__nv_bfloat16>::load(y + r * C + tc * 8, f);
+            V8<__nv_bfloat16>::load(y + r * ld + tc * 8, f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) s[k] += f[k];
         }
@@ -1439,12 +1439,17 @@ static int bn_act_bwd_apply_impl(const void* y, int y_dtype, const void* g, int 
 
 extern "C" __attribute__((visibility("default"))) int fv_colsum(const void* y, float* sums, long long P, int C, void* ws, void* stream) {
     if (!y || !sums) return fail(FV_ERR_ARG, "fv_colsum: null pointer");
-    if (int e = check_c8("fv_colsum", C)) return e;
-    int grid; size_t sh;
-    reduce_geometry(C, P, grid, sh);
-    if (int e = check_ws("fv_colsum", ws, grid, C, 4)) return e;
-    colsum_kernel<<<grid, kThreads, sh, STREAM>>>((const __nv_bfloat16*)y, sums, P, C, ws);
-    FV_LAUNCH_CHECK("colsum_kernel");
+    if (C % 8 || C < 8) return fail(FV_ERR_UNSUPPORTED, "fv_colsum: channel count %d must be a multiple of 8", C);
+    // rows wider than 2048 channels (the 16 -> 256*16 mid_conv of EFE_conv5) are walked in column chunks of <= 2048
+    for (int c0 = 0; c0 < C; c0 += 2048) {
+        const int cn = C - c0 < 2048 ? C - c0 : 2048;
+        if (int e = check_c8("fv_colsum", cn)) return e;
+        int grid; size_t sh;
+        reduce_geometry(cn, P, grid, sh);
+        if (int e = check_ws("fv_colsum", ws, grid, cn, 4)) return e;
+        colsum_kernel<<<grid, kThreads, sh, STREAM>>>((const __nv_bfloat16*)y + c0, sums + c0, P, cn, (long long)C, ws);
+        FV_LAUNCH_CHECK("colsum_kernel");
+    }
     return FV_OK;
 }
 

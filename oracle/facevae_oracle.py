@@ -202,15 +202,18 @@ def _elr_act(x, act):
     return x
 
 
-def conv2d_elr(x, weight, bias, stride, padding, norm=None, act=None):
+def conv2d_elr(x, weight, bias, stride, padding, norm=None, act=None, wround=None):
     """Conv2dELR.forward without style modulation (reference models_utils.py:686-744): weight / ||weight||_(ci,r,s) when
-    norm == "demod", times weightgain = actgain * (1 if demod else 1/sqrt(fan_in)); conv; + bias; activation."""
+    norm == "demod", times weightgain = actgain * (1 if demod else 1/sqrt(fan_in)); conv; + bias; activation.
+    ``wround``: optional rounding applied to the effective filter (oracle/emulate.py's bf16 storage hook)."""
     co, ci, k, _ = weight.shape
     gain = _elr_act_gain(act) * (1.0 if norm == "demod" else 1.0 / float(np.sqrt(ci * k * k)))
     w = weight
     if norm == "demod":
         w = w / w.flatten(1).norm(dim=1).clamp_min(1e-12)[:, None, None, None]
     w = w * gain
+    if wround is not None:
+        w = wround(w)
     return _elr_act(F.conv2d(x, w, None, stride=stride, padding=padding) + bias[None, :, None, None], act)
 
 

@@ -42,11 +42,15 @@ def test_conv2d_elr_module(fv, tag):
         m.weight.copy_(w)
         m.bias.copy_(b)
     m = m.cuda()
-    # bf16-representable input so that the only differences are the bf16 filter / output roundings
+    # bf16-representable input and upstream gradient, and the effective filter rounded to bf16 where the CUDA path rounds it
+    # (oracle/emulate.py's storage hook): what is left is accumulation order and the bf16 rounding of the outputs -- with an
+    # fp32 filter on the reference side ~0.3 % of the ReLU masks flip and dx cannot be compared per element
+    from oracle import emulate as E
     xq = x.bfloat16().float()
+    gy = gy.bfloat16().float()
     xr = xq.clone().requires_grad_(True)
     wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
-    yr = O.conv2d_elr(xr, wr, br, s, pd, norm, act)
+    yr = O.conv2d_elr(xr, wr, br, s, pd, norm, act, wround=E.BF16.rf)
     (yr * gy).sum().backward()
     xc = xq.cuda().requires_grad_(True)
     y = m(xc)
