@@ -57,6 +57,10 @@ SIGNATURES = {
     "fv_bn_act_bwd_reduce": [_p, _i, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "fv_bn_bwd_finalize": [_p, _p, _d, _p, _p, _p, _i, _i, _p],
     "fv_bn_act_bwd_apply": [_p, _i, _p, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fv_in_stats": [_p, _p, _i, _i, _i, _i, _f, _p],
+    "fv_in_act_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "fv_in_bwd_sums": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "fv_in_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "fv_reparam_kl_fwd": [_p, _p, _ll, _p, _p, _p, _i, _i, _p],
     "fv_reparam_kl_bwd": [_p, _p, _ll, _p, _p, _p, _p, _f, _p, _p, _p, _ll, _i, _i, _p],
     "fv_recon_loss": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p],
@@ -69,6 +73,8 @@ SIGNATURES = {
     "fv_pw_bwd_reduce": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
     "fv_pw_bwd_finalize": [_p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "fv_bn_finalize_xrank": [_p, _p, _i, _i, _p, _i, _d, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i, _i, _p],
+    "fv_bn_stats_xrank": [_p, _i, _p, _ll, _i, _p, _p, _i, _i, _p, _d, _p, _p, _p, _p, _f, _f, _p, _p],
+    "fv_bn_act_bwd_reduce_xrank": [_p, _i, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _d, _p, _p, _p, _p],
     "fv_bn_finalize_xrank_emulate": [_p, _p, _i, _p, _i, _d, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i, _i, _p],
     "fv_debug_mma_rate": [_i, _i, _i, _i, _i, _i, _p, _p],
     "fv_debug_trace_set": [_p],

@@ -10,13 +10,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfacevae_b200.so")
-SOURCES = ["fv_host.cu", "fv_glue.cu", "fv_conv.cu", "fv_conv_ring.cu", "fv_wgrad.cu", "fv_wgrad_ring.cu", "fv_xrank.cu", "fv_pointwise.cu", "fv_outconv.cu", "fv_debug.cu"]
+SOURCES = ["fv_host.cu", "fv_glue.cu", "fv_conv.cu", "fv_conv_ring.cu", "fv_conv_win.cu", "fv_wgrad.cu", "fv_wgrad_ring.cu", "fv_xrank.cu", "fv_pointwise.cu", "fv_outconv.cu", "fv_debug.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
 # --use_fast_math (approximate division / exp, flush-to-zero) only where nothing is contracted to 1e-4: the tensor-core
 # translation units, whose epilogues round to bf16 anyway.  The fp32 glue (KL, losses, batch-norm finalize, Adam), the
 # cross-rank exchange and the first-layer kernels are compiled with IEEE semantics.
-FAST_MATH_SOURCES = {"fv_conv.cu", "fv_conv_ring.cu", "fv_wgrad.cu", "fv_wgrad_ring.cu", "fv_debug.cu"}
+FAST_MATH_SOURCES = {"fv_conv.cu", "fv_conv_ring.cu", "fv_conv_win.cu", "fv_wgrad.cu", "fv_wgrad_ring.cu", "fv_debug.cu"}
 if os.environ.get("FV_TRACE"):                       # role-loop cycle counters in the ring kernels (debug only)
     NVCC_FLAGS = NVCC_FLAGS + ["-DFV_TRACE", "-rdc=false"]
 

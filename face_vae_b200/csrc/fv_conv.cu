@@ -378,6 +378,11 @@ int conv2d_ring_eligible(int out_mode, int H, int W, int Ci, int Co_pad, int R, 
 int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
                     int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, void* red_ws, cudaStream_t stream);
 
+// fv_conv_win.cu: resident-filter / slab-window schedule of the x2 and s2 geometries for thin layers on 128-pixel row tiles
+int conv_win_eligible(int kind, int out_mode, int W, int Ci, int Co_pad);
+int conv_win_try(int kind, const void* x, const void* w, const float* bias, void* y, int out_mode, int N, int H, int W, int Ci, int Co, int Co_pad,
+                 float* stats, void* red_ws, cudaStream_t stream);
+
 }  // namespace fv
 
 // 1 when fv_conv2d_stats produces the statistics inside the convolution's epilogue for this shape, 0 when it runs a separate
@@ -397,6 +402,7 @@ extern "C" __attribute__((visibility("default"))) int fv_conv2d_fuses_stats(int 
 extern "C" __attribute__((visibility("default"))) int fv_conv2d_geom_fuses_stats(int kind, int out_mode, int N, int H, int W, int Ci, int Co_pad) {
     using namespace fv;
     if (out_mode == FV_OUT_NCHW_F32 || (kind != CONV_X2 && kind != CONV_S2)) return 0;
+    if (conv_win_eligible(kind, out_mode, W, Ci, Co_pad)) return kind == CONV_X2 && env_int("FV_CONV_FUSE_STATS", 1) ? 1 : 0;
     if (Co_pad > 256) return 1;
     int tw = 0, th = 0, tn = 0;
     if (pick_tile(N, H, W, tw, th, tn)) return 0;
@@ -467,6 +473,12 @@ static int conv_chunk(const ConvCall& c, int co_base, int Co_pad, int Co) {
         const int rr = conv2d_ring_try(c.x, c.w, c.bias, c.residual, c.y, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, ring_stats, out_cs, c.red_ws, s);
         if (rr > 0) return rr;
         if (rr == 0) return (stats && !ring_stats) ? fv_bn_stats(c.y, y_dtype, stats, (long long)N * H * W, Co_pad, c.red_ws, c.stream) : FV_OK;
+    }
+    if (c.kind != CONV_SAME && out_cs == Co_pad && c.act == FV_ACT_NONE && !c.residual) {
+        float* win_stats = (stats && c.kind == CONV_X2 && env_int("FV_CONV_FUSE_STATS", 1)) ? stats : nullptr;
+        const int rr = conv_win_try(c.kind, c.x, c.w, c.bias, c.y, out_mode, N, H, W, Ci, Co, Co_pad, win_stats, c.red_ws, s);
+        if (rr > 0) return rr;
+        if (rr == 0) return (stats && !win_stats) ? fv_bn_stats(c.y, y_dtype, stats, (long long)N * Ho * Wo, Co_pad, c.red_ws, c.stream) : FV_OK;
     }
     ConvParams p{};
     p.N = N; p.H = H; p.W = W; p.Ci = Ci; p.Co = Co; p.Co_pad = Co_pad;

@@ -3,12 +3,14 @@
 // fused with the KL reduction, and the reconstruction loss fused with its gradient.  Every kernel is a single
 // coalesced, 16-byte-vectorised pass (8 channels per thread in NHWC), sized in multiples of the SM count.
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 
 #include "../../include/facevae_b200.h"
 #include "fv_host.h"
 #include "fv_ptx.cuh"
 #include "fv_reduce.cuh"
+#include "fv_xrank.cuh"
 
 namespace fv {
 
@@ -448,9 +450,10 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ out, const __nv
 // blockDim = 256; a block covers rows_per_iter = 256 / (C/8) rows per step; cross-row reduction through shared memory,
 // then the deterministic cross-block reduction of fv_reduce.cuh (fixed summation order: bitwise reproducible).
 template <typename T>
-__global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sums, long long P, int C, void* ws) {
+__global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sums, long long P, int C, void* ws, const XrankArgs xr) {
     extern __shared__ float sh[];   // [2][rows_per_iter][C] | block vector [2C] | totals [2C]
     __shared__ int red_flag;
+    __shared__ uint32_t xr_epoch;
     const int tpr = C / 8;                       // threads per row
     const int rpi = blockDim.x / tpr;            // rows per iteration
     const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
@@ -497,8 +500,13 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, float* __restrict__ sum
         blk[c] = a;
     }
     __syncthreads();
-    if (det_reduce<float>(ws, 2 * C, gridDim.x, blockIdx.x, blk, tot, threadIdx.x, blockDim.x, BlockSync{}, &red_flag))
+    if (det_reduce<float>(ws, 2 * C, gridDim.x, blockIdx.x, blk, tot, threadIdx.x, blockDim.x, BlockSync{}, &red_flag)) {
         for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sums[c] = tot[c];
+        if (xr.peer_bufs) {         // data parallel: the block holding the totals exchanges them with the other ranks and finalizes
+            __syncthreads();
+            xrank_exchange_finalize(xr, tot, &xr_epoch);
+        }
+    }
 }
 
 // mean / invstd / folded scale+shift from the (possibly cross-rank reduced) sums; running-stat update with the
@@ -739,9 +747,10 @@ __device__ __forceinline__ void row_to_nhw(unsigned r, int H, int W, unsigned& n
 template <typename TY, typename TG, int MODE, bool GN>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, const float* __restrict__ stat,
-                         float* __restrict__ sums, int N, int H, int W, int C, int act, void* ws) {
+                         float* __restrict__ sums, int N, int H, int W, int C, int act, void* ws, const XrankArgs xr) {
     extern __shared__ float sh[];   // [2][rows_per_iter][C] | block vector [2C] | totals [2C]
     __shared__ int red_flag;
+    __shared__ uint32_t xr_epoch;
     const int tpr = C / 8, rpi = blockDim.x / tpr;
     const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
     const unsigned P = (unsigned)N * H * W;
@@ -804,8 +813,13 @@ bn_act_bwd_reduce_kernel(const TY* __restrict__ y, const TG* __restrict__ g, con
         blk[c] = a;
     }
     __syncthreads();
-    if (det_reduce<float>(ws, 2 * C, gridDim.x, blockIdx.x, blk, tot, threadIdx.x, blockDim.x, BlockSync{}, &red_flag))
+    if (det_reduce<float>(ws, 2 * C, gridDim.x, blockIdx.x, blk, tot, threadIdx.x, blockDim.x, BlockSync{}, &red_flag)) {
         for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sums[c] = tot[c];
+        if (xr.peer_bufs) {
+            __syncthreads();
+            xrank_exchange_finalize(xr, tot, &xr_epoch);
+        }
+    }
 }
 
 // dgamma += s2, dbeta += s1 (local sums: autograd's gradient all-reduce averages them later); coef = (cross-rank) sums / count
@@ -931,6 +945,118 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ y, float* __rest
         for (int c = threadIdx.x; c < C; c += blockDim.x) sums[c] = tot[c];
 }
 
+// ---------------------------------------------------------------- instance norm
+// nn.InstanceNorm2d(C, affine=True) + LeakyReLU of the Discriminator's blocks (reference modules.py:21, models.py:1120-1127):
+// statistics per (image, channel) over H*W (biased variance, eps), no running statistics.  One block per (image, 64-channel
+// slice): 32 row lanes x 8 channel groups; the row lanes are combined in lane order -- no cross-block reduction, reproducible.
+// in_stats:   stat[n][0][c] = mean, stat[n][1][c] = invstd
+// in_act_fwd: out = act(gamma * (y - mean) * invstd + beta)
+// in_bwd_sums: sums[n][0][c] = sum dz, sums[n][1][c] = sum dz * xhat   (dz = g * act'(...)); dgamma / dbeta = their sums over n
+// in_bwd_apply: dy = gamma * invstd * (dz - mean_p(dz) - xhat * mean_p(dz * xhat))
+template <int PASS>     // 0: statistics of y; 1: backward sums
+__global__ void __launch_bounds__(256)
+in_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ g, const float* __restrict__ stat,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out, int P, int C, int act, float eps) {
+    __shared__ float sh[2][32][64];
+    const int n = blockIdx.y, c0 = blockIdx.x * 64;
+    const int tc = threadIdx.x & 7, tr = threadIdx.x >> 3;
+    const int c = c0 + tc * 8;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float mean[8], inv[8], ga[8], be[8];
+    if (PASS == 1 && c < C) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            mean[k] = stat[((size_t)n * 2) * C + c + k];
+            inv[k] = stat[((size_t)n * 2 + 1) * C + c + k];
+            ga[k] = gamma[c + k];
+            be[k] = beta[c + k];
+        }
+    }
+    if (c < C) {
+        for (int r = tr; r < P; r += 32) {
+            float f[8];
+            V8<__nv_bfloat16>::load(y + ((size_t)n * P + r) * C + c, f);
+            if (PASS == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    a[k] += f[k];
+                    b[k] = fmaf(f[k], f[k], b[k]);
+                }
+            } else {
+                float gg[8];
+                V8<__nv_bfloat16>::load(g + ((size_t)n * P + r) * C + c, gg);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float xh = (f[k] - mean[k]) * inv[k];
+                    const float dz = gg[k] * act_grad(fmaf(ga[k], xh, be[k]), act);
+                    a[k] += dz;
+                    b[k] = fmaf(dz, xh, b[k]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        sh[0][tr][tc * 8 + k] = a[k];
+        sh[1][tr][tc * 8 + k] = b[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int which = threadIdx.x >> 6, ch = threadIdx.x & 63;
+        if (c0 + ch < C) {
+            float t = 0.f;
+            for (int r = 0; r < 32; ++r) t += sh[which][r][ch];
+            if (PASS == 0) {
+                // mean / invstd need both sums: the `which == 0` thread writes the mean, its partner computes the variance
+                sh[which][0][ch] = t;
+            } else {
+                out[((size_t)n * 2 + which) * C + c0 + ch] = t;
+            }
+        }
+    }
+    if (PASS == 0) {
+        __syncthreads();
+        if (threadIdx.x < 64 && c0 + threadIdx.x < C) {
+            const double m = (double)sh[0][0][threadIdx.x] / P;
+            double var = (double)sh[1][0][threadIdx.x] / P - m * m;
+            if (var < 0) var = 0;
+            out[((size_t)n * 2) * C + c0 + threadIdx.x] = (float)m;
+            out[((size_t)n * 2 + 1) * C + c0 + threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+    }
+}
+
+template <int PASS>     // 0: forward; 1: backward apply (sums = the per-image backward sums)
+__global__ void __launch_bounds__(256)
+in_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ g, const float* __restrict__ stat,
+                const float* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                __nv_bfloat16* __restrict__ out, int N, int P, int C, int act) {
+    const int groups = C / 8;
+    const long long total = (long long)N * P * groups;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int grp = (int)(i % groups);
+        const long long pix = i / groups;
+        const int n = (int)(pix / P), c = grp * 8;
+        float f[8], r[8], gg[8];
+        V8<__nv_bfloat16>::load(y + pix * C + c, f);
+        if (PASS == 1) V8<__nv_bfloat16>::load(g + pix * C + c, gg);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float mean = __ldg(stat + ((size_t)n * 2) * C + c + k), inv = __ldg(stat + ((size_t)n * 2 + 1) * C + c + k);
+            const float ga = __ldg(gamma + c + k), be = __ldg(beta + c + k);
+            const float xh = (f[k] - mean) * inv, z = fmaf(ga, xh, be);
+            if (PASS == 0) {
+                r[k] = act_fwd(z, act);
+            } else {
+                const float dz = gg[k] * act_grad(z, act);
+                const float c1 = __ldg(sums + ((size_t)n * 2) * C + c + k) / P, c2 = __ldg(sums + ((size_t)n * 2 + 1) * C + c + k) / P;
+                r[k] = ga * inv * (dz - c1 - xh * c2);
+            }
+        }
+        V8<__nv_bfloat16>::store(out + pix * C + c, r);
+    }
+}
+
 // ---------------------------------------------------------------- re-parameterisation + KL
 // h = [N][2*Dz] fp32 (mu | logstd, the NCHW flatten of the encoder output; reference models.py:559-560),
 // z = mu + exp(logstd) * eps (models.py:561), sum_blocks kl_part[n][.] = sum_d(-0.5 - ls + 0.5 mu^2 + 0.5 exp(2 ls)) (losses.py:392).
@@ -1003,38 +1129,63 @@ __global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu_p, const floa
 // l = squared (ReconLoss / nn.MSELoss, losses.py:396-403) or absolute (nn.L1Loss, losses.py:128) error;
 // grad = gscale * dl/dlogits, written fp32 (same layout as the inputs) and/or bf16 NHWC padded to Cp channels.
 // Block reduce: warp shuffle -> shared -> one atomicAdd per block.
+// VEC = 4: a thread owns four consecutive pixels of one image (HW % 4 == 0): every plane access is a 16-byte vector.
+template <int VEC>
 __global__ void recon_loss_kernel(const float* __restrict__ logits, const float* __restrict__ target, float* __restrict__ pred_out,
                                   float* __restrict__ grad_f32, __nv_bfloat16* __restrict__ grad_nhwc, float* __restrict__ loss_sum,
                                   int N, int C, int HW, int Cp, int l1, int use_sigmoid, float gscale, void* ws) {
     __shared__ float red[34];
     __shared__ int red_flag;
     float acc = 0.f;
-    const long long P = (long long)N * HW;
-    for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < P; pix += (long long)gridDim.x * blockDim.x) {
+    const long long P = (long long)N * HW / VEC;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < P; q += (long long)gridDim.x * blockDim.x) {
+        const long long pix = q * VEC;
         const int n = (int)(pix / HW), hw = (int)(pix % HW);
-        float gr[16];
+        float gr[VEC][16];
+        if (grad_nhwc) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) gr[k] = 0.f;
+            for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                for (int k = 0; k < 16; ++k) gr[v][k] = 0.f;
+        }
         for (int c = 0; c < C; ++c) {
             const long long idx = ((long long)n * C + c) * HW + hw;
-            const float o = __ldg(logits + idx), t = __ldg(target + idx);
-            const float s = use_sigmoid ? 1.f / (1.f + expf(-o)) : o;
-            const float d = s - t;
-            acc += l1 ? fabsf(d) : d * d;
-            float gd = l1 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : 2.f * d;
-            if (use_sigmoid) gd *= s * (1.f - s);
-            gd *= gscale;
-            if (pred_out) pred_out[idx] = s;
-            if (grad_f32) grad_f32[idx] = gd;
-            if (c < 16) gr[c] = gd;
+            float o[VEC], t[VEC], sg[VEC], gd[VEC];
+            if (VEC == 4) {
+                const float4 o4 = __ldg(reinterpret_cast<const float4*>(logits + idx)), t4 = __ldg(reinterpret_cast<const float4*>(target + idx));
+                o[0] = o4.x; o[1 % VEC] = o4.y; o[2 % VEC] = o4.z; o[3 % VEC] = o4.w;
+                t[0] = t4.x; t[1 % VEC] = t4.y; t[2 % VEC] = t4.z; t[3 % VEC] = t4.w;
+            } else {
+                o[0] = __ldg(logits + idx);
+                t[0] = __ldg(target + idx);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                sg[v] = use_sigmoid ? 1.f / (1.f + expf(-o[v])) : o[v];
+                const float d = sg[v] - t[v];
+                acc += l1 ? fabsf(d) : d * d;
+                float g = l1 ? (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) : 2.f * d;
+                if (use_sigmoid) g *= sg[v] * (1.f - sg[v]);
+                gd[v] = g * gscale;
+                if (grad_nhwc && c < 16) gr[v][c] = gd[v];
+            }
+            if (VEC == 4) {
+                if (pred_out) *reinterpret_cast<float4*>(pred_out + idx) = make_float4(sg[0], sg[1 % VEC], sg[2 % VEC], sg[3 % VEC]);
+                if (grad_f32) *reinterpret_cast<float4*>(grad_f32 + idx) = make_float4(gd[0], gd[1 % VEC], gd[2 % VEC], gd[3 % VEC]);
+            } else {
+                if (pred_out) pred_out[idx] = sg[0];
+                if (grad_f32) grad_f32[idx] = gd[0];
+            }
         }
         if (grad_nhwc) {
-            for (int c0 = 0; c0 < Cp; c0 += 8) {
-                float f[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) f[k] = (c0 + k < 16) ? gr[c0 + k] : 0.f;
-                V8<__nv_bfloat16>::store(grad_nhwc + pix * Cp + c0, f);
-            }
+            for (int v = 0; v < VEC; ++v)
+                for (int c0 = 0; c0 < Cp; c0 += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] = (c0 + k < 16) ? gr[v][c0 + k] : 0.f;
+                    V8<__nv_bfloat16>::store(grad_nhwc + (pix + v) * Cp + c0, f);
+                }
         }
     }
     acc = warp_sum(acc);
@@ -1264,6 +1415,50 @@ extern "C" __attribute__((visibility("default"))) int fv_act_bwd(const void* out
     return FV_OK;
 }
 
+static int in_check(const char* who, int N, int H, int W, int C) {
+    if (N < 1 || H < 1 || W < 1 || C < 8 || C % 8) return fail(FV_ERR_UNSUPPORTED, "%s: N=%d H=%d W=%d C=%d (C must be a multiple of 8)", who, N, H, W, C);
+    if ((long long)N * H * W * (C / 8) >= (1LL << 40)) return fail(FV_ERR_UNSUPPORTED, "%s: tensor too large", who);
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_in_stats(const void* y, float* stat, int N, int H, int W, int C, float eps, void* stream) {
+    if (!y || !stat) return fail(FV_ERR_ARG, "fv_in_stats: null pointer");
+    if (int e = in_check("fv_in_stats", N, H, W, C)) return e;
+    in_reduce_kernel<0><<<dim3((C + 63) / 64, N), 256, 0, STREAM>>>((const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, stat, H * W, C, 0, eps);
+    FV_LAUNCH_CHECK("in_reduce_kernel<stats>");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_in_act_fwd(const void* y, const float* stat, const float* gamma, const float* beta, void* out, int N, int H,
+                                                                  int W, int C, int act, void* stream) {
+    if (!y || !stat || !gamma || !beta || !out) return fail(FV_ERR_ARG, "fv_in_act_fwd: null pointer");
+    if (int e = in_check("fv_in_act_fwd", N, H, W, C)) return e;
+    in_apply_kernel<0><<<grid_for((long long)N * H * W * (C / 8)), 256, 0, STREAM>>>((const __nv_bfloat16*)y, nullptr, stat, nullptr, gamma, beta,
+                                                                                     (__nv_bfloat16*)out, N, H * W, C, act);
+    FV_LAUNCH_CHECK("in_apply_kernel<fwd>");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_in_bwd_sums(const void* y, const void* g, const float* stat, const float* gamma, const float* beta,
+                                                                   float* sums, int N, int H, int W, int C, int act, void* stream) {
+    if (!y || !g || !stat || !gamma || !beta || !sums) return fail(FV_ERR_ARG, "fv_in_bwd_sums: null pointer");
+    if (int e = in_check("fv_in_bwd_sums", N, H, W, C)) return e;
+    in_reduce_kernel<1><<<dim3((C + 63) / 64, N), 256, 0, STREAM>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)g, stat, gamma, beta, sums, H * W, C,
+                                                                     act, 0.f);
+    FV_LAUNCH_CHECK("in_reduce_kernel<bwd>");
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_in_bwd_apply(const void* y, const void* g, const float* stat, const float* sums, const float* gamma,
+                                                                    const float* beta, void* dy, int N, int H, int W, int C, int act, void* stream) {
+    if (!y || !g || !stat || !sums || !gamma || !beta || !dy) return fail(FV_ERR_ARG, "fv_in_bwd_apply: null pointer");
+    if (int e = in_check("fv_in_bwd_apply", N, H, W, C)) return e;
+    in_apply_kernel<1><<<grid_for((long long)N * H * W * (C / 8)), 256, 0, STREAM>>>((const __nv_bfloat16*)y, (const __nv_bfloat16*)g, stat, sums, gamma, beta,
+                                                                                     (__nv_bfloat16*)dy, N, H * W, C, act);
+    FV_LAUNCH_CHECK("in_apply_kernel<bwd>");
+    return FV_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) long long fv_reduce_ws_bytes(void) {
     return (long long)det_reduce_ws_bytes(kRedGroup * kRedMaxGroups, 1024, sizeof(float));
 }
@@ -1288,18 +1483,47 @@ static int reduce_geometry(int C, long long P, int& grid, size_t& shmem, int res
     return rpi;
 }
 
-extern "C" __attribute__((visibility("default"))) int fv_bn_stats(const void* y, int dtype, float* sums, long long P, int C, void* ws, void* stream) {
+static unsigned long long xrank_timeout_ns_glue() {
+    static unsigned long long cached = 0;
+    if (!cached) {
+        const char* v = getenv("FACEVAE_XRANK_TIMEOUT_S");
+        double s_ = v ? atof(v) : 600.0;
+        if (!(s_ > 0)) s_ = 600.0;
+        cached = (unsigned long long)(s_ * 1e9);
+    }
+    return cached;
+}
+
+static int bn_stats_impl(const void* y, int dtype, float* sums, long long P, int C, void* ws, const XrankArgs& xr, void* stream) {
     if (!y || !sums) return fail(FV_ERR_ARG, "fv_bn_stats: null pointer");
     if (int e = check_c8("fv_bn_stats", C)) return e;
     int grid; size_t sh;
     reduce_geometry(C, P, grid, sh, 4);            // 51 registers: four 256-thread blocks per SM
     if (int e = check_ws("fv_bn_stats", ws, grid, 2 * C, 4)) return e;
     if (dtype == FV_DT_BF16)
-        bn_stats_kernel<__nv_bfloat16><<<grid, kThreads, sh, STREAM>>>((const __nv_bfloat16*)y, sums, P, C, ws);
+        bn_stats_kernel<__nv_bfloat16><<<grid, kThreads, sh, STREAM>>>((const __nv_bfloat16*)y, sums, P, C, ws, xr);
     else
-        bn_stats_kernel<float><<<grid, kThreads, sh, STREAM>>>((const float*)y, sums, P, C, ws);
+        bn_stats_kernel<float><<<grid, kThreads, sh, STREAM>>>((const float*)y, sums, P, C, ws, xr);
     FV_LAUNCH_CHECK("bn_stats_kernel");
     return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bn_stats(const void* y, int dtype, float* sums, long long P, int C, void* ws, void* stream) {
+    XrankArgs xr{};
+    return bn_stats_impl(y, dtype, sums, P, C, ws, xr, stream);
+}
+
+// fv_bn_stats + fv_bn_finalize_xrank(mode 0) in ONE launch: the block that ends up with this rank's sums pushes them to the
+// peers, gathers theirs and writes stat[4][C] (+ running statistics).  `sums` still receives the LOCAL sums.
+extern "C" __attribute__((visibility("default"))) int fv_bn_stats_xrank(const void* y, int dtype, float* sums, long long P, int C, void* ws, void* peer_bufs_dev,
+                                                                      int rank, int world, void* epoch_ctr, double count, const float* gamma,
+                                                                      const float* beta, float* running_mean, float* running_var, float momentum,
+                                                                      float eps, float* stat, void* stream) {
+    if (!peer_bufs_dev || !epoch_ctr || !gamma || !beta || !stat || count <= 0 || world < 1 || world > kXMaxWorld || rank < 0 || rank >= world || 2 * C > kXRow)
+        return fail(FV_ERR_ARG, "fv_bn_stats_xrank: bad arguments (rank %d / world %d, C=%d)", rank, world, C);
+    XrankArgs xr{sums, reinterpret_cast<unsigned long long* const*>(peer_bufs_dev), rank, world, reinterpret_cast<unsigned long long*>(epoch_ctr), C, 0,
+                 count, gamma, beta, running_mean, running_var, momentum, eps, stat, nullptr, nullptr, 0, xrank_timeout_ns_glue()};
+    return bn_stats_impl(y, dtype, sums, P, C, ws, xr, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int fv_bn_finalize(const float* sums, double count, const float* gamma, const float* beta, float* running_mean,
@@ -1358,8 +1582,8 @@ static int bn_act_fwd_impl(const void* y, int in_dtype, const float* stat, void*
     return FV_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_reduce(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat,
-                                    float* sums, int N, int H, int W, int C, int mode, int act, void* ws, void* stream) {
+static int bn_act_bwd_reduce_impl(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat,
+                                    float* sums, int N, int H, int W, int C, int mode, int act, void* ws, const XrankArgs& xr, void* stream) {
     if (!y || !g || !stat || !sums) return fail(FV_ERR_ARG, "fv_bn_act_bwd_reduce: null pointer");
     if (int e = check_c8("fv_bn_act_bwd_reduce", C)) return e;
     if ((long long)N * H * W >= (1LL << 31)) return fail(FV_ERR_UNSUPPORTED, "fv_bn_act_bwd_reduce: tensor too large for 32-bit indexing");
@@ -1369,7 +1593,7 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_reduce(const
     // channels = 150 k serialised atomics cost more than the second wave's tail gains)
     reduce_geometry(C, (long long)N * H * W, grid, sh, 2, 16, 2);
     if (int e = check_ws("fv_bn_act_bwd_reduce", ws, grid, 2 * C, 4)) return e;
-#define LAUNCH3(TY, TG, M, GNF) bn_act_bwd_reduce_kernel<TY, TG, M, GNF><<<grid, kThreads, sh, STREAM>>>((const TY*)y, (const TG*)g, stat, sums, N, H, W, C, act, ws)
+#define LAUNCH3(TY, TG, M, GNF) bn_act_bwd_reduce_kernel<TY, TG, M, GNF><<<grid, kThreads, sh, STREAM>>>((const TY*)y, (const TG*)g, stat, sums, N, H, W, C, act, ws, xr)
 #define LAUNCH2(TY, TG) do { \
         if (mode == FV_MODE_POOL) { if (g_nchw) LAUNCH3(TY, TG, FV_MODE_POOL, true); else LAUNCH3(TY, TG, FV_MODE_POOL, false); } \
         else if (mode == FV_MODE_UP) LAUNCH3(TY, TG, FV_MODE_UP, false); \
@@ -1382,6 +1606,26 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_reduce(const
 #undef LAUNCH3
     FV_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
     return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_reduce(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat,
+                                    float* sums, int N, int H, int W, int C, int mode, int act, void* ws, void* stream) {
+    XrankArgs xr{};
+    return bn_act_bwd_reduce_impl(y, y_dtype, g, g_dtype, g_nchw, stat, sums, N, H, W, C, mode, act, ws, xr, stream);
+}
+
+// fv_bn_act_bwd_reduce + fv_bn_finalize_xrank(mode 1) in ONE launch: coef[2][C] from the cross-rank sums, dgamma / dbeta from the
+// local ones (`sums` still receives the local sums).
+extern "C" __attribute__((visibility("default"))) int fv_bn_act_bwd_reduce_xrank(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw,
+                                                                               const float* stat, float* sums, int N, int H, int W, int C, int mode,
+                                                                               int act, void* ws, void* peer_bufs_dev, int rank, int world,
+                                                                               void* epoch_ctr, double count, float* coef, float* dgamma, float* dbeta,
+                                                                               void* stream) {
+    if (!peer_bufs_dev || !epoch_ctr || !coef || count <= 0 || world < 1 || world > kXMaxWorld || rank < 0 || rank >= world || 2 * C > kXRow)
+        return fail(FV_ERR_ARG, "fv_bn_act_bwd_reduce_xrank: bad arguments (rank %d / world %d, C=%d)", rank, world, C);
+    XrankArgs xr{sums, reinterpret_cast<unsigned long long* const*>(peer_bufs_dev), rank, world, reinterpret_cast<unsigned long long*>(epoch_ctr), C, 1,
+                 count, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, coef, dgamma, dbeta, 0, xrank_timeout_ns_glue()};
+    return bn_act_bwd_reduce_impl(y, y_dtype, g, g_dtype, g_nchw, stat, sums, N, H, W, C, mode, act, ws, xr, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int fv_bn_bwd_finalize(const float* sums_local, const float* sums_global, double count, float* dgamma, float* dbeta,
@@ -1440,9 +1684,10 @@ static int bn_act_bwd_apply_impl(const void* y, int y_dtype, const void* g, int 
 extern "C" __attribute__((visibility("default"))) int fv_colsum(const void* y, float* sums, long long P, int C, void* ws, void* stream) {
     if (!y || !sums) return fail(FV_ERR_ARG, "fv_colsum: null pointer");
     if (C % 8 || C < 8) return fail(FV_ERR_UNSUPPORTED, "fv_colsum: channel count %d must be a multiple of 8", C);
-    // rows wider than 2048 channels (the 16 -> 256*16 mid_conv of EFE_conv5) are walked in column chunks of <= 2048
-    for (int c0 = 0; c0 < C; c0 += 2048) {
-        const int cn = C - c0 < 2048 ? C - c0 : 2048;
+    // rows wider than 1024 channels (the 16 -> 256*16 mid_conv of EFE_conv5) are walked in column chunks of <= 1024 (the
+    // reduction workspace holds vectors of up to 1024 floats)
+    for (int c0 = 0; c0 < C; c0 += 1024) {
+        const int cn = C - c0 < 1024 ? C - c0 : 1024;
         if (int e = check_c8("fv_colsum", cn)) return e;
         int grid; size_t sh;
         reduce_geometry(cn, P, grid, sh);
@@ -1492,10 +1737,16 @@ extern "C" __attribute__((visibility("default"))) int fv_recon_loss(const float*
                              void* ws, void* stream) {
     if (!logits || !target || !loss_sum) return fail(FV_ERR_ARG, "fv_recon_loss: null pointer");
     if (grad_nhwc && (Cp % 8 || Cp < C || C > 16)) return fail(FV_ERR_UNSUPPORTED, "fv_recon_loss: NHWC gradient needs C <= 16 <= Cp, Cp %% 8 == 0");
-    const int grid = grid_for((long long)N * H * W);
+    const bool vec = (H * W) % 4 == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(pred_out) |
+                                           reinterpret_cast<uintptr_t>(grad_f32)) & 15) == 0;
+    const int grid = grid_for((long long)N * H * W / (vec ? 4 : 1));
     if (int e = check_ws("fv_recon_loss", ws, grid, 1, 4)) return e;
-    recon_loss_kernel<<<grid, kThreads, 0, STREAM>>>(logits, target, pred_out, grad_f32, (__nv_bfloat16*)grad_nhwc, loss_sum, N, C, H * W, Cp, l1,
-                                                     use_sigmoid, gscale, ws);
+    if (vec)
+        recon_loss_kernel<4><<<grid, kThreads, 0, STREAM>>>(logits, target, pred_out, grad_f32, (__nv_bfloat16*)grad_nhwc, loss_sum, N, C, H * W, Cp, l1,
+                                                            use_sigmoid, gscale, ws);
+    else
+        recon_loss_kernel<1><<<grid, kThreads, 0, STREAM>>>(logits, target, pred_out, grad_f32, (__nv_bfloat16*)grad_nhwc, loss_sum, N, C, H * W, Cp, l1,
+                                                            use_sigmoid, gscale, ws);
     FV_LAUNCH_CHECK("recon_loss_kernel");
     return FV_OK;
 }

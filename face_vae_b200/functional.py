@@ -21,6 +21,7 @@ _SYNC_BN = True
 import os as _os
 _FUSE_STATS = _os.environ.get("FACEVAE_FUSE_BN_STATS", "1") != "0"
 _FUSE_FIN = _os.environ.get("FACEVAE_FUSE_BN_FINALIZE", "1") != "0"
+_FUSE_XRANK = _os.environ.get("FACEVAE_FUSE_XRANK", "1") != "0"
 
 
 def _fin_fused(training: bool) -> bool:
@@ -38,6 +39,17 @@ def _world() -> int:
     if _SYNC_BN and dist.is_available() and dist.is_initialized():
         return dist.get_world_size()
     return 1
+
+
+def _bn_backward_sums(y, g, stat, post_mode, act, g_nchw, count, training):
+    """Backward pass 1 of a norm + act layer -> (dgamma, dbeta, coef) with the cross-rank exchange folded into the reduction
+    kernel when data parallel, else None (the caller runs the separate reduce / finalize)."""
+    if not training or _world() == 1 or not _FUSE_XRANK:
+        return None
+    xc = xrank.get()
+    if xc is None:
+        return None
+    return xc.reduce_finalize_bwd(y, g, stat, post_mode, act, g_nchw, count)
 
 
 def _bn_backward_finalize(s_local, count, c, training):
@@ -112,9 +124,13 @@ def _bn_forward(y, gamma, beta, running_mean, running_var, training, momentum, e
     if not training:
         return ops.bn_eval_affine(gamma, beta, running_mean, running_var, eps), n * h * w
     count = n * h * w * _world()
+    xc = xrank.get() if _world() > 1 else None
+    if xc is not None and sums is None and _FUSE_XRANK:
+        # statistic pass, NVLink exchange and finalize in one launch: the reduction's last block pushes this rank's sums to all
+        # peers, gathers theirs and writes the stat block
+        return xc.stats_finalize_fwd(y, count, gamma, beta, running_mean, running_var, momentum, eps), count
     if sums is None:
         sums = ops.bn_stats(y)
-    xc = xrank.get() if _world() > 1 else None
     if xc is not None:   # one kernel: push partial sums to all peers over NVLink, reduce, finalize
         return xc.finalize_fwd(sums, count, gamma, beta, running_mean, running_var, momentum, eps), count
     sums = _allreduce_sum(sums)
@@ -198,12 +214,17 @@ class ConvBNAct(torch.autograd.Function):
         g = g.contiguous()
         c = y.shape[3]
         # eval mode: running statistics are constants, dy = scale * dz, no coupling terms
-        s_local = ops.bn_act_bwd_reduce(y, g, stat, post_mode, act, out_nchw_f32)
-        if _fin_fused(training):
-            dy, dgamma, dbeta = ops.bn_act_bwd_apply_fin(y, g, stat, s_local, count, post_mode, act, None, out_nchw_f32)
-        else:
-            dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
+        fused = _bn_backward_sums(y, g, stat, post_mode, act, out_nchw_f32, count, training)
+        if fused is not None:
+            dgamma, dbeta, coef = fused
             dy = ops.bn_act_bwd_apply(y, g, stat, coef, post_mode, act, None, out_nchw_f32)
+        else:
+            s_local = ops.bn_act_bwd_reduce(y, g, stat, post_mode, act, out_nchw_f32)
+            if _fin_fused(training):
+                dy, dgamma, dbeta = ops.bn_act_bwd_apply_fin(y, g, stat, s_local, count, post_mode, act, None, out_nchw_f32)
+            else:
+                dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
+                dy = ops.bn_act_bwd_apply(y, g, stat, coef, post_mode, act, None, out_nchw_f32)
         dx, dw = _conv_backward(geom, x, dy, weight, wd, ksize, ctx.needs_input_grad[0])
         db = None
         if ctx.has_bias:
@@ -259,6 +280,44 @@ class ConvELRAct(torch.autograd.Function):
                     _, wback = ops.weight_prep(ops.demod_fwd(weight, gain, demod)[0], False, True)
                 dx = ops.conv2d(dy, wback, None, x.shape[3], ksize, None, OUT_NHWC_BF16, (co, ci))
         return dx, dw, db, None, None, None, None, None
+
+
+class InstanceNormAct(torch.autograd.Function):
+    """nn.InstanceNorm2d(C, affine=True) + ReLU / LeakyReLU(0.2) on NHWC bf16 (reference modules.py:21,27,29; the Discriminator's
+    blocks, models.py:1120-1127): per-(image, channel) statistics over H*W, no running statistics."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, act, eps):
+        stat = ops.in_stats(y, eps)
+        out = ops.in_act_fwd(y, stat, gamma, beta, act)
+        ctx.save_for_backward(y, stat, gamma, beta)
+        ctx.act = act
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y, stat, gamma, beta = ctx.saved_tensors
+        dy, dgamma, dbeta = ops.in_bwd(y, g.contiguous(), stat, gamma, beta, ctx.act)
+        return dy, dgamma, dbeta, None, None
+
+
+class ActOnly(torch.autograd.Function):
+    """ReLU / LeakyReLU(0.2) on an NHWC bf16 tensor (a block without a norm layer)."""
+
+    @staticmethod
+    def forward(ctx, y, act):
+        c = y.shape[3]
+        stat = torch.zeros((4, c), device=y.device, dtype=torch.float32)
+        stat[1:3].fill_(1.0)                     # identity affine
+        out = ops.bn_act_fwd(y, stat, MODE_NONE, act, torch.bfloat16)
+        ctx.save_for_backward(out)
+        ctx.act = act
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        return ops.act_bwd(out, g.contiguous(), ctx.act), None
 
 
 class PointwiseBNAct(torch.autograd.Function):
@@ -333,12 +392,17 @@ class BNActConv(torch.autograd.Function):
         db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
         da, dw = _conv_backward(GEOM_SAME, a, g, weight, wd, ksize, True)
         c = x.shape[3]
-        s_local = ops.bn_act_bwd_reduce(x, da, stat, MODE_NONE, act)
-        if _fin_fused(training):
-            dx, dgamma, dbeta = ops.bn_act_bwd_apply_fin(x, da, stat, s_local, count, MODE_NONE, act)
-        else:
-            dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
+        fused = _bn_backward_sums(x, da, stat, MODE_NONE, act, False, count, training)
+        if fused is not None:
+            dgamma, dbeta, coef = fused
             dx = ops.bn_act_bwd_apply(x, da, stat, coef, MODE_NONE, act) if ctx.needs_input_grad[0] else None
+        else:
+            s_local = ops.bn_act_bwd_reduce(x, da, stat, MODE_NONE, act)
+            if _fin_fused(training):
+                dx, dgamma, dbeta = ops.bn_act_bwd_apply_fin(x, da, stat, s_local, count, MODE_NONE, act)
+            else:
+                dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
+                dx = ops.bn_act_bwd_apply(x, da, stat, coef, MODE_NONE, act) if ctx.needs_input_grad[0] else None
         dres = g if ctx.has_res else None
         return dx, dres, dw, db, dgamma, dbeta, None, None, None, None, None, None, None
 

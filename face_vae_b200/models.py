@@ -122,6 +122,68 @@ class EFE_conv5(nn.Module):
                                   "the hot path (SURVEY.md 2.1); use forward_2d for the 2-D stage")
 
 
+class Generator(nn.Module):
+    """The 2-D decoder of the reference's ``Generator`` (models.py:1085-1111): in_conv (CNA 3x3, LeakyReLU) -> mid_conv (1x1) ->
+    occlusion gate -> ResBlock2D x n_res -> UpBlock2D stack -> out_conv (7x7) -> sigmoid, every block spectral-normalised
+    (``use_weight_norm=True``).  Same constructor, sub-module names and state_dict keys.  The reference's ``forward(fs,
+    deformation, occlusion)`` first warps the 3-D feature volume with ``F.grid_sample`` (keypoint / motion geometry, outside the
+    hot path); ``forward_2d(fs2d, occlusion)`` takes the warped features already flattened to [N, C*D, H, W] (models.py:1102)."""
+
+    def __init__(self, use_weight_norm=True, n_res=6, up_seq=[256, 128, 64], D=16, C=32):
+        super().__init__()
+        from .modules import ConvBlock2D
+        self.in_conv = ConvBlock2D("CNA", C * D, up_seq[0], 3, 1, 1, use_weight_norm, nonlinearity_type="leakyrelu")
+        self.mid_conv = Conv2d(up_seq[0], up_seq[0], 1, 1, 0)
+        self.res = nn.Sequential(*[ResBlock2D(up_seq[0], use_weight_norm) for _ in range(n_res)])
+        self.up = nn.Sequential(*[UpBlock2D(up_seq[i], up_seq[i + 1], use_weight_norm) for i in range(len(up_seq) - 1)])
+        self.out_conv = Conv2d(up_seq[-1], 3, 7, 1, 3)
+
+    def forward_2d(self, fs2d, occlusion=None):
+        t = self.in_conv.forward_nhwc(as_nhwc(fs2d))
+        t = Fn.ConvOnly.apply(t, self.mid_conv.weight, self.mid_conv.bias, 1, OUT_NHWC_BF16)
+        if occlusion is not None:                                    # fs = fs * occlusion (models.py:1105): [N,1,H,W] gate
+            t = t * occlusion.permute(0, 2, 3, 1).to(t.dtype)
+        for blk in self.res:
+            t = blk.forward_nhwc(t.contiguous())
+        for blk in self.up:
+            t = blk.forward_nhwc(t)
+        logits = Fn.ConvOnly.apply(t, self.out_conv.weight, self.out_conv.bias, 7, OUT_NCHW_F32)
+        return torch.sigmoid(logits)
+
+    def forward(self, fs, deformation, occlusion):
+        raise NotImplementedError("Generator.forward warps a 3-D feature volume with F.grid_sample (models.py:1101-1102), which is outside "
+                                  "the hot path; use forward_2d(fs2d, occlusion) on the warped, flattened features")
+
+
+class Discriminator(nn.Module):
+    """The reference's patch ``Discriminator`` (models.py:1114-1139): spectral-normalised CNA blocks with instance norm and
+    LeakyReLU(0.2), 3x3 stride 2 / stride 1, and a final un-normalised 3x3 ``CN`` block.  Same constructor, ``layers`` ModuleList
+    and state_dict keys.  ``forward(x, kp)`` needs the keypoint heat-map ``kp2gaussian_2d`` (reference utils.py, outside the hot
+    path); ``forward_features(x_cat)`` takes the concatenated ``[frame | heat-map]`` tensor (models.py:1130-1131) and returns
+    ``(output, features)`` as the reference does."""
+
+    def __init__(self, use_weight_norm=True, down_seq=[64, 128, 256, 512], K=15):
+        super().__init__()
+        from .modules import ConvBlock2D
+        layers = [ConvBlock2D("CNA", 3 + K, down_seq[0], 3, 2, 1, use_weight_norm, "instance", "leakyrelu")]
+        layers.extend([ConvBlock2D("CNA", down_seq[i], down_seq[i + 1], 3, 2 if i < len(down_seq) - 2 else 1, 1, use_weight_norm, "instance",
+                                   "leakyrelu") for i in range(len(down_seq) - 1)])
+        layers.append(ConvBlock2D("CN", down_seq[-1], 1, 3, 1, 1, use_weight_norm, activation_type="none"))
+        self.layers = nn.ModuleList(layers)
+
+    def forward_features(self, x_cat):
+        res = [x_cat]
+        t = as_nhwc(x_cat)
+        for layer in self.layers:
+            t = layer.forward_nhwc(t)
+            res.append(as_nchw(t, layer.out_channels))
+        return res[-1], res[1:-1]
+
+    def forward(self, x, kp):
+        raise NotImplementedError("Discriminator.forward builds a keypoint heat-map with kp2gaussian_2d (reference utils.py:121-127), which is "
+                                  "outside the hot path; use forward_features(torch.cat([x, heatmap], dim=1))")
+
+
 class FaceVAE(nn.Module):
     """The anchor "face-vae" (SURVEY.md section 8).  Sub-module names give the oracle's state_dict keys."""
 

@@ -72,19 +72,88 @@ class _Conv2dParams(nn.Module):
 
     def __init__(self, ci: int, co: int, k: int, stride: int, padding: int):
         super().__init__()
-        if stride != 1 or padding != (k - 1) // 2 or k % 2 == 0:
-            raise NotImplementedError("only stride-1 'same' convolutions with odd kernels are on the hot path "
-                                      "(SURVEY.md section 8); strided Conv2dELR is listed under 8f")
-        self.in_channels, self.out_channels, self.kernel_size = ci, co, k
+        _check_conv_geometry(k, stride, padding)
+        self.in_channels, self.out_channels, self.kernel_size, self.stride = ci, co, k, stride
         self.weight = nn.Parameter(torch.empty(co, ci, k, k))
         self.bias = nn.Parameter(torch.empty(co))
         nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
         bound = 1.0 / math.sqrt(ci * k * k)
         nn.init.uniform_(self.bias, -bound, bound)
 
+    def effective_weight(self) -> torch.Tensor:
+        return self.weight
+
     def forward(self, x):                      # plain conv on a logical NCHW tensor
-        y = Fn.ConvOnly.apply(as_nhwc(x), self.weight, self.bias, self.kernel_size, OUT_NHWC_BF16)
+        y = _conv_nhwc(as_nhwc(x), self.weight, self.bias, self.kernel_size, self.stride)
         return as_nchw(y, self.out_channels)
+
+
+def _check_conv_geometry(k: int, stride: int, padding: int) -> None:
+    same = stride == 1 and k % 2 == 1 and padding == (k - 1) // 2
+    strided = stride == 2 and k == 3 and padding == 1          # the Discriminator's down-sampling blocks (reference models.py:1120-1123)
+    if not (same or strided):
+        raise NotImplementedError(f"conv kernel {k} stride {stride} padding {padding}: supported are stride-1 'same' convolutions with odd "
+                                  "kernels and 3x3 stride-2 padding-1 (4x4 stride 2 lives in Conv2dELR)")
+
+
+def _conv_nhwc(x, weight, bias, k: int, stride: int):
+    """Plain convolution on an NHWC bf16 tensor.  3x3 stride 2 pad 1 is the 4x4 stride-2 pad-1 kernel with a zero fourth row and
+    column of taps (output pixel i reads input rows 2i-1 .. 2i+1); the zero padding is a torch op on the (tiny) weight, so its
+    gradient is sliced back by autograd."""
+    if stride == 2:
+        w4 = torch.nn.functional.pad(weight, (0, 1, 0, 1))
+        return Fn.ConvELRAct.apply(x, w4.contiguous(), bias, 4, 2, 1.0, False, ACT_NONE)
+    return Fn.ConvOnly.apply(x, weight, bias, k, OUT_NHWC_BF16)
+
+
+class _SpectralConv2dParams(nn.Module):
+    """``torch.nn.utils.spectral_norm(nn.Conv2d(...))`` as the reference's ``_ConvBlock`` builds it with ``use_weight_norm=True``
+    (reference modules.py:11,14,32): state_dict keys ``weight_orig``, ``bias``, ``weight_u``, ``weight_v``; one power iteration per
+    training-mode forward (u, v updated in place, no gradient through them), W = W_orig / (u^T W_orig v).  The power iteration and
+    the division are a handful of matrix-vector products on the [Co, Ci*k*k] filter -- library calls on the weight, whose result
+    feeds the same convolution kernels; autograd carries the gradient of W back to ``weight_orig``."""
+
+    def __init__(self, ci: int, co: int, k: int, stride: int, padding: int, n_power_iterations: int = 1, eps: float = 1e-12):
+        super().__init__()
+        _check_conv_geometry(k, stride, padding)
+        self.in_channels, self.out_channels, self.kernel_size, self.stride = ci, co, k, stride
+        self.n_power_iterations, self.eps = n_power_iterations, eps
+        self.weight_orig = nn.Parameter(torch.empty(co, ci, k, k))
+        self.bias = nn.Parameter(torch.empty(co))
+        nn.init.kaiming_uniform_(self.weight_orig, a=math.sqrt(5))
+        bound = 1.0 / math.sqrt(ci * k * k)
+        nn.init.uniform_(self.bias, -bound, bound)
+        self.register_buffer("weight_u", torch.nn.functional.normalize(torch.randn(co), dim=0, eps=eps))
+        self.register_buffer("weight_v", torch.nn.functional.normalize(torch.randn(ci * k * k), dim=0, eps=eps))
+        self.prep_kind = -1            # the filter operand depends on sigma: prepared per call
+
+    def effective_weight(self) -> torch.Tensor:
+        w = self.weight_orig
+        mat = w.reshape(w.shape[0], -1)
+        u, v = self.weight_u, self.weight_v
+        if self.training:
+            with torch.no_grad():
+                for _ in range(self.n_power_iterations):
+                    v = torch.nn.functional.normalize(torch.mv(mat.t(), u), dim=0, eps=self.eps, out=v)
+                    u = torch.nn.functional.normalize(torch.mv(mat, v), dim=0, eps=self.eps, out=u)
+                u, v = u.clone(), v.clone()
+        sigma = torch.dot(u, torch.mv(mat, v))
+        return w / sigma
+
+    def forward(self, x):
+        y = _conv_nhwc(as_nhwc(x), self.effective_weight().contiguous(), self.bias, self.kernel_size, self.stride)
+        return as_nchw(y, self.out_channels)
+
+
+class _InstanceNormParams(nn.Module):
+    """Parameter holder with nn.InstanceNorm2d(C, affine=True)'s state_dict keys (weight, bias; no running statistics)."""
+
+    def __init__(self, c: int):
+        super().__init__()
+        self.num_features = c
+        self.eps = BN_EPS
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
 
 
 class _Act(nn.Module):
@@ -102,52 +171,68 @@ class Conv2d(_Conv2dParams):
 
 # ---------------------------------------------------------------------------------------------------- blocks
 class ConvBlock2D(nn.Module):
-    """_ConvBlock / ConvBlock2D (reference modules.py:8-49): ``pattern`` in {"CNA", "NAC", "CN"}."""
+    """_ConvBlock / ConvBlock2D (reference modules.py:8-49): ``pattern`` in {"CNA", "NAC", "CN"}; ``activation_type`` "batch"
+    (SyncBatchNorm), "instance" (InstanceNorm2d, affine) or "none"; ``use_weight_norm`` wraps the conv in spectral norm
+    (modules.py:11,14).  The hot path of SURVEY.md section 8 is batch norm without weight norm at stride 1; the spectral-norm /
+    instance-norm / 3x3 stride-2 variants are the Generator's and Discriminator's blocks (section 8f rank 2)."""
 
     def __init__(self, pattern, in_channels, out_channels, kernel_size, stride, padding, use_weight_norm,
                  activation_type="batch", nonlinearity_type="relu"):
         super().__init__()
-        if use_weight_norm:
-            raise NotImplementedError("spectral-norm blocks are outside the hot path (SURVEY.md 2.1 row 1, 8f rank 2)")
-        if activation_type != "batch":
-            raise NotImplementedError("only activation_type='batch' (SyncBatchNorm) is on the hot path")
+        if activation_type not in ("batch", "instance", "none"):
+            raise NotImplementedError(f"activation_type {activation_type!r}: the reference uses batch, instance and none")
         if pattern not in ("CNA", "NAC", "CN"):
             raise NotImplementedError(f"pattern {pattern!r}: the reference uses CNA, NAC and CN only")
+        if pattern == "NAC" and (activation_type != "batch" or stride != 1):
+            raise NotImplementedError("NAC blocks (ResBlock2D) are batch-normalised stride-1 blocks in the reference")
+        if activation_type == "batch" and stride != 1:
+            raise NotImplementedError("strided blocks are instance-normalised in the reference (Discriminator)")
         norm_channels = out_channels if pattern.find("C") < pattern.find("N") else in_channels
-        if norm_channels != pad_channels(norm_channels):
+        if activation_type != "none" and norm_channels != pad_channels(norm_channels):
             raise NotImplementedError("normalised channel counts must be 16, 32 or a multiple of 64")
         self.pattern = pattern
+        self.activation_type = activation_type
         self.act = ACT_NONE if "A" not in pattern else (ACT_RELU if nonlinearity_type == "relu" else ACT_LEAKY)
-        mods = {"C": _Conv2dParams(in_channels, out_channels, kernel_size, stride, padding),
-                "N": _BatchNormParams(norm_channels), "A": _Act(self.act)}
+        conv_cls = _SpectralConv2dParams if use_weight_norm else _Conv2dParams
+        norm = {"batch": _BatchNormParams, "instance": _InstanceNormParams}.get(activation_type)
+        mods = {"C": conv_cls(in_channels, out_channels, kernel_size, stride, padding),
+                "N": norm(norm_channels) if norm is not None else nn.Identity(), "A": _Act(self.act)}
         self.layers = nn.Sequential(*[mods[ch] for ch in pattern])      # same indices as the reference => same keys
-        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        self.in_channels, self.out_channels, self.kernel_size, self.stride = in_channels, out_channels, kernel_size, stride
 
     @property
-    def conv(self) -> _Conv2dParams:
+    def conv(self):
         return self.layers[self.pattern.index("C")]
 
     @property
-    def norm(self) -> _BatchNormParams:
+    def norm(self):
         return self.layers[self.pattern.index("N")]
 
     def forward_nhwc(self, x, post_mode=MODE_NONE, residual=None, out_nchw_f32=False, upsample_input=False):
         """``upsample_input``: the conv reads the nearest-2x up-sampled x (UpBlock2D) -- computed on the coarse grid by the
         phase-decomposed kernel, the up-sampled tensor is never written."""
         conv, bn = self.conv, self.norm
+        weight = conv.effective_weight()
+        if self.activation_type != "batch":
+            if post_mode != MODE_NONE or out_nchw_f32 or upsample_input or residual is not None:
+                raise NotImplementedError("instance-normalised / un-normalised blocks have no fused pool, up-sampling or residual")
+            y = _conv_nhwc(x, weight.contiguous(), conv.bias, self.kernel_size, self.stride)
+            if self.activation_type == "instance":
+                return Fn.InstanceNormAct.apply(y, bn.weight, bn.bias, self.act, bn.eps)
+            return Fn.ActOnly.apply(y, self.act) if self.act != ACT_NONE else y
         if self.training:
             ops.bump_counter(bn.num_batches_tracked)
         if self.pattern in ("CNA", "CN"):
             geom = Fn.GEOM_UP if upsample_input else Fn.GEOM_SAME
             if upsample_input and self.kernel_size != 3:
                 raise NotImplementedError("the fused up-sampling convolution is 3x3 (UpBlock2D)")
-            return Fn.ConvBNAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+            return Fn.ConvBNAct.apply(x, weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                       self.kernel_size, post_mode, self.act, self.training, out_nchw_f32, bn.momentum, bn.eps, geom)
         if upsample_input:
             raise NotImplementedError("NAC blocks have no fused up-sampling")
         if post_mode != MODE_NONE or out_nchw_f32:
             raise NotImplementedError("NAC blocks have no fused pool/upsample")
-        return Fn.BNActConv.apply(x, residual, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+        return Fn.BNActConv.apply(x, residual, weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                   self.kernel_size, self.act, self.training, bn.momentum, bn.eps)
 
     def forward(self, x):
@@ -187,7 +272,8 @@ class UpBlock2D(nn.Module):
     def __init__(self, in_channels, out_channels, use_weight_norm):
         super().__init__()
         self.layers = nn.Sequential(_Up(), ConvBlock2D("CNA", in_channels, out_channels, 3, 1, 1, use_weight_norm))
-        self.layers[1].conv.prep_kind = ops.PREP_UP        # ops.step_scope prepares the phase filters for this weight
+        if not use_weight_norm:
+            self.layers[1].conv.prep_kind = ops.PREP_UP    # ops.step_scope prepares the phase filters for this weight
         self.out_channels = out_channels
 
     def forward_nhwc(self, x, pre_upsampled=False, post_mode=MODE_NONE):
@@ -214,7 +300,7 @@ class SameBlock2D(nn.Module):
         blk = self.layers
         return (self.training and x.dim() == 4 and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
                 and not x.requires_grad and x.shape[1] <= 4 and blk.in_channels == x.shape[1] and blk.out_channels == 32
-                and blk.pattern == "CNA")
+                and blk.pattern == "CNA" and blk.activation_type == "batch" and isinstance(blk.conv, _Conv2dParams))
 
     def forward_from_frames(self, x):
         """x: NCHW fp32 frames -> NHWC bf16 [N,H,W,32]."""

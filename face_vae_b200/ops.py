@@ -679,6 +679,38 @@ def bn_act_bwd_apply(y: torch.Tensor, g: torch.Tensor, stat: torch.Tensor, coef:
     return dy
 
 
+# ------------------------------------------------------------------------------------------------ instance norm (Discriminator blocks)
+def in_stats(y: torch.Tensor, eps: float = BN_EPS) -> torch.Tensor:
+    """NHWC bf16 [N,H,W,C] -> stat [N, 2, C] (mean | invstd per image and channel): nn.InstanceNorm2d statistics."""
+    _chk(y, "y", torch.bfloat16)
+    n, h, w, c = y.shape
+    stat = torch.empty((n, 2, c), device=y.device, dtype=torch.float32)
+    call("fv_in_stats", y.data_ptr(), stat.data_ptr(), n, h, w, c, float(eps), _stream(), meta=_bytes(y))
+    return stat
+
+
+def in_act_fwd(y, stat, gamma, beta, act: int) -> torch.Tensor:
+    n, h, w, c = y.shape
+    out = torch.empty_like(y)
+    call("fv_in_act_fwd", y.data_ptr(), stat.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), n, h, w, c, act, _stream(),
+         meta=_bytes(y, out))
+    return out
+
+
+def in_bwd(y, g, stat, gamma, beta, act: int):
+    """-> (dy NHWC bf16, dgamma [C], dbeta [C])."""
+    _chk(g, "g", torch.bfloat16)
+    n, h, w, c = y.shape
+    sums = torch.empty((n, 2, c), device=y.device, dtype=torch.float32)
+    call("fv_in_bwd_sums", y.data_ptr(), g.data_ptr(), stat.data_ptr(), gamma.data_ptr(), beta.data_ptr(), sums.data_ptr(), n, h, w, c, act,
+         _stream(), meta=_bytes(y, g))
+    dy = torch.empty_like(y)
+    call("fv_in_bwd_apply", y.data_ptr(), g.data_ptr(), stat.data_ptr(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), dy.data_ptr(), n, h,
+         w, c, act, _stream(), meta=_bytes(y, g, dy))
+    tot = sums.sum(dim=0)                      # a [N, 2, C] -> [2, C] sum: torch's reduction (deterministic for a fixed shape)
+    return dy, tot[1].contiguous(), tot[0].contiguous()
+
+
 # ------------------------------------------------------------------------------------------------ VAE bottleneck + losses
 def reparam_kl_fwd(mu: torch.Tensor, logstd: torch.Tensor, eps: Optional[torch.Tensor], want_z: bool = True,
                    want_kl: bool = True):

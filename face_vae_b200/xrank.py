@@ -44,6 +44,31 @@ class StatExchange:
                   torch.cuda.current_stream().cuda_stream)
         return stat
 
+    def stats_finalize_fwd(self, y, count, gamma, beta, running_mean, running_var, momentum, eps):
+        """Statistics of y, exchange and finalize in ONE launch (the reduction's last block does the exchange) -> stat [4, C]."""
+        from . import ops
+        c = y.shape[-1]
+        sums = torch.empty((2 * c,), device=y.device, dtype=torch.float32)
+        stat = torch.empty((4, c), device=y.device, dtype=torch.float32)
+        _lib.call("fv_bn_stats_xrank", y.data_ptr(), ops._dt(y), sums.data_ptr(), y.numel() // c, c, ops._red_ws(), self.peer_ptrs_dev, self.rank,
+                  self.world, self.epoch.data_ptr(), float(count), gamma.data_ptr(), beta.data_ptr(),
+                  None if running_mean is None else running_mean.data_ptr(), None if running_var is None else running_var.data_ptr(), momentum, eps,
+                  stat.data_ptr(), torch.cuda.current_stream().cuda_stream, meta=ops._bytes(y))
+        return stat
+
+    def reduce_finalize_bwd(self, y, g, stat, mode, act, g_nchw, count):
+        """Backward sums of a norm + act layer, exchange and finalize in ONE launch -> (dgamma, dbeta, coef [2, C])."""
+        from . import ops
+        n, h, w, c = y.shape
+        sums = torch.empty((2 * c,), device=y.device, dtype=torch.float32)
+        dgamma = torch.empty((c,), device=y.device, dtype=torch.float32)
+        dbeta = torch.empty((c,), device=y.device, dtype=torch.float32)
+        coef = torch.empty((2, c), device=y.device, dtype=torch.float32)
+        _lib.call("fv_bn_act_bwd_reduce_xrank", y.data_ptr(), ops._dt(y), g.data_ptr(), ops._dt(g), int(g_nchw), stat.data_ptr(), sums.data_ptr(), n, h, w, c,
+                  mode, act, ops._red_ws(), self.peer_ptrs_dev, self.rank, self.world, self.epoch.data_ptr(), float(count), coef.data_ptr(),
+                  dgamma.data_ptr(), dbeta.data_ptr(), torch.cuda.current_stream().cuda_stream, meta=ops._bytes(y, g))
+        return dgamma, dbeta, coef
+
     def finalize_bwd(self, sums_local, count, c):
         dgamma = torch.empty((c,), device=sums_local.device, dtype=torch.float32)
         dbeta = torch.empty((c,), device=sums_local.device, dtype=torch.float32)

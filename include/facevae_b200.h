@@ -191,6 +191,17 @@ int fv_bn_act_bwd_apply_fin(const void* y, int y_dtype, const void* g, int g_dty
                             double count, float* dgamma, float* dbeta, const void* add, void* dy, int N, int H, int W, int C, int mode,
                             int act, void* stream);
 
+/* ---- nn.InstanceNorm2d(C, affine=True) + ReLU / LeakyReLU (modules.py:21,27,29: the Discriminator's blocks, models.py:1120-1127) on
+ *      NHWC bf16: statistics per (image, channel) over H*W, biased variance, no running statistics.
+ *      stat [N][2][C] = mean | invstd;  sums [N][2][C] = sum dz | sum dz*xhat per image (dgamma / dbeta are their sums over N). */
+int fv_in_stats(const void* y, float* stat, int N, int H, int W, int C, float eps, void* stream);
+int fv_in_act_fwd(const void* y, const float* stat, const float* gamma, const float* beta, void* out, int N, int H, int W, int C, int act,
+                  void* stream);
+int fv_in_bwd_sums(const void* y, const void* g, const float* stat, const float* gamma, const float* beta, float* sums, int N, int H, int W,
+                   int C, int act, void* stream);
+int fv_in_bwd_apply(const void* y, const void* g, const float* stat, const float* sums, const float* gamma, const float* beta, void* dy,
+                    int N, int H, int W, int C, int act, void* stream);
+
 /* ---- first encoder layer: SameBlock2D(C <= 4 -> 32) on raw NCHW fp32 frames (modules.py:97-108 via models.py:749) ----
  * 1x1 conv + training-mode batch norm + ReLU is a per-pixel affine map whose statistics follow from the input moments.
  * sums are double: forward [C + C*C] = sum x_c | sum x_c x_d; backward [Co + Co*C] = sum dz | sum dz x_c (written;
@@ -214,6 +225,15 @@ long long fv_xrank_buffer_floats(void);
 int fv_bn_finalize_xrank(const float* sums_local, void* peer_bufs_dev, int rank, int world, void* epoch_ctr, int mode, double count,
                          const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                          float* out, float* dgamma, float* dbeta, int accumulate, int C, void* stream);
+/* fv_bn_stats / fv_bn_act_bwd_reduce with the exchange and the finalize step run by the LAST block of the reduction itself (one
+ * launch instead of two per batch-norm layer and pass on the data-parallel critical path).  `sums` still receives the local sums;
+ * forward: stat[4][C] (+ running statistics); backward: coef[2][C], dgamma / dbeta (from the local sums, may be NULL). */
+int fv_bn_stats_xrank(const void* y, int dtype, float* sums, long long P, int C, void* red_ws, void* peer_bufs_dev, int rank, int world,
+                      void* epoch_ctr, double count, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      float momentum, float eps, float* stat, void* stream);
+int fv_bn_act_bwd_reduce_xrank(const void* y, int y_dtype, const void* g, int g_dtype, int g_nchw, const float* stat, float* sums, int N, int H,
+                               int W, int C, int mode, int act, void* red_ws, void* peer_bufs_dev, int rank, int world, void* epoch_ctr,
+                               double count, float* coef, float* dgamma, float* dbeta, void* stream);
 /* The same exchange with all `world` ranks emulated as the blocks of ONE cooperative launch on one GPU (block r = rank r):
  * every per-rank array is the concatenation of the ranks' arrays; peer_bufs_dev points at `world` local buffers.  For the
  * single-GPU parity test of the protocol (waiting kernels must be co-resident, which separate launches do not guarantee).

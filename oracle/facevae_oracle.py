@@ -91,14 +91,50 @@ class BNState:
         self.updates: Dict[str, torch.Tensor] = {}
 
 
+def spectral_norm_weight(w, u, v, training=True, eps=1e-12, n_power_iterations=1):
+    """torch.nn.utils.spectral_norm as ``_ConvBlock`` applies it with ``use_weight_norm=True`` (reference modules.py:11,14,32;
+    torch/nn/utils/spectral_norm.py): in training mode one power iteration v <- normalize(W^T u), u <- normalize(W v) on the
+    [Co, Ci*k*k] matrix without gradient, then W / (u^T W v).  Returns (w_sn, u_new, v_new)."""
+    mat = w.reshape(w.shape[0], -1)
+    if training:
+        with torch.no_grad():
+            for _ in range(n_power_iterations):
+                v = F.normalize(torch.mv(mat.t(), u), dim=0, eps=eps)
+                u = F.normalize(torch.mv(mat, v), dim=0, eps=eps)
+    sigma = torch.dot(u, torch.mv(mat, v))
+    return w / sigma, u, v
+
+
+def instance_norm(x, gamma, beta, eps=BN_EPS):
+    """nn.InstanceNorm2d(C, affine=True) (reference modules.py:21): per-(sample, channel) statistics over (H, W), biased variance."""
+    mean = x.mean(dim=(2, 3), keepdim=True)
+    var = ((x - mean) ** 2).mean(dim=(2, 3), keepdim=True)
+    return (x - mean) / torch.sqrt(var + eps) * gamma[None, :, None, None] + beta[None, :, None, None]
+
+
 def conv_block(pattern, x, p, prefix, kernel_size, stride, padding, training=True,
                nonlinearity="relu", bn_state: Optional[BNState] = None):
-    """_ConvBlock.forward (reference modules.py:8-42): layers applied in ``pattern`` order."""
+    """_ConvBlock.forward (reference modules.py:8-42): layers applied in ``pattern`` order.  The variant is read off the
+    parameter names, as a state_dict of the reference block carries them: ``weight_orig`` / ``weight_u`` / ``weight_v`` =
+    spectral norm (use_weight_norm=True); a norm layer with running statistics = SyncBatchNorm, with affine parameters only =
+    InstanceNorm2d, without parameters = Identity (activation_type "none")."""
     for idx, ch in enumerate(pattern):
         key = f"{prefix}layers.{idx}."
         if ch == "C":
-            x = conv2d(x, p[key + "weight"], p[key + "bias"], stride, padding)
+            if key + "weight_orig" in p:
+                w, u, v = spectral_norm_weight(p[key + "weight_orig"], p[key + "weight_u"], p[key + "weight_v"], training)
+                if bn_state is not None and training:
+                    bn_state.updates[key + "weight_u"] = u
+                    bn_state.updates[key + "weight_v"] = v
+            else:
+                w = p[key + "weight"]
+            x = conv2d(x, w, p[key + "bias"], stride, padding)
         elif ch == "N":
+            if key + "weight" not in p:
+                continue
+            if key + "running_mean" not in p:
+                x = instance_norm(x, p[key + "weight"], p[key + "bias"])
+                continue
             if training:
                 x, rm, rv = batch_norm_train(x, p[key + "weight"], p[key + "bias"],
                                              p.get(key + "running_mean"), p.get(key + "running_var"))

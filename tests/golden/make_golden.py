@@ -297,6 +297,58 @@ def golden_losses(path):
     print(path, {k: float(v) for k, v in store.items() if np.ndim(v) == 0})
 
 
+def golden_f2(path):
+    """the Generator's / Discriminator's block variants -- spectral norm (use_weight_norm=True), instance norm,
+    3x3 stride 2, the un-normalised CN block -- from the unmodified reference ConvBlock2D / ResBlock2D / UpBlock2D."""
+    store = {}
+    n, hw = 2, 8
+
+    def run(tag, blk, ci):
+        blk.train()
+        sd = blk.state_dict()
+        for k in list(sd):
+            if k.endswith("num_batches_tracked"):
+                continue
+            seed = detgen.name_seed(tag + "." + k)
+            shape = tuple(sd[k].shape)
+            if k.endswith("running_mean"):
+                v = np.zeros(shape, np.float32)
+            elif k.endswith("running_var"):
+                v = np.ones(shape, np.float32)
+            elif k.endswith("weight_u") or k.endswith("weight_v"):
+                v = detgen.det_normal(shape, seed)
+                v = v / np.sqrt((v * v).sum())
+            elif len(shape) == 4:
+                b = 1.0 / np.sqrt(shape[1] * shape[2] * shape[3])
+                v = detgen.det_uniform(shape, seed, -b, b)
+            elif k.endswith("weight"):
+                v = detgen.det_uniform(shape, seed, 0.5, 1.5)
+            else:
+                v = detgen.det_uniform(shape, seed, -0.2, 0.2)
+            sd[k] = torch.from_numpy(v.astype(np.float32))
+        blk.load_state_dict(sd)
+        x = torch.from_numpy(detgen.det_uniform((n, ci, hw, hw), detgen.name_seed(tag + ".x"), -1.0, 1.0)).requires_grad_(True)
+        y = blk(x)
+        g = torch.from_numpy(detgen.det_uniform(tuple(y.shape), detgen.name_seed(tag + ".g"), -1.0, 1.0))
+        (y * g).sum().backward()
+        put(store, f"{tag}/y", y, full_below=1 << 20)
+        put(store, f"{tag}/dx", x.grad, full_below=1 << 20)
+        for k, v in blk.named_parameters():
+            put(store, f"{tag}/grad/{k}", v.grad)
+        for k, v in blk.named_buffers():
+            if not k.endswith("num_batches_tracked"):
+                put(store, f"{tag}/buf/{k}", v, full_below=1 << 20)
+
+    run("sn_in_s2", ref_modules.ConvBlock2D("CNA", 32, 64, 3, 2, 1, True, "instance", "leakyrelu"), 32)     # Discriminator down block
+    run("sn_in_s1", ref_modules.ConvBlock2D("CNA", 64, 64, 3, 1, 1, True, "instance", "leakyrelu"), 64)
+    run("sn_cn_none", ref_modules.ConvBlock2D("CN", 64, 1, 3, 1, 1, True, activation_type="none"), 64)      # Discriminator head
+    run("sn_bn_leaky", ref_modules.ConvBlock2D("CNA", 32, 64, 3, 1, 1, True, nonlinearity_type="leakyrelu"), 32)   # Generator.in_conv
+    run("sn_res", ref_modules.ResBlock2D(32, True), 32)
+    run("sn_up", ref_modules.UpBlock2D(32, 16, True), 32)
+    np.savez_compressed(path, **store)
+    print(path, len(store), "arrays")
+
+
 def golden_elr(path):
     """Conv2dELR (4x4 stride 2 + demod + LeakyReLU, and a plain 3x3), flatten_vae6, LinearELR and the
     bilinear pre-scale -- outputs of the unmodified reference classes / the reference's own F.interpolate call."""
@@ -357,6 +409,7 @@ if __name__ == "__main__":
     golden_losses(os.path.join(HERE, "losses.npz"))
     golden_blocks(os.path.join(HERE, "blocks.npz"))
     golden_elr(os.path.join(HERE, "elr.npz"))
+    golden_f2(os.path.join(HERE, "f2.npz"))
     golden_anchor(4, 64, 0, os.path.join(HERE, "anchor_n4_64.npz"))     # BASELINE.json configs[0]
     golden_anchor(2, 64, 1, os.path.join(HERE, "anchor_n2_64_b1.npz"))
     if "--large" in sys.argv:       # minutes of CPU time: BASELINE.json configs[1] and the configs[3] architecture at 512x512

@@ -30,6 +30,10 @@ def _ref_up(x, w, b):
     (5, 4, 4, 32, 16),         # tiles spanning several images, masked tail
     (2, 8, 8, 512, 512),       # 512-deep variant: more than 256 output channels (chunks)
     (1, 6, 256, 16, 32),       # two tiles per row
+    (8, 64, 128, 64, 32),      # window schedule (fv_conv_win.cu): several tiles per CTA, slab ring wraps around
+    (3, 5, 256, 32, 64),       # window schedule: column changes inside a CTA's run, 64 output channels (4 x 64 TMEM columns x 2)
+    (2, 7, 128, 16, 16),       # window schedule: 32-byte slab rows
+    (37, 4, 128, 64, 32),      # window schedule: runs that start on the last row of a column
 ])
 def test_upsample_conv_forward_backward(ops, n, h, w, ci, co):
     from face_vae_b200.ops import pad_channels
@@ -63,7 +67,8 @@ def test_upsample_conv_forward_backward(ops, n, h, w, ci, co):
     assert err <= 2e-3 * scale + 1e-5, (err, scale)
 
 
-@pytest.mark.parametrize("n,h,w,ci,co", [(2, 16, 16, 256, 256), (2, 16, 128, 64, 32), (3, 8, 8, 64, 128), (2, 4, 4, 128, 512)])
+@pytest.mark.parametrize("n,h,w,ci,co", [(2, 16, 16, 256, 256), (2, 16, 128, 64, 32), (3, 8, 8, 64, 128), (2, 4, 4, 128, 512), (9, 33, 128, 64, 32),
+                                         (2, 9, 256, 32, 64), (2, 6, 128, 16, 16)])
 def test_upsample_conv_fused_statistics(ops, n, h, w, ci, co):
     """fv_conv2d_x2 with the batch-norm sums of y from the epilogue (or the separate pass, per the library's predicate)."""
     from face_vae_b200.ops import pad_channels
