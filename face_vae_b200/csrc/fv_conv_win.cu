@@ -73,7 +73,8 @@ struct WinTapC {
     static __host__ __device__ __forceinline__ constexpr int region(int i) { return KIND == 1 ? (i >> 2) : 0; }
 };
 
-template <int NM, int KIND>
+// KS = K steps of 16 channels per table entry (Ci / 16), compile time as well: the issue loop is straight-line code.
+template <int NM, int KIND, int KS>
 __global__ void __launch_bounds__(kWinThreads, 1)
 conv_win_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ WinParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -161,7 +162,16 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const uint32_t w_step = (uint32_t)p.w_slice_stride >> 4;
             const uint32_t a_shift = (uint32_t)p.arow >> 4;
             const uint32_t khalf16 = (uint32_t)p.brow >> 4;            // s2: the b = 1 half of a slab row starts C channels (= one filter row) in
-            const int ksteps = p.tap[0].ksteps;
+            // everything that does not change from tile to tile is formed once: per entry the filter descriptor and the offset of
+            // its activation view inside a slab; per tile only the four slab addresses (ring rotation) and the accumulator base
+            uint32_t wb[16], aoff[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                wb[i] = w_base + (uint32_t)i * w_step;
+                aoff[i] = (uint32_t)WinTapC<KIND>::shift(i) * a_shift + (uint32_t)WinTapC<KIND>::khalf(i) * khalf16;
+            }
+            const uint32_t nmma = (uint32_t)p.Nmma, ring = (uint32_t)p.ring, slab_stride16 = (uint32_t)p.slab_stride >> 4;
+            const uint32_t slab0 = (smem_base >> 4) | LBO_LO;
             mbar_wait(wbar, 0);
             uint32_t first = 0, wait_slot = 0, wait_ph = 0, tcount = 0;
             int h = t0 % p.H;
@@ -176,24 +186,24 @@ conv_win_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     if (++wait_slot == (uint32_t)p.ring) { wait_slot = 0; wait_ph ^= 1; }
                 }
                 tc_fence_after();
-                const uint32_t d_base = tmem_base + acc * (uint32_t)(p.nacc * p.Nmma);
+                const uint32_t d_base = tmem_base + acc * (uint32_t)p.nacc * nmma;
                 uint32_t sa[4];                                    // descriptor low words of the window's slabs (J <= 4)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint32_t slot = first + j;
-                    if (slot >= (uint32_t)p.ring) slot -= (uint32_t)p.ring;
-                    sa[j] = ((smem_base + slot * (uint32_t)p.slab_stride) >> 4) | LBO_LO;
+                    if (slot >= ring) slot -= ring;
+                    sa[j] = slab0 + slot * slab_stride16;
                 }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     using T = WinTapC<KIND>;
-                    const uint32_t a_lo = sa[T::slab(i)] + (uint32_t)T::shift(i) * a_shift + (uint32_t)T::khalf(i) * khalf16;
-                    const uint32_t b_lo = w_base + (uint32_t)i * w_step;
-                    const uint32_t d = d_base + (uint32_t)T::region(i) * (uint32_t)p.Nmma;
+                    const uint32_t a_lo = sa[T::slab(i)] + aoff[i];
+                    const uint32_t d = d_base + (uint32_t)T::region(i) * nmma;
                     // the first entry of every accumulator region overwrites it: x2 -> the first tap of each phase, s2 -> entry 0
                     const bool first_of_region = KIND == 1 ? (i & 3) == 0 : i == 0;
-                    for (int j = 0; j < ksteps; ++j)
-                        if (leader) tc_mma_f16_lohi2(d, a_lo + 2 * j, a_hi, b_lo + 2 * j, b_hi, idesc, (first_of_region && j == 0) ? 0u : 1u);
+#pragma unroll
+                    for (int j = 0; j < KS; ++j)
+                        if (leader) tc_mma_f16_lohi2(d, a_lo + 2 * j, a_hi, wb[i] + 2 * j, b_hi, idesc, (first_of_region && j == 0) ? 0u : 1u);
                 }
                 if (leader) tc_commit(&tfull[acc]);
                 // release the slabs the next tile will not read: `adv` when it continues this column, the whole window otherwise
@@ -396,14 +406,20 @@ int conv_win_try(int kind, const void* x, const void* w, const float* bias, void
         uint32_t box[2] = {(uint32_t)Ci, (uint32_t)Co_pad};
         if (int e = encode_tmap_bf16(&tmW, w, 2, dims, str, box, p.brow)) return e;
     }
-#define FV_WIN_LAUNCH(NM_, KIND_)                                                                                                    \
+#define FV_WIN_LAUNCH3(NM_, KIND_, KS_)                                                                                              \
     do {                                                                                                                             \
         static bool attr_set = false;                                                                                                \
         if (!attr_set) {                                                                                                             \
-            FV_CUDA(cudaFuncSetAttribute(conv_win_kernel<NM_, KIND_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
+            FV_CUDA(cudaFuncSetAttribute(conv_win_kernel<NM_, KIND_, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
             attr_set = true;                                                                                                         \
         }                                                                                                                            \
-        conv_win_kernel<NM_, KIND_><<<grid, kWinThreads, smem, stream>>>(tmX, tmW, p);                                               \
+        conv_win_kernel<NM_, KIND_, KS_><<<grid, kWinThreads, smem, stream>>>(tmX, tmW, p);                                          \
+    } while (0)
+#define FV_WIN_LAUNCH(NM_, KIND_)                                                                                                    \
+    do {                                                                                                                             \
+        if (Ci == 64) FV_WIN_LAUNCH3(NM_, KIND_, 4);                                                                                 \
+        else if (Ci == 32) FV_WIN_LAUNCH3(NM_, KIND_, 2);                                                                            \
+        else FV_WIN_LAUNCH3(NM_, KIND_, 1);                                                                                          \
     } while (0)
     if (kind == 1 && p.Nmma == 16) FV_WIN_LAUNCH(1, 1);
     else if (kind == 1 && p.Nmma == 32) FV_WIN_LAUNCH(2, 1);
@@ -413,6 +429,7 @@ int conv_win_try(int kind, const void* x, const void* w, const float* bias, void
         FV_WIN_LAUNCH(0, 2);
     }
 #undef FV_WIN_LAUNCH
+#undef FV_WIN_LAUNCH3
     FV_LAUNCH_CHECK("conv_win_kernel");
     return FV_OK;
 }
