@@ -183,6 +183,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 int conv2d_wgrad_ring_splits(int N, int H, int W, int Ci, int Co_pad, int R, int S);     // 0 when not eligible
 int conv2d_wgrad_ring_try(const void* x, const void* dy, float* part, long long split_stride, int N, int H, int W, int Ci, int Co_pad, int R,
                           int S, int pad, cudaStream_t stream);
+int conv2d_wgrad_ring_x2_splits(int N, int H, int W, int Ci, int Co_pad);                 // 0 when not eligible
+int conv2d_wgrad_ring_x2_try(const void* x, const void* dy, float* part, long long split_stride, int N, int H, int W, int Ci, int Co_pad,
+                             cudaStream_t stream);
 
 static int pick_pixel_block(int H, int W, int& pw, int& ph, int& pn) {
     if (W >= 64) {
@@ -244,6 +247,10 @@ static int wgrad_splits(int kind, int N, int H, int W, int Ci, int Co_pad, int R
     if (check_channels(Ci, Co_pad)) return 0;
     if (kind == CONV_SAME) {
         const int rs = conv2d_wgrad_ring_splits(N, H, W, Ci, Co_pad, R, S);
+        if (rs > 0) return rs;
+    }
+    if (kind == CONV_X2) {
+        const int rs = conv2d_wgrad_ring_x2_splits(N, H, W, Ci, Co_pad);
         if (rs > 0) return rs;
     }
     int splits = 0;
@@ -339,6 +346,10 @@ static int wgrad_any(int kind, const void* x, const void* dy, float* part, int s
     const long long split_stride = (long long)nph * Co_pad * taps * Ci;
     if (kind == CONV_SAME) {
         const int rr = conv2d_wgrad_ring_try(x, dy, part, split_stride, N, H, W, Ci, Co_pad, R, S, pad, (cudaStream_t)stream);
+        if (rr >= 0) return rr;
+    }
+    if (kind == CONV_X2) {
+        const int rr = conv2d_wgrad_ring_x2_try(x, dy, part, split_stride, N, H, W, Ci, Co_pad, (cudaStream_t)stream);
         if (rr >= 0) return rr;
     }
     // output-channel counts beyond one UMMA N (256) are handled in chunks of <= 256 channels of dY

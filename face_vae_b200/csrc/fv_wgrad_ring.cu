@@ -31,6 +31,10 @@ struct WRingParams {
     // D[(tap t, ci), co] -> dw[cta * split_stride + ci + t * st + co * sb]: st = total input channels, sb = taps * st (dw already points at this
     // launch's channel chunk when the wide operand is walked in chunks of 64)
     long long st, sb;
+    // x2 mode (weight gradient of the up-sampling convolution, x2_co > 0): dY is the parity-x2_a rows of the fine gradient seen as
+    // [N][H][W][(b, co)] and only the filter rows r_lo <= r < r_hi are accumulated; the epilogue scatters D[(r, s), (b, co)] into
+    // the phase layout [4][x2_co][4][Ci] of fv_conv2d_wgrad_x2 (phase (a, b), tap (u, v) = (r - a, s - b))
+    int r_lo, r_hi, x2_a, x2_co;
     long long* trace;
 };
 
@@ -171,7 +175,7 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                         const uint32_t d_col = tmem_base + (uint32_t)((r * TPR + part) * p.Co_pad);
 #pragma unroll
                         for (int k4 = 0; k4 < kPX / 16; ++k4)
-                            if (leader && (uint32_t)((r * TPR + part) & 1) == issuer)
+                            if (leader && (uint32_t)((r * TPR + part) & 1) == issuer && r >= p.r_lo && r < p.r_hi)
                                 tc_mma_f16_lohi2(d_col, a_row + (uint32_t)(part * CPT * (AROW >> 4)) + k4 * a_kstep, a_hi, b_lo + k4 * b_kstep,
                                                  b_hi, idesc, accumulate | (uint32_t)(k4 > 0));
                     }
@@ -212,6 +216,23 @@ conv_wgrad_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 const int s = part * p.cpt + chunk;
                 const bool valid = s < p.S;
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + (uint32_t)mt * p.Co_pad;
+                if (r < p.r_lo || r >= p.r_hi) continue;
+                if (p.x2_co) {
+                    const int u = r - p.x2_a;
+                    float* dst = p.dw + (size_t)blockIdx.x * p.split_stride + ci;
+                    for (int c0 = 0; c0 < p.Co_pad; c0 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(taddr + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int b = (c0 + i) / p.x2_co, co = (c0 + i) - b * p.x2_co, vv = s - b;
+                            if (valid && vv >= 0 && vv < 2)
+                                dst[((size_t)((p.x2_a * 2 + b) * p.x2_co + co) * 4 + (u * 2 + vv)) * CW] = __uint_as_float(v[i]);
+                        }
+                    }
+                    continue;
+                }
                 const int t = r * p.S + s;
                 float* dst = p.dw + (size_t)blockIdx.x * p.split_stride + ci + (size_t)t * p.st;
                 for (int c0 = 0; c0 < p.Co_pad; c0 += 16) {
@@ -264,8 +285,13 @@ static bool wring_shape_ok(int W, int Ci, int Co_pad, int R, int S) {
     return smem <= 225 * 1024 && !(env && atoi(env) == 0);
 }
 
+struct WRingX2 {            // x2 mode of conv2d_wgrad_ring_ex (see WRingParams)
+    int a, co;
+    long long dy_row, dy_img;   // element strides of the dY view between rows / images
+};
+
 int conv2d_wgrad_ring_ex(const void* x, int x_cs, const void* dy, int dy_cs, float* dw_acc, long long split_stride, long long st, long long sb, int N,
-                         int H, int W, int Ci, int Co_pad, int R, int S, int pad, cudaStream_t stream) {
+                         int H, int W, int Ci, int Co_pad, int R, int S, int pad, cudaStream_t stream, const WRingX2* x2 = nullptr) {
     if (!wring_shape_ok(W, Ci, Co_pad, R, S)) return -1;
     const int kPX = (W % 128 == 0) ? 128 : 64;
     WRingParams p{};
@@ -294,6 +320,8 @@ int conv2d_wgrad_ring_ex(const void* x, int x_cs, const void* dy, int dy_cs, flo
     p.dw = dw_acc;
     p.split_stride = split_stride;
     p.st = st; p.sb = sb;
+    p.r_lo = 0; p.r_hi = R;
+    if (x2) { p.r_lo = x2->a; p.r_hi = x2->a + 2; p.x2_a = x2->a; p.x2_co = x2->co; }
     p.trace = trace_ptr();
     const int sms = num_sms();
     p.blocks_per_cta = (p.num_blocks + sms - 1) / sms;
@@ -309,6 +337,7 @@ int conv2d_wgrad_ring_ex(const void* x, int x_cs, const void* dy, int dy_cs, flo
     {
         uint64_t dims[4] = {(uint64_t)Co_pad, (uint64_t)W, (uint64_t)H, (uint64_t)N};
         uint64_t str[3] = {(uint64_t)dy_cs * 2, (uint64_t)W * dy_cs * 2, (uint64_t)H * W * dy_cs * 2};
+        if (x2) { str[1] = (uint64_t)x2->dy_row * 2; str[2] = (uint64_t)x2->dy_img * 2; }
         uint32_t box[4] = {(uint32_t)Co_pad, (uint32_t)kPX, 1, 1};
         if (int e = encode_tmap_bf16(&tmDY, dy, 4, dims, str, box, brow)) return e;
     }
@@ -329,6 +358,36 @@ static int wring_mode(int W, int Ci, int Co_pad, int R, int S) {
     if (Ci <= 64 && Co_pad % 64 == 0 && Co_pad <= 256) return wring_shape_ok(W, Ci, 64, R, S) ? 2 : 0;
     if (Co_pad <= 64 && Ci % 64 == 0 && Ci <= 256) return wring_shape_ok(W, 64, Co_pad, R, S) ? 3 : 0;
     return 0;
+}
+
+// ---- x2: weight gradient of the nearest-2x up-sampling 3x3 convolution on the coarse grid ---------------------------------------
+// With y = 2h + a, x = 2w + b the fine pixel (y + kh - 1, x + kw - 1) of the up-sampled input is the coarse pixel
+// (h + floor((a + kh - 1) / 2), w + floor((b + kw - 1) / 2)): per row parity a the phase-filter gradients are entries of an ordinary
+// 3x3 "same" weight gradient between the coarse input and the parity-a rows of dY read as [N][H][W][(b, co)] (a plain strided NHWC
+// view: row stride 4 W Co, pixel stride 2 Co).  Two launches (a = 0, 1) of the ring kernel with N = 2 Co columns, filter rows
+// {a, a + 1}; the epilogue keeps column shift s for parity b when v = s - b is 0 or 1.
+static bool wring_x2_ok(int W, int Ci, int Co_pad) {
+    const char* env = getenv("FV_WGRAD_RING_X2");
+    if (env && atoi(env) == 0) return false;
+    if (Ci != 16 && Ci != 32 && Ci != 64) return false;
+    if (Co_pad != 16 && Co_pad != 32) return false;
+    return wring_shape_ok(W, Ci, 2 * Co_pad, 3, 3);
+}
+int conv2d_wgrad_ring_x2_splits(int N, int H, int W, int Ci, int Co_pad) {
+    if (!wring_x2_ok(W, Ci, Co_pad)) return 0;
+    return wring_grid(N, H, W, (W % 128 == 0) ? 128 : 64);
+}
+// part[cta][4][Co_pad][4][Ci]; -1 when not eligible
+int conv2d_wgrad_ring_x2_try(const void* x, const void* dy, float* part, long long split_stride, int N, int H, int W, int Ci, int Co_pad,
+                             cudaStream_t stream) {
+    if (!wring_x2_ok(W, Ci, Co_pad)) return -1;
+    for (int a = 0; a < 2; ++a) {
+        WRingX2 x2{a, Co_pad, 4LL * W * Co_pad, 4LL * H * W * Co_pad};
+        const int e = conv2d_wgrad_ring_ex(x, Ci, static_cast<const char*>(dy) + (size_t)a * 2 * W * Co_pad * 2, 2 * Co_pad, part, split_stride, 0, 0, N,
+                                           H, W, Ci, 2 * Co_pad, 3, 3, 1, stream, &x2);
+        if (e) return e < 0 ? fail(FV_ERR_INTERNAL, "fv_conv2d_wgrad_x2: ring schedule refused a shape it had accepted") : e;
+    }
+    return FV_OK;
 }
 
 // number of partial slabs (= CTAs) the ring schedule writes for this shape; 0 when it does not take the shape

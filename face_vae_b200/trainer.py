@@ -116,7 +116,12 @@ class VAETrainer:
                 if self.use_cuda_graph:
                     kw["capturable"] = True
             self.optimizer = torch.optim.Adam(params, lr=lr, betas=(0.5, 0.999), **kw)
+        bucket_mb = float(os.environ.get("FACEVAE_BUCKET_MB", bucket_mb))
         self.reducer = fdist.GradientReducer(params, bucket_mb) if world > 1 else None
+        if os.environ.get("FACEVAE_DIAG_SKIP_GRAD_REDUCE") == "1":      # timing diagnostic only: ranks diverge
+            if self.reducer is not None:
+                self.reducer.remove()
+            self.reducer = None
         self._graph = None
         self._graph_key = None
         self._cap_stream = None
