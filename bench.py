@@ -36,18 +36,52 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and throttle reasons while the timed region runs: NVML in-process (a few microseconds per query, no child
+    process competing for the driver), `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_s: float = 0.025):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.period = period_s
+        self.samples = []          # (t, [sm, max_sm, power, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap]) as strings
         self.proc = None
+        self._halt = threading.Event()
+        self.source = "nvml"
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self._visible_index())
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = (nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown, nv.nvmlClocksEventReasonSwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwPowerCap)
+        while not self._halt.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+            except Exception:
+                pw = 0.0
+            self.samples.append((time.perf_counter(), [str(sm), str(mx), f"{pw:.1f}"] + ["Active" if r & b else "Not Active" for b in bits]))
+            self._halt.wait(self.period)
 
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -59,6 +93,7 @@ class ClockSampler(threading.Thread):
             pass
 
     def stop(self):
+        self._halt.set()
         if self.proc is not None:
             self.proc.terminate()
 
@@ -71,7 +106,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in rows for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(rows)}
+                "samples": len(rows), "source": self.source}
 
 
 def run_reference(args):
@@ -293,8 +328,8 @@ def main():
     # set-up outside the timed region: the pinned loss buffer (cudaHostAlloc synchronises the device) and two untimed
     # passes so that the caching allocator already holds the prefetch buffers
     log = AsyncScalarLog(args.steps)
-    prefetch = DevicePrefetcher()
-    for x, e in prefetch.over(host[i % 2] for i in range(3)):
+    prefetch = DevicePrefetcher(depth=4)      # the host may run three batches ahead: rides out scheduling hiccups of a few ms
+    for x, e in prefetch.over(host[i % 2] for i in range(prefetch.depth + 1)):
         trainer.step(x, e)
     barrier()
     t0 = time.perf_counter()
@@ -401,8 +436,10 @@ def main():
         for tname in ("r02_conv_traffic.json", "r01_final_conv_traffic.json"):
             tpath = os.path.join(ROOT, "profiles", tname)
             if os.path.exists(tpath) and B == 32 and S == 256 and not args.deep:
-                t = json.load(open(tpath))
-                roofline["traffic"] = t["bytes_per_launch"]
+                try:
+                    roofline["traffic"] = float(json.load(open(tpath))["bytes_per_launch"])
+                except (KeyError, ValueError, TypeError):
+                    continue
                 roofline["traffic_source"] = f"profiles/{tname} (ncu dram__bytes_read.sum + dram__bytes_write.sum, average per launch)"
                 break
     glue = None

@@ -76,11 +76,12 @@ SIGNATURES = {
     "fv_bn_stats_xrank": [_p, _i, _p, _ll, _i, _p, _p, _i, _i, _p, _d, _p, _p, _p, _p, _f, _f, _p, _p],
     "fv_bn_act_bwd_reduce_xrank": [_p, _i, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _d, _p, _p, _p, _p],
     "fv_bn_finalize_xrank_emulate": [_p, _p, _i, _p, _i, _d, _p, _p, _p, _p, _f, _f, _p, _p, _p, _i, _i, _p],
+    "fv_grad_allreduce": [_p, _p, _i, _i, _ll, _p, _p, _f, _p],
     "fv_debug_mma_rate": [_i, _i, _i, _i, _i, _i, _p, _p],
     "fv_debug_trace_set": [_p],
 }
 _STR = ("fv_last_error", "fv_version")
-_LL = ("fv_xrank_buffer_floats", "fv_reduce_ws_bytes")
+_LL = ("fv_xrank_buffer_floats", "fv_reduce_ws_bytes", "fv_grad_allreduce_flag_words")
 # predicates / planning queries: the return value is the answer
 _PLAIN_INT = {"fv_outconv_supported": [_i, _i, _i, _i, _i, _i, _i], "fv_conv2d_fuses_stats": [_i, _i, _i, _i, _i, _i, _i, _i, _i],
               "fv_conv2d_wgrad_splits": [_i, _i, _i, _i, _i, _i, _i, _i],

@@ -51,6 +51,116 @@ __global__ void __launch_bounds__(256, 1) bn_xrank_emulate_kernel(const XrankArg
     xrank_exchange_finalize(a, tot, &epoch_s);
 }
 
+// ---- gradient mean all-reduce over peer memory (reference: DistributedDataParallel's bucketed NCCL all-reduce, logger.py:55) ---
+// The flat gradient buffer of distributed.GradientReducer is a symmetric allocation: every rank can address every rank's copy.
+// ONE kernel per step, two-shot and in place: rank r owns the r-th slice; it PULLS that slice from all ranks over NVLink, adds
+// the R values in rank order (so the result is bitwise identical everywhere and run to run), scales by 1/R and PUSHES the
+// result into the same offsets of all R buffers.  Two flag barriers (64-bit epochs in a small symmetric flag array
+// [2][kXMaxWorld]): "my gradients are complete" before the pull, "my pushes have landed and I no longer read your buffer" after
+// it -- the second one is what allows the next kernel (Adam) to read the buffer and the next backward to overwrite it.
+// NCCL needed ~80 us (one bucket) to ~105 us (2 MB buckets; its CTAs displace the persistent one-CTA-per-SM convolution kernels
+// they are supposed to overlap with) for these 15 MB at 2 GPUs.
+struct GradArArgs {
+    float* const* bufs;                   // [world] peer-mapped flat buffers
+    unsigned long long* const* flags;     // [world] peer-mapped flag arrays [2][kXMaxWorld]
+    int rank, world;
+    long long n4;                         // float4 elements of the buffer
+    unsigned long long* epoch_ctr;
+    unsigned int* ticket;
+    float scale;
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void st_flag_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_flag_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_f4_sys(const float4* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long e, unsigned long long timeout_ns, int rank, int peer,
+                                          const char* what) {
+    unsigned int spins = 0;
+    unsigned long long t0 = 0;
+    while (ld_flag_sys(p) < e) {
+        if ((++spins & 0x3FFu) == 0) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > timeout_ns) {
+                printf("fv: gradient all-reduce timed out after %llu s (rank %d waiting for rank %d, %s, epoch %llu)\n", timeout_ns / 1000000000ULL,
+                       rank, peer, what, e);
+                __trap();
+            }
+            __nanosleep(100);
+        }
+    }
+}
+
+// W: world size known at compile time (0 = run-time loop); U float4 elements per thread and iteration, U * W loads in flight
+template <int W, int U>
+__global__ void __launch_bounds__(256) grad_allreduce_kernel(const GradArArgs a) {
+    const int world = W ? W : a.world;
+    const unsigned long long e = *a.epoch_ctr + 1ULL;
+    unsigned long long* my_flags = a.flags[a.rank];
+    if (blockIdx.x == 0 && threadIdx.x < world && (int)threadIdx.x != a.rank) st_flag_sys(a.flags[threadIdx.x] + a.rank, e);
+    if (threadIdx.x < world && (int)threadIdx.x != a.rank) wait_flag(my_flags + threadIdx.x, e, a.timeout_ns, a.rank, threadIdx.x, "gradients ready");
+    __syncthreads();
+    const long long lo = a.n4 * a.rank / world, hi = a.n4 * (a.rank + 1) / world;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * U) {
+        float4 v[U][W ? W : 1];
+        if (W) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int p = 0; p < (W ? W : 1); ++p)
+                    if (i0 + u * stride < hi) v[u][p] = ld_f4_sys(reinterpret_cast<const float4*>(a.bufs[p]) + i0 + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= hi) break;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (W) {
+#pragma unroll
+                for (int p = 0; p < (W ? W : 1); ++p) { acc.x += v[u][p].x; acc.y += v[u][p].y; acc.z += v[u][p].z; acc.w += v[u][p].w; }
+            } else {
+                for (int p = 0; p < world; ++p) {
+                    const float4 t = ld_f4_sys(reinterpret_cast<const float4*>(a.bufs[p]) + i);
+                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                }
+            }
+            acc.x *= a.scale; acc.y *= a.scale; acc.z *= a.scale; acc.w *= a.scale;
+#pragma unroll
+            for (int p = 0; p < (W ? W : kXMaxWorld); ++p)
+                if (p < world) reinterpret_cast<float4*>(a.bufs[p])[i] = acc;
+        }
+    }
+    // every block: its pushes are ordered before the ticket; the last block tells the peers and waits for theirs
+    __shared__ unsigned int last_s;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last_s = atomicAdd(a.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!last_s) return;
+    __threadfence_system();
+    if (threadIdx.x < world && (int)threadIdx.x != a.rank) {
+        st_flag_sys(a.flags[threadIdx.x] + kXMaxWorld + a.rank, e);
+        wait_flag(my_flags + kXMaxWorld + threadIdx.x, e, a.timeout_ns, a.rank, threadIdx.x, "pushes landed");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *a.ticket = 0u;
+        *a.epoch_ctr = e;
+    }
+}
+
 static unsigned long long xrank_timeout_ns() {
     static unsigned long long cached = 0;
     if (!cached) {
@@ -106,5 +216,34 @@ extern "C" __attribute__((visibility("default"))) int fv_bn_finalize_xrank_emula
                 C, mode, count, gamma, beta, running_mean, running_var, momentum, eps, out, dgamma, dbeta, accumulate, xrank_timeout_ns()};
     void* args[] = {&a};
     FV_CUDA(cudaLaunchCooperativeKernel((const void*)bn_xrank_emulate_kernel, dim3(world), dim3(256), args, 0, (cudaStream_t)stream));
+    return FV_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) long long fv_grad_allreduce_flag_words(void) { return 2 * fv::kXMaxWorld; }
+
+// In-place mean (scale = 1 / world) all-reduce of the symmetric flat gradient buffers: bufs_dev / flags_dev are device arrays of
+// `world` peer-mapped pointers (buffer of n floats, n % 4 == 0, 16-byte aligned; flag array of fv_grad_allreduce_flag_words()
+// zero-initialised 64-bit words), epoch_ctr (u64) and ticket (u32) zero-initialised device words of this rank.
+extern "C" __attribute__((visibility("default"))) int fv_grad_allreduce(void* bufs_dev, void* flags_dev, int rank, int world, long long n, void* epoch_ctr,
+                                                                      void* ticket, float scale, void* stream) {
+    using namespace fv;
+    if (!bufs_dev || !flags_dev || !epoch_ctr || !ticket || n < 4 || n % 4) return fail(FV_ERR_ARG, "fv_grad_allreduce: bad arguments (n=%lld)", n);
+    if (world < 1 || world > kXMaxWorld || rank < 0 || rank >= world) return fail(FV_ERR_ARG, "fv_grad_allreduce: rank %d / world %d", rank, world);
+    GradArArgs a{reinterpret_cast<float* const*>(bufs_dev), reinterpret_cast<unsigned long long* const*>(flags_dev), rank, world, n / 4,
+                 reinterpret_cast<unsigned long long*>(epoch_ctr), reinterpret_cast<unsigned int*>(ticket), scale, xrank_timeout_ns()};
+    const long long slice = (a.n4 + world - 1) / world;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto blocks = [&](int u) {
+        long long b = (slice + 256LL * u - 1) / (256LL * u);
+        const int cap = num_sms();
+        return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+    };
+    switch (world) {
+        case 2: grad_allreduce_kernel<2, 8><<<blocks(8), 256, 0, st>>>(a); break;
+        case 4: grad_allreduce_kernel<4, 4><<<blocks(4), 256, 0, st>>>(a); break;
+        case 8: grad_allreduce_kernel<8, 2><<<blocks(2), 256, 0, st>>>(a); break;
+        default: grad_allreduce_kernel<0, 2><<<blocks(2), 256, 0, st>>>(a); break;
+    }
+    FV_LAUNCH_CHECK("grad_allreduce_kernel");
     return FV_OK;
 }

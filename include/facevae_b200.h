@@ -242,6 +242,17 @@ int fv_bn_finalize_xrank_emulate(const float* sums_local, void* peer_bufs_dev, i
                                  const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
                                  float eps, float* out, float* dgamma, float* dbeta, int accumulate, int C, void* stream);
 
+/* ---- gradient averaging of the data-parallel step (DistributedDataParallel's all-reduce, logger.py:55) over peer memory ----
+ * In-place mean all-reduce of the ranks' flat gradient buffers, ONE kernel: rank r pulls slice r from all ranks over NVLink, adds
+ * the `world` values in rank order (bitwise identical on every rank), multiplies by scale (1 / world) and pushes the result into
+ * all buffers; epoch-flag barriers before the pull and after the push.  bufs_dev / flags_dev: device arrays of `world`
+ * peer-mapped pointers -- buffers of n floats (n % 4 == 0, 16-byte aligned) and flag arrays of fv_grad_allreduce_flag_words()
+ * zero-initialised 64-bit words; epoch_ctr (u64) and ticket (u32): zero-initialised device words owned by this rank.  world = 1
+ * degenerates to the scaling.  A peer that never arrives traps after FACEVAE_XRANK_TIMEOUT_S seconds. */
+long long fv_grad_allreduce_flag_words(void);
+int fv_grad_allreduce(void* bufs_dev, void* flags_dev, int rank, int world, long long n, void* epoch_ctr, void* ticket, float scale,
+                      void* stream);
+
 /* ---- re-parameterisation (models.py:559-561) fused with KLDivergenceLoss (losses.py:385-393) ------------- */
 /* mu/logstd: fp32 rows of Dz values (Dz % 4 == 0, 16-byte aligned), row_stride apart; z[N,Dz] = mu + exp(logstd)*eps (NULL
  * eps => z = mu; NULL z => KL only); kl_part[N][P] (may be NULL), P = fv_reparam_kl_parts(N, Dz): per-block partial sums of

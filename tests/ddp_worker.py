@@ -140,11 +140,41 @@ def scenario_skew(rank, world):
         print(f"ddp skew world={world}: ok")
 
 
+def scenario_gradar(rank, world):
+    """fv_grad_allreduce (peer-memory, one kernel) against NCCL on odd-sized tensors, 20 back-to-back epochs."""
+    sizes = [5, 1023, 4096, 333, 70001, 1 << 20, 7]
+    params = [torch.nn.Parameter(torch.zeros(n, device="cuda")) for n in sizes]
+    red = fd.GradientReducer(params)
+    assert red.peer, "peer-memory gradient all-reduce must be active on an NVLink box"
+    for it in range(20):
+        torch.manual_seed(1000 * it + rank)
+        gs = [torch.randn(n, device="cuda") * (1 + it) for n in sizes]
+        ref = []
+        for g in gs:
+            t = g.clone()
+            dist.all_reduce(t)
+            ref.append(t / world)
+        if rank == it % world:
+            torch.cuda._sleep(int(1e8))
+        for q, g in zip(params, gs):
+            q.grad = g
+        for q in reversed(params):
+            red._hook(q)
+        red.finish()
+        torch.cuda.synchronize()
+        for i, (q, r) in enumerate(zip(params, ref)):
+            assert q.grad.data_ptr() == red._slot[id(q)].data_ptr()
+            assert torch.allclose(q.grad, r, rtol=1e-5, atol=1e-5 * (1 + it)), (it, i, (q.grad - r).abs().max().item())
+            same_on_all_ranks(f"gradar it={it} tensor {i}", q.grad, rank)
+    if rank == 0:
+        print(f"ddp gradar world={world}: ok")
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     fd.init_dist(int(os.environ["LOCAL_RANK"]), world, "nccl")
-    {"block": scenario_block, "model": scenario_model, "skew": scenario_skew}[sys.argv[1]](rank, world)
+    {"block": scenario_block, "model": scenario_model, "skew": scenario_skew, "gradar": scenario_gradar}[sys.argv[1]](rank, world)
     dist.barrier()
     dist.destroy_process_group()
 

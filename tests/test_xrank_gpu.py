@@ -87,3 +87,25 @@ def test_backward_exchange_and_slot_ring(lib, world):
                 torch.testing.assert_close(dgamma[r], local[r, c:])
     torch.cuda.synchronize()
     assert int(W.epoch[0]) == 100 and bool((W.epoch == 100).all())
+
+
+@pytest.mark.parametrize("n", [4, 4 * 1000 + 8, 1 << 20])
+def test_grad_allreduce_single_rank_degenerates_to_scaling(lib, n):
+    """world = 1 through the C-ABI: the pull / sum / push loop and both flag barriers with no peers (the 2-rank behaviour is
+    tests/test_ddp_gpu.py::gradar); five back-to-back epochs exercise the ticket / epoch reset."""
+    torch.manual_seed(n)
+    words = int(lib.load().fv_grad_allreduce_flag_words())
+    buf = torch.randn(n, device="cuda")
+    ref = buf.clone()
+    flags = torch.zeros(words, dtype=torch.int64, device="cuda")
+    bufs = torch.tensor([buf.data_ptr()], dtype=torch.int64, device="cuda")
+    fl = torch.tensor([flags.data_ptr()], dtype=torch.int64, device="cuda")
+    epoch = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for it in range(5):
+        lib.call("fv_grad_allreduce", bufs.data_ptr(), fl.data_ptr(), 0, 1, n, epoch.data_ptr(), ticket.data_ptr(), 0.5,
+                 torch.cuda.current_stream().cuda_stream)
+        ref = ref * 0.5
+    torch.cuda.synchronize()
+    assert torch.equal(buf, ref)
+    assert int(epoch.item()) == 5 and int(ticket.item()) == 0
