@@ -345,6 +345,42 @@ __global__ void wgrad_finish_up_kernel(const float* __restrict__ part, float* __
     }
 }
 
+// few outputs, many slabs (the per-CTA slabs of the tap-folded out_conv weight gradient: 4.7 k floats x 148): the kernel above has
+// one thread walk all slabs of its output serially (24 us of dependent loads).  Here 8 thread groups of a block each add a contiguous
+// eighth of the slabs, in slab order, and the eight partial sums are combined in group order: a fixed grouping, still reproducible.
+__global__ void __launch_bounds__(256) slab_sum_wide_kernel(const float4* __restrict__ part, int slabs, long long stride4, float4* __restrict__ out, long long n4,
+                                                            int accumulate) {
+    __shared__ float4 sm[8][32];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * 32 + lane;
+    const int per = (slabs + 7) / 8, s0 = g * per, s1 = min(slabs, s0 + per);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+        int sp = s0;
+        for (; sp + 4 <= s1; sp += 4) {
+            const float4 a0 = __ldg(part + (sp + 0) * stride4 + i), a1 = __ldg(part + (sp + 1) * stride4 + i), a2 = __ldg(part + (sp + 2) * stride4 + i),
+                         a3 = __ldg(part + (sp + 3) * stride4 + i);
+            v.x += a0.x; v.y += a0.y; v.z += a0.z; v.w += a0.w;
+            v.x += a1.x; v.y += a1.y; v.z += a1.z; v.w += a1.w;
+            v.x += a2.x; v.y += a2.y; v.z += a2.z; v.w += a2.w;
+            v.x += a3.x; v.y += a3.y; v.z += a3.z; v.w += a3.w;
+        }
+        for (; sp < s1; ++sp) {
+            const float4 a = __ldg(part + sp * stride4 + i);
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        }
+    }
+    sm[g][lane] = v;
+    __syncthreads();
+    if (g == 0 && i < n4) {
+        float4 t = sm[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { const float4 a = sm[k][lane]; t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w; }
+        if (accumulate) { const float4 c = out[i]; t.x += c.x; t.y += c.y; t.z += c.z; t.w += c.w; }
+        out[i] = t;
+    }
+}
+
 // ---- filters of the 4x4 stride-2 convolution (Conv2dELR as used by EFE_conv6, reference models_utils.py:632-744) ---------------
 // w fp32 [Co][Ci][4][4] -> wf bf16 [Co_pad][16][Ci_pad] (fv_conv2d_s2 operand) and wx2 bf16 [4 phases][Ci_pad][4 taps][Co_pad]
 // (fv_conv2d_x2 operand of the data gradient: phase (a, b), tap (u, v) <- filter tap (3 - 2u - a, 3 - 2v - b)).
@@ -1357,6 +1393,13 @@ extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const floa
 extern "C" __attribute__((visibility("default"))) int fv_slab_sum(const float* part, int slabs, long long slab_stride, float* out, long long n, int accumulate,
                                                                 void* stream) {
     if (!part || !out || slabs < 1 || n < 1) return fail(FV_ERR_ARG, "fv_slab_sum: bad arguments");
+    const bool aligned = n % 4 == 0 && slab_stride % 4 == 0 && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (aligned && slabs >= 32 && n / 4 <= 32LL * 4 * fv::num_sms()) {         // at most ~4 blocks per SM: the serial walk would leave the GPU idle
+        slab_sum_wide_kernel<<<(unsigned)((n / 4 + 31) / 32), 256, 0, STREAM>>>(reinterpret_cast<const float4*>(part), slabs, slab_stride / 4,
+                                                                               reinterpret_cast<float4*>(out), n / 4, accumulate);
+        FV_LAUNCH_CHECK("slab_sum_wide_kernel");
+        return FV_OK;
+    }
     slab_sum_kernel<<<grid_for(n / 4 + 1), kThreads, 0, STREAM>>>(part, slabs, slab_stride, out, n, accumulate);
     FV_LAUNCH_CHECK("slab_sum_kernel");
     return FV_OK;

@@ -229,7 +229,7 @@ class ConvBNAct(torch.autograd.Function):
         db = None
         if ctx.has_bias:
             # a bias in front of a (training-mode) batch norm has zero gradient analytically; eval mode: real sum
-            db = torch.zeros((co,), device=x.device, dtype=torch.float32) if training else ops.colsum(dy)[:co].clone()
+            db = ops.zero_grad_const(co, x.device) if training else ops.colsum(dy)[:co].clone()
         return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None, None, None
 
 
@@ -358,34 +358,42 @@ class PointwiseBNAct(torch.autograd.Function):
             # the gradient of the global-mean loss -- the same value per-rank SyncBN gradients average to
             inv = 1.0 / _world()
             dw, dgamma, dbeta = dw * inv, dgamma * inv, dbeta * inv
-        db = torch.zeros((wshape[0],), device=x.device, dtype=torch.float32) if has_bias else None
+        db = ops.zero_grad_const(wshape[0], x.device) if has_bias else None
         return None, dw.reshape(wshape), db, dgamma, dbeta, None, None, None, None, None
 
 
 class BNActConv(torch.autograd.Function):
     """Pattern "NAC" of _ConvBlock as used by ResBlock2D (reference modules.py:116-130): norm + act on the block
-    input, then the conv; ``residual`` (NHWC bf16) is added in the conv epilogue (the ``x +`` of modules.py:125)."""
+    input, then the conv; ``residual`` (NHWC bf16) is added in the conv epilogue (the ``x +`` of modules.py:125).
+    ``sums_in``: the batch-norm sums of x when the kernel that produced x already emitted them (replaces the fv_bn_stats pass);
+    ``emit``: also return the sums of the output (for the next norm layer) -- second output, not differentiable."""
 
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, gamma, beta, running_mean, running_var, ksize, act, training, momentum, eps):
+    def forward(ctx, x, residual, weight, bias, gamma, beta, running_mean, running_var, ksize, act, training, momentum, eps,
+                sums_in=None, emit=False):
         co, ci = weight.shape[0], weight.shape[1]
         if _fin_fused(training):
             count = x.shape[0] * x.shape[1] * x.shape[2]
-            a, stat = ops.bn_act_fwd_fin(x, ops.bn_stats(x), count, gamma, beta, running_mean, running_var, MODE_NONE, act,
-                                         torch.bfloat16, False, momentum, eps)
+            a, stat = ops.bn_act_fwd_fin(x, ops.bn_stats(x) if sums_in is None else sums_in, count, gamma, beta, running_mean, running_var,
+                                         MODE_NONE, act, torch.bfloat16, False, momentum, eps)
         else:
-            stat, count = _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps)
+            stat, count = _bn_forward(x, gamma, beta, running_mean, running_var, training, momentum, eps, sums=sums_in if training else None)
             a = ops.bn_act_fwd(x, stat, MODE_NONE, act, torch.bfloat16)
         wf, wd = ops.weight_prep(weight, True, True)
-        y = ops.conv2d(a, wf, bias, co, ksize, residual, OUT_NHWC_BF16, (ci, co))
+        sums_out = None
+        if emit:
+            y, sums_out = ops.conv2d(a, wf, bias, co, ksize, residual, OUT_NHWC_BF16, (ci, co), want_stats=True)
+            ctx.mark_non_differentiable(sums_out)
+        else:
+            y = ops.conv2d(a, wf, bias, co, ksize, residual, OUT_NHWC_BF16, (ci, co))
         ctx.save_for_backward(x, a, stat, weight, wd)
         ctx.cfg = (ksize, act, training, count, co, ci)
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
-        return y
+        return y, sums_out
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _gsums=None):
         x, a, stat, weight, wd = ctx.saved_tensors
         ksize, act, training, count, co, ci = ctx.cfg
         g = g.contiguous()
@@ -404,15 +412,17 @@ class BNActConv(torch.autograd.Function):
                 dgamma, dbeta, coef = _bn_backward_finalize(s_local, count, c, training)
                 dx = ops.bn_act_bwd_apply(x, da, stat, coef, MODE_NONE, act) if ctx.needs_input_grad[0] else None
         dres = g if ctx.has_res else None
-        return dx, dres, dw, db, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx, dres, dw, db, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 class ConvOnly(torch.autograd.Function):
-    """Plain nn.Conv2d (mid_conv, reference models.py:750 / 1096; out_conv, models.py:1099)."""
+    """Plain nn.Conv2d (mid_conv, reference models.py:750 / 1096; out_conv, models.py:1099).  ``emit``: second output = the
+    batch-norm sums of the output for a following "NAC" block (not differentiable)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, ksize, out_mode):
+    def forward(ctx, x, weight, bias, ksize, out_mode, emit=False):
         co, ci = weight.shape[0], weight.shape[1]
+        sums_out = None
         if out_mode == OUT_NCHW_F32 and _outconv_fold_ok(x, weight):
             # full-resolution 7x7 output convolution (inference / eval path): tap-folded forward kernel; the backward below
             # prepares its own operands for the generic kernels when it is ever needed
@@ -421,14 +431,18 @@ class ConvOnly(torch.autograd.Function):
             wd = None
         else:
             wf, wd = ops.weight_prep(weight, True, x.requires_grad)
-            y = ops.conv2d(x, wf, bias, co, ksize, None, out_mode, (ci, co))
+            if emit and out_mode == OUT_NHWC_BF16:
+                y, sums_out = ops.conv2d(x, wf, bias, co, ksize, None, out_mode, (ci, co), want_stats=True)
+                ctx.mark_non_differentiable(sums_out)
+            else:
+                y = ops.conv2d(x, wf, bias, co, ksize, None, out_mode, (ci, co))
         ctx.save_for_backward(x, weight, wd)
         ctx.cfg = (ksize, out_mode, co, ci)
         ctx.has_bias = bias is not None
-        return y
+        return y, sums_out
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _gsums=None):
         x, weight, wd = ctx.saved_tensors
         ksize, out_mode, co, ci = ctx.cfg
         if out_mode == OUT_NCHW_F32:
@@ -438,7 +452,7 @@ class ConvOnly(torch.autograd.Function):
         g = g.contiguous()
         db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
         dx, dw = _conv_backward(GEOM_SAME, x, g, weight, wd, ksize, ctx.needs_input_grad[0])
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------------- VAE bottleneck / losses

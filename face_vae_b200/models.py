@@ -15,7 +15,7 @@ from torch import nn
 
 from . import functional as Fn
 from . import ops
-from .modules import (Conv2d, DownBlock2D, ResBlock2D, SameBlock2D, UpBlock2D, as_nchw, as_nhwc, to_float_nchw)
+from .modules import (Conv2d, DownBlock2D, ResBlock2D, SameBlock2D, UpBlock2D, as_nchw, as_nhwc, chain_res_blocks, to_float_nchw)
 from .ops import MODE_NONE, MODE_UP, OUT_NCHW_F32, OUT_NHWC_BF16
 
 
@@ -112,7 +112,7 @@ class EFE_conv5(nn.Module):
             x_z = x_hat
         else:
             x_mu = x_logstd = x_hat = x_vae = None
-        t = Fn.ConvOnly.apply(Fn.ToNHWC.apply(x_z.contiguous()), self.mid_conv.weight, self.mid_conv.bias, 1, OUT_NHWC_BF16)
+        t = Fn.ConvOnly.apply(Fn.ToNHWC.apply(x_z.contiguous()), self.mid_conv.weight, self.mid_conv.bias, 1, OUT_NHWC_BF16)[0]
         y = as_nchw(t, self.mid_conv.out_channels)                 # logical [N, C*D, h, w]
         n, _, h, w = y.shape
         return y.reshape(n, self.C, self.D, h, w), x_c, x_a_c, (x_mu, x_logstd), (x_vae, x_hat)
@@ -135,19 +135,20 @@ class Generator(nn.Module):
         self.in_conv = ConvBlock2D("CNA", C * D, up_seq[0], 3, 1, 1, use_weight_norm, nonlinearity_type="leakyrelu")
         self.mid_conv = Conv2d(up_seq[0], up_seq[0], 1, 1, 0)
         self.res = nn.Sequential(*[ResBlock2D(up_seq[0], use_weight_norm) for _ in range(n_res)])
+        chain_res_blocks(self.res)
         self.up = nn.Sequential(*[UpBlock2D(up_seq[i], up_seq[i + 1], use_weight_norm) for i in range(len(up_seq) - 1)])
         self.out_conv = Conv2d(up_seq[-1], 3, 7, 1, 3)
 
     def forward_2d(self, fs2d, occlusion=None):
         t = self.in_conv.forward_nhwc(as_nhwc(fs2d))
-        t = Fn.ConvOnly.apply(t, self.mid_conv.weight, self.mid_conv.bias, 1, OUT_NHWC_BF16)
+        t = Fn.ConvOnly.apply(t, self.mid_conv.weight, self.mid_conv.bias, 1, OUT_NHWC_BF16)[0]
         if occlusion is not None:                                    # fs = fs * occlusion (models.py:1105): [N,1,H,W] gate
             t = t * occlusion.permute(0, 2, 3, 1).to(t.dtype)
         for blk in self.res:
             t = blk.forward_nhwc(t.contiguous())
         for blk in self.up:
             t = blk.forward_nhwc(t)
-        logits = Fn.ConvOnly.apply(t, self.out_conv.weight, self.out_conv.bias, 7, OUT_NCHW_F32)
+        logits = Fn.ConvOnly.apply(t, self.out_conv.weight, self.out_conv.bias, 7, OUT_NCHW_F32)[0]
         return torch.sigmoid(logits)
 
     def forward(self, fs, deformation, occlusion):
@@ -197,6 +198,7 @@ class FaceVAE(nn.Module):
         self.zc = d[-1] // 2
         self.mid_conv = Conv2d(self.zc, u[0], 1, 1, 0)
         self.res = nn.Sequential(*[ResBlock2D(u[0], use_weight_norm) for _ in range(n_res)])
+        chain_res_blocks(self.res)
         self.up = nn.Sequential(*[UpBlock2D(u[i], u[i + 1], use_weight_norm) for i in range(len(u) - 1)])
         self.out_conv = Conv2d(u[-1], 3, 7, 1, 3)
         self.out_conv.prep_kind = -1 if u[-1] == 32 else 0     # the tap-folded out_conv kernels prepare their own operands
@@ -222,7 +224,10 @@ class FaceVAE(nn.Module):
     def decode_nhwc(self, z_nchw: torch.Tensor) -> torch.Tensor:
         """z [N,zc,h,w] fp32 -> decoder features NHWC bf16 in front of out_conv."""
         t = Fn.ToNHWC.apply(z_nchw)
-        t = Fn.ConvOnly.apply(t, self.mid_conv.weight, self.mid_conv.bias, 1, OUT_NHWC_BF16)
+        # mid_conv's epilogue emits the batch sums of its output when a ResBlock2D (which normalises its input) follows
+        emit = self.training and len(self.res) > 0
+        t, sums = Fn.ConvOnly.apply(t, self.mid_conv.weight, self.mid_conv.bias, 1, OUT_NHWC_BF16, emit)
+        ops.attach_stats(t, sums)
         for blk in self.res:
             t = blk.forward_nhwc(t)
         for blk in self.up:
@@ -235,7 +240,7 @@ class FaceVAE(nn.Module):
         h = self.encode_nchw(x)
         mu, logstd, z = self.vae(h, train_vae, eps)
         d = self.decode_nhwc(z)
-        logits = Fn.ConvOnly.apply(d, self.out_conv.weight, self.out_conv.bias, 7, OUT_NCHW_F32)
+        logits = Fn.ConvOnly.apply(d, self.out_conv.weight, self.out_conv.bias, 7, OUT_NCHW_F32)[0]
         return mu, logstd, torch.sigmoid(logits)
 
     def forward_loss(self, x: torch.Tensor, eps: Optional[torch.Tensor] = None, l1: bool = False):

@@ -103,7 +103,7 @@ def _conv_nhwc(x, weight, bias, k: int, stride: int):
     if stride == 2:
         w4 = torch.nn.functional.pad(weight, (0, 1, 0, 1))
         return Fn.ConvELRAct.apply(x, w4.contiguous(), bias, 4, 2, 1.0, False, ACT_NONE)
-    return Fn.ConvOnly.apply(x, weight, bias, k, OUT_NHWC_BF16)
+    return Fn.ConvOnly.apply(x, weight, bias, k, OUT_NHWC_BF16)[0]
 
 
 class _SpectralConv2dParams(nn.Module):
@@ -232,8 +232,13 @@ class ConvBlock2D(nn.Module):
             raise NotImplementedError("NAC blocks have no fused up-sampling")
         if post_mode != MODE_NONE or out_nchw_f32:
             raise NotImplementedError("NAC blocks have no fused pool/upsample")
-        return Fn.BNActConv.apply(x, residual, weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                  self.kernel_size, self.act, self.training, bn.momentum, bn.eps)
+        # statistics of the input come from the kernel that produced it when that kernel emitted them (ops.attach_stats); this
+        # block emits those of its output when the parent wired a norm layer behind it (ResBlock2D: emit_stats)
+        sums_in = ops.attached_stats(x) if self.training else None
+        y, sums = Fn.BNActConv.apply(x, residual, weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                     self.kernel_size, self.act, self.training, bn.momentum, bn.eps, sums_in,
+                                     bool(getattr(self, "emit_stats", False)) and self.training)
+        return ops.attach_stats(y, sums)
 
     def forward(self, x):
         return as_nchw(self.forward_nhwc(as_nhwc(x)), self.out_channels)
@@ -326,6 +331,8 @@ class ResBlock2D(nn.Module):
             ConvBlock2D("NAC", in_channels, in_channels, 3, 1, 1, use_weight_norm),
         )
         self.out_channels = in_channels
+        self.layers[0].emit_stats = True       # its output is normalised by layers[1]: the conv epilogue emits the batch sums
+        # layers[1].emit_stats is set by a parent that puts another ResBlock2D behind this one (chain_res_blocks)
 
     def forward_nhwc(self, x):
         h = self.layers[0].forward_nhwc(x)
@@ -333,6 +340,15 @@ class ResBlock2D(nn.Module):
 
     def forward(self, x):
         return as_nchw(self.forward_nhwc(as_nhwc(x)), self.out_channels)
+
+
+def chain_res_blocks(blocks) -> None:
+    """Tell every ResBlock2D that is followed by another one to emit the batch-norm sums of its output (the next block normalises
+    its input): saves one statistics pass per block."""
+    blocks = list(blocks)
+    for a, b in zip(blocks[:-1], blocks[1:]):
+        if isinstance(a, ResBlock2D) and isinstance(b, ResBlock2D):
+            a.layers[1].emit_stats = True
 
 
 # ---------------------------------------------------------------------------------------------------- ELR layers (SURVEY.md 8f rank 1)

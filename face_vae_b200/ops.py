@@ -137,6 +137,39 @@ def bump_counter(t: torch.Tensor) -> None:
         t += 1
 
 
+# ---- batch-norm statistics handed from the convolution that PRODUCES a tensor to the norm layer that consumes it ------------------
+# A "NAC" block (ResBlock2D) normalises its INPUT: the statistics pass over that input (fv_bn_stats, a separate launch per norm
+# layer) is a sum the producing convolution's epilogue can emit.  The producer's module attaches them to the tensor OBJECT it
+# returns (no global table: the hint lives and dies with that object, and an in-place change of the tensor invalidates it).
+def attach_stats(y: torch.Tensor, sums: Optional[torch.Tensor]) -> torch.Tensor:
+    if sums is not None:
+        y._fv_sums = (y._version, tuple(y.shape), sums)
+    return y
+
+
+def attached_stats(x: torch.Tensor) -> Optional[torch.Tensor]:
+    hit = getattr(x, "_fv_sums", None)
+    if hit is None or hit[0] != x._version or hit[1] != tuple(x.shape):
+        return None
+    return hit[2]
+
+
+_zero_consts = {}
+
+
+def zero_grad_const(n: int, device) -> torch.Tensor:
+    """fp32 zeros [n] for a gradient that is analytically zero (the bias of a conv that feeds a batch norm).  Inside a step_scope
+    (the trainer's step) this is ONE shared, never-written tensor per (device, n) instead of a fill kernel per layer and step --
+    the optimiser only reads gradients; outside the scope the caller owns a fresh tensor."""
+    if not _scope_active:
+        return torch.zeros((n,), device=device, dtype=torch.float32)
+    key = (str(device), int(n))
+    z = _zero_consts.get(key)
+    if z is None:
+        z = _zero_consts[key] = torch.zeros((n,), device=device, dtype=torch.float32)
+    return z
+
+
 class step_scope:
     """``with ops.step_scope(model):`` around forward + backward of one train step (VAETrainer does this): the bf16 filter
     operands of all convolutions come from ONE batched launch (a device table of layer descriptors; modules tag their

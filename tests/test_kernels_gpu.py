@@ -141,6 +141,42 @@ def test_conv_fused_bn_statistics(ops, n, h, w, ci, co, k):
     _report("bn_stats kernel", ref.reshape(1, 1, 1, -1), exact.reshape(1, 1, 1, -1), 1e-4, 1e-5)
 
 
+def test_conv_fused_statistics_with_residual(ops):
+    """The second conv of a ResBlock2D emits the sums of (conv + bias + residual) as stored -- what the next block's norm reads."""
+    n, h, w, c = 32, 16, 16, 256
+    x = _rand((n, c, h, w), 75)
+    r = _rand((n, c, h, w), 76)
+    wt = _rand((c, c, 3, 3), 77, -1.0 / math.sqrt(c * 9), 1.0 / math.sqrt(c * 9))
+    b = _rand((c,), 78, bf16_exact=False)
+    wf, _ = ops.weight_prep(wt, True, False)
+    xn, rn = ops.nchw_to_nhwc(x), ops.nchw_to_nhwc(r)
+    y, sums = ops.conv2d(xn, wf, b, c, 3, rn, want_stats=True)
+    y_ref = ops.conv2d(xn, wf, b, c, 3, rn)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
+    yf = y.float().reshape(-1, c)
+    exact = torch.cat([yf.sum(0), (yf * yf).sum(0)])
+    _report("fused stats with residual", sums.reshape(1, 1, 1, -1), exact.reshape(1, 1, 1, -1), 1e-4, 1e-5)
+
+
+def test_res_block_chain_passes_statistics(ops):
+    """ResBlock2D chain with the producer-emitted statistics (ops.attach_stats) against the same chain with the hints removed."""
+    from face_vae_b200.modules import ResBlock2D, chain_res_blocks
+    torch.manual_seed(5)
+    blocks = torch.nn.Sequential(ResBlock2D(64, False), ResBlock2D(64, False)).cuda().train()
+    x = ops.nchw_to_nhwc(_rand((4, 64, 16, 16), 79))
+    ref = blocks[1].forward_nhwc(blocks[0].forward_nhwc(x)).float()
+    chain_res_blocks(blocks)
+    assert blocks[0].layers[0].emit_stats and blocks[0].layers[1].emit_stats and not getattr(blocks[1].layers[1], "emit_stats", False)
+    h = blocks[0].forward_nhwc(x)
+    assert ops.attached_stats(h) is not None
+    got = blocks[1].forward_nhwc(h).float()
+    torch.cuda.synchronize()
+    assert torch.allclose(got, ref, rtol=2e-2, atol=2e-2 * ref.abs().max().item())
+    h.add_(0)                                   # an in-place change invalidates the hint
+    assert ops.attached_stats(h) is None
+
+
 def test_conv_wide_row_tiles_with_256_output_channels(ops):
     # 512-deep variant at 512x512: 128 -> 256 channels on 128-pixel row tiles (the slab stage does not fit twice: tap schedule)
     _conv_case(ops, 1, 6, 128, 128, 256, 3, seed=80)

@@ -108,7 +108,7 @@ def _run_layerwise(fv, cfg, n, hw, base):
     z, kl = Fn.ReparamKL.apply(h.view(b, 2 * dz), eps)
     recs.append(("vae", h, (z, kl)))
     zin = z.detach().view(b, cfg.zc, hh, ww).requires_grad_(True)
-    out = Fn.ConvOnly.apply(Fn.ToNHWC.apply(zin), m.mid_conv.weight, m.mid_conv.bias, 1, OUT_NHWC_BF16)
+    out = Fn.ConvOnly.apply(Fn.ToNHWC.apply(zin), m.mid_conv.weight, m.mid_conv.bias, 1, OUT_NHWC_BF16)[0]
     recs.append(("mid_conv", zin, out))
     for r, blk in enumerate(m.res):
         inp = out.detach().requires_grad_(True)
