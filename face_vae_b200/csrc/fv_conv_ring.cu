@@ -351,21 +351,41 @@ static int launch_ring(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUt
 
 // Returns FV_OK after launching, or -1 when the configuration is not eligible (caller falls through to the generic kernel).
 // 1 when conv2d_ring_try takes this shape (same conditions, no launch)
+// ring slots (R + 3 preferred, down to R + 1: one slab of prefetch) with which the kernel's shared memory fits; 0 = does not fit
+static size_t ring_smem(int ring, int out_mode, int Ci, int Co_pad, int R, int S) {
+    const int row_bytes = Ci * 2;
+    const int slab_stride = ((128 + S - 1) * row_bytes + 1023) & ~1023;
+    int off = ring * slab_stride + R * S * ((Co_pad * row_bytes + 1023) & ~1023);
+    if (out_mode == FV_OUT_NHWC_BF16 && Co_pad <= 64) off += 2 * ((128 * Co_pad * 2 + 1023) & ~1023);
+    return (size_t)off + (2 * ring + 8) * 8 + 16 + (size_t)Co_pad * 52 + 1024 + 64;
+}
+static int ring_slots(int out_mode, int Ci, int Co_pad, int R, int S) {
+    for (int ring = R + 3; ring >= R + 1; --ring)
+        if (ring_smem(ring, out_mode, Ci, Co_pad, R, S) <= 225 * 1024) return ring;
+    return 0;
+}
+
+static bool ring_chunked_ok(int out_mode, int Co_pad) {
+    // measured on enc.2 (64 -> 128 at 128 x 128, batch 32): 2 x 44.5 us against 86 us for the generic schedule -- no gain, so this is
+    // opt-in (FV_CONV_RING_CHUNK=1); the single pass with a 4-slot ring (ring_slots) is what the layer runs
+    const char* env = getenv("FV_CONV_RING_CHUNK");
+    return out_mode == FV_OUT_NHWC_BF16 && Co_pad > 64 && Co_pad % 64 == 0 && env && atoi(env) == 1;
+}
+
 int conv2d_ring_eligible(int out_mode, int H, int W, int Ci, int Co_pad, int R, int S, bool residual) {
     if ((S != 3 && S != 5 && S != 7) || R != S || W % 128 || Ci > 64 || residual) return 0;
     const char* env = getenv("FV_CONV_RING");
     if (env && atoi(env) == 0) return 0;
-    const int row_bytes = Ci * 2;
-    const int slab_stride = ((128 + S - 1) * row_bytes + 1023) & ~1023;
-    int off = (R + 3) * slab_stride + R * S * ((Co_pad * row_bytes + 1023) & ~1023);
-    if (out_mode == FV_OUT_NHWC_BF16 && Co_pad <= 64) off += 2 * ((128 * Co_pad * 2 + 1023) & ~1023);
-    const size_t smem = (size_t)off + (2 * (R + 3) + 8) * 8 + 16 + (size_t)Co_pad * 52 + 1024 + 64;
+    if (Co_pad > 256) return 0;
+    if (ring_slots(out_mode, Ci, Co_pad, R, S)) return 1;
+    if (ring_chunked_ok(out_mode, Co_pad)) return ring_slots(out_mode, Ci, 64, R, S) ? 1 : 0;
     (void)H;
-    return smem <= 225 * 1024 ? 1 : 0;
+    return ring_slots(out_mode, Ci, Co_pad, R, S) ? 1 : 0;
 }
 
-int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
-                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, void* red_ws, cudaStream_t stream) {
+// y_cs: channel stride of the output tensor in elements (== Co_pad unless this launch writes a 64-channel chunk of a wider tensor)
+static int ring_launch(const void* x, const void* w, const float* bias, const void* residual, void* y, int y_cs, int out_mode, int N, int H,
+                       int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, void* red_ws, cudaStream_t stream) {
     if ((S != 3 && S != 5 && S != 7) || W % 128 || Ci > 64 || residual) return -1;
     if (stats && !(out_mode == FV_OUT_NHWC_BF16 && Co_pad <= 64)) return -1;      // fused statistics: staged-store epilogue only
     const char* env = getenv("FV_CONV_RING");
@@ -378,7 +398,8 @@ int conv2d_ring_try(const void* x, const void* w, const float* bias, const void*
     const int a_rows = 128 + S - 1;
     p.slab_tx = a_rows * row_bytes;
     p.slab_stride = (p.slab_tx + 1023) & ~1023;
-    p.ring = R + 3;
+    p.ring = ring_slots(out_mode, Ci, Co_pad, R, S);
+    if (!p.ring || Co_pad > 256) return -1;
     p.w_slice_stride = (Co_pad * row_bytes + 1023) & ~1023;
     p.w_tx = R * S * Co_pad * row_bytes;
     p.w_off = p.ring * p.slab_stride;
@@ -419,7 +440,7 @@ int conv2d_ring_try(const void* x, const void* w, const float* bias, const void*
     }
     if (tma_store) {
         uint64_t dims[4] = {(uint64_t)Co_pad, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[3] = {(uint64_t)Co_pad * 2, (uint64_t)W * Co_pad * 2, (uint64_t)H * W * Co_pad * 2};
+        uint64_t str[3] = {(uint64_t)y_cs * 2, (uint64_t)W * y_cs * 2, (uint64_t)H * W * y_cs * 2};
         uint32_t box[4] = {(uint32_t)Co_pad, 128, 1, 1};
         if (int e = encode_tmap_bf16(&tmY, y, 4, dims, str, box, Co_pad * 2)) return e;
     } else {
@@ -432,6 +453,24 @@ int conv2d_ring_try(const void* x, const void* w, const float* bias, const void*
     if (KB == 32) return FV_RING(32);
     return FV_RING(16);
 #undef FV_RING
+}
+
+// Layers with Ci <= 64 but MORE than 64 output channels (enc.2: 64 -> 128 at 128 x 128): the resident filter of the whole layer
+// (147 KB) leaves no room for the slab ring, and under the generic schedule the filter is re-streamed for every 128-pixel tile
+// (ncu: 808 MB through L2 -> SM for a 67 MB input, tensor pipe 44 %).  Run the ring kernel once per 64-channel chunk of the output
+// instead: each pass keeps its 74 KB filter slice resident and re-reads the (narrow) input.
+int conv2d_ring_try(const void* x, const void* w, const float* bias, const void* residual, void* y, int out_mode, int N, int H,
+                    int W, int Ci, int Co, int Co_pad, int R, int S, int pad, float* stats, int stats_c, void* red_ws, cudaStream_t stream) {
+    if (!ring_chunked_ok(out_mode, Co_pad) || W % 128 || Ci > 64 || residual || R != S || ring_slots(out_mode, Ci, Co_pad, R, S))
+        return ring_launch(x, w, bias, residual, y, Co_pad, out_mode, N, H, W, Ci, Co, Co_pad, R, S, pad, stats, stats_c, red_ws, stream);
+    if (stats || !conv2d_ring_eligible(out_mode, H, W, Ci, 64, R, S, false)) return -1;
+    for (int c0 = 0; c0 < Co_pad; c0 += 64) {
+        const int co = Co - c0 < 64 ? (Co - c0 < 1 ? 1 : Co - c0) : 64;
+        const int e = ring_launch(x, static_cast<const char*>(w) + (size_t)c0 * R * S * Ci * 2, bias ? bias + c0 : nullptr, nullptr,
+                                  static_cast<char*>(y) + (size_t)c0 * 2, Co_pad, out_mode, N, H, W, Ci, co, 64, R, S, pad, nullptr, 0, red_ws, stream);
+        if (e) return e < 0 ? fail(FV_ERR_INTERNAL, "fv_conv2d: ring schedule refused a chunk it had accepted") : e;
+    }
+    return FV_OK;
 }
 
 }  // namespace fv

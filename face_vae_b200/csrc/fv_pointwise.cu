@@ -10,6 +10,8 @@
 //              dbeta follow in closed form (the BN coupling terms need only those sums and the input moments).
 // All sums are accumulated in double, combined across blocks in a fixed order (fv_reduce.cuh: bitwise reproducible) and
 // all-reduced by the host across data-parallel ranks like every other batch-norm statistic.
+#include <cstdlib>
+
 #include "../../include/facevae_b200.h"
 #include "fv_host.h"
 #include "fv_ptx.cuh"
@@ -219,6 +221,118 @@ pw_bwd_reduce_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
         for (int i = threadIdx.x; i < CO * (C + 1); i += blockDim.x) sums[i] = tot[i];
 }
 
+// The same sums with the loads decoupled from the arithmetic: the kernel above issues a tile's loads, waits a full HBM latency
+// (~2 us at 16 warps per SM) and only then computes -- 28 such rounds per SM = the whole 78 us it took (ncu: DRAM 25 %, every
+// warp parked on its first use of g).  Here one thread streams 256-pixel tiles (the contiguous 16 KB of g and the C 1-KB rows of
+// x) into a 4-stage shared-memory ring with cp.async.bulk (TMA, completion on an mbarrier) three tiles ahead of the arithmetic.
+// Requires HW % 256 == 0 (a tile stays inside one image plane) and 16-byte aligned tensors.
+static constexpr int kPwTile = 256, kPwStages = 4;
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int C, int CO>
+__global__ void __launch_bounds__(kPwThreads, 2)
+pw_bwd_reduce_pipe_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ g, const float* __restrict__ coef,
+                          double* __restrict__ sums, int N, int HW, int act, void* ws) {
+    constexpr int CH = CO / 2;
+    constexpr int G_BYTES = kPwTile * CO * 2, X_BYTES = kPwTile * 4, STAGE = G_BYTES + C * X_BYTES;
+    extern __shared__ __align__(128) uint8_t pw_smem[];
+    __shared__ float cs[CO * (C + 1)];
+    __shared__ float red[kPwThreads / 32][2][CH * (C + 1)];
+    __shared__ double blk[CO * (C + 1)], tot[CO * (C + 1)];
+    __shared__ int red_flag;
+    __shared__ __align__(8) uint64_t full[kPwStages];
+    for (int i = threadIdx.x; i < CO * (C + 1); i += blockDim.x) cs[i] = coef[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPwStages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int tiles_per_img = HW / kPwTile;
+    const long long num_tiles = (long long)N * tiles_per_img;
+    auto issue = [&](long long tile, int slot) {          // thread 0 only
+        const int n = (int)(tile / tiles_per_img), hw0 = (int)(tile % tiles_per_img) * kPwTile;
+        uint8_t* dst = pw_smem + (size_t)slot * STAGE;
+        mbar_arrive_expect_tx(&full[slot], (uint32_t)STAGE);
+        bulk_load(dst, g + ((long long)n * HW + hw0) * CO, G_BYTES, &full[slot]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) bulk_load(dst + G_BYTES + c * X_BYTES, x + ((long long)n * C + c) * HW + hw0, X_BYTES, &full[slot]);
+    };
+    if (threadIdx.x == 0)
+        for (int k = 0; k < kPwStages - 1; ++k)
+            if (blockIdx.x + (long long)k * gridDim.x < num_tiles) issue(blockIdx.x + (long long)k * gridDim.x, k);
+    const int half = threadIdx.x & 1, px = threadIdx.x >> 1;
+    float acc[CH][C + 1];
+#pragma unroll
+    for (int co = 0; co < CH; ++co)
+#pragma unroll
+        for (int c = 0; c <= C; ++c) acc[co][c] = 0.f;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int slot = it % kPwStages;
+        // the slot refilled here was read in the previous iteration: the barrier at its end ordered those reads before this copy
+        if (threadIdx.x == 0) {
+            const long long nxt = tile + (long long)(kPwStages - 1) * gridDim.x;
+            if (nxt < num_tiles) issue(nxt, (it + kPwStages - 1) % kPwStages);
+        }
+        mbar_wait(&full[slot], (it / kPwStages) & 1);
+        const uint8_t* st = pw_smem + (size_t)slot * STAGE;
+        const float* xs = reinterpret_cast<const float*>(st + G_BYTES);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int p = px + u * (kPwThreads / 2);
+            float v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = xs[c * kPwTile + p];
+            const uint4* gp = reinterpret_cast<const uint4*>(st + (size_t)p * CO * 2 + half * CH * 2);
+#pragma unroll
+            for (int grp = 0; grp < CH / 8; ++grp) {
+                const uint4 raw = gp[grp];
+                const float gg[8] = {bf16_lo(raw.x), bf16_hi(raw.x), bf16_lo(raw.y), bf16_hi(raw.y), bf16_lo(raw.z), bf16_hi(raw.z), bf16_lo(raw.w), bf16_hi(raw.w)};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int col = grp * 8 + k;
+                    const float* cc = cs + (half * CH + col) * (C + 1);
+                    float z = cc[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) z = fmaf(cc[c], v[c], z);
+                    const float d = act == FV_ACT_RELU ? (z > 0.f ? 1.f : 0.f) : (act == FV_ACT_LEAKY ? (z > 0.f ? 1.f : 0.2f) : 1.f);
+                    const float dz = gg[k] * d;
+                    acc[col][C] += dz;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) acc[col][c] = fmaf(dz, v[c], acc[col][c]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int co = 0; co < CH; ++co)
+#pragma unroll
+        for (int c = 0; c <= C; ++c) {
+            float a = acc[co][c];
+#pragma unroll
+            for (int o = 16; o > 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane < 2) red[warp][lane][co * (C + 1) + c] = a;
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CO * (C + 1); i += blockDim.x) {
+        const int co = i / (C + 1), c = i % (C + 1);
+        const int h = co / CH, col = co % CH;
+        double a = 0;
+        for (int w = 0; w < kPwThreads / 32; ++w) a += (double)red[w][h][col * (C + 1) + c];
+        blk[c == C ? co : CO + co * C + c] = a;
+    }
+    __syncthreads();
+    if (det_reduce<double>(ws, CO * (C + 1), gridDim.x, blockIdx.x, blk, tot, threadIdx.x, blockDim.x, BlockSync{}, &red_flag))
+        for (int i = threadIdx.x; i < CO * (C + 1); i += blockDim.x) sums[i] = tot[i];
+}
+
 // closed-form parameter gradients from the forward moments (fs) and the backward sums (bs); see the header comment
 __global__ void pw_bwd_finalize_kernel(const double* __restrict__ fs, const double* __restrict__ bs, double count, const float* __restrict__ w,
                                        const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ stat,
@@ -295,6 +409,20 @@ extern "C" __attribute__((visibility("default"))) int fv_pw_bwd_reduce(const flo
     if (Co != 32 || C < 1 || C > kPwMaxC) return fail(FV_ERR_UNSUPPORTED, "fv_pw_bwd_reduce: supports C in 1..4 and Co = 32 (got %d -> %d)", C, Co);
     const int grid = pw_grid((long long)N * HW);
     const __nv_bfloat16* gp = (const __nv_bfloat16*)g;
+    const char* env = getenv("FV_PW_PIPE");
+    if (C == 3 && HW % kPwTile == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g)) & 15) == 0 && !(env && atoi(env) == 0)) {
+        constexpr size_t smem = (size_t)kPwStages * (kPwTile * 32 * 2 + 3 * kPwTile * 4);
+        static bool attr_set = false;
+        if (!attr_set) {
+            FV_CUDA(cudaFuncSetAttribute(pw_bwd_reduce_pipe_kernel<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        const long long tiles = (long long)N * (HW / kPwTile);
+        const int pgrid = (int)(tiles < 2LL * num_sms() ? tiles : 2LL * num_sms());
+        pw_bwd_reduce_pipe_kernel<3, 32><<<pgrid, kPwThreads, smem, STREAM>>>(x, gp, coef, sums, N, HW, act, ws);
+        FV_LAUNCH_CHECK("pw_bwd_reduce_pipe_kernel");
+        return FV_OK;
+    }
     PW_DISPATCH_C(C, (pw_bwd_reduce_kernel<3, 32><<<grid, kPwThreads, 0, STREAM>>>(x, gp, coef, sums, N, HW, act, ws)),
                   (pw_bwd_reduce_kernel<4, 32><<<grid, kPwThreads, 0, STREAM>>>(x, gp, coef, sums, N, HW, act, ws)),
                   (pw_bwd_reduce_kernel<1, 32><<<grid, kPwThreads, 0, STREAM>>>(x, gp, coef, sums, N, HW, act, ws)),

@@ -402,12 +402,13 @@ def test_wgrad_ring_schedule(ops, n, h, w, ci, co, k):
     assert err <= 2e-3 * scale + 1e-5, f"wgrad mismatch {err} vs {scale}"
 
 
-@pytest.mark.parametrize("c", [3, 1, 4])
-def test_pointwise_first_layer(ops, c):
+@pytest.mark.parametrize("c,n,h,w", [(3, 3, 24, 40), (1, 3, 24, 40), (4, 3, 24, 40),
+                                     (3, 3, 32, 64), (3, 7, 64, 128)])     # the last two: H*W % 256 == 0 -> the cp.async.bulk pipeline
+def test_pointwise_first_layer(ops, c, n, h, w):
     """SameBlock2D(c <= 4 -> 32) fast path (fv_pointwise.cu): statistics from input moments, closed-form parameter
     gradients; against F.conv2d + F.batch_norm + relu in fp32."""
     from face_vae_b200.ops import ACT_RELU
-    n, h, w, co = 3, 24, 40, 32
+    co = 32
     x = _rand((n, c, h, w), 60, 0.0, 1.0, False)
     wt = _rand((co, c, 1, 1), 61, -0.6, 0.6, False).requires_grad_(True)
     b = _rand((co,), 62, -0.2, 0.2, False).requires_grad_(True)
