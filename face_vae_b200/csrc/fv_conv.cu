@@ -58,6 +58,10 @@ struct ConvParams {
     int w_rows_per_phase;   // rows of the filter matrix per phase (= total Co_pad of the layer)
     int co_parts, Nc;       // output channels split over co_parts CTAs per pixel tile (few tiles): Nc = Co_pad / co_parts
     int num_vtiles;         // nph * co_parts * num_tiles
+    // filter-resident mode (b_res): a CTA works on a contiguous run of pixel tiles of ONE (phase, channel part), loads that filter
+    // slice once (b_res_off) and streams only activation stages -- otherwise every 128-pixel tile re-fetches the whole slice
+    int b_res, b_res_off, b_slice_bytes, bar_off;
+    int ctas_per_slice, tiles_per_cta;
     const float* bias;
     const __nv_bfloat16* residual;
     void* out;
@@ -101,11 +105,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // align up with arithmetic on the array itself so the compiler keeps the shared address space (LDS/STS, not generic)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_stride);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.bar_off);
     uint64_t* empty = full + p.stages;
     uint64_t* tfull = empty + p.stages;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* wfull = tempty + 2;                                 // resident filter slice landed (b_res)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
     int* red_flag = reinterpret_cast<int*>(tmem_slot + 2);
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);      // [Co_pad]
     float* stat_w = bias_s + p.Co_pad;                            // [4 epilogue warps][2][Co_pad] (when p.stats)
@@ -125,11 +130,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], 4);
         }
+        mbar_init(wfull, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
         tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
         tmem_relinquish();
+    }
+    // this CTA's virtual tiles: strided over the grid, or (b_res) a contiguous run inside one (phase, part) slice
+    int vt_begin = blockIdx.x, vt_end = p.num_vtiles, vt_step = gridDim.x;
+    if (p.b_res) {
+        const int slice = blockIdx.x / p.ctas_per_slice, j = blockIdx.x - slice * p.ctas_per_slice;
+        vt_begin = slice * p.num_tiles + j * p.tiles_per_cta;
+        vt_end = min(vt_begin + p.tiles_per_cta, (slice + 1) * p.num_tiles);
+        vt_step = 1;
     }
     for (int c = threadIdx.x; c < p.Co_pad; c += blockDim.x) bias_s[c] = (p.bias && c < p.Co) ? p.bias[c] : 0.f;
     if (p.stats)
@@ -143,7 +157,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         {
             const bool leader = elect_one_sync();      // role loops stay warp-uniform; only the issue is predicated
             uint32_t st = 0, ph = 0;
-            for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x) {
+            if (p.b_res && vt_begin < vt_end) {       // the whole filter slice of this CTA's (phase, part), once
+                int phase, part, tile;
+                decode_vtile(p, vt_begin, phase, part, tile);
+                const int wrow = phase * p.w_rows_per_phase + p.co_base + part * p.Nc;
+                if (leader) mbar_arrive_expect_tx(wfull, (uint32_t)(p.groups * p.kc_blocks * p.nsub * p.b_slice_bytes));
+                for (int g = 0; g < p.groups; ++g)
+                    for (int kc = 0; kc < p.kc_blocks; ++kc)
+                        for (int sm = 0; sm < p.nsub; ++sm)
+                            if (leader)
+                                tma_load_2d(smem + p.b_res_off + (size_t)((g * p.kc_blocks + kc) * p.nsub + sm) * p.b_slice_stride, &tmW, wfull,
+                                            (g * p.nsub + sm) * p.Ci + kc * KB, wrow);
+            }
+            for (int vt = vt_begin; vt < vt_end; vt += vt_step) {
                 int phase, part, tile;
                 decode_vtile(p, vt, phase, part, tile);
                 const int wrow = phase * p.w_rows_per_phase + p.co_base + part * p.Nc;   // first row of this CTA's filter slice
@@ -159,8 +185,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                             mbar_arrive_expect_tx(&full[st], (uint32_t)p.tx_bytes);
                             tma_load_5d(a_dst, &tmX, &full[st], kc * KB + tp.x, t.w0 + tp.y, tp.z, t.h0 + tp.w, t.n0);
                         }
-                        for (int sm = 0; sm < p.nsub; ++sm)
-                            if (leader) tma_load_2d(b_dst + sm * p.b_slice_stride, &tmW, &full[st], wtap + sm * p.Ci + kc * KB, wrow);
+                        if (!p.b_res)
+                            for (int sm = 0; sm < p.nsub; ++sm)
+                                if (leader) tma_load_2d(b_dst + sm * p.b_slice_stride, &tmW, &full[st], wtap + sm * p.Ci + kc * KB, wrow);
                         if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
                     }
                 }
@@ -178,7 +205,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             // consumed after them -- an mbarrier round trip costs the issuing warp 150-300 cycles even when the phase is
             // complete, and the (blocking) issue of 4-12 MMAs per stage hides it
             uint32_t probe = 0;
-            for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x, ++tcount) {
+            if (p.b_res && vt_begin < vt_end) mbar_wait(wfull, 0);
+            for (int vt = vt_begin; vt < vt_end; vt += vt_step, ++tcount) {
                 const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
                 mbar_wait(&tempty[acc], aph ^ 1);
                 tc_fence_after();
@@ -192,7 +220,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         probe = mbar_test_wait(&full[nst], nph);
                     }
                     const uint32_t a_addr = smem_base + st * (uint32_t)p.stage_stride;
-                    const uint32_t b_addr = a_addr + (uint32_t)p.a_off_b;
+                    const uint32_t b_addr = p.b_res ? smem_base + (uint32_t)p.b_res_off + (uint32_t)(g * p.nsub) * (uint32_t)p.b_slice_stride
+                                                    : a_addr + (uint32_t)p.a_off_b;
                     for (int sm = 0; sm < p.nsub; ++sm) {
                         const uint32_t a_lo = (a_addr + (uint32_t)sm * ROW) >> 4;   // slab: tap sm == slab shifted by sm pixel rows
                         const uint32_t b_lo = (b_addr + (uint32_t)sm * p.b_slice_stride) >> 4;
@@ -216,7 +245,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int w_l = row % p.tw, h_l = (row / p.tw) % p.th, n_l = row / (p.tw * p.th);
         float* my_stat = stat_w + q * 2 * p.Co_pad;      // this warp's accumulators: lane pair k <-> channel 16 c + k, plain adds
         uint32_t tcount = 0;
-        for (int vt = blockIdx.x; vt < p.num_vtiles; vt += gridDim.x, ++tcount) {
+        for (int vt = vt_begin; vt < vt_end; vt += vt_step, ++tcount) {
             int phase, part, tile;
             decode_vtile(p, vt, phase, part, tile);
             const int co0 = part * p.Nc;
@@ -533,6 +562,7 @@ static int conv_chunk(const ConvCall& c, int co_base, int Co_pad, int Co) {
     p.a_off_b = (a_rows * row_bytes + 1023) & ~1023;
     p.stage_stride = p.a_off_b + p.b_slice_stride * p.nsub;
     p.tx_bytes = a_rows * row_bytes + p.nsub * p.Nc * row_bytes;
+    p.b_slice_bytes = p.Nc * row_bytes;
     const int groups = p.groups * p.kc_blocks;
     int stages = (196 * 1024) / p.stage_stride;
     if (stages > 8) stages = 8;
@@ -541,6 +571,32 @@ static int conv_chunk(const ConvCall& c, int co_base, int Co_pad, int Co) {
     if ((size_t)stages * p.stage_stride > 200 * 1024)
         return fail(FV_ERR_INTERNAL, "fv_conv2d: stage of %d bytes does not fit twice in shared memory", p.stage_stride);
     p.stages = stages;
+    p.bar_off = p.stages * p.stage_stride;
+    int grid = p.num_vtiles < num_sms() ? p.num_vtiles : num_sms();
+    {
+        // Filter-resident mode: worth it when the filter slice of one (phase, part) fits beside >= 4 activation stages, every slice
+        // gets at least one CTA and a CTA amortises the load over several tiles.  Measured on up.2 forward (x2, 128 -> 64) and the
+        // enc.2 data gradient (128 -> 64 at 128 x 128): 805 / 1013 MB through L2 -> SM for 35 / 134 MB inputs, most of it the filter.
+        const int slices = p.nph * p.co_parts;
+        const long long b_total = (long long)groups * p.nsub * p.b_slice_stride;
+        const int a_stage = p.a_off_b;
+        const long long room = 218LL * 1024 - b_total - (long long)Co_pad * 52 - 2048;
+        int a_stages = (int)(room / a_stage);
+        if (a_stages > 8) a_stages = 8;
+        const int cps = slices <= num_sms() ? num_sms() / slices : 0;
+        if (env_int("FV_CONV_BRES", 1) && b_total <= 160 * 1024 && a_stages >= 4 && cps >= 1 && p.num_tiles >= 2 * cps) {
+            p.b_res = 1;
+            p.ctas_per_slice = cps;
+            p.tiles_per_cta = (p.num_tiles + cps - 1) / cps;
+            p.ctas_per_slice = (p.num_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+            p.stage_stride = a_stage;
+            p.tx_bytes = a_rows * row_bytes;
+            p.stages = a_stages;
+            p.b_res_off = p.stages * p.stage_stride;
+            p.bar_off = p.b_res_off + (int)b_total;
+            grid = slices * p.ctas_per_slice;
+        }
+    }
     p.out_mode = out_mode;
     int cols = 32;
     while (cols < 2 * p.Nc) cols <<= 1;
@@ -573,8 +629,7 @@ static int conv_chunk(const ConvCall& c, int co_base, int Co_pad, int Co) {
         uint32_t box[2] = {(uint32_t)KB, (uint32_t)p.Nc};
         if (int e = encode_tmap_bf16(&tmW, c.w, 2, dims, str, box, row_bytes)) return e;
     }
-    const size_t smem = (size_t)p.stages * p.stage_stride + 1024 + 256 + (size_t)Co_pad * 52 + 64;
-    const int grid = p.num_vtiles < num_sms() ? p.num_vtiles : num_sms();
+    const size_t smem = (size_t)p.bar_off + 1024 + 256 + (size_t)Co_pad * 52 + 64;
     const int e = KB == 64 ? launch_conv<64>(tmX, tmW, p, smem, grid, s) : (KB == 32 ? launch_conv<32>(tmX, tmW, p, smem, grid, s) : launch_conv<16>(tmX, tmW, p, smem, grid, s));
     if (e || !stats || fuse_stats) return e;
     return fv_bn_stats(c.y, y_dtype, stats, (long long)N * Ho * Wo, Co_pad, c.red_ws, c.stream);
