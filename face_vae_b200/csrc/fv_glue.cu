@@ -162,14 +162,13 @@ __device__ __forceinline__ float up_tap_sum(const float* __restrict__ w9, int a,
         for (int s_ = s0; s_ <= s1; ++s_) acc += __ldg(w9 + r * 3 + s_);
     return acc;
 }
-__global__ void weight_prep_batched_kernel(const fv_prep_desc* __restrict__ table) {
-    const fv_prep_desc d = table[blockIdx.y];
+// one item (index i of the padded operand layouts) of one layer of the batched filter preparation
+__device__ __forceinline__ void prep_item(const fv_prep_desc& d, unsigned i) {
     const float* __restrict__ w = d.w;
     __nv_bfloat16* o0 = static_cast<__nv_bfloat16*>(d.wf);
     __nv_bfloat16* o1 = static_cast<__nv_bfloat16*>(d.wd);
     const unsigned taps = d.kind == 0 ? d.R * d.S : 16, cip = d.Ci_pad, cop = d.Co_pad;
-    const unsigned nf = cop * taps * cip;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) {
+    {
         if (d.kind == 0) {
             if (o0) {
                 const unsigned ci = i % cip, t2 = i / cip;
@@ -207,6 +206,35 @@ __global__ void weight_prep_batched_kernel(const fv_prep_desc* __restrict__ tabl
                 o1[i] = __float2bfloat16((co < (unsigned)d.Co && ci < (unsigned)d.Ci) ? __ldg(w + (co * d.Ci + ci) * 16 + r4 * 4 + s4) : 0.f);
             }
         }
+    }
+}
+
+__global__ void weight_prep_batched_kernel(const fv_prep_desc* __restrict__ table) {
+    const fv_prep_desc d = table[blockIdx.y];
+    const unsigned taps = d.kind == 0 ? d.R * d.S : 16;
+    const unsigned nf = (unsigned)d.Co_pad * taps * (unsigned)d.Ci_pad;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) prep_item(d, i);
+}
+
+// Flat grid: block b works on 1024 consecutive items of the layer whose [reserved, next.reserved) range contains b -- blocks in
+// proportion to the layer sizes (they differ 1000x), one item per thread and pass instead of ~30 serial items per thread.
+static constexpr int kPrepBlockItems = 1024;
+__global__ void __launch_bounds__(256) weight_prep_flat_kernel(const fv_prep_desc* __restrict__ table, int n_layers) {
+    __shared__ int layer_s;
+    if (threadIdx.x == 0) {
+        int l = 0;
+        while (l + 1 < n_layers && table[l + 1].reserved <= (int)blockIdx.x) ++l;
+        layer_s = l;
+    }
+    __syncthreads();
+    const fv_prep_desc d = table[layer_s];
+    const unsigned taps = d.kind == 0 ? d.R * d.S : 16;
+    const unsigned nf = (unsigned)d.Co_pad * taps * (unsigned)d.Ci_pad;
+    const unsigned base = (blockIdx.x - (unsigned)d.reserved) * kPrepBlockItems;
+#pragma unroll
+    for (int k = 0; k < kPrepBlockItems / 256; ++k) {
+        const unsigned i = base + k * 256 + threadIdx.x;
+        if (i < nf) prep_item(d, i);
     }
 }
 
@@ -1381,6 +1409,14 @@ extern "C" __attribute__((visibility("default"))) int fv_weight_prep_batched(con
     return FV_OK;
 }
 
+extern "C" __attribute__((visibility("default"))) int fv_weight_prep_flat(const fv_prep_desc* table_dev, int n_layers, int total_blocks, void* stream) {
+    if (!table_dev || n_layers < 1 || total_blocks < 1) return fail(FV_ERR_ARG, "fv_weight_prep_flat: bad arguments");
+    weight_prep_flat_kernel<<<(unsigned)total_blocks, 256, 0, STREAM>>>(table_dev, n_layers);
+    FV_LAUNCH_CHECK("weight_prep_flat_kernel");
+    return FV_OK;
+}
+extern "C" __attribute__((visibility("default"))) int fv_weight_prep_block_items(void) { return kPrepBlockItems; }
+
 extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const float* part, int splits, float* grad, int Co, int Ci, int R, int S, int Co_pad,
                                                                     int Ci_pad, int accumulate, void* stream) {
     if (!part || !grad || splits < 1) return fail(FV_ERR_ARG, "fv_wgrad_finish: bad arguments");
@@ -1520,7 +1556,8 @@ static int reduce_geometry(int C, long long P, int& grid, size_t& shmem, int res
     // measured ~5 % faster there than a single wave.
     const long long row_blocks = (P + rpi - 1) / rpi;
     long long blocks = (row_blocks + rows_per_thread - 1) / rows_per_thread;
-    const long long cap = (long long)num_sms() * (row_blocks > (long long)num_sms() * 64 ? big_waves : resident);
+    static const int big_rows = getenv("FV_REDUCE_BIG") ? atoi(getenv("FV_REDUCE_BIG")) : 64;
+    const long long cap = (long long)num_sms() * (row_blocks > (long long)num_sms() * big_rows ? big_waves : resident);
     grid = (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
     shmem = ((size_t)2 * rpi * C + 4 * (size_t)C) * sizeof(float);   // row partials | block vector [2C] | totals [2C]
     return rpi;
@@ -1541,7 +1578,9 @@ static int bn_stats_impl(const void* y, int dtype, float* sums, long long P, int
     if (!y || !sums) return fail(FV_ERR_ARG, "fv_bn_stats: null pointer");
     if (int e = check_c8("fv_bn_stats", C)) return e;
     int grid; size_t sh;
-    reduce_geometry(C, P, grid, sh, 4);            // 51 registers: four 256-thread blocks per SM
+    // 51 registers: four 256-thread blocks per SM; one resident wave for every size (measured with the ordered cross-block
+    // reduction: 63 / 38 / 25 us -> 59 / 33 / 21 us on the 268 / 134 / 67 MB tensors against two waves of smaller blocks)
+    reduce_geometry(C, P, grid, sh, 4, 16, 4);
     if (int e = check_ws("fv_bn_stats", ws, grid, 2 * C, 4)) return e;
     if (dtype == FV_DT_BF16)
         bn_stats_kernel<__nv_bfloat16><<<grid, kThreads, sh, STREAM>>>((const __nv_bfloat16*)y, sums, P, C, ws, xr);

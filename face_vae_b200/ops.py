@@ -93,6 +93,8 @@ class _PrepCache:
                                                         ("kind", "<i4"), ("reserved", "<i4")]))
         self.map, self.map_up, self.map_s2 = {}, {}, {}
         self.max_items = 0
+        per_block = int(_lib.load().fv_weight_prep_block_items())
+        self.total_blocks = 0
         for i, (w, kind) in enumerate(weights):
             co, ci, r, s_ = w.shape
             cop, cip = pad_channels(co), pad_channels(ci)
@@ -111,7 +113,9 @@ class _PrepCache:
                 o1 = torch.empty((cip, r * s_, cop), device=dev, dtype=torch.bfloat16)
                 self.map[w.data_ptr()] = (o0, o1)
                 items = cop * cip * r * s_
-            rec[i] = (w.data_ptr(), o0.data_ptr(), o1.data_ptr(), (co, ci, r, s_, cop, cip), kind, 0)
+            # `reserved` = first block of this layer in the flat grid of fv_weight_prep_flat
+            rec[i] = (w.data_ptr(), o0.data_ptr(), o1.data_ptr(), (co, ci, r, s_, cop, cip), kind, self.total_blocks)
+            self.total_blocks += (items + per_block - 1) // per_block
             self.max_items = max(self.max_items, items)
         self.table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)
         self.key = tuple((w.data_ptr(), kind) for w, kind in weights)
@@ -120,7 +124,7 @@ class _PrepCache:
         key = tuple((w.data_ptr(), kind) for w, kind in weights)
         if key != self.key:
             self.build(weights)
-        call("fv_weight_prep_batched", self.table.data_ptr(), len(weights), self.max_items, _stream())
+        call("fv_weight_prep_flat", self.table.data_ptr(), len(weights), self.total_blocks, _stream())
         self.valid = True
 
 

@@ -61,6 +61,12 @@ typedef struct {
     int kind, reserved;
 } fv_prep_desc;
 int fv_weight_prep_batched(const fv_prep_desc* table_dev, int n_layers, long long max_items, void* stream);
+/* The same with a flat grid sized by the layers: desc.reserved = index of the layer's first block, a block covering
+ * fv_weight_prep_block_items() consecutive items of the layer's Co_pad * taps * Ci_pad (taps = R*S for kind 0, 16 otherwise);
+ * total_blocks = sum over the layers.  (The 2-D grid of fv_weight_prep_batched gives every layer the same block count although
+ * the layers differ 1000x in size: 58 us for the anchor's 13 convolutions.) */
+int fv_weight_prep_block_items(void);
+int fv_weight_prep_flat(const fv_prep_desc* table_dev, int n_layers, int total_blocks, void* stream);
 /* y = conv(x, wf) + bias (+ residual); stride 1, odd square filter, pad = (R-1)/2.  tcgen05 implicit GEMM.
  * x: NHWC bf16 [N,H,W,Ci] (Ci = 16, 32 or a multiple of 64); wf: [Co_pad][R*S][Ci]; bias: fp32 [Co] or NULL;
  * residual: NHWC bf16 [N,H,W,Co_pad] or NULL (the `x +` of ResBlock2D, modules.py:124-125);

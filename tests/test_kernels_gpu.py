@@ -455,3 +455,37 @@ def test_conv_more_than_256_output_channels(ops, ci, co, k, h, w, n):
     _report(f"dgrad ci{ci} co{co}", dx[..., :ci], x.grad.permute(0, 2, 3, 1), 2e-2, 4e-3)
     err, scale = (dw - wt.grad).abs().max().item(), wt.grad.abs().max().item()
     assert err <= 2e-3 * scale + 1e-5, (err, scale)
+
+
+def test_batched_weight_prep_matches_single_layer_entry_points(ops):
+    """ops.step_scope prepares the bf16 operands of every conv of a model with ONE flat-grid launch (fv_weight_prep_flat): bitwise
+    equal to the per-layer entry points for the three operand kinds (plain, up-sampling 3x3, 4x4 stride 2)."""
+    from face_vae_b200 import ops as O
+    torch.manual_seed(3)
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = torch.nn.Conv2d(3, 32, 1)
+            self.b = torch.nn.Conv2d(32, 64, 3, padding=1)
+            self.c = torch.nn.Conv2d(256, 256, 3, padding=1)
+            self.c.prep_kind = O.PREP_UP
+            self.d = torch.nn.Conv2d(64, 128, 4, 2, 1)
+            self.d.prep_kind = O.PREP_S2
+            self.e = torch.nn.Conv2d(16, 256, 1)
+            self.f = torch.nn.Conv2d(128, 64, 3, padding=1)
+            self.f.prep_kind = O.PREP_UP
+
+    m = M().cuda()
+    with O.step_scope(m):
+        got = {"a": O.weight_prep(m.a.weight, True, True), "b": O.weight_prep(m.b.weight, True, True), "e": O.weight_prep(m.e.weight, True, True),
+               "c": O.weight_prep_up(m.c.weight, True, True), "f": O.weight_prep_up(m.f.weight, True, True),
+               "d": O.weight_prep_s2(m.d.weight, True, True)}
+        got = {k: tuple(t.clone() for t in v) for k, v in got.items()}
+    ref = {"a": O.weight_prep(m.a.weight, True, True), "b": O.weight_prep(m.b.weight, True, True), "e": O.weight_prep(m.e.weight, True, True),
+           "c": O.weight_prep_up(m.c.weight, True, True), "f": O.weight_prep_up(m.f.weight, True, True),
+           "d": O.weight_prep_s2(m.d.weight, True, True)}
+    torch.cuda.synchronize()
+    for k in ref:
+        for g, r in zip(got[k], ref[k]):
+            assert g.shape == r.shape and torch.equal(g, r), k
