@@ -28,6 +28,7 @@ SIGNATURES = {
     "fv_weight_prep": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fv_weight_prep_batched": [_p, _i, _ll, _p],
     "fv_weight_prep_flat": [_p, _i, _i, _p],
+    "fv_weight_prep_tiled": [_p, _i, _i, _p],
     "fv_weight_prep_up": [_p, _p, _p, _i, _i, _i, _i, _p],
     "fv_weight_prep_s2": [_p, _p, _p, _i, _i, _i, _i, _p],
     "fv_conv2d": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p],
@@ -87,7 +88,7 @@ _LL = ("fv_xrank_buffer_floats", "fv_reduce_ws_bytes", "fv_grad_allreduce_flag_w
 _PLAIN_INT = {"fv_outconv_supported": [_i, _i, _i, _i, _i, _i, _i], "fv_conv2d_fuses_stats": [_i, _i, _i, _i, _i, _i, _i, _i, _i],
               "fv_conv2d_wgrad_splits": [_i, _i, _i, _i, _i, _i, _i, _i],
               "fv_conv2d_geom_fuses_stats": [_i, _i, _i, _i, _i, _i, _i], "fv_outconv_wgrad_splits": [_i, _i, _i],
-              "fv_reparam_kl_parts": [_i, _i], "fv_abi_version": [], "fv_weight_prep_block_items": []}
+              "fv_reparam_kl_parts": [_i, _i], "fv_abi_version": [], "fv_weight_prep_block_items": [], "fv_weight_prep_tiled_blocks": [_i, _i, _i, _i, _i]}
 ABI_VERSION = 2            # include/facevae_b200.h FV_ABI_VERSION
 
 _lock = threading.Lock()

@@ -256,6 +256,100 @@ __global__ void __launch_bounds__(256) weight_prep_flat_kernel(const fv_prep_des
     }
 }
 
+// Tile version: a block stages a [16 output channels][32 input channels][taps] tile of the fp32 filter in shared memory with
+// coalesced reads (32 * taps contiguous floats per output channel) and writes both operands from there in THEIR storage order.
+// The item-wise kernels read the filter with the stride of whichever operand they are writing: for the data-gradient operand
+// (output channel fastest) that is one 32-byte sector per element -- 43 us for the anchor's 3.8 M weights.
+static constexpr int kPrepTco = 16, kPrepTci = 32, kPrepMaxTaps = 16;
+__device__ __forceinline__ float up_tap_sum_s(const float* w9, int a, int u, int b, int v) {
+    int r0, r1, s0, s1;
+    up_rows(a, u, r0, r1);
+    up_rows(b, v, s0, s1);
+    float acc = 0.f;
+    for (int r = r0; r <= r1; ++r)
+        for (int s_ = s0; s_ <= s1; ++s_) acc += w9[r * 3 + s_];
+    return acc;
+}
+__global__ void __launch_bounds__(256) weight_prep_tile_kernel(const fv_prep_desc* __restrict__ table, int n_layers) {
+    __shared__ float ws[kPrepTco][kPrepTci * (kPrepMaxTaps + 1)];
+    __shared__ int layer_s;
+    if (threadIdx.x == 0) {
+        int l = 0;
+        while (l + 1 < n_layers && table[l + 1].reserved <= (int)blockIdx.x) ++l;
+        layer_s = l;
+    }
+    __syncthreads();
+    const fv_prep_desc d = table[layer_s];
+    const int taps = d.kind == 0 ? d.R * d.S : (d.kind == 1 ? 9 : 16);          // taps of the SOURCE filter
+    const int cip = d.Ci_pad, cop = d.Co_pad;
+    const int local = (int)blockIdx.x - d.reserved;
+    if (taps > kPrepMaxTaps) {                                                    // 5x5 / 7x7 filters: item-wise
+        const unsigned nf = (unsigned)cop * (unsigned)taps * (unsigned)cip;
+        const unsigned base = (unsigned)local * kPrepBlockItems;
+        for (int k = 0; k < kPrepBlockItems / 256; ++k) {
+            const unsigned i = base + k * 256 + threadIdx.x;
+            if (i < nf) prep_item(d, i);
+        }
+        return;
+    }
+    const int tiles_ci = (cip + kPrepTci - 1) / kPrepTci;
+    const int co0 = (local / tiles_ci) * kPrepTco, ci0 = (local % tiles_ci) * kPrepTci;
+    const int ts = taps | 1;                                                     // odd row stride: conflict-free strided reads
+    // stage: ws[co_l][ci_l * ts + t] = w[co0 + co_l][ci0 + ci_l][t] (zero outside the real filter)
+    const int per_co = kPrepTci * taps;
+    for (int e = threadIdx.x; e < kPrepTco * per_co; e += 256) {
+        const int co_l = e / per_co, rem = e - co_l * per_co;
+        const int ci_l = rem / taps, t = rem - ci_l * taps;
+        const int co = co0 + co_l, ci = ci0 + ci_l;
+        ws[co_l][ci_l * ts + t] = (co < d.Co && ci < d.Ci) ? __ldg(d.w + ((size_t)co * d.Ci + ci) * taps + t) : 0.f;
+    }
+    __syncthreads();
+    __nv_bfloat16* o0 = static_cast<__nv_bfloat16*>(d.wf);
+    __nv_bfloat16* o1 = static_cast<__nv_bfloat16*>(d.wd);
+    const int nci = min(kPrepTci, cip - ci0);                                    // input channels of this tile inside the padded extent
+    if (d.kind == 0) {
+        if (o0)                                                                  // wf [Co_pad][taps][Ci_pad]: ci fastest
+            for (int e = threadIdx.x; e < kPrepTco * taps * kPrepTci; e += 256) {
+                const int ci_l = e % kPrepTci, t = (e / kPrepTci) % taps, co_l = e / (kPrepTci * taps);
+                if (ci_l < nci) o0[((size_t)(co0 + co_l) * taps + t) * cip + ci0 + ci_l] = __float2bfloat16(ws[co_l][ci_l * ts + t]);
+            }
+        if (o1)                                                                  // wd [Ci_pad][taps][Co_pad], taps rotated: co fastest
+            for (int e = threadIdx.x; e < kPrepTci * taps * kPrepTco; e += 256) {
+                const int co_l = e % kPrepTco, t = (e / kPrepTco) % taps, ci_l = e / (kPrepTco * taps);
+                if (ci_l < nci) o1[((size_t)(ci0 + ci_l) * taps + t) * cop + co0 + co_l] = __float2bfloat16(ws[co_l][ci_l * ts + (taps - 1 - t)]);
+            }
+    } else if (d.kind == 1) {
+        if (o0)                                                                  // wx2 [4 phases][Co_pad][4 taps][Ci_pad]
+            for (int e = threadIdx.x; e < 4 * kPrepTco * 4 * kPrepTci; e += 256) {
+                const int ci_l = e % kPrepTci, tap = (e / kPrepTci) % 4, co_l = (e / (4 * kPrepTci)) % kPrepTco, ph = e / (4 * kPrepTci * kPrepTco);
+                if (ci_l < nci)
+                    o0[(((size_t)ph * cop + co0 + co_l) * 4 + tap) * cip + ci0 + ci_l] =
+                        __float2bfloat16(up_tap_sum_s(&ws[co_l][ci_l * ts], ph >> 1, tap >> 1, ph & 1, tap & 1));
+            }
+        if (o1)                                                                  // ws2 [Ci_pad][16 taps][Co_pad]
+            for (int e = threadIdx.x; e < kPrepTci * 16 * kPrepTco; e += 256) {
+                const int co_l = e % kPrepTco, t16 = (e / kPrepTco) % 16, ci_l = e / (16 * kPrepTco);
+                const int r4 = t16 >> 2, s4 = t16 & 3;
+                if (ci_l < nci)
+                    o1[((size_t)(ci0 + ci_l) * 16 + t16) * cop + co0 + co_l] =
+                        __float2bfloat16(up_tap_sum_s(&ws[co_l][ci_l * ts], (r4 & 1) ? 0 : 1, r4 < 2 ? 1 : 0, (s4 & 1) ? 0 : 1, s4 < 2 ? 1 : 0));
+            }
+    } else {
+        if (o0)                                                                  // wf [Co_pad][16][Ci_pad]
+            for (int e = threadIdx.x; e < kPrepTco * 16 * kPrepTci; e += 256) {
+                const int ci_l = e % kPrepTci, t = (e / kPrepTci) % 16, co_l = e / (kPrepTci * 16);
+                if (ci_l < nci) o0[((size_t)(co0 + co_l) * 16 + t) * cip + ci0 + ci_l] = __float2bfloat16(ws[co_l][ci_l * ts + t]);
+            }
+        if (o1)                                                                  // wx2 [4 phases][Ci_pad][4 taps][Co_pad]
+            for (int e = threadIdx.x; e < 4 * kPrepTci * 4 * kPrepTco; e += 256) {
+                const int co_l = e % kPrepTco, tap = (e / kPrepTco) % 4, ci_l = (e / (4 * kPrepTco)) % kPrepTci, ph = e / (4 * kPrepTco * kPrepTci);
+                const int r4 = 3 - 2 * (tap >> 1) - (ph >> 1), s4 = 3 - 2 * (tap & 1) - (ph & 1);
+                if (ci_l < nci)
+                    o1[(((size_t)ph * cip + ci0 + ci_l) * 4 + tap) * cop + co0 + co_l] = __float2bfloat16(ws[co_l][ci_l * ts + r4 * 4 + s4]);
+            }
+    }
+}
+
 // dW partials fp32 [splits][Co_pad][taps][Ci_pad] (one slab per pixel split of the weight-gradient kernels, plain stores) ->
 // grad fp32 [Co][Ci][R][S]: the splits are added in split order (reproducible; replaces red.global.add into one buffer).
 __global__ void wgrad_finish_kernel(const float* __restrict__ part, float* __restrict__ grad, int Co, int Ci, int taps,
@@ -1435,6 +1529,19 @@ extern "C" __attribute__((visibility("default"))) int fv_weight_prep_flat(const 
     return FV_OK;
 }
 extern "C" __attribute__((visibility("default"))) int fv_weight_prep_block_items(void) { return kPrepBlockItems; }
+
+// blocks of one layer in the grid of fv_weight_prep_tiled (desc.reserved = running sum of these)
+extern "C" __attribute__((visibility("default"))) int fv_weight_prep_tiled_blocks(int kind, int Co_pad, int Ci_pad, int R, int S) {
+    const int taps = kind == 0 ? R * S : (kind == 1 ? 9 : 16);
+    if (taps > kPrepMaxTaps) return (int)(((long long)Co_pad * taps * Ci_pad + kPrepBlockItems - 1) / kPrepBlockItems);
+    return ((Co_pad + kPrepTco - 1) / kPrepTco) * ((Ci_pad + kPrepTci - 1) / kPrepTci);
+}
+extern "C" __attribute__((visibility("default"))) int fv_weight_prep_tiled(const fv_prep_desc* table_dev, int n_layers, int total_blocks, void* stream) {
+    if (!table_dev || n_layers < 1 || total_blocks < 1) return fail(FV_ERR_ARG, "fv_weight_prep_tiled: bad arguments");
+    weight_prep_tile_kernel<<<(unsigned)total_blocks, 256, 0, STREAM>>>(table_dev, n_layers);
+    FV_LAUNCH_CHECK("weight_prep_tile_kernel");
+    return FV_OK;
+}
 
 extern "C" __attribute__((visibility("default"))) int fv_wgrad_finish(const float* part, int splits, float* grad, int Co, int Ci, int R, int S, int Co_pad,
                                                                     int Ci_pad, int accumulate, void* stream) {

@@ -93,7 +93,7 @@ class _PrepCache:
                                                         ("kind", "<i4"), ("reserved", "<i4")]))
         self.map, self.map_up, self.map_s2 = {}, {}, {}
         self.max_items = 0
-        per_block = int(_lib.load().fv_weight_prep_block_items())
+        lib = _lib.load()
         self.total_blocks = 0
         for i, (w, kind) in enumerate(weights):
             co, ci, r, s_ = w.shape
@@ -113,9 +113,9 @@ class _PrepCache:
                 o1 = torch.empty((cip, r * s_, cop), device=dev, dtype=torch.bfloat16)
                 self.map[w.data_ptr()] = (o0, o1)
                 items = cop * cip * r * s_
-            # `reserved` = first block of this layer in the flat grid of fv_weight_prep_flat
+            # `reserved` = first block of this layer in the grid of fv_weight_prep_tiled
             rec[i] = (w.data_ptr(), o0.data_ptr(), o1.data_ptr(), (co, ci, r, s_, cop, cip), kind, self.total_blocks)
-            self.total_blocks += (items + per_block - 1) // per_block
+            self.total_blocks += int(lib.fv_weight_prep_tiled_blocks(int(kind), cop, cip, r, s_))
             self.max_items = max(self.max_items, items)
         self.table = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)
         self.key = tuple((w.data_ptr(), kind) for w, kind in weights)
@@ -124,7 +124,7 @@ class _PrepCache:
         key = tuple((w.data_ptr(), kind) for w, kind in weights)
         if key != self.key:
             self.build(weights)
-        call("fv_weight_prep_flat", self.table.data_ptr(), len(weights), self.total_blocks, _stream())
+        call("fv_weight_prep_tiled", self.table.data_ptr(), len(weights), self.total_blocks, _stream())
         self.valid = True
 
 

@@ -67,6 +67,10 @@ int fv_weight_prep_batched(const fv_prep_desc* table_dev, int n_layers, long lon
  * the layers differ 1000x in size: 58 us for the anchor's 13 convolutions.) */
 int fv_weight_prep_block_items(void);
 int fv_weight_prep_flat(const fv_prep_desc* table_dev, int n_layers, int total_blocks, void* stream);
+/* The same through shared-memory tiles (coalesced filter reads, both operands written in their storage order): desc.reserved = running
+ * sum of fv_weight_prep_tiled_blocks(kind, Co_pad, Ci_pad, R, S) over the preceding layers, total_blocks = the sum over all. */
+int fv_weight_prep_tiled_blocks(int kind, int Co_pad, int Ci_pad, int R, int S);
+int fv_weight_prep_tiled(const fv_prep_desc* table_dev, int n_layers, int total_blocks, void* stream);
 /* y = conv(x, wf) + bias (+ residual); stride 1, odd square filter, pad = (R-1)/2.  tcgen05 implicit GEMM.
  * x: NHWC bf16 [N,H,W,Ci] (Ci = 16, 32 or a multiple of 64); wf: [Co_pad][R*S][Ci]; bias: fp32 [Co] or NULL;
  * residual: NHWC bf16 [N,H,W,Co_pad] or NULL (the `x +` of ResBlock2D, modules.py:124-125);

@@ -475,14 +475,18 @@ def test_batched_weight_prep_matches_single_layer_entry_points(ops):
             self.e = torch.nn.Conv2d(16, 256, 1)
             self.f = torch.nn.Conv2d(128, 64, 3, padding=1)
             self.f.prep_kind = O.PREP_UP
+            self.g = torch.nn.Conv2d(16, 32, 5, padding=2)          # more than 16 taps: item-wise blocks inside the tiled launch
+            self.h = torch.nn.Conv2d(48, 24, 3, padding=1)          # padded to 64 / 32 channels
 
     m = M().cuda()
     with O.step_scope(m):
         got = {"a": O.weight_prep(m.a.weight, True, True), "b": O.weight_prep(m.b.weight, True, True), "e": O.weight_prep(m.e.weight, True, True),
+               "g": O.weight_prep(m.g.weight, True, True), "h": O.weight_prep(m.h.weight, True, True),
                "c": O.weight_prep_up(m.c.weight, True, True), "f": O.weight_prep_up(m.f.weight, True, True),
                "d": O.weight_prep_s2(m.d.weight, True, True)}
         got = {k: tuple(t.clone() for t in v) for k, v in got.items()}
     ref = {"a": O.weight_prep(m.a.weight, True, True), "b": O.weight_prep(m.b.weight, True, True), "e": O.weight_prep(m.e.weight, True, True),
+           "g": O.weight_prep(m.g.weight, True, True), "h": O.weight_prep(m.h.weight, True, True),
            "c": O.weight_prep_up(m.c.weight, True, True), "f": O.weight_prep_up(m.f.weight, True, True),
            "d": O.weight_prep_s2(m.d.weight, True, True)}
     torch.cuda.synchronize()

@@ -77,8 +77,9 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg"]
 
 
-def full():
-    src = P + "_full_raw.csv"
+def full(src=None, dst=None, note=""):
+    src = src or P + "_full_raw.csv"
+    dst = dst or os.path.join(prof, f"{TAG}_ncu_full_step.md")
     if not os.path.exists(src):
         return
     rows = list(csv.reader(open(src, errors="replace")))
@@ -91,8 +92,8 @@ def full():
     for r in rows[2:]:
         if len(r) > kn:
             fam.setdefault(short(r[kn]), []).append(r)
-    with open(os.path.join(prof, f"{TAG}_ncu_full_step.md"), "w") as fh:
-        fh.write("# `ncu --set full --clock-control none --import-source on -k regex:fv::` over ONE eager train step (batch 32, 256x256)\n\n"
+    with open(dst, "w") as fh:
+        fh.write("# `ncu --set full --clock-control none --import-source on` over ONE eager train step (batch 32, 256x256)\n\n" + note +
                  "Command: `STEPS=1 ncu ... python tools/ncu_one.py` (tools/gpu_profiles.sh). One row per launch, launch order within a kernel "
                  "family; times are ncu's (cold cache, serialised). `xbar2l1tex` = bytes delivered L2 -> SM; `tensor%` = "
                  "sm__pipe_tensor_cycles_active of active cycles.\n")
@@ -151,7 +152,11 @@ def copies():
 
 if __name__ == "__main__":
     launches()
-    full()
+    full(note="Captured at commit 16c89dc (before the last round-2 optimisations: see r02_ncu_changed_kernels.md for the kernels that changed "
+              "afterwards).\n\n")
+    full(P + "_changed_raw.csv", os.path.join(prof, f"{TAG}_ncu_changed_kernels.md"),
+         "Kernels changed after the full-step capture (filter-resident implicit GEMM, 4-slot ring for N = 128, pipelined pw_bwd_reduce, flat "
+         "weight prep, wide slab sum), captured at the final commit of the round with `-k regex:...`.\n\n")
     source_pages()
     copies()
     print("profiles written")
