@@ -270,38 +270,39 @@ __device__ __forceinline__ float up_tap_sum_s(const float* w9, int a, int u, int
         for (int s_ = s0; s_ <= s1; ++s_) acc += w9[r * 3 + s_];
     return acc;
 }
-__global__ void __launch_bounds__(256) weight_prep_tile_kernel(const fv_prep_desc* __restrict__ table, int n_layers) {
-    __shared__ float ws[kPrepTco][kPrepTci * (kPrepMaxTaps + 1)];
-    __shared__ int layer_s;
-    if (threadIdx.x == 0) {
-        int l = 0;
-        while (l + 1 < n_layers && table[l + 1].reserved <= (int)blockIdx.x) ++l;
-        layer_s = l;
-    }
-    __syncthreads();
-    const fv_prep_desc d = table[layer_s];
-    const int taps = d.kind == 0 ? d.R * d.S : (d.kind == 1 ? 9 : 16);          // taps of the SOURCE filter
+static constexpr int kPrepRow = kPrepTci * (kPrepMaxTaps + 1) + 1;   // + 1: output-channel-fastest reads hit 16 banks, not one
+// TAPS > 0: the source filter's tap count as a compile-time constant (the index arithmetic divides by it per element)
+template <int TAPS>
+__device__ __forceinline__ void prep_tile_body(const fv_prep_desc& d, int local, int taps_rt, float (*ws)[kPrepRow]) {
+    const int taps = TAPS ? TAPS : taps_rt;
     const int cip = d.Ci_pad, cop = d.Co_pad;
-    const int local = (int)blockIdx.x - d.reserved;
-    if (taps > kPrepMaxTaps) {                                                    // 5x5 / 7x7 filters: item-wise
-        const unsigned nf = (unsigned)cop * (unsigned)taps * (unsigned)cip;
-        const unsigned base = (unsigned)local * kPrepBlockItems;
-        for (int k = 0; k < kPrepBlockItems / 256; ++k) {
-            const unsigned i = base + k * 256 + threadIdx.x;
-            if (i < nf) prep_item(d, i);
-        }
-        return;
-    }
     const int tiles_ci = (cip + kPrepTci - 1) / kPrepTci;
     const int co0 = (local / tiles_ci) * kPrepTco, ci0 = (local % tiles_ci) * kPrepTci;
     const int ts = taps | 1;                                                     // odd row stride: conflict-free strided reads
     // stage: ws[co_l][ci_l * ts + t] = w[co0 + co_l][ci0 + ci_l][t] (zero outside the real filter)
     const int per_co = kPrepTci * taps;
-    for (int e = threadIdx.x; e < kPrepTco * per_co; e += 256) {
-        const int co_l = e / per_co, rem = e - co_l * per_co;
-        const int ci_l = rem / taps, t = rem - ci_l * taps;
-        const int co = co0 + co_l, ci = ci0 + ci_l;
-        ws[co_l][ci_l * ts + t] = (co < d.Co && ci < d.Ci) ? __ldg(d.w + ((size_t)co * d.Ci + ci) * taps + t) : 0.f;
+    // eight loads in flight per thread: one load -> one shared store per iteration left every thread waiting a full memory
+    // latency 18 times in a row (ncu: the store's scoreboard stall was the whole kernel)
+    constexpr int kBatch = 8;
+    for (int e0 = threadIdx.x; e0 < kPrepTco * per_co; e0 += 256 * kBatch) {
+        float v[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int e = e0 + k * 256;
+            const int co_l = e / per_co, rem = e - co_l * per_co;
+            const int ci_l = rem / taps, t = rem - ci_l * taps;
+            const int co = co0 + co_l, ci = ci0 + ci_l;
+            v[k] = (e < kPrepTco * per_co && co < d.Co && ci < d.Ci) ? __ldg(d.w + ((size_t)co * d.Ci + ci) * taps + t) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int e = e0 + k * 256;
+            if (e < kPrepTco * per_co) {
+                const int co_l = e / per_co, rem = e - co_l * per_co;
+                const int ci_l = rem / taps, t = rem - ci_l * taps;
+                ws[co_l][ci_l * ts + t] = v[k];
+            }
+        }
     }
     __syncthreads();
     __nv_bfloat16* o0 = static_cast<__nv_bfloat16*>(d.wf);
@@ -348,6 +349,33 @@ __global__ void __launch_bounds__(256) weight_prep_tile_kernel(const fv_prep_des
                     o1[(((size_t)ph * cip + ci0 + ci_l) * 4 + tap) * cop + co0 + co_l] = __float2bfloat16(ws[co_l][ci_l * ts + r4 * 4 + s4]);
             }
     }
+}
+
+__global__ void __launch_bounds__(256) weight_prep_tile_kernel(const fv_prep_desc* __restrict__ table, int n_layers) {
+    __shared__ float ws[kPrepTco][kPrepRow];
+    __shared__ int layer_s;
+    if (threadIdx.x == 0) {
+        int l = 0;
+        while (l + 1 < n_layers && table[l + 1].reserved <= (int)blockIdx.x) ++l;
+        layer_s = l;
+    }
+    __syncthreads();
+    const fv_prep_desc d = table[layer_s];
+    const int taps = d.kind == 0 ? d.R * d.S : (d.kind == 1 ? 9 : 16);          // taps of the SOURCE filter
+    const int local = (int)blockIdx.x - d.reserved;
+    if (taps > kPrepMaxTaps) {                                                    // 5x5 / 7x7 filters: item-wise
+        const unsigned nf = (unsigned)d.Co_pad * (unsigned)taps * (unsigned)d.Ci_pad;
+        const unsigned base = (unsigned)local * kPrepBlockItems;
+        for (int k = 0; k < kPrepBlockItems / 256; ++k) {
+            const unsigned i = base + k * 256 + threadIdx.x;
+            if (i < nf) prep_item(d, i);
+        }
+        return;
+    }
+    if (taps == 9) prep_tile_body<9>(d, local, taps, ws);
+    else if (taps == 16) prep_tile_body<16>(d, local, taps, ws);
+    else if (taps == 1) prep_tile_body<1>(d, local, taps, ws);
+    else prep_tile_body<0>(d, local, taps, ws);
 }
 
 // dW partials fp32 [splits][Co_pad][taps][Ci_pad] (one slab per pixel split of the weight-gradient kernels, plain stores) ->
