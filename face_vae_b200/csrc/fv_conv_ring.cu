@@ -35,10 +35,11 @@ struct RingParams {
     float* stats;                         // optional [2][stats_c]: per-channel sum and sum of squares of the stored output
     int stats_c;
     void* red_ws;                         // fv_reduce.cuh workspace (with stats)
+    int dual;                             // two issuer warps on alternating tiles (3x3 only)
     long long* trace;
 };
 
-static constexpr int kRingThreads = 192;
+static constexpr int kRingThreads = 224;   // producer, issuer A, 4 epilogue warps, issuer B (dual mode)
 
 template <int KB, int S_>
 __global__ void __launch_bounds__(kRingThreads, 1)
@@ -77,7 +78,7 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (p.stage_stride) tma_prefetch_desc(&tmY);
         for (int i = 0; i < p.ring; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&empty[i], 1);
+            mbar_init(&empty[i], p.dual ? 2 : 1);      // dual mode: one arrival from each issuer (see below)
         }
         mbar_init(wbar, 1);
         for (int i = 0; i < 2; ++i) {
@@ -119,6 +120,85 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 }
                 fresh = false;
                 if (++h == p.H) { h = 0; ++col; fresh = true; }
+            }
+        }
+    } else if ((warp == 1 || warp == 6) && p.dual) {
+        // Two issuer warps on alternating tiles (3x3 filters).  A tile's fixed costs in the issuing thread -- observing the accumulator
+        // and slab barriers, two commits: ~500-1200 cycles against 860-1600 cycles of MMA issue -- are serial with its MMAs in one
+        // thread; with two threads one tile's bookkeeping overlaps the other tile's MMAs (the accumulators are already double-buffered:
+        // issuer w owns accumulator w).  Both warps run the same slot / phase bookkeeping over ALL tiles and act on their own.
+        // Slab row r is read by tiles r-1, r, r+1, i.e. by both issuers: its `empty` barrier takes two arrivals, one from each issuer
+        // after that issuer's LAST tile reading it -- after its own tile t an issuer commits rows t-1 and t (slots first, first+1);
+        // the first tile of a run commits row t-1 twice (no predecessor tile), the last tile of a column rows t and t+1 twice.
+        if (t0 < t1) {
+            const uint32_t me = warp == 6 ? 1u : 0u;
+            const bool leader = elect_one_sync();
+            const uint32_t idesc = umma_idesc_bf16(128, p.Co_pad, 0, 0);
+            const uint32_t desc_hi = (uint32_t)(umma_smem_desc(0, 16, SBO, LAYOUT) >> 32);
+            constexpr uint32_t LBO_LO = (16u >> 4) << 16;
+            const uint32_t smem_base = smem_u32(smem);
+            const uint32_t w_base = ((smem_base + (uint32_t)p.w_off) >> 4) | LBO_LO;
+            const uint32_t w_step = (uint32_t)p.w_slice_stride >> 4;
+            mbar_wait(wbar, 0);
+            // `first` / `first_ph`: ring slot and fill parity of the tile's top slab (row h - 1); the tile reads the S_ consecutive slabs
+            uint32_t first = 0, first_ph = 0, tcount = 0;
+            int h = t0 % p.H;
+            bool fresh = true;
+            auto nxt = [&](uint32_t s) { return s + 1 == (uint32_t)p.ring ? 0u : s + 1; };
+            for (int t = t0; t < t1; ++t, ++tcount) {
+                const uint32_t acc = tcount & 1;
+                const bool mine = acc == me;
+                const bool last_in_col = (h + 1 == p.H);
+                if (mine) {
+                    mbar_wait(&tempty[acc], ((tcount >> 1) & 1) ^ 1);
+                    // every slab this tile reads is observed by THIS thread (two of them were new for tiles of the other issuer)
+                    {
+                        uint32_t ws_ = first, wp_ = first_ph;
+#pragma unroll
+                        for (int i = 0; i < S_; ++i) {
+                            mbar_wait(&full[ws_], wp_);
+                            if (++ws_ == (uint32_t)p.ring) { ws_ = 0; wp_ ^= 1; }
+                        }
+                    }
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Co_pad;
+                    uint32_t accumulate = 0, slot = first, wtap = w_base;
+#pragma unroll
+                    for (int r = 0; r < S_; ++r) {
+                        const uint32_t a_row = ((smem_base + slot * (uint32_t)p.slab_stride) >> 4) | LBO_LO;
+#pragma unroll
+                        for (int s = 0; s < S_; ++s) {
+#pragma unroll
+                            for (int j = 0; j < KSUB; ++j) {
+                                if (leader)
+                                    tc_mma_f16_lohi(d_tmem, a_row + (uint32_t)(s * (ROW >> 4) + 2 * j), wtap + (uint32_t)(2 * j), desc_hi, idesc,
+                                                    accumulate);
+                                accumulate = 1;
+                            }
+                            wtap += w_step;
+                        }
+                        slot = nxt(slot);
+                    }
+                    if (leader) {
+                        tc_commit(&tfull[acc]);
+                        if (t + 1 < t1) {          // (the CTA's last tile releases nothing: no load is waiting)
+                            const uint32_t s0 = first, s1 = nxt(first), s2 = nxt(s1);
+                            tc_commit(&empty[s0]);
+                            if (fresh) tc_commit(&empty[s0]);
+                            tc_commit(&empty[s1]);
+                            if (last_in_col) {
+                                tc_commit(&empty[s1]);
+                                tc_commit(&empty[s2]);
+                                tc_commit(&empty[s2]);
+                            }
+                        }
+                    }
+                }
+                const int n_rel = last_in_col ? S_ : 1;
+                for (int i = 0; i < n_rel; ++i)
+                    if (++first == (uint32_t)p.ring) { first = 0; first_ph ^= 1; }
+                fresh = last_in_col;
+                if (++h == p.H) h = 0;
             }
         }
     } else if (warp == 1) {
@@ -203,7 +283,7 @@ conv_ring_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
             FV_TACC(5, t_all);
         }
-    } else {
+    } else if (warp >= 2 && warp <= 5) {
         const int q = warp & 3;
         const int row = q * 32 + lane;                   // pixel within the tile == w offset
         constexpr int EPI_BAR = 1;
@@ -420,6 +500,10 @@ static int ring_launch(const void* x, const void* w, const float* bias, const vo
     p.stats = stats;
     p.stats_c = stats_c;
     p.red_ws = red_ws;
+    {
+        const char* denv = getenv("FV_RING_DUAL");
+        p.dual = (S == 3 && !(denv && atoi(denv) == 0)) ? 1 : 0;
+    }
     p.trace = trace_ptr();
     const int sms = num_sms();
     p.tiles_per_cta = (p.num_tiles + sms - 1) / sms;
