@@ -219,13 +219,30 @@ def run_inference(args, torch, _lib, real_stdout, peaks, warmup):
             model(xs[i % 2], True, eps)
         e1.record()
         torch.cuda.synchronize()
+    ms_eager = e0.elapsed_time(e1) / args.steps
+    # the same forward replayed from a CUDA graph (face_vae_b200.trainer.GraphedInference): what a serving loop would call
+    from face_vae_b200.trainer import GraphedInference
+    engine = GraphedInference(model)
+    for i in range(max(warmup, 3)):
+        out_g = engine(xs[i % 2], True, eps)
+    with torch.no_grad():
+        ref = model(xs[(max(warmup, 3) - 1) % 2], True, eps)
+    torch.cuda.synchronize()
+    if not torch.equal(out_g[2], ref[2]):
+        raise SystemExit("bench.py --infer: graph replay and eager forward disagree")
+    e0.record()
+    for i in range(args.steps):
+        engine(xs[i % 2], True, eps)
+    e1.record()
+    torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     line = {"metric": "inference images/sec at 256x256 (encode -> sample -> decode)", "value": B / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"face-vae anchor eval-mode encode -> sample -> decode, batch {B} at {S}x{S} (BASELINE.json configs[4])",
                        "l2": "two alternating input batches"},
-            "gpu_launches": per_step * args.steps, "latency_ms": ms, "peaks": peaks}
+            "gpu_launches": per_step * args.steps, "latency_ms": ms, "cuda_graph": True,
+            "eager": {"value": B / (ms_eager * 1e-3), "ms_per_step": ms_eager}, "peaks": peaks}
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 

@@ -112,3 +112,32 @@ def test_gradients_are_bitwise_reproducible_smoke_size(ops):
     torch.cuda.synchronize()
     for k in grads[0]:
         assert torch.equal(grads[0][k], grads[1][k]), k
+
+
+def test_graphed_inference_matches_eager_forward():
+    """trainer.GraphedInference: the eval-mode forward replayed from a CUDA graph is bitwise the eager forward, per input shape;
+    training mode and CPU tensors are refused."""
+    from face_vae_b200.models import FaceVAE
+    from face_vae_b200.trainer import GraphedInference
+    torch.manual_seed(11)
+    m = FaceVAE().cuda().eval()
+    eng = GraphedInference(m)
+    for n, hw in ((2, 64), (1, 128), (2, 64)):
+        x = torch.rand((n, 3, hw, hw), device="cuda")
+        eps = torch.randn((n, m.latent_dim(hw, hw)), device="cuda")
+        with torch.no_grad():
+            mu, logstd, xh = m(x, True, eps)
+        gmu, glogstd, gxh = eng(x, True, eps)
+        torch.cuda.synchronize()
+        assert torch.equal(gxh, xh) and torch.equal(gmu, mu) and torch.equal(glogstd, logstd)
+        _, _, gx0 = eng(x, False)
+        with torch.no_grad():
+            _, _, x0 = m(x, False)
+        torch.cuda.synchronize()
+        assert torch.equal(gx0, x0)
+    assert len(eng._graphs) == 4
+    with pytest.raises(RuntimeError):
+        eng(torch.rand((1, 3, 64, 64)), True)
+    m.train()
+    with pytest.raises(RuntimeError):
+        eng(torch.rand((2, 3, 64, 64), device="cuda"), True)
