@@ -28,6 +28,7 @@
 //             (NHWC bf16, NHWC fp32 or NCHW fp32); overlapped with the next tile's MMAs via the second buffer.  Optional
 //             fused batch-norm statistics of the stored values, reduced across CTAs in a fixed order (fv_reduce.cuh).
 #include <cstdio>
+#include <type_traits>
 #include <cstdlib>
 
 #include "../../include/facevae_b200.h"
@@ -45,6 +46,7 @@ struct ConvParams {
     int Ho, Wo, osy, osx;   // output image size and pixel stride: tile pixel (h, w) of phase ph -> (h*osy + oy[ph], w*osx + ox[ph])
     int tw, th, tn, tiles_w, tiles_h, tiles_n, num_tiles;
     int kc_blocks, stages;
+    int kcps;               // K blocks per shared-memory stage (1, 2 or 4): fewer barrier round trips per MMA for the small stages
     int groups;             // TMA groups per (phase, tile)
     int nsub;               // filter taps per group (slab schedule: S, tap schedule: 1)
     int nph;                // output phases: 1, or 4 (X2)
@@ -177,17 +179,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 for (int g = 0; g < p.groups; ++g) {
                     const short4 tp = p.tap[phase * p.groups + g];
                     const int wtap = g * p.nsub * p.Ci;                   // first filter column of this group
-                    for (int kc = 0; kc < p.kc_blocks; ++kc) {
+                    for (int kc0 = 0; kc0 < p.kc_blocks; kc0 += p.kcps) {
                         mbar_wait(&empty[st], ph ^ 1);
                         uint8_t* a_dst = smem + (size_t)st * p.stage_stride;
-                        uint8_t* b_dst = a_dst + p.a_off_b;
-                        if (leader) {
-                            mbar_arrive_expect_tx(&full[st], (uint32_t)p.tx_bytes);
-                            tma_load_5d(a_dst, &tmX, &full[st], kc * KB + tp.x, t.w0 + tp.y, tp.z, t.h0 + tp.w, t.n0);
+                        uint8_t* b_dst = a_dst + p.kcps * p.a_off_b;
+                        if (leader) mbar_arrive_expect_tx(&full[st], (uint32_t)(p.tx_bytes * p.kcps));
+                        for (int q = 0; q < p.kcps; ++q) {
+                            const int kc = kc0 + q;
+                            if (leader) tma_load_5d(a_dst + q * p.a_off_b, &tmX, &full[st], kc * KB + tp.x, t.w0 + tp.y, tp.z, t.h0 + tp.w, t.n0);
+                            if (!p.b_res)
+                                for (int sm = 0; sm < p.nsub; ++sm)
+                                    if (leader)
+                                        tma_load_2d(b_dst + (q * p.nsub + sm) * p.b_slice_stride, &tmW, &full[st], wtap + sm * p.Ci + kc * KB, wrow);
                         }
-                        if (!p.b_res)
-                            for (int sm = 0; sm < p.nsub; ++sm)
-                                if (leader) tma_load_2d(b_dst + sm * p.b_slice_stride, &tmW, &full[st], wtap + sm * p.Ci + kc * KB, wrow);
                         if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
                     }
                 }
@@ -199,44 +203,76 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t idesc = umma_idesc_bf16(128, p.Nc, 0, 0);
             const uint64_t desc_hi = umma_smem_desc(0, 16, SBO, LAYOUT);   // template: all fields but the start address
             const uint32_t smem_base = smem_u32(smem);
-            const int groups = p.groups * p.kc_blocks;
+            const int groups = p.groups * (p.kc_blocks / p.kcps);     // stages per tile
             uint32_t st = 0, ph = 0, tcount = 0;
             // `probe`: the NEXT stage's full barrier, tested (non-blocking) before the current stage's MMAs are issued and
             // consumed after them -- an mbarrier round trip costs the issuing warp 150-300 cycles even when the phase is
             // complete, and the (blocking) issue of 4-12 MMAs per stage hides it
             uint32_t probe = 0;
+            const uint32_t a_q16 = (uint32_t)p.a_off_b >> 4, b_slice16 = (uint32_t)p.b_slice_stride >> 4;
+            const uint32_t b_stage_off = (uint32_t)(p.kcps * p.a_off_b) >> 4, bres_base = (smem_base + (uint32_t)p.b_res_off) >> 4;
             if (p.b_res && vt_begin < vt_end) mbar_wait(wfull, 0);
-            for (int vt = vt_begin; vt < vt_end; vt += vt_step, ++tcount) {
-                const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-                mbar_wait(&tempty[acc], aph ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Nc;
-                uint32_t accumulate = 0;
-                for (int g = 0; g < groups; ++g) {
-                    if (!probe) mbar_wait(&full[st], ph);
+            // The whole tile loop is instantiated for the common (K blocks per stage, taps per group) pairs and selected ONCE: a
+            // run-time loop nest -- or a per-stage dispatch -- around four MMAs costs the issuing thread ~5-9 % of the kernel (measured)
+            auto run = [&](auto q_tag, auto s_tag) {
+                constexpr int Q = decltype(q_tag)::value, NS = decltype(s_tag)::value;      // 0 = run-time count
+                const int nq = Q ? Q : p.kcps, ns = NS ? NS : p.nsub;
+                for (int vt = vt_begin; vt < vt_end; vt += vt_step, ++tcount) {
+                    const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+                    mbar_wait(&tempty[acc], aph ^ 1);
                     tc_fence_after();
-                    {
-                        const uint32_t nst = st + 1 == (uint32_t)p.stages ? 0u : st + 1, nph = st + 1 == (uint32_t)p.stages ? ph ^ 1u : ph;
-                        probe = mbar_test_wait(&full[nst], nph);
-                    }
-                    const uint32_t a_addr = smem_base + st * (uint32_t)p.stage_stride;
-                    const uint32_t b_addr = p.b_res ? smem_base + (uint32_t)p.b_res_off + (uint32_t)(g * p.nsub) * (uint32_t)p.b_slice_stride
-                                                    : a_addr + (uint32_t)p.a_off_b;
-                    for (int sm = 0; sm < p.nsub; ++sm) {
-                        const uint32_t a_lo = (a_addr + (uint32_t)sm * ROW) >> 4;   // slab: tap sm == slab shifted by sm pixel rows
-                        const uint32_t b_lo = (b_addr + (uint32_t)sm * p.b_slice_stride) >> 4;
-#pragma unroll
-                        for (int j = 0; j < KSUB; ++j) {
-                            if (leader)
-                                tc_mma_f16(d_tmem, desc_hi | (uint64_t)((a_lo + 2 * j) & 0x3FFFu),
-                                           desc_hi | (uint64_t)((b_lo + 2 * j) & 0x3FFFu), idesc, accumulate);
-                            accumulate = 1;
+                    const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.Nc;
+                    uint32_t accumulate = 0;
+                    uint32_t b_res_lo = bres_base;
+                    for (int g = 0; g < groups; ++g) {
+                        if (!probe) mbar_wait(&full[st], ph);
+                        tc_fence_after();
+                        {
+                            const uint32_t nst = st + 1 == (uint32_t)p.stages ? 0u : st + 1, nph = st + 1 == (uint32_t)p.stages ? ph ^ 1u : ph;
+                            probe = mbar_test_wait(&full[nst], nph);
                         }
+                        // descriptor start addresses (16-byte units) advance by additions only
+                        uint32_t a_lo = (smem_base + st * (uint32_t)p.stage_stride) >> 4;
+                        uint32_t b_lo = p.b_res ? b_res_lo : a_lo + b_stage_off;
+#pragma unroll
+                        for (int q = 0; q < nq; ++q) {
+                            uint32_t a_s = a_lo;
+#pragma unroll
+                            for (int sm = 0; sm < ns; ++sm) {               // slab: tap sm == slab shifted by sm pixel rows
+#pragma unroll
+                                for (int j = 0; j < KSUB; ++j) {
+                                    if (leader)
+                                        tc_mma_f16(d_tmem, desc_hi | (uint64_t)((a_s + 2 * j) & 0x3FFFu), desc_hi | (uint64_t)((b_lo + 2 * j) & 0x3FFFu),
+                                                   idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                                a_s += ROW >> 4;
+                                b_lo += b_slice16;
+                            }
+                            a_lo += a_q16;
+                        }
+                        b_res_lo = b_lo;
+                        if (leader) tc_commit(&empty[st]);   // frees the smem stage once these MMAs have read it
+                        if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
                     }
-                    if (leader) tc_commit(&empty[st]);   // frees the smem stage once these MMAs have read it
-                    if (++st == (uint32_t)p.stages) { st = 0; ph ^= 1; }
+                    if (leader) tc_commit(&tfull[acc]);      // accumulator complete -> epilogue
                 }
-                if (leader) tc_commit(&tfull[acc]);      // accumulator complete -> epilogue
+            };
+            using I0 = std::integral_constant<int, 0>;
+            using I1 = std::integral_constant<int, 1>;
+            using I2 = std::integral_constant<int, 2>;
+            using I3 = std::integral_constant<int, 3>;
+            using I4 = std::integral_constant<int, 4>;
+            if (p.nsub == 1) {
+                if (p.kcps == 1) run(I1{}, I1{});
+                else if (p.kcps == 2) run(I2{}, I1{});
+                else run(I4{}, I1{});
+            } else if (p.nsub == 3) {
+                if (p.kcps == 1) run(I1{}, I3{});
+                else if (p.kcps == 2) run(I2{}, I3{});
+                else run(I0{}, I0{});
+            } else {
+                run(I0{}, I0{});
             }
         }
     } else {
@@ -560,10 +596,15 @@ static int conv_chunk(const ConvCall& c, int co_base, int Co_pad, int Co) {
     }
     const int a_rows = slab ? p.tw + S - 1 : 128;
     p.a_off_b = (a_rows * row_bytes + 1023) & ~1023;
-    p.stage_stride = p.a_off_b + p.b_slice_stride * p.nsub;
-    p.tx_bytes = a_rows * row_bytes + p.nsub * p.Nc * row_bytes;
+    // K blocks per stage: as many as keep >= 3 stages of <= 64 KB (a stage of one tap x 64 channels is 4 MMAs: the barrier round trips
+    // of the issuing thread then cost as much as the MMAs)
+    p.kcps = 1;
+    for (int k = 4; k >= 2; k >>= 1)
+        if (env_int("FV_CONV_KCPS", 1) && p.kc_blocks % k == 0 && (long long)k * (p.a_off_b + p.b_slice_stride * p.nsub) <= 64 * 1024) { p.kcps = k; break; }
+    p.stage_stride = p.kcps * (p.a_off_b + p.b_slice_stride * p.nsub);
+    p.tx_bytes = a_rows * row_bytes + p.nsub * p.Nc * row_bytes;          // per K block
     p.b_slice_bytes = p.Nc * row_bytes;
-    const int groups = p.groups * p.kc_blocks;
+    const int groups = p.groups * (p.kc_blocks / p.kcps);
     int stages = (196 * 1024) / p.stage_stride;
     if (stages > 8) stages = 8;
     if (stages > groups) stages = groups;
@@ -578,19 +619,23 @@ static int conv_chunk(const ConvCall& c, int co_base, int Co_pad, int Co) {
         // gets at least one CTA and a CTA amortises the load over several tiles.  Measured on up.2 forward (x2, 128 -> 64) and the
         // enc.2 data gradient (128 -> 64 at 128 x 128): 805 / 1013 MB through L2 -> SM for 35 / 134 MB inputs, most of it the filter.
         const int slices = p.nph * p.co_parts;
-        const long long b_total = (long long)groups * p.nsub * p.b_slice_stride;
-        const int a_stage = p.a_off_b;
+        const long long b_total = (long long)p.groups * p.kc_blocks * p.nsub * p.b_slice_stride;
+        int rk = 1;                                              // K blocks per (activation-only) stage in this mode
+        for (int k = 4; k >= 2; k >>= 1)
+            if (env_int("FV_CONV_KCPS", 1) && p.kc_blocks % k == 0 && (long long)k * p.a_off_b <= 64 * 1024) { rk = k; break; }
+        const int a_stage = rk * p.a_off_b;
         const long long room = 218LL * 1024 - b_total - (long long)Co_pad * 52 - 2048;
         int a_stages = (int)(room / a_stage);
         if (a_stages > 8) a_stages = 8;
         const int cps = slices <= num_sms() ? num_sms() / slices : 0;
-        if (env_int("FV_CONV_BRES", 1) && b_total <= 160 * 1024 && a_stages >= 4 && cps >= 1 && p.num_tiles >= 2 * cps) {
+        if (env_int("FV_CONV_BRES", 1) && b_total <= 160 * 1024 && a_stages * rk >= 4 && a_stages >= 2 && cps >= 1 && p.num_tiles >= 2 * cps) {
             p.b_res = 1;
+            p.kcps = rk;
             p.ctas_per_slice = cps;
             p.tiles_per_cta = (p.num_tiles + cps - 1) / cps;
             p.ctas_per_slice = (p.num_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
             p.stage_stride = a_stage;
-            p.tx_bytes = a_rows * row_bytes;
+            p.tx_bytes = a_rows * row_bytes;                     // per K block
             p.stages = a_stages;
             p.b_res_off = p.stages * p.stage_stride;
             p.bar_off = p.b_res_off + (int)b_total;
