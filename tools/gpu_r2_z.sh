@@ -1,9 +1,7 @@
 #!/bin/bash
-# validation: several K blocks per shared-memory stage in the implicit-GEMM kernel
+# validation: two issuer warps (alternating tiles) in the implicit-GEMM kernel
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_updown_gpu.py tests/test_parity_gpu.py tests/test_layerwise_gpu.py tests/test_determinism_gpu.py tests/test_elr_gpu.py tests/test_f2_gpu.py -x -q -m gpu > gpurun_out/r2z_tests.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/r2z_summary.txt
 timeout 300 python tools/step_timeline.py > gpurun_out/r2z_timeline.log 2>&1; echo "timeline rc=$?" | tee -a gpurun_out/r2z_summary.txt
-FV_CONV_KCPS=0 timeout 300 python tools/step_timeline.py > gpurun_out/r2z_timeline_off.log 2>&1; echo "timeline off rc=$?" | tee -a gpurun_out/r2z_summary.txt
 tail -3 gpurun_out/r2z_tests.log
 head -1 gpurun_out/r2z_timeline.log; grep -E "conv_igemm_kernel<64>" gpurun_out/r2z_timeline.log | head -4
-head -1 gpurun_out/r2z_timeline_off.log; grep -E "conv_igemm_kernel<64>" gpurun_out/r2z_timeline_off.log | head -4
