@@ -493,3 +493,27 @@ def test_batched_weight_prep_matches_single_layer_entry_points(ops):
     for k in ref:
         for g, r in zip(got[k], ref[k]):
             assert g.shape == r.shape and torch.equal(g, r), k
+
+
+@pytest.mark.parametrize("mean_over_std", [8.0, 64.0])
+def test_bn_statistics_with_large_mean(ops, mean_over_std):
+    """Round-1 ADVICE: the variance is formed as E[y^2] - E[y]^2 from fp32 sums -- prone to cancellation when |mean| >> std, unlike
+    torch's Welford.  The sums are tree-reduced (per-thread partials of <= a few hundred values, then ordered block sums) and the
+    subtraction is done in double: with a mean 8 / 64 standard deviations away from zero over 512 k values per channel the variance
+    must still be within 1e-3 / 3e-2 relative of the fp64 value (bf16 activations cannot carry a larger ratio with a non-trivial spread)."""
+    n, h, w, c = 8, 256, 256, 32
+    g = torch.Generator(device="cuda").manual_seed(7)
+    y32 = torch.randn((n, h, w, c), device="cuda", generator=g) + mean_over_std
+    y = y32.to(torch.bfloat16)
+    yd = y.double().reshape(-1, c)
+    var_ref = yd.var(dim=0, unbiased=False)
+    mean_ref = yd.mean(dim=0)
+    gamma, beta = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+    stat = ops.bn_finalize(ops.bn_stats(y), n * h * w, gamma, beta, None, None)
+    torch.cuda.synchronize()
+    mean, invstd = stat[0].double(), stat[1].double()
+    var = 1.0 / invstd ** 2 - 1e-5
+    assert torch.allclose(mean, mean_ref, rtol=1e-5, atol=0)
+    rel = ((var - var_ref).abs() / var_ref).max().item()
+    print(f"bn large-mean: mean/std {mean_over_std}: variance rel err {rel:.2e}")
+    assert rel < (1e-3 if mean_over_std <= 8 else 3e-2), rel

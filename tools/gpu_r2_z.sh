@@ -1,7 +1,5 @@
 #!/bin/bash
-# validation: two issuer warps (alternating tiles) in the implicit-GEMM kernel
+# last check of the round: the kernel test file (incl. the large-mean batch-norm statistics test)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_updown_gpu.py tests/test_parity_gpu.py tests/test_layerwise_gpu.py tests/test_determinism_gpu.py tests/test_elr_gpu.py tests/test_f2_gpu.py -x -q -m gpu > gpurun_out/r2z_tests.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/r2z_summary.txt
-timeout 300 python tools/step_timeline.py > gpurun_out/r2z_timeline.log 2>&1; echo "timeline rc=$?" | tee -a gpurun_out/r2z_summary.txt
-tail -3 gpurun_out/r2z_tests.log
-head -1 gpurun_out/r2z_timeline.log; grep -E "conv_igemm_kernel<64>" gpurun_out/r2z_timeline.log | head -4
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -s -k "large_mean or batched_weight or pointwise" > gpurun_out/r2z_tests.log 2>&1; echo "tests rc=$?" | tee gpurun_out/r2z_summary.txt
+grep -E "bn large-mean|passed|failed" gpurun_out/r2z_tests.log | tail -5
