@@ -1,9 +1,10 @@
 """Data-parallel launch helpers with the reference's names and meanings (reference distributed.py:9-74), plus the
 gradient reducer that replaces the DDP wrap of logger.py:55.
 
-One process per GPU; NCCL over NVLink/NVSwitch carries (a) the bucketed gradient all-reduce, launched from
-grad-ready hooks on a side stream so it overlaps the rest of backward, and (b) the per-layer batch-norm statistic
-all-reduces issued from face_vae_b200.functional.
+One process per GPU.  Two exchanges per step: (a) the gradient mean all-reduce -- by default ONE peer-memory kernel over
+NVLink at the end of backward (csrc/fv_xrank.cu, ``fv_grad_allreduce``) on a flat, symmetric gradient buffer; NCCL buckets
+launched from grad-ready hooks on a side stream are the fallback -- and (b) the per-layer batch-norm statistic exchange
+issued from face_vae_b200.functional (face_vae_b200.xrank, NCCL all-reduce as the fallback).
 """
 from __future__ import annotations
 

@@ -43,6 +43,68 @@ class flatten_vae_nl(nn.Module):
         return mu, logstd, z.view(b, zc, h, w)
 
 
+class flatten_vae(nn.Module):
+    """reference models.py:484-522: LinearELR encoder -> (mu_fc * 0.1, logstd_fc * 0.01) -> z = mu + exp(logstd) * randn ->
+    view back to the input shape (no decoder).  ``forward(x, train_vae)`` -> ``(mu, logstd, x_hat)`` when train_vae, else
+    ``(None, None, x_hat)`` with x_hat == mu (the reference multiplies logstd and the noise by 0).  Same constructor,
+    sub-module names and state_dict keys; the sampling runs in the fused re-parameterisation kernel; ``eps`` may be injected."""
+
+    def __init__(self, down_seq=[16 * 4 * 4, 256], up_seq=[256], vae_seq=[256, 256], use_weight_norm=False, lin=None) -> None:
+        super().__init__()
+        from .modules import LinearELR
+        lin = LinearELR if lin is None else lin
+        self.encoder = nn.Sequential(*[lin(down_seq[i], down_seq[i + 1], norm="demod", act=nn.LeakyReLU(0.2)) for i in range(len(down_seq) - 1)])
+        self.mu_fc = lin(vae_seq[0], vae_seq[1])
+        self.logstd_fc = lin(vae_seq[0], vae_seq[1])
+
+    def forward(self, x, train_vae, eps: Optional[torch.Tensor] = None):
+        x = to_float_nchw(x) if x.dim() == 4 else x
+        shape = x.shape
+        x_fl = self.encoder(x.flatten(start_dim=1))
+        mu = self.mu_fc(x_fl) * 0.1
+        if not train_vae:
+            return None, None, mu.view(shape)
+        logstd = self.logstd_fc(x_fl) * 0.01
+        if eps is None:
+            eps = torch.randn(*logstd.size(), device=logstd.device)
+        z = Fn.Reparam.apply(mu.contiguous(), logstd.contiguous(), eps.reshape(mu.shape).contiguous().float())
+        return mu, logstd, z.view(shape)
+
+
+class local_vae(nn.Module):
+    """reference models.py:442-482: DownBlock2D encoder -> flatten -> ``map_fc1`` (LinearELR, demodulated, LeakyReLU) ->
+    ``map_fc2`` -> ``view(b, up_seq[0], 4, 4)`` -> UpBlock2D decoder.  The sampling lines are commented out in the reference, so the
+    module is a deterministic bottleneck: ``forward(x)`` -> ``(None, None, x_hat)``.  Same constructor, sub-module names and
+    state_dict keys (``map_fc1`` is hard-wired to 128 * 4 * 4 inputs as in the reference, models.py:464).  The blocks run on the
+    sm_100a kernels (pool fused into the norm pass, up-sampling folded into the convolution); the two fully connected layers are
+    library GEMMs on the flattened NCHW-ordered features."""
+
+    def __init__(self, down_seq=[128, 128], up_seq=[128, 128], vae_seq=[512, 256], use_weight_norm=False, lin=None) -> None:
+        super().__init__()
+        from .modules import LinearELR
+        lin = LinearELR if lin is None else lin
+        self.up_seq = up_seq
+        self.encoder = nn.Sequential(*[DownBlock2D(down_seq[i], down_seq[i + 1], use_weight_norm) for i in range(len(down_seq) - 1)])
+        self.decoder = nn.Sequential(*[UpBlock2D(up_seq[i], up_seq[i + 1], use_weight_norm) for i in range(len(up_seq) - 1)])
+        self.map_fc1 = lin(128 * 4 * 4, vae_seq[0], norm="demod", act=nn.LeakyReLU(0.2))
+        self.map_fc2 = lin(vae_seq[0], 128 * 4 * 4, norm="demod", act=nn.LeakyReLU(0.2))
+
+    def forward(self, x):
+        b = x.shape[0]
+        t = as_nhwc(x)
+        last = len(self.encoder) - 1
+        for i, blk in enumerate(self.encoder):
+            t = blk.forward_nhwc(t, out_nchw_f32=(i == last))        # the last block writes fp32 NCHW: flatten() is then a view
+        if len(self.encoder) == 0:
+            t = to_float_nchw(x)
+        x_fl = self.map_fc1(t.flatten(start_dim=1))
+        x_de = self.map_fc2(x_fl).view(b, self.up_seq[0], 4, 4)
+        t = Fn.ToNHWC.apply(x_de.contiguous())
+        for blk in self.decoder:
+            t = blk.forward_nhwc(t)
+        return None, None, as_nchw(t, self.decoder[-1].out_channels if len(self.decoder) else self.up_seq[0])
+
+
 class flatten_vae6(nn.Module):
     """reference models.py:802-833: LinearELR encoder -> (mu_fc * 0.1, logstd_fc * 0.01) -> z = mu + exp(logstd) * randn (training)
     / z = mu (eval) -> LinearELR decoder -> view back to the input shape.  ``forward(x)`` -> ``(mu, logstd, x_hat)``.  The

@@ -3,8 +3,9 @@
 
 Tensors cross the module boundary as logical NCHW: fp32 contiguous frames/latents are converted once by a CUDA
 kernel; between blocks the tensors stay bf16 channels-last (a zero-copy view of the internal NHWC buffer), which is
-what the blocks hand to each other.  Only 2-D blocks with ``activation_type="batch"`` and ``use_weight_norm=False``
-are in scope; anything else raises.
+what the blocks hand to each other.  In scope: the 2-D blocks of SURVEY.md section 8 -- batch-normalised stride-1 blocks
+(rows a1-a6), their spectral-norm / instance-norm / 3x3 stride-2 variants (row f2) and the ELR layers (row f1); 3-D blocks
+and any other geometry raise ``NotImplementedError``.
 """
 from __future__ import annotations
 

@@ -280,6 +280,44 @@ def flatten_vae6_forward(x, p, eps, training=True):
     return mu, logstd, z.view(shape)
 
 
+def flatten_vae_forward(x, p, eps, train_vae=True):
+    """flatten_vae.forward (reference models.py:509-522) with eps injected: LinearELR encoder -> mu_fc * 0.1, logstd_fc * 0.01 ->
+    z = mu + exp(logstd) * eps -> view back to the input shape (no decoder).  train_vae False: logstd and the noise are
+    multiplied by 0 (z = mu) and (None, None, x_hat) is returned."""
+    shape = x.shape
+    h = x.flatten(start_dim=1)
+    i = 0
+    while f"encoder.{i}.weight" in p:
+        h = linear_elr(h, p[f"encoder.{i}.weight"], p[f"encoder.{i}.bias"], "demod", "leaky")
+        i += 1
+    on = 1 if train_vae else 0
+    mu = linear_elr(h, p["mu_fc.weight"], p["mu_fc.bias"]) * 0.1
+    logstd = linear_elr(h, p["logstd_fc.weight"], p["logstd_fc.bias"]) * 0.01 * on
+    z = mu + torch.exp(logstd) * eps * on
+    x_hat = z.view(shape)
+    return (mu, logstd, x_hat) if train_vae else (None, None, x_hat)
+
+
+def local_vae_forward(x, p, **kw):
+    """local_vae.forward (reference models.py:471-482): DownBlock2D encoder -> flatten -> map_fc1 (LinearELR demod, LeakyReLU) ->
+    map_fc2 -> view(b, up_seq[0], 4, 4) -> UpBlock2D decoder.  The sampling lines are commented out in the reference: the
+    module is a deterministic bottleneck and returns (None, None, x_hat).  ``kw``: conv_block options (training, ...)."""
+    b = x.shape[0]
+    h, i = x, 0
+    while f"encoder.{i}.layers.0.layers.0.weight" in p:
+        h = down_block(h, p, f"encoder.{i}.", **kw)
+        i += 1
+    h = linear_elr(h.flatten(start_dim=1), p["map_fc1.weight"], p["map_fc1.bias"], "demod", "leaky")
+    h = linear_elr(h, p["map_fc2.weight"], p["map_fc2.bias"], "demod", "leaky")
+    c0 = p["decoder.0.layers.1.layers.0.weight"].shape[1] if "decoder.0.layers.1.layers.0.weight" in p else h.shape[1] // 16
+    h = h.view(b, c0, 4, 4)
+    i = 0
+    while f"decoder.{i}.layers.1.layers.0.weight" in p:
+        h = up_block(h, p, f"decoder.{i}.", **kw)
+        i += 1
+    return None, None, h
+
+
 def bilinear_prescale(x, scale_factor=0.25):
     """F.interpolate(x, mode="bilinear", scale_factor=s, align_corners=False, recompute_scale_factor=True) written out
     (reference models.py:764): Ho = floor(H s); source index (o + 0.5) * (H / Ho) - 0.5 clamped at 0; 4-neighbour blend."""

@@ -404,12 +404,77 @@ def golden_elr(path):
     print(path, len(store), "arrays")
 
 
+def golden_vae_variants(path):
+    """The other bottlenecks built from the same formula / blocks ("same formula in flatten_vae"; 8b callers:
+    local_vae, models.py:461-462,473,480): outputs of the unmodified reference classes ``flatten_vae`` (models.py:484-522,
+    eps injected) and ``local_vae`` (models.py:442-482)."""
+    store = {}
+
+    def det_load(m, tag):
+        sd = m.state_dict()
+        for k in sd:
+            shp = tuple(sd[k].shape)
+            if k.endswith("num_batches_tracked"):
+                continue
+            if k.endswith("running_var"):
+                sd[k] = torch.from_numpy(detgen.det_uniform(shp, detgen.name_seed(tag + k), 0.5, 1.5))
+            elif k.endswith("layers.1.weight") and len(shp) == 1:      # batch-norm gamma
+                sd[k] = torch.from_numpy(detgen.det_uniform(shp, detgen.name_seed(tag + k), 0.5, 1.5))
+            elif len(shp) == 4:                                        # conv filters: fan-in scaled
+                sd[k] = torch.from_numpy(detgen.det_normal(shp, detgen.name_seed(tag + k)) / np.sqrt(shp[1] * shp[2] * shp[3])).float()
+            else:
+                sd[k] = torch.from_numpy(detgen.det_normal(shp, detgen.name_seed(tag + k)) * (0.2 if len(shp) == 1 else 1.0))
+        m.load_state_dict(sd)
+        store[f"{tag}keys"] = np.array(sorted(sd.keys()))
+
+    # flatten_vae, training and not
+    vae = ref_models.flatten_vae()
+    det_load(vae, "fvae.")
+    x = torch.from_numpy(detgen.det_uniform((3, 16, 4, 4), 191, -1.0, 1.0)).requires_grad_(True)
+    eps = torch.from_numpy(detgen.det_normal((3, 256), 192))
+    with injected_randn(eps):
+        mu, ls, xh = vae(x, True)
+    gy = torch.from_numpy(detgen.det_uniform((3, 16, 4, 4), 193, -1.0, 1.0))
+    ((xh * gy).sum() + 3.0 * ref_losses.KLDivergenceLoss()((mu, ls))).backward()
+    for k, v in (("mu", mu), ("logstd", ls), ("xhat", xh), ("dx", x.grad)):
+        put(store, f"fvae/{k}", v, full_below=1 << 20)
+    for k, v in vae.named_parameters():
+        put(store, f"fvae/grad/{k}", v.grad)
+    with injected_randn(eps):
+        mu0, ls0, xh0 = vae(x.detach(), False)
+    assert mu0 is None and ls0 is None
+    put(store, "fvae/eval_xhat", xh0, full_below=1 << 20)
+
+    # local_vae: [N, 128, 8, 8] -> DownBlock2D -> 2048 -> 512 -> 2048 -> [N, 128, 4, 4] -> UpBlock2D -> [N, 128, 8, 8]
+    lv = ref_models.local_vae()
+    det_load(lv, "lvae.")
+    lv.train()
+    x = torch.from_numpy(detgen.det_uniform((4, 128, 8, 8), 194, -1.0, 1.0)).requires_grad_(True)
+    m0, l0, xh = lv(x)
+    assert m0 is None and l0 is None
+    gy = torch.from_numpy(detgen.det_uniform(tuple(xh.shape), 195, -1.0, 1.0))
+    (xh * gy).sum().backward()
+    put(store, "lvae/xhat", xh, full_below=1 << 20)
+    put(store, "lvae/dx", x.grad, full_below=1 << 20)
+    for k, v in lv.named_parameters():
+        put(store, f"lvae/grad/{k}", v.grad, full_below=1 << 12)
+    for k, v in lv.named_buffers():
+        if not k.endswith("num_batches_tracked"):
+            put(store, f"lvae/buf/{k}", v, full_below=1 << 20)
+    lv.eval()
+    _, _, xh_e = lv(x.detach())
+    put(store, "lvae/eval_xhat", xh_e, full_below=1 << 20)
+    np.savez_compressed(path, **store)
+    print(path, len(store), "arrays")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     golden_losses(os.path.join(HERE, "losses.npz"))
     golden_blocks(os.path.join(HERE, "blocks.npz"))
     golden_elr(os.path.join(HERE, "elr.npz"))
     golden_f2(os.path.join(HERE, "f2.npz"))
+    golden_vae_variants(os.path.join(HERE, "vae_variants.npz"))
     golden_anchor(4, 64, 0, os.path.join(HERE, "anchor_n4_64.npz"))     # BASELINE.json configs[0]
     golden_anchor(2, 64, 1, os.path.join(HERE, "anchor_n2_64_b1.npz"))
     if "--large" in sys.argv:       # minutes of CPU time: BASELINE.json configs[1] and the configs[3] architecture at 512x512

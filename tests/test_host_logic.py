@@ -171,3 +171,17 @@ def test_generator_full_keeps_the_reference_call_contract():
     assert list(g.weights) == keys
     with pytest.raises(ValueError):
         GeneratorFull()
+
+
+def test_vae_variants_keep_the_reference_state_dict_keys_and_refuse_cpu_tensors():
+    """flatten_vae / local_vae (reference models.py:484-522, 442-482): the key lists stored next to the golden outputs are the
+    unmodified reference modules' state_dict keys, so a reference checkpoint loads unchanged; no CPU path."""
+    from tests import goldenlib as G
+    from face_vae_b200 import models as MO
+    g = G.load("vae_variants.npz")
+    assert sorted(MO.flatten_vae().state_dict().keys()) == [str(k) for k in g["fvae.keys"]]
+    assert sorted(MO.local_vae().state_dict().keys()) == [str(k) for k in g["lvae.keys"]]
+    with pytest.raises(RuntimeError):
+        MO.flatten_vae()(torch.zeros(2, 16, 4, 4), True)
+    with pytest.raises(RuntimeError):
+        MO.local_vae()(torch.zeros(2, 128, 8, 8))
