@@ -373,6 +373,8 @@ def main():
         pass
     graph_mode = trainer.use_cuda_graph
     trainer.use_cuda_graph = False                 # eager replay of the same step: one event pair per launch
+    from face_vae_b200 import ops as _ops
+    side_mode = _ops.set_wgrad_stream(False)       # ... on ONE stream: an event pair must not span a kernel running beside its own
     trainer.step(*dev[0])
     _lib.profile_start()
     for i in range(args.profile_steps):
@@ -382,6 +384,7 @@ def main():
         trainer.step(*dev[i % 2])
     recs = _lib.profile_stop()
     trainer.use_cuda_graph = graph_mode
+    _ops.set_wgrad_stream(side_mode)
     agg = {}
     for name, t_ms, meta in recs:
         a = agg.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "flops_exec": 0.0, "bytes": 0.0, "big_bytes": 0.0, "big_ms": 0.0})
@@ -481,7 +484,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": f"face-vae {'512-deep variant' if args.deep else 'anchor'} (SURVEY.md section 8) train step, batch {B} per GPU at {S}x{S}, "
                                        f"0.2*KL + 10*MSE, Adam(5e-5, betas 0.5/0.999), bf16 storage / fp32 accumulate",
-                           "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(trainer.use_cuda_graph),
+                           "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(trainer.use_cuda_graph), "wgrad_side_stream": bool(side_mode),
                            "l2": "working set per step (activations + gradients, >3 GB) far exceeds the 126 MB L2; inputs alternate between two batches"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * S * S * 4 + B * dz * 4, "d2h_bytes_per_step": 4,

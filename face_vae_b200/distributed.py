@@ -204,6 +204,9 @@ class GradientReducer:
     def _launch(self, bi: int) -> None:
         bucket = self.buckets[bi]
         lo, hi = self._range[bi]
+        if self.params and self.params[0].is_cuda:
+            from . import ops
+            ops.join_wgrad_stream()       # weight gradients issued on the side stream are complete before they are gathered
         # gather this bucket's gradients into their slots (one multi-tensor copy on the compute stream, right behind the
         # kernels that produced them) and make the slots the parameters' .grad
         src = [p.grad for p in bucket if p.grad is not None and p.grad.data_ptr() != self._slot[id(p)].data_ptr()]

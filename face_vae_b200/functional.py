@@ -163,7 +163,8 @@ def _conv_backward(geom, x, dy, weight, wd, ksize, need_dx):
     """-> (dx | None, dw) for y = conv(x, weight) in geometry ``geom``; dy: NHWC bf16 gradient of y."""
     co, ci = weight.shape[0], weight.shape[1]
     if geom == GEOM_UP:
-        dw = ops.wgrad_finish_up(ops.conv2d_wgrad_x2(x, dy, (ci, co)), co, ci)
+        with ops.wgrad_stream(x, dy):
+            dw = ops.wgrad_finish_up(ops.conv2d_wgrad_x2(x, dy, (ci, co)), co, ci)
         dx = None
         if need_dx:
             if wd is None:
@@ -171,7 +172,8 @@ def _conv_backward(geom, x, dy, weight, wd, ksize, need_dx):
             # 4x4 stride-2 convolution of dY with the summed, mirrored taps: the 2x2 sum of the up-sampling backward is inside
             dx = ops.conv2d_s2(dy, wd, None, x.shape[3], OUT_NHWC_BF16, (co, ci), alg_taps=36)
         return dx, dw
-    dw = ops.wgrad_finish(ops.conv2d_wgrad(x, dy, ksize, (ci, co)), co, ci, ksize)
+    with ops.wgrad_stream(x, dy):
+        dw = ops.wgrad_finish(ops.conv2d_wgrad(x, dy, ksize, (ci, co)), co, ci, ksize)
     dx = None
     if need_dx:
         if wd is None:
@@ -587,7 +589,8 @@ class ConvSigmoidRecon(torch.autograd.Function):
         if ctx.fold:
             d, weight, g4, wdq, gsum = ctx.saved_tensors
             db = gsum * gl if ctx.has_bias else None
-            dw = ops.outconv_wgrad(d, g4, gl, co)
+            with ops.wgrad_stream(d, g4, gl):
+                dw = ops.outconv_wgrad(d, g4, gl, co)
             dx = None
             if ctx.needs_input_grad[0]:
                 if wdq is None:

@@ -7,6 +7,7 @@ Activations are explicit NHWC tensors ``[N, H, W, C]`` (bf16 unless stated), C p
 from __future__ import annotations
 
 import math
+import os as _os
 from typing import Optional, Tuple
 
 import torch
@@ -68,6 +69,67 @@ def _red_ws() -> int:
         buf = torch.zeros((int(_lib.load().fv_reduce_ws_bytes()),), dtype=torch.uint8, device="cuda")
         _red_ws_cache[key] = buf
     return buf.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------ weight-gradient side stream
+# Inside a step scope the weight-gradient kernels (tensor bound, nothing downstream of them until the optimiser) can be issued
+# on a second stream: they then run beside the HBM-bound norm / activation passes of the layers further down the backward
+# chain instead of in front of them.  Fork: the side stream waits for an event recorded on the compute stream right after dY
+# was produced; join: the compute stream waits for the side stream when the scope closes (and before a gradient reducer
+# touches the gradients).  Operands of a side-stream kernel are kept referenced until the join, so the caching allocator
+# cannot hand their memory to a later compute-stream kernel while the side stream still reads it.  Under CUDA-graph capture
+# fork and join become graph edges.  Results do not depend on the schedule (no atomics): bitwise equal to the serial order.
+_WGRAD_STREAM = _os.environ.get("FACEVAE_WGRAD_STREAM", "0") == "1"
+_wgrad_side = {}           # (device, compute stream) -> side stream
+_wgrad_live = []           # tensors a pending side-stream kernel reads
+_wgrad_dirty = {}          # (device, compute stream) -> (compute stream, side stream) with un-joined work
+
+
+def set_wgrad_stream(enabled: bool) -> bool:
+    """Switch the weight-gradient side stream on / off; -> the previous setting.  (bench.py times kernels one by one with it off.)"""
+    global _WGRAD_STREAM
+    prev, _WGRAD_STREAM = _WGRAD_STREAM, bool(enabled)
+    return prev
+
+
+class wgrad_stream:
+    """``with ops.wgrad_stream(x, dy):`` -- the kernels issued inside run on the weight-gradient side stream (when enabled and
+    inside a step scope; otherwise on the current stream as usual).  ``tensors``: what those kernels read."""
+
+    def __init__(self, *tensors):
+        self.tensors = [t for t in tensors if t is not None]
+        self.ctx = None
+
+    def __enter__(self):
+        if not (_WGRAD_STREAM and _scope_active):
+            return self
+        main = torch.cuda.current_stream()
+        key = (torch.cuda.current_device(), main.cuda_stream)
+        side = _wgrad_side.get(key)
+        if side is None:
+            side = _wgrad_side[key] = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        _wgrad_live.extend(self.tensors)
+        _wgrad_dirty.setdefault(key, (main, side))
+        self.ctx = torch.cuda.stream(side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.ctx = None
+        return False
+
+
+def join_wgrad_stream() -> None:
+    """The compute stream(s) wait for the pending weight-gradient kernels; their operands may be released afterwards."""
+    while _wgrad_dirty:
+        _, (main, side) = _wgrad_dirty.popitem()
+        main.wait_stream(side)
+    _wgrad_live.clear()
 
 
 # ------------------------------------------------------------------------------------------------ per-step scope
@@ -206,6 +268,7 @@ class step_scope:
 
     def __exit__(self, *exc):
         global _scope_active
+        join_wgrad_stream()
         _scope_active = False
         _prep.valid = False
         if _pending_counters:

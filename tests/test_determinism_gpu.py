@@ -90,6 +90,31 @@ def test_train_step_is_bitwise_reproducible(ops, n, hw):
             assert torch.equal(a[1][k], other[1][k]), k
 
 
+@pytest.mark.parametrize("n,hw", [(4, 64), (32, 256)])
+def test_weight_gradient_side_stream_gives_the_serial_bits(ops, n, hw):
+    """ops.wgrad_stream: the weight-gradient kernels on a second stream (beside the norm / activation passes further down the
+    backward chain) change the schedule, not the arithmetic -- losses, weights and running statistics after two optimiser steps
+    are bitwise those of the one-stream order, eager and CUDA-graph; nothing is left un-joined."""
+    import face_vae_b200.models as MO
+    import face_vae_b200.ops as OPS
+    import face_vae_b200.trainer as T
+    prev = OPS.set_wgrad_stream(False)
+    try:
+        a = _one_step(MO, T, n, hw, 5, False)
+        OPS.set_wgrad_stream(True)
+        b = _one_step(MO, T, n, hw, 5, False)
+        c = _one_step(MO, T, n, hw, 5, True)
+        assert not OPS._wgrad_dirty and not OPS._wgrad_live
+    finally:
+        OPS.set_wgrad_stream(prev)
+    for other in (b, c):
+        for la, lb in zip(a[0], other[0]):
+            for k in la:
+                assert torch.equal(la[k], lb[k]), (k, la[k].item(), lb[k].item())
+        for k in a[1]:
+            assert torch.equal(a[1][k], other[1][k]), k
+
+
 def test_gradients_are_bitwise_reproducible_smoke_size(ops):
     """The quantity __graft_entry__.smoke() prints (worst gradient deviation from the oracle) is the same on every run
     because the gradients are: forward + backward twice on one model."""
