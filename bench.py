@@ -426,11 +426,34 @@ def main():
     # pass above inflates every launch by its host gap, so the in-graph SHARE of the convolutions times the device-timed step
     # (measured without any profiler, above) is the better estimate of their time in the real step
     in_graph = None
+    one_stream_ms = None
     if trainer.use_cuda_graph:
+        serial = bool(side_mode) and world == 1
         try:
+            if serial:
+                # With the weight-gradient side stream the convolutions run BESIDE the norm / activation passes: per-kernel
+                # durations then overlap and a share of their sum is no longer a share of the step.  The split is therefore
+                # taken on the one-stream schedule of the same kernels (graph re-captured with the side stream off, its step
+                # timed with CUDA events without a profiler); the headline value above is the overlapped step.
+                _ops.set_wgrad_stream(False)
+                trainer._graph = None
+                for i in range(3):
+                    trainer.step(*dev[i % 2])
+                torch.cuda.synchronize()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                for i in range(10):
+                    trainer.step(*dev[i % 2])
+                s1.record()
+                torch.cuda.synchronize()
+                one_stream_ms = s0.elapsed_time(s1) / 10
             in_graph = _in_graph_shares(torch, trainer, dev)
         except Exception as e:                      # profiler unavailable: keep the event-pair numbers only
             in_graph = {"error": f"{type(e).__name__}: {e}"}
+        finally:
+            if serial:
+                _ops.set_wgrad_stream(True)
+                trainer._graph = None
     if conv["ms"] > 0:
         per_step_ms = conv["ms"] / args.profile_steps
         flops_step = conv["flops"] / args.profile_steps
@@ -449,10 +472,14 @@ def main():
                     "ms_per_step": per_step_ms, "avg_launch_ms": conv["ms"] / conv["launches"],
                     "launches_per_step": conv["launches"] / args.profile_steps, "traffic": None}
         if in_graph and "conv_share" in in_graph:
-            ms_in = in_graph["conv_share"] * (ms / args.steps)
+            ms_in = in_graph["conv_share"] * (one_stream_ms if one_stream_ms else ms / args.steps)
             roofline["in_graph"] = {"conv_share_of_kernel_time": in_graph["conv_share"], "conv_ms_per_step": ms_in,
                                     "achieved": flops_step / (ms_in * 1e-3) / 1e12, "frac": flops_step / (ms_in * 1e-3) / 1e12 / peak,
-                                    "how": "share of the convolution kernels in the CUPTI kernel time of three graph replays x the device-timed step"}
+                                    "how": "share of the convolution kernels in the CUPTI kernel time of three graph replays x the device-timed step"
+                                           + (" of the ONE-STREAM schedule (graph re-captured with the weight-gradient side stream off; "
+                                              "the headline step overlaps these kernels with the norm / activation passes)" if one_stream_ms else "")}
+            if one_stream_ms:
+                roofline["in_graph"]["one_stream_ms_per_step"] = one_stream_ms
         elif in_graph:
             roofline["in_graph"] = in_graph
         # DRAM bytes per launch of these kernels from the committed ncu launch list of this command (profiles/)

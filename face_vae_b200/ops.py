@@ -79,7 +79,7 @@ def _red_ws() -> int:
 # touches the gradients).  Operands of a side-stream kernel are kept referenced until the join, so the caching allocator
 # cannot hand their memory to a later compute-stream kernel while the side stream still reads it.  Under CUDA-graph capture
 # fork and join become graph edges.  Results do not depend on the schedule (no atomics): bitwise equal to the serial order.
-_WGRAD_STREAM = _os.environ.get("FACEVAE_WGRAD_STREAM", "0") == "1"
+_WGRAD_STREAM = _os.environ.get("FACEVAE_WGRAD_STREAM", "1") != "0"
 _wgrad_side = {}           # (device, compute stream) -> side stream
 _wgrad_live = []           # tensors a pending side-stream kernel reads
 _wgrad_dirty = {}          # (device, compute stream) -> (compute stream, side stream) with un-joined work

@@ -6,7 +6,9 @@
  model   the whole data-parallel train step: identical (bitwise) averaged gradients and running statistics on every rank,
          and agreement with the single-process global-batch run within the bf16 yardstick;
  skew    round-1 ADVICE (high): one rank is delayed before backward; gradients must still be bitwise equal across ranks, in
-         eager mode and through the CUDA-graph-captured step."""
+         eager mode and through the CUDA-graph-captured step;
+ gradar  the peer-memory gradient all-reduce kernel against NCCL;
+ wstream the weight-gradient side stream (ops.wgrad_stream) gives the one-stream bits under data parallelism."""
 import os
 import sys
 
@@ -140,6 +142,43 @@ def scenario_skew(rank, world):
         print(f"ddp skew world={world}: ok")
 
 
+def scenario_wstream(rank, world):
+    """ops.wgrad_stream under data parallelism: with the weight-gradient kernels on the side stream (joined before the gradient
+    all-reduce gathers the gradients) three optimiser steps give bitwise the weights of the one-stream order, eager and captured,
+    with a different rank delayed every step; identical on all ranks."""
+    from face_vae_b200 import ops
+    cfg = O.CFG_256
+    p = O.det_anchor_params(cfg, 0)
+    per, hw = 4, 64
+    x, eps = O.det_inputs(per * world, hw, hw, cfg, 6)
+    xs, es = x[rank * per:(rank + 1) * per].cuda(), eps[rank * per:(rank + 1) * per].cuda()
+    prev = ops.set_wgrad_stream(False)
+    try:
+        for use_graph in (False, True):
+            res = []
+            for side in (False, True):
+                ops.set_wgrad_stream(side)
+                m = make_model(p)
+                tr = VAETrainer(m, lr=1e-3, use_cuda_graph=use_graph)
+                for it in range(3):
+                    if side and rank == (it % world):
+                        torch.cuda._sleep(int(2e8))
+                    tr.step(xs, es)
+                torch.cuda.synchronize()
+                assert tr.use_cuda_graph == use_graph, "graph capture must not silently fall back"
+                assert not ops._wgrad_dirty and not ops._wgrad_live
+                res.append({k: v.detach().clone() for k, v in m.state_dict().items()})
+                for k, q in m.named_parameters():
+                    same_on_all_ranks(f"graph={use_graph} side={side} weight {k}", q.data, rank)
+                del tr
+            for k in res[0]:
+                assert torch.equal(res[0][k], res[1][k]), (use_graph, k)
+    finally:
+        ops.set_wgrad_stream(prev)
+    if rank == 0:
+        print(f"ddp wstream world={world}: ok")
+
+
 def scenario_gradar(rank, world):
     """fv_grad_allreduce (peer-memory, one kernel) against NCCL on odd-sized tensors, 20 back-to-back epochs."""
     sizes = [5, 1023, 4096, 333, 70001, 1 << 20, 7]
@@ -174,7 +213,7 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     fd.init_dist(int(os.environ["LOCAL_RANK"]), world, "nccl")
-    {"block": scenario_block, "model": scenario_model, "skew": scenario_skew, "gradar": scenario_gradar}[sys.argv[1]](rank, world)
+    {"block": scenario_block, "model": scenario_model, "skew": scenario_skew, "gradar": scenario_gradar, "wstream": scenario_wstream}[sys.argv[1]](rank, world)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -12,11 +12,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("scenario", ["block", "model", "skew", "gradar"])
+@pytest.mark.parametrize("scenario", ["block", "model", "skew", "gradar", "wstream"])
 def test_two_rank_data_parallel(scenario):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    port = 29600 + {"block": 1, "model": 2, "skew": 3, "gradar": 4}[scenario]
+    port = 29600 + {"block": 1, "model": 2, "skew": 3, "gradar": 4, "wstream": 5}[scenario]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "ddp_worker.py"), scenario]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)

@@ -1,10 +1,9 @@
 #!/bin/bash
-# A/B of the weight-gradient side stream (FACEVAE_WGRAD_STREAM): correctness with it on, then the bench line both ways.
+# A/B of the capture-stream priority with the weight-gradient side stream on.
 mkdir -p gpurun_out
-P=gpurun_out/ab
-timeout 150 python -m pytest tests/test_determinism_gpu.py -x -q -k "side_stream or train_step" > ${P}_det.log 2>&1; echo "determinism rc=$?" | tee ${P}_summary.txt
-for F in 0 1; do
-  FACEVAE_WGRAD_STREAM=$F timeout 120 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-glue-roofline --profile-steps 1 > ${P}_bench_$F.json 2>> ${P}_bench.err
-  echo "flag $F rc=$? $(python tools/show_bench.py ${P}_bench_$F.json 2>/dev/null | head -1)" | tee -a ${P}_summary.txt
+P=gpurun_out/ab2
+: > ${P}_summary.txt
+for PR in 0 -1 0 -1; do
+  FACEVAE_WGRAD_STREAM=1 FACEVAE_CAP_PRIORITY=$PR timeout 120 python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-glue-roofline --profile-steps 1 > ${P}_bench.json 2>> ${P}_bench.err
+  echo "priority $PR rc=$? $(python tools/show_bench.py ${P}_bench.json 2>/dev/null | head -1 | cut -c1-90)" | tee -a ${P}_summary.txt
 done
-tail -5 ${P}_det.log
