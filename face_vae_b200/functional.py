@@ -399,7 +399,8 @@ class BNActConv(torch.autograd.Function):
         x, a, stat, weight, wd = ctx.saved_tensors
         ksize, act, training, count, co, ci = ctx.cfg
         g = g.contiguous()
-        db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
+        with ops.wgrad_stream(g, extra=True):       # the bias gradient is off the dependent chain as well
+            db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
         da, dw = _conv_backward(GEOM_SAME, a, g, weight, wd, ksize, True)
         c = x.shape[3]
         fused = _bn_backward_sums(x, da, stat, MODE_NONE, act, False, count, training)
@@ -452,7 +453,8 @@ class ConvOnly(torch.autograd.Function):
         elif g.dtype != torch.bfloat16:
             g = g.to(torch.bfloat16)
         g = g.contiguous()
-        db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
+        with ops.wgrad_stream(g, extra=True):
+            db = ops.colsum(g)[:co].clone() if ctx.has_bias else None
         dx, dw = _conv_backward(GEOM_SAME, x, g, weight, wd, ksize, ctx.needs_input_grad[0])
         return dx, dw, db, None, None, None
 

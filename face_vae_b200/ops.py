@@ -80,6 +80,8 @@ def _red_ws() -> int:
 # cannot hand their memory to a later compute-stream kernel while the side stream still reads it.  Under CUDA-graph capture
 # fork and join become graph edges.  Results do not depend on the schedule (no atomics): bitwise equal to the serial order.
 _WGRAD_STREAM = _os.environ.get("FACEVAE_WGRAD_STREAM", "1") != "0"
+# "2" (default): the bias column sums of the un-normalised convolutions and the per-step filter preparation use the side stream as well
+_SIDE_EXTRAS = _os.environ.get("FACEVAE_WGRAD_STREAM", "2") == "2"
 _wgrad_side = {}           # (device, compute stream) -> side stream
 _wgrad_live = []           # tensors a pending side-stream kernel reads
 _wgrad_dirty = {}          # (device, compute stream) -> (compute stream, side stream) with un-joined work
@@ -96,12 +98,13 @@ class wgrad_stream:
     """``with ops.wgrad_stream(x, dy):`` -- the kernels issued inside run on the weight-gradient side stream (when enabled and
     inside a step scope; otherwise on the current stream as usual).  ``tensors``: what those kernels read."""
 
-    def __init__(self, *tensors):
+    def __init__(self, *tensors, extra: bool = False):
         self.tensors = [t for t in tensors if t is not None]
         self.ctx = None
+        self.extra = extra
 
     def __enter__(self):
-        if not (_WGRAD_STREAM and _scope_active):
+        if not (_WGRAD_STREAM and _scope_active) or (self.extra and not _SIDE_EXTRAS):
             return self
         main = torch.cuda.current_stream()
         key = (torch.cuda.current_device(), main.cuda_stream)
@@ -147,6 +150,7 @@ class _PrepCache:
         self.table = None
         self.max_items = 0
         self.valid = False
+        self.joined = True     # False while this step's batched launch may still be running on the side stream
 
     def build(self, weights):
         import numpy as np
@@ -261,9 +265,13 @@ class step_scope:
                     if kind == PREP_S2 and tuple(w.shape[2:]) != (4, 4):
                         continue
                     weights.append((w, kind))
-        if weights:
-            _prep.run(weights)
         _scope_active = True
+        if weights:
+            # the filter preparation only depends on the weights: it runs on the side stream beside the first encoder layer (which
+            # reads the fp32 frames and its fp32 1x1 filter directly) and is joined by the first convolution that asks for an operand
+            with wgrad_stream(extra=True) as ws:
+                _prep.run(weights)
+                _prep.joined = ws.ctx is None
         return self
 
     def __exit__(self, *exc):
@@ -331,6 +339,9 @@ def weight_prep(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = True
     _chk(w, "weight", torch.float32)
     if _prep.valid:
         hit = _prep.map.get(w.data_ptr())
+        if hit is not None and not _prep.joined:
+            join_wgrad_stream()
+            _prep.joined = True
         if hit is not None:                      # prepared by this step's batched launch (ops.step_scope)
             return (hit[0] if want_fwd else None), (hit[1] if want_dgrad else None)
     co, ci, r, s = w.shape
@@ -417,6 +428,9 @@ def weight_prep_up(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = Tr
     _chk(w, "weight", torch.float32)
     if _prep.valid:
         hit = _prep.map_up.get(w.data_ptr())
+        if hit is not None and not _prep.joined:
+            join_wgrad_stream()
+            _prep.joined = True
         if hit is not None:                      # prepared by this step's batched launch (ops.step_scope)
             return (hit[0] if want_fwd else None), (hit[1] if want_dgrad else None)
     co, ci, r, s = w.shape
@@ -434,6 +448,9 @@ def weight_prep_s2(w: torch.Tensor, want_fwd: bool = True, want_dgrad: bool = Tr
     _chk(w, "weight", torch.float32)
     if _prep.valid:
         hit = _prep.map_s2.get(w.data_ptr())
+        if hit is not None and not _prep.joined:
+            join_wgrad_stream()
+            _prep.joined = True
         if hit is not None:
             return (hit[0] if want_fwd else None), (hit[1] if want_dgrad else None)
     co, ci, r, s = w.shape
