@@ -185,3 +185,22 @@ def test_vae_variants_keep_the_reference_state_dict_keys_and_refuse_cpu_tensors(
         MO.flatten_vae()(torch.zeros(2, 16, 4, 4), True)
     with pytest.raises(RuntimeError):
         MO.local_vae()(torch.zeros(2, 128, 8, 8))
+
+
+def test_side_stream_context_is_inert_outside_a_step_scope():
+    """ops.wgrad_stream only forks inside ops.step_scope (and never without CUDA work): outside a scope the body runs on the
+    caller's stream and nothing is left to join; set_wgrad_stream returns the previous setting."""
+    from face_vae_b200 import ops
+    prev = ops.set_wgrad_stream(True)
+    try:
+        with ops.wgrad_stream(torch.zeros(3)) as ws:
+            assert ws.ctx is None
+        assert not ops._wgrad_dirty and not ops._wgrad_live
+        ops.join_wgrad_stream()                      # nothing pending: a no-op
+        assert ops.set_wgrad_stream(False) is True
+        with ops.step_scope(torch.nn.Linear(2, 2)):  # a CPU module: no 4-d CUDA weights, nothing prepared, nothing forked
+            with ops.wgrad_stream(torch.zeros(3)) as ws:
+                assert ws.ctx is None
+        assert not ops._scope_active
+    finally:
+        ops.set_wgrad_stream(prev)
