@@ -87,10 +87,11 @@ class GeneratorFull(nn.Module):
 class VAETrainer:
     """One-model version of the reference Logger's optimisation step (logger.py:52-63, 150-164).
 
-    ``use_cuda_graph`` (default: on for a single CUDA process, off under data parallelism or with
-    FACEVAE_CUDA_GRAPH=0): the whole step -- zero_grad, forward, backward, Adam -- is captured once per input shape into
-    a CUDA graph and replayed, which removes the ~260 per-launch host round trips of the eager step.  The captured
-    sequence is exactly the eager one (same kernels, same order, same stream semantics)."""
+    ``use_cuda_graph`` (default: on for CUDA parameters; FACEVAE_CUDA_GRAPH=0 switches it off, FACEVAE_CUDA_GRAPH_DDP=0 only
+    under data parallelism): the whole step -- zero_grad, forward, backward, gradient all-reduce, Adam -- is captured once per
+    input shape into a CUDA graph and replayed, which removes the ~160 per-launch host round trips of the eager step.  The
+    captured sequence is exactly the eager one: same kernels, same dependencies -- including the fork / join of the
+    weight-gradient side stream (ops.wgrad_stream) -- on a high-priority capture stream."""
 
     def __init__(self, vae: FaceVAE, lr: float = 5e-5, weights: Optional[Dict[str, float]] = None, bucket_mb: float = 2.0,
                  fused_adam: bool = True, use_cuda_graph: Optional[bool] = None):
