@@ -266,12 +266,19 @@ class step_scope:
                         continue
                     weights.append((w, kind))
         _scope_active = True
-        if weights:
-            # the filter preparation only depends on the weights: it runs on the side stream beside the first encoder layer (which
-            # reads the fp32 frames and its fp32 1x1 filter directly) and is joined by the first convolution that asks for an operand
-            with wgrad_stream(extra=True) as ws:
-                _prep.run(weights)
-                _prep.joined = ws.ctx is None
+        try:
+            if weights:
+                # the filter preparation only depends on the weights: it runs on the side stream beside the first encoder layer
+                # (which reads the fp32 frames and its fp32 1x1 filter directly) and is joined by the first convolution that asks
+                # for an operand
+                with wgrad_stream(extra=True) as ws:
+                    _prep.run(weights)
+                    _prep.joined = ws.ctx is None
+        except BaseException:           # __exit__ does not run when __enter__ raises: leave no scope behind
+            join_wgrad_stream()
+            _scope_active = False
+            _prep.valid = False
+            raise
         return self
 
     def __exit__(self, *exc):

@@ -204,3 +204,30 @@ def test_side_stream_context_is_inert_outside_a_step_scope():
         assert not ops._scope_active
     finally:
         ops.set_wgrad_stream(prev)
+
+
+def test_step_scope_leaves_no_scope_behind_when_the_filter_preparation_fails(monkeypatch):
+    """__exit__ does not run when __enter__ raises: a failing batched preparation must not leave the process inside a scope
+    (shared zero gradients, side stream) for ever."""
+    from face_vae_b200 import ops
+
+    class CudaLookingWeight(torch.nn.Parameter):
+        @property
+        def is_cuda(self):
+            return True
+
+    m = torch.nn.Conv2d(3, 4, 3)
+    m.weight = CudaLookingWeight(m.weight.data)
+
+    def boom(weights):
+        raise RuntimeError("preparation failed")
+
+    monkeypatch.setattr(ops._prep, "run", boom)
+    prev = ops.set_wgrad_stream(False)
+    try:
+        with pytest.raises(RuntimeError):
+            with ops.step_scope(m):
+                pass
+        assert not ops._scope_active and not ops._prep.valid and not ops._wgrad_dirty
+    finally:
+        ops.set_wgrad_stream(prev)
