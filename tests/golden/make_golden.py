@@ -468,6 +468,49 @@ def golden_vae_variants(path):
     print(path, len(store), "arrays")
 
 
+def golden_efe5(path):
+    """the 2-D stage of the reference's EFE_conv5 (models.py:764-787) executed with the reference's own
+    sub-modules in the reference's order -- F.interpolate pre-scale -> ``down`` -> ``vae`` (flatten_vae_nl, eps injected) ->
+    ``mid_conv`` -> view(N, C, D, H, W).  (The rest of EFE_conv5.forward needs key points and CUDA-only helpers.)"""
+    store = {}
+    m = ref_models.EFE_conv5()
+    sd = m.state_dict()
+    keys = [k for k in sd if k.startswith("down.") or k.startswith("mid_conv.")]
+    for k in keys:
+        shp = tuple(sd[k].shape)
+        if k.endswith("num_batches_tracked"):
+            continue
+        if k.endswith("running_var") or (k.endswith("layers.1.weight") and len(shp) == 1):
+            sd[k] = torch.from_numpy(detgen.det_uniform(shp, detgen.name_seed("efe5." + k), 0.5, 1.5))
+        elif len(shp) == 4:
+            sd[k] = torch.from_numpy(detgen.det_normal(shp, detgen.name_seed("efe5." + k)) / np.sqrt(shp[1] * shp[2] * shp[3])).float()
+        else:
+            sd[k] = torch.from_numpy(detgen.det_normal(shp, detgen.name_seed("efe5." + k)) * 0.2)
+    m.load_state_dict(sd)
+    m.train()
+    store["keys"] = np.array(sorted(keys))
+    x = torch.from_numpy(detgen.det_unit((2, 3, 256, 256), 291))
+    eps = torch.from_numpy(detgen.det_normal((2, 256), 292))
+    xs = torch.nn.functional.interpolate(x, mode="bilinear", scale_factor=m.scale_factor, align_corners=False, recompute_scale_factor=True)
+    h = m.down(xs)
+    with injected_randn(eps):
+        mu, ls, xhat = m.vae(h, True)
+    y = m.mid_conv(xhat)
+    n, _, hh, ww = y.shape
+    y3 = y.view(n, m.C, m.D, hh, ww)
+    gy = torch.from_numpy(detgen.det_uniform(tuple(y3.shape), 293, -1.0, 1.0))
+    (y3 * gy).sum().backward()
+    put(store, "h", h, full_below=1 << 20)
+    put(store, "mu", mu, full_below=1 << 20)
+    put(store, "logstd", ls, full_below=1 << 20)
+    put(store, "x3d", y3)
+    for k, v in m.named_parameters():
+        if (k.startswith("down.") or k.startswith("mid_conv.")) and v.grad is not None:
+            put(store, f"grad/{k}", v.grad)
+    np.savez_compressed(path, **store)
+    print(path, len(store), "arrays")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     golden_losses(os.path.join(HERE, "losses.npz"))
@@ -475,6 +518,7 @@ if __name__ == "__main__":
     golden_elr(os.path.join(HERE, "elr.npz"))
     golden_f2(os.path.join(HERE, "f2.npz"))
     golden_vae_variants(os.path.join(HERE, "vae_variants.npz"))
+    golden_efe5(os.path.join(HERE, "efe5.npz"))
     golden_anchor(4, 64, 0, os.path.join(HERE, "anchor_n4_64.npz"))     # BASELINE.json configs[0]
     golden_anchor(2, 64, 1, os.path.join(HERE, "anchor_n2_64_b1.npz"))
     if "--large" in sys.argv:       # minutes of CPU time: BASELINE.json configs[1] and the configs[3] architecture at 512x512
